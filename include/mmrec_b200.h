@@ -1,0 +1,184 @@
+/*
+ * mmrec_b200 -- C ABI of the B200-native graph-propagation hot path.
+ *
+ * The reference (EXLYSHA/Recommendar-Systems, an MMRec fork) has no FFI layer: its operator
+ * boundary is the set of torch call sites inside the model files. Every entry point below
+ * replaces one family of those call sites (cited as path:line under /root/reference/src).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - Every pointer is a DEVICE pointer unless its name ends in _host.
+ *   - Matrices are dense row-major float32 with leading dimension == number of columns.
+ *   - `stream` is a cudaStream_t passed as void*. No entry point synchronises, allocates or
+ *     frees device memory, so all of them can be captured in a CUDA graph.
+ *   - Return value: 0 on success, a negative MMREC_E_* code otherwise; mmrec_last_error()
+ *     returns a thread-local human-readable message for the last failure.
+ *   - Index widths: node / item / user ids int32 on the device side of a CSR, int64 where the
+ *     reference hands over LongTensors (batches, COO indices). Row pointers are int32 unless
+ *     the function takes a `rowptr64` flag.
+ */
+#ifndef MMREC_B200_H
+#define MMREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMREC_OK 0
+#define MMREC_E_BADARG (-1)     /* null pointer, negative size, unsupported embedding width */
+#define MMREC_E_ALIGN (-2)      /* pointer not 16-byte aligned */
+#define MMREC_E_OVERFLOW (-3)   /* index does not fit the kernel's index type */
+#define MMREC_E_CUDA (-4)       /* CUDA runtime error, see mmrec_last_error() */
+#define MMREC_E_WORKSPACE (-5)  /* workspace too small */
+
+int mmrec_abi_version(void);
+const char *mmrec_last_error(void);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches claim). */
+int64_t mmrec_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Adjacency construction (K11/K12).
+ * Replaces LayerGCN/FREEDOM/LightGCN.get_norm_adj_mat (models/layergcn.py:91-117,
+ * models/freedom.py:102-128, models/lightgcn.py:65-103), MGCN/SMORE.get_adj_mat
+ * (models/mgcn.py:109-136, models/smore.py:176-199) and the per-epoch re-normalisation in
+ * pre_epoch_processing/_normalize_adj_m (models/layergcn.py:51-81, models/freedom.py:130-156).
+ *
+ * Builds the CSR of A_hat = D^-1/2 [[0,R],[R^T,0]] D^-1/2 (N = U + I rows, 2E non-zeros, columns
+ * sorted inside each row) from E unique training edges. deg^-1/2 comes from a caller-supplied
+ * look-up table indexed by degree (the caller evaluates the reference's own pow() on the host so
+ * the result is bit-exact): lut_is_f64 = 1 -> value = (float)(lut[deg_r] * lut[deg_c]) with the
+ * product in double (layergcn.py recipe); 0 -> float product (mgcn.py / _normalize_adj_m recipe).
+ * deg_out (int32[N], optional) receives the degrees.
+ * ---------------------------------------------------------------------------------------- */
+size_t mmrec_ui_adj_workspace_bytes(int64_t n_edges, int32_t n_users, int32_t n_items);
+int mmrec_ui_adj_build(const int64_t *users, const int64_t *items, int64_t n_edges,
+                       int32_t n_users, int32_t n_items, const void *lut, int32_t lut_len,
+                       int32_t lut_is_f64, int32_t *row_ptr, int32_t *col_idx, float *vals,
+                       int32_t *deg_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Generic COO (int64 indices, possibly unsorted, duplicates kept) -> CSR with sorted columns.
+ * Replaces the per-call coalesce()+COO->CSR conversion torch.sparse.mm performs on the
+ * reference's uncoalesced tensors (every call site listed under mmrec_spmm_csr_f32). If
+ * `transpose` is non-zero the CSR of A^T is produced (needed for the backward of the
+ * non-symmetric item-item graphs, utils/utils.py:171-184). perm_out (int64[nnz], optional)
+ * receives, for every CSR slot, the index of the COO entry it came from. */
+size_t mmrec_csr_from_coo_workspace_bytes(int64_t nnz);
+int mmrec_csr_from_coo(const int64_t *rows, const int64_t *cols, const float *vals, int64_t nnz,
+                       int32_t n_rows, int32_t n_cols, int32_t transpose, int32_t *row_ptr,
+                       int32_t *col_idx, float *out_vals, int64_t *perm_out, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SpMM with fused layer combination (K1/K2/K3).
+ * Replaces torch.sparse.mm at models/layergcn.py:133, models/freedom.py:169,174,
+ * models/mgcn.py:162,172,176,180,184, models/smore.py:282,293,297,303,307,313,317,
+ * models/lightgcn.py:122, the stack+mean at freedom.py:177-178 / mgcn.py:165-166 /
+ * smore.py:285-286 / lightgcn.py:124-125 and the cosine refinement at layergcn.py:134-138.
+ *
+ *   y[r]  = sum_k vals[k] * X[col_idx[k] - col_offset]      for k in row r (sched order)
+ *   LayerGCN mode (cos_ref != NULL): Y_pre[r] = y (optional), w = cos(y, cos_ref[r]) with
+ *       torch-2 semantics (each vector / max(norm, 1e-8)), cos_w[r] = w, y *= w
+ *   Y[r]       = y                                   (optional)
+ *   acc_out[r] = (acc_in[r] + y) * acc_scale  or  y * acc_scale if acc_in == NULL   (optional)
+ *
+ * row_sched: permutation of the rows in descending degree order; the first n_long entries are
+ * processed by a whole CTA each, the rest by one sub-warp each. d must be 32, 64, 128 or 256.
+ * The same entry point runs the backward (A_hat is symmetric; otherwise pass the CSR of A^T).
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
+                       const int32_t *row_sched, int32_t n_rows, int32_t n_long,
+                       int32_t col_offset, const float *X, int32_t d, float *Y,
+                       const float *acc_in, float *acc_out, float acc_scale,
+                       const float *cos_ref, float *cos_w, float *Y_pre, void *stream);
+
+/* Backward row-operator of one LayerGCN layer (layergcn.py:134-135 differentiated):
+ * given dE = dL/d(w*p), p = Y_pre, w = cos_w, e0 = cos_ref:
+ *   dP[r]   = w*dE + <dE,p> * d cos(p,e0)/dp ;  dE0[r] += <dE,p> * d cos(p,e0)/de0        */
+int mmrec_layergcn_cos_bwd_f32(const float *dE, const float *P, const float *E0, const float *W,
+                               int32_t n_rows, int32_t d, float *dP, float *dE0_accum,
+                               void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BPR gather-dot loss (K6). Replaces LayerGCN.bpr_loss + emb_loss (layergcn.py:142-163),
+ * FREEDOM.bpr_loss (freedom.py:182-189), MGCN/SMORE.bpr_loss (mgcn.py:210-222,
+ * smore.py:366-378).
+ *   x_b = <u_b, p_b> - <u_b, n_b>;   out[0] = sum_b -logsigmoid(x_b);
+ *   out[1] = sum_b 0.5*(|u_b|^2 + |p_b|^2 + |n_b|^2);   sig[b] = sigmoid(-x_b)  (saved)
+ * Backward: with coef[0] = dL/d out[0], coef[1] = dL/d out[1] (device scalars),
+ *   d_user[u_b] += coef0*(-sig_b)*(p_b - n_b) + coef1*u_b, etc. (atomic scatter-add,
+ *   duplicates allowed). partial must hold 2*B floats; counter one zero-initialised uint32.
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_bpr_fwd_f32(const float *user_emb, const float *item_emb, int32_t d,
+                      const int64_t *users, const int64_t *pos, const int64_t *neg, int32_t batch,
+                      float *out2, float *sig, float *partial, uint32_t *counter, void *stream);
+int mmrec_bpr_bwd_f32(const float *user_emb, const float *item_emb, int32_t d,
+                      const int64_t *users, const int64_t *pos, const int64_t *neg, int32_t batch,
+                      const float *sig, const float *coef2, float *d_user_emb, float *d_item_emb,
+                      void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * InfoNCE (K7). Replaces MGCN/SMORE.InfoNCE (mgcn.py:224-231, smore.py:380-387).
+ *   v1 = normalize(T1[idx]), v2 = normalize(T2[idx]) (F.normalize, eps 1e-12)
+ *   loss = mean_i( -log( exp(<v1_i,v2_i>/t) / sum_j exp(<v1_i,v2_j>/t) ) )
+ * The B x B score matrix never reaches HBM. fwd saves V1n,V2n [B,d], inv norms [2B], ttl [B].
+ * bwd scatter-adds into dT1/dT2 (table-shaped, atomics). coef = dL/dloss (device scalar).
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d, const int64_t *idx,
+                          int32_t batch, float inv_temp, float *loss_out, float *V1n, float *V2n,
+                          float *inv_norm, float *ttl, float *partial, uint32_t *counter,
+                          void *stream);
+int mmrec_infonce_bwd_f32(const float *V1n, const float *V2n, const float *inv_norm,
+                          const float *ttl, int32_t d, const int64_t *idx, int32_t batch,
+                          float inv_temp, const float *coef, float *dV1_ws, float *dV2_ws,
+                          float *dT1, float *dT2, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spectrum-based modality fusion (K5). Replaces SMORE.spectrum_convolution
+ * (models/smore.py:209-238): rfft -> complex filter (unit-magnitude normalised when
+ * weight_norm) -> irfft for image and text, and irfft(rfft(t)*rfft(v)*w_f) for the fusion
+ * view, norm='ortho'. Implemented as the equivalent real circulant operators.
+ * w_* are the raw parameters [d/2+1, 2]. d in {32, 64, 128}. taps_ws: 3*d floats, receives the
+ * real impulse responses h = irfft(w_hat) of the three filters (reused by the backward).
+ * Backward produces dImg, dTxt and the gradients of the three raw weights ([d/2+1,2] each,
+ * overwritten). dh_ws: 3*d floats, zero-initialised by the caller (tap gradients are
+ * accumulated there with atomics, then chained through irfft and the unit-magnitude map).
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_spectral_fwd_f32(const float *img, const float *txt, int32_t n_rows, int32_t d,
+                           const float *w_img, const float *w_txt, const float *w_fus,
+                           int32_t weight_norm, float *taps_ws, float *img_conv, float *txt_conv,
+                           float *fus_conv, void *stream);
+int mmrec_spectral_bwd_f32(const float *img, const float *txt, int32_t n_rows, int32_t d,
+                           const float *w_img, const float *w_txt, const float *w_fus,
+                           int32_t weight_norm, const float *taps_ws, const float *g_img_conv,
+                           const float *g_txt_conv, const float *g_fus_conv, float *d_img,
+                           float *d_txt, float *dh_ws, float *d_w_img, float *d_w_txt,
+                           float *d_w_fus, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Full-rank scoring fused with train-item masking and per-user top-K (K8/K9/K10).
+ * Replaces `scores = u @ item_e.T` (layergcn.py:187, freedom.py:221, mgcn.py:262,
+ * smore.py:421), `scores[mask] = -1e10` (common/trainer.py:522-524) and
+ * torch.topk(scores, max(topk)) (trainer.py:526). Scores never reach HBM.
+ *   users[b] selects the row of user_emb; items are item_emb[0..n_items) with global ids
+ *   item_offset + j (item-sharded evaluation); mask_rowptr[b]..mask_rowptr[b+1] index
+ *   mask_cols (global item ids, ascending inside each user). Tie rule: lower id first.
+ * Produces `n_splits` partial lists per user (item range split across CTAs) in ws_val/ws_idx
+ * ([n_splits, n_users, k]) and merges them into out_val/out_idx ([n_users, k], ids int64).
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *users, int32_t n_users,
+                              const float *item_emb, int32_t n_items, int32_t item_offset,
+                              int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,
+                              int32_t k, int32_t n_splits, float *ws_val, int32_t *ws_idx,
+                              float *out_val, int64_t *out_idx, void *stream);
+/* K-way merge of `n_lists` descending lists per user (local top-K of every rank after the
+ * all-gather). Same tie rule. lists are [n_lists, n_users, k]. */
+int mmrec_topk_merge(const float *vals, const int32_t *idx, int32_t n_lists, int32_t n_users,
+                     int32_t k, float *out_val, int64_t *out_idx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMREC_B200_H */

@@ -1,0 +1,88 @@
+// Shared helpers for the mmrec_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mmrec_b200.h"
+
+namespace mmrec {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#define MMREC_REQUIRE(cond, code, ...)        \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::mmrec::set_error(__VA_ARGS__);        \
+      return (code);                          \
+    }                                         \
+  } while (0)
+
+#define MMREC_CHECK_LAUNCH(name)                                                  \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      ::mmrec::set_error("%s: %s", name, cudaGetErrorString(e__));                \
+      return MMREC_E_CUDA;                                                        \
+    }                                                                             \
+    ::mmrec::count_launch();                                                      \
+  } while (0)
+
+#define MMREC_CUDA(call)                                                          \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) {                                                     \
+      ::mmrec::set_error("%s: %s", #call, cudaGetErrorString(e__));               \
+      return MMREC_E_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float4 ldg4(const float *p) {
+  return __ldg(reinterpret_cast<const float4 *>(p));
+}
+__device__ __forceinline__ void fma4(float4 &a, float s, const float4 &x) {
+  a.x = fmaf(s, x.x, a.x);
+  a.y = fmaf(s, x.y, a.y);
+  a.z = fmaf(s, x.z, a.z);
+  a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+// Butterfly sum over an aligned sub-warp of WIDTH lanes. The shuffle mask names only that
+// sub-warp, so sibling sub-warps of the same warp may be divergent or exited.
+template <int WIDTH>
+__device__ __forceinline__ float group_sum(float v) {
+  unsigned mask = 0xffffffffu;
+  if constexpr (WIDTH < 32) {
+    const unsigned lane = threadIdx.x & 31u;
+    mask = ((1u << WIDTH) - 1u) << (WIDTH * (lane / WIDTH));
+  }
+#pragma unroll
+  for (int o = WIDTH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, WIDTH);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
+
+// Deterministic block reduction of `v` (valid in every thread) -> result in thread 0.
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float *smem /* THREADS/32 floats */) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = lane < THREADS / 32 ? smem[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+}  // namespace mmrec

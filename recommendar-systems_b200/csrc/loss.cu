@@ -1,0 +1,463 @@
+// BPR gather-dot loss (K6) and streaming InfoNCE (K7) -- see include/mmrec_b200.h.
+//
+// BPR: one warp per (user, pos, neg) triple; the three embedding rows are gathered with 16-byte
+// loads, the two dots, -logsigmoid and the L2 term are formed in registers; per-sample results go
+// to a small buffer and the last CTA to finish reduces it in a fixed order (deterministic scalar).
+// Backward: sigma(-x) saved by the forward scales the rows, gradients are scatter-added with
+// vector atomics (red.global.add.v4.f32) because users/items repeat inside a batch.
+//
+// InfoNCE: rows are gathered + L2-normalised once, then a 64x64-tile kernel streams V1 V2^T
+// through shared memory, applies exp(s/t) and keeps only row sums -- the B x B matrix never
+// reaches HBM. Backward recomputes the tiles (flash-style) for the row pass (dV1) and the column
+// pass (dV2). All scalars are reduced in a fixed order.
+#include "common.cuh"
+
+namespace mmrec {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float softplus_neg(float x) {  // -logsigmoid(x)
+  return fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoid_neg(float x) {  // sigmoid(-x)
+  if (x >= 0.f) {
+    const float e = expf(-x);
+    return e / (1.f + e);
+  }
+  return 1.f / (1.f + expf(x));
+}
+
+// Returns true in every thread of the last CTA to arrive; resets the counter for the next call.
+__device__ __forceinline__ bool last_block_arrives(uint32_t *counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t total = gridDim.x * gridDim.y;
+    const uint32_t prev = atomicAdd(counter, 1u);
+    is_last = (prev == total - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// ------------------------------------------------------------------------------------------ BPR
+__global__ void __launch_bounds__(kThreads)
+bpr_fwd_kernel(const float *__restrict__ ue, const float *__restrict__ ie, int d,
+               const int64_t *__restrict__ users, const int64_t *__restrict__ pos,
+               const int64_t *__restrict__ neg, int batch, float *__restrict__ out2,
+               float *__restrict__ sig, float *__restrict__ partial, uint32_t *counter) {
+  __shared__ float red[kThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (kThreads / 32) + warp;
+  if (b < batch) {
+    const float *u = ue + (size_t)users[b] * d;
+    const float *p = ie + (size_t)pos[b] * d;
+    const float *n = ie + (size_t)neg[b] * d;
+    float sp = 0.f, sn = 0.f, sq = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 a = ldg4(u + c), x = ldg4(p + c), y = ldg4(n + c);
+      sp += dot4(a, x);
+      sn += dot4(a, y);
+      sq += dot4(a, a) + dot4(x, x) + dot4(y, y);
+    }
+    sp = warp_sum(sp);
+    sn = warp_sum(sn);
+    sq = warp_sum(sq);
+    if (lane == 0) {
+      const float x = sp - sn;
+      partial[b] = softplus_neg(x);
+      partial[batch + b] = 0.5f * sq;
+      sig[b] = sigmoid_neg(x);
+    }
+  }
+  if (last_block_arrives(counter)) {
+    float l = 0.f, r = 0.f;
+    for (int i = threadIdx.x; i < batch; i += kThreads) {
+      l += __ldcg(partial + i);
+      r += __ldcg(partial + batch + i);
+    }
+    l = block_sum<kThreads>(l, red);
+    r = block_sum<kThreads>(r, red);
+    if (threadIdx.x == 0) {
+      out2[0] = l;
+      out2[1] = r;
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add4(float *addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+bpr_bwd_kernel(const float *__restrict__ ue, const float *__restrict__ ie, int d,
+               const int64_t *__restrict__ users, const int64_t *__restrict__ pos,
+               const int64_t *__restrict__ neg, int batch, const float *__restrict__ sig,
+               const float *__restrict__ coef2, float *__restrict__ d_ue, float *__restrict__ d_ie) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (kThreads / 32) + warp;
+  if (b >= batch) return;
+  const float c0 = coef2[0], c1 = coef2[1];
+  const float s = -c0 * sig[b];  // d(-logsigmoid(x))/dx = -sigmoid(-x)
+  const size_t ou = (size_t)users[b] * d, op = (size_t)pos[b] * d, on = (size_t)neg[b] * d;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 a = ldg4(ue + ou + c), x = ldg4(ie + op + c), y = ldg4(ie + on + c);
+    float4 gu, gp, gn;
+    gu.x = s * (x.x - y.x) + c1 * a.x; gu.y = s * (x.y - y.y) + c1 * a.y;
+    gu.z = s * (x.z - y.z) + c1 * a.z; gu.w = s * (x.w - y.w) + c1 * a.w;
+    gp.x = s * a.x + c1 * x.x; gp.y = s * a.y + c1 * x.y; gp.z = s * a.z + c1 * x.z; gp.w = s * a.w + c1 * x.w;
+    gn.x = -s * a.x + c1 * y.x; gn.y = -s * a.y + c1 * y.y; gn.z = -s * a.z + c1 * y.z; gn.w = -s * a.w + c1 * y.w;
+    red_add4(d_ue + ou + c, gu);
+    red_add4(d_ie + op + c, gp);
+    red_add4(d_ie + on + c, gn);
+  }
+}
+
+// -------------------------------------------------------------------------------------- InfoNCE
+__global__ void __launch_bounds__(kThreads)
+infonce_normalize_kernel(const float *__restrict__ T1, const float *__restrict__ T2, int d,
+                         const int64_t *__restrict__ idx, int batch, float *__restrict__ V1n,
+                         float *__restrict__ V2n, float *__restrict__ inv_norm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (kThreads / 32) + warp;
+  if (b >= batch) return;
+  const size_t src = (size_t)idx[b] * d, dst = (size_t)b * d;
+  float n1 = 0.f, n2 = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 a = ldg4(T1 + src + c), x = ldg4(T2 + src + c);
+    n1 += dot4(a, a);
+    n2 += dot4(x, x);
+  }
+  const float i1 = 1.f / fmaxf(sqrtf(warp_sum(n1)), 1e-12f);
+  const float i2 = 1.f / fmaxf(sqrtf(warp_sum(n2)), 1e-12f);
+  for (int c = lane * 4; c < d; c += 128) {
+    float4 a = ldg4(T1 + src + c), x = ldg4(T2 + src + c);
+    a.x *= i1; a.y *= i1; a.z *= i1; a.w *= i1;
+    x.x *= i2; x.y *= i2; x.z *= i2; x.w *= i2;
+    *reinterpret_cast<float4 *>(V1n + dst + c) = a;
+    *reinterpret_cast<float4 *>(V2n + dst + c) = x;
+  }
+  if (lane == 0) {
+    inv_norm[b] = i1;
+    inv_norm[batch + b] = i2;
+  }
+}
+
+constexpr int kTile = 64;  // 64 x 64 score tile, 16 x 16 threads, 4 x 4 scores per thread
+
+// Load `kTile` rows (row0..) of M [batch, D] into smem [kTile][D + 4]; rows past `batch` -> 0.
+template <int D>
+__device__ __forceinline__ void load_tile(float *s, const float *__restrict__ M, int row0, int batch) {
+  constexpr int LD = D + 4, V = D / 4;
+  for (int t = threadIdx.x; t < kTile * V; t += kThreads) {
+    const int r = t / V, c = (t % V) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < batch) v = ldg4(M + (size_t)(row0 + r) * D + c);
+    *reinterpret_cast<float4 *>(s + r * LD + c) = v;
+  }
+}
+
+// acc[i][j] = <A[ty + 16 i], B[tx + 16 j]> over D
+template <int D>
+__device__ __forceinline__ void tile_dots(float (&acc)[4][4], const float *sA, const float *sB, int tx, int ty) {
+  constexpr int LD = D + 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < D; k += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(sA + (ty + 16 * i) * LD + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4 *>(sB + (tx + 16 * j) * LD + k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += dot4(a[i], b[j]);
+  }
+}
+
+// grid = (row tiles, column splits). ttl_part[split][row] = sum over the split's columns of
+// exp(s/t); pos[row] = s_ii. The last CTA combines splits in order and writes the mean loss.
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+infonce_fwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n, int batch,
+                   float inv_temp, int tiles_per_split, float *__restrict__ ttl_part,
+                   float *__restrict__ pos, float *__restrict__ ttl, float *__restrict__ loss_out,
+                   uint32_t *counter) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LD = D + 4;
+  float *sA = smem, *sB = smem + kTile * LD;
+  __shared__ float red[kThreads / 32];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int row0 = blockIdx.x * kTile;
+  const int n_tiles = (batch + kTile - 1) / kTile;
+  const int t_begin = blockIdx.y * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
+  load_tile<D>(sA, V1n, row0, batch);
+  float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = t_begin; t < t_end; ++t) {
+    __syncthreads();
+    load_tile<D>(sB, V2n, t * kTile, batch);
+    __syncthreads();
+    float acc[4][4];
+    tile_dots<D>(acc, sA, sB, tx, ty);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + ty + 16 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = t * kTile + tx + 16 * j;
+        if (c < batch) rowsum[i] += expf(acc[i][j] * inv_temp);
+        if (c == r && r < batch) pos[r] = acc[i][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float s = group_sum<16>(rowsum[i]);
+    const int r = row0 + ty + 16 * i;
+    if (tx == 0 && r < batch) ttl_part[(size_t)blockIdx.y * batch + r] = s;
+  }
+  if (last_block_arrives(counter)) {
+    float l = 0.f;
+    for (int r = threadIdx.x; r < batch; r += kThreads) {
+      float s = 0.f;
+      for (int sp = 0; sp < (int)gridDim.y; ++sp) s += __ldcg(ttl_part + (size_t)sp * batch + r);
+      ttl[r] = s;
+      // -log(exp(s_ii/t) / ttl)
+      l += logf(s) - __ldcg(pos + r) * inv_temp;
+    }
+    l = block_sum<kThreads>(l, red);
+    if (threadIdx.x == 0) loss_out[0] = l / (float)batch;
+  }
+}
+
+// Backward tile pass. ROWPASS: CTA owns 64 rows i of V1 and loops over column tiles j, producing
+// dV1n[i] = sum_j g_ij V2n[j]. Otherwise the CTA owns 64 columns j and loops over row tiles i,
+// producing dV2n[j] = sum_i g_ij V1n[i]. g_ij = coef/B/t * (exp(s_ij/t)/ttl_i - delta_ij).
+template <int D, bool ROWPASS>
+__global__ void __launch_bounds__(kThreads)
+infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
+                   const float *__restrict__ ttl, int batch, float inv_temp,
+                   const float *__restrict__ coef, float *__restrict__ dOut) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LD = D + 4, GL = kTile + 4;
+  float *sOwn = smem, *sOther = smem + kTile * LD, *sG = smem + 2 * kTile * LD;  // sG[own][other]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int own0 = blockIdx.x * kTile;
+  const int n_tiles = (batch + kTile - 1) / kTile;
+  const float scale = coef[0] / (float)batch * inv_temp;
+  const float *Own = ROWPASS ? V1n : V2n, *Other = ROWPASS ? V2n : V1n;
+  load_tile<D>(sOwn, Own, own0, batch);
+  // output accumulators: thread (tx, ty) owns rows {ty + 16 i} x column chunk of D/16 floats at tx
+  constexpr int CW = D / 16;
+  float out[4][CW];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < CW; ++c) out[i][c] = 0.f;
+  for (int t = 0; t < n_tiles; ++t) {
+    __syncthreads();
+    load_tile<D>(sOther, Other, t * kTile, batch);
+    __syncthreads();
+    float acc[4][4];
+    tile_dots<D>(acc, sOwn, sOther, tx, ty);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = own0 + ty + 16 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = t * kTile + tx + 16 * j;
+        const int row = ROWPASS ? o : x, col = ROWPASS ? x : o;
+        float g = 0.f;
+        if (o < batch && x < batch) {
+          g = expf(acc[i][j] * inv_temp) / __ldg(ttl + row);
+          if (row == col) g -= 1.f;
+          g *= scale;
+        }
+        sG[(ty + 16 * i) * GL + tx + 16 * j] = g;
+      }
+    }
+    __syncthreads();
+    // out[own][:] += sum_x G[own][x] * Other[x][:]
+#pragma unroll 4
+    for (int x = 0; x < kTile; ++x) {
+      float ov[CW];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) ov[c] = sOther[x * LD + tx * CW + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float g = sG[(ty + 16 * i) * GL + x];
+#pragma unroll
+        for (int c = 0; c < CW; ++c) out[i][c] = fmaf(g, ov[c], out[i][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = own0 + ty + 16 * i;
+    if (o < batch) {
+#pragma unroll
+      for (int c = 0; c < CW; ++c) dOut[(size_t)o * D + tx * CW + c] = out[i][c];
+    }
+  }
+}
+
+// Chain through F.normalize and scatter-add into the table-shaped gradients.
+__global__ void __launch_bounds__(kThreads)
+infonce_scatter_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
+                       const float *__restrict__ inv_norm, const float *__restrict__ dV1,
+                       const float *__restrict__ dV2, int d, const int64_t *__restrict__ idx,
+                       int batch, float *__restrict__ dT1, float *__restrict__ dT2) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (kThreads / 32) + warp;
+  if (b >= batch) return;
+  const size_t src = (size_t)b * d, dst = (size_t)idx[b] * d;
+  float p1 = 0.f, p2 = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    p1 += dot4(ldg4(V1n + src + c), ldg4(dV1 + src + c));
+    p2 += dot4(ldg4(V2n + src + c), ldg4(dV2 + src + c));
+  }
+  p1 = warp_sum(p1);
+  p2 = warp_sum(p2);
+  const float i1 = inv_norm[b], i2 = inv_norm[batch + b];
+  // norm clamped at eps: v = x / eps is linear in x, no projection term
+  const float k1 = i1 < 1e12f ? p1 : 0.f, k2 = i2 < 1e12f ? p2 : 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 v1 = ldg4(V1n + src + c), g1 = ldg4(dV1 + src + c);
+    const float4 v2 = ldg4(V2n + src + c), g2 = ldg4(dV2 + src + c);
+    float4 a, x;
+    a.x = i1 * (g1.x - k1 * v1.x); a.y = i1 * (g1.y - k1 * v1.y);
+    a.z = i1 * (g1.z - k1 * v1.z); a.w = i1 * (g1.w - k1 * v1.w);
+    x.x = i2 * (g2.x - k2 * v2.x); x.y = i2 * (g2.y - k2 * v2.y);
+    x.z = i2 * (g2.z - k2 * v2.z); x.w = i2 * (g2.w - k2 * v2.w);
+    red_add4(dT1 + dst + c, a);
+    red_add4(dT2 + dst + c, x);
+  }
+}
+
+template <int D>
+int infonce_fwd_launch(const float *V1n, const float *V2n, int batch, float inv_temp, float *partial,
+                       float *ttl, float *loss_out, uint32_t *counter, cudaStream_t stream) {
+  const int n_tiles = (batch + kTile - 1) / kTile;
+  int splits = max(1, min(n_tiles, (kNumSMs + n_tiles - 1) / n_tiles));
+  const int tiles_per_split = (n_tiles + splits - 1) / splits;
+  splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+  // partial layout: pos[batch] then ttl_part[splits][batch]; caller guarantees 16*batch floats
+  if (splits > 15) splits = 15;
+  const size_t smem = 2 * kTile * (D + 4) * sizeof(float);
+  MMREC_CUDA(cudaFuncSetAttribute(infonce_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tps = (n_tiles + splits - 1) / splits;
+  infonce_fwd_kernel<D><<<dim3(n_tiles, splits), kThreads, smem, stream>>>(
+      V1n, V2n, batch, inv_temp, tps, partial + batch, partial, ttl, loss_out, counter);
+  MMREC_CHECK_LAUNCH("infonce_fwd_kernel");
+  return MMREC_OK;
+}
+
+template <int D>
+int infonce_bwd_launch(const float *V1n, const float *V2n, const float *ttl, int batch, float inv_temp,
+                       const float *coef, float *dV1, float *dV2, cudaStream_t stream) {
+  const int n_tiles = (batch + kTile - 1) / kTile;
+  const size_t smem = (2 * kTile * (D + 4) + kTile * (kTile + 4)) * sizeof(float);
+  MMREC_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMREC_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  infonce_bwd_kernel<D, true><<<n_tiles, kThreads, smem, stream>>>(V1n, V2n, ttl, batch, inv_temp, coef, dV1);
+  MMREC_CHECK_LAUNCH("infonce_bwd_kernel<row>");
+  infonce_bwd_kernel<D, false><<<n_tiles, kThreads, smem, stream>>>(V1n, V2n, ttl, batch, inv_temp, coef, dV2);
+  MMREC_CHECK_LAUNCH("infonce_bwd_kernel<col>");
+  return MMREC_OK;
+}
+
+}  // namespace
+}  // namespace mmrec
+
+using namespace mmrec;
+
+extern "C" int mmrec_bpr_fwd_f32(const float *user_emb, const float *item_emb, int32_t d,
+                                 const int64_t *users, const int64_t *pos, const int64_t *neg, int32_t batch,
+                                 float *out2, float *sig, float *partial, uint32_t *counter, void *stream) {
+  MMREC_REQUIRE(user_emb && item_emb && users && pos && neg && out2 && sig && partial && counter,
+                MMREC_E_BADARG, "bpr_fwd: null pointer");
+  MMREC_REQUIRE(batch > 0 && d > 0 && d % 4 == 0, MMREC_E_BADARG, "bpr_fwd: need batch > 0 and d %% 4 == 0");
+  MMREC_REQUIRE(aligned16(user_emb) && aligned16(item_emb), MMREC_E_ALIGN, "bpr_fwd: tables must be 16-byte aligned");
+  const int wpb = kThreads / 32;
+  bpr_fwd_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, (cudaStream_t)stream>>>(
+      user_emb, item_emb, d, users, pos, neg, batch, out2, sig, partial, counter);
+  MMREC_CHECK_LAUNCH("bpr_fwd_kernel");
+  return MMREC_OK;
+}
+
+extern "C" int mmrec_bpr_bwd_f32(const float *user_emb, const float *item_emb, int32_t d,
+                                 const int64_t *users, const int64_t *pos, const int64_t *neg, int32_t batch,
+                                 const float *sig, const float *coef2, float *d_user_emb, float *d_item_emb,
+                                 void *stream) {
+  MMREC_REQUIRE(user_emb && item_emb && users && pos && neg && sig && coef2 && d_user_emb && d_item_emb,
+                MMREC_E_BADARG, "bpr_bwd: null pointer");
+  MMREC_REQUIRE(batch > 0 && d > 0 && d % 4 == 0, MMREC_E_BADARG, "bpr_bwd: need batch > 0 and d %% 4 == 0");
+  MMREC_REQUIRE(aligned16(user_emb) && aligned16(item_emb) && aligned16(d_user_emb) && aligned16(d_item_emb),
+                MMREC_E_ALIGN, "bpr_bwd: tables must be 16-byte aligned");
+  const int wpb = kThreads / 32;
+  bpr_bwd_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, (cudaStream_t)stream>>>(
+      user_emb, item_emb, d, users, pos, neg, batch, sig, coef2, d_user_emb, d_item_emb);
+  MMREC_CHECK_LAUNCH("bpr_bwd_kernel");
+  return MMREC_OK;
+}
+
+extern "C" int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d, const int64_t *idx,
+                                     int32_t batch, float inv_temp, float *loss_out, float *V1n, float *V2n,
+                                     float *inv_norm, float *ttl, float *partial, uint32_t *counter,
+                                     void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMREC_REQUIRE(T1 && T2 && idx && loss_out && V1n && V2n && inv_norm && ttl && partial && counter,
+                MMREC_E_BADARG, "infonce_fwd: null pointer");
+  MMREC_REQUIRE(batch > 0, MMREC_E_BADARG, "infonce_fwd: empty batch");
+  MMREC_REQUIRE(aligned16(T1) && aligned16(T2) && aligned16(V1n) && aligned16(V2n), MMREC_E_ALIGN,
+                "infonce_fwd: operands must be 16-byte aligned");
+  const int wpb = kThreads / 32;
+  infonce_normalize_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(T1, T2, d, idx, batch, V1n, V2n,
+                                                                           inv_norm);
+  MMREC_CHECK_LAUNCH("infonce_normalize_kernel");
+  switch (d) {
+    case 32: return infonce_fwd_launch<32>(V1n, V2n, batch, inv_temp, partial, ttl, loss_out, counter, stream);
+    case 64: return infonce_fwd_launch<64>(V1n, V2n, batch, inv_temp, partial, ttl, loss_out, counter, stream);
+    case 128: return infonce_fwd_launch<128>(V1n, V2n, batch, inv_temp, partial, ttl, loss_out, counter, stream);
+    default:
+      set_error("infonce_fwd: unsupported d=%d (32, 64, 128)", d);
+      return MMREC_E_BADARG;
+  }
+}
+
+extern "C" int mmrec_infonce_bwd_f32(const float *V1n, const float *V2n, const float *inv_norm, const float *ttl,
+                                     int32_t d, const int64_t *idx, int32_t batch, float inv_temp,
+                                     const float *coef, float *dV1_ws, float *dV2_ws, float *dT1, float *dT2,
+                                     void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMREC_REQUIRE(V1n && V2n && inv_norm && ttl && idx && coef && dV1_ws && dV2_ws && dT1 && dT2, MMREC_E_BADARG,
+                "infonce_bwd: null pointer");
+  MMREC_REQUIRE(batch > 0, MMREC_E_BADARG, "infonce_bwd: empty batch");
+  MMREC_REQUIRE(aligned16(V1n) && aligned16(V2n) && aligned16(dV1_ws) && aligned16(dV2_ws) && aligned16(dT1) &&
+                    aligned16(dT2), MMREC_E_ALIGN, "infonce_bwd: operands must be 16-byte aligned");
+  int rc;
+  switch (d) {
+    case 32: rc = infonce_bwd_launch<32>(V1n, V2n, ttl, batch, inv_temp, coef, dV1_ws, dV2_ws, stream); break;
+    case 64: rc = infonce_bwd_launch<64>(V1n, V2n, ttl, batch, inv_temp, coef, dV1_ws, dV2_ws, stream); break;
+    case 128: rc = infonce_bwd_launch<128>(V1n, V2n, ttl, batch, inv_temp, coef, dV1_ws, dV2_ws, stream); break;
+    default:
+      set_error("infonce_bwd: unsupported d=%d (32, 64, 128)", d);
+      return MMREC_E_BADARG;
+  }
+  if (rc != MMREC_OK) return rc;
+  const int wpb = kThreads / 32;
+  infonce_scatter_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(V1n, V2n, inv_norm, dV1_ws, dV2_ws, d,
+                                                                         idx, batch, dT1, dT2);
+  MMREC_CHECK_LAUNCH("infonce_scatter_kernel");
+  return MMREC_OK;
+}

@@ -1,0 +1,296 @@
+// CSR row-split SpMM with fused layer combination (K1/K2/K3) -- see include/mmrec_b200.h.
+//
+// Layout: CSR (int32 row_ptr / col_idx, float32 vals), X and Y row-major [n, d].
+// Work split: rows are visited in descending-degree order (row_sched). The n_long heaviest rows
+// get one CTA each (their non-zeros are strided over the CTA's sub-warps and reduced through
+// shared memory in a fixed order); every other row gets one sub-warp of LANES = d/4 threads
+// (16 lanes x float4 for d = 64, a full warp for d = 128), so each gathered embedding row is one
+// fully coalesced 16-byte-per-lane request. Column indices and values are loaded once per LANES
+// non-zeros (coalesced) and broadcast with shuffles; four gathers are kept in flight per lane.
+// No atomics: results are bit-reproducible run to run.
+#include "common.cuh"
+
+namespace mmrec {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int LANES>
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (LANES == 32) {
+    return 0xffffffffu;
+  } else {
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << LANES) - 1u) << (LANES * (lane / LANES));
+  }
+}
+
+__device__ __forceinline__ int ld_stream_i32(const int32_t *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// Accumulate rows [begin, end) of the CSR slice, visiting chunk `base, base+stride, ...`.
+template <int LANES, int CHUNKS>
+__device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t *__restrict__ col_idx,
+                                            const float *__restrict__ vals, int begin, int end,
+                                            int stride, int lane, const float *__restrict__ X,
+                                            int d, int col_offset) {
+  const unsigned mask = group_mask<LANES>();
+  for (int base = begin; base < end; base += stride) {
+    const int k = base + lane;
+    int c = 0;
+    float v = 0.f;
+    if (k < end) {
+      c = ld_stream_i32(col_idx + k) - col_offset;
+      v = ld_stream_f32(vals + k);
+    }
+    const int cnt = min(LANES, end - base);
+    int j = 0;
+    for (; j + 4 <= cnt; j += 4) {
+      int cc[4];
+      float vv[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        cc[t] = __shfl_sync(mask, c, j + t, LANES);
+        vv[t] = __shfl_sync(mask, v, j + t, LANES);
+      }
+      float4 x[4][CHUNKS];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int q = 0; q < CHUNKS; ++q)
+          x[t][q] = ldg4(X + (size_t)cc[t] * d + (q * LANES + lane) * 4);
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int q = 0; q < CHUNKS; ++q) fma4(acc[q], vv[t], x[t][q]);
+    }
+    for (; j < cnt; ++j) {
+      const int c1 = __shfl_sync(mask, c, j, LANES);
+      const float v1 = __shfl_sync(mask, v, j, LANES);
+#pragma unroll
+      for (int q = 0; q < CHUNKS; ++q)
+        fma4(acc[q], v1, ldg4(X + (size_t)c1 * d + (q * LANES + lane) * 4));
+    }
+  }
+}
+
+struct Epilogue {
+  float *Y;
+  const float *acc_in;
+  float *acc_out;
+  float acc_scale;
+  const float *cos_ref;
+  float *cos_w;
+  float *Y_pre;
+};
+
+template <int LANES, int CHUNKS>
+__device__ __forceinline__ void finish_row(float4 (&acc)[CHUNKS], int row, int lane, int d,
+                                           const Epilogue &ep) {
+  const size_t off = (size_t)row * d;
+  if (ep.cos_ref != nullptr) {
+    float4 e0[CHUNKS];
+    float dot = 0.f, ny = 0.f, n0 = 0.f;
+#pragma unroll
+    for (int q = 0; q < CHUNKS; ++q) {
+      e0[q] = ldg4(ep.cos_ref + off + (q * LANES + lane) * 4);
+      if (ep.Y_pre) *reinterpret_cast<float4 *>(ep.Y_pre + off + (q * LANES + lane) * 4) = acc[q];
+      ny += dot4(acc[q], acc[q]);
+      n0 += dot4(e0[q], e0[q]);
+    }
+    ny = group_sum<LANES>(ny);
+    n0 = group_sum<LANES>(n0);
+    const float iy = 1.f / fmaxf(sqrtf(ny), 1e-8f), i0 = 1.f / fmaxf(sqrtf(n0), 1e-8f);
+#pragma unroll
+    for (int q = 0; q < CHUNKS; ++q) {
+      float4 a = acc[q], b = e0[q];
+      a.x *= iy; a.y *= iy; a.z *= iy; a.w *= iy;
+      b.x *= i0; b.y *= i0; b.z *= i0; b.w *= i0;
+      dot += dot4(a, b);
+    }
+    const float w = group_sum<LANES>(dot);
+    if (lane == 0 && ep.cos_w) ep.cos_w[row] = w;
+#pragma unroll
+    for (int q = 0; q < CHUNKS; ++q) {
+      acc[q].x *= w; acc[q].y *= w; acc[q].z *= w; acc[q].w *= w;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < CHUNKS; ++q) {
+    const size_t o = off + (q * LANES + lane) * 4;
+    if (ep.Y) *reinterpret_cast<float4 *>(ep.Y + o) = acc[q];
+    if (ep.acc_out) {
+      float4 r = acc[q];
+      if (ep.acc_in) {
+        const float4 a = *reinterpret_cast<const float4 *>(ep.acc_in + o);
+        r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+      }
+      r.x *= ep.acc_scale; r.y *= ep.acc_scale; r.z *= ep.acc_scale; r.w *= ep.acc_scale;
+      *reinterpret_cast<float4 *>(ep.acc_out + o) = r;
+    }
+  }
+}
+
+template <int LANES, int CHUNKS>
+__global__ void __launch_bounds__(kThreads)
+spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                const float *__restrict__ vals, const int32_t *__restrict__ row_sched, int n_rows,
+                int n_long, int col_offset, const float *__restrict__ X, int d, Epilogue ep) {
+  constexpr int GROUPS = kThreads / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int group = threadIdx.x / LANES;
+  float4 acc[CHUNKS];
+#pragma unroll
+  for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if ((int)blockIdx.x < n_long) {
+    // one CTA per heavy row: sub-warps stride over the row, fixed-order shared-memory reduce
+    __shared__ float4 red[GROUPS][LANES * CHUNKS];
+    const int row = row_sched[blockIdx.x];
+    const int begin = row_ptr[row], end = row_ptr[row + 1];
+    gather_rows<LANES, CHUNKS>(acc, col_idx, vals, begin + group * LANES, end, GROUPS * LANES, lane,
+                               X, d, col_offset);
+#pragma unroll
+    for (int q = 0; q < CHUNKS; ++q) red[group][q * LANES + lane] = acc[q];
+    __syncthreads();
+    if (group == 0) {
+#pragma unroll
+      for (int q = 0; q < CHUNKS; ++q) {
+        float4 s = red[0][q * LANES + lane];
+        for (int g = 1; g < GROUPS; ++g) {
+          const float4 t = red[g][q * LANES + lane];
+          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        acc[q] = s;
+      }
+      finish_row<LANES, CHUNKS>(acc, row, lane, d, ep);
+    }
+    return;
+  }
+  const int slot = n_long + ((int)blockIdx.x - n_long) * GROUPS + group;
+  if (slot >= n_rows) return;
+  const int row = row_sched[slot];
+  const int begin = row_ptr[row], end = row_ptr[row + 1];
+  gather_rows<LANES, CHUNKS>(acc, col_idx, vals, begin, end, LANES, lane, X, d, col_offset);
+  finish_row<LANES, CHUNKS>(acc, row, lane, d, ep);
+}
+
+// ---- LayerGCN cosine refinement, backward row operator --------------------------------------
+template <int LANES, int CHUNKS>
+__global__ void __launch_bounds__(kThreads)
+layergcn_cos_bwd_kernel(const float *__restrict__ dE, const float *__restrict__ P,
+                        const float *__restrict__ E0, const float *__restrict__ W, int n_rows,
+                        int d, float *__restrict__ dP, float *__restrict__ dE0) {
+  constexpr int GROUPS = kThreads / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int row = blockIdx.x * GROUPS + threadIdx.x / LANES;
+  if (row >= n_rows) return;
+  const size_t off = (size_t)row * d;
+  float4 g[CHUNKS], p[CHUNKS], e0[CHUNKS];
+  float gp = 0.f, ny = 0.f, n0 = 0.f;
+#pragma unroll
+  for (int q = 0; q < CHUNKS; ++q) {
+    const size_t o = off + (q * LANES + lane) * 4;
+    g[q] = ldg4(dE + o);
+    p[q] = ldg4(P + o);
+    e0[q] = ldg4(E0 + o);
+    gp += dot4(g[q], p[q]);
+    ny += dot4(p[q], p[q]);
+    n0 += dot4(e0[q], e0[q]);
+  }
+  gp = group_sum<LANES>(gp);
+  ny = sqrtf(group_sum<LANES>(ny));
+  n0 = sqrtf(group_sum<LANES>(n0));
+  const float w = W[row];
+  const float cy = fmaxf(ny, 1e-8f), c0 = fmaxf(n0, 1e-8f);
+  const float iy = 1.f / cy, i0 = 1.f / c0;
+  // d cos / dp = (e0n - [ny > eps] * w * pn) / max(ny, eps); same for e0 with roles swapped
+  const float sy = ny > 1e-8f ? w : 0.f, s0 = n0 > 1e-8f ? w : 0.f;
+#pragma unroll
+  for (int q = 0; q < CHUNKS; ++q) {
+    const size_t o = off + (q * LANES + lane) * 4;
+    const float4 a = p[q], b = e0[q], gg = g[q];
+    float4 dp, de;
+    dp.x = w * gg.x + gp * (b.x * i0 - sy * a.x * iy) * iy;
+    dp.y = w * gg.y + gp * (b.y * i0 - sy * a.y * iy) * iy;
+    dp.z = w * gg.z + gp * (b.z * i0 - sy * a.z * iy) * iy;
+    dp.w = w * gg.w + gp * (b.w * i0 - sy * a.w * iy) * iy;
+    *reinterpret_cast<float4 *>(dP + o) = dp;
+    float4 acc = *reinterpret_cast<const float4 *>(dE0 + o);
+    de.x = gp * (a.x * iy - s0 * b.x * i0) * i0;
+    de.y = gp * (a.y * iy - s0 * b.y * i0) * i0;
+    de.z = gp * (a.z * iy - s0 * b.z * i0) * i0;
+    de.w = gp * (a.w * iy - s0 * b.w * i0) * i0;
+    acc.x += de.x; acc.y += de.y; acc.z += de.z; acc.w += de.w;
+    *reinterpret_cast<float4 *>(dE0 + o) = acc;
+  }
+}
+
+template <typename F>
+int dispatch_width(int d, F &&f) {
+  switch (d) {
+    case 32: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
+    case 64: return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 1>{});
+    case 128: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 1>{});
+    case 256: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 2>{});
+    default:
+      set_error("unsupported embedding width d=%d (supported: 32, 64, 128, 256)", d);
+      return MMREC_E_BADARG;
+  }
+}
+
+}  // namespace
+}  // namespace mmrec
+
+using namespace mmrec;
+
+extern "C" int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
+                                  const int32_t *row_sched, int32_t n_rows, int32_t n_long,
+                                  int32_t col_offset, const float *X, int32_t d, float *Y,
+                                  const float *acc_in, float *acc_out, float acc_scale,
+                                  const float *cos_ref, float *cos_w, float *Y_pre, void *stream) {
+  MMREC_REQUIRE(row_ptr && col_idx && vals && row_sched && X, MMREC_E_BADARG, "spmm: null input");
+  MMREC_REQUIRE(Y || acc_out, MMREC_E_BADARG, "spmm: no output requested");
+  MMREC_REQUIRE(n_rows >= 0 && n_long >= 0 && n_long <= n_rows, MMREC_E_BADARG, "spmm: bad sizes");
+  MMREC_REQUIRE(aligned16(X) && aligned16(Y) && aligned16(acc_in) && aligned16(acc_out) &&
+                    aligned16(cos_ref) && aligned16(Y_pre),
+                MMREC_E_ALIGN, "spmm: dense operands must be 16-byte aligned");
+  MMREC_REQUIRE(X != Y && X != acc_out, MMREC_E_BADARG, "spmm: X must not alias an output");
+  if (n_rows == 0) return MMREC_OK;
+  Epilogue ep{Y, acc_in, acc_out, acc_scale, cos_ref, cos_w, Y_pre};
+  return dispatch_width(d, [&](auto lanes, auto chunks) {
+    constexpr int L = decltype(lanes)::value, C = decltype(chunks)::value;
+    constexpr int GROUPS = kThreads / L;
+    const int n_short = n_rows - n_long;
+    const int blocks = n_long + (n_short + GROUPS - 1) / GROUPS;
+    spmm_csr_kernel<L, C><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        row_ptr, col_idx, vals, row_sched, n_rows, n_long, col_offset, X, d, ep);
+    MMREC_CHECK_LAUNCH("spmm_csr_kernel");
+    return MMREC_OK;
+  });
+}
+
+extern "C" int mmrec_layergcn_cos_bwd_f32(const float *dE, const float *P, const float *E0,
+                                          const float *W, int32_t n_rows, int32_t d, float *dP,
+                                          float *dE0_accum, void *stream) {
+  MMREC_REQUIRE(dE && P && E0 && W && dP && dE0_accum, MMREC_E_BADARG, "layergcn_cos_bwd: null");
+  MMREC_REQUIRE(aligned16(dE) && aligned16(P) && aligned16(E0) && aligned16(dP) && aligned16(dE0_accum),
+                MMREC_E_ALIGN, "layergcn_cos_bwd: operands must be 16-byte aligned");
+  if (n_rows == 0) return MMREC_OK;
+  return dispatch_width(d, [&](auto lanes, auto chunks) {
+    constexpr int L = decltype(lanes)::value, C = decltype(chunks)::value;
+    constexpr int GROUPS = kThreads / L;
+    layergcn_cos_bwd_kernel<L, C><<<(n_rows + GROUPS - 1) / GROUPS, kThreads, 0, (cudaStream_t)stream>>>(
+        dE, P, E0, W, n_rows, d, dP, dE0_accum);
+    MMREC_CHECK_LAUNCH("layergcn_cos_bwd_kernel");
+    return MMREC_OK;
+  });
+}

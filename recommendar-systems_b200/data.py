@@ -218,7 +218,9 @@ class EvalDataLoader(AbstractDataLoader):
         self.eval_u = torch.from_numpy(eval_u).to(self.device)
         # device copies for the fused kernel: int32 CSR of the same mask
         self._mask_rowptr_dev = torch.from_numpy(self.mask_rowptr.astype(np.int32)).to(self.device)
-        self._mask_cols_dev = self.pos_items_per_u[1].to(torch.int32)
+        # ascending item ids inside each user (the kernel walks the list with a cursor)
+        o = np.lexsort((flat, rows))
+        self._mask_cols_dev = torch.from_numpy(flat[o].astype(np.int32)).to(self.device)
 
     @property
     def pr_end(self):

@@ -1,0 +1,129 @@
+"""Device-resident CSR graphs for the propagation kernels.
+
+HBM layout: `row_ptr` int32 [rows+1], `col_idx` int32 [nnz], `vals` float32
+[nnz], plus `sched` int32 [rows] -- the row visiting order (descending degree) of
+mmrec_spmm_csr_f32. The symmetric user-item adjacency is stored once; R = A[:U, U:] and R^T are
+zero-copy views of it (a row-pointer slice + a column offset), so SMORE/MGCN's `R` propagation
+and its transposed backward need no extra storage.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import lib
+
+LONG_ROW = 512      # rows with at least this many non-zeros get a whole CTA
+
+
+class CSRGraph:
+    def __init__(self, row_ptr, col_idx, vals, n_rows, n_cols, col_offset=0, symmetric=False):
+        self.row_ptr, self.col_idx, self.vals = row_ptr, col_idx, vals
+        self.n_rows, self.n_cols, self.col_offset = int(n_rows), int(n_cols), int(col_offset)
+        deg = (row_ptr[1:] - row_ptr[:-1])
+        self.sched = torch.argsort(deg, descending=True, stable=True).to(torch.int32)
+        self.n_long = int((deg >= LONG_ROW).sum().item())
+        self.nnz = int((row_ptr[-1] - row_ptr[0]).item())
+        self.t = self if symmetric else None
+
+    @property
+    def device(self):
+        return self.vals.device
+
+    def algorithmic_bytes(self, d):
+        """8*nnz + 4*(rows+1) + 4*d*(rows + cols)."""
+        return 8 * self.nnz + 4 * (self.n_rows + 1) + 4 * d * (self.n_rows + self.n_cols)
+
+    def to_torch_coo(self):
+        """For tests: (rows int64, cols int64, vals) on the host."""
+        rp = self.row_ptr.cpu().numpy().astype(np.int64)
+        base = rp[0]
+        counts = np.diff(rp)
+        rows = np.repeat(np.arange(self.n_rows, dtype=np.int64), counts)
+        cols = self.col_idx.cpu().numpy()[base:base + counts.sum()].astype(np.int64) - self.col_offset
+        vals = self.vals.cpu().numpy()[base:base + counts.sum()]
+        return rows, cols, vals
+
+
+def _degree_lut(recipe, n):
+    """deg -> deg^-1/2 with the reference's own host arithmetic (bit-exact by construction)."""
+    if recipe == "f64eps":        # layergcn.py:103-107: np.power(deg + 1e-7, -0.5) in float64
+        return np.power(np.arange(n, dtype=np.float64) + 1e-7, -0.5), True
+    if recipe == "f32":           # mgcn.py:120-123: np.power(rowsum_f32, -0.5), inf -> 0
+        with np.errstate(divide="ignore"):
+            t = np.power(np.arange(n, dtype=np.float32), np.float32(-0.5)).astype(np.float32)
+        t[np.isinf(t)] = 0.0
+        return t, False
+    if recipe == "edge_f32":      # layergcn.py:72-81: torch.pow(1e-7 + deg_int64, -0.5) float32
+        return torch.pow(1e-7 + torch.arange(n, dtype=torch.int64), -0.5).numpy(), False
+    raise ValueError(f"unknown normalisation recipe {recipe!r}")
+
+
+def build_ui_graph(users, items, n_users, n_items, recipe):
+    """K11/K12: CSR of D^-1/2 [[0,R],[R^T,0]] D^-1/2 from unique (user, item) edges on device."""
+    lib.require_cuda(users, items)
+    dev = users.device
+    users = users.to(torch.int64).contiguous()
+    items = items.to(torch.int64).contiguous()
+    E = users.numel()
+    n = n_users + n_items
+    lut_np, is64 = _degree_lut(recipe, max(n_users, n_items) + 1)
+    lut = torch.from_numpy(lut_np).to(dev)
+    row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    col_idx = torch.empty(2 * E, dtype=torch.int32, device=dev)
+    vals = torch.empty(2 * E, dtype=torch.float32, device=dev)
+    L = lib.load()
+    ws_bytes = L.mmrec_ui_adj_workspace_bytes(E, n_users, n_items)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    lib.call("mmrec_ui_adj_build", lib.ptr(users), lib.ptr(items), E, n_users, n_items, lib.ptr(lut),
+             lut.numel(), int(is64), lib.ptr(row_ptr), lib.ptr(col_idx), lib.ptr(vals), None,
+             lib.ptr(ws), ws_bytes, lib.stream())
+    g = CSRGraph(row_ptr, col_idx, vals, n, n, symmetric=True)
+    g.n_users, g.n_items = n_users, n_items
+    return g
+
+
+def ui_blocks(g):
+    """(R, R^T) views of a user-item graph: R = A[:U, U:] (mgcn.py:134, smore.py:198)."""
+    U, I = g.n_users, g.n_items
+    R = CSRGraph(g.row_ptr[:U + 1], g.col_idx, g.vals, U, I, col_offset=U)
+    Rt = CSRGraph(g.row_ptr[U:], g.col_idx, g.vals, I, U, col_offset=0)
+    R.t, Rt.t = Rt, R
+    return R, Rt
+
+
+def csr_from_coo(rows, cols, vals, n_rows, n_cols, with_transpose=True):
+    """COO (int64, unsorted, duplicates kept) -> CSRGraph; optionally with its transpose for
+    the backward of non-symmetric graphs."""
+    lib.require_cuda(rows, cols, vals)
+    dev = rows.device
+    rows = rows.to(torch.int64).contiguous()
+    cols = cols.to(torch.int64).contiguous()
+    vals = vals.to(torch.float32).contiguous()
+    nnz = rows.numel()
+    L = lib.load()
+    ws_bytes = L.mmrec_csr_from_coo_workspace_bytes(nnz)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+    def one(transpose):
+        out_rows = n_cols if transpose else n_rows
+        out_cols = n_rows if transpose else n_cols
+        row_ptr = torch.empty(out_rows + 1, dtype=torch.int32, device=dev)
+        col_idx = torch.empty(nnz, dtype=torch.int32, device=dev)
+        out_vals = torch.empty(nnz, dtype=torch.float32, device=dev)
+        lib.call("mmrec_csr_from_coo", lib.ptr(rows), lib.ptr(cols), lib.ptr(vals), nnz, n_rows,
+                 n_cols, int(transpose), lib.ptr(row_ptr), lib.ptr(col_idx), lib.ptr(out_vals), None,
+                 lib.ptr(ws), ws_bytes, lib.stream())
+        return CSRGraph(row_ptr, col_idx, out_vals, out_rows, out_cols)
+
+    g = one(False)
+    if with_transpose:
+        g.t = one(True)
+        g.t.t = g
+    return g
+
+
+def from_torch_sparse(a, with_transpose=True):
+    """A torch sparse COO tensor (as the reference builds them) -> CSRGraph."""
+    idx, val = a._indices(), a._values()
+    return csr_from_coo(idx[0], idx[1], val, a.shape[0], a.shape[1], with_transpose)

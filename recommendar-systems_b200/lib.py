@@ -1,0 +1,92 @@
+"""ctypes binding of libmmrec_b200.so (the C ABI declared in include/mmrec_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+torch tensors cross the boundary as raw device pointers + sizes; kernels are enqueued on
+torch's current CUDA stream so they compose with autograd, NCCL and CUDA-graph capture.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmrec_b200.so")
+
+_p, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/mmrec_b200.h
+SIGNATURES = {
+    "mmrec_abi_version": (C.c_int, []),
+    "mmrec_last_error": (C.c_char_p, []),
+    "mmrec_launch_count": (_i64, []),
+    "mmrec_ui_adj_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "mmrec_ui_adj_build": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p,
+                                     _sz, _p]),
+    "mmrec_csr_from_coo_workspace_bytes": (_sz, [_i64]),
+    "mmrec_csr_from_coo": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _sz,
+                                     _p]),
+    "mmrec_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _f32,
+                                     _p, _p, _p, _p]),
+    "mmrec_layergcn_cos_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
+    "mmrec_bpr_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "mmrec_bpr_bwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "mmrec_infonce_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p, _p, _p,
+                                        _p]),
+    "mmrec_infonce_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p,
+                                        _p]),
+    "mmrec_spectral_fwd_f32": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "mmrec_spectral_bwd_f32": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p,
+                                         _p, _p, _p, _p, _p, _p]),
+    "mmrec_score_mask_topk_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _i32, _p, _p, _i32, _i32,
+                                            _p, _p, _p, _p, _p]),
+    "mmrec_topk_merge": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if a declared symbol is absent
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.mmrec_last_error().decode(errors="replace")
+        raise RuntimeError(f"{name} failed with code {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().mmrec_launch_count())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmrec_b200 operators need CUDA tensors; there is no CPU fallback")

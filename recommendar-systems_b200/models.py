@@ -1,0 +1,576 @@
+"""LayerGCN, LightGCN, FREEDOM, MGCN and SMORE on the B200 operator layer.
+
+Same constructor `(config, dataloader)`, parameter names (state_dicts are interchangeable with the
+reference), RNG consumption order at init (same seed -> same initial parameters) and methods
+(`pre_epoch_processing`, `forward`, `calculate_loss`, `full_sort_predict`) as
+/root/reference/src/models/{layergcn,lightgcn,freedom,mgcn,smore}.py; the torch.sparse.mm /
+loss / spectral call sites are replaced by `ops.*` (hand-written sm_100a kernels). Adjacency
+tensors are `graph.CSRGraph` objects instead of torch sparse COO tensors.
+
+Additions that the reference does not have: `restore_embeddings()` (one propagation shared by
+all eval batches; parameters are frozen under eval) and `full_sort_topk()` (fused
+score + mask + top-K).
+"""
+from __future__ import annotations
+
+import os
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import graph as G
+from . import ops
+
+
+class AbstractRecommender(nn.Module):
+    """common/abstract_recommender.py:10-67."""
+
+    def pre_epoch_processing(self):
+        pass
+
+    def post_epoch_processing(self):
+        pass
+
+    def calculate_loss(self, interaction):
+        raise NotImplementedError
+
+    def predict(self, interaction):
+        raise NotImplementedError
+
+    def full_sort_predict(self, interaction):
+        raise NotImplementedError
+
+    def __str__(self):
+        params = sum(int(np.prod(p.size())) for p in self.parameters())
+        return super().__str__() + "\nTrainable parameters: {}".format(params)
+
+
+class GeneralRecommender(AbstractRecommender):
+    """common/abstract_recommender.py:70-103. Features come from `config['v_feat']`/`['t_feat']`
+    (synthetic tensors) or from the reference's .npy files under data_path/dataset."""
+
+    def __init__(self, config, dataloader):
+        super().__init__()
+        self.USER_ID, self.ITEM_ID = config["USER_ID_FIELD"], config["ITEM_ID_FIELD"]
+        self.NEG_ITEM_ID = config["NEG_PREFIX"] + self.ITEM_ID
+        self.n_users = dataloader.dataset.get_user_num()
+        self.n_items = dataloader.dataset.get_item_num()
+        self.batch_size = config["train_batch_size"]
+        self.device = config["device"]
+        self.v_feat, self.t_feat = None, None
+        if not config["end2end"] and config["is_multimodal_model"]:
+            v, t = config["v_feat"], config["t_feat"]
+            if v is None and t is None and config["data_path"]:
+                path = os.path.abspath(config["data_path"] + config["dataset"])
+                vp = os.path.join(path, config["vision_feature_file"])
+                tp = os.path.join(path, config["text_feature_file"])
+                v = np.load(vp, allow_pickle=True) if os.path.isfile(vp) else None
+                t = np.load(tp, allow_pickle=True) if os.path.isfile(tp) else None
+            if v is not None:
+                self.v_feat = torch.as_tensor(v).type(torch.FloatTensor).to(self.device)
+            if t is not None:
+                self.t_feat = torch.as_tensor(t).type(torch.FloatTensor).to(self.device)
+            assert self.v_feat is not None or self.t_feat is not None, "Features all NONE"
+        # training edges in the reference's order: inter_matrix('coo').astype(float32) is in
+        # canonical (user, item)-sorted order with the installed scipy (layergcn.py:20-21)
+        ds = dataloader.dataset
+        order = np.lexsort((ds.items, ds.users))
+        self._edge_u = torch.from_numpy(ds.users[order]).to(self.device)
+        self._edge_i = torch.from_numpy(ds.items[order]).to(self.device)
+        key = ds.users.astype(np.int64) * self.n_items + ds.items
+        if len(np.unique(key)) != len(key):
+            raise ValueError("duplicate (user, item) training interactions are not supported")
+        self._eval_cache = None
+
+    def train(self, mode=True):
+        self._eval_cache = None
+        return super().train(mode)
+
+    # -- evaluation helpers ----------------------------------------------------------------
+    def _eval_forward(self):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def restore_embeddings(self):
+        """(user_e, item_e) of the evaluation forward, computed once per eval pass."""
+        if self.training or self._eval_cache is None:
+            ue, ie = self._eval_forward()
+            if self.training:
+                return ue, ie
+            self._eval_cache = (ue.contiguous(), ie.contiguous())
+        return self._eval_cache
+
+    @torch.no_grad()
+    def full_sort_predict(self, interaction):
+        """[Bu, n_items] scores (layergcn.py:179-188, freedom.py:214-222, mgcn.py:255-263,
+        smore.py:414-422): API-compatible dense path. The trainer uses full_sort_topk."""
+        ue, ie = self._eval_forward()
+        return torch.matmul(ue[interaction[0]], ie.transpose(0, 1))
+
+    @torch.no_grad()
+    def full_sort_topk(self, users, k, mask_rowptr=None, mask_cols=None):
+        ue, ie = self.restore_embeddings()
+        return ops.score_mask_topk(ue, users, ie, k, mask_rowptr, mask_cols)
+
+
+def _split(x, n_users):
+    return x[:n_users], x[n_users:]
+
+
+# ============================================================================== LightGCN
+class LightGCN(GeneralRecommender):
+    """models/lightgcn.py (propagation + scoring are the hot path of config 5)."""
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.latent_dim = config["embedding_size"]
+        self.n_layers = config["n_layers"]
+        self.reg_weight = config["reg_weight"]
+        init = nn.init.xavier_uniform_
+        self.embedding_dict = nn.ParameterDict({
+            "user_emb": nn.Parameter(init(torch.empty(self.n_users, self.latent_dim))),
+            "item_emb": nn.Parameter(init(torch.empty(self.n_items, self.latent_dim)))})
+        self.norm_adj_matrix = G.build_ui_graph(self._edge_u, self._edge_i, self.n_users,
+                                                self.n_items, "f64eps")
+
+    def get_ego_embeddings(self):
+        return torch.cat([self.embedding_dict["user_emb"], self.embedding_dict["item_emb"]], 0)
+
+    def forward(self):
+        out = ops.propagate_mean(self.norm_adj_matrix, self.get_ego_embeddings(), self.n_layers)
+        return _split(out, self.n_users)
+
+    _eval_forward = forward
+
+    def calculate_loss(self, interaction):
+        user, pos, neg = interaction[0], interaction[1], interaction[2]
+        ue, ie = self.forward()
+        # BPRLoss with gamma (common/loss.py:28-36) and EmbLoss: plain torch, not a named hot op
+        ps = (ue[user] * ie[pos]).sum(1)
+        ns = (ue[user] * ie[neg]).sum(1)
+        mf = -torch.log(1e-10 + torch.sigmoid(ps - ns)).mean()
+        e = self.embedding_dict
+        reg = (torch.norm(e["user_emb"][user]) + torch.norm(e["item_emb"][pos]) +
+               torch.norm(e["item_emb"][neg])) / user.shape[0]
+        return mf + self.reg_weight * reg
+
+
+# ============================================================================== LayerGCN
+class LayerGCN(GeneralRecommender):
+    """models/layergcn.py:15-188."""
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.latent_dim = config["embedding_size"]
+        self.n_layers = config["n_layers"]
+        self.reg_weight = config["reg_weight"]
+        self.dropout = config["dropout"]
+        self.n_nodes = self.n_users + self.n_items
+        self.user_embeddings = nn.Parameter(nn.init.xavier_uniform_(torch.empty(self.n_users, self.latent_dim)))
+        self.item_embeddings = nn.Parameter(nn.init.xavier_uniform_(torch.empty(self.n_items, self.latent_dim)))
+        self.norm_adj_matrix = G.build_ui_graph(self._edge_u, self._edge_i, self.n_users,
+                                                self.n_items, "f64eps")
+        self.masked_adj = None
+        self.forward_adj = None
+        self.pruning_random = False
+        # layergcn.py:42,83-89: edge values stay on the CPU (the multinomial draws from the CPU RNG)
+        self.edge_values = _edge_values_cpu(self._edge_u, self._edge_i, self.n_users, self.n_items)
+
+    def pre_epoch_processing(self):
+        """layergcn.py:51-70: same RNG calls (torch.multinomial on CPU / random.sample,
+        alternating); re-normalisation + CSR rebuild on device (K12)."""
+        if self.dropout <= .0:
+            self.masked_adj = self.norm_adj_matrix
+            return
+        keep_len = int(self.edge_values.size(0) * (1. - self.dropout))
+        if self.pruning_random:
+            keep_idx = torch.tensor(random.sample(range(self.edge_values.size(0)), keep_len))
+        else:
+            keep_idx = torch.multinomial(self.edge_values, keep_len)
+        self.pruning_random = True ^ self.pruning_random
+        self.masked_adj = self._masked_graph(keep_idx)
+
+    def _masked_graph(self, keep_idx):
+        keep_idx = keep_idx.to(self.device)
+        return G.build_ui_graph(self._edge_u[keep_idx], self._edge_i[keep_idx], self.n_users,
+                                self.n_items, "edge_f32")
+
+    def get_ego_embeddings(self):
+        return torch.cat([self.user_embeddings, self.item_embeddings], 0)
+
+    def forward(self):
+        out = ops.layergcn_propagate(self.forward_adj, self.get_ego_embeddings(), self.n_layers)
+        return _split(out, self.n_users)
+
+    def _eval_forward(self):
+        self.forward_adj = self.norm_adj_matrix
+        return self.forward()
+
+    def calculate_loss(self, interaction):
+        """layergcn.py:165-177: sum-BPR on propagated rows + reg_weight * L2 on the ego rows."""
+        user, pos, neg = interaction[0], interaction[1], interaction[2]
+        self.forward_adj = self.masked_adj
+        ego = self.get_ego_embeddings()
+        out = ops.layergcn_propagate(self.forward_adj, ego, self.n_layers)
+        mf_loss = ops.bpr_table(out, self.n_users, user, pos, neg)[0]
+        reg_loss = ops.bpr_table(ego, self.n_users, user, pos, neg)[1]
+        return mf_loss + self.reg_weight * reg_loss
+
+
+def _edge_values_cpu(edge_u, edge_i, n_users, n_items):
+    """get_edge_info/_normalize_adj_m (layergcn.py:72-89) on the CPU, float32."""
+    u, i = edge_u.cpu(), edge_i.cpu()
+    r = torch.pow(1e-7 + torch.bincount(u, minlength=n_users), -0.5)
+    c = torch.pow(1e-7 + torch.bincount(i, minlength=n_items), -0.5)
+    return r[u] * c[i]
+
+
+# ----------------------------------------------------------------------------- item graphs
+def _build_sim(feat):
+    """utils/utils.py:134-137."""
+    n = feat.div(torch.norm(feat, p=2, dim=-1, keepdim=True))
+    return torch.mm(n, n.transpose(1, 0))
+
+
+def knn_sym_coo(feat, k):
+    """build_sim + build_knn_normalized_graph(sparse, 'sym') + get_sparse_laplacian
+    (utils/utils.py:134-152, 171-184) without the per-element Python list comprehension."""
+    sim = _build_sim(feat)
+    knn_val, knn_ind = torch.topk(sim, k, dim=-1)
+    n = sim.shape[0]
+    rows = torch.arange(n, device=feat.device).unsqueeze(1).expand(-1, k).flatten()
+    cols = knn_ind.flatten()
+    w = knn_val.flatten()
+    deg = torch.zeros(n, dtype=w.dtype, device=w.device).index_add_(0, rows, w)
+    dis = deg.pow(-0.5)
+    dis.masked_fill_(dis == float("inf"), 0)
+    return rows, cols, dis[rows] * w * dis[cols]
+
+
+def freedom_knn_coo(feat, k):
+    """FREEDOM.get_knn_adj_mat + compute_normalized_laplacian (freedom.py:79-100)."""
+    sim = _build_sim(feat)
+    _, knn_ind = torch.topk(sim, k, dim=-1)
+    n = sim.shape[0]
+    rows = torch.arange(n, device=feat.device).unsqueeze(1).expand(-1, k).flatten()
+    cols = knn_ind.flatten()
+    row_sum = 1e-7 + torch.bincount(rows, minlength=n)
+    r = torch.pow(row_sum, -0.5)
+    return rows, cols, r[rows] * r[cols]
+
+
+def max_pool_fusion_coo(a, b, n):
+    """SMORE.max_pool_fusion (smore.py:153-174)."""
+    ka = a[0] * n + a[1]
+    kb = b[0] * n + b[1]
+    keys, inv = torch.unique(torch.cat([ka, kb]), return_inverse=True)
+    va = torch.full((keys.numel(),), float("-inf"), device=keys.device)
+    vb = torch.full((keys.numel(),), float("-inf"), device=keys.device)
+    va[inv[:ka.numel()]] = a[2]
+    vb[inv[ka.numel():]] = b[2]
+    return keys // n, keys % n, torch.maximum(va, vb)
+
+
+def _coo_override(config, name, device):
+    """Tests inject reference-built graphs through config['item_graphs'][name] = (r, c, v)."""
+    g = (config["item_graphs"] or {}).get(name)
+    if g is None:
+        return None
+    return tuple(torch.as_tensor(x).to(device) for x in g)
+
+
+# ============================================================================== FREEDOM
+class FREEDOM(GeneralRecommender):
+    """models/freedom.py:22-222."""
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.embedding_dim = config["embedding_size"]
+        self.feat_embed_dim = config["feat_embed_dim"]
+        self.knn_k = config["knn_k"]
+        self.n_layers = config["n_mm_layers"]
+        self.n_ui_layers = config["n_ui_layers"]
+        self.reg_weight = config["reg_weight"]
+        self.mm_image_weight = config["mm_image_weight"]
+        self.dropout = config["dropout"]
+        self.n_nodes = self.n_users + self.n_items
+        self.norm_adj = G.build_ui_graph(self._edge_u, self._edge_i, self.n_users, self.n_items,
+                                         "f64eps")
+        self.masked_adj, self.mm_adj = None, None
+        # freedom.py:45-46: edge values live on the device (multinomial draws from the CUDA RNG)
+        self.edge_values = _edge_values_cpu(self._edge_u, self._edge_i, self.n_users,
+                                            self.n_items).to(self.device)
+        self.user_embedding = nn.Embedding(self.n_users, self.embedding_dim)
+        self.item_id_embedding = nn.Embedding(self.n_items, self.embedding_dim)
+        nn.init.xavier_uniform_(self.user_embedding.weight)
+        nn.init.xavier_uniform_(self.item_id_embedding.weight)
+        if self.v_feat is not None:
+            self.image_embedding = nn.Embedding.from_pretrained(self.v_feat, freeze=False)
+            self.image_trs = nn.Linear(self.v_feat.shape[1], self.feat_embed_dim)
+        if self.t_feat is not None:
+            self.text_embedding = nn.Embedding.from_pretrained(self.t_feat, freeze=False)
+            self.text_trs = nn.Linear(self.t_feat.shape[1], self.feat_embed_dim)
+        coo = _coo_override(config, "mm_adj", self.device)
+        if coo is None:
+            # freedom.py:64-77: w * image_adj + (1-w) * text_adj; duplicates are summed by SpMM
+            ri, ci, vi = freedom_knn_coo(self.v_feat, self.knn_k)
+            rt, ct, vt = freedom_knn_coo(self.t_feat, self.knn_k)
+            w = self.mm_image_weight
+            coo = (torch.cat([ri, rt]), torch.cat([ci, ct]), torch.cat([w * vi, (1.0 - w) * vt]))
+        self.mm_adj = G.csr_from_coo(*coo, self.n_items, self.n_items)
+
+    def pre_epoch_processing(self):
+        """freedom.py:130-145."""
+        if self.dropout <= .0:
+            self.masked_adj = self.norm_adj
+            return
+        degree_len = int(self.edge_values.size(0) * (1. - self.dropout))
+        degree_idx = torch.multinomial(self.edge_values, degree_len)
+        self.masked_adj = self._masked_graph(degree_idx)
+
+    def _masked_graph(self, keep_idx):
+        keep_idx = keep_idx.to(self.device)
+        return G.build_ui_graph(self._edge_u[keep_idx], self._edge_i[keep_idx], self.n_users,
+                                self.n_items, "edge_f32")
+
+    def forward(self, adj):
+        h = self.item_id_embedding.weight
+        for _ in range(self.n_layers):
+            h = ops.spmm(self.mm_adj, h)
+        ego = torch.cat((self.user_embedding.weight, self.item_id_embedding.weight), dim=0)
+        out = ops.propagate_mean(adj, ego, self.n_ui_layers)
+        u_g, i_g = _split(out, self.n_users)
+        return u_g, i_g + h
+
+    def _eval_forward(self):
+        return self.forward(self.norm_adj)
+
+    def calculate_loss(self, interaction):
+        """freedom.py:191-212."""
+        users, pos, neg = interaction[0], interaction[1], interaction[2]
+        ua, ia = self.forward(self.masked_adj)
+        B = users.shape[0]
+        loss = ops.bpr(ua, ia, users, pos, neg)[0] / B
+        mf_v = mf_t = 0.0
+        if self.t_feat is not None:
+            text_feats = self.text_trs(self.text_embedding.weight)
+            mf_t = ops.bpr(ua, text_feats, users, pos, neg)[0] / B
+        if self.v_feat is not None:
+            image_feats = self.image_trs(self.image_embedding.weight)
+            mf_v = ops.bpr(ua, image_feats, users, pos, neg)[0] / B
+        return loss + self.reg_weight * (mf_t + mf_v)
+
+
+# ============================================================================== MGCN / SMORE
+class _MultiViewBase(GeneralRecommender):
+    """Shared pieces of MGCN (mgcn.py) and SMORE (smore.py)."""
+
+    def _init_ui(self):
+        self.norm_adj = G.build_ui_graph(self._edge_u, self._edge_i, self.n_users, self.n_items,
+                                         "f32")
+        self.R, self.R_t = G.ui_blocks(self.norm_adj)
+
+    def _item_graph(self, config, name, feat, k):
+        coo = _coo_override(config, name, self.device)
+        if coo is None:
+            coo = knn_sym_coo(feat, k)
+        return coo, G.csr_from_coo(*coo, self.n_items, self.n_items)
+
+    def _reg_bpr(self, all_e, users, pos, neg):
+        """mgcn.py:210-222 / smore.py:366-378: mean BPR + reg_weight * L2/2 / train_batch_size."""
+        o = ops.bpr_table(all_e, self.n_users, users, pos, neg)
+        return o[0] / users.shape[0] + self.reg_weight * (o[1] / self.batch_size)
+
+    def _view(self, x, item_graph):
+        for _ in range(self.n_layers):
+            x = ops.spmm(item_graph, x)
+        return torch.cat([ops.spmm(self.R, x), x], dim=0)
+
+    def _eval_forward(self):
+        return self.forward(self.norm_adj)
+
+
+class MGCN(_MultiViewBase):
+    """models/mgcn.py:21-263."""
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.sparse = True
+        self.cl_loss = config["cl_loss"]
+        self.n_ui_layers = config["n_ui_layers"]
+        self.embedding_dim = config["embedding_size"]
+        self.knn_k = config["knn_k"]
+        self.n_layers = config["n_layers"]
+        self.reg_weight = config["reg_weight"]
+        d = self.embedding_dim
+        self.user_embedding = nn.Embedding(self.n_users, d)
+        self.item_id_embedding = nn.Embedding(self.n_items, d)
+        nn.init.xavier_uniform_(self.user_embedding.weight)
+        nn.init.xavier_uniform_(self.item_id_embedding.weight)
+        self._init_ui()
+        self.image_embedding = nn.Embedding.from_pretrained(self.v_feat, freeze=False)
+        _, self.image_original_adj = self._item_graph(config, "image_adj", self.v_feat, self.knn_k)
+        self.text_embedding = nn.Embedding.from_pretrained(self.t_feat, freeze=False)
+        _, self.text_original_adj = self._item_graph(config, "text_adj", self.t_feat, self.knn_k)
+        self.image_trs = nn.Linear(self.v_feat.shape[1], d)
+        self.text_trs = nn.Linear(self.t_feat.shape[1], d)
+        self.softmax = nn.Softmax(dim=-1)
+        self.query_common = nn.Sequential(nn.Linear(d, d), nn.Tanh(), nn.Linear(d, 1, bias=False))
+        self.gate_v = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.gate_t = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.gate_image_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.gate_text_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.tau = 0.5
+
+    def forward(self, adj, train=False):
+        """mgcn.py:146-208."""
+        all_e, side, content = self._forward_full(adj)
+        u, i = _split(all_e, self.n_users)
+        return (u, i, side, content) if train else (u, i)
+
+    def _forward_full(self, adj):
+        image_feats = self.image_trs(self.image_embedding.weight)
+        text_feats = self.text_trs(self.text_embedding.weight)
+        item = self.item_id_embedding.weight
+        image_item = item * self.gate_v(image_feats)
+        text_item = item * self.gate_t(text_feats)
+        ego = torch.cat([self.user_embedding.weight, item], dim=0)
+        content = ops.propagate_mean(adj, ego, self.n_ui_layers)
+        image_embeds = self._view(image_item, self.image_original_adj)
+        text_embeds = self._view(text_item, self.text_original_adj)
+        att = torch.cat([self.query_common(image_embeds), self.query_common(text_embeds)], dim=-1)
+        w = self.softmax(att)
+        common = w[:, 0].unsqueeze(1) * image_embeds + w[:, 1].unsqueeze(1) * text_embeds
+        sep_i = self.gate_image_prefer(content) * (image_embeds - common)
+        sep_t = self.gate_text_prefer(content) * (text_embeds - common)
+        side = (sep_i + sep_t + common) / 3
+        return content + side, side, content
+
+    def calculate_loss(self, interaction):
+        """mgcn.py:233-253."""
+        users, pos, neg = interaction[0], interaction[1], interaction[2]
+        all_e, side, content = self._forward_full(self.norm_adj)
+        loss = self._reg_bpr(all_e, users, pos, neg)
+        cl = ops.infonce_pair(side, content, self.n_users, users, pos, 0.2)
+        return loss + self.cl_loss * cl
+
+
+class SMORE(_MultiViewBase):
+    """models/smore.py:24-449 (this fork: residual injection, unit-magnitude spectral weights,
+    mirror-gradient flags read by the trainer)."""
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.sparse = True
+        self.cl_loss = config["cl_loss"]
+        self.n_ui_layers = config["n_ui_layers"]
+        self.embedding_dim = config["embedding_size"]
+        self.n_layers = config["n_layers"]
+        self.reg_weight = config["reg_weight"]
+        self.image_knn_k = config["image_knn_k"]
+        self.text_knn_k = config["text_knn_k"]
+        self.dropout_rate = config["dropout_rate"]
+        self.dropout = nn.Dropout(p=self.dropout_rate)
+        d = self.embedding_dim
+        self.user_embedding = nn.Embedding(self.n_users, d)
+        self.item_id_embedding = nn.Embedding(self.n_items, d)
+        nn.init.xavier_uniform_(self.user_embedding.weight)
+        nn.init.xavier_uniform_(self.item_id_embedding.weight)
+        self._init_ui()
+        self.image_embedding = nn.Embedding.from_pretrained(self.v_feat, freeze=False)
+        img_coo, self.image_original_adj = self._item_graph(config, "image_adj", self.v_feat,
+                                                            self.image_knn_k)
+        self.text_embedding = nn.Embedding.from_pretrained(self.t_feat, freeze=False)
+        txt_coo, self.text_original_adj = self._item_graph(config, "text_adj", self.t_feat,
+                                                           self.text_knn_k)
+        fus = _coo_override(config, "fusion_adj", self.device)
+        if fus is None:
+            fus = max_pool_fusion_coo(img_coo, txt_coo, self.n_items)
+        self.fusion_adj = G.csr_from_coo(*fus, self.n_items, self.n_items)
+        self.image_trs = nn.Linear(self.v_feat.shape[1], d)
+        self.text_trs = nn.Linear(self.t_feat.shape[1], d)
+        self.softmax = nn.Softmax(dim=-1)
+        self.query_v = nn.Sequential(nn.Linear(d, d), nn.Tanh(), nn.Linear(d, d, bias=False))
+        self.query_t = nn.Sequential(nn.Linear(d, d), nn.Tanh(), nn.Linear(d, d, bias=False))
+        self.gate_v = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.gate_t = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.gate_f = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.gate_image_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.gate_text_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.gate_fusion_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.image_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))
+        self.text_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))
+        self.fusion_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))
+        # smore.py:128-146
+        self.mg_enable = bool(config.get("mg_enable", True))
+        self.mg_interval = int(config.get("mg_interval", 3))
+        self.mg_alpha = float(config.get("mg_alpha", 0.5))
+        self.mg_beta = float(config.get("mg_beta", 0.2))
+        self.mg_verbose = bool(config.get("mg_verbose", False))
+        self.global_step = 0
+        self.inject_mode = config.get("inject_mode", "residual")
+        self.inject_scale = float(config.get("inject_scale", 0.7))
+        self.spectral_weight_norm = bool(config.get("spectral_weight_norm", True))
+        self.cl_temp = float(config.get("cl_temp", 0.2))
+
+    def spectrum_convolution(self, image_embeds, text_embeds):
+        """smore.py:209-252 without the band-energy .item() syncs (diagnostics only)."""
+        return ops.spectrum_convolution(image_embeds, text_embeds, self.image_complex_weight[0],
+                                        self.text_complex_weight[0], self.fusion_complex_weight[0],
+                                        self.spectral_weight_norm)
+
+    def forward(self, adj, train=False):
+        """smore.py:255-364."""
+        all_e, side, content = self._forward_full(adj)
+        u, i = _split(all_e, self.n_users)
+        return (u, i, side, content) if train else (u, i)
+
+    def _forward_full(self, adj):
+        image_feats = self.image_trs(self.image_embedding.weight)
+        text_feats = self.text_trs(self.text_embedding.weight)
+        image_conv, text_conv, fusion_conv = self.spectrum_convolution(image_feats, text_feats)
+        item = self.item_id_embedding.weight
+        if self.inject_mode == "mul":
+            image_item = item * self.gate_v(image_conv)
+            text_item = item * self.gate_t(text_conv)
+            fusion_item = item * self.gate_f(fusion_conv)
+        else:
+            image_item = item + self.inject_scale * self.gate_v(image_conv)
+            text_item = item + self.inject_scale * self.gate_t(text_conv)
+            fusion_item = item + self.inject_scale * self.gate_f(fusion_conv)
+        ego = torch.cat([self.user_embedding.weight, item], dim=0)
+        content = ops.propagate_mean(adj, ego, self.n_ui_layers)
+        image_embeds = self._view(image_item, self.image_original_adj)
+        text_embeds = self._view(text_item, self.text_original_adj)
+        fusion_embeds = self._view(fusion_item, self.fusion_adj)
+        # modality-aware preference module (smore.py:321-341): dense side network, torch ops
+        agg_image = self.softmax(self.query_v(fusion_embeds)) * image_embeds
+        agg_text = self.softmax(self.query_t(fusion_embeds)) * text_embeds
+        image_prefer = self.dropout(self.gate_image_prefer(content))
+        text_prefer = self.dropout(self.gate_text_prefer(content))
+        fusion_prefer = self.dropout(self.gate_fusion_prefer(content))
+        side = torch.mean(torch.stack([image_prefer * agg_image, text_prefer * agg_text,
+                                       fusion_prefer * fusion_embeds]), dim=0)
+        return content + side, side, content
+
+    def calculate_loss(self, interaction):
+        """smore.py:389-411 (global_step is bumped here, which is what makes every step after
+        the second a mirror-gradient step in the trainer -- SURVEY 3.2)."""
+        users, pos, neg = interaction[0], interaction[1], interaction[2]
+        all_e, side, content = self._forward_full(self.norm_adj)
+        self.global_step += 1
+        loss = self._reg_bpr(all_e, users, pos, neg)
+        cl = ops.infonce_pair(side, content, self.n_users, users, pos, self.cl_temp)
+        return loss + self.cl_loss * cl
+
+
+MODELS = {"LightGCN": LightGCN, "LayerGCN": LayerGCN, "FREEDOM": FREEDOM, "MGCN": MGCN,
+          "SMORE": SMORE}
+
+
+def get_model(model_name):
+    """utils/utils.py:28-41."""
+    return MODELS[model_name]

@@ -1,0 +1,351 @@
+"""torch.autograd wrappers over the C ABI: the operator layer the models are written against.
+
+Each Function replaces a family of torch call sites in the reference models (file:line cited per
+op). Everything runs on CUDA through libmmrec_b200.so; there is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib
+from .graph import CSRGraph
+
+_counters = {}
+
+
+def _counter(device):
+    """Zero-initialised arrival counter shared by the self-resetting last-block reductions."""
+    key = (device.type, device.index)
+    if key not in _counters:
+        _counters[key] = torch.zeros(4, dtype=torch.int32, device=device)
+    return _counters[key]
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def spmm_raw(g: CSRGraph, X, Y=None, acc_in=None, acc_out=None, acc_scale=1.0, cos_ref=None,
+             cos_w=None, y_pre=None):
+    """mmrec_spmm_csr_f32 on already-allocated tensors (no autograd)."""
+    lib.require_cuda(X)
+    d = X.shape[1]
+    if X.shape[0] < g.n_cols:
+        raise RuntimeError(f"spmm: X has {X.shape[0]} rows, graph has {g.n_cols} columns")
+    lib.call("mmrec_spmm_csr_f32", lib.ptr(g.row_ptr), lib.ptr(g.col_idx), lib.ptr(g.vals),
+             lib.ptr(g.sched), g.n_rows, g.n_long, g.col_offset, lib.ptr(X), d, lib.ptr(Y),
+             lib.ptr(acc_in), lib.ptr(acc_out), float(acc_scale), lib.ptr(cos_ref), lib.ptr(cos_w),
+             lib.ptr(y_pre), lib.stream())
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, g):
+        X = _f32c(X)
+        Y = torch.empty(g.n_rows, X.shape[1], dtype=torch.float32, device=X.device)
+        spmm_raw(g, X, Y=Y)
+        ctx.g = g
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        g = ctx.g
+        if g.t is None:
+            raise RuntimeError("spmm backward needs the transposed CSR (build with_transpose=True)")
+        dY = _f32c(dY)
+        dX = torch.empty(g.t.n_rows, dY.shape[1], dtype=torch.float32, device=dY.device)
+        spmm_raw(g.t, dY, Y=dX)
+        return dX, None
+
+
+def spmm(g: CSRGraph, X):
+    """Y = A X; replaces torch.sparse.mm(A, X) (layergcn.py:133, freedom.py:169,174,
+    mgcn.py:162-184, smore.py:282-317, lightgcn.py:122). Backward: dX = A^T dY."""
+    return _SpMM.apply(X, g)
+
+
+def _horner(g, G, n_layers, scale_last):
+    """t <- G + A t, n_layers times, starting from t = G; last step scaled."""
+    t = G
+    for l in range(n_layers):
+        out = torch.empty_like(G)
+        spmm_raw(g, t, acc_in=G, acc_out=out, acc_scale=scale_last if l == n_layers - 1 else 1.0)
+        t = out
+    return t
+
+
+class _PropagateMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X0, g, n_layers):
+        X0 = _f32c(X0)
+        ctx.g, ctx.n_layers = g, n_layers
+        if n_layers == 0:
+            return X0.clone()
+        inv = 1.0 / (n_layers + 1)
+        acc = torch.empty_like(X0)
+        x = X0
+        for l in range(1, n_layers + 1):
+            last = l == n_layers
+            y = None if last else torch.empty_like(X0)
+            spmm_raw(g, x, Y=y, acc_in=X0 if l == 1 else acc, acc_out=acc,
+                     acc_scale=inv if last else 1.0)
+            x = y
+        return acc
+
+    @staticmethod
+    def backward(ctx, dOut):
+        g, L = ctx.g, ctx.n_layers
+        dOut = _f32c(dOut)
+        if L == 0:
+            return dOut, None, None
+        gt = g.t
+        if gt is None:
+            raise RuntimeError("propagate_mean backward needs the transposed CSR")
+        # d X0 = 1/(L+1) * sum_l (A^T)^l dOut, evaluated as a Horner chain
+        return _horner(gt, dOut, L, 1.0 / (L + 1)), None, None
+
+
+def propagate_mean(g: CSRGraph, X0, n_layers):
+    """mean_{l=0..L} A^l X0 with the running sum fused into the SpMM epilogue; replaces the
+    layer loop + stack + mean at freedom.py:171-179, mgcn.py:159-167, smore.py:278-287,
+    lightgcn.py:118-128."""
+    return _PropagateMean.apply(X0, g, n_layers)
+
+
+class _LayerGCNPropagate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X0, g, n_layers):
+        X0 = _f32c(X0)
+        n, d = X0.shape
+        P = torch.empty(n_layers, n, d, dtype=torch.float32, device=X0.device)
+        W = torch.empty(n_layers, n, dtype=torch.float32, device=X0.device)
+        acc = torch.empty_like(X0)
+        x = X0
+        for l in range(n_layers):
+            y = torch.empty_like(X0) if l < n_layers - 1 else None
+            spmm_raw(g, x, Y=y, acc_in=None if l == 0 else acc, acc_out=acc, acc_scale=1.0,
+                     cos_ref=X0, cos_w=W[l], y_pre=P[l])
+            x = y
+        ctx.g, ctx.n_layers = g, n_layers
+        ctx.save_for_backward(X0, P, W)
+        return acc
+
+    @staticmethod
+    def backward(ctx, dOut):
+        X0, P, W = ctx.saved_tensors
+        g, L = ctx.g, ctx.n_layers
+        gt = g.t
+        dOut = _f32c(dOut)
+        n, d = X0.shape
+        dE0 = torch.zeros_like(X0)
+        dE = dOut
+        for l in range(L - 1, -1, -1):
+            dP = torch.empty_like(X0)
+            lib.call("mmrec_layergcn_cos_bwd_f32", lib.ptr(dE), lib.ptr(P[l]), lib.ptr(X0),
+                     lib.ptr(W[l]), n, d, lib.ptr(dP), lib.ptr(dE0), lib.stream())
+            if l > 0:
+                nxt = torch.empty_like(X0)
+                spmm_raw(gt, dP, acc_in=dOut, acc_out=nxt)       # dE_{l-1} = dOut + A^T dP_l
+                dE = nxt
+            else:
+                spmm_raw(gt, dP, acc_in=dE0, acc_out=dE0)        # dX0 = dE0 + A^T dP_1
+        return dE0, None, None
+
+
+def layergcn_propagate(g: CSRGraph, X0, n_layers):
+    """LayerGCN.forward's layer loop (layergcn.py:127-140): SpMM, cosine re-weighting against the
+    ego layer and the layer sum fused in one kernel per layer."""
+    return _LayerGCNPropagate.apply(X0, g, n_layers)
+
+
+# ----------------------------------------------------------------------------------------- BPR
+def _bpr_fwd(ue, ie, users, pos, neg):
+    B, d = users.numel(), ue.shape[1]
+    out = torch.empty(2, dtype=torch.float32, device=ue.device)
+    sig = torch.empty(B, dtype=torch.float32, device=ue.device)
+    partial = torch.empty(2 * B, dtype=torch.float32, device=ue.device)
+    lib.call("mmrec_bpr_fwd_f32", lib.ptr(ue), lib.ptr(ie), d, lib.ptr(users), lib.ptr(pos),
+             lib.ptr(neg), B, lib.ptr(out), lib.ptr(sig), lib.ptr(partial),
+             lib.ptr(_counter(ue.device)), lib.stream())
+    return out, sig
+
+
+class _BPRSplit(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ue, ie, users, pos, neg):
+        ue, ie = _f32c(ue), _f32c(ie)
+        out, sig = _bpr_fwd(ue, ie, users, pos, neg)
+        ctx.save_for_backward(ue, ie, users, pos, neg, sig)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ue, ie, users, pos, neg, sig = ctx.saved_tensors
+        g = _f32c(g)
+        due, die = torch.zeros_like(ue), torch.zeros_like(ie)
+        lib.call("mmrec_bpr_bwd_f32", lib.ptr(ue), lib.ptr(ie), ue.shape[1], lib.ptr(users),
+                 lib.ptr(pos), lib.ptr(neg), users.numel(), lib.ptr(sig), lib.ptr(g), lib.ptr(due),
+                 lib.ptr(die), lib.stream())
+        return due, die, None, None, None
+
+
+class _BPRTable(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, n_users, users, pos, neg):
+        emb = _f32c(emb)
+        out, sig = _bpr_fwd(emb[:n_users], emb[n_users:], users, pos, neg)
+        ctx.n_users = n_users
+        ctx.save_for_backward(emb, users, pos, neg, sig)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        emb, users, pos, neg, sig = ctx.saved_tensors
+        nu = ctx.n_users
+        g = _f32c(g)
+        d_emb = torch.zeros_like(emb)
+        lib.call("mmrec_bpr_bwd_f32", lib.ptr(emb[:nu]), lib.ptr(emb[nu:]), emb.shape[1],
+                 lib.ptr(users), lib.ptr(pos), lib.ptr(neg), users.numel(), lib.ptr(sig), lib.ptr(g),
+                 lib.ptr(d_emb[:nu]), lib.ptr(d_emb[nu:]), lib.stream())
+        return d_emb, None, None, None, None
+
+
+def bpr(user_emb, item_emb, users, pos, neg):
+    """-> tensor[2] = (sum_b -logsigmoid(<u,p> - <u,n>), sum_b 0.5(|u|^2+|p|^2+|n|^2)).
+    Replaces the gather + mul + sum + logsigmoid chains at layergcn.py:142-163,
+    freedom.py:182-189, mgcn.py:210-222, smore.py:366-378."""
+    return _BPRSplit.apply(user_emb, item_emb, users, pos, neg)
+
+
+def bpr_table(all_emb, n_users, users, pos, neg):
+    """Same, for a stacked [users; items] table (one dense gradient instead of two slices)."""
+    return _BPRTable.apply(all_emb, n_users, users, pos, neg)
+
+
+# ------------------------------------------------------------------------------------- InfoNCE
+class _InfoNCEPair(torch.autograd.Function):
+    """cl_items + cl_users of MGCN/SMORE.calculate_loss (mgcn.py:248-251, smore.py:403-408) on
+    stacked [users; items] tables."""
+
+    @staticmethod
+    def forward(ctx, side, content, n_users, users, pos_items, temperature):
+        side, content = _f32c(side), _f32c(content)
+        dev, d = side.device, side.shape[1]
+        inv_t = 1.0 / temperature
+        saved = []
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        for slot, (row0, idx) in enumerate(((n_users, pos_items), (0, users))):
+            B = idx.numel()
+            V1 = torch.empty(B, d, dtype=torch.float32, device=dev)
+            V2 = torch.empty_like(V1)
+            inv_norm = torch.empty(2 * B, dtype=torch.float32, device=dev)
+            ttl = torch.empty(B, dtype=torch.float32, device=dev)
+            partial = torch.empty(16 * B, dtype=torch.float32, device=dev)
+            lib.call("mmrec_infonce_fwd_f32", lib.ptr(side[row0:]), lib.ptr(content[row0:]), d,
+                     lib.ptr(idx), B, inv_t, lib.ptr(losses[slot:]), lib.ptr(V1), lib.ptr(V2),
+                     lib.ptr(inv_norm), lib.ptr(ttl), lib.ptr(partial), lib.ptr(_counter(dev)),
+                     lib.stream())
+            saved += [V1, V2, inv_norm, ttl, idx]
+        ctx.n_users, ctx.inv_t, ctx.shape = n_users, inv_t, side.shape
+        ctx.save_for_backward(*saved)
+        return losses.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        n, d = ctx.shape
+        dev = g.device
+        coef = _f32c(g).reshape(1)
+        d_side = torch.zeros(n, d, dtype=torch.float32, device=dev)
+        d_content = torch.zeros(n, d, dtype=torch.float32, device=dev)
+        for slot, row0 in enumerate((ctx.n_users, 0)):
+            V1, V2, inv_norm, ttl, idx = saved[5 * slot: 5 * slot + 5]
+            B = idx.numel()
+            ws1, ws2 = torch.empty_like(V1), torch.empty_like(V2)
+            lib.call("mmrec_infonce_bwd_f32", lib.ptr(V1), lib.ptr(V2), lib.ptr(inv_norm),
+                     lib.ptr(ttl), d, lib.ptr(idx), B, ctx.inv_t, lib.ptr(coef), lib.ptr(ws1),
+                     lib.ptr(ws2), lib.ptr(d_side[row0:]), lib.ptr(d_content[row0:]), lib.stream())
+        return d_side, d_content, None, None, None, None
+
+
+def infonce_pair(side, content, n_users, users, pos_items, temperature):
+    return _InfoNCEPair.apply(side, content, n_users, users, pos_items, temperature)
+
+
+# ------------------------------------------------------------------------------------ spectral
+class _Spectral(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, txt, w_img, w_txt, w_fus, weight_norm):
+        img, txt = _f32c(img), _f32c(txt)
+        w_img, w_txt, w_fus = _f32c(w_img), _f32c(w_txt), _f32c(w_fus)
+        n, d = img.shape
+        taps = torch.empty(3 * d, dtype=torch.float32, device=img.device)
+        ic, tc, fc = torch.empty_like(img), torch.empty_like(img), torch.empty_like(img)
+        lib.call("mmrec_spectral_fwd_f32", lib.ptr(img), lib.ptr(txt), n, d, lib.ptr(w_img),
+                 lib.ptr(w_txt), lib.ptr(w_fus), int(weight_norm), lib.ptr(taps), lib.ptr(ic),
+                 lib.ptr(tc), lib.ptr(fc), lib.stream())
+        ctx.weight_norm = int(weight_norm)
+        ctx.save_for_backward(img, txt, w_img, w_txt, w_fus, taps)
+        return ic, tc, fc
+
+    @staticmethod
+    def backward(ctx, g_ic, g_tc, g_fc):
+        img, txt, w_img, w_txt, w_fus, taps = ctx.saved_tensors
+        n, d = img.shape
+        g_ic, g_tc, g_fc = _f32c(g_ic), _f32c(g_tc), _f32c(g_fc)
+        d_img, d_txt = torch.empty_like(img), torch.empty_like(txt)
+        dh = torch.zeros(3 * d, dtype=torch.float32, device=img.device)
+        dwi, dwt, dwf = torch.empty_like(w_img), torch.empty_like(w_txt), torch.empty_like(w_fus)
+        lib.call("mmrec_spectral_bwd_f32", lib.ptr(img), lib.ptr(txt), n, d, lib.ptr(w_img),
+                 lib.ptr(w_txt), lib.ptr(w_fus), ctx.weight_norm, lib.ptr(taps), lib.ptr(g_ic),
+                 lib.ptr(g_tc), lib.ptr(g_fc), lib.ptr(d_img), lib.ptr(d_txt), lib.ptr(dh),
+                 lib.ptr(dwi), lib.ptr(dwt), lib.ptr(dwf), lib.stream())
+        return d_img, d_txt, dwi, dwt, dwf, None
+
+
+def spectrum_convolution(img, txt, w_img, w_txt, w_fus, weight_norm=True):
+    """SMORE.spectrum_convolution (smore.py:209-238) -> (image_conv, text_conv, fusion_conv)."""
+    return _Spectral.apply(img, txt, w_img, w_txt, w_fus, weight_norm)
+
+
+# -------------------------------------------------------------------------------- score + top-K
+def choose_splits(n_users, n_items):
+    tiles = (n_users + 127) // 128
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return int(max(1, min(want, 16, (n_items + 255) // 256)))
+
+
+@torch.no_grad()
+def score_mask_topk(user_emb, users, item_emb, k, mask_rowptr=None, mask_cols=None, item_offset=0,
+                    n_splits=None, return_scores=False, merge=True):
+    """Fused `u @ item_e.T` + `scores[mask] = -1e10` + top-K (smore.py:421 / trainer.py:522-526).
+    Returns ids int64 [n_users, k] (+ scores). With merge=False returns the per-split partial
+    lists (vals [S, n, k], ids int32 [S, n, k]) for a cross-rank merge."""
+    user_emb, item_emb = _f32c(user_emb), _f32c(item_emb)
+    lib.require_cuda(user_emb, item_emb, users)
+    n, n_items, d = users.numel(), item_emb.shape[0], item_emb.shape[1]
+    dev = user_emb.device
+    S = n_splits or choose_splits(n, n_items)
+    ws_val = torch.empty(S, n, k, dtype=torch.float32, device=dev)
+    ws_idx = torch.empty(S, n, k, dtype=torch.int32, device=dev)
+    out_val = torch.empty(n, k, dtype=torch.float32, device=dev)
+    out_idx = torch.empty(n, k, dtype=torch.int64, device=dev)
+    lib.call("mmrec_score_mask_topk_f32", lib.ptr(user_emb), lib.ptr(users), n, lib.ptr(item_emb),
+             n_items, item_offset, d, lib.ptr(mask_rowptr), lib.ptr(mask_cols), k, S,
+             lib.ptr(ws_val), lib.ptr(ws_idx), lib.ptr(out_val), lib.ptr(out_idx), lib.stream())
+    if not merge:
+        return ws_val, ws_idx
+    return (out_idx, out_val) if return_scores else out_idx
+
+
+@torch.no_grad()
+def topk_merge(vals, idx):
+    """K-way merge of [L, n, k] descending lists (ties -> lower id)."""
+    L, n, k = vals.shape
+    out_val = torch.empty(n, k, dtype=torch.float32, device=vals.device)
+    out_idx = torch.empty(n, k, dtype=torch.int64, device=vals.device)
+    lib.call("mmrec_topk_merge", lib.ptr(vals.contiguous()), lib.ptr(idx.contiguous()), L, n, k,
+             lib.ptr(out_val), lib.ptr(out_idx), lib.stream())
+    return out_idx, out_val

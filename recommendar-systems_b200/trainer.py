@@ -1,0 +1,333 @@
+"""Trainer / TopKEvaluator with the reference's contract.
+
+Mirror of /root/reference/src/common/trainer.py:47-548 (`fit`, `_train_epoch` including the
+mirror-gradient schedule of models with `mg_enable`, `evaluate`) and
+/root/reference/src/utils/topk_evaluator.py:19-149 + utils/metrics.py:12-109.
+
+Differences, all on the host side of the hot path:
+* `evaluate` propagates once per pass (`model.restore_embeddings`) and runs the fused
+  score + mask + top-K kernel per user batch instead of materialising [Bu, n_items] scores; it
+  still hands `batch_matrix_list` (int64 [Bu, max(topk)]) to the evaluator. Ties are broken by
+  lower item id (the reference's torch.topk order is arbitrary).
+* the hit matrix is built with vectorised numpy (sorted ground truth + searchsorted) instead of a
+  Python membership loop; the metric formulas are the reference's, in float64.
+* with `sync_free` (default) the loss is accumulated on the device and the NaN abort
+  (trainer.py:201-203) is evaluated once per epoch instead of forcing a host sync per batch.
+"""
+from __future__ import annotations
+
+import itertools
+from logging import getLogger
+from time import time
+
+import numpy as np
+import torch
+import torch.optim as optim
+from torch.nn.utils.clip_grad import clip_grad_norm_
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------- metrics
+def recall_(hits, pos_len):
+    return (np.cumsum(hits, axis=1) / pos_len.reshape(-1, 1)).mean(axis=0)
+
+
+def recall2_(hits, pos_len):
+    return np.cumsum(hits, axis=1).sum(axis=0) / pos_len.sum()
+
+
+def precision_(hits, pos_len):
+    return (hits.cumsum(axis=1) / np.arange(1, hits.shape[1] + 1)).mean(axis=0)
+
+
+def ndcg_(hits, pos_len):
+    """metrics.py:35-64: per-user IDCG truncated at min(pos_len, K)."""
+    k = hits.shape[1]
+    disc = 1.0 / np.log2(np.arange(1, k + 1, dtype=np.float64) + 1)
+    idcg_all = np.cumsum(disc)
+    idcg_len = np.minimum(pos_len, k)
+    idcg = idcg_all[np.minimum(np.arange(k)[None, :], idcg_len[:, None] - 1)]
+    dcg = np.cumsum(np.where(hits, disc[None, :], 0.0), axis=1)
+    return (dcg / idcg).mean(axis=0)
+
+
+def map_(hits, pos_len):
+    """metrics.py:67-92."""
+    k = hits.shape[1]
+    pre = hits.cumsum(axis=1) / np.arange(1, k + 1)
+    sum_pre = np.cumsum(pre * hits.astype(np.float64), axis=1)
+    ranges = np.minimum(np.arange(1, k + 1)[None, :], np.minimum(pos_len, k)[:, None])
+    return (sum_pre / ranges).mean(axis=0)
+
+
+metrics_dict = {"ndcg": ndcg_, "recall": recall_, "recall2": recall2_, "precision": precision_,
+                "map": map_}
+
+
+class TopKEvaluator:
+    """utils/topk_evaluator.py:19-149."""
+
+    def __init__(self, config):
+        self.config = config
+        self.metrics = config["metrics"]
+        self.topk = config["topk"]
+        if isinstance(self.metrics, str):
+            self.metrics = [self.metrics]
+        for m in self.metrics:
+            if m.lower() not in metrics_dict:
+                raise ValueError("There is no user grouped topk metric named {}!".format(m))
+        self.metrics = [m.lower() for m in self.metrics]
+        if isinstance(self.topk, int):
+            self.topk = [self.topk]
+        for k in self.topk:
+            if k <= 0:
+                raise ValueError("topk must be a positive integer or a list of positive integers, "
+                                 "but get `{}`".format(k))
+
+    @staticmethod
+    def hit_matrix(pos_items, topk_index):
+        """topk_evaluator.py:88-93 vectorised: hits[u, r] = topk_index[u, r] in pos_items[u]."""
+        n, k = topk_index.shape
+        lens = np.fromiter((len(p) for p in pos_items), dtype=np.int64, count=n)
+        stride = int(topk_index.max()) + 2 if topk_index.size else 1
+        flat = np.concatenate(pos_items) if n else np.zeros(0, np.int64)
+        keys = np.sort(np.repeat(np.arange(n, dtype=np.int64), lens) * stride + flat)
+        q = np.arange(n, dtype=np.int64)[:, None] * stride + topk_index
+        pos = np.searchsorted(keys, q.ravel())
+        pos = np.minimum(pos, len(keys) - 1)
+        return (keys[pos] == q.ravel()).reshape(n, k)
+
+    def evaluate(self, batch_matrix_list, eval_data, is_test=False, idx=0):
+        pos_items = eval_data.get_eval_items()
+        pos_len_list = eval_data.get_eval_len_list()
+        topk_index = torch.cat(batch_matrix_list, dim=0).cpu().numpy()
+        assert len(pos_len_list) == len(topk_index)
+        hits = self.hit_matrix(pos_items, topk_index)
+        result = self._calculate_metrics(pos_len_list, hits)
+        out = {}
+        for metric, value in zip(self.metrics, result):
+            for k in self.topk:
+                out["{}@{}".format(metric, k)] = round(value[k - 1], 4)
+        return out
+
+    def _calculate_metrics(self, pos_len_list, hits):
+        return np.stack([metrics_dict[m](hits, np.asarray(pos_len_list)) for m in self.metrics],
+                        axis=0)
+
+
+def early_stopping(value, best, cur_step, max_step, bigger=True):
+    """utils/utils.py:57-98."""
+    stop_flag = update_flag = False
+    better = value > best if bigger else value < best
+    if better:
+        cur_step, best, update_flag = 0, value, True
+    else:
+        cur_step += 1
+        if cur_step > max_step:
+            stop_flag = True
+    return best, cur_step, stop_flag, update_flag
+
+
+def dict2str(d):
+    return "".join(str(k) + ": " + "%.04f" % v + "    " for k, v in d.items())
+
+
+# ------------------------------------------------------------------------------------- trainer
+class Trainer:
+    def __init__(self, config, model, mg=False):
+        self.config, self.model = config, model
+        self.logger = getLogger()
+        self.learner = config["learner"]
+        self.learning_rate = config["learning_rate"]
+        self.epochs = config["epochs"]
+        self.eval_step = min(config["eval_step"], self.epochs)
+        self.stopping_step = config["stopping_step"]
+        self.clip_grad_norm = config["clip_grad_norm"]
+        self.valid_metric = config["valid_metric"].lower()
+        self.valid_metric_bigger = config["valid_metric_bigger"]
+        self.test_batch_size = config["eval_batch_size"]
+        self.device = config["device"]
+        wd = config["weight_decay"]
+        self.weight_decay = 0.0 if wd is None else (eval(wd) if isinstance(wd, str) else wd)
+        self.req_training = config["req_training"]
+        self.start_epoch = self.cur_step = 0
+        tmp = {f"{j.lower()}@{k}": 0.0 for j, k in itertools.product(config["metrics"], config["topk"])}
+        self.best_valid_score = -1
+        self.best_valid_result, self.best_test_upon_valid = tmp, tmp
+        self.train_loss_dict = {}
+        self.optimizer = self._build_optimizer()
+        sch = config["learning_rate_scheduler"]
+        self.lr_scheduler = optim.lr_scheduler.LambdaLR(self.optimizer,
+                                                        lr_lambda=lambda e: sch[0] ** (e / sch[1]))
+        self.evaluator = TopKEvaluator(config)
+        self.mg = mg
+        self.alpha1, self.alpha2, self.beta = config["alpha1"], config["alpha2"], config["beta"]
+        self.mg_target_rel_step = float(config.get("mg_target_rel_step", 1e-3))
+        self.mg_alpha_max_scale = float(config.get("mg_alpha_max_scale", 20.0))
+        self.sync_free = bool(config.get("sync_free", True))
+
+    def _build_optimizer(self):
+        """trainer.py:126-143."""
+        name = self.learner.lower()
+        kw = dict(lr=self.learning_rate, weight_decay=self.weight_decay)
+        cls = {"adam": optim.Adam, "sgd": optim.SGD, "adagrad": optim.Adagrad,
+               "rmsprop": optim.RMSprop}.get(name)
+        if cls is None:
+            self.logger.warning("Received unrecognized optimizer, set default Adam optimizer")
+            return optim.Adam(self.model.parameters(), lr=self.learning_rate)
+        return cls(self.model.parameters(), **kw)
+
+    # ---- one step of the mirror-gradient schedule (trainer.py:268-335) ----------------------
+    def _mirror_gradient_step(self, loss_func, mirror_input):
+        opt, model = self.optimizer, self.model
+        lr = opt.param_groups[0].get("lr", 1.0)
+        opt.zero_grad(set_to_none=True)
+        loss_curr = loss_func(mirror_input)
+        (sum(loss_curr) if isinstance(loss_curr, tuple) else loss_curr).backward()
+        params, grads = [], []
+        for p in model.parameters():
+            if p.requires_grad and p.grad is not None:
+                params.append(p)
+                grads.append(p.grad.detach().clone())
+        alpha_base = float(getattr(model, "mg_alpha", 0.5))
+        with torch.no_grad():
+            if not grads:
+                alpha_eff = alpha_base
+            else:
+                # grad_rms / param_rms as device scalars; one host read for alpha_eff
+                g2 = torch.stack([g.pow(2).sum() for g in grads]).sum()
+                p2 = torch.stack([p.detach().pow(2).sum() for p in params]).sum()
+                numel = float(sum(g.numel() for g in grads))
+                rms = torch.stack([g2, p2]).sqrt().div(numel ** 0.5).tolist()
+                grad_rms, param_rms = rms[0], rms[1] + 1e-12
+                target_step = self.mg_target_rel_step * param_rms
+                alpha_eff = max(alpha_base, target_step / (lr * grad_rms + 1e-12))
+                alpha_eff = min(alpha_eff, alpha_base * self.mg_alpha_max_scale)
+            model._alpha_eff = float(alpha_eff)
+            torch._foreach_add_(params, grads, alpha=-alpha_eff * lr)
+        opt.zero_grad(set_to_none=True)
+        loss_mirror = loss_func(mirror_input)
+        (sum(loss_mirror) if isinstance(loss_mirror, tuple) else loss_mirror).backward()
+        with torch.no_grad():
+            mg = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
+            torch._foreach_mul_(mg, -float(getattr(model, "mg_beta", 0.2)))
+            torch._foreach_add_(params, grads, alpha=alpha_eff * lr)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    def _train_epoch(self, train_data, epoch_idx, loss_func=None):
+        """trainer.py:145-356."""
+        if not self.req_training:
+            return 0.0, []
+        self.model.train()
+        loss_func = loss_func or self.model.calculate_loss
+        total_loss = None
+        loss_batches = []
+        for batch_idx, interaction in enumerate(train_data):
+            self.optimizer.zero_grad(set_to_none=True)
+            second_inter = interaction.clone()
+            losses = loss_func(interaction)
+            loss = sum(losses) if isinstance(losses, tuple) else losses
+            if self.sync_free:
+                total_loss = loss.detach().clone() if total_loss is None else total_loss + loss.detach()
+            else:
+                total_loss = loss.item() if total_loss is None else total_loss + loss.item()
+                if torch.isnan(loss):
+                    self.logger.info("Loss is nan at epoch: {}, batch index: {}. Exiting.".format(
+                        epoch_idx, batch_idx))
+                    return loss, torch.tensor(0.0)
+            model_has_mirror = bool(getattr(self.model, "mg_enable", False))
+            if not model_has_mirror:
+                if self.mg and batch_idx % self.beta == 0:
+                    (self.alpha1 * loss).backward()
+                    self.optimizer.step()
+                    self.optimizer.zero_grad()
+                    losses = loss_func(second_inter)
+                    loss = sum(losses) if isinstance(losses, tuple) else losses
+                    (-1 * self.alpha2 * loss).backward()
+                else:
+                    loss.backward()
+                if self.clip_grad_norm:
+                    clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
+                self.optimizer.step()
+                loss_batches.append(loss.detach())
+                continue
+            loss.backward()
+            if self.clip_grad_norm:
+                clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
+            self.optimizer.step()
+            loss_batches.append(loss.detach())
+            mg_interval = int(getattr(self.model, "mg_interval", 0))
+            if mg_interval > 0 and int(getattr(self.model, "global_step", 0)) % mg_interval == 0:
+                self._mirror_gradient_step(loss_func, second_inter)
+        if self.sync_free and total_loss is not None:
+            if torch.isnan(total_loss):
+                self.logger.info("Loss is nan at epoch: {}. Exiting.".format(epoch_idx))
+                return total_loss, torch.tensor(0.0)
+            total_loss = total_loss.item()
+        return total_loss, loss_batches
+
+    def _valid_epoch(self, valid_data):
+        valid_result = self.evaluate(valid_data)
+        valid_score = valid_result[self.valid_metric] if self.valid_metric else valid_result["NDCG@20"]
+        return valid_score, valid_result
+
+    def fit(self, train_data, valid_data=None, test_data=None, saved=False, verbose=True):
+        """trainer.py:385-506."""
+        for epoch_idx in range(self.start_epoch, self.epochs):
+            t0 = time()
+            self.model.cur_epoch = epoch_idx
+            self.model.pre_epoch_processing()
+            train_loss, _ = self._train_epoch(train_data, epoch_idx)
+            if torch.is_tensor(train_loss):
+                break
+            self.lr_scheduler.step()
+            self.train_loss_dict[epoch_idx] = sum(train_loss) if isinstance(train_loss, tuple) else train_loss
+            t1 = time()
+            post_info = self.model.post_epoch_processing()
+            if verbose:
+                self.logger.info("epoch %d training [time: %.2fs, train loss: %.4f]" % (epoch_idx, t1 - t0, train_loss))
+                if post_info is not None:
+                    self.logger.info(post_info)
+            if (epoch_idx + 1) % self.eval_step == 0:
+                v0 = time()
+                valid_score, valid_result = self._valid_epoch(valid_data)
+                self.best_valid_score, self.cur_step, stop_flag, update_flag = early_stopping(
+                    valid_score, self.best_valid_score, self.cur_step, max_step=self.stopping_step,
+                    bigger=self.valid_metric_bigger)
+                v1 = time()
+                _, test_result = self._valid_epoch(test_data)
+                if verbose:
+                    self.logger.info("epoch %d evaluating [time: %.2fs, valid_score: %f]" % (epoch_idx, v1 - v0, valid_score))
+                    self.logger.info("valid result: \n" + dict2str(valid_result))
+                    self.logger.info("test result: \n" + dict2str(test_result))
+                if update_flag:
+                    if verbose:
+                        self.logger.info("██ " + str(self.config["model"]) + "--Best validation results updated!!!")
+                    self.best_valid_result = valid_result
+                    self.best_test_upon_valid = test_result
+                if stop_flag:
+                    if verbose:
+                        self.logger.info("+++++Finished training, best eval result in epoch %d" %
+                                         (epoch_idx - self.cur_step * self.eval_step))
+                    break
+        return self.best_valid_score, self.best_valid_result, self.best_test_upon_valid
+
+    @torch.no_grad()
+    def evaluate_topk(self, eval_data):
+        """Fused evaluation: list of int64 [Bu, max(topk)] (trainer.py:509-527)."""
+        self.model.eval()
+        k = max(self.config["topk"])
+        users = eval_data.eval_u
+        n, step = users.shape[0], eval_data.step
+        out = []
+        for start in range(0, n, step):
+            stop = min(n, start + step)
+            rowptr, cols = eval_data.mask_csr(start, stop)
+            out.append(self.model.full_sort_topk(users[start:stop], k, rowptr, cols))
+        return out
+
+    @torch.no_grad()
+    def evaluate(self, eval_data, is_test=False, idx=0):
+        return self.evaluator.evaluate(self.evaluate_topk(eval_data), eval_data, is_test=is_test, idx=idx)

@@ -1,0 +1,296 @@
+"""GPU parity tests: every call goes through the C ABI (libmmrec_b200.so) and is compared with
+the CPU oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, pkg
+from oracle import graph as ograph
+from oracle import ops as oops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+def random_graph(n_rows, n_cols, nnz, seed, heavy_row=None):
+    g = torch.Generator().manual_seed(seed)
+    rows = torch.randint(0, n_rows, (nnz,), generator=g)
+    cols = torch.randint(0, n_cols, (nnz,), generator=g)
+    if heavy_row is not None:
+        rows[: nnz // 3] = heavy_row
+    vals = torch.rand(nnz, generator=g) + 0.1
+    return rows, cols, vals
+
+
+@pytest.mark.parametrize("d", [32, 64, 128, 256])
+def test_spmm_and_transpose_backward(d):
+    G, ops = pkg("graph"), pkg("ops")
+    rows, cols, vals = random_graph(700, 500, 9000, 1, heavy_row=3)      # row 3 takes the CTA path
+    g = G.csr_from_coo(rows.to(DEV), cols.to(DEV), vals.to(DEV), 700, 500)
+    assert g.n_long >= 1
+    A = ograph.to_torch_csr(rows.numpy(), cols.numpy(), vals.numpy(), (700, 500), torch.float64)
+    X = torch.randn(500, d, generator=torch.Generator().manual_seed(2))
+    Xg = X.to(DEV).requires_grad_(True)
+    Y = ops.spmm(g, Xg)
+    Xo = X.double().requires_grad_(True)
+    Yo = torch.sparse.mm(A, Xo)
+    assert rel(Y, Yo) < 1e-5
+    W = torch.randn(700, d, generator=torch.Generator().manual_seed(3))
+    (Y * W.to(DEV)).sum().backward()
+    (Yo * W.double()).sum().backward()
+    assert rel(Xg.grad, Xo.grad) < 1e-5
+
+
+def test_spmm_empty_rows_and_duplicates():
+    G, ops = pkg("graph"), pkg("ops")
+    rows = torch.tensor([0, 0, 0, 5, 5, 9]); cols = torch.tensor([1, 1, 2, 0, 0, 3]); vals = torch.ones(6)
+    g = G.csr_from_coo(rows.to(DEV), cols.to(DEV), vals.to(DEV), 10, 4)
+    X = torch.arange(4 * 64, dtype=torch.float32).view(4, 64)
+    Y = ops.spmm(g, X.to(DEV)).cpu()
+    want = torch.zeros(10, 64)
+    want.index_add_(0, rows, X[cols])
+    assert torch.equal(Y, want)                      # duplicates summed, empty rows exactly 0
+
+
+@pytest.mark.parametrize("layers", [0, 1, 2, 4])
+def test_propagate_mean_forward_backward(layers, tiny_data, tiny_train):
+    G, ops = pkg("graph"), pkg("ops")
+    u, i = tiny_train
+    U, I = tiny_data.n_users, tiny_data.n_items
+    g = G.build_ui_graph(torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), U, I, "f32")
+    r, c, v = ograph.norm_adj_f32(u, i, U, I)
+    gr, gc, gv = g.to_torch_coo()
+    assert np.array_equal(gr, r) and np.array_equal(gc, c)
+    assert np.array_equal(gv.view(np.uint32), v.view(np.uint32))         # bit-exact adjacency
+    A = ograph.to_torch_csr(r, c, v, (U + I, U + I), torch.float64)
+    X = torch.randn(U + I, 64, generator=torch.Generator().manual_seed(5))
+    Xg = X.to(DEV).requires_grad_(True)
+    out = ops.propagate_mean(g, Xg, layers)
+    Xo = X.double().requires_grad_(True)
+    oout = oops.propagate_mean(A, Xo, layers)
+    assert rel(out, oout) < 1e-5
+    W = torch.randn(U + I, 64, generator=torch.Generator().manual_seed(6))
+    (out * W.to(DEV)).sum().backward()
+    (oout * W.double()).sum().backward()
+    assert rel(Xg.grad, Xo.grad) < 1e-5
+
+
+def test_adjacency_f64eps_recipe_bit_exact(tiny_data, tiny_train):
+    G = pkg("graph")
+    u, i = tiny_train
+    U, I = tiny_data.n_users, tiny_data.n_items
+    g = G.build_ui_graph(torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), U, I, "f64eps")
+    ref = golden("tiny_layergcn")
+    gr, gc, gv = g.to_torch_coo()
+    assert np.array_equal(np.vstack([gr, gc]), ref["adj/norm_adj_matrix/idx"])
+    assert np.array_equal(gv.view(np.uint32), ref["adj/norm_adj_matrix/val"].view(np.uint32))
+    # R / R^T views
+    R, Rt = G.ui_blocks(G.build_ui_graph(torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), U, I, "f32"))
+    sm = golden("tiny_smore")
+    rr, rc, rv = R.to_torch_coo()
+    assert np.array_equal(np.vstack([rr, rc]), sm["adj/R/idx"])
+    assert np.array_equal(rv.view(np.uint32), sm["adj/R/val"].view(np.uint32))
+    tr, tc, tv = Rt.to_torch_coo()
+    o = np.lexsort((rr, rc))
+    assert np.array_equal(tr, rc[o]) and np.array_equal(tc, rr[o]) and np.array_equal(tv, rv[o])
+
+
+def test_layergcn_propagate_forward_backward(tiny_data, tiny_train):
+    G, ops = pkg("graph"), pkg("ops")
+    u, i = tiny_train
+    U, I = tiny_data.n_users, tiny_data.n_items
+    g = G.build_ui_graph(torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), U, I, "f64eps")
+    r, c, v = ograph.norm_adj_f64eps(u, i, U, I)
+    A = ograph.to_torch_csr(r, c, v, (U + I, U + I), torch.float64)
+    X = torch.randn(U + I, 64, generator=torch.Generator().manual_seed(7)) * 0.1
+    Xg = X.to(DEV).requires_grad_(True)
+    out = ops.layergcn_propagate(g, Xg, 4)
+    Xo = X.double().requires_grad_(True)
+    oout = oops.layergcn_propagate(A, Xo, 4)
+    assert rel(out, oout) < 1e-5
+    W = torch.randn(U + I, 64, generator=torch.Generator().manual_seed(8))
+    (out * W.to(DEV)).sum().backward()
+    (oout * W.double()).sum().backward()
+    assert rel(Xg.grad, Xo.grad) < 2e-5
+
+
+def test_micro_layergcn_known_answer():
+    """SURVEY appendix A vectors produced by the reference's own functions (d padded to 32)."""
+    G, ops = pkg("graph"), pkg("ops")
+    m = golden("micro")
+    u = torch.tensor([0, 0, 1, 2]); i = torch.tensor([0, 1, 1, 0])
+    g = G.build_ui_graph(u.to(DEV), i.to(DEV), 3, 2, "f64eps")
+    _, _, v = g.to_torch_coo()
+    assert np.array_equal(v.view(np.uint32), m["layergcn_adj_val"].view(np.uint32))
+    x0 = torch.zeros(5, 32)
+    x0[:, :2] = torch.tensor([[1., 0], [0, 1], [1, 1], [1, 2], [2, 1]])
+    out = ops.layergcn_propagate(g, x0.to(DEV), 2).cpu()
+    np.testing.assert_allclose(out[:3, :2].numpy(), m["layergcn_fwd_user"], rtol=1e-5)
+    np.testing.assert_allclose(out[3:, :2].numpy(), m["layergcn_fwd_item"], rtol=1e-5)
+    mean = ops.propagate_mean(g, x0.to(DEV), 2).cpu()
+    np.testing.assert_allclose(mean[:, :2].numpy(), m["lightgcn_mean"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,d", [(1, 64), (777, 64), (2048, 128)])
+def test_bpr_forward_backward(B, d):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(11)
+    ue = torch.randn(300, d, generator=gen) * 0.3
+    ie = torch.randn(200, d, generator=gen) * 0.3
+    users = torch.randint(0, 300, (B,), generator=gen)
+    pos = torch.randint(0, 200, (B,), generator=gen)
+    neg = torch.randint(0, 200, (B,), generator=gen)
+    a, b = ue.to(DEV).requires_grad_(True), ie.to(DEV).requires_grad_(True)
+    out = ops.bpr(a, b, users.to(DEV), pos.to(DEV), neg.to(DEV))
+    (0.7 * out[0] + 0.3 * out[1]).backward()
+    ao, bo = ue.double().requires_grad_(True), ie.double().requires_grad_(True)
+    l = oops.bpr_sum(ao[users], bo[pos], bo[neg])
+    r = oops.l2_half(ao[users], bo[pos], bo[neg])
+    (0.7 * l + 0.3 * r).backward()
+    assert abs(out[0].item() - l.item()) / abs(l.item()) < 1e-5
+    assert abs(out[1].item() - r.item()) / abs(r.item()) < 1e-5
+    assert rel(a.grad, ao.grad) < 1e-5 and rel(b.grad, bo.grad) < 1e-5
+    # stacked-table variant
+    t = torch.cat([ue, ie]).to(DEV).requires_grad_(True)
+    out2 = ops.bpr_table(t, 300, users.to(DEV), pos.to(DEV), neg.to(DEV))
+    (0.7 * out2[0] + 0.3 * out2[1]).backward()
+    assert torch.equal(out2, out)
+    assert rel(t.grad, torch.cat([ao.grad, bo.grad])) < 1e-5
+
+
+@pytest.mark.parametrize("B,d", [(5, 64), (300, 64), (2048, 64), (513, 128)])
+def test_infonce_pair_forward_backward(B, d):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(13)
+    nu, ni = 150, 120
+    side = torch.randn(nu + ni, d, generator=gen)
+    content = torch.randn(nu + ni, d, generator=gen)
+    users = torch.randint(0, nu, (B,), generator=gen)
+    pos = torch.randint(0, ni, (B,), generator=gen)
+    s, c = side.to(DEV).requires_grad_(True), content.to(DEV).requires_grad_(True)
+    loss = ops.infonce_pair(s, c, nu, users.to(DEV), pos.to(DEV), 0.2)
+    loss.backward()
+    so, co = side.double().requires_grad_(True), content.double().requires_grad_(True)
+    lo = oops.infonce(so[nu:][pos], co[nu:][pos], 0.2) + oops.infonce(so[:nu][users], co[:nu][users], 0.2)
+    lo.backward()
+    assert abs(loss.item() - lo.item()) / abs(lo.item()) < 1e-5
+    assert rel(s.grad, so.grad) < 2e-5 and rel(c.grad, co.grad) < 2e-5
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_spectral_forward_backward(d):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(17)
+    n = 333
+    img, txt = torch.randn(n, d, generator=gen), torch.randn(n, d, generator=gen)
+    ws = [torch.randn(1, d // 2 + 1, 2, generator=gen) for _ in range(3)]
+    a, b = img.to(DEV).requires_grad_(True), txt.to(DEV).requires_grad_(True)
+    wg = [w.to(DEV).requires_grad_(True) for w in ws]
+    ic, tc, fc = ops.spectrum_convolution(a, b, wg[0][0], wg[1][0], wg[2][0], True)
+    ao, bo = img.double().requires_grad_(True), txt.double().requires_grad_(True)
+    wo = [w.double().requires_grad_(True) for w in ws]
+    oic, otc, ofc = oops.spectrum_convolution(ao, bo, *wo, True)
+    assert rel(ic, oic) < 1e-5 and rel(tc, otc) < 1e-5 and rel(fc, ofc) < 1e-5
+    gs = [torch.randn(n, d, generator=gen) for _ in range(3)]
+    (ic * gs[0].to(DEV) + tc * gs[1].to(DEV) + fc * gs[2].to(DEV)).sum().backward()
+    (oic * gs[0].double() + otc * gs[1].double() + ofc * gs[2].double()).sum().backward()
+    assert rel(a.grad, ao.grad) < 1e-5 and rel(b.grad, bo.grad) < 1e-5
+    for x, y in zip(wg, wo):
+        assert rel(x.grad, y.grad) < 2e-5
+
+
+def test_spectral_known_answer_d8_embedded():
+    """The reference's d=8 known-answer vector cannot run (d in {32,64,128}); instead check the
+    kernel against the reference's own SMORE spectrum output on the tiny dataset."""
+    ops = pkg("ops")
+    g = golden("tiny_smore")
+    w = [torch.from_numpy(g["param0/" + k]).to(DEV)[0] for k in
+         ("image_complex_weight", "text_complex_weight", "fusion_complex_weight")]
+    ic, tc, fc = ops.spectrum_convolution(torch.from_numpy(g["spec/image_feats"]).to(DEV),
+                                          torch.from_numpy(g["spec/text_feats"]).to(DEV), *w, True)
+    for ours, key in ((ic, "image_conv"), (tc, "text_conv"), (fc, "fusion_conv")):
+        assert rel(ours, torch.from_numpy(g["spec/" + key])) < 1e-5
+
+
+@pytest.mark.parametrize("n_users,n_items,d,k,splits", [(64, 96, 64, 50, 1), (300, 1000, 64, 50, 4),
+                                                       (129, 777, 128, 20, 3), (1000, 5000, 32, 50, None)])
+def test_score_mask_topk_matches_stable_sort(n_users, n_items, d, k, splits):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(19)
+    ue = torch.randn(400, d, generator=gen)
+    ie = torch.randn(n_items, d, generator=gen)
+    ie[5] = ie[3]                                    # exact ties: lower id must win
+    ie[n_items - 1] = ie[3]
+    users = torch.randint(0, 400, (n_users,), generator=gen)
+    lens = torch.randint(0, 40, (n_users,), generator=gen)
+    lens[0] = 0
+    lens[1] = min(n_items, 90)                       # more masked items than n_items - k when small
+    cols = [torch.randperm(n_items, generator=gen)[:l].sort()[0] for l in lens.tolist()]
+    rowptr = torch.tensor([0] + np.cumsum(lens.numpy()).tolist(), dtype=torch.int32)
+    flat = torch.cat(cols).to(torch.int32)
+    ids, vals = ops.score_mask_topk(ue.to(DEV), users.to(DEV), ie.to(DEV), k, rowptr.to(DEV), flat.to(DEV),
+                                    n_splits=splits, return_scores=True)
+    scores = (ue.to(DEV)[users.to(DEV)] @ ie.to(DEV).T).cpu()          # fp32 reference scores
+    mrows = torch.repeat_interleave(torch.arange(n_users), lens)
+    want = oops.mask_topk(scores, mrows, flat.long(), k)
+    s = scores.clone()
+    s[mrows, flat.long()] = -1e10
+    got = ids.cpu()
+    # identical ids except where two fp32 summation orders flip a near-tie
+    same = (got == want)
+    if not bool(same.all()):
+        gs, ws = s.gather(1, got), s.gather(1, want)
+        assert float((gs - ws).abs().max()) < 1e-4
+        assert same.float().mean() > 0.999
+    assert rel(vals, s.gather(1, got)) < 1e-5
+    # the duplicated item rows tie exactly: ids must be ascending inside equal scores
+    v = vals.cpu()
+    eq = v[:, 1:] == v[:, :-1]
+    assert bool((got[:, 1:][eq] > got[:, :-1][eq]).all())
+
+
+def test_topk_merge_matches_single_pass():
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(23)
+    ue, ie = torch.randn(50, 64, generator=gen).to(DEV), torch.randn(2000, 64, generator=gen).to(DEV)
+    users = torch.arange(50).to(DEV)
+    one = ops.score_mask_topk(ue, users, ie, 50, n_splits=1)
+    # item-sharded: 3 "ranks" each score a slice with a global id offset, then merge
+    parts_v, parts_i = [], []
+    for lo, hi in ((0, 700), (700, 1400), (1400, 2000)):
+        v, i = ops.score_mask_topk(ue, users, ie[lo:hi].contiguous(), 50, item_offset=lo, n_splits=2, merge=False)
+        mi, mv = ops.topk_merge(v, i)
+        parts_v.append(mv)
+        parts_i.append(mi.to(torch.int32))
+    merged, _ = ops.topk_merge(torch.stack(parts_v), torch.stack(parts_i))
+    assert torch.equal(merged, one)
+
+
+@pytest.mark.parametrize("model", ["LightGCN", "LayerGCN", "FREEDOM", "MGCN", "SMORE"])
+def test_model_parity_with_reference(model):
+    from parity_util import run_model_parity
+    rep = run_model_parity(model, DEV)
+    assert rep["init_bit_exact"], rep
+    assert rep["ok"], rep
+
+
+def test_missing_transpose_is_an_error():
+    G, ops = pkg("graph"), pkg("ops")
+    rows, cols, vals = random_graph(50, 40, 300, 4)
+    g = G.csr_from_coo(rows.to(DEV), cols.to(DEV), vals.to(DEV), 50, 40, with_transpose=False)
+    X = torch.randn(40, 64, device=DEV, requires_grad=True)
+    with pytest.raises(RuntimeError):
+        ops.spmm(g, X).sum().backward()
+    with pytest.raises(RuntimeError):
+        ops.spmm(g, torch.randn(40, 48, device=DEV))          # unsupported width
+
+
+def test_cpu_tensors_are_rejected():
+    G = pkg("graph")
+    with pytest.raises(RuntimeError):
+        G.build_ui_graph(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 2, 2, "f32")

@@ -1,0 +1,142 @@
+"""CPU tests: loaders / sampler / evaluator vs the reference's golden vectors, C-ABI exports."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, TINY, golden, pkg
+
+
+def _env(model="LightGCN", overrides=None):
+    synth, cfgm, data_m = pkg("synth"), pkg("config"), pkg("data")
+    data = synth.make_dataset("tiny", **TINY)
+    cd = {"device": torch.device("cpu"), "train_batch_size": 512, "eval_batch_size": 64,
+          "data_path": None}
+    cd.update(overrides or {})
+    config = cfgm.Config(model, "tiny", cd)
+    ds = data_m.RecDataset(config, data.users, data.items, data.labels)
+    tr, va, te = ds.split()
+    train = data_m.TrainDataLoader(config, tr, batch_size=512, shuffle=True)
+    valid = data_m.EvalDataLoader(config, va, additional_dataset=tr, batch_size=64)
+    test = data_m.EvalDataLoader(config, te, additional_dataset=tr, batch_size=64)
+    return config, data, train, valid, test
+
+
+def test_train_loader_replays_reference_batches():
+    """Same shuffle (numpy global RNG) and same negatives (Python random) as the reference."""
+    g = golden("tiny_lightgcn")
+    config, data, train, valid, test = _env()
+    pkg("config").init_seed(999)
+    train.pretrain_setup()
+    assert train.all_items == g["all_items_shuffled"].tolist()
+    it = iter(train)
+    b0, b1 = next(it), next(it)
+    assert b0.dtype == torch.int64 and tuple(b0.shape) == (3, 512)
+    assert np.array_equal(b0.numpy(), g["batch0"])
+    assert np.array_equal(b1.numpy(), g["batch1"])
+    n = 2 + sum(1 for _ in it)
+    assert n == len(train) == int(np.ceil(len(train.dataset) / 512))
+
+
+def test_negatives_never_in_history():
+    config, data, train, valid, test = _env()
+    pkg("config").init_seed(3)
+    train.pretrain_setup()
+    for b in train:
+        u, neg = b[0].tolist(), b[2].tolist()
+        assert all(n not in train.history_items_per_u[x] for x, n in zip(u, neg))
+
+
+def test_eval_loader_matches_reference():
+    g = golden("tiny_lightgcn")
+    config, data, train, valid, test = _env()
+    b = next(iter(valid))
+    valid.pr = valid.inter_pr = 0
+    assert np.array_equal(b[0].numpy(), g["eval_batch_users"])
+    assert np.array_equal(b[1].numpy(), g["eval_batch_mask"])
+    # the CSR view of the same mask: ascending item ids per user
+    rp, cols = valid.mask_csr(0, 64)
+    rp, cols = rp.numpy(), cols.numpy()
+    m = g["eval_batch_mask"]
+    for r in range(64):
+        assert sorted(m[1][m[0] == r].tolist()) == cols[rp[r]:rp[r + 1]].tolist()
+    # iteration covers every eval user exactly once, ragged last batch included
+    seen = torch.cat([bb[0] for bb in valid])
+    assert torch.equal(seen, valid.eval_u) and len(valid) == int(np.ceil(len(seen) / 64))
+
+
+@pytest.mark.parametrize("tag", ["tiny_lightgcn", "tiny_smore", "tiny_freedom"])
+def test_evaluator_metrics_match_reference(tag):
+    g = golden(tag)
+    config, data, train, valid, test = _env()
+    ev = pkg("trainer").TopKEvaluator(config)
+    topk = g["fit/valid_topk"]
+    hits = ev.hit_matrix(valid.get_eval_items(), topk)
+    slow = np.asarray([[i in set(m.tolist()) for i in n] for m, n in zip(valid.get_eval_items(), topk)])
+    assert np.array_equal(hits, slow)
+    raw = ev._calculate_metrics(valid.get_eval_len_list(), hits)
+    assert list(g["fit/metric_names"]) == ev.metrics
+    np.testing.assert_allclose(raw, g["fit/valid_metrics_raw"], rtol=1e-12, atol=0)
+    out = ev.evaluate([torch.from_numpy(topk)], valid)
+    keys = [str(k) for k in g["fit/metric_keys"]]
+    assert [out[k] for k in keys] == pytest.approx(g["fit/valid"][-1].tolist(), abs=1e-12)
+
+
+def test_evaluator_rejects_bad_args():
+    config, *_ = _env()
+    config["metrics"] = ["Recall", "Nope"]
+    with pytest.raises(ValueError):
+        pkg("trainer").TopKEvaluator(config)
+    config["metrics"], config["topk"] = ["Recall"], [0]
+    with pytest.raises(ValueError):
+        pkg("trainer").TopKEvaluator(config)
+
+
+def test_tsv_round_trip(tmp_path):
+    synth, cfgm, data_m = pkg("synth"), pkg("config"), pkg("data")
+    data = synth.make_dataset("tiny", **TINY)
+    d = synth.write_reference_layout(data, str(tmp_path))
+    config = cfgm.Config("LightGCN", "tiny", {"device": torch.device("cpu")})
+    ds = data_m.RecDataset(config, path=os.path.join(d, "tiny.inter"))
+    assert ds.user_num == data.n_users and ds.item_num == data.n_items
+    assert np.array_equal(ds.users, data.users) and np.array_equal(ds.labels, data.labels)
+
+
+def test_synth_shapes():
+    synth = pkg("synth")
+    for name in ("tiny", "small"):
+        d = synth.make_dataset(name, features=False)
+        U, I, E = synth.SHAPES[name]
+        assert len(d.users) == E and d.users.max() == U - 1 and d.items.max() == I - 1
+        assert len(np.unique(d.users * I + d.items)) == E
+        first = np.concatenate(([0], np.flatnonzero(np.diff(d.users)) + 1))
+        assert (d.labels[first] == 0).all()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The library loads without a GPU and exports exactly what include/mmrec_b200.h declares."""
+    lib = pkg("lib")
+    hdr = open(os.path.join(REPO, "include", "mmrec_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mmrec_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    L = lib.load()
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.mmrec_abi_version() == 1
+
+
+def test_product_does_not_import_oracle():
+    root = os.path.join(REPO, "recommendar-systems_b200")
+    for fn in os.listdir(root):
+        if fn.endswith(".py"):
+            src = open(os.path.join(root, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_ops_fail_loudly_without_cuda():
+    ops, graph = pkg("ops"), pkg("graph")
+    with pytest.raises(RuntimeError):
+        graph.build_ui_graph(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 2, 2, "f32")
