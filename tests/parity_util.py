@@ -67,8 +67,8 @@ def oracle_cfg(config):
     return {k: config[k] for k in keys if config[k] is not None}
 
 
-def run_model_parity(model_name, device="cuda:0", tol=1e-5):
-    env = make_env(model_name, device)
+def run_model_parity(model_name, device="cuda:0", tol=1e-5, tag=None, overrides=None):
+    env = make_env(model_name, device, tag=tag, overrides=overrides)
     model, g, config, data = env["model"], env["golden"], env["config"], env["data"]
     rep = {}
     # 1. same seed -> same initial parameters as the reference (RNG consumption order)
@@ -96,7 +96,7 @@ def run_model_parity(model_name, device="cuda:0", tol=1e-5):
     rep["fwd_vs_reference"] = max(rel_err(ue.cpu(), g["eval_user_emb"]), rel_err(ie.cpu(), g["eval_item_emb"]))
     # 4. loss + gradients on the reference's first batch
     model.train()
-    if model_name in ("LayerGCN", "FREEDOM"):
+    if model_name in ("LayerGCN", "FREEDOM") and config["dropout"] > 0:
         midx, mval = g["adj/masked_adj/idx"], g["adj/masked_adj/val"]
         n = data.n_users + data.n_items
         from oracle import graph as ograph
@@ -114,6 +114,8 @@ def run_model_parity(model_name, device="cuda:0", tol=1e-5):
             np.array_equal(v.view(np.uint32), mval[o].view(np.uint32)))
     else:
         model.pre_epoch_processing()
+        if "masked_adj" not in G and "norm_adj" in G:
+            G["masked_adj"] = G["norm_adj"]
     batch = torch.from_numpy(g["batch0"]).to(device)
     model.zero_grad()
     loss = model.calculate_loss(batch)

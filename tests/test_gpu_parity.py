@@ -279,6 +279,48 @@ def test_model_parity_with_reference(model):
     assert rep["ok"], rep
 
 
+def test_layergcn_edge_dropout_parity():
+    """a4/K12: the reference's kept edges -> bit-exact re-normalised adjacency, and the training
+    loss / gradients on it."""
+    from parity_util import run_model_parity
+    rep = run_model_parity("LayerGCN", DEV, tag="tiny_layergcn_drop",
+                           overrides={"dropout": 0.1, "reg_weight": 1e-3})
+    assert rep["masked_adj_bit_exact"] and rep["ok"], rep
+
+
+@pytest.mark.parametrize("model,tag,over", [
+    ("LayerGCN", "tiny_layergcn", {}), ("MGCN", "tiny_mgcn", {}), ("SMORE", "tiny_smore", {}),
+    ("SMORE", "tiny_smore_nomg", {"mg_enable": False})])
+def test_trainer_two_epochs_match_reference(model, tag, over):
+    """Our Trainer (fused eval, sync-free loss accumulation, mirror-gradient schedule) reproduces
+    the reference Trainer's two-epoch trajectory: epoch losses, global_step, final metrics."""
+    from parity_util import make_env, golden_params
+    env = make_env(model, DEV, tag=tag, overrides=over)
+    g, m, train, valid, test = env["golden"], env["model"], env["train"], env["valid"], env["test"]
+    m.load_state_dict({k: v.to(DEV) for k, v in golden_params(g).items()})
+    it = iter(train)
+    next(it), next(it)
+    train.pr = 0
+    tr = pkg("trainer").Trainer(env["config"], m)
+    losses, valids = [], []
+    for epoch in range(2):
+        m.pre_epoch_processing()
+        loss, _ = tr._train_epoch(train, epoch)
+        tr.lr_scheduler.step()
+        losses.append(loss)
+        v = tr.evaluate(valid)
+        tr.evaluate(test)
+        valids.append([v[str(k)] for k in g["fit/metric_keys"]])
+    np.testing.assert_allclose(losses, g["fit/train_loss"], rtol=1e-4)
+    if "fit/global_step" in g.files:
+        assert m.global_step == int(g["fit/global_step"])
+    np.testing.assert_allclose(np.asarray(valids), g["fit/valid"], atol=2e-3)
+    for k in g.files:
+        if k.startswith("fit/param/"):
+            ours = m.state_dict()[k[len("fit/param/"):]].cpu().numpy()
+            assert np.abs(ours - g[k]).max() / np.abs(g[k]).max() < 1e-3, k
+
+
 def test_missing_transpose_is_an_error():
     G, ops = pkg("graph"), pkg("ops")
     rows, cols, vals = random_graph(50, 40, 300, 4)

@@ -194,3 +194,59 @@ def test_scores_topk_metrics(model):
     assert np.array_equal(np.take_along_axis(s, ours, 1), np.take_along_axis(s, ref, 1))
     same = (ours == ref).mean()
     assert same > 0.99
+
+
+# --------------------------------------------------------------------------- trainer trajectory
+def replay_golden_prologue(train_loader):
+    """RNG consumption of tests/golden/make_golden.py before its two-epoch loop: seed, item
+    shuffle, one dataset shuffle and two batches of negatives."""
+    pkg("config").init_seed(999)
+    train_loader.pretrain_setup()
+    it = iter(train_loader)
+    next(it), next(it)
+    train_loader.pr = 0
+
+
+def _loaders():
+    import torch as _t
+    synth, cfgm, data_m = pkg("synth"), pkg("config"), pkg("data")
+    from conftest import TINY
+    data = synth.make_dataset("tiny", **TINY)
+    config = cfgm.Config("LightGCN", "tiny", {"device": _t.device("cpu"), "data_path": None})
+    ds = data_m.RecDataset(config, data.users, data.items, data.labels)
+    tr, va, te = ds.split()
+    return data_m.TrainDataLoader(config, tr, batch_size=512, shuffle=True), \
+        data_m.EvalDataLoader(config, va, additional_dataset=tr, batch_size=64)
+
+
+@pytest.mark.parametrize("model,tag,mg", [("LayerGCN", "tiny_layergcn", False), ("MGCN", "tiny_mgcn", False),
+                                          ("SMORE", "tiny_smore", True), ("SMORE", "tiny_smore_nomg", False)])
+def test_oracle_trainer_trajectory(model, tag, mg, tiny_data, tiny_train):
+    """Two epochs through the restated training step (incl. the mirror-gradient schedule) land on
+    the reference's losses and parameters."""
+    from oracle.train import OracleTrainer
+    g = golden(tag)
+    G, _ = _graphs(model, tiny_data, tiny_train)
+    G.setdefault("masked_adj", G["norm_adj"])
+    cfg = dict(CFG[model])
+    sched = (0.96, 50) if model in ("MGCN", "SMORE") else (1.0, 50)
+    tr = OracleTrainer(model, _params(g), G, cfg, lr=1e-3, lr_scheduler=sched, mg_enable=mg)
+    train, valid = _loaders()
+    replay_golden_prologue(train)
+    losses = [tr.train_epoch(train) for _ in range(2)]
+    np.testing.assert_allclose(losses, g["fit/train_loss"], rtol=2e-5)
+    if "fit/global_step" in g.files:
+        assert tr.global_step == int(g["fit/global_step"])
+    for k in g.files:
+        if k.startswith("fit/param/"):
+            ref = g[k]
+            ours = tr.P[k[len("fit/param/"):]].detach().numpy()
+            assert np.abs(ours - ref).max() / np.abs(ref).max() < 1e-4, k
+    # final valid metrics through the oracle's scoring / top-K / metric formulas
+    ue, ie = tr.embeddings()
+    rows = []
+    for b in valid:
+        s = ops.full_sort_scores(ue, ie, b[0])
+        rows.append(ops.mask_topk(s, b[1][0], b[1][1], 50).numpy())
+    raw = ops.calculate_metrics(valid.get_eval_items(), valid.get_eval_len_list(), np.concatenate(rows))
+    np.testing.assert_allclose(raw, g["fit/valid_metrics_raw"], atol=2e-3)
