@@ -78,20 +78,24 @@ int mmrec_csr_from_coo(const int64_t *rows, const int64_t *cols, const float *va
  * models/lightgcn.py:122, the stack+mean at freedom.py:177-178 / mgcn.py:165-166 /
  * smore.py:285-286 / lightgcn.py:124-125 and the cosine refinement at layergcn.py:134-138.
  *
- *   y[r]  = sum_k vals[k] * X[col_idx[k] - col_offset]      for k in row r (sched order)
+ *   y[r]  = sum_k vals[k] * X[col_idx[k] - col_offset]      for k in row r
  *   LayerGCN mode (cos_ref != NULL): Y_pre[r] = y (optional), w = cos(y, cos_ref[r]) with
  *       torch-2 semantics (each vector / max(norm, 1e-8)), cos_w[r] = w, y *= w
  *   Y[r]       = y                                   (optional)
  *   acc_out[r] = (acc_in[r] + y) * acc_scale  or  y * acc_scale if acc_in == NULL   (optional)
  *
- * row_sched: permutation of the rows in descending degree order; the first n_long entries are
- * processed by a whole CTA each, the rest by one sub-warp each. d must be 32, 64, 128 or 256.
- * The same entry point runs the backward (A_hat is symmetric; otherwise pass the CSR of A^T).
+ * Work list (built once per graph, see graph.py): `tasks` is int32[n_tasks][4] =
+ * {row, begin, end, slot}; one sub-warp of d/4 lanes runs one task of at most 64 non-zeros.
+ * slot < 0: the task covers a whole row. slot >= 0: the row is cut into ceil(deg/64) tasks;
+ * partial sums go to scratch[(slot_base[slot] + part) * d ...] and the last task to arrive on
+ * counters[slot] (zero-initialised, self-resetting) reduces them in part order and runs the
+ * epilogue. d must be 32, 64, 128 or 256. The same entry point runs the backward (A_hat is
+ * symmetric; otherwise pass the CSR of A^T).
  * ---------------------------------------------------------------------------------------- */
 int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
-                       const int32_t *row_sched, int32_t n_rows, int32_t n_long,
-                       int32_t col_offset, const float *X, int32_t d, float *Y,
-                       const float *acc_in, float *acc_out, float acc_scale,
+                       const int32_t *tasks, int32_t n_tasks, const int32_t *slot_base,
+                       int32_t *counters, float *scratch, int32_t col_offset, const float *X,
+                       int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
                        const float *cos_ref, float *cos_w, float *Y_pre, void *stream);
 
 /* Backward row-operator of one LayerGCN layer (layergcn.py:134-135 differentiated):
@@ -125,6 +129,9 @@ int mmrec_bpr_bwd_f32(const float *user_emb, const float *item_emb, int32_t d,
  *   loss = mean_i( -log( exp(<v1_i,v2_i>/t) / sum_j exp(<v1_i,v2_j>/t) ) )
  * The B x B score matrix never reaches HBM. fwd saves V1n,V2n [B,d], inv norms [2B], ttl [B].
  * bwd scatter-adds into dT1/dT2 (table-shaped, atomics). coef = dL/dloss (device scalar).
+ * The "other" dimension of each backward pass is cut into n_splits ranges (grid.y) so that a
+ * 2048-row batch fills 148 SMs; dV1_ws/dV2_ws hold n_splits*batch*d floats of partial sums that
+ * the scatter kernel adds in split order. partial (fwd) must hold 16*batch floats.
  * ---------------------------------------------------------------------------------------- */
 int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d, const int64_t *idx,
                           int32_t batch, float inv_temp, float *loss_out, float *V1n, float *V2n,
@@ -132,8 +139,8 @@ int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d, const int
                           void *stream);
 int mmrec_infonce_bwd_f32(const float *V1n, const float *V2n, const float *inv_norm,
                           const float *ttl, int32_t d, const int64_t *idx, int32_t batch,
-                          float inv_temp, const float *coef, float *dV1_ws, float *dV2_ws,
-                          float *dT1, float *dT2, void *stream);
+                          float inv_temp, const float *coef, int32_t n_splits, float *dV1_ws,
+                          float *dV2_ws, float *dT1, float *dT2, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Spectrum-based modality fusion (K5). Replaces SMORE.spectrum_convolution
@@ -156,6 +163,42 @@ int mmrec_spectral_bwd_f32(const float *img, const float *txt, int32_t n_rows, i
                            const float *g_txt_conv, const float *g_fus_conv, float *d_img,
                            float *d_txt, float *dh_ws, float *d_w_img, float *d_w_txt,
                            float *d_w_fus, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense projections (K4): fp32-accurate tensor-core GEMM (3xTF32 split, fp32 accumulate).
+ * Replaces nn.Linear / F.linear over whole tables and its two backward GEMMs:
+ * image_trs / text_trs (smore.py:257-259, mgcn.py:148-150, freedom.py:207-210) and the d x d
+ * gate / query layers (smore.py:265-272, 321-330; mgcn.py:153-154, 188-203).
+ *   C[M,N] = op(A) * op(B) (+ bias[N])
+ *   a_kcontig = 1: A is [M,K] row-major;  0: A is stored [K,M] row-major (A^T of a [K,M] array)
+ *   b_kcontig = 1: B is [N,K] row-major;  0: B is stored [K,N] row-major
+ * forward  y = x W^T + b : (A=x, 1), (B=W, 1);  dW = dy^T x : (A=dy, 0), (B=x, 0);
+ * dx = dy W : (A=dy, 1), (B=W, 0). (A M-contiguous with B K-contiguous is not provided.)
+ * splits > 1 cuts K over grid.z; ws must then hold splits*M*N floats (summed in split order).
+ * N and the contiguous dimensions must be multiples of 4. mmrec_gemm_splits suggests `splits`.
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_gemm_splits(int32_t M, int32_t N, int32_t K, int32_t a_kcontig, int32_t b_kcontig);
+int mmrec_gemm_tf32x3_f32(const float *A, int32_t a_kcontig, const float *B, int32_t b_kcontig,
+                          const float *bias, float *C, int32_t M, int32_t N, int32_t K,
+                          int32_t splits, float *ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam (K13). Replaces optim.Adam.step (common/trainer.py:126-143, 255, 331)
+ * with one pass: 28 bytes per parameter. The four pointer arrays and numel are HOST arrays of
+ * n_tensors device pointers / element counts (they travel as kernel arguments). hyper is a
+ * DEVICE array of two doubles: hyper[0] = learning rate, hyper[1] = update count; the call
+ * increments hyper[1] and uses it for the bias corrections, so a captured CUDA graph replays
+ * with the right step and a host-updated learning rate. Same formulas as torch's Adam.
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_adam_step_f32(float *const *params_host, const float *const *grads_host,
+                        float *const *exp_avg_host, float *const *exp_avg_sq_host,
+                        const int64_t *numel_host, int32_t n_tensors, double *hyper, double beta1,
+                        double beta2, double eps, double weight_decay, void *stream);
+/* y_t += sign * coef[0] * x_t for n_tensors tensors in one launch; coef is a device scalar
+ * (the mirror-gradient perturbation theta -/+ alpha_eff*lr*g of trainer.py:307-329 without a
+ * host round trip for alpha_eff). */
+int mmrec_axpy_multi_f32(float *const *y_host, const float *const *x_host, const int64_t *numel_host,
+                         int32_t n_tensors, const float *coef, float sign, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Full-rank scoring fused with train-item masking and per-user top-K (K8/K9/K10).

@@ -246,8 +246,8 @@ infonce_fwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
 template <int D, bool ROWPASS>
 __global__ void __launch_bounds__(kThreads)
 infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
-                   const float *__restrict__ ttl, int batch, float inv_temp,
-                   const float *__restrict__ coef, float *__restrict__ dOut) {
+                   const float *__restrict__ ttl, int batch, float inv_temp, int tiles_per_split,
+                   const float *__restrict__ coef, float *__restrict__ dOutAll) {
   extern __shared__ __align__(16) float smem[];
   constexpr int LD = D + 4, GL = kTile + 4;
   float *sOwn = smem, *sOther = smem + kTile * LD, *sG = smem + 2 * kTile * LD;  // sG[own][other]
@@ -256,6 +256,9 @@ infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
   const int n_tiles = (batch + kTile - 1) / kTile;
   const float scale = coef[0] / (float)batch * inv_temp;
   const float *Own = ROWPASS ? V1n : V2n, *Other = ROWPASS ? V2n : V1n;
+  // blockIdx.y owns a contiguous range of "other" tiles; partial sums go to its own slab
+  const int t_begin = blockIdx.y * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
+  float *dOut = dOutAll + (size_t)blockIdx.y * batch * D;
   load_tile<D>(sOwn, Own, own0, batch);
   // output accumulators: thread (tx, ty) owns rows {ty + 16 i} x column chunk of D/16 floats at tx
   constexpr int CW = D / 16;
@@ -264,7 +267,7 @@ infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int c = 0; c < CW; ++c) out[i][c] = 0.f;
-  for (int t = 0; t < n_tiles; ++t) {
+  for (int t = t_begin; t < t_end; ++t) {
     __syncthreads();
     load_tile<D>(sOther, Other, t * kTile, batch);
     __syncthreads();
@@ -315,16 +318,27 @@ infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
 __global__ void __launch_bounds__(kThreads)
 infonce_scatter_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
                        const float *__restrict__ inv_norm, const float *__restrict__ dV1,
-                       const float *__restrict__ dV2, int d, const int64_t *__restrict__ idx,
-                       int batch, float *__restrict__ dT1, float *__restrict__ dT2) {
+                       const float *__restrict__ dV2, int n_splits, int d,
+                       const int64_t *__restrict__ idx, int batch, float *__restrict__ dT1,
+                       float *__restrict__ dT2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * (kThreads / 32) + warp;
   if (b >= batch) return;
   const size_t src = (size_t)b * d, dst = (size_t)idx[b] * d;
+  const size_t slab = (size_t)batch * d;
+  // sum the per-split partial gradients in split order (deterministic)
+  auto sum_splits = [&](const float *p, int c) {
+    float4 s = ldg4(p + src + c);
+    for (int k = 1; k < n_splits; ++k) {
+      const float4 v = ldg4(p + k * slab + src + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    return s;
+  };
   float p1 = 0.f, p2 = 0.f;
   for (int c = lane * 4; c < d; c += 128) {
-    p1 += dot4(ldg4(V1n + src + c), ldg4(dV1 + src + c));
-    p2 += dot4(ldg4(V2n + src + c), ldg4(dV2 + src + c));
+    p1 += dot4(ldg4(V1n + src + c), sum_splits(dV1, c));
+    p2 += dot4(ldg4(V2n + src + c), sum_splits(dV2, c));
   }
   p1 = warp_sum(p1);
   p2 = warp_sum(p2);
@@ -332,8 +346,8 @@ infonce_scatter_kernel(const float *__restrict__ V1n, const float *__restrict__ 
   // norm clamped at eps: v = x / eps is linear in x, no projection term
   const float k1 = i1 < 1e12f ? p1 : 0.f, k2 = i2 < 1e12f ? p2 : 0.f;
   for (int c = lane * 4; c < d; c += 128) {
-    const float4 v1 = ldg4(V1n + src + c), g1 = ldg4(dV1 + src + c);
-    const float4 v2 = ldg4(V2n + src + c), g2 = ldg4(dV2 + src + c);
+    const float4 v1 = ldg4(V1n + src + c), g1 = sum_splits(dV1, c);
+    const float4 v2 = ldg4(V2n + src + c), g2 = sum_splits(dV2, c);
     float4 a, x;
     a.x = i1 * (g1.x - k1 * v1.x); a.y = i1 * (g1.y - k1 * v1.y);
     a.z = i1 * (g1.z - k1 * v1.z); a.w = i1 * (g1.w - k1 * v1.w);
@@ -364,14 +378,16 @@ int infonce_fwd_launch(const float *V1n, const float *V2n, int batch, float inv_
 
 template <int D>
 int infonce_bwd_launch(const float *V1n, const float *V2n, const float *ttl, int batch, float inv_temp,
-                       const float *coef, float *dV1, float *dV2, cudaStream_t stream) {
+                       int n_splits, const float *coef, float *dV1, float *dV2, cudaStream_t stream) {
   const int n_tiles = (batch + kTile - 1) / kTile;
+  const int tps = (n_tiles + n_splits - 1) / n_splits;   // splits past the end write zeros
+  const dim3 grid(n_tiles, n_splits);
   const size_t smem = (2 * kTile * (D + 4) + kTile * (kTile + 4)) * sizeof(float);
   MMREC_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MMREC_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  infonce_bwd_kernel<D, true><<<n_tiles, kThreads, smem, stream>>>(V1n, V2n, ttl, batch, inv_temp, coef, dV1);
+  infonce_bwd_kernel<D, true><<<grid, kThreads, smem, stream>>>(V1n, V2n, ttl, batch, inv_temp, tps, coef, dV1);
   MMREC_CHECK_LAUNCH("infonce_bwd_kernel<row>");
-  infonce_bwd_kernel<D, false><<<n_tiles, kThreads, smem, stream>>>(V1n, V2n, ttl, batch, inv_temp, coef, dV2);
+  infonce_bwd_kernel<D, false><<<grid, kThreads, smem, stream>>>(V1n, V2n, ttl, batch, inv_temp, tps, coef, dV2);
   MMREC_CHECK_LAUNCH("infonce_bwd_kernel<col>");
   return MMREC_OK;
 }
@@ -437,27 +453,27 @@ extern "C" int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d
 
 extern "C" int mmrec_infonce_bwd_f32(const float *V1n, const float *V2n, const float *inv_norm, const float *ttl,
                                      int32_t d, const int64_t *idx, int32_t batch, float inv_temp,
-                                     const float *coef, float *dV1_ws, float *dV2_ws, float *dT1, float *dT2,
-                                     void *stream_) {
+                                     const float *coef, int32_t n_splits, float *dV1_ws, float *dV2_ws,
+                                     float *dT1, float *dT2, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MMREC_REQUIRE(V1n && V2n && inv_norm && ttl && idx && coef && dV1_ws && dV2_ws && dT1 && dT2, MMREC_E_BADARG,
                 "infonce_bwd: null pointer");
-  MMREC_REQUIRE(batch > 0, MMREC_E_BADARG, "infonce_bwd: empty batch");
+  MMREC_REQUIRE(batch > 0 && n_splits >= 1 && n_splits <= 64, MMREC_E_BADARG, "infonce_bwd: bad sizes");
   MMREC_REQUIRE(aligned16(V1n) && aligned16(V2n) && aligned16(dV1_ws) && aligned16(dV2_ws) && aligned16(dT1) &&
                     aligned16(dT2), MMREC_E_ALIGN, "infonce_bwd: operands must be 16-byte aligned");
   int rc;
   switch (d) {
-    case 32: rc = infonce_bwd_launch<32>(V1n, V2n, ttl, batch, inv_temp, coef, dV1_ws, dV2_ws, stream); break;
-    case 64: rc = infonce_bwd_launch<64>(V1n, V2n, ttl, batch, inv_temp, coef, dV1_ws, dV2_ws, stream); break;
-    case 128: rc = infonce_bwd_launch<128>(V1n, V2n, ttl, batch, inv_temp, coef, dV1_ws, dV2_ws, stream); break;
+    case 32: rc = infonce_bwd_launch<32>(V1n, V2n, ttl, batch, inv_temp, n_splits, coef, dV1_ws, dV2_ws, stream); break;
+    case 64: rc = infonce_bwd_launch<64>(V1n, V2n, ttl, batch, inv_temp, n_splits, coef, dV1_ws, dV2_ws, stream); break;
+    case 128: rc = infonce_bwd_launch<128>(V1n, V2n, ttl, batch, inv_temp, n_splits, coef, dV1_ws, dV2_ws, stream); break;
     default:
       set_error("infonce_bwd: unsupported d=%d (32, 64, 128)", d);
       return MMREC_E_BADARG;
   }
   if (rc != MMREC_OK) return rc;
   const int wpb = kThreads / 32;
-  infonce_scatter_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(V1n, V2n, inv_norm, dV1_ws, dV2_ws, d,
-                                                                         idx, batch, dT1, dT2);
+  infonce_scatter_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(V1n, V2n, inv_norm, dV1_ws, dV2_ws,
+                                                                         n_splits, d, idx, batch, dT1, dT2);
   MMREC_CHECK_LAUNCH("infonce_scatter_kernel");
   return MMREC_OK;
 }

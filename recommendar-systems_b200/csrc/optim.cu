@@ -1,0 +1,178 @@
+// Fused multi-tensor Adam (K13) -- one launch updates every parameter tensor of the model.
+//
+// torch.optim.Adam's default (foreach) path makes ~8 passes over param/grad/exp_avg/exp_avg_sq
+// (trainer.py:126-143); for SMORE's 33.6 M parameters (28.9 M of them the trainable 7050 x 4096
+// image table) that is the largest HBM consumer of a step. Here each element is read once
+// (p, g, m, v) and written once (p, m, v): 28 bytes per parameter, the roofline of the update.
+// The arithmetic follows torch's single-tensor formulas (lerp for exp_avg, mul+addcmul for
+// exp_avg_sq, sqrt / bias_correction2_sqrt + eps, addcdiv with lr / bias_correction1).
+#include "common.cuh"
+
+namespace mmrec {
+namespace {
+
+constexpr int kMaxTensors = 48;
+constexpr int kChunk = 16384;      // elements per CTA-iteration
+constexpr int kThreads = 256;
+
+struct AdamPack {
+  float *p[kMaxTensors];
+  const float *g[kMaxTensors];
+  float *m[kMaxTensors];
+  float *v[kMaxTensors];
+  int chunk_begin[kMaxTensors + 1];   // prefix sum of ceil(numel / kChunk)
+  int64_t numel[kMaxTensors];
+  int n_tensors;
+};
+
+// hyper[0] = learning rate, hyper[1] = number of updates including this one (device memory, so a
+// captured CUDA graph replays with the current values).
+__global__ void adam_tick_kernel(double *hyper) { hyper[1] += 1.0; }
+
+__global__ void __launch_bounds__(kThreads)
+adam_kernel(const __grid_constant__ AdamPack pack, const double *__restrict__ hyper, double beta1d,
+            double beta2d, float eps, float weight_decay) {
+  __shared__ float s_hyper[2];
+  if (threadIdx.x == 0) {
+    const double lr = hyper[0], step = hyper[1];
+    s_hyper[0] = (float)(lr / (1.0 - pow(beta1d, step)));      // lr / bias_correction1
+    s_hyper[1] = (float)sqrt(1.0 - pow(beta2d, step));         // sqrt(bias_correction2)
+  }
+  __syncthreads();
+  const float step_size = s_hyper[0], bc2_sqrt = s_hyper[1];
+  const float beta1 = (float)beta1d, beta2 = (float)beta2d;
+  const int chunk = blockIdx.x;
+  int t = 0;
+  while (t + 1 < pack.n_tensors && pack.chunk_begin[t + 1] <= chunk) ++t;
+  const int64_t begin = (int64_t)(chunk - pack.chunk_begin[t]) * kChunk;
+  const int64_t n = pack.numel[t];
+  const int64_t end = min(n, begin + kChunk);
+  float *__restrict__ p = pack.p[t];
+  const float *__restrict__ g = pack.g[t];
+  float *__restrict__ m = pack.m[t];
+  float *__restrict__ v = pack.v[t];
+  const float w1 = (float)(1.0 - beta1d), w2 = (float)(1.0 - beta2d);
+  (void)beta1;
+  auto upd = [&](float &pp, float gg, float &mm, float &vv) {
+    if (weight_decay != 0.f) gg = fmaf(weight_decay, pp, gg);
+    mm = mm + w1 * (gg - mm);
+    vv = vv * beta2 + w2 * gg * gg;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp = pp - step_size * (mm / denom);
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                     reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15u) == 0;
+  if (vec) {
+    const int64_t end4 = begin + ((end - begin) & ~int64_t(3));
+    for (int64_t i = begin + threadIdx.x * 4; i < end4; i += kThreads * 4) {
+      float4 pp = *reinterpret_cast<float4 *>(p + i), mm = *reinterpret_cast<float4 *>(m + i),
+             vv = *reinterpret_cast<float4 *>(v + i);
+      const float4 gg = __ldcs(reinterpret_cast<const float4 *>(g + i));
+      upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y);
+      upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+      *reinterpret_cast<float4 *>(p + i) = pp;
+      *reinterpret_cast<float4 *>(m + i) = mm;
+      *reinterpret_cast<float4 *>(v + i) = vv;
+    }
+    for (int64_t i = end4 + threadIdx.x; i < end; i += kThreads) upd(p[i], g[i], m[i], v[i]);
+  } else {
+    for (int64_t i = begin + threadIdx.x; i < end; i += kThreads) upd(p[i], g[i], m[i], v[i]);
+  }
+}
+
+struct AxpyPack {
+  float *y[kMaxTensors];
+  const float *x[kMaxTensors];
+  int chunk_begin[kMaxTensors + 1];
+  int64_t numel[kMaxTensors];
+  int n_tensors;
+};
+
+// y_t += sign * coef[0] * x_t for every tensor t (coef is a device scalar)
+__global__ void __launch_bounds__(kThreads)
+axpy_multi_kernel(const __grid_constant__ AxpyPack pack, const float *__restrict__ coef, float sign) {
+  const int chunk = blockIdx.x;
+  int t = 0;
+  while (t + 1 < pack.n_tensors && pack.chunk_begin[t + 1] <= chunk) ++t;
+  const int64_t begin = (int64_t)(chunk - pack.chunk_begin[t]) * kChunk;
+  const int64_t end = min(pack.numel[t], begin + kChunk);
+  float *__restrict__ y = pack.y[t];
+  const float *__restrict__ x = pack.x[t];
+  const float a = sign * coef[0];
+  const bool vec = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0;
+  int64_t i = begin + (vec ? threadIdx.x * 4 : threadIdx.x);
+  if (vec) {
+    const int64_t end4 = begin + ((end - begin) & ~int64_t(3));
+    for (; i < end4; i += kThreads * 4) {
+      float4 yy = *reinterpret_cast<float4 *>(y + i);
+      const float4 xx = *reinterpret_cast<const float4 *>(x + i);
+      yy.x = fmaf(a, xx.x, yy.x); yy.y = fmaf(a, xx.y, yy.y); yy.z = fmaf(a, xx.z, yy.z); yy.w = fmaf(a, xx.w, yy.w);
+      *reinterpret_cast<float4 *>(y + i) = yy;
+    }
+    for (i = end4 + threadIdx.x; i < end; i += kThreads) y[i] = fmaf(a, x[i], y[i]);
+  } else {
+    for (; i < end; i += kThreads) y[i] = fmaf(a, x[i], y[i]);
+  }
+}
+
+}  // namespace
+}  // namespace mmrec
+
+using namespace mmrec;
+
+extern "C" int mmrec_adam_step_f32(float *const *params_host, const float *const *grads_host,
+                                   float *const *exp_avg_host, float *const *exp_avg_sq_host,
+                                   const int64_t *numel_host, int32_t n_tensors, double *hyper, double beta1,
+                                   double beta2, double eps, double weight_decay, void *stream) {
+  MMREC_REQUIRE(params_host && grads_host && exp_avg_host && exp_avg_sq_host && numel_host && hyper,
+                MMREC_E_BADARG, "adam: null pointer");
+  MMREC_REQUIRE(n_tensors >= 0, MMREC_E_BADARG, "adam: bad sizes");
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+  MMREC_CHECK_LAUNCH("adam_tick_kernel");
+  for (int base = 0; base < n_tensors; base += kMaxTensors) {
+    AdamPack pack;
+    pack.n_tensors = min(kMaxTensors, n_tensors - base);
+    int chunks = 0;
+    for (int i = 0; i < pack.n_tensors; ++i) {
+      pack.p[i] = params_host[base + i];
+      pack.g[i] = grads_host[base + i];
+      pack.m[i] = exp_avg_host[base + i];
+      pack.v[i] = exp_avg_sq_host[base + i];
+      pack.numel[i] = numel_host[base + i];
+      MMREC_REQUIRE(pack.p[i] && pack.g[i] && pack.m[i] && pack.v[i] && pack.numel[i] >= 0, MMREC_E_BADARG,
+                    "adam: bad tensor %d", base + i);
+      pack.chunk_begin[i] = chunks;
+      chunks += (int)((pack.numel[i] + kChunk - 1) / kChunk);
+    }
+    pack.chunk_begin[pack.n_tensors] = chunks;
+    if (chunks == 0) continue;
+    adam_kernel<<<chunks, kThreads, 0, (cudaStream_t)stream>>>(pack, hyper, beta1, beta2, (float)eps,
+                                                              (float)weight_decay);
+    MMREC_CHECK_LAUNCH("adam_kernel");
+  }
+  return MMREC_OK;
+}
+
+extern "C" int mmrec_axpy_multi_f32(float *const *y_host, const float *const *x_host, const int64_t *numel_host,
+                                    int32_t n_tensors, const float *coef, float sign, void *stream) {
+  MMREC_REQUIRE(y_host && x_host && numel_host && coef, MMREC_E_BADARG, "axpy_multi: null pointer");
+  for (int base = 0; base < n_tensors; base += kMaxTensors) {
+    AxpyPack pack;
+    pack.n_tensors = min(kMaxTensors, n_tensors - base);
+    int chunks = 0;
+    for (int i = 0; i < pack.n_tensors; ++i) {
+      pack.y[i] = y_host[base + i];
+      pack.x[i] = x_host[base + i];
+      pack.numel[i] = numel_host[base + i];
+      MMREC_REQUIRE(pack.y[i] && pack.x[i] && pack.numel[i] >= 0, MMREC_E_BADARG, "axpy_multi: bad tensor %d",
+                    base + i);
+      pack.chunk_begin[i] = chunks;
+      chunks += (int)((pack.numel[i] + kChunk - 1) / kChunk);
+    }
+    pack.chunk_begin[pack.n_tensors] = chunks;
+    if (chunks == 0) continue;
+    axpy_multi_kernel<<<chunks, kThreads, 0, (cudaStream_t)stream>>>(pack, coef, sign);
+    MMREC_CHECK_LAUNCH("axpy_multi_kernel");
+  }
+  return MMREC_OK;
+}

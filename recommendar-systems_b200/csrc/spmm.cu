@@ -1,13 +1,17 @@
 // CSR row-split SpMM with fused layer combination (K1/K2/K3) -- see include/mmrec_b200.h.
 //
 // Layout: CSR (int32 row_ptr / col_idx, float32 vals), X and Y row-major [n, d].
-// Work split: rows are visited in descending-degree order (row_sched). The n_long heaviest rows
-// get one CTA each (their non-zeros are strided over the CTA's sub-warps and reduced through
-// shared memory in a fixed order); every other row gets one sub-warp of LANES = d/4 threads
-// (16 lanes x float4 for d = 64, a full warp for d = 128), so each gathered embedding row is one
-// fully coalesced 16-byte-per-lane request. Column indices and values are loaded once per LANES
-// non-zeros (coalesced) and broadcast with shuffles; four gathers are kept in flight per lane.
-// No atomics: results are bit-reproducible run to run.
+// Work split: the graph carries a task list built once per graph (graph.py): every task is one
+// sub-warp of LANES = d/4 threads (16 lanes x float4 for d = 64, a full warp for d = 128) and at
+// most SEG = 64 non-zeros, so the longest dependent chain of gathers in the whole launch is a
+// handful of rounds whatever the degree distribution (power-law item rows would otherwise
+// serialise thousands of DRAM round trips in one sub-warp). Light rows (deg <= SEG) are one task;
+// a heavy row is cut into ceil(deg/SEG) tasks whose partial sums go to a scratch buffer, and
+// the last task to arrive (per-row counter, self-resetting) adds them in part order and runs
+// the fused epilogue -- no floating-point atomics, results are bit-reproducible run to run.
+// Each gathered embedding row is one coalesced 16-byte-per-lane request; column indices and
+// values are loaded once per LANES non-zeros and broadcast with shuffles; eight gathers are kept
+// in flight per lane.
 #include "common.cuh"
 
 namespace mmrec {
@@ -53,6 +57,25 @@ __device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t
     }
     const int cnt = min(LANES, end - base);
     int j = 0;
+    for (; j + 8 <= cnt; j += 8) {
+      int cc[8];
+      float vv[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        cc[t] = __shfl_sync(mask, c, j + t, LANES);
+        vv[t] = __shfl_sync(mask, v, j + t, LANES);
+      }
+      float4 x[8][CHUNKS];
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int q = 0; q < CHUNKS; ++q)
+          x[t][q] = ldg4(X + (size_t)cc[t] * d + (q * LANES + lane) * 4);
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int q = 0; q < CHUNKS; ++q) fma4(acc[q], vv[t], x[t][q]);
+    }
     for (; j + 4 <= cnt; j += 4) {
       int cc[4];
       float vv[4];
@@ -139,47 +162,64 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[CHUNKS], int row, int l
   }
 }
 
+constexpr int kSeg = 64;  // non-zeros per task; must match graph.py SEG
+
 template <int LANES, int CHUNKS>
 __global__ void __launch_bounds__(kThreads)
 spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
-                const float *__restrict__ vals, const int32_t *__restrict__ row_sched, int n_rows,
-                int n_long, int col_offset, const float *__restrict__ X, int d, Epilogue ep) {
+                const float *__restrict__ vals, const int4 *__restrict__ tasks, int n_tasks,
+                const int32_t *__restrict__ slot_base, int32_t *__restrict__ counters,
+                float *__restrict__ scratch, int col_offset, const float *__restrict__ X, int d,
+                Epilogue ep) {
   constexpr int GROUPS = kThreads / LANES;
   const int lane = threadIdx.x % LANES;
-  const int group = threadIdx.x / LANES;
+  const int t = blockIdx.x * GROUPS + threadIdx.x / LANES;
+  if (t >= n_tasks) return;
+  const int4 task = __ldg(tasks + t);          // {row, begin, end, slot}
+  const int row = task.x;
   float4 acc[CHUNKS];
 #pragma unroll
   for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  if ((int)blockIdx.x < n_long) {
-    // one CTA per heavy row: sub-warps stride over the row, fixed-order shared-memory reduce
-    __shared__ float4 red[GROUPS][LANES * CHUNKS];
-    const int row = row_sched[blockIdx.x];
-    const int begin = row_ptr[row], end = row_ptr[row + 1];
-    gather_rows<LANES, CHUNKS>(acc, col_idx, vals, begin + group * LANES, end, GROUPS * LANES, lane,
-                               X, d, col_offset);
+  gather_rows<LANES, CHUNKS>(acc, col_idx, vals, task.y, task.z, LANES, lane, X, d, col_offset);
+  if (task.w >= 0) {
+    // heavy row: publish this part, the last arriver reduces all parts in order
+    const unsigned mask = group_mask<LANES>();
+    const int r0 = row_ptr[row];
+    const int n_parts = (row_ptr[row + 1] - r0 + kSeg - 1) / kSeg;
+    const int part = (task.y - r0) / kSeg;
+    float *base = scratch + (size_t)slot_base[task.w] * d;
 #pragma unroll
-    for (int q = 0; q < CHUNKS; ++q) red[group][q * LANES + lane] = acc[q];
-    __syncthreads();
-    if (group == 0) {
-#pragma unroll
-      for (int q = 0; q < CHUNKS; ++q) {
-        float4 s = red[0][q * LANES + lane];
-        for (int g = 1; g < GROUPS; ++g) {
-          const float4 t = red[g][q * LANES + lane];
-          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-        }
-        acc[q] = s;
-      }
-      finish_row<LANES, CHUNKS>(acc, row, lane, d, ep);
+    for (int q = 0; q < CHUNKS; ++q)
+      __stcg(reinterpret_cast<float4 *>(base + (size_t)part * d + (q * LANES + lane) * 4), acc[q]);
+    __threadfence();
+    __syncwarp(mask);
+    int last = 0;
+    if (lane == 0) {
+      last = atomicAdd(counters + task.w, 1) == n_parts - 1;
+      if (last) counters[task.w] = 0;
     }
-    return;
+    last = __shfl_sync(mask, last, 0, LANES);
+    if (!last) return;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < n_parts; p += 4) {
+      float4 v[4][CHUNKS];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < CHUNKS; ++q)
+          v[u][q] = p + u < n_parts
+                        ? __ldcg(reinterpret_cast<const float4 *>(base + (size_t)(p + u) * d + (q * LANES + lane) * 4))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < CHUNKS; ++q) {
+          acc[q].x += v[u][q].x; acc[q].y += v[u][q].y; acc[q].z += v[u][q].z; acc[q].w += v[u][q].w;
+        }
+    }
   }
-  const int slot = n_long + ((int)blockIdx.x - n_long) * GROUPS + group;
-  if (slot >= n_rows) return;
-  const int row = row_sched[slot];
-  const int begin = row_ptr[row], end = row_ptr[row + 1];
-  gather_rows<LANES, CHUNKS>(acc, col_idx, vals, begin, end, LANES, lane, X, d, col_offset);
   finish_row<LANES, CHUNKS>(acc, row, lane, d, ep);
 }
 
@@ -253,26 +293,26 @@ int dispatch_width(int d, F &&f) {
 using namespace mmrec;
 
 extern "C" int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
-                                  const int32_t *row_sched, int32_t n_rows, int32_t n_long,
-                                  int32_t col_offset, const float *X, int32_t d, float *Y,
-                                  const float *acc_in, float *acc_out, float acc_scale,
+                                  const int32_t *tasks, int32_t n_tasks, const int32_t *slot_base,
+                                  int32_t *counters, float *scratch, int32_t col_offset, const float *X,
+                                  int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
                                   const float *cos_ref, float *cos_w, float *Y_pre, void *stream) {
-  MMREC_REQUIRE(row_ptr && col_idx && vals && row_sched && X, MMREC_E_BADARG, "spmm: null input");
+  MMREC_REQUIRE(row_ptr && col_idx && vals && tasks && X, MMREC_E_BADARG, "spmm: null input");
   MMREC_REQUIRE(Y || acc_out, MMREC_E_BADARG, "spmm: no output requested");
-  MMREC_REQUIRE(n_rows >= 0 && n_long >= 0 && n_long <= n_rows, MMREC_E_BADARG, "spmm: bad sizes");
+  MMREC_REQUIRE(n_tasks >= 0, MMREC_E_BADARG, "spmm: bad sizes");
   MMREC_REQUIRE(aligned16(X) && aligned16(Y) && aligned16(acc_in) && aligned16(acc_out) &&
-                    aligned16(cos_ref) && aligned16(Y_pre),
-                MMREC_E_ALIGN, "spmm: dense operands must be 16-byte aligned");
+                    aligned16(cos_ref) && aligned16(Y_pre) && aligned16(tasks) && aligned16(scratch),
+                MMREC_E_ALIGN, "spmm: dense operands and the task list must be 16-byte aligned");
   MMREC_REQUIRE(X != Y && X != acc_out, MMREC_E_BADARG, "spmm: X must not alias an output");
-  if (n_rows == 0) return MMREC_OK;
+  if (n_tasks == 0) return MMREC_OK;
   Epilogue ep{Y, acc_in, acc_out, acc_scale, cos_ref, cos_w, Y_pre};
   return dispatch_width(d, [&](auto lanes, auto chunks) {
     constexpr int L = decltype(lanes)::value, C = decltype(chunks)::value;
     constexpr int GROUPS = kThreads / L;
-    const int n_short = n_rows - n_long;
-    const int blocks = n_long + (n_short + GROUPS - 1) / GROUPS;
+    const int blocks = (n_tasks + GROUPS - 1) / GROUPS;
     spmm_csr_kernel<L, C><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
-        row_ptr, col_idx, vals, row_sched, n_rows, n_long, col_offset, X, d, ep);
+        row_ptr, col_idx, vals, reinterpret_cast<const int4 *>(tasks), n_tasks, slot_base, counters, scratch,
+        col_offset, X, d, ep);
     MMREC_CHECK_LAUNCH("spmm_csr_kernel");
     return MMREC_OK;
   });

@@ -1,8 +1,8 @@
 """Device-resident CSR graphs for the propagation kernels.
 
 HBM layout: `row_ptr` int32 [rows+1], `col_idx` int32 [nnz], `vals` float32
-[nnz], plus `sched` int32 [rows] -- the row visiting order (descending degree) of
-mmrec_spmm_csr_f32. The symmetric user-item adjacency is stored once; R = A[:U, U:] and R^T are
+[nnz], plus the SpMM work list `tasks` int32 [n_tasks, 4] (<= 64 non-zeros per task, see
+build_tasks) with its reduction slots for heavy rows. The symmetric user-item adjacency is stored once; R = A[:U, U:] and R^T are
 zero-copy views of it (a row-pointer slice + a column offset), so SMORE/MGCN's `R` propagation
 and its transposed backward need no extra storage.
 """
@@ -13,18 +13,60 @@ import torch
 
 from . import lib
 
-LONG_ROW = 512      # rows with at least this many non-zeros get a whole CTA
+SEG = 64            # non-zeros per SpMM task (kSeg in csrc/spmm.cu)
+
+
+def build_tasks(row_ptr):
+    """Work list of mmrec_spmm_csr_f32: int32 [n_tasks, 4] = {row, begin, end, slot}. Rows with at
+    most SEG non-zeros are one task (slot -1, longest first so that the sub-warps of a warp have
+    similar trip counts); heavier rows are cut into SEG-sized parts that share a reduction slot.
+    Returns (tasks, slot_base int32 [n_heavy], total_parts)."""
+    dev = row_ptr.device
+    rp = row_ptr.to(torch.int64)
+    begin, end = rp[:-1], rp[1:]
+    deg = end - begin
+    rows = torch.arange(deg.numel(), device=dev, dtype=torch.int64)
+    heavy = deg > SEG
+    light_rows = rows[~heavy & (deg >= 0)]
+    order = torch.argsort(deg[light_rows], descending=True, stable=True)
+    light_rows = light_rows[order]
+    light = torch.stack([light_rows, begin[light_rows], end[light_rows],
+                         torch.full_like(light_rows, -1)], dim=1)
+    h_rows = rows[heavy]
+    n_parts = (deg[h_rows] + SEG - 1) // SEG
+    slot_base = torch.cumsum(n_parts, 0) - n_parts
+    total_parts = int(n_parts.sum().item()) if h_rows.numel() else 0
+    if total_parts:
+        slot = torch.repeat_interleave(torch.arange(h_rows.numel(), device=dev), n_parts)
+        part = torch.arange(total_parts, device=dev) - slot_base[slot]
+        r = h_rows[slot]
+        b = begin[r] + part * SEG
+        e = torch.minimum(b + SEG, end[r])
+        heavy_tasks = torch.stack([r, b, e, slot], dim=1)
+        tasks = torch.cat([heavy_tasks, light], dim=0)
+    else:
+        tasks = light
+    return tasks.to(torch.int32).contiguous(), slot_base.to(torch.int32).contiguous(), total_parts
 
 
 class CSRGraph:
     def __init__(self, row_ptr, col_idx, vals, n_rows, n_cols, col_offset=0, symmetric=False):
         self.row_ptr, self.col_idx, self.vals = row_ptr, col_idx, vals
         self.n_rows, self.n_cols, self.col_offset = int(n_rows), int(n_cols), int(col_offset)
-        deg = (row_ptr[1:] - row_ptr[:-1])
-        self.sched = torch.argsort(deg, descending=True, stable=True).to(torch.int32)
-        self.n_long = int((deg >= LONG_ROW).sum().item())
+        self.tasks, self.slot_base, self.total_parts = build_tasks(row_ptr)
+        self.n_tasks = int(self.tasks.shape[0])
+        self.counters = torch.zeros(max(1, self.slot_base.numel()), dtype=torch.int32,
+                                    device=row_ptr.device)
+        self._scratch = {}
         self.nnz = int((row_ptr[-1] - row_ptr[0]).item())
         self.t = self if symmetric else None
+
+    def scratch(self, d):
+        """Partial-sum buffer of the heavy rows for embedding width d (allocated once)."""
+        if d not in self._scratch:
+            self._scratch[d] = torch.empty(max(1, self.total_parts) * d, dtype=torch.float32,
+                                           device=self.vals.device)
+        return self._scratch[d]
 
     @property
     def device(self):

@@ -27,18 +27,23 @@ SIGNATURES = {
     "mmrec_csr_from_coo_workspace_bytes": (_sz, [_i64]),
     "mmrec_csr_from_coo": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _sz,
                                      _p]),
-    "mmrec_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _f32,
-                                     _p, _p, _p, _p]),
+    "mmrec_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p,
+                                     _f32, _p, _p, _p, _p]),
     "mmrec_layergcn_cos_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
     "mmrec_bpr_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "mmrec_bpr_bwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "mmrec_infonce_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p, _p, _p,
                                         _p]),
-    "mmrec_infonce_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p,
-                                        _p]),
+    "mmrec_infonce_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _f32, _p, _i32, _p, _p, _p,
+                                        _p, _p]),
     "mmrec_spectral_fwd_f32": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "mmrec_spectral_bwd_f32": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p,
                                          _p, _p, _p, _p, _p, _p]),
+    "mmrec_gemm_splits": (C.c_int, [_i32, _i32, _i32, _i32, _i32]),
+    "mmrec_gemm_tf32x3_f32": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "mmrec_adam_step_f32": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double,
+                                      C.c_double, _p]),
+    "mmrec_axpy_multi_f32": (C.c_int, [_p, _p, _p, _i32, _p, _f32, _p]),
     "mmrec_score_mask_topk_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _i32, _p, _p, _i32, _i32,
                                             _p, _p, _p, _p, _p]),
     "mmrec_topk_merge": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),

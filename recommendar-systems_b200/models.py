@@ -309,10 +309,10 @@ class FREEDOM(GeneralRecommender):
         nn.init.xavier_uniform_(self.item_id_embedding.weight)
         if self.v_feat is not None:
             self.image_embedding = nn.Embedding.from_pretrained(self.v_feat, freeze=False)
-            self.image_trs = nn.Linear(self.v_feat.shape[1], self.feat_embed_dim)
+            self.image_trs = ops.Linear(self.v_feat.shape[1], self.feat_embed_dim)
         if self.t_feat is not None:
             self.text_embedding = nn.Embedding.from_pretrained(self.t_feat, freeze=False)
-            self.text_trs = nn.Linear(self.t_feat.shape[1], self.feat_embed_dim)
+            self.text_trs = ops.Linear(self.t_feat.shape[1], self.feat_embed_dim)
         coo = _coo_override(config, "mm_adj", self.device)
         if coo is None:
             # freedom.py:64-77: w * image_adj + (1-w) * text_adj; duplicates are summed by SpMM
@@ -415,14 +415,14 @@ class MGCN(_MultiViewBase):
         _, self.image_original_adj = self._item_graph(config, "image_adj", self.v_feat, self.knn_k)
         self.text_embedding = nn.Embedding.from_pretrained(self.t_feat, freeze=False)
         _, self.text_original_adj = self._item_graph(config, "text_adj", self.t_feat, self.knn_k)
-        self.image_trs = nn.Linear(self.v_feat.shape[1], d)
-        self.text_trs = nn.Linear(self.t_feat.shape[1], d)
+        self.image_trs = ops.Linear(self.v_feat.shape[1], d)
+        self.text_trs = ops.Linear(self.t_feat.shape[1], d)
         self.softmax = nn.Softmax(dim=-1)
-        self.query_common = nn.Sequential(nn.Linear(d, d), nn.Tanh(), nn.Linear(d, 1, bias=False))
-        self.gate_v = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
-        self.gate_t = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
-        self.gate_image_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
-        self.gate_text_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.query_common = nn.Sequential(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, 1, bias=False))
+        self.gate_v = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_t = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_image_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_text_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
         self.tau = 0.5
 
     def forward(self, adj, train=False):
@@ -490,17 +490,17 @@ class SMORE(_MultiViewBase):
         if fus is None:
             fus = max_pool_fusion_coo(img_coo, txt_coo, self.n_items)
         self.fusion_adj = G.csr_from_coo(*fus, self.n_items, self.n_items)
-        self.image_trs = nn.Linear(self.v_feat.shape[1], d)
-        self.text_trs = nn.Linear(self.t_feat.shape[1], d)
+        self.image_trs = ops.Linear(self.v_feat.shape[1], d)
+        self.text_trs = ops.Linear(self.t_feat.shape[1], d)
         self.softmax = nn.Softmax(dim=-1)
-        self.query_v = nn.Sequential(nn.Linear(d, d), nn.Tanh(), nn.Linear(d, d, bias=False))
-        self.query_t = nn.Sequential(nn.Linear(d, d), nn.Tanh(), nn.Linear(d, d, bias=False))
-        self.gate_v = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
-        self.gate_t = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
-        self.gate_f = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
-        self.gate_image_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
-        self.gate_text_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
-        self.gate_fusion_prefer = nn.Sequential(nn.Linear(d, d), nn.Sigmoid())
+        self.query_v = nn.Sequential(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, d, bias=False))
+        self.query_t = nn.Sequential(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, d, bias=False))
+        self.gate_v = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_t = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_f = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_image_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_text_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_fusion_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
         self.image_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))
         self.text_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))
         self.fusion_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))

@@ -35,7 +35,8 @@ def spmm_raw(g: CSRGraph, X, Y=None, acc_in=None, acc_out=None, acc_scale=1.0, c
     if X.shape[0] < g.n_cols:
         raise RuntimeError(f"spmm: X has {X.shape[0]} rows, graph has {g.n_cols} columns")
     lib.call("mmrec_spmm_csr_f32", lib.ptr(g.row_ptr), lib.ptr(g.col_idx), lib.ptr(g.vals),
-             lib.ptr(g.sched), g.n_rows, g.n_long, g.col_offset, lib.ptr(X), d, lib.ptr(Y),
+             lib.ptr(g.tasks), g.n_tasks, lib.ptr(g.slot_base), lib.ptr(g.counters),
+             lib.ptr(g.scratch(d)), g.col_offset, lib.ptr(X), d, lib.ptr(Y),
              lib.ptr(acc_in), lib.ptr(acc_out), float(acc_scale), lib.ptr(cos_ref), lib.ptr(cos_w),
              lib.ptr(y_pre), lib.stream())
 
@@ -263,9 +264,12 @@ class _InfoNCEPair(torch.autograd.Function):
         for slot, row0 in enumerate((ctx.n_users, 0)):
             V1, V2, inv_norm, ttl, idx = saved[5 * slot: 5 * slot + 5]
             B = idx.numel()
-            ws1, ws2 = torch.empty_like(V1), torch.empty_like(V2)
+            tiles = (B + 63) // 64
+            S = max(1, min(tiles, (2 * 148 + tiles - 1) // tiles, 16))
+            ws1 = torch.empty(S, B, d, dtype=torch.float32, device=dev)
+            ws2 = torch.empty_like(ws1)
             lib.call("mmrec_infonce_bwd_f32", lib.ptr(V1), lib.ptr(V2), lib.ptr(inv_norm),
-                     lib.ptr(ttl), d, lib.ptr(idx), B, ctx.inv_t, lib.ptr(coef), lib.ptr(ws1),
+                     lib.ptr(ttl), d, lib.ptr(idx), B, ctx.inv_t, lib.ptr(coef), S, lib.ptr(ws1),
                      lib.ptr(ws2), lib.ptr(d_side[row0:]), lib.ptr(d_content[row0:]), lib.stream())
         return d_side, d_content, None, None, None, None
 
@@ -308,6 +312,54 @@ class _Spectral(torch.autograd.Function):
 def spectrum_convolution(img, txt, w_img, w_txt, w_fus, weight_norm=True):
     """SMORE.spectrum_convolution (smore.py:209-238) -> (image_conv, text_conv, fusion_conv)."""
     return _Spectral.apply(img, txt, w_img, w_txt, w_fus, weight_norm)
+
+
+# --------------------------------------------------------------------------------- dense linear
+def gemm(A, a_kcontig, B, b_kcontig, M, N, K, bias=None):
+    """mmrec_gemm_tf32x3_f32: C[M,N] = op(A) op(B) (+bias), fp32-accurate on tensor cores."""
+    L = lib.load()
+    splits = L.mmrec_gemm_splits(M, N, K, int(a_kcontig), int(b_kcontig))
+    C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    ws = torch.empty(splits, M, N, dtype=torch.float32, device=A.device) if splits > 1 else None
+    lib.call("mmrec_gemm_tf32x3_f32", lib.ptr(A), int(a_kcontig), lib.ptr(B), int(b_kcontig),
+             lib.ptr(bias), lib.ptr(C), M, N, K, splits, lib.ptr(ws), lib.stream())
+    return C
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x, W = _f32c(x), _f32c(W)
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return gemm(x, True, W, True, x.shape[0], W.shape[0], W.shape[1], None if b is None else _f32c(b))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = _f32c(dy)
+        M, K = x.shape
+        N = W.shape[0]
+        dx = gemm(dy, True, W, False, M, K, N) if ctx.needs_input_grad[0] else None
+        dW = gemm(dy, False, x, False, N, K, M) if ctx.needs_input_grad[1] else None
+        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dW, db
+
+
+def linear(x, W, b=None):
+    """F.linear(x, W, b) for 2-D x on the 3xTF32 tensor-core GEMM (K4); shapes the kernel does not
+    cover (output or input width not a multiple of 4) go to cuBLAS through F.linear."""
+    if x.dim() != 2 or W.shape[0] % 4 or W.shape[1] % 4 or not x.is_cuda:
+        lib.require_cuda(x)
+        return torch.nn.functional.linear(x, W, b)
+    return _Linear.apply(x, W, b)
+
+
+class Linear(torch.nn.Linear):
+    """nn.Linear with the same parameters / init / state_dict keys, forward on `linear`."""
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)
 
 
 # -------------------------------------------------------------------------------- score + top-K

@@ -136,3 +136,21 @@ def write_reference_layout(data: SynthData, root: str, uid="userID", iid="itemID
     if data.text_feat is not None:
         np.save(os.path.join(d, "text_feat.npy"), data.text_feat)
     return d
+
+
+def make_scaled_edges(device, n_users, n_items, n_edges, seed=2024):
+    """Config 5 (scaled power-law graph): edges generated directly on the device -- user degrees
+    ~ 5 + Pareto tail, item popularity ~ Zipf(0.8). Duplicate (u, i) pairs are removed, so the
+    result has slightly fewer than `n_edges` edges. Returns int64 (users, items)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    w = torch.rand(n_users, generator=g, device=device).clamp_min(1e-6).pow(-1.0 / 1.6)
+    extra = max(0, n_edges - 5 * n_users)
+    deg = 5 + torch.floor(w / w.sum() * extra).to(torch.int64)
+    users = torch.repeat_interleave(torch.arange(n_users, device=device), deg)
+    pop = torch.arange(1, n_items + 1, device=device, dtype=torch.float64).pow(-0.8)
+    pop = pop[torch.randperm(n_items, generator=g, device=device)]
+    cdf = torch.cumsum(pop / pop.sum(), 0).to(torch.float32)
+    items = torch.searchsorted(cdf, torch.rand(users.numel(), generator=g, device=device)).clamp_max(n_items - 1)
+    key = torch.unique(users * n_items + items)
+    return key // n_items, key % n_items

@@ -166,11 +166,20 @@ class Trainer:
         self.mg_target_rel_step = float(config.get("mg_target_rel_step", 1e-3))
         self.mg_alpha_max_scale = float(config.get("mg_alpha_max_scale", 20.0))
         self.sync_free = bool(config.get("sync_free", True))
+        # steady-state steps are replayed from a CUDA graph (needs the device-side Adam counters)
+        self.use_cuda_graph = bool(config.get("cuda_graph", True)) and self.sync_free and \
+            hasattr(self.optimizer, "lr_tensor") and not self.clip_grad_norm and not self.mg
+        self.graph_warmup = int(config.get("graph_warmup", 2))
+        self._graphs = {}
 
     def _build_optimizer(self):
         """trainer.py:126-143."""
         name = self.learner.lower()
         kw = dict(lr=self.learning_rate, weight_decay=self.weight_decay)
+        if name == "adam" and self.config.get("fused_adam", True) and \
+                all(p.is_cuda for p in self.model.parameters()):
+            from .optim import FusedAdam
+            return FusedAdam(self.model.parameters(), **kw)
         cls = {"adam": optim.Adam, "sgd": optim.SGD, "adagrad": optim.Adagrad,
                "rmsprop": optim.RMSprop}.get(name)
         if cls is None:
@@ -180,8 +189,10 @@ class Trainer:
 
     # ---- one step of the mirror-gradient schedule (trainer.py:268-335) ----------------------
     def _mirror_gradient_step(self, loss_func, mirror_input):
+        """trainer.py:268-335. Same arithmetic, but alpha_eff stays a device scalar (no host
+        round trip, CUDA-graph capturable) and the gradients of pass 1 are kept by reference
+        instead of being cloned (zero_grad(set_to_none) detaches them from the parameters)."""
         opt, model = self.optimizer, self.model
-        lr = opt.param_groups[0].get("lr", 1.0)
         opt.zero_grad(set_to_none=True)
         loss_curr = loss_func(mirror_input)
         (sum(loss_curr) if isinstance(loss_curr, tuple) else loss_curr).backward()
@@ -189,32 +200,112 @@ class Trainer:
         for p in model.parameters():
             if p.requires_grad and p.grad is not None:
                 params.append(p)
-                grads.append(p.grad.detach().clone())
+                grads.append(p.grad.detach())
         alpha_base = float(getattr(model, "mg_alpha", 0.5))
         with torch.no_grad():
-            if not grads:
-                alpha_eff = alpha_base
+            dev = params[0].device
+            if hasattr(opt, "lr_tensor"):
+                lr = opt.lr_tensor().to(torch.float32)
             else:
-                # grad_rms / param_rms as device scalars; one host read for alpha_eff
-                g2 = torch.stack([g.pow(2).sum() for g in grads]).sum()
-                p2 = torch.stack([p.detach().pow(2).sum() for p in params]).sum()
-                numel = float(sum(g.numel() for g in grads))
-                rms = torch.stack([g2, p2]).sqrt().div(numel ** 0.5).tolist()
-                grad_rms, param_rms = rms[0], rms[1] + 1e-12
-                target_step = self.mg_target_rel_step * param_rms
-                alpha_eff = max(alpha_base, target_step / (lr * grad_rms + 1e-12))
-                alpha_eff = min(alpha_eff, alpha_base * self.mg_alpha_max_scale)
-            model._alpha_eff = float(alpha_eff)
-            torch._foreach_add_(params, grads, alpha=-alpha_eff * lr)
+                lr = torch.tensor([opt.param_groups[0].get("lr", 1.0)], dtype=torch.float32, device=dev)
+            numel = float(sum(g.numel() for g in grads))
+            g2 = torch.stack(torch._foreach_norm(grads)).pow(2).sum()
+            p2 = torch.stack(torch._foreach_norm([p.detach() for p in params])).pow(2).sum()
+            grad_rms = (g2 / numel).sqrt()
+            param_rms = (p2 / numel).sqrt() + 1e-12
+            alpha_eff = torch.clamp(self.mg_target_rel_step * param_rms / (lr * grad_rms + 1e-12),
+                                    min=alpha_base, max=alpha_base * self.mg_alpha_max_scale)
+            model._alpha_eff = alpha_eff                      # device scalar (logging only)
+            coef = (alpha_eff * lr).reshape(1).contiguous()
+            from .optim import axpy_multi
+            axpy_multi(params, grads, coef, sign=-1.0)        # theta' = theta - alpha_eff*lr*g
         opt.zero_grad(set_to_none=True)
         loss_mirror = loss_func(mirror_input)
         (sum(loss_mirror) if isinstance(loss_mirror, tuple) else loss_mirror).backward()
         with torch.no_grad():
             mg = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
             torch._foreach_mul_(mg, -float(getattr(model, "mg_beta", 0.2)))
-            torch._foreach_add_(params, grads, alpha=alpha_eff * lr)
+            axpy_multi(params, grads, coef, sign=1.0)         # back to theta
         opt.step()
         opt.zero_grad(set_to_none=True)
+
+    def _train_batch(self, interaction, batch_idx=0, loss_func=None):
+        """Body of the batch loop of trainer.py:186-335 for one [3, B] interaction; returns the
+        detached loss of the first forward (what the reference accumulates)."""
+        loss_func = loss_func or self.model.calculate_loss
+        self.optimizer.zero_grad(set_to_none=True)
+        second_inter = interaction
+        losses = loss_func(interaction)
+        loss = sum(losses) if isinstance(losses, tuple) else losses
+        first = loss.detach()
+        model_has_mirror = bool(getattr(self.model, "mg_enable", False))
+        if not model_has_mirror:
+            if self.mg and batch_idx % self.beta == 0:
+                (self.alpha1 * loss).backward()
+                self.optimizer.step()
+                self.optimizer.zero_grad()
+                losses = loss_func(second_inter)
+                loss = sum(losses) if isinstance(losses, tuple) else losses
+                (-1 * self.alpha2 * loss).backward()
+            else:
+                loss.backward()
+            if self.clip_grad_norm:
+                clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
+            self.optimizer.step()
+            return first
+        loss.backward()
+        if self.clip_grad_norm:
+            clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
+        self.optimizer.step()
+        mg_interval = int(getattr(self.model, "mg_interval", 0))
+        if mg_interval > 0 and int(getattr(self.model, "global_step", 0)) % mg_interval == 0:
+            self._mirror_gradient_step(loss_func, second_inter)
+        return first
+
+    # ---- CUDA-graph replay of the steady-state step ------------------------------------------
+    def _graph_key(self, interaction):
+        m = self.model
+        interval = int(getattr(m, "mg_interval", 0)) if getattr(m, "mg_enable", False) else 0
+        is_mg = bool(interval > 0 and (int(getattr(m, "global_step", 0)) + 1) % interval == 0)
+        return (tuple(interaction.shape), is_mg, int(getattr(m, "graph_version", 0)))
+
+    def _train_batch_graphed(self, interaction, batch_idx=0):
+        """Run `_train_batch` through a captured CUDA graph once the same control-flow variant
+        (batch shape, mirror-gradient or plain step, adjacency version) has been seen
+        `graph_warmup` times; the first executions and ragged batches run eagerly."""
+        key = self._graph_key(interaction)
+        ent = self._graphs.get(key)
+        if ent is None:
+            stale = [k for k in self._graphs if k[2] != key[2]]
+            for k in stale:
+                del self._graphs[k]
+            ent = self._graphs[key] = {"seen": 0, "graph": None}
+        if ent["graph"] is None:
+            if ent["seen"] < self.graph_warmup:
+                ent["seen"] += 1
+                return self._train_batch(interaction, batch_idx)
+            if hasattr(self.optimizer, "sync_lr"):
+                self.optimizer.sync_lr()
+            static_in = interaction.clone()
+            gs0 = int(getattr(self.model, "global_step", 0))
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._train_batch(static_in, batch_idx)
+            ent.update(graph=g, static_in=static_in, static_out=static_out,
+                       step_delta=int(getattr(self.model, "global_step", 0)) - gs0)
+            if ent["step_delta"]:
+                self.model.global_step = gs0       # capture ran no kernels; the replay below does
+        return self._replay(ent, interaction)
+
+    def _replay(self, ent, interaction):
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()
+        ent["static_in"].copy_(interaction, non_blocking=True)
+        ent["graph"].replay()
+        if ent["step_delta"]:
+            self.model.global_step += ent["step_delta"]
+        return ent["static_out"].clone()
 
     def _train_epoch(self, train_data, epoch_idx, loss_func=None):
         """trainer.py:145-356."""
@@ -224,43 +315,19 @@ class Trainer:
         loss_func = loss_func or self.model.calculate_loss
         total_loss = None
         loss_batches = []
+        graphed = self.use_cuda_graph and loss_func == self.model.calculate_loss
         for batch_idx, interaction in enumerate(train_data):
-            self.optimizer.zero_grad(set_to_none=True)
-            second_inter = interaction.clone()
-            losses = loss_func(interaction)
-            loss = sum(losses) if isinstance(losses, tuple) else losses
+            loss = self._train_batch_graphed(interaction, batch_idx) if graphed \
+                else self._train_batch(interaction, batch_idx, loss_func)
             if self.sync_free:
-                total_loss = loss.detach().clone() if total_loss is None else total_loss + loss.detach()
+                total_loss = loss.clone() if total_loss is None else total_loss + loss
             else:
                 total_loss = loss.item() if total_loss is None else total_loss + loss.item()
                 if torch.isnan(loss):
                     self.logger.info("Loss is nan at epoch: {}, batch index: {}. Exiting.".format(
                         epoch_idx, batch_idx))
                     return loss, torch.tensor(0.0)
-            model_has_mirror = bool(getattr(self.model, "mg_enable", False))
-            if not model_has_mirror:
-                if self.mg and batch_idx % self.beta == 0:
-                    (self.alpha1 * loss).backward()
-                    self.optimizer.step()
-                    self.optimizer.zero_grad()
-                    losses = loss_func(second_inter)
-                    loss = sum(losses) if isinstance(losses, tuple) else losses
-                    (-1 * self.alpha2 * loss).backward()
-                else:
-                    loss.backward()
-                if self.clip_grad_norm:
-                    clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
-                self.optimizer.step()
-                loss_batches.append(loss.detach())
-                continue
-            loss.backward()
-            if self.clip_grad_norm:
-                clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
-            self.optimizer.step()
-            loss_batches.append(loss.detach())
-            mg_interval = int(getattr(self.model, "mg_interval", 0))
-            if mg_interval > 0 and int(getattr(self.model, "global_step", 0)) % mg_interval == 0:
-                self._mirror_gradient_step(loss_func, second_inter)
+            loss_batches.append(loss)
         if self.sync_free and total_loss is not None:
             if torch.isnan(total_loss):
                 self.logger.info("Loss is nan at epoch: {}. Exiting.".format(epoch_idx))
