@@ -207,7 +207,7 @@ def run_ours(args):
     batches = take_batches(env["train"], W + K)
     model.train()
     for b in batches[:W]:
-        trainer._train_batch(b)
+        trainer._train_batch_graphed(b)          # eager twice per variant, then captured + replayed
     torch.cuda.synchronize()
 
     def barrier():
@@ -218,14 +218,14 @@ def run_ours(args):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    l0 = lib.launch_count()
+    l0 = lib.launch_count() + trainer.replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for b in batches[W:]:
-        trainer._train_batch(b)
+        trainer._train_batch_graphed(b)
     e1.record()
     barrier()
-    launches = lib.launch_count() - l0
+    launches = lib.launch_count() + trainer.replayed_launches - l0
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     if world > 1:
@@ -241,7 +241,7 @@ def run_ours(args):
     done = 0
     while done < K:
         for b in env["train"]:
-            loss = trainer._train_batch(b, done)
+            loss = trainer._train_batch_graphed(b, done)
             loss.item()
             done += 1
             if done == K:

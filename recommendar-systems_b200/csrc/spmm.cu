@@ -10,8 +10,9 @@
 // the last task to arrive (per-row counter, self-resetting) adds them in part order and runs
 // the fused epilogue -- no floating-point atomics, results are bit-reproducible run to run.
 // Each gathered embedding row is one coalesced 16-byte-per-lane request; column indices and
-// values are loaded once per LANES non-zeros and broadcast with shuffles; eight gathers are kept
-// in flight per lane.
+// values are loaded once per LANES non-zeros and broadcast with shuffles; four gathers are kept
+// in flight per lane and registers are capped so that 6 CTAs (75% occupancy) fit per SM -- the
+// kernel is a chain of dependent L2/DRAM round trips, so resident warps are what hides latency.
 #include "common.cuh"
 
 namespace mmrec {
@@ -57,25 +58,6 @@ __device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t
     }
     const int cnt = min(LANES, end - base);
     int j = 0;
-    for (; j + 8 <= cnt; j += 8) {
-      int cc[8];
-      float vv[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        cc[t] = __shfl_sync(mask, c, j + t, LANES);
-        vv[t] = __shfl_sync(mask, v, j + t, LANES);
-      }
-      float4 x[8][CHUNKS];
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-#pragma unroll
-        for (int q = 0; q < CHUNKS; ++q)
-          x[t][q] = ldg4(X + (size_t)cc[t] * d + (q * LANES + lane) * 4);
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-#pragma unroll
-        for (int q = 0; q < CHUNKS; ++q) fma4(acc[q], vv[t], x[t][q]);
-    }
     for (; j + 4 <= cnt; j += 4) {
       int cc[4];
       float vv[4];
@@ -165,7 +147,7 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[CHUNKS], int row, int l
 constexpr int kSeg = 64;  // non-zeros per task; must match graph.py SEG
 
 template <int LANES, int CHUNKS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 6 : 3)
 spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                 const float *__restrict__ vals, const int4 *__restrict__ tasks, int n_tasks,
                 const int32_t *__restrict__ slot_base, int32_t *__restrict__ counters,
@@ -180,6 +162,12 @@ spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__
   float4 acc[CHUNKS];
 #pragma unroll
   for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (task.w < 0) {
+    // start fetching the epilogue operands of this row while the gathers are in flight
+    const size_t o = (size_t)row * d + lane * 4;
+    if (ep.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.acc_in + o));
+    if (ep.cos_ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.cos_ref + o));
+  }
   gather_rows<LANES, CHUNKS>(acc, col_idx, vals, task.y, task.z, LANES, lane, X, d, col_offset);
   if (task.w >= 0) {
     // heavy row: publish this part, the last arriver reduces all parts in order

@@ -171,6 +171,7 @@ class Trainer:
             hasattr(self.optimizer, "lr_tensor") and not self.clip_grad_norm and not self.mg
         self.graph_warmup = int(config.get("graph_warmup", 2))
         self._graphs = {}
+        self.replayed_launches = 0
 
     def _build_optimizer(self):
         """trainer.py:126-143."""
@@ -290,9 +291,12 @@ class Trainer:
             gs0 = int(getattr(self.model, "global_step", 0))
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            from . import lib
+            l0 = lib.launch_count()
             with torch.cuda.graph(g):
                 static_out = self._train_batch(static_in, batch_idx)
             ent.update(graph=g, static_in=static_in, static_out=static_out,
+                       launches=lib.launch_count() - l0,
                        step_delta=int(getattr(self.model, "global_step", 0)) - gs0)
             if ent["step_delta"]:
                 self.model.global_step = gs0       # capture ran no kernels; the replay below does
@@ -303,6 +307,7 @@ class Trainer:
             self.optimizer.sync_lr()
         ent["static_in"].copy_(interaction, non_blocking=True)
         ent["graph"].replay()
+        self.replayed_launches += ent["launches"]     # library kernels inside the replayed graph
         if ent["step_delta"]:
             self.model.global_step += ent["step_delta"]
         return ent["static_out"].clone()

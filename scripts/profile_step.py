@@ -14,15 +14,15 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 env = bench.build_env("cuda:0", model_name=model_name,
                       overrides={} if model_name in ("SMORE", "MGCN", "FREEDOM") else {"is_multimodal_model": False})
 trainer = bench.pkg("trainer").Trainer(env["config"], env["model"])
-batches = bench.take_batches(env["train"], 5 + steps)
+batches = bench.take_batches(env["train"], 8 + steps)
 env["model"].train()
 env["model"].pre_epoch_processing()
-for b in batches[:5]:
-    trainer._train_batch(b)
+for b in batches[:8]:
+    trainer._train_batch_graphed(b)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for b in batches[5:]:
-        trainer._train_batch(b)
+    for b in batches[8:]:
+        trainer._train_batch_graphed(b)
     torch.cuda.synchronize()
 ka = prof.key_averages()
 rows = sorted([(e.device_time_total, e.count, e.key) for e in ka if e.device_time_total > 0 and e.device_type.name == "CUDA"],
