@@ -1,0 +1,178 @@
+"""Multi-GPU paths that shard naturally. One process per GPU,
+torch.distributed (NCCL over NVLink/NVSwitch on the B200 box, gloo in the CPU tests).
+
+* Propagation: nodes are cut into P contiguous row ranges balanced by non-zeros; rank p owns the
+  CSR rows of its range (all columns) and computes those rows of every layer; one all-gather per
+  layer rebuilds the full embedding table. Ranges have different lengths, so nodes are renumbered
+  into a *padded* layout (`pid = owner * R + local`, R = longest range): every rank writes its
+  slice of the next layer in place and `all_gather_into_tensor` needs no packing or compaction;
+  the local CSR's column indices are rewritten to padded ids once.
+  Backward (training with replicated loss): the same loop on the gradient (A_hat symmetric).
+* Evaluation: items are cut into P equal ranges; every rank runs the fused score + mask + top-K
+  kernel on its item slice (global ids via `item_offset`), the [n, K] (score, id) lists are
+  all-gathered and merged with `mmrec_topk_merge` (same tie rule: lower id first).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import graph as G
+from . import ops
+
+
+def partition_by_nnz(row_ptr_host: np.ndarray, world: int) -> np.ndarray:
+    """Row boundaries b[0..world] with ~equal (nnz + rows) per part. row_ptr_host: int64 [n+1]."""
+    n = len(row_ptr_host) - 1
+    cost = row_ptr_host.astype(np.int64) + np.arange(n + 1, dtype=np.int64)   # nnz + one unit per row
+    targets = cost[-1] * np.arange(1, world, dtype=np.float64) / world
+    cuts = np.searchsorted(cost, targets, side="left")
+    b = np.concatenate(([0], cuts, [n])).astype(np.int64)
+    return np.maximum.accumulate(b)
+
+
+class PaddedLayout:
+    """Node id <-> padded id for row ranges of unequal length."""
+
+    def __init__(self, bounds: np.ndarray):
+        self.bounds = np.asarray(bounds, dtype=np.int64)
+        self.world = len(self.bounds) - 1
+        self.sizes = np.diff(self.bounds)
+        self.R = int(max(1, self.sizes.max()))
+        self.n = int(self.bounds[-1])
+
+    def to_padded(self, ids: torch.Tensor) -> torch.Tensor:
+        b = torch.as_tensor(self.bounds, device=ids.device)
+        owner = torch.searchsorted(b, ids.to(torch.int64), right=True) - 1
+        return owner * self.R + (ids.to(torch.int64) - b[owner])
+
+    def pad(self, X: torch.Tensor) -> torch.Tensor:
+        """[n, d] -> [world * R, d] (rows of rank p at p*R...)."""
+        out = X.new_zeros(self.world * self.R, X.shape[1])
+        for p in range(self.world):
+            lo, hi = int(self.bounds[p]), int(self.bounds[p + 1])
+            out[p * self.R: p * self.R + hi - lo] = X[lo:hi]
+        return out
+
+    def unpad(self, Xp: torch.Tensor) -> torch.Tensor:
+        parts = [Xp[p * self.R: p * self.R + int(self.sizes[p])] for p in range(self.world)]
+        return torch.cat(parts, dim=0)
+
+
+class ShardedUIGraph:
+    """This rank's row slice of a (symmetric) CSRGraph in the padded numbering."""
+
+    def __init__(self, full: G.CSRGraph, rank: int, world: int, bounds=None):
+        rp = full.row_ptr.cpu().numpy().astype(np.int64)
+        self.layout = PaddedLayout(partition_by_nnz(rp, world) if bounds is None else bounds)
+        self.rank, self.world = rank, world
+        lo, hi = int(self.layout.bounds[rank]), int(self.layout.bounds[rank + 1])
+        self.lo, self.hi = lo, hi
+        a, b = int(rp[lo]), int(rp[hi])
+        row_ptr = (full.row_ptr[lo: hi + 1] - a).contiguous()
+        col = self.layout.to_padded(full.col_idx[a:b]).to(torch.int32).contiguous()
+        vals = full.vals[a:b].contiguous()
+        self.local = G.CSRGraph(row_ptr, col, vals, hi - lo, self.layout.world * self.layout.R)
+        self.local.t = self.local          # A_hat symmetric: the backward uses the same rows
+
+    @property
+    def n_local(self):
+        return self.hi - self.lo
+
+
+def _all_gather_rows(buf: torch.Tensor, rank: int, R: int, group=None):
+    """In-place all-gather of the [R, d] slices of `buf` ([world * R, d])."""
+    dist.all_gather_into_tensor(buf, buf[rank * R: (rank + 1) * R], group=group)
+
+
+def _local_spmm(sg, x_pad, y_slice, acc_in, acc_out, scale):
+    ops.spmm_raw(sg.local, x_pad, Y=y_slice, acc_in=acc_in, acc_out=acc_out, acc_scale=scale)
+
+
+def _propagate_padded(sg: ShardedUIGraph, x0_pad, n_layers, scale_last, acc0, group=None,
+                      local_spmm=_local_spmm):
+    """acc <- (acc0 + sum_{l=1..L} A^l x0) * scale_last on the padded layout. acc0 is the local
+    [n_local, d] slice to start the running sum from (x0's own rows for the forward mean, the
+    gradient for the backward Horner chain... see callers). Returns the full padded result."""
+    R, rank, nl = sg.layout.R, sg.rank, sg.n_local
+    x = x0_pad
+    acc = torch.zeros(R, x0_pad.shape[1], dtype=x0_pad.dtype, device=x0_pad.device)
+    for l in range(1, n_layers + 1):
+        last = l == n_layers
+        nxt = None
+        y_slice = None
+        if not last:
+            nxt = torch.zeros_like(x0_pad)
+            y_slice = nxt[rank * R: rank * R + nl]
+        local_spmm(sg, x, y_slice, acc0 if l == 1 else acc[:nl], acc[:nl], scale_last if last else 1.0)
+        if not last:
+            _all_gather_rows(nxt, rank, R, group)
+            x = nxt
+    out = torch.zeros_like(x0_pad)
+    out[rank * R: rank * R + nl] = acc[:nl]
+    _all_gather_rows(out, rank, R, group)
+    return out
+
+
+class _ShardedPropagateMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X0, sg, n_layers, group, local_spmm):
+        ctx.sg, ctx.n_layers, ctx.group, ctx.local_spmm = sg, n_layers, group, local_spmm
+        if n_layers == 0:
+            return X0.clone()
+        x0_pad = sg.layout.pad(X0.contiguous())
+        own = x0_pad[sg.rank * sg.layout.R: sg.rank * sg.layout.R + sg.n_local]
+        out = _propagate_padded(sg, x0_pad, n_layers, 1.0 / (n_layers + 1), own, group, local_spmm)
+        return sg.layout.unpad(out)
+
+    @staticmethod
+    def backward(ctx, dOut):
+        sg, L = ctx.sg, ctx.n_layers
+        if L == 0:
+            return dOut, None, None, None, None
+        # replicated loss: dOut is identical on every rank. Horner: t <- g + A t, L times.
+        g_pad = sg.layout.pad(dOut.contiguous())
+        R, rank, nl = sg.layout.R, sg.rank, sg.n_local
+        own = g_pad[rank * R: rank * R + nl]
+        t = g_pad
+        for l in range(L):
+            nxt = torch.zeros_like(g_pad)
+            ctx.local_spmm(sg, t, None, own, nxt[rank * R: rank * R + nl], 1.0 / (L + 1) if l == L - 1 else 1.0)
+            _all_gather_rows(nxt, rank, R, ctx.group)
+            t = nxt
+        return sg.layout.unpad(t), None, None, None, None
+
+
+def sharded_propagate_mean(sg: ShardedUIGraph, X0, n_layers, group=None, local_spmm=_local_spmm):
+    """mean_{l=0..L} A^l X0 with rows sharded over the process group; every rank passes the full
+    X0 [n, d] and gets the full result."""
+    return _ShardedPropagateMean.apply(X0, sg, n_layers, group, local_spmm)
+
+
+def item_range(n_items: int, rank: int, world: int):
+    per = -(-n_items // world)
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+@torch.no_grad()
+def sharded_score_topk(user_emb, users, item_emb_local, item_lo, k, mask_rowptr=None, mask_cols=None,
+                       group=None, local_topk=None, merge=None):
+    """Item-sharded full-rank top-K: local fused top-K on this rank's item slice, all-gather of the
+    (score, id) lists, K-way merge. Every rank returns the same ids int64 [n, k]."""
+    world = dist.get_world_size(group)
+    if local_topk is None:
+        ids, vals = ops.score_mask_topk(user_emb, users, item_emb_local, k, mask_rowptr, mask_cols,
+                                        item_offset=item_lo, return_scores=True)
+    else:
+        ids, vals = local_topk(user_emb, users, item_emb_local, item_lo, k, mask_rowptr, mask_cols)
+    n = users.numel()
+    all_v = torch.empty(world * n, k, dtype=torch.float32, device=vals.device)
+    all_i = torch.empty(world * n, k, dtype=torch.int32, device=vals.device)
+    dist.all_gather_into_tensor(all_v, vals.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, ids.to(torch.int32).contiguous(), group=group)
+    all_v, all_i = all_v.view(world, n, k), all_i.view(world, n, k)
+    if merge is None:
+        return ops.topk_merge(all_v, all_i)[0]
+    return merge(all_v, all_i)

@@ -414,3 +414,48 @@ def test_cpu_tensors_are_rejected():
     G = pkg("graph")
     with pytest.raises(RuntimeError):
         G.build_ui_graph(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 2, 2, "f32")
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        G, ops, par, synth = pkg("graph"), pkg("ops"), pkg("parallel"), pkg("synth")
+        from conftest import TINY
+        data = synth.make_dataset("small", features=False)
+        u, i = data.split(0)
+        U, I = data.n_users, data.n_items
+        full = G.build_ui_graph(torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev), U, I, "f32")
+        sg = par.ShardedUIGraph(full, rank, world)
+        X = torch.randn(U + I, 64, generator=torch.Generator().manual_seed(1)).to(dev)
+        Xa, Xb = X.clone().requires_grad_(True), X.clone().requires_grad_(True)
+        want = ops.propagate_mean(full, Xa, 3)
+        got = par.sharded_propagate_mean(sg, Xb, 3)
+        assert rel(got, want) < 1e-6
+        W = torch.randn(U + I, 64, generator=torch.Generator().manual_seed(2)).to(dev)
+        (want * W).sum().backward()
+        (got * W).sum().backward()
+        assert rel(Xb.grad, Xa.grad) < 1e-6
+        users = torch.arange(0, U, 3, device=dev)
+        lo, hi = par.item_range(I, rank, world)
+        one = ops.score_mask_topk(want[:U].detach(), users, want[U:].detach().contiguous(), 50)
+        many = par.sharded_score_topk(want[:U].detach(), users, want[U + lo: U + hi].detach().contiguous(), lo, 50)
+        assert torch.equal(one, many)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_paths_nccl(tmp_path):
+    """Row-sharded propagation (+backward) and item-sharded top-K over NCCL == single GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(2))
