@@ -221,6 +221,21 @@ int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *users, int32
 int mmrec_topk_merge(const float *vals, const int32_t *idx, int32_t n_lists, int32_t n_users,
                      int32_t k, float *out_val, int64_t *out_idx, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Negative sampling (host side of the [3, B] training batch). Replaces the Python
+ * loop of TrainDataLoader._sample_neg_ids / _random (utils/dataloader.py:267-275, 307-309):
+ *   iid = random.sample(all_items, 1)[0]; while iid in history_items_per_u[u]: redraw
+ * with a bit-exact replay of CPython's Mersenne Twister (random.sample(list, 1) ==
+ * list[_randbelow(len)], _randbelow = getrandbits(n.bit_length()) with rejection).
+ * ALL pointers are HOST pointers. mt_state_host holds random.getstate()[1] (624 words + the
+ * position) and is advanced in place; the caller writes it back with random.setstate().
+ * hist_rowptr/hist_cols: per-user CSR of training items, ascending inside a user.
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_neg_sample_mt19937_host(uint32_t *mt_state_host, const int64_t *all_items_host,
+                                  int64_t n_items, const int64_t *hist_rowptr_host,
+                                  const int64_t *hist_cols_host, int64_t n_hist_users,
+                                  const int64_t *users_host, int64_t n, int64_t *neg_out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,13 @@ class TrainDataLoader(AbstractDataLoader):
         self.history_items_per_u = {
             int(g[0]): set(h.tolist())
             for g, h in zip(np.split(su, bounds), np.split(si, bounds))}
+        # the same history as a per-user CSR (ascending inside a user) for the native sampler
+        o2 = np.lexsort((dataset.items, dataset.users))
+        self._hist_cols = np.ascontiguousarray(dataset.items[o2], dtype=np.int64)
+        self._hist_rowptr = np.zeros(dataset.user_num + 1, dtype=np.int64)
+        np.cumsum(np.bincount(dataset.users, minlength=dataset.user_num), out=self._hist_rowptr[1:])
+        self._items_arr = None
+        self.native_sampler = bool(config.get("native_sampler", True))
 
     def pretrain_setup(self):
         """dataloader.py:140-151: restore file order, sort items, then random.shuffle them."""
@@ -141,6 +148,7 @@ class TrainDataLoader(AbstractDataLoader):
             self.dataset = self.dataset_bk.copy(self.dataset_bk.users, self.dataset_bk.items)
         self.all_items.sort()
         random.shuffle(self.all_items)
+        self._items_arr = None
 
     def inter_matrix(self, form="coo", value_field=None):
         """dataloader.py:155-210: scipy COO U x I with float64 ones."""
@@ -160,6 +168,22 @@ class TrainDataLoader(AbstractDataLoader):
     def _shuffle(self):
         self.dataset.shuffle()
 
+    def _sample_neg_ids_native(self, u):
+        """Same draws as `_sample_neg_ids`, replayed in C on CPython's Mersenne Twister state
+        (mmrec_neg_sample_mt19937_host); the advanced state is written back to `random`."""
+        from . import lib
+        if self._items_arr is None or len(self._items_arr) != len(self.all_items):
+            self._items_arr = np.asarray(self.all_items, dtype=np.int64)
+        ver, mt, gauss = random.getstate()
+        st = np.array(mt, dtype=np.uint32)
+        u = np.ascontiguousarray(u, dtype=np.int64)
+        neg = np.empty(len(u), dtype=np.int64)
+        lib.call("mmrec_neg_sample_mt19937_host", st.ctypes.data, self._items_arr.ctypes.data,
+                 len(self._items_arr), self._hist_rowptr.ctypes.data, self._hist_cols.ctypes.data,
+                 len(self._hist_rowptr) - 1, u.ctypes.data, len(u), neg.ctypes.data)
+        random.setstate((ver, tuple(st.tolist()), gauss))
+        return neg
+
     def _sample_neg_ids(self, u_ids):
         """dataloader.py:267-275 + 307-309, same `random` call per draw."""
         neg = []
@@ -177,7 +201,10 @@ class TrainDataLoader(AbstractDataLoader):
         u = self.dataset.users[self.pr: self.pr + self.step]
         i = self.dataset.items[self.pr: self.pr + self.step]
         self.pr += self.step
-        neg = np.asarray(self._sample_neg_ids(u.tolist()), dtype=np.int64)
+        if self.native_sampler:
+            neg = self._sample_neg_ids_native(u)
+        else:
+            neg = np.asarray(self._sample_neg_ids(u.tolist()), dtype=np.int64)
         batch = torch.from_numpy(np.stack([u, i, neg]))
         if self.device.type == "cuda":
             batch = batch.pin_memory().to(self.device, non_blocking=True)

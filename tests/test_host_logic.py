@@ -49,6 +49,51 @@ def test_negatives_never_in_history():
         assert all(n not in train.history_items_per_u[x] for x, n in zip(u, neg))
 
 
+def test_native_sampler_replays_cpython_random():
+    """mmrec_neg_sample_mt19937_host draws the same negatives as random.sample(all_items, 1)[0]
+    with history rejection and leaves Python's global Mersenne Twister in the same state."""
+    import random
+    config, data, train, valid, test = _env()
+    for seed in (999, 7):
+        pkg("config").init_seed(seed)
+        train.pretrain_setup()
+        st = random.getstate()
+        users = train.dataset.users[:1500]
+        want = train._sample_neg_ids(users.tolist())
+        after_py = random.getstate()
+        random.setstate(st)
+        got = train._sample_neg_ids_native(users)
+        assert got.tolist() == want
+        assert random.getstate() == after_py
+        assert random.random() == (random.setstate(after_py) or random.random())
+    # tiny item universes exercise the rejection loop of _randbelow (n not a power of two)
+    L = pkg("lib")
+    items = np.array([5, 3, 9], dtype=np.int64)
+    rowptr = np.array([0, 1, 1], dtype=np.int64)
+    cols = np.array([3], dtype=np.int64)
+    u = np.array([0, 1] * 200, dtype=np.int64)
+    random.seed(11)
+    st = random.getstate()
+    ref = []
+    for x in u.tolist():
+        iid = random.sample(items.tolist(), 1)[0]
+        while x == 0 and iid == 3:
+            iid = random.sample(items.tolist(), 1)[0]
+        ref.append(iid)
+    mt = np.array(st[1], dtype=np.uint32)
+    out = np.empty(len(u), dtype=np.int64)
+    L.call("mmrec_neg_sample_mt19937_host", mt.ctypes.data, items.ctypes.data, 3, rowptr.ctypes.data,
+           cols.ctypes.data, 2, u.ctypes.data, len(u), out.ctypes.data)
+    assert out.tolist() == ref
+    assert tuple(mt.tolist()) == random.getstate()[1]
+    # error behaviour: a user who has seen everything cannot be sampled for
+    full = np.array([0, 3], dtype=np.int64)
+    with pytest.raises(RuntimeError):
+        L.call("mmrec_neg_sample_mt19937_host", mt.ctypes.data, items.ctypes.data, 3, full.ctypes.data,
+               np.array([3, 5, 9], dtype=np.int64).ctypes.data, 1, np.zeros(1, np.int64).ctypes.data, 1,
+               out.ctypes.data)
+
+
 def test_eval_loader_matches_reference():
     g = golden("tiny_lightgcn")
     config, data, train, valid, test = _env()
