@@ -216,6 +216,14 @@ int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *users, int32
                               int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,
                               int32_t k, int32_t n_splits, float *ws_val, int32_t *ws_idx,
                               float *out_val, int64_t *out_idx, void *stream);
+/* The same contract on the CUDA-core (fp32 FMA) kernel: d = 128, K too large for the tensor-core
+ * tiling, and the A/B baseline of bench.py. mmrec_score_mask_topk_f32 runs the tcgen05 kernel
+ * (3xTF32 split, fp32-accurate) for d = 32 / 64 and this one otherwise. */
+int mmrec_score_mask_topk_simt_f32(const float *user_emb, const int64_t *users, int32_t n_users,
+                                   const float *item_emb, int32_t n_items, int32_t item_offset,
+                                   int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,
+                                   int32_t k, int32_t n_splits, float *ws_val, int32_t *ws_idx,
+                                   float *out_val, int64_t *out_idx, void *stream);
 /* K-way merge of `n_lists` descending lists per user (local top-K of every rank after the
  * all-gather). Same tie rule. lists are [n_lists, n_users, k]. */
 int mmrec_topk_merge(const float *vals, const int32_t *idx, int32_t n_lists, int32_t n_users,

@@ -161,6 +161,11 @@ int launch_score(const float *user_emb, const int64_t *users, int n_users, const
 }
 
 }  // namespace
+
+int score_topk_tc_dispatch(const float *user_emb, const int64_t *users, int n_users, const float *item_emb,
+                           int n_items, int item_offset, int d, const int32_t *mask_rowptr,
+                           const int32_t *mask_cols, int k, int n_splits, float *ws_val, int32_t *ws_idx,
+                           cudaStream_t stream);   // score_topk_tc.cu
 }  // namespace mmrec
 
 using namespace mmrec;
@@ -176,11 +181,11 @@ extern "C" int mmrec_topk_merge(const float *vals, const int32_t *idx, int32_t n
   return MMREC_OK;
 }
 
-extern "C" int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *users, int32_t n_users,
-                                         const float *item_emb, int32_t n_items, int32_t item_offset, int32_t d,
-                                         const int32_t *mask_rowptr, const int32_t *mask_cols, int32_t k,
-                                         int32_t n_splits, float *ws_val, int32_t *ws_idx, float *out_val,
-                                         int64_t *out_idx, void *stream_) {
+static int score_mask_topk(bool allow_tc, const float *user_emb, const int64_t *users, int32_t n_users,
+                           const float *item_emb, int32_t n_items, int32_t item_offset, int32_t d,
+                           const int32_t *mask_rowptr, const int32_t *mask_cols, int32_t k,
+                           int32_t n_splits, float *ws_val, int32_t *ws_idx, float *out_val,
+                           int64_t *out_idx, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MMREC_REQUIRE(user_emb && users && item_emb && ws_val && ws_idx && out_idx, MMREC_E_BADARG,
                 "score_mask_topk: null pointer");
@@ -190,8 +195,12 @@ extern "C" int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *u
   MMREC_REQUIRE(n_splits >= 1 && n_splits <= kMaxLists, MMREC_E_BADARG, "score_mask_topk: bad n_splits");
   MMREC_REQUIRE(aligned16(user_emb) && aligned16(item_emb), MMREC_E_ALIGN,
                 "score_mask_topk: tables must be 16-byte aligned");
-  int rc;
-  switch (d) {
+  int rc = 1;
+  if (allow_tc)      // tcgen05 path (d = 32 / 64); 1 = not covered -> SIMT kernel below
+    rc = score_topk_tc_dispatch(user_emb, users, n_users, item_emb, n_items, item_offset, d, mask_rowptr, mask_cols,
+                                k, n_splits, ws_val, ws_idx, stream);
+  if (rc < 0) return rc;
+  if (rc == 1) switch (d) {
     case 32: rc = launch_score<32>(user_emb, users, n_users, item_emb, n_items, item_offset, mask_rowptr, mask_cols,
                                    k, n_splits, ws_val, ws_idx, stream); break;
     case 64: rc = launch_score<64>(user_emb, users, n_users, item_emb, n_items, item_offset, mask_rowptr, mask_cols,
@@ -204,4 +213,22 @@ extern "C" int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *u
   }
   if (rc != MMREC_OK) return rc;
   return mmrec_topk_merge(ws_val, ws_idx, n_splits, n_users, k, out_val, out_idx, stream);
+}
+
+extern "C" int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *users, int32_t n_users,
+                                         const float *item_emb, int32_t n_items, int32_t item_offset, int32_t d,
+                                         const int32_t *mask_rowptr, const int32_t *mask_cols, int32_t k,
+                                         int32_t n_splits, float *ws_val, int32_t *ws_idx, float *out_val,
+                                         int64_t *out_idx, void *stream) {
+  return score_mask_topk(true, user_emb, users, n_users, item_emb, n_items, item_offset, d, mask_rowptr, mask_cols, k,
+                         n_splits, ws_val, ws_idx, out_val, out_idx, stream);
+}
+
+extern "C" int mmrec_score_mask_topk_simt_f32(const float *user_emb, const int64_t *users, int32_t n_users,
+                                              const float *item_emb, int32_t n_items, int32_t item_offset,
+                                              int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,
+                                              int32_t k, int32_t n_splits, float *ws_val, int32_t *ws_idx,
+                                              float *out_val, int64_t *out_idx, void *stream) {
+  return score_mask_topk(false, user_emb, users, n_users, item_emb, n_items, item_offset, d, mask_rowptr, mask_cols,
+                         k, n_splits, ws_val, ws_idx, out_val, out_idx, stream);
 }

@@ -364,14 +364,16 @@ class Linear(torch.nn.Linear):
 
 # -------------------------------------------------------------------------------- score + top-K
 def choose_splits(n_users, n_items):
+    """Item-range splits so that (user tiles x splits) is close to one wave of 148 CTAs (the
+    tensor-core kernel runs one 128-user CTA per SM); never fewer than 256 items per split."""
     tiles = (n_users + 127) // 128
-    want = max(1, (2 * 148 + tiles - 1) // tiles)
-    return int(max(1, min(want, 16, (n_items + 255) // 256)))
+    want = max(1, 148 // tiles)
+    return int(max(1, min(want, 32, (n_items + 255) // 256)))
 
 
 @torch.no_grad()
 def score_mask_topk(user_emb, users, item_emb, k, mask_rowptr=None, mask_cols=None, item_offset=0,
-                    n_splits=None, return_scores=False, merge=True):
+                    n_splits=None, return_scores=False, merge=True, simt=False):
     """Fused `u @ item_e.T` + `scores[mask] = -1e10` + top-K (smore.py:421 / trainer.py:522-526).
     Returns ids int64 [n_users, k] (+ scores). With merge=False returns the per-split partial
     lists (vals [S, n, k], ids int32 [S, n, k]) for a cross-rank merge."""
@@ -384,7 +386,8 @@ def score_mask_topk(user_emb, users, item_emb, k, mask_rowptr=None, mask_cols=No
     ws_idx = torch.empty(S, n, k, dtype=torch.int32, device=dev)
     out_val = torch.empty(n, k, dtype=torch.float32, device=dev)
     out_idx = torch.empty(n, k, dtype=torch.int64, device=dev)
-    lib.call("mmrec_score_mask_topk_f32", lib.ptr(user_emb), lib.ptr(users), n, lib.ptr(item_emb),
+    lib.call("mmrec_score_mask_topk_simt_f32" if simt else "mmrec_score_mask_topk_f32",
+             lib.ptr(user_emb), lib.ptr(users), n, lib.ptr(item_emb),
              n_items, item_offset, d, lib.ptr(mask_rowptr), lib.ptr(mask_cols), k, S,
              lib.ptr(ws_val), lib.ptr(ws_idx), lib.ptr(out_val), lib.ptr(out_idx), lib.stream())
     if not merge:
