@@ -131,8 +131,13 @@ int mmrec_bpr_bwd_f32(const float *user_emb, const float *item_emb, int32_t d,
  * bwd scatter-adds into dT1/dT2 (table-shaped, atomics). coef = dL/dloss (device scalar).
  * The "other" dimension of each backward pass is cut into n_splits ranges (grid.y) so that a
  * 2048-row batch fills 148 SMs; dV1_ws/dV2_ws hold n_splits*batch*d floats of partial sums that
- * the scatter kernel adds in split order. partial (fwd) must hold 16*batch floats.
+ * the scatter kernel adds in split order; mmrec_infonce_splits(batch) is the count that fills
+ * the GPU (4 co-resident CTAs per SM). partial (fwd) must hold
+ * mmrec_infonce_fwd_workspace_floats(batch) floats; counter is an array of 1 + ceil(batch/64)
+ * zero-initialised uint32 (self-resetting); batch <= 65472.
  * ---------------------------------------------------------------------------------------- */
+int32_t mmrec_infonce_splits(int32_t batch);
+size_t mmrec_infonce_fwd_workspace_floats(int32_t batch);
 int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d, const int64_t *idx,
                           int32_t batch, float inv_temp, float *loss_out, float *V1n, float *V2n,
                           float *inv_norm, float *ttl, float *partial, uint32_t *counter,
@@ -181,6 +186,25 @@ int mmrec_gemm_splits(int32_t M, int32_t N, int32_t K, int32_t a_kcontig, int32_
 int mmrec_gemm_tf32x3_f32(const float *A, int32_t a_kcontig, const float *B, int32_t b_kcontig,
                           const float *bias, float *C, int32_t M, int32_t N, int32_t K,
                           int32_t splits, float *ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * d x d dense layers of the modality side networks with fused bias + activation (K4b):
+ * gate_v/gate_t/gate_f, query_v/query_t, gate_*_prefer (smore.py:265-272, 321-330) and the MGCN
+ * gates / query_common (mgcn.py:153-154, 188-203), i.e. nn.Sequential(nn.Linear(d, d), nn.Tanh() |
+ * nn.Sigmoid()) and bare nn.Linear(d, d). X [M,K], W [N,K] row-major, K = N in {32, 64, 128}.
+ *   act: 0 = identity, 1 = tanh, 2 = sigmoid
+ *   fwd: Y = act(X W^T + bias)                         (bias may be NULL)
+ *   bwd: dZ = dY * act'(Y); dX = dZ W (skipped if dX NULL); dW = dZ^T X; db = sum_rows dZ (if db)
+ * Exact fp32 FMA arithmetic. The backward needs mmrec_dense_act_bwd_workspace_bytes of scratch;
+ * per-CTA partial sums of dW/db are added in a fixed order (bit-reproducible).
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_dense_act_supported(int32_t K, int32_t N);
+size_t mmrec_dense_act_bwd_workspace_bytes(int32_t K, int32_t N);
+int mmrec_dense_act_fwd_f32(const float *X, const float *W, const float *bias, float *Y, int32_t M,
+                            int32_t K, int32_t N, int32_t act, void *stream);
+int mmrec_dense_act_bwd_f32(const float *dY, const float *Y, const float *X, const float *W,
+                            float *dX, float *dW, float *db, float *ws, int32_t M, int32_t K,
+                            int32_t N, int32_t act, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam (K13). Replaces optim.Adam.step (common/trainer.py:126-143, 255, 331)

@@ -1,0 +1,390 @@
+// d x d dense layers of the modality side networks, fused with bias + activation (K4b):
+//   forward   Y = act(X W^T + b)                                  one launch
+//   backward  dZ = dY * act'(Y);  dX = dZ W;  dW = dZ^T X;  db = sum_m dZ     one launch + reduce
+// for X [M, K], W [N, K] with K, N in {32, 64, 128} (the embedding width): gate_v/t/f, query_v/t,
+// gate_*_prefer of SMORE (smore.py:265-272, 321-330) and the MGCN gates (mgcn.py:153-154,
+// 188-203). These GEMMs are tall and skinny (M = 7k..60k rows, K = N = 64): 0.2 GFLOP and 14 MB
+// each, so the exact fp32 FMA pipe finishes them in the time HBM needs to stream X and Y; what
+// matters is one pass over the operands and no intermediate tensors, not tensor cores.
+//
+// Tiling: 256 threads = (256 / (N/4)) row groups x (N/4) column groups; a thread owns TM rows x 4
+// columns. X tiles are staged row-major in shared memory (pitch K+4, conflict-free float4 reads:
+// a warp touches at most 4 rows, 4 banks apart), W is staged once per CTA k-major so that the 4
+// output columns of a thread are one float4. The backward shares the dZ / X tiles between the
+// dX product and the dW outer-product accumulation; per-CTA dW / db partials are summed by a
+// second small kernel in a fixed order (no floating-point atomics: bit-reproducible). Grids are
+// sized so that the whole layer is one wave of 3 CTAs per SM (64-row tiles): loads of one CTA
+// overlap the FMA loop of its neighbours.
+#include "common.cuh"
+
+namespace mmrec {
+namespace {
+
+constexpr int kT = 256;
+
+enum Act { kNone = 0, kTanh = 1, kSigmoid = 2 };
+
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float z) {
+  if constexpr (ACT == kTanh) return tanhf(z);
+  if constexpr (ACT == kSigmoid) return 1.f / (1.f + expf(-z));
+  return z;
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd(float dy, float y) {
+  if constexpr (ACT == kTanh) return dy * (1.f - y * y);
+  if constexpr (ACT == kSigmoid) return dy * ((1.f - y) * y);
+  return dy;
+}
+
+template <int K, int N, int TM>
+struct Tile {
+  static constexpr int CG = N / 4;          // column groups (4 output columns each)
+  static constexpr int RG = kT / CG;        // row groups
+  static constexpr int BM = RG * TM;        // rows per tile
+  static constexpr int XP = K + 4;          // pitch of a staged X row (floats)
+};
+
+// Rows [m0, m0+BM) of a row-major [M, C] array on their way to shared memory (pitch C+4; rows
+// >= M are zero), in two phases: load() puts every global load of the thread in flight, store()
+// parks the values. Whatever sits between the two (the W staging of the first tile) overlaps the
+// DRAM round trip instead of adding one.
+template <int C, int BM>
+struct RowStage {
+  static constexpr int V = C / 4, PER = BM * V / kT;
+  static_assert(BM * V % kT == 0, "tile must be a multiple of the CTA");
+  float4 v[PER];
+  __device__ __forceinline__ void load(const float *__restrict__ src, int m0, int M) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + i * kT, r = idx / V, c4 = idx % V;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M) v[i] = ldg4(src + (size_t)(m0 + r) * C + c4 * 4);
+    }
+  }
+  __device__ __forceinline__ void store(float *dst) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + i * kT, r = idx / V, c4 = idx % V;
+      *reinterpret_cast<float4 *>(dst + r * (C + 4) + c4 * 4) = v[i];
+    }
+  }
+};
+
+// acc[i][0..3] += sum_k A[row_i][k] * B[k][c0..c0+3]; A staged with pitch KK+4, B k-major pitch NB
+template <int KK, int TM, int RG, int NB>
+__device__ __forceinline__ void tile_mma(float (&acc)[TM][4], const float *__restrict__ As, int rg,
+                                         const float *__restrict__ Bs, int c0) {
+#pragma unroll 4
+  for (int k4 = 0; k4 < KK / 4; ++k4) {
+    float4 a[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+      a[i] = *reinterpret_cast<const float4 *>(As + (rg + RG * i) * (KK + 4) + k4 * 4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 b = *reinterpret_cast<const float4 *>(Bs + (k4 * 4 + kk) * NB + c0);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+        acc[i][0] = fmaf(av, b.x, acc[i][0]);
+        acc[i][1] = fmaf(av, b.y, acc[i][1]);
+        acc[i][2] = fmaf(av, b.z, acc[i][2]);
+        acc[i][3] = fmaf(av, b.w, acc[i][3]);
+      }
+    }
+  }
+}
+
+template <int K, int N, int TM, int ACT>
+__global__ void __launch_bounds__(kT, K <= 64 ? 3 : 2)
+dense_fwd_kernel(const float *__restrict__ X, const float *__restrict__ W, const float *__restrict__ bias,
+                 float *__restrict__ Y, int M, int n_tiles) {
+  using T = Tile<K, N, TM>;
+  extern __shared__ float4 smem4[];
+  float *Ws = reinterpret_cast<float *>(smem4);      // [K][N]   Ws[k][n] = W[n][k]
+  float *Xs = Ws + K * N;                            // [BM][K+4]
+  const int cg = threadIdx.x % T::CG, rg = threadIdx.x / T::CG, c0 = cg * 4;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias != nullptr) bv = ldg4(bias + c0);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int m0 = tile * T::BM;
+    RowStage<K, T::BM> xs;
+    xs.load(X, m0, M);
+    if (tile == (int)blockIdx.x) {
+      // first tile: transpose W into shared memory while the X rows are in flight
+      constexpr int WPER = N * (K / 4) / kT;
+      float4 w[WPER];
+#pragma unroll
+      for (int i = 0; i < WPER; ++i) {
+        const int idx = threadIdx.x + i * kT, n = idx % N, k4 = idx / N;
+        w[i] = ldg4(W + (size_t)n * K + k4 * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < WPER; ++i) {
+        const int idx = threadIdx.x + i * kT, n = idx % N, k4 = idx / N;
+        Ws[(k4 * 4 + 0) * N + n] = w[i].x;
+        Ws[(k4 * 4 + 1) * N + n] = w[i].y;
+        Ws[(k4 * 4 + 2) * N + n] = w[i].z;
+        Ws[(k4 * 4 + 3) * N + n] = w[i].w;
+      }
+    } else {
+      __syncthreads();                               // previous tile fully consumed
+    }
+    xs.store(Xs);
+    __syncthreads();
+    float acc[TM][4];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
+    tile_mma<K, TM, T::RG, N>(acc, Xs, rg, Ws, c0);
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = m0 + rg + T::RG * i;
+      if (m < M) {
+        float4 y;
+        y.x = act_fwd<ACT>(acc[i][0]); y.y = act_fwd<ACT>(acc[i][1]);
+        y.z = act_fwd<ACT>(acc[i][2]); y.w = act_fwd<ACT>(acc[i][3]);
+        *reinterpret_cast<float4 *>(Y + (size_t)m * N + c0) = y;
+      }
+    }
+  }
+}
+
+// Backward. partial layout per CTA: [N*K] dW then [N] db.
+template <int K, int N, int TM, int ACT>
+__global__ void __launch_bounds__(kT, K <= 64 ? 3 : 1)
+dense_bwd_kernel(const float *__restrict__ dY, const float *__restrict__ Y, const float *__restrict__ X,
+                 const float *__restrict__ W, float *__restrict__ dX, float *__restrict__ partial, int M,
+                 int n_tiles) {
+  constexpr int CGK = K / 4, RGK = kT / CGK, BM = RGK * TM;   // dX tile: TM rows x 4 k-columns per thread
+  constexpr int TN = N / 16, TK = K / 16;                      // dW tile per thread (16 x 16 threads)
+  extern __shared__ float4 smem4[];
+  float *Wn = reinterpret_cast<float *>(smem4);     // [N][K]       natural layout (n-major)
+  float *Zs = Wn + N * K;                           // [BM][N+4]    dZ tile
+  float *Xs = Zs + BM * (N + 4);                    // [BM][K+4]    X tile
+  const int cg = threadIdx.x % CGK, rg = threadIdx.x / CGK, c0 = cg * 4;
+  const int tk = threadIdx.x % 16, tn = threadIdx.x / 16, k0 = tk * TK, n0 = tn * TN;
+  float dw[TN][TK], db[TN];
+#pragma unroll
+  for (int a = 0; a < TN; ++a) {
+    db[a] = 0.f;
+#pragma unroll
+    for (int b = 0; b < TK; ++b) dw[a][b] = 0.f;
+  }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int m0 = tile * BM;
+    // every global load of the tile (and, first time, of W) is in flight before the first store
+    RowStage<N, BM> gs, ys;
+    RowStage<K, BM> xs;
+    static_assert(K == N, "square layers only");
+    gs.load(dY, m0, M);
+    xs.load(X, m0, M);
+    if constexpr (ACT != kNone) ys.load(Y, m0, M);
+    if (tile == (int)blockIdx.x) {
+      constexpr int WPER = N * K / 4 / kT;
+      float4 w[WPER];
+#pragma unroll
+      for (int i = 0; i < WPER; ++i) w[i] = ldg4(W + (threadIdx.x + i * kT) * 4);
+#pragma unroll
+      for (int i = 0; i < WPER; ++i) reinterpret_cast<float4 *>(Wn)[threadIdx.x + i * kT] = w[i];
+    } else {
+      __syncthreads();                               // previous tile fully consumed
+    }
+    if constexpr (ACT != kNone) {                    // dZ = dY * act'(Y)
+#pragma unroll
+      for (int i = 0; i < RowStage<N, BM>::PER; ++i) {
+        gs.v[i].x = act_bwd<ACT>(gs.v[i].x, ys.v[i].x); gs.v[i].y = act_bwd<ACT>(gs.v[i].y, ys.v[i].y);
+        gs.v[i].z = act_bwd<ACT>(gs.v[i].z, ys.v[i].z); gs.v[i].w = act_bwd<ACT>(gs.v[i].w, ys.v[i].w);
+      }
+    }
+    gs.store(Zs);
+    xs.store(Xs);
+    __syncthreads();
+    if (dX != nullptr) {
+      float acc[TM][4];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+      tile_mma<N, TM, RGK, K>(acc, Zs, rg, Wn, c0);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const int m = m0 + rg + RGK * i;
+        if (m < M)
+          *reinterpret_cast<float4 *>(dX + (size_t)m * K + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      }
+    }
+    // dW[n0.., k0..] += dZ[m][n0..] * X[m][k0..]   (rows beyond M are zero in both tiles)
+#pragma unroll 4
+    for (int m = 0; m < BM; ++m) {
+      float z[TN], x[TK];
+#pragma unroll
+      for (int a = 0; a < TN; a += (TN >= 4 ? 4 : TN)) {
+        if constexpr (TN >= 4) {
+          const float4 v = *reinterpret_cast<const float4 *>(Zs + m * (N + 4) + n0 + a);
+          z[a] = v.x; z[a + 1] = v.y; z[a + 2] = v.z; z[a + 3] = v.w;
+        } else {
+          const float2 v = *reinterpret_cast<const float2 *>(Zs + m * (N + 4) + n0 + a);
+          z[a] = v.x; z[a + 1] = v.y;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < TK; b += (TK >= 4 ? 4 : TK)) {
+        if constexpr (TK >= 4) {
+          const float4 v = *reinterpret_cast<const float4 *>(Xs + m * (K + 4) + k0 + b);
+          x[b] = v.x; x[b + 1] = v.y; x[b + 2] = v.z; x[b + 3] = v.w;
+        } else {
+          const float2 v = *reinterpret_cast<const float2 *>(Xs + m * (K + 4) + k0 + b);
+          x[b] = v.x; x[b + 1] = v.y;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < TN; ++a) {
+        if (tk == 0) db[a] += z[a];
+#pragma unroll
+        for (int b = 0; b < TK; ++b) dw[a][b] = fmaf(z[a], x[b], dw[a][b]);
+      }
+    }
+  }
+  float *p = partial + (size_t)blockIdx.x * (N * K + N);
+#pragma unroll
+  for (int a = 0; a < TN; ++a) {
+#pragma unroll
+    for (int b = 0; b < TK; ++b) p[(n0 + a) * K + k0 + b] = dw[a][b];
+    if (tk == 0) p[N * K + n0 + a] = db[a];
+  }
+}
+
+// out[j] = sum over CTAs of partial[cta][j]; j < n_w -> dW, the rest -> db. 64 outputs per CTA,
+// 16 thread rows each summing every 16th partial (independent coalesced loads), combined in a
+// fixed order through shared memory: deterministic, and two memory round trips deep.
+__global__ void __launch_bounds__(1024)
+dense_partial_reduce_kernel(const float *__restrict__ partial, int n_parts, int n_w, int n_b,
+                            float *__restrict__ dW, float *__restrict__ db) {
+  __shared__ float sm[16][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + tx;
+  const size_t stride = (size_t)n_w + n_b;
+  float s0 = 0.f, s1 = 0.f;
+  if (j < n_w + n_b) {
+    int p = ty;
+    for (; p + 16 < n_parts; p += 32) {
+      s0 += partial[(size_t)p * stride + j];
+      s1 += partial[(size_t)(p + 16) * stride + j];
+    }
+    if (p < n_parts) s0 += partial[(size_t)p * stride + j];
+  }
+  sm[ty][tx] = s0 + s1;
+  __syncthreads();
+  if (ty == 0 && j < n_w + n_b) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) s += sm[g][tx];
+    if (j < n_w) dW[j] = s;
+    else if (db != nullptr) db[j - n_w] = s;
+  }
+}
+
+template <int D> struct RowsPerThread { static constexpr int value = D == 128 ? 8 : 4; };
+constexpr int kMaxParts = 4 * kNumSMs;   // cap on CTAs (= dW partials) of the backward
+
+template <int D, int TM>
+constexpr size_t fwd_smem() { return sizeof(float) * (D * D + Tile<D, D, TM>::BM * (D + 4)); }
+template <int D, int TM>
+constexpr size_t bwd_smem() { return sizeof(float) * (D * D + 2 * Tile<D, D, TM>::BM * (D + 4)); }
+
+template <int D, int ACT>
+int launch_fwd(const float *X, const float *W, const float *b, float *Y, int M, cudaStream_t st) {
+  constexpr int TM = RowsPerThread<D>::value;
+  using T = Tile<D, D, TM>;
+  constexpr size_t smem = fwd_smem<D, TM>();
+  static bool attr = false;
+  if (!attr) {
+    MMREC_CUDA(cudaFuncSetAttribute(dense_fwd_kernel<D, D, TM, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int n_tiles = (M + T::BM - 1) / T::BM;
+  const int grid = min(n_tiles, 8 * kNumSMs);
+  dense_fwd_kernel<D, D, TM, ACT><<<grid, kT, smem, st>>>(X, W, b, Y, M, n_tiles);
+  MMREC_CHECK_LAUNCH("dense_fwd_kernel");
+  return MMREC_OK;
+}
+
+template <int D, int ACT>
+int launch_bwd(const float *dY, const float *Y, const float *X, const float *W, float *dX, float *dW, float *db,
+               float *ws, int M, cudaStream_t st) {
+  constexpr int TM = RowsPerThread<D>::value;
+  using T = Tile<D, D, TM>;
+  constexpr size_t smem = bwd_smem<D, TM>();
+  static bool attr = false;
+  if (!attr) {
+    MMREC_CUDA(cudaFuncSetAttribute(dense_bwd_kernel<D, D, TM, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int n_tiles = (M + T::BM - 1) / T::BM;
+  const int grid = max(1, min(n_tiles, kMaxParts));
+  dense_bwd_kernel<D, D, TM, ACT><<<grid, kT, smem, st>>>(dY, Y, X, W, dX, ws, M, n_tiles);
+  MMREC_CHECK_LAUNCH("dense_bwd_kernel");
+  const int n_out = D * D + D;
+  dense_partial_reduce_kernel<<<(n_out + 63) / 64, 1024, 0, st>>>(ws, grid, D * D, D, dW, db);
+  MMREC_CHECK_LAUNCH("dense_partial_reduce_kernel");
+  return MMREC_OK;
+}
+
+}  // namespace
+}  // namespace mmrec
+
+using namespace mmrec;
+
+extern "C" int mmrec_dense_act_supported(int32_t K, int32_t N) {
+  return K == N && (K == 32 || K == 64 || K == 128);
+}
+
+extern "C" size_t mmrec_dense_act_bwd_workspace_bytes(int32_t K, int32_t N) {
+  return sizeof(float) * (size_t)kMaxParts * ((size_t)N * K + N);
+}
+
+#define MMREC_DENSE_DISPATCH(FN, ...)                          \
+  switch (K * 4 + act) {                                       \
+    case 32 * 4 + 0: return FN<32, kNone>(__VA_ARGS__);        \
+    case 32 * 4 + 1: return FN<32, kTanh>(__VA_ARGS__);        \
+    case 32 * 4 + 2: return FN<32, kSigmoid>(__VA_ARGS__);     \
+    case 64 * 4 + 0: return FN<64, kNone>(__VA_ARGS__);        \
+    case 64 * 4 + 1: return FN<64, kTanh>(__VA_ARGS__);        \
+    case 64 * 4 + 2: return FN<64, kSigmoid>(__VA_ARGS__);     \
+    case 128 * 4 + 0: return FN<128, kNone>(__VA_ARGS__);      \
+    case 128 * 4 + 1: return FN<128, kTanh>(__VA_ARGS__);      \
+    case 128 * 4 + 2: return FN<128, kSigmoid>(__VA_ARGS__);   \
+  }
+
+extern "C" int mmrec_dense_act_fwd_f32(const float *X, const float *W, const float *bias, float *Y, int32_t M,
+                                       int32_t K, int32_t N, int32_t act, void *stream) {
+  MMREC_REQUIRE(X && W && Y, MMREC_E_BADARG, "dense_act_fwd: null pointer");
+  MMREC_REQUIRE(mmrec_dense_act_supported(K, N), MMREC_E_BADARG,
+                "dense_act_fwd: K = N in {32, 64, 128} required (got K=%d N=%d)", K, N);
+  MMREC_REQUIRE(act >= 0 && act <= 2 && M >= 0, MMREC_E_BADARG, "dense_act_fwd: bad act / M");
+  MMREC_REQUIRE(aligned16(X) && aligned16(W) && aligned16(Y) && aligned16(bias), MMREC_E_ALIGN,
+                "dense_act_fwd: operands must be 16-byte aligned");
+  if (M == 0) return MMREC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  MMREC_DENSE_DISPATCH(launch_fwd, X, W, bias, Y, M, st);
+  return MMREC_E_BADARG;
+}
+
+extern "C" int mmrec_dense_act_bwd_f32(const float *dY, const float *Y, const float *X, const float *W,
+                                       float *dX, float *dW, float *db, float *ws, int32_t M, int32_t K,
+                                       int32_t N, int32_t act, void *stream) {
+  MMREC_REQUIRE(dY && X && W && dW && ws, MMREC_E_BADARG, "dense_act_bwd: null pointer");
+  MMREC_REQUIRE(act == 0 || Y != nullptr, MMREC_E_BADARG, "dense_act_bwd: the activation needs Y");
+  MMREC_REQUIRE(mmrec_dense_act_supported(K, N), MMREC_E_BADARG,
+                "dense_act_bwd: K = N in {32, 64, 128} required (got K=%d N=%d)", K, N);
+  MMREC_REQUIRE(act >= 0 && act <= 2 && M >= 0, MMREC_E_BADARG, "dense_act_bwd: bad act / M");
+  MMREC_REQUIRE(aligned16(dY) && aligned16(Y) && aligned16(X) && aligned16(W) && aligned16(dX), MMREC_E_ALIGN,
+                "dense_act_bwd: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) {
+    MMREC_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * N * K, st));
+    if (db) MMREC_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
+    return MMREC_OK;
+  }
+  MMREC_DENSE_DISPATCH(launch_bwd, dY, Y, X, W, dX, dW, db, ws, M, st);
+  return MMREC_E_BADARG;
+}

@@ -152,14 +152,22 @@ infonce_normalize_kernel(const float *__restrict__ T1, const float *__restrict__
 constexpr int kTile = 64;  // 64 x 64 score tile, 16 x 16 threads, 4 x 4 scores per thread
 
 // Load `kTile` rows (row0..) of M [batch, D] into smem [kTile][D + 4]; rows past `batch` -> 0.
+// Every load of the thread is in flight before the first store: one L2 round trip per tile.
 template <int D>
 __device__ __forceinline__ void load_tile(float *s, const float *__restrict__ M, int row0, int batch) {
-  constexpr int LD = D + 4, V = D / 4;
-  for (int t = threadIdx.x; t < kTile * V; t += kThreads) {
-    const int r = t / V, c = (t % V) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < batch) v = ldg4(M + (size_t)(row0 + r) * D + c);
-    *reinterpret_cast<float4 *>(s + r * LD + c) = v;
+  constexpr int LD = D + 4, V = D / 4, PER = kTile * V / kThreads;
+  static_assert(kTile * V % kThreads == 0, "tile must be a multiple of the CTA");
+  float4 v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int t = threadIdx.x + i * kThreads, r = t / V, c = (t % V) * 4;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < batch) v[i] = ldg4(M + (size_t)(row0 + r) * D + c);
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int t = threadIdx.x + i * kThreads, r = t / V, c = (t % V) * 4;
+    *reinterpret_cast<float4 *>(s + r * LD + c) = v[i];
   }
 }
 
@@ -186,17 +194,21 @@ __device__ __forceinline__ void tile_dots(float (&acc)[4][4], const float *sA, c
 }
 
 // grid = (row tiles, column splits). ttl_part[split][row] = sum over the split's columns of
-// exp(s/t); pos[row] = s_ii. The last CTA combines splits in order and writes the mean loss.
+// exp(s/t); pos[row] = s_ii. The last CTA of every row tile adds the splits in order (ttl, and the
+// 64 per-row losses -> tile_loss); the last row tile adds the tile losses in order: the scalar is
+// bit-reproducible and no single CTA walks the whole batch.
+// counters: [0] = row tiles done, [1 + row tile] = splits done (zero on entry, self-resetting).
 template <int D>
 __global__ void __launch_bounds__(kThreads)
 infonce_fwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n, int batch,
                    float inv_temp, int tiles_per_split, float *__restrict__ ttl_part,
-                   float *__restrict__ pos, float *__restrict__ ttl, float *__restrict__ loss_out,
-                   uint32_t *counter) {
+                   float *__restrict__ pos, float *__restrict__ tile_loss, float *__restrict__ ttl,
+                   float *__restrict__ loss_out, uint32_t *counters) {
   extern __shared__ __align__(16) float smem[];
   constexpr int LD = D + 4;
   float *sA = smem, *sB = smem + kTile * LD;
   __shared__ float red[kThreads / 32];
+  __shared__ bool is_last;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int row0 = blockIdx.x * kTile;
   const int n_tiles = (batch + kTile - 1) / kTile;
@@ -226,18 +238,43 @@ infonce_fwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
     const int r = row0 + ty + 16 * i;
     if (tx == 0 && r < batch) ttl_part[(size_t)blockIdx.y * batch + r] = s;
   }
-  if (last_block_arrives(counter)) {
-    float l = 0.f;
-    for (int r = threadIdx.x; r < batch; r += kThreads) {
-      float s = 0.f;
-      for (int sp = 0; sp < (int)gridDim.y; ++sp) s += __ldcg(ttl_part + (size_t)sp * batch + r);
-      ttl[r] = s;
-      // -log(exp(s_ii/t) / ttl)
-      l += logf(s) - __ldcg(pos + r) * inv_temp;
-    }
-    l = block_sum<kThreads>(l, red);
-    if (threadIdx.x == 0) loss_out[0] = l / (float)batch;
+  // ---- last split of this row tile: ttl + per-row loss ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(counters + 1 + blockIdx.x, 1u);
+    is_last = prev == gridDim.y - 1;
+    if (is_last) counters[1 + blockIdx.x] = 0u;
   }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float l = 0.f;
+  if (threadIdx.x < kTile && row0 + threadIdx.x < batch) {
+    const int r = row0 + threadIdx.x;
+    float s = 0.f;
+#pragma unroll 4
+    for (int sp = 0; sp < (int)gridDim.y; ++sp) s += __ldcg(ttl_part + (size_t)sp * batch + r);
+    ttl[r] = s;
+    l = logf(s) - __ldcg(pos + r) * inv_temp;      // -log(exp(s_ii/t) / ttl)
+  }
+  l = block_sum<kThreads>(l, red);
+  if (threadIdx.x == 0) tile_loss[blockIdx.x] = l;
+  // ---- last row tile: the scalar ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(counters, 1u);
+    is_last = prev == gridDim.x - 1;
+    if (is_last) counters[0] = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float tot = 0.f;
+  for (int t = threadIdx.x; t < n_tiles; t += kThreads) tot += __ldcg(tile_loss + t);
+  tot = block_sum<kThreads>(tot, red);
+  if (threadIdx.x == 0) loss_out[0] = tot / (float)batch;
 }
 
 // Backward tile pass. ROWPASS: CTA owns 64 rows i of V1 and loops over column tiles j, producing
@@ -329,6 +366,7 @@ infonce_scatter_kernel(const float *__restrict__ V1n, const float *__restrict__ 
   // sum the per-split partial gradients in split order (deterministic)
   auto sum_splits = [&](const float *p, int c) {
     float4 s = ldg4(p + src + c);
+#pragma unroll 8
     for (int k = 1; k < n_splits; ++k) {
       const float4 v = ldg4(p + k * slab + src + c);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -358,20 +396,33 @@ infonce_scatter_kernel(const float *__restrict__ V1n, const float *__restrict__ 
   }
 }
 
+constexpr int kMaxInfoSplits = 32;
+constexpr int kMaxInfoTiles = 1023;   // arrival counters: 1 + row tiles (ops.py keeps 1024)
+
+// column splits so that the grid is ~4 CTAs per SM (35 KB of smem each: they are co-resident)
+inline int infonce_splits(int batch) {
+  const int n_tiles = (batch + kTile - 1) / kTile;
+  int splits = max(1, min(min(n_tiles, kMaxInfoSplits), (4 * kNumSMs + n_tiles - 1) / n_tiles));
+  const int tps = (n_tiles + splits - 1) / splits;
+  return (n_tiles + tps - 1) / tps;
+}
+
 template <int D>
 int infonce_fwd_launch(const float *V1n, const float *V2n, int batch, float inv_temp, float *partial,
-                       float *ttl, float *loss_out, uint32_t *counter, cudaStream_t stream) {
+                       float *ttl, float *loss_out, uint32_t *counters, cudaStream_t stream) {
   const int n_tiles = (batch + kTile - 1) / kTile;
-  int splits = max(1, min(n_tiles, (kNumSMs + n_tiles - 1) / n_tiles));
-  const int tiles_per_split = (n_tiles + splits - 1) / splits;
-  splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-  // partial layout: pos[batch] then ttl_part[splits][batch]; caller guarantees 16*batch floats
-  if (splits > 15) splits = 15;
-  const size_t smem = 2 * kTile * (D + 4) * sizeof(float);
-  MMREC_CUDA(cudaFuncSetAttribute(infonce_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int splits = infonce_splits(batch);
   const int tps = (n_tiles + splits - 1) / splits;
+  // partial layout: pos[batch], ttl_part[splits][batch], tile_loss[n_tiles]
+  const size_t smem = 2 * kTile * (D + 4) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    MMREC_CUDA(cudaFuncSetAttribute(infonce_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
   infonce_fwd_kernel<D><<<dim3(n_tiles, splits), kThreads, smem, stream>>>(
-      V1n, V2n, batch, inv_temp, tps, partial + batch, partial, ttl, loss_out, counter);
+      V1n, V2n, batch, inv_temp, tps, partial + batch, partial, partial + (size_t)(1 + splits) * batch, ttl,
+      loss_out, counters);
   MMREC_CHECK_LAUNCH("infonce_fwd_kernel");
   return MMREC_OK;
 }
@@ -383,8 +434,12 @@ int infonce_bwd_launch(const float *V1n, const float *V2n, const float *ttl, int
   const int tps = (n_tiles + n_splits - 1) / n_splits;   // splits past the end write zeros
   const dim3 grid(n_tiles, n_splits);
   const size_t smem = (2 * kTile * (D + 4) + kTile * (kTile + 4)) * sizeof(float);
-  MMREC_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MMREC_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr = false;
+  if (!attr) {
+    MMREC_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMREC_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
   infonce_bwd_kernel<D, true><<<grid, kThreads, smem, stream>>>(V1n, V2n, ttl, batch, inv_temp, tps, coef, dV1);
   MMREC_CHECK_LAUNCH("infonce_bwd_kernel<row>");
   infonce_bwd_kernel<D, false><<<grid, kThreads, smem, stream>>>(V1n, V2n, ttl, batch, inv_temp, tps, coef, dV2);
@@ -427,6 +482,11 @@ extern "C" int mmrec_bpr_bwd_f32(const float *user_emb, const float *item_emb, i
   return MMREC_OK;
 }
 
+extern "C" int32_t mmrec_infonce_splits(int32_t batch) { return infonce_splits(batch); }
+extern "C" size_t mmrec_infonce_fwd_workspace_floats(int32_t batch) {
+  return (size_t)(1 + infonce_splits(batch)) * batch + (batch + kTile - 1) / kTile;
+}
+
 extern "C" int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d, const int64_t *idx,
                                      int32_t batch, float inv_temp, float *loss_out, float *V1n, float *V2n,
                                      float *inv_norm, float *ttl, float *partial, uint32_t *counter,
@@ -434,7 +494,8 @@ extern "C" int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d
   cudaStream_t stream = (cudaStream_t)stream_;
   MMREC_REQUIRE(T1 && T2 && idx && loss_out && V1n && V2n && inv_norm && ttl && partial && counter,
                 MMREC_E_BADARG, "infonce_fwd: null pointer");
-  MMREC_REQUIRE(batch > 0, MMREC_E_BADARG, "infonce_fwd: empty batch");
+  MMREC_REQUIRE(batch > 0 && (batch + kTile - 1) / kTile <= kMaxInfoTiles, MMREC_E_BADARG,
+                "infonce_fwd: batch must be in [1, %d]", kMaxInfoTiles * kTile);
   MMREC_REQUIRE(aligned16(T1) && aligned16(T2) && aligned16(V1n) && aligned16(V2n), MMREC_E_ALIGN,
                 "infonce_fwd: operands must be 16-byte aligned");
   const int wpb = kThreads / 32;

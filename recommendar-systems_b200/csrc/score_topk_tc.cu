@@ -50,6 +50,55 @@ struct Better {   // strict total order on (score, id): a ranks before b
   __device__ static bool worse(float av, int ai, float bv, int bi) { return av < bv || (av == bv && ai > bi); }
 };
 
+// The K best of a user live in an 8-ary heap in shared memory, column `tid` of [k][128] arrays
+// (bank = lane: conflict-free), root = the worst kept entry. K <= 73 gives depth 2: replacing the
+// root is two rounds of eight independent shared-memory loads instead of the six dependent
+// rounds of a binary heap -- the epilogue is a chain of dependent smem latencies, not throughput.
+constexpr int kAry = 8;
+
+// Place (sc, gid) at `pos` of the heap prefix [0, lim) and sift it down.
+__device__ __forceinline__ void heap_sift_down(float *hv, int32_t *hi_, int pos, int lim, float sc, int gid) {
+  for (;;) {
+    const int c0 = kAry * pos + 1;
+    if (c0 >= lim) break;
+    float v[kAry];
+    int id[kAry];
+#pragma unroll
+    for (int j = 0; j < kAry; ++j) {
+      const bool in = c0 + j < lim;
+      v[j] = in ? hv[(c0 + j) * kTileM] : CUDART_INF_F;      // +inf never wins "worst"
+      id[j] = in ? hi_[(c0 + j) * kTileM] : 0;
+    }
+    int w = 0;
+    float wv = v[0];
+    int wi = id[0];
+#pragma unroll
+    for (int j = 1; j < kAry; ++j)
+      if (Better::worse(v[j], id[j], wv, wi)) { w = j; wv = v[j]; wi = id[j]; }
+    if (!Better::worse(wv, wi, sc, gid)) break;
+    hv[pos * kTileM] = wv;
+    hi_[pos * kTileM] = wi;
+    pos = c0 + w;
+  }
+  hv[pos * kTileM] = sc;
+  hi_[pos * kTileM] = gid;
+}
+
+// Append (sc, gid) at `pos` (= current size) and sift it up.
+__device__ __forceinline__ void heap_sift_up(float *hv, int32_t *hi_, int pos, float sc, int gid) {
+  while (pos > 0) {
+    const int par = (pos - 1) / kAry;
+    const float pv = hv[par * kTileM];
+    const int pi = hi_[par * kTileM];
+    if (!Better::worse(sc, gid, pv, pi)) break;
+    hv[pos * kTileM] = pv;
+    hi_[pos * kTileM] = pi;
+    pos = par;
+  }
+  hv[pos * kTileM] = sc;
+  hi_[pos * kTileM] = gid;
+}
+
 template <int D>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restrict__ users, int n_users,
@@ -58,7 +107,9 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
                      int items_per_split, float *__restrict__ ws_val, int32_t *__restrict__ ws_idx, int dbg) {
   using C = Cfg<D>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (SW128 atoms) by an offset on the __shared__ array itself: pointers derived
+  // through an integer cast would lose their address space and compile to generic LD/ST
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float *h_val = reinterpret_cast<float *>(smem + C::OFF_HEAP);              // [k][128]
   int32_t *h_idx = reinterpret_cast<int32_t *>(h_val + (size_t)k * kTileM);  // [k][128]
   float *c_val = reinterpret_cast<float *>(h_idx + (size_t)k * kTileM);      // [32][128]
@@ -136,31 +187,32 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
   } else if (warp == 8) {
     // =============================== MMA issuer ==============================================
     constexpr uint32_t idesc = idesc_tf32(kTileM, kTileN, false, false);
+    const uint64_t a_hi = smem_desc_sw128(smem_base, 16, 1024);
+    const uint64_t a_lo = smem_desc_sw128(smem_base + C::A_HALF, 16, 1024);
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % C::STAGES, b = t % kAcc;
       mbar_wait(full + s, (t / C::STAGES) & 1);
       mbar_wait(tempty + b, ((t / kAcc) & 1) ^ 1);
       fence_after_sync();
-      if (lane == 0) {
-        const uint32_t d_tmem = tmem_base + b * kTileN;
-        const uint32_t a_hi = smem_base, a_lo = smem_base + C::A_HALF;
-        const uint32_t b_hi = smem_base + C::OFF_B + s * C::STAGE, b_lo = b_hi + C::B_HALF;
-        uint32_t acc = 0;
-        // small cross terms first, the dominant hi*hi product last
+      const uint32_t d_tmem = tmem_base + b * kTileN;
+      const uint64_t b_hi = smem_desc_sw128(smem_base + C::OFF_B + s * C::STAGE, 16, 1024);
+      const uint64_t b_lo = b_hi + (C::B_HALF >> 4);
+      // small cross terms first, the dominant hi*hi product last; a K step inside the swizzle atom
+      // (and the next atom) is a plain offset in the descriptor's 16-byte-unit address field
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = pass == 0 ? a_lo : a_hi;
-          const uint32_t b0 = pass == 1 ? b_lo : b_hi;
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t a0 = pass == 0 ? a_lo : a_hi;
+        const uint64_t b0 = pass == 1 ? b_lo : b_hi;
 #pragma unroll
-          for (int kb = 0; kb < C::KB; ++kb)
+        for (int kb = 0; kb < C::KB; ++kb)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ad = smem_desc_sw128(a0 + kb * (kTileM * 128) + ks * 32, 16, 1024);
-              const uint64_t bd = smem_desc_sw128(b0 + kb * (kTileN * 128) + ks * 32, 16, 1024);
-              umma_tf32_ss(d_tmem, ad, bd, idesc, acc);
-              acc = 1;
-            }
-        }
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = a0 + ((kb * (kTileM * 128) + ks * 32) >> 4);
+            const uint64_t bd = b0 + ((kb * (kTileN * 128) + ks * 32) >> 4);
+            if (elect_one()) umma_tf32_ss(d_tmem, ad, bd, idesc, (pass | kb | ks) != 0);
+          }
+      }
+      if (elect_one()) {
         umma_commit(empty + s);     // smem stage reusable once these MMAs have read it
         umma_commit(tfull + b);     // accumulator ready for the epilogue
       }
@@ -229,38 +281,10 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
             }
             if (gid == next_masked) sc = -1e10f;                  // trainer.py:524
             if (cnt < k) {
-              int pos = cnt++;                                    // sift up
-              while (pos > 0) {
-                const int par = (pos - 1) >> 1;
-                const float pv = hv[par * kTileM];
-                const int pi = hi_[par * kTileM];
-                if (!Better::worse(sc, gid, pv, pi)) break;
-                hv[pos * kTileM] = pv;
-                hi_[pos * kTileM] = pi;
-                pos = par;
-              }
-              hv[pos * kTileM] = sc;
-              hi_[pos * kTileM] = gid;
+              heap_sift_up(hv, hi_, cnt++, sc, gid);
               if (cnt == k) thr = hv[0];
             } else if (sc > thr) {
-              int pos = 0;                                        // replace the worst, sift down
-              for (;;) {
-                int ch = 2 * pos + 1;
-                if (ch >= k) break;
-                float chv = hv[ch * kTileM];
-                int chi = hi_[ch * kTileM];
-                if (ch + 1 < k) {
-                  const float v2 = hv[(ch + 1) * kTileM];
-                  const int i2 = hi_[(ch + 1) * kTileM];
-                  if (Better::worse(v2, i2, chv, chi)) { ++ch; chv = v2; chi = i2; }
-                }
-                if (!Better::worse(chv, chi, sc, gid)) break;
-                hv[pos * kTileM] = chv;
-                hi_[pos * kTileM] = chi;
-                pos = ch;
-              }
-              hv[pos * kTileM] = sc;
-              hi_[pos * kTileM] = gid;
+              heap_sift_down(hv, hi_, 0, k, sc, gid);             // replace the worst kept entry
               thr = hv[0];
             }
           }
@@ -275,25 +299,7 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
         const int li = hi_[(size - 1) * kTileM];
         hv[(size - 1) * kTileM] = hv[0];
         hi_[(size - 1) * kTileM] = hi_[0];
-        int pos = 0;
-        const int lim = size - 1;
-        for (;;) {
-          int ch = 2 * pos + 1;
-          if (ch >= lim) break;
-          float chv = hv[ch * kTileM];
-          int chi = hi_[ch * kTileM];
-          if (ch + 1 < lim) {
-            const float v2 = hv[(ch + 1) * kTileM];
-            const int i2 = hi_[(ch + 1) * kTileM];
-            if (Better::worse(v2, i2, chv, chi)) { ++ch; chv = v2; chi = i2; }
-          }
-          if (!Better::worse(chv, chi, lv, li)) break;
-          hv[pos * kTileM] = chv;
-          hi_[pos * kTileM] = chi;
-          pos = ch;
-        }
-        hv[pos * kTileM] = lv;
-        hi_[pos * kTileM] = li;
+        heap_sift_down(hv, hi_, 0, size - 1, lv, li);
       }
       float *ov = ws_val + ((size_t)blockIdx.y * n_users + b_user) * k;
       int32_t *oi = ws_idx + ((size_t)blockIdx.y * n_users + b_user) * k;

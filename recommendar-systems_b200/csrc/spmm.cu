@@ -9,10 +9,11 @@
 // a heavy row is cut into ceil(deg/SEG) tasks whose partial sums go to a scratch buffer, and
 // the last task to arrive (per-row counter, self-resetting) adds them in part order and runs
 // the fused epilogue -- no floating-point atomics, results are bit-reproducible run to run.
-// Each gathered embedding row is one coalesced 16-byte-per-lane request; column indices and
-// values are loaded once per LANES non-zeros and broadcast with shuffles; four gathers are kept
-// in flight per lane and registers are capped so that 6 CTAs (75% occupancy) fit per SM -- the
-// kernel is a chain of dependent L2/DRAM round trips, so resident warps are what hides latency.
+// Each gathered embedding row is one coalesced 16-byte-per-lane request; the column indices and
+// values of a whole task are loaded in one round and broadcast with shuffles; eight gathers are
+// kept in flight per lane. The kernel is a chain of dependent L2/DRAM round trips: on the small
+// graphs (Baby: 27k tasks = 1.4 waves) the length of that chain IS the kernel time, on graphs
+// larger than L2 the bytes in flight per SM (4 CTAs x 16 tasks x 8 rows x 256 B) saturate HBM.
 #include "common.cuh"
 
 namespace mmrec {
@@ -41,48 +42,59 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
   return v;
 }
 
-// Accumulate rows [begin, end) of the CSR slice, visiting chunk `base, base+stride, ...`.
+constexpr int kSeg = 64;   // non-zeros per task; must match graph.py SEG
+constexpr int kDepth = 8;  // embedding-row gathers in flight per lane
+
+// Accumulate the (at most kSeg) non-zeros [begin, end) of one task. A task is a chain of dependent
+// memory round trips (task -> indices -> rows), so the chain is kept as short as it can be: every
+// column index / value of the task is fetched in ONE round (kSeg / LANES per lane), then the rows
+// are gathered kDepth at a time (16 bytes per lane each); partial groups are predicated off, not
+// padded. The sum runs in CSR order whatever the grouping.
 template <int LANES, int CHUNKS>
 __device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t *__restrict__ col_idx,
-                                            const float *__restrict__ vals, int begin, int end,
-                                            int stride, int lane, const float *__restrict__ X,
-                                            int d, int col_offset) {
+                                            const float *__restrict__ vals, int begin, int end, int lane,
+                                            const float *__restrict__ X, int d, int col_offset) {
+  constexpr int NIDX = kSeg / LANES;
+  constexpr int DEPTH = CHUNKS == 1 ? kDepth : kDepth / 2;
   const unsigned mask = group_mask<LANES>();
-  for (int base = begin; base < end; base += stride) {
-    const int k = base + lane;
-    int c = 0;
-    float v = 0.f;
+  const int n = end - begin;
+  int c[NIDX];
+  float v[NIDX];
+#pragma unroll
+  for (int i = 0; i < NIDX; ++i) {
+    const int k = begin + i * LANES + lane;
+    c[i] = 0;
+    v[i] = 0.f;
     if (k < end) {
-      c = ld_stream_i32(col_idx + k) - col_offset;
-      v = ld_stream_f32(vals + k);
+      c[i] = ld_stream_i32(col_idx + k) - col_offset;
+      v[i] = ld_stream_f32(vals + k);
     }
-    const int cnt = min(LANES, end - base);
-    int j = 0;
-    for (; j + 4 <= cnt; j += 4) {
-      int cc[4];
-      float vv[4];
+  }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        cc[t] = __shfl_sync(mask, c, j + t, LANES);
-        vv[t] = __shfl_sync(mask, v, j + t, LANES);
+  for (int i = 0; i < NIDX; ++i) {
+#pragma unroll
+    for (int j = 0; j < LANES; j += DEPTH) {
+      const int base = i * LANES + j;
+      if (base < n) {
+        int cc[DEPTH];
+        float vv[DEPTH];
+        float4 x[DEPTH][CHUNKS];
+#pragma unroll
+        for (int t = 0; t < DEPTH; ++t) {
+          cc[t] = __shfl_sync(mask, c[i], j + t, LANES);
+          vv[t] = __shfl_sync(mask, v[i], j + t, LANES);
+        }
+#pragma unroll
+        for (int t = 0; t < DEPTH; ++t)
+#pragma unroll
+          for (int q = 0; q < CHUNKS; ++q)
+            x[t][q] = base + t < n ? ldg4(X + (size_t)cc[t] * d + (q * LANES + lane) * 4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < DEPTH; ++t)
+#pragma unroll
+          for (int q = 0; q < CHUNKS; ++q) fma4(acc[q], vv[t], x[t][q]);
       }
-      float4 x[4][CHUNKS];
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int q = 0; q < CHUNKS; ++q)
-          x[t][q] = ldg4(X + (size_t)cc[t] * d + (q * LANES + lane) * 4);
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int q = 0; q < CHUNKS; ++q) fma4(acc[q], vv[t], x[t][q]);
-    }
-    for (; j < cnt; ++j) {
-      const int c1 = __shfl_sync(mask, c, j, LANES);
-      const float v1 = __shfl_sync(mask, v, j, LANES);
-#pragma unroll
-      for (int q = 0; q < CHUNKS; ++q)
-        fma4(acc[q], v1, ldg4(X + (size_t)c1 * d + (q * LANES + lane) * 4));
     }
   }
 }
@@ -144,10 +156,8 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[CHUNKS], int row, int l
   }
 }
 
-constexpr int kSeg = 64;  // non-zeros per task; must match graph.py SEG
-
 template <int LANES, int CHUNKS>
-__global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 6 : 3)
+__global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 4 : 3)
 spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                 const float *__restrict__ vals, const int4 *__restrict__ tasks, int n_tasks,
                 const int32_t *__restrict__ slot_base, int32_t *__restrict__ counters,
@@ -168,7 +178,7 @@ spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__
     if (ep.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.acc_in + o));
     if (ep.cos_ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.cos_ref + o));
   }
-  gather_rows<LANES, CHUNKS>(acc, col_idx, vals, task.y, task.z, LANES, lane, X, d, col_offset);
+  gather_rows<LANES, CHUNKS>(acc, col_idx, vals, task.y, task.z, lane, X, d, col_offset);
   if (task.w >= 0) {
     // heavy row: publish this part, the last arriver reduces all parts in order
     const unsigned mask = group_mask<LANES>();

@@ -32,6 +32,8 @@ SIGNATURES = {
     "mmrec_layergcn_cos_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
     "mmrec_bpr_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "mmrec_bpr_bwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "mmrec_infonce_splits": (_i32, [_i32]),
+    "mmrec_infonce_fwd_workspace_floats": (_sz, [_i32]),
     "mmrec_infonce_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p, _p, _p,
                                         _p]),
     "mmrec_infonce_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _f32, _p, _i32, _p, _p, _p,
@@ -41,6 +43,10 @@ SIGNATURES = {
                                          _p, _p, _p, _p, _p, _p]),
     "mmrec_gemm_splits": (C.c_int, [_i32, _i32, _i32, _i32, _i32]),
     "mmrec_gemm_tf32x3_f32": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "mmrec_dense_act_supported": (C.c_int, [_i32, _i32]),
+    "mmrec_dense_act_bwd_workspace_bytes": (_sz, [_i32, _i32]),
+    "mmrec_dense_act_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "mmrec_dense_act_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "mmrec_adam_step_f32": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double,
                                       C.c_double, _p]),
     "mmrec_axpy_multi_f32": (C.c_int, [_p, _p, _p, _i32, _p, _f32, _p]),

@@ -418,11 +418,11 @@ class MGCN(_MultiViewBase):
         self.image_trs = ops.Linear(self.v_feat.shape[1], d)
         self.text_trs = ops.Linear(self.t_feat.shape[1], d)
         self.softmax = nn.Softmax(dim=-1)
-        self.query_common = nn.Sequential(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, 1, bias=False))
-        self.gate_v = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
-        self.gate_t = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
-        self.gate_image_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
-        self.gate_text_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.query_common = ops.DenseStack(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, 1, bias=False))
+        self.gate_v = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_t = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_image_prefer = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_text_prefer = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
         self.tau = 0.5
 
     def forward(self, adj, train=False):
@@ -493,14 +493,14 @@ class SMORE(_MultiViewBase):
         self.image_trs = ops.Linear(self.v_feat.shape[1], d)
         self.text_trs = ops.Linear(self.t_feat.shape[1], d)
         self.softmax = nn.Softmax(dim=-1)
-        self.query_v = nn.Sequential(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, d, bias=False))
-        self.query_t = nn.Sequential(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, d, bias=False))
-        self.gate_v = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
-        self.gate_t = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
-        self.gate_f = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
-        self.gate_image_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
-        self.gate_text_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
-        self.gate_fusion_prefer = nn.Sequential(ops.Linear(d, d), nn.Sigmoid())
+        self.query_v = ops.DenseStack(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, d, bias=False))
+        self.query_t = ops.DenseStack(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, d, bias=False))
+        self.gate_v = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_t = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_f = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_image_prefer = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_text_prefer = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
+        self.gate_fusion_prefer = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
         self.image_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))
         self.text_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))
         self.fusion_complex_weight = nn.Parameter(torch.randn(1, d // 2 + 1, 2, dtype=torch.float32))

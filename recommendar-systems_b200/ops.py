@@ -17,7 +17,7 @@ def _counter(device):
     """Zero-initialised arrival counter shared by the self-resetting last-block reductions."""
     key = (device.type, device.index)
     if key not in _counters:
-        _counters[key] = torch.zeros(4, dtype=torch.int32, device=device)
+        _counters[key] = torch.zeros(1024, dtype=torch.int32, device=device)
     return _counters[key]
 
 
@@ -243,7 +243,8 @@ class _InfoNCEPair(torch.autograd.Function):
             V2 = torch.empty_like(V1)
             inv_norm = torch.empty(2 * B, dtype=torch.float32, device=dev)
             ttl = torch.empty(B, dtype=torch.float32, device=dev)
-            partial = torch.empty(16 * B, dtype=torch.float32, device=dev)
+            partial = torch.empty(lib.load().mmrec_infonce_fwd_workspace_floats(B), dtype=torch.float32,
+                                  device=dev)
             lib.call("mmrec_infonce_fwd_f32", lib.ptr(side[row0:]), lib.ptr(content[row0:]), d,
                      lib.ptr(idx), B, inv_t, lib.ptr(losses[slot:]), lib.ptr(V1), lib.ptr(V2),
                      lib.ptr(inv_norm), lib.ptr(ttl), lib.ptr(partial), lib.ptr(_counter(dev)),
@@ -264,8 +265,7 @@ class _InfoNCEPair(torch.autograd.Function):
         for slot, row0 in enumerate((ctx.n_users, 0)):
             V1, V2, inv_norm, ttl, idx = saved[5 * slot: 5 * slot + 5]
             B = idx.numel()
-            tiles = (B + 63) // 64
-            S = max(1, min(tiles, (2 * 148 + tiles - 1) // tiles, 16))
+            S = lib.load().mmrec_infonce_splits(B)
             ws1 = torch.empty(S, B, d, dtype=torch.float32, device=dev)
             ws2 = torch.empty_like(ws1)
             lib.call("mmrec_infonce_bwd_f32", lib.ptr(V1), lib.ptr(V2), lib.ptr(inv_norm),
@@ -360,6 +360,75 @@ class Linear(torch.nn.Linear):
 
     def forward(self, x):
         return linear(x, self.weight, self.bias)
+
+
+_ACT_CODE = {None: 0, "tanh": 1, "sigmoid": 2}
+
+
+def _dense_workspace(K, N, dev):
+    """Scratch for the per-CTA dW/db partial sums of mmrec_dense_act_bwd_f32 (caching allocator)."""
+    nbytes = lib.load().mmrec_dense_act_bwd_workspace_bytes(K, N)
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+
+
+class _DenseAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        x, W = _f32c(x), _f32c(W)
+        b = None if b is None else _f32c(b)
+        M, K = x.shape
+        N = W.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        lib.call("mmrec_dense_act_fwd_f32", lib.ptr(x), lib.ptr(W), lib.ptr(b), lib.ptr(y), M, K, N,
+                 act, lib.stream())
+        ctx.act, ctx.has_bias = act, b is not None
+        ctx.save_for_backward(x, W, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dy = _f32c(dy)
+        M, K = x.shape
+        N = W.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dW = torch.empty_like(W)
+        db = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        lib.call("mmrec_dense_act_bwd_f32", lib.ptr(dy), lib.ptr(y), lib.ptr(x), lib.ptr(W), lib.ptr(dx),
+                 lib.ptr(dW), lib.ptr(db), lib.ptr(_dense_workspace(K, N, x.device)), M, K, N, ctx.act,
+                 lib.stream())
+        return dx, dW, db, None
+
+
+def dense_act(x, W, b=None, act=None):
+    """act(F.linear(x, W, b)) for the d x d side-network layers in ONE launch (forward) and one
+    launch + a partial-sum reduce (backward: dX, dW, db and the activation derivative together);
+    exact fp32. Other shapes: `linear` + torch activation."""
+    if x.dim() == 2 and x.is_cuda and lib.load().mmrec_dense_act_supported(W.shape[1], W.shape[0]):
+        return _DenseAct.apply(x, W, b, _ACT_CODE[act])
+    y = linear(x, W, b)
+    return y if act is None else (torch.tanh(y) if act == "tanh" else torch.sigmoid(y))
+
+
+class DenseStack(torch.nn.Sequential):
+    """nn.Sequential of Linear / Tanh / Sigmoid with the reference's module indices (so the
+    state_dict keys `gate_v.0.weight`, `query_v.2.weight` ... are unchanged) whose forward fuses
+    every Linear with the activation that follows it."""
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(m, torch.nn.Linear):
+                act = "tanh" if isinstance(nxt, torch.nn.Tanh) else "sigmoid" if isinstance(nxt, torch.nn.Sigmoid) else None
+                x = dense_act(x, m.weight, m.bias, act)
+                i += 2 if act else 1
+            else:
+                x = m(x)
+                i += 1
+        return x
 
 
 # -------------------------------------------------------------------------------- score + top-K

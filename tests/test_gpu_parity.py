@@ -238,6 +238,49 @@ def test_linear_tf32x3_forward_backward(M, N, K):
     assert rel(y, yo) < 4 * max(rel(yc, yo), 1e-7)
 
 
+@pytest.mark.parametrize("M,d,act,bias", [(26495, 64, "sigmoid", True), (7050, 64, "tanh", True),
+                                          (7050, 64, None, False), (1, 64, "sigmoid", True),
+                                          (333, 32, "tanh", True), (20000, 32, None, True),
+                                          (5000, 128, "sigmoid", True), (10001, 128, "tanh", False)])
+def test_dense_act_forward_backward(M, d, act, bias):
+    """K4b: fused act(x W^T + b) and its one-launch backward (dX, dW, db, act') vs float64 torch."""
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(31)
+    x, W = torch.randn(M, d, generator=gen), torch.randn(d, d, generator=gen) * 0.2
+    b = torch.randn(d, generator=gen) if bias else None
+    gy = torch.randn(M, d, generator=gen)
+    f = {None: lambda t: t, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[act]
+    xg, Wg = x.to(DEV).requires_grad_(True), W.to(DEV).requires_grad_(True)
+    bg = b.to(DEV).requires_grad_(True) if bias else None
+    y = ops.dense_act(xg, Wg, bg, act)
+    y.backward(gy.to(DEV))
+    xo, Wo = x.double().requires_grad_(True), W.double().requires_grad_(True)
+    bo = b.double().requires_grad_(True) if bias else None
+    yo = f(torch.nn.functional.linear(xo, Wo, bo))
+    yo.backward(gy.double())
+    tol = 1e-5
+    assert rel(y, yo) < tol
+    assert rel(xg.grad, xo.grad) < tol and rel(Wg.grad, Wo.grad) < tol
+    if bias:
+        assert rel(bg.grad, bo.grad) < tol
+    # input that needs no gradient: dX is skipped, dW/db unchanged; bit-reproducible run to run
+    x2, W2 = x.to(DEV), W.to(DEV).requires_grad_(True)
+    y2 = ops.dense_act(x2, W2, None if not bias else b.to(DEV), act)
+    y2.backward(gy.to(DEV))
+    assert torch.equal(W2.grad, Wg.grad) and torch.equal(y2, y)
+
+
+def test_dense_stack_keeps_reference_state_dict_keys():
+    ops = pkg("ops")
+    torch.manual_seed(3)
+    ref = torch.nn.Sequential(torch.nn.Linear(64, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64, bias=False)).to(DEV)
+    ours = ops.DenseStack(ops.Linear(64, 64), torch.nn.Tanh(), ops.Linear(64, 64, bias=False)).to(DEV)
+    assert list(ref.state_dict()) == list(ours.state_dict())
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(1000, 64, device=DEV)
+    assert rel(ours(x), ref(x)) < 1e-5
+
+
 @pytest.mark.parametrize("n_users,n_items,d,k,splits", [(64, 96, 64, 50, 1), (300, 1000, 64, 50, 4),
                                                        (129, 777, 128, 20, 3), (1000, 5000, 32, 50, None)])
 def test_score_mask_topk_matches_stable_sort(n_users, n_items, d, k, splits):
