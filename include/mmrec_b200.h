@@ -207,6 +207,35 @@ int mmrec_dense_act_bwd_f32(const float *dY, const float *Y, const float *X, con
                             int32_t N, int32_t act, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SMORE modality-aware preference module, fused (K14). Replaces smore.py:321-341 -- query_v /
+ * query_t (Linear, Tanh, Linear), nn.Softmax(dim=-1), the three gate_*_prefer (Linear, Sigmoid),
+ * nn.Dropout on each gate, the products, torch.stack + torch.mean and `content + side` -- and the
+ * whole autograd graph under it, by one forward and one backward launch (+ a partial-sum reduce).
+ *   F = fusion_embeds, V = image_embeds, T = text_embeds, C = content_embeds: [n, d], d in {32, 64}
+ *   W_host / b_host: HOST arrays of 7 device pointers, order
+ *       query_v.0, query_v.2, query_t.0, query_t.2, gate_image_prefer.0, gate_text_prefer.0,
+ *       gate_fusion_prefer.0   (each [d, d] row-major as nn.Linear stores it; b NULL = no bias)
+ *   masks: [3, n, d] dropout multipliers (0 or 1/(1-p)) for the image / text / fusion gate, or
+ *          NULL (eval, p = 0)
+ *   saved: [7, n, d] written by fwd, read by bwd (tanh outputs, softmax outputs, gate sigmoids)
+ *   fwd -> side [n, d] (smore.py:339-340) and all = C + side (smore.py:341)
+ *   bwd <- d_all, d_side (either may be NULL) -> dF, dV, dT, dC (dC includes d_all), dW[7], db[7]
+ *          (db entries may be NULL); ws = mmrec_smore_side_bwd_workspace_bytes(n, d) of scratch.
+ * Exact fp32 FMA arithmetic; gradients are bit-reproducible (partials added in a fixed order).
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_smore_side_supported(int32_t d);
+size_t mmrec_smore_side_bwd_workspace_bytes(int32_t n, int32_t d);
+int mmrec_smore_side_fwd_f32(const float *F, const float *V, const float *T, const float *C,
+                             const float *const *W_host, const float *const *b_host,
+                             const float *masks, float *saved, float *side, float *all, int32_t n,
+                             int32_t d, void *stream);
+int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side, const float *F, const float *V,
+                             const float *T, const float *C, const float *const *W_host,
+                             const float *const *b_host, const float *masks, const float *saved,
+                             float *dF, float *dV, float *dT, float *dC, float *const *dW_host,
+                             float *const *db_host, float *ws, int32_t n, int32_t d, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam (K13). Replaces optim.Adam.step (common/trainer.py:126-143, 255, 331)
  * with one pass: 28 bytes per parameter. The four pointer arrays and numel are HOST arrays of
  * n_tensors device pointers / element counts (they travel as kernel arguments). hyper is a

@@ -15,86 +15,12 @@
 // second small kernel in a fixed order (no floating-point atomics: bit-reproducible). Grids are
 // sized so that the whole layer is one wave of 3 CTAs per SM (64-row tiles): loads of one CTA
 // overlap the FMA loop of its neighbours.
-#include "common.cuh"
+#include "dense_tile.cuh"
 
 namespace mmrec {
 namespace {
 
-constexpr int kT = 256;
-
-enum Act { kNone = 0, kTanh = 1, kSigmoid = 2 };
-
-template <int ACT>
-__device__ __forceinline__ float act_fwd(float z) {
-  if constexpr (ACT == kTanh) return tanhf(z);
-  if constexpr (ACT == kSigmoid) return 1.f / (1.f + expf(-z));
-  return z;
-}
-template <int ACT>
-__device__ __forceinline__ float act_bwd(float dy, float y) {
-  if constexpr (ACT == kTanh) return dy * (1.f - y * y);
-  if constexpr (ACT == kSigmoid) return dy * ((1.f - y) * y);
-  return dy;
-}
-
-template <int K, int N, int TM>
-struct Tile {
-  static constexpr int CG = N / 4;          // column groups (4 output columns each)
-  static constexpr int RG = kT / CG;        // row groups
-  static constexpr int BM = RG * TM;        // rows per tile
-  static constexpr int XP = K + 4;          // pitch of a staged X row (floats)
-};
-
-// Rows [m0, m0+BM) of a row-major [M, C] array on their way to shared memory (pitch C+4; rows
-// >= M are zero), in two phases: load() puts every global load of the thread in flight, store()
-// parks the values. Whatever sits between the two (the W staging of the first tile) overlaps the
-// DRAM round trip instead of adding one.
-template <int C, int BM>
-struct RowStage {
-  static constexpr int V = C / 4, PER = BM * V / kT;
-  static_assert(BM * V % kT == 0, "tile must be a multiple of the CTA");
-  float4 v[PER];
-  __device__ __forceinline__ void load(const float *__restrict__ src, int m0, int M) {
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int idx = threadIdx.x + i * kT, r = idx / V, c4 = idx % V;
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + r < M) v[i] = ldg4(src + (size_t)(m0 + r) * C + c4 * 4);
-    }
-  }
-  __device__ __forceinline__ void store(float *dst) const {
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int idx = threadIdx.x + i * kT, r = idx / V, c4 = idx % V;
-      *reinterpret_cast<float4 *>(dst + r * (C + 4) + c4 * 4) = v[i];
-    }
-  }
-};
-
-// acc[i][0..3] += sum_k A[row_i][k] * B[k][c0..c0+3]; A staged with pitch KK+4, B k-major pitch NB
-template <int KK, int TM, int RG, int NB>
-__device__ __forceinline__ void tile_mma(float (&acc)[TM][4], const float *__restrict__ As, int rg,
-                                         const float *__restrict__ Bs, int c0) {
-#pragma unroll 4
-  for (int k4 = 0; k4 < KK / 4; ++k4) {
-    float4 a[TM];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-      a[i] = *reinterpret_cast<const float4 *>(As + (rg + RG * i) * (KK + 4) + k4 * 4);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const float4 b = *reinterpret_cast<const float4 *>(Bs + (k4 * 4 + kk) * NB + c0);
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-        acc[i][0] = fmaf(av, b.x, acc[i][0]);
-        acc[i][1] = fmaf(av, b.y, acc[i][1]);
-        acc[i][2] = fmaf(av, b.z, acc[i][2]);
-        acc[i][3] = fmaf(av, b.w, acc[i][3]);
-      }
-    }
-  }
-}
+using namespace dense;
 
 template <int K, int N, int TM, int ACT>
 __global__ void __launch_bounds__(kT, K <= 64 ? 3 : 2)
@@ -213,36 +139,7 @@ dense_bwd_kernel(const float *__restrict__ dY, const float *__restrict__ Y, cons
       }
     }
     // dW[n0.., k0..] += dZ[m][n0..] * X[m][k0..]   (rows beyond M are zero in both tiles)
-#pragma unroll 4
-    for (int m = 0; m < BM; ++m) {
-      float z[TN], x[TK];
-#pragma unroll
-      for (int a = 0; a < TN; a += (TN >= 4 ? 4 : TN)) {
-        if constexpr (TN >= 4) {
-          const float4 v = *reinterpret_cast<const float4 *>(Zs + m * (N + 4) + n0 + a);
-          z[a] = v.x; z[a + 1] = v.y; z[a + 2] = v.z; z[a + 3] = v.w;
-        } else {
-          const float2 v = *reinterpret_cast<const float2 *>(Zs + m * (N + 4) + n0 + a);
-          z[a] = v.x; z[a + 1] = v.y;
-        }
-      }
-#pragma unroll
-      for (int b = 0; b < TK; b += (TK >= 4 ? 4 : TK)) {
-        if constexpr (TK >= 4) {
-          const float4 v = *reinterpret_cast<const float4 *>(Xs + m * (K + 4) + k0 + b);
-          x[b] = v.x; x[b + 1] = v.y; x[b + 2] = v.z; x[b + 3] = v.w;
-        } else {
-          const float2 v = *reinterpret_cast<const float2 *>(Xs + m * (K + 4) + k0 + b);
-          x[b] = v.x; x[b + 1] = v.y;
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < TN; ++a) {
-        if (tk == 0) db[a] += z[a];
-#pragma unroll
-        for (int b = 0; b < TK; ++b) dw[a][b] = fmaf(z[a], x[b], dw[a][b]);
-      }
-    }
+    tile_outer<N, K, BM, TN, TK>(dw, db, Zs, n0, Xs, k0, tk == 0);
   }
   float *p = partial + (size_t)blockIdx.x * (N * K + N);
 #pragma unroll

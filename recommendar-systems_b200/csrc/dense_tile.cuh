@@ -1,0 +1,125 @@
+// Shared pieces of the fp32 FMA tile kernels for the d x d dense layers (dense_small.cu) and the
+// fused SMORE side network (side_net.cu): activation helpers, the two-phase global -> shared row
+// stager, the register-tile product and the dW outer-product accumulation.
+#pragma once
+#include "common.cuh"
+
+namespace mmrec {
+namespace dense {
+
+constexpr int kT = 256;
+
+enum Act { kNone = 0, kTanh = 1, kSigmoid = 2 };
+
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float z) {
+  if constexpr (ACT == kTanh) return tanhf(z);
+  if constexpr (ACT == kSigmoid) return 1.f / (1.f + expf(-z));
+  return z;
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd(float dy, float y) {
+  if constexpr (ACT == kTanh) return dy * (1.f - y * y);
+  if constexpr (ACT == kSigmoid) return dy * ((1.f - y) * y);
+  return dy;
+}
+
+template <int K, int N, int TM>
+struct Tile {
+  static constexpr int CG = N / 4;          // column groups (4 output columns each)
+  static constexpr int RG = kT / CG;        // row groups
+  static constexpr int BM = RG * TM;        // rows per tile
+  static constexpr int XP = K + 4;          // pitch of a staged X row (floats)
+};
+
+// Rows [m0, m0+BM) of a row-major [M, C] array on their way to shared memory (pitch C+4; rows
+// >= M are zero), in two phases: load() puts every global load of the thread in flight, store()
+// parks the values. Whatever sits between the two (the W staging of the first tile) overlaps the
+// DRAM round trip instead of adding one.
+template <int C, int BM>
+struct RowStage {
+  static constexpr int V = C / 4, PER = BM * V / kT;
+  static_assert(BM * V % kT == 0, "tile must be a multiple of the CTA");
+  float4 v[PER];
+  __device__ __forceinline__ void load(const float *__restrict__ src, int m0, int M) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + i * kT, r = idx / V, c4 = idx % V;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M) v[i] = ldg4(src + (size_t)(m0 + r) * C + c4 * 4);
+    }
+  }
+  __device__ __forceinline__ void store(float *dst) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + i * kT, r = idx / V, c4 = idx % V;
+      *reinterpret_cast<float4 *>(dst + r * (C + 4) + c4 * 4) = v[i];
+    }
+  }
+};
+
+// acc[i][0..3] += sum_k A[row_i][k] * B[k][c0..c0+3]; A staged with pitch KK+4, B k-major pitch NB
+template <int KK, int TM, int RG, int NB>
+__device__ __forceinline__ void tile_mma(float (&acc)[TM][4], const float *__restrict__ As, int rg,
+                                         const float *__restrict__ Bs, int c0) {
+#pragma unroll 4
+  for (int k4 = 0; k4 < KK / 4; ++k4) {
+    float4 a[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+      a[i] = *reinterpret_cast<const float4 *>(As + (rg + RG * i) * (KK + 4) + k4 * 4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 b = *reinterpret_cast<const float4 *>(Bs + (k4 * 4 + kk) * NB + c0);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+        acc[i][0] = fmaf(av, b.x, acc[i][0]);
+        acc[i][1] = fmaf(av, b.y, acc[i][1]);
+        acc[i][2] = fmaf(av, b.z, acc[i][2]);
+        acc[i][3] = fmaf(av, b.w, acc[i][3]);
+      }
+    }
+  }
+}
+
+
+// dw[a][b] += sum_m Z[m][n0 + a] * X[m][k0 + b] over the BM staged rows (pitches NN+4 / KK+4);
+// db[a] += sum_m Z[m][n0 + a] in the threads with `with_db`. TN, TK in {2, 4, 8}.
+template <int NN, int KK, int BM, int TN, int TK>
+__device__ __forceinline__ void tile_outer(float (&dw)[TN][TK], float (&db)[TN], const float *__restrict__ Zs, int n0,
+                                           const float *__restrict__ Xs, int k0, bool with_db) {
+#pragma unroll 4
+  for (int m = 0; m < BM; ++m) {
+    float z[TN], x[TK];
+#pragma unroll
+    for (int a = 0; a < TN; a += (TN >= 4 ? 4 : TN)) {
+      if constexpr (TN >= 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(Zs + m * (NN + 4) + n0 + a);
+        z[a] = v.x; z[a + 1] = v.y; z[a + 2] = v.z; z[a + 3] = v.w;
+      } else {
+        const float2 v = *reinterpret_cast<const float2 *>(Zs + m * (NN + 4) + n0 + a);
+        z[a] = v.x; z[a + 1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < TK; b += (TK >= 4 ? 4 : TK)) {
+      if constexpr (TK >= 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(Xs + m * (KK + 4) + k0 + b);
+        x[b] = v.x; x[b + 1] = v.y; x[b + 2] = v.z; x[b + 3] = v.w;
+      } else {
+        const float2 v = *reinterpret_cast<const float2 *>(Xs + m * (KK + 4) + k0 + b);
+        x[b] = v.x; x[b + 1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < TN; ++a) {
+      if (with_db) db[a] += z[a];
+#pragma unroll
+      for (int b = 0; b < TK; ++b) dw[a][b] = fmaf(z[a], x[b], dw[a][b]);
+    }
+  }
+}
+
+}  // namespace dense
+}  // namespace mmrec

@@ -327,17 +327,35 @@ infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
       }
     }
     __syncthreads();
-    // out[own][:] += sum_x G[own][x] * Other[x][:]
-#pragma unroll 4
-    for (int x = 0; x < kTile; ++x) {
-      float ov[CW];
+    // out[own][:] += sum_x G[own][x] * Other[x][:]   (16-byte shared loads: 8 per 64 FMAs)
+#pragma unroll 2
+    for (int x = 0; x < kTile; x += 4) {
+      float4 g4[4];
 #pragma unroll
-      for (int c = 0; c < CW; ++c) ov[c] = sOther[x * LD + tx * CW + c];
+      for (int i = 0; i < 4; ++i) g4[i] = *reinterpret_cast<const float4 *>(sG + (ty + 16 * i) * GL + x);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float g = sG[(ty + 16 * i) * GL + x];
+      for (int xx = 0; xx < 4; ++xx) {
+        float ov[CW];
+        const float *src = sOther + (x + xx) * LD + tx * CW;
+        if constexpr (CW % 4 == 0) {
 #pragma unroll
-        for (int c = 0; c < CW; ++c) out[i][c] = fmaf(g, ov[c], out[i][c]);
+          for (int c = 0; c < CW; c += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(src + c);
+            ov[c] = v.x; ov[c + 1] = v.y; ov[c + 2] = v.z; ov[c + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < CW; c += 2) {
+            const float2 v = *reinterpret_cast<const float2 *>(src + c);
+            ov[c] = v.x; ov[c + 1] = v.y;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float g = xx == 0 ? g4[i].x : xx == 1 ? g4[i].y : xx == 2 ? g4[i].z : g4[i].w;
+#pragma unroll
+          for (int c = 0; c < CW; ++c) out[i][c] = fmaf(g, ov[c], out[i][c]);
+        }
       }
     }
   }

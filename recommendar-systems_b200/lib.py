@@ -47,6 +47,11 @@ SIGNATURES = {
     "mmrec_dense_act_bwd_workspace_bytes": (_sz, [_i32, _i32]),
     "mmrec_dense_act_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "mmrec_dense_act_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "mmrec_smore_side_supported": (C.c_int, [_i32]),
+    "mmrec_smore_side_bwd_workspace_bytes": (_sz, [_i32, _i32]),
+    "mmrec_smore_side_fwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
+    "mmrec_smore_side_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                           _p, _i32, _i32, _p]),
     "mmrec_adam_step_f32": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double,
                                       C.c_double, _p]),
     "mmrec_axpy_multi_f32": (C.c_int, [_p, _p, _p, _i32, _p, _f32, _p]),

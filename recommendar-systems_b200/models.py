@@ -546,7 +546,18 @@ class SMORE(_MultiViewBase):
         image_embeds = self._view(image_item, self.image_original_adj)
         text_embeds = self._view(text_item, self.text_original_adj)
         fusion_embeds = self._view(fusion_item, self.fusion_adj)
-        # modality-aware preference module (smore.py:321-341): dense side network, torch ops
+        # modality-aware preference module (smore.py:321-341): one fused kernel for d = 32 / 64
+        if ops.smore_side_supported(self.embedding_dim):
+            masks = None
+            if self.training and self.dropout_rate > 0:
+                # the three nn.Dropout masks (smore.py:331-333) drawn in one call
+                masks = torch.nn.functional.dropout(
+                    torch.ones(3, *content.shape, dtype=content.dtype, device=content.device),
+                    p=self.dropout_rate, training=True)
+            layers = (self.query_v[0], self.query_v[2], self.query_t[0], self.query_t[2],
+                      self.gate_image_prefer[0], self.gate_text_prefer[0], self.gate_fusion_prefer[0])
+            all_e, side = ops.smore_side(fusion_embeds, image_embeds, text_embeds, content, layers, masks)
+            return all_e, side, content
         agg_image = self.softmax(self.query_v(fusion_embeds)) * image_embeds
         agg_text = self.softmax(self.query_t(fusion_embeds)) * text_embeds
         image_prefer = self.dropout(self.gate_image_prefer(content))

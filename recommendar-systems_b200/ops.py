@@ -431,6 +431,76 @@ class DenseStack(torch.nn.Sequential):
         return x
 
 
+# ------------------------------------------------------------------- SMORE side network (fused)
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+class _SmoreSide(torch.autograd.Function):
+    """smore.py:321-341 in one forward / one backward launch (mmrec_smore_side_*_f32).
+    apply(F, V, T, C, masks, W0, b0, ..., W6, b6) -> (all_embeds, side_embeds)."""
+
+    @staticmethod
+    def forward(ctx, F, V, T, C_, masks, *wb):
+        F, V, T, C_ = _f32c(F), _f32c(V), _f32c(T), _f32c(C_)
+        Ws = [_f32c(w) for w in wb[0::2]]
+        bs = [None if b is None else _f32c(b) for b in wb[1::2]]
+        masks = None if masks is None else _f32c(masks)
+        n, d = F.shape
+        saved = torch.empty(7, n, d, dtype=torch.float32, device=F.device)
+        side, all_e = torch.empty_like(F), torch.empty_like(F)
+        lib.call("mmrec_smore_side_fwd_f32", lib.ptr(F), lib.ptr(V), lib.ptr(T), lib.ptr(C_),
+                 _ptr_array(Ws), _ptr_array(bs), lib.ptr(masks), lib.ptr(saved), lib.ptr(side),
+                 lib.ptr(all_e), n, d, lib.stream())
+        ctx.has_mask = masks is not None
+        ctx.has_bias = [b is not None for b in bs]
+        ctx.save_for_backward(F, V, T, C_, saved, *Ws, *[b for b in bs if b is not None],
+                              *([masks] if masks is not None else []))
+        return all_e, side
+
+    @staticmethod
+    def backward(ctx, g_all, g_side):
+        t = ctx.saved_tensors
+        F, V, T, C_, saved = t[:5]
+        Ws = list(t[5:12])
+        rest = list(t[12:])
+        bs = [rest.pop(0) if hb else None for hb in ctx.has_bias]
+        masks = rest.pop(0) if ctx.has_mask else None
+        n, d = F.shape
+        g_all = None if g_all is None else _f32c(g_all)
+        g_side = None if g_side is None else _f32c(g_side)
+        dF, dV, dT, dC = (torch.empty_like(F) for _ in range(4))
+        dWs = [torch.empty_like(w) for w in Ws]
+        dbs = [None if b is None else torch.empty_like(b) for b in bs]
+        ws = torch.empty(lib.load().mmrec_smore_side_bwd_workspace_bytes(n, d) // 4, dtype=torch.float32,
+                         device=F.device)
+        lib.call("mmrec_smore_side_bwd_f32", lib.ptr(g_all), lib.ptr(g_side), lib.ptr(F), lib.ptr(V),
+                 lib.ptr(T), lib.ptr(C_), _ptr_array(Ws), _ptr_array(bs), lib.ptr(masks), lib.ptr(saved),
+                 lib.ptr(dF), lib.ptr(dV), lib.ptr(dT), lib.ptr(dC), _ptr_array(dWs), _ptr_array(dbs),
+                 lib.ptr(ws), n, d, lib.stream())
+        grads = []
+        for dw, db in zip(dWs, dbs):
+            grads += [dw, db]
+        return (dF, dV, dT, dC, None, *grads)
+
+
+def smore_side_supported(d):
+    return bool(lib.load().mmrec_smore_side_supported(int(d)))
+
+
+def smore_side(fusion, image, text, content, layers, masks=None):
+    """Fused modality-aware preference module. `layers` = the seven nn.Linear modules in the
+    order query_v.0, query_v.2, query_t.0, query_t.2, gate_image_prefer.0, gate_text_prefer.0,
+    gate_fusion_prefer.0; masks = [3, n, d] dropout multipliers or None.
+    Returns (content + side, side)."""
+    lib.require_cuda(fusion, image, text, content)
+    wb = []
+    for m in layers:
+        wb += [m.weight, m.bias]
+    return _SmoreSide.apply(fusion, image, text, content, masks, *wb)
+
+
 # -------------------------------------------------------------------------------- score + top-K
 def choose_splits(n_users, n_items):
     """Item-range splits so that (user tiles x splits) is close to one wave of 148 CTAs (the

@@ -281,6 +281,70 @@ def test_dense_stack_keeps_reference_state_dict_keys():
     assert rel(ours(x), ref(x)) < 1e-5
 
 
+def _side_reference(F, V, T, C, layers, masks):
+    """smore.py:321-341 written with plain torch ops (float64)."""
+    lin = torch.nn.functional.linear
+    q = lambda a, b, x: lin(torch.tanh(lin(x, a.weight, a.bias)), b.weight)
+    agg_i = torch.softmax(q(layers[0], layers[1], F), dim=-1) * V
+    agg_t = torch.softmax(q(layers[2], layers[3], F), dim=-1) * T
+    gate = lambda l: torch.sigmoid(lin(C, l.weight, l.bias))
+    m = masks if masks is not None else torch.ones(3, *C.shape, dtype=C.dtype)
+    side = torch.mean(torch.stack([m[0] * gate(layers[4]) * agg_i, m[1] * gate(layers[5]) * agg_t,
+                                   m[2] * gate(layers[6]) * F]), dim=0)
+    return C + side, side
+
+
+@pytest.mark.parametrize("n,d,drop", [(26495, 64, 0.1), (7050, 64, 0.0), (1, 64, 0.0), (333, 32, 0.2),
+                                      (70001, 64, 0.0)])
+def test_smore_side_network_fused_forward_backward(n, d, drop):
+    """K14: the fused preference module (one fwd + one bwd launch) vs float64 torch autograd."""
+    ops = pkg("ops")
+    torch.manual_seed(41)
+    mk = lambda bias: torch.nn.Linear(d, d, bias=bias)
+    layers64 = [mk(True), mk(False), mk(True), mk(False), mk(True), mk(True), mk(True)]
+    for l in layers64:
+        l.weight.data *= 3.0                   # spread the softmax / saturate some gates
+    ins64 = [torch.randn(n, d) for _ in range(4)]
+    masks64 = None
+    if drop > 0:
+        masks64 = (torch.rand(3, n, d) >= drop).float() / (1 - drop)
+    g_all, g_side = torch.randn(n, d), torch.randn(n, d)
+    # ours
+    layers = [torch.nn.Linear(d, d, bias=l.bias is not None).to(DEV) for l in layers64]
+    for a, b in zip(layers, layers64):
+        a.load_state_dict(b.state_dict())
+    ins = [t.to(DEV).requires_grad_(True) for t in ins64]
+    all_e, side = ops.smore_side(*ins, layers, None if masks64 is None else masks64.to(DEV))
+    (all_e * g_all.to(DEV)).sum().add((side * g_side.to(DEV)).sum()).backward()
+    # reference
+    ref_layers = [l.double() for l in layers64]
+    rin = [t.double().requires_grad_(True) for t in ins64]
+    ra, rs = _side_reference(*rin, ref_layers, None if masks64 is None else masks64.double())
+    (ra * g_all.double()).sum().add((rs * g_side.double()).sum()).backward()
+    tol = 1e-5
+    assert rel(all_e, ra) < tol and rel(side, rs) < tol
+    for name, a, b in zip("FVTC", ins, rin):
+        assert rel(a.grad, b.grad) < tol, name
+    for i, (a, b) in enumerate(zip(layers, ref_layers)):
+        assert rel(a.weight.grad, b.weight.grad) < tol, i
+        if b.bias is not None:
+            assert rel(a.bias.grad, b.bias.grad) < tol, i
+    # only one of the two outputs used downstream (d_side = None path); run-to-run reproducible
+    ins2 = [t.to(DEV).requires_grad_(True) for t in ins64]
+    for l in layers:
+        l.zero_grad()
+    a2, s2 = ops.smore_side(*ins2, layers, None if masks64 is None else masks64.to(DEV))
+    assert torch.equal(a2, all_e) and torch.equal(s2, side)
+    (a2 * g_all.to(DEV)).sum().backward()
+    rin2 = [t.double().requires_grad_(True) for t in ins64]
+    for l in ref_layers:
+        l.zero_grad()
+    ra2, _ = _side_reference(*rin2, ref_layers, None if masks64 is None else masks64.double())
+    (ra2 * g_all.double()).sum().backward()
+    assert rel(ins2[0].grad, rin2[0].grad) < tol and rel(ins2[3].grad, rin2[3].grad) < tol
+    assert rel(layers[0].weight.grad, ref_layers[0].weight.grad) < tol
+
+
 @pytest.mark.parametrize("n_users,n_items,d,k,splits", [(64, 96, 64, 50, 1), (300, 1000, 64, 50, 4),
                                                        (129, 777, 128, 20, 3), (1000, 5000, 32, 50, None)])
 def test_score_mask_topk_matches_stable_sort(n_users, n_items, d, k, splits):
