@@ -1,0 +1,365 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), 3xTF32 split: the
+// modality projections of SMORE / MGCN / FREEDOM and their two backward GEMMs (K4), i.e. the only
+// dense contractions of a training step that touch the 115 MB feature tables:
+//   forward  y  = x W^T      x [I, F] (F = 4096 / 384), W [d, F]      A K-major,  B K-major, split-K
+//   dW       dW = dy^T x     reduction over the I items               A MN-major, B MN-major, split-K,
+//                                                                     computed as dW^T and stored transposed
+//   dx       dx = dy W       output [I, F]                            A K-major,  B MN-major, N ranges
+// One CTA owns 128 rows of the UMMA M dimension. Warp roles:
+//   warps 4-11 producers : stream 32-wide K blocks of both operands from HBM/L2 (coalesced float4,
+//                          prefetched one block ahead in registers), split every value into tf32
+//                          hi/lo and store both halves into swizzled canonical UMMA tiles (K-major
+//                          SWIZZLE_128B or MN-major SWIZZLE_128B_BASE32B, so neither backward
+//                          GEMM transposes the table);
+//   warp  12   MMA       : tcgen05.mma kind::tf32, lo*hi + hi*lo + hi*hi per K step, fp32
+//                          accumulation in one of two TMEM buffers; tcgen05.commit hands the smem
+//                          stage back to the producers and the accumulator to the epilogue;
+//   warps 0-3  epilogue  : tcgen05.ld (TMEM lane = output row), bias, plain or transposed store.
+// The kernels are HBM-bound by construction: per 16 KB of table streamed an SM issues 12 MMAs
+// (384 tensor cycles) and ~200 producer issue slots against ~700 cycles of its HBM share.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace mmrec {
+namespace {
+
+using namespace tc05;
+
+constexpr int kBM = 128;            // UMMA M
+constexpr int kKB = 32;             // floats of K per pipeline stage (one 128-byte swizzle atom)
+constexpr int kChunkKB = 2;         // K blocks per tensor-core accumulation chain
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kThreadsG = 128 + kProdThreads + 32;
+
+struct GemmArgs {
+  const float *A, *B, *bias;
+  float *C;
+  int M, N, K;                      // UMMA-space problem: C[M, N] = A[M, K] B[N, K]^T
+  int lda, ldb, ldc;
+  int kb_per_split;                 // K blocks per blockIdx.y
+  int nt_per_cta;                   // N tiles per blockIdx.z
+  size_t slab;                      // floats between the output slabs of consecutive K splits
+};
+
+// Byte offset of element chunk inside one operand tile (extent E along M/N, 32 along K).
+// K-major: 16-byte chunk c (4 floats of K) of row r.  MN-major: chunk q (4 floats of M/N) of K row k.
+template <int E>
+__device__ __forceinline__ uint32_t off_kmajor(int r, int c) {
+  return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+}
+template <int E>
+__device__ __forceinline__ uint32_t off_mnmajor(int k, int q) {
+  // SWIZZLE_128B_BASE32B: atoms of 4 K rows x 128 B; [K group][M/N atom] order; 32-byte chunks swizzled
+  return (uint32_t)((k >> 2) * (E / 32) + (q >> 3)) * 512u + (uint32_t)(k & 3) * 128u +
+         (uint32_t)(((((q & 7) >> 1) ^ (k & 3)) << 5) | ((q & 1) << 4));
+}
+
+// One operand block [E x 32] in flight: PER float4 per producer thread.
+template <int E, bool MN>
+struct Block {
+  static constexpr int PER = E * 8 / kProdThreads;
+  static_assert(E * 8 % kProdThreads == 0, "operand block must be a multiple of the producer count");
+  float4 v[PER];
+  // src element (i, k): K-major src[i * ld + k]; MN-major src[k * ld + i]. i < lim_i, k < lim_k else 0.
+  __device__ __forceinline__ void load(const float *__restrict__ src, int ld, int i0, int lim_i, int k0, int lim_k,
+                                       int ptid) {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int idx = ptid + j * kProdThreads;
+      int i, k;
+      if constexpr (!MN) { i = i0 + idx / 8; k = k0 + (idx % 8) * 4; }
+      else { k = k0 + idx / (E / 4); i = i0 + (idx % (E / 4)) * 4; }
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < lim_i && k < lim_k) v[j] = ldg4(MN ? src + (size_t)k * ld + i : src + (size_t)i * ld + k);
+    }
+  }
+  __device__ __forceinline__ void store(uint8_t *hi_tile, uint8_t *lo_tile, int ptid) const {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int idx = ptid + j * kProdThreads;
+      const uint32_t off = MN ? off_mnmajor<E>(idx / (E / 4), idx % (E / 4)) : off_kmajor<E>(idx / 8, idx % 8);
+      float4 hi, lo;
+      split_tf32x4(v[j], hi, lo);
+      *reinterpret_cast<float4 *>(hi_tile + off) = hi;
+      *reinterpret_cast<float4 *>(lo_tile + off) = lo;
+    }
+  }
+};
+
+template <int NT>
+struct GCfg {
+  static constexpr uint32_t A_HALF = kBM * 128, B_HALF = NT * 128;
+  static constexpr uint32_t STAGE = 2 * (A_HALF + B_HALF);
+  static constexpr int STAGES = NT <= 64 ? 4 : NT <= 128 ? 3 : 2;
+  static constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
+};
+
+template <bool A_MN, bool B_MN, int NT, bool TRANS_OUT>
+__global__ void __launch_bounds__(kThreadsG, 1)
+gemm_tc05_kernel(const GemmArgs g) {
+  using C = GCfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE);
+  uint64_t *full = bars, *empty = bars + C::STAGES, *tfull = empty + C::STAGES, *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+  // warp index through a broadcast: provably warp-uniform, so role branches and the MMA issue
+  // loop (descriptor arithmetic included) compile to the uniform datapath
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int m0 = blockIdx.x * kBM;
+  const int n_kb_total = (g.K + kKB - 1) / kKB;
+  const int kb_begin = blockIdx.y * g.kb_per_split, kb_end = min(n_kb_total, kb_begin + g.kb_per_split);
+  const int n_nt_total = (g.N + NT - 1) / NT;
+  const int nt_begin = blockIdx.z * g.nt_per_cta, nt_end = min(n_nt_total, nt_begin + g.nt_per_cta);
+  const int n_kb = max(0, kb_end - kb_begin), n_nt = max(0, nt_end - nt_begin);
+  const int n_iter = n_kb * n_nt;
+  const int n_ck = (n_kb + kChunkKB - 1) / kChunkKB;   // accumulator chunks per N tile
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, kProdThreads); mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp >= 4 && warp < 12) {
+    // =============================== producers ===============================================
+    // PD K blocks of loads are in flight per thread (72-96 KB per SM): the stream is latency-bound
+    // otherwise -- one block per DRAM round trip is ~20 GB/s per SM, half of its HBM share.
+    const int ptid = tid - 128;
+    constexpr int PD = NT <= 64 ? 4 : 2;
+    Block<kBM, A_MN> a[PD];
+    Block<NT, B_MN> b[PD];
+    auto load_iter = [&](Block<kBM, A_MN> &ab, Block<NT, B_MN> &bb, int it) {
+      const int nt = nt_begin + it / n_kb, kb = kb_begin + it % n_kb;
+      const int k_lim = min(g.K, kb_end * kKB);
+      ab.load(g.A, g.lda, m0, g.M, kb * kKB, k_lim, ptid);
+      bb.load(g.B, g.ldb, nt * NT, g.N, kb * kKB, k_lim, ptid);
+    };
+#pragma unroll
+    for (int u = 0; u < PD; ++u)
+      if (u < n_iter) load_iter(a[u], b[u], u);
+    for (int it0 = 0; it0 < n_iter; it0 += PD) {
+#pragma unroll
+      for (int u = 0; u < PD; ++u) {
+        const int it = it0 + u;
+        if (it < n_iter) {
+          const int s = it % C::STAGES;
+          mbar_wait(empty + s, ((it / C::STAGES) & 1) ^ 1);
+          uint8_t *stage = smem + s * C::STAGE;
+          a[u].store(stage, stage + C::A_HALF, ptid);
+          b[u].store(stage + 2 * C::A_HALF, stage + 2 * C::A_HALF + C::B_HALF, ptid);
+          fence_proxy_async_smem();
+          mbar_arrive(full + s);
+          if (it + PD < n_iter) load_iter(a[u], b[u], it + PD);
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // =============================== MMA issuer ==============================================
+    constexpr uint32_t idesc = idesc_tf32(kBM, NT, A_MN, B_MN);
+    // K-major (SWIZZLE_128B): SBO = 1024 (next 8 rows); a K step of 8 floats is +32 bytes in the atom.
+    // MN-major (SWIZZLE_128B_BASE32B): LBO = 512 (next 32 floats of M/N), SBO = next 4 K rows;
+    // a K step of 8 is two such groups.
+    constexpr uint32_t a_sbo = A_MN ? (kBM / 32) * 512 : 1024, b_sbo = B_MN ? (NT / 32) * 512 : 1024;
+    constexpr uint32_t a_step = A_MN ? 2 * a_sbo : 32, b_step = B_MN ? 2 * b_sbo : 32;
+    for (int it = 0; it < n_iter; ++it) {
+      // accumulator chunk: kChunkKB K blocks of one N tile; chunks alternate between the two buffers
+      const int s = it % C::STAGES, j = it / n_kb, kb = it % n_kb;
+      const int ck = j * n_ck + kb / kChunkKB, kc = kb % kChunkKB, buf = ck & 1;
+      mbar_wait(full + s, (it / C::STAGES) & 1);
+      if (kc == 0) mbar_wait(tempty + buf, ((ck >> 1) & 1) ^ 1);
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * NT;
+      const uint32_t st = smem_base + s * C::STAGE;
+      const uint64_t a_hi = A_MN ? smem_desc_mn32(st, 512, a_sbo) : smem_desc_sw128(st, 16, 1024);
+      const uint64_t a_lo = A_MN ? smem_desc_mn32(st + C::A_HALF, 512, a_sbo) : smem_desc_sw128(st + C::A_HALF, 16, 1024);
+      const uint64_t b_hi = B_MN ? smem_desc_mn32(st + 2 * C::A_HALF, 512, b_sbo)
+                                 : smem_desc_sw128(st + 2 * C::A_HALF, 16, 1024);
+      const uint64_t b_lo = B_MN ? smem_desc_mn32(st + 2 * C::A_HALF + C::B_HALF, 512, b_sbo)
+                                 : smem_desc_sw128(st + 2 * C::A_HALF + C::B_HALF, 16, 1024);
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t a0 = pass == 0 ? a_lo : a_hi;
+        const uint64_t b0 = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+        for (int ks = 0; ks < kKB / 8; ++ks) {
+          const uint64_t ad = a0 + ((ks * a_step) >> 4);
+          const uint64_t bd = b0 + ((ks * b_step) >> 4);
+          const uint32_t accumulate = (kc | pass | ks) != 0;
+          if (elect_one()) umma_tf32_ss(d_tmem, ad, bd, idesc, accumulate);
+        }
+      }
+      if (elect_one()) {
+        umma_commit(empty + s);
+        if (kc == kChunkKB - 1 || kb == n_kb - 1) umma_commit(tfull + buf);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== epilogue ================================================
+    // The tensor core truncates its fp32 accumulator after every instruction, a bias that grows with
+    // the length of the chain; chains are therefore cut every kChunkKB K blocks (24 instructions) and
+    // the chunks are added here in registers with round-to-nearest (fp32-class accuracy at K = 20k+).
+    const int m = m0 + warp * 32 + lane;
+    float *Cs = g.C + (size_t)blockIdx.y * g.slab;
+    for (int j = 0; j < (n_kb > 0 ? n_nt : 0); ++j) {
+      const int n0 = (nt_begin + j) * NT;
+      float acc[NT];
+#pragma unroll
+      for (int q = 0; q < NT; ++q) acc[q] = 0.f;
+      for (int c = 0; c < n_ck; ++c) {
+        const int ck = j * n_ck + c, buf = ck & 1;
+        mbar_wait(tfull + buf, (ck >> 1) & 1);
+        fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * NT;
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) acc[c0 + q] += __uint_as_float(r[q]);
+        }
+        fence_before_sync();
+        mbar_arrive(tempty + buf);
+      }
+      if (m < g.M) {
+        if constexpr (!TRANS_OUT) {
+          float *dst = Cs + (size_t)m * g.ldc + n0;
+#pragma unroll
+          for (int q = 0; q < NT; q += 4) {
+            if (n0 + q < g.N) {
+              float4 o = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
+              if (g.bias != nullptr) {
+                const float4 bv = ldg4(g.bias + n0 + q);
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              }
+              *reinterpret_cast<float4 *>(dst + q) = o;
+            }
+          }
+        } else {
+          // C^T: lane = column of the stored matrix, so every register is one coalesced row segment
+#pragma unroll
+          for (int q = 0; q < NT; ++q)
+            if (n0 + q < g.N) Cs[(size_t)(n0 + q) * g.ldc + m] = acc[q];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 12) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <bool A_MN, bool B_MN, int NT, bool TRANS_OUT>
+int launch_tc05(const GemmArgs &g, int k_splits, int n_chunks, cudaStream_t stream) {
+  using C = GCfg<NT>;
+  const size_t smem = 1024 + (size_t)C::STAGES * C::STAGE + (2 * C::STAGES + 4) * 8 + 16;
+  auto kern = gemm_tc05_kernel<A_MN, B_MN, NT, TRANS_OUT>;
+  static bool attr = false;
+  if (!attr) {
+    MMREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid((g.M + kBM - 1) / kBM, k_splits, n_chunks);
+  kern<<<grid, kThreadsG, smem, stream>>>(g);
+  MMREC_CHECK_LAUNCH("gemm_tc05_kernel");
+  return MMREC_OK;
+}
+
+template <bool A_MN, bool B_MN, bool TRANS_OUT>
+int launch_tc05_nt(int nt, const GemmArgs &g, int k_splits, int n_chunks, cudaStream_t stream) {
+  switch (nt) {
+    case 32: return launch_tc05<A_MN, B_MN, 32, TRANS_OUT>(g, k_splits, n_chunks, stream);
+    case 64: return launch_tc05<A_MN, B_MN, 64, TRANS_OUT>(g, k_splits, n_chunks, stream);
+    case 128: return launch_tc05<A_MN, B_MN, 128, TRANS_OUT>(g, k_splits, n_chunks, stream);
+    default: return 1;
+  }
+}
+
+}  // namespace
+
+// Which (layout, shape) combinations run on the tcgen05 kernel. The caller-facing problem is
+// C[M,N] = op(A) op(B) with the a_kcontig / b_kcontig flags of mmrec_gemm_tf32x3_f32.
+//   kind 1: A [M,K], B [N,K]      (forward)   -> split-K, N tile = N
+//   kind 2: A [K,M], B [K,N]      (dW)        -> computed as C^T: UMMA M = N, UMMA N = M, split-K
+//   kind 3: A [M,K], B [K,N]      (dx)        -> N ranges, no split-K
+int gemm_tc05_kind(int M, int N, int K, int a_kcontig, int b_kcontig) {
+  auto tile_ok = [](int n) { return n == 32 || n == 64 || n == 128; };
+  if (a_kcontig && b_kcontig) return (M >= 1024 && K >= 256 && tile_ok(N) && K % 4 == 0) ? 1 : 0;
+  if (!a_kcontig && !b_kcontig) return (N >= 1024 && K >= 256 && tile_ok(M) && N % 4 == 0) ? 2 : 0;
+  if (a_kcontig && !b_kcontig) return (M >= 1024 && N >= 1024 && N % 128 == 0 && K % 4 == 0 && K <= 256) ? 3 : 0;
+  return 0;
+}
+
+// Pick the number of equal parts (<= max_parts) of `units` work units per row tile that wastes the
+// least of the last wave: one CTA per SM is resident (192 KB of shared memory), so 448 CTAs would
+// run as 3 full waves + 4 stragglers, and every wave pays its own pipeline fill (first DRAM round
+// trips, TMEM allocation). Cost = waves x (units per CTA + fill).
+static int best_parts(int row_tiles, int units, int max_parts, int fill) {
+  int best = 1;
+  long best_cost = -1;
+  for (int p = 1; p <= max_parts; ++p) {
+    const int per = (units + p - 1) / p, parts = (units + per - 1) / per;
+    if (parts != p) continue;
+    const long ctas = (long)row_tiles * parts, waves = (ctas + kNumSMs - 1) / kNumSMs;
+    const long cost = waves * (per + fill);            // fill: pipeline ramp of a CTA, in work units
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = p; }
+  }
+  return best;
+}
+
+int gemm_tc05_splits(int M, int N, int K, int kind) {
+  if (kind == 3) return 1;
+  const int m_tiles = kind == 2 ? (N + kBM - 1) / kBM : (M + kBM - 1) / kBM;
+  const int n_kb = (K + kKB - 1) / kKB;
+  return best_parts(m_tiles, (n_kb + kChunkKB - 1) / kChunkKB, 32, 3);
+}
+
+// Returns MMREC_OK, a negative error, or 1 when the shape is not covered.
+int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcontig, const float *bias, float *C,
+                       int M, int N, int K, int splits, float *ws, cudaStream_t stream) {
+  const int kind = gemm_tc05_kind(M, N, K, a_kcontig, b_kcontig);
+  if (kind == 0) return 1;
+  GemmArgs g{};
+  const int n_kb = (K + kKB - 1) / kKB, n_units = (n_kb + kChunkKB - 1) / kChunkKB;
+  g.kb_per_split = (n_units + splits - 1) / splits * kChunkKB;
+  const int k_splits = (n_kb + g.kb_per_split - 1) / g.kb_per_split;
+  if (kind != 3 && k_splits != splits) return 1;       // workspace laid out for another split count
+  float *out = splits > 1 ? ws : C;
+  g.bias = splits > 1 ? nullptr : bias;
+  g.slab = (size_t)M * N;
+  if (kind == 1) {
+    g.A = A; g.lda = K; g.B = B; g.ldb = K; g.C = out; g.ldc = N; g.M = M; g.N = N; g.K = K; g.nt_per_cta = 1;
+    return launch_tc05_nt<false, false, false>(N, g, k_splits, 1, stream);
+  }
+  if (kind == 2) {
+    // C^T [N, M] = B^T [N, K] * A [K, M]: UMMA A = caller's B (MN-major), UMMA B = caller's A (MN-major)
+    g.A = B; g.lda = N; g.B = A; g.ldb = M; g.C = out; g.ldc = N; g.M = N; g.N = M; g.K = K; g.nt_per_cta = 1;
+    if (bias != nullptr && splits == 1) return 1;      // bias indexes the other axis here
+    return launch_tc05_nt<true, true, true>(M, g, k_splits, 1, stream);
+  }
+  // kind 3
+  if (splits != 1) return 1;
+  g.A = A; g.lda = K; g.B = B; g.ldb = N; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K; g.bias = bias;
+  g.kb_per_split = n_kb;
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = N / 128;
+  int chunks = best_parts(m_tiles, n_tiles, n_tiles, 1);
+  g.nt_per_cta = (n_tiles + chunks - 1) / chunks;
+  chunks = (n_tiles + g.nt_per_cta - 1) / g.nt_per_cta;
+  return launch_tc05<false, true, 128, false>(g, 1, chunks, stream);
+}
+
+}  // namespace mmrec

@@ -14,6 +14,8 @@
 // fragments are read with conflict-free scalar LDS thanks to the +4 / +8 word row padding.
 // Split-K (grid.z) fills the 148 SMs when M*N is small (weight gradients); partial tiles go to a
 // workspace and are summed in split order by a second kernel (deterministic, no atomics).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mmrec {
@@ -225,11 +227,25 @@ int launch(const float *A, const float *B, const float *bias, float *C, float *w
 }
 
 }  // namespace
+
+// gemm_tc05.cu: the tcgen05 path for the table-sized projections
+int gemm_tc05_kind(int M, int N, int K, int a_kcontig, int b_kcontig);
+int gemm_tc05_splits(int M, int N, int K, int kind);
+int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcontig, const float *bias, float *C,
+                       int M, int N, int K, int splits, float *ws, cudaStream_t stream);
+static bool tc05_enabled() {
+  static const bool on = !(getenv("MMREC_GEMM_TC") && atoi(getenv("MMREC_GEMM_TC")) == 0);
+  return on;
+}
 }  // namespace mmrec
 
 using namespace mmrec;
 
 extern "C" int mmrec_gemm_splits(int32_t M, int32_t N, int32_t K, int32_t a_kcontig, int32_t b_kcontig) {
+  if (tc05_enabled()) {
+    const int kind = gemm_tc05_kind(M, N, K, a_kcontig, b_kcontig);
+    if (kind) return gemm_tc05_splits(M, N, K, kind);
+  }
   // enough CTAs for ~2 waves of 148 SMs; never split a short K
   const int bm = (!a_kcontig || M <= 64) ? 64 : 128;
   const int bn = (!b_kcontig && N > 64) ? 128 : 64;
@@ -254,6 +270,18 @@ extern "C" int mmrec_gemm_tf32x3_f32(const float *A, int32_t a_kcontig, const fl
   MMREC_REQUIRE((a_kcontig ? K : M) % 4 == 0 && (b_kcontig ? K : N) % 4 == 0, MMREC_E_BADARG,
                 "gemm: contiguous dimensions must be multiples of 4 floats");
   MMREC_REQUIRE(splits == 1 || ws, MMREC_E_WORKSPACE, "gemm: split-K needs a workspace of splits*M*N floats");
+  if (tc05_enabled()) {     // tcgen05 kernel for the table-sized projections; 1 = shape not covered
+    const int rc = gemm_tc05_dispatch(A, a_kcontig, B, b_kcontig, bias, C, M, N, K, splits, ws, stream);
+    if (rc <= 0) {
+      if (rc == MMREC_OK && splits > 1) {
+        const int64_t mn = (int64_t)M * N;
+        splitk_reduce_kernel<<<(unsigned)((mn / 4 + kThreads - 1) / kThreads), kThreads, 0, stream>>>(ws, bias, C, mn,
+                                                                                                     N, splits);
+        MMREC_CHECK_LAUNCH("splitk_reduce_kernel");
+      }
+      return rc;
+    }
+  }
   const bool big_m = a_kcontig && M > 64;
   const bool big_n = !b_kcontig && N > 64;
   if (a_kcontig && b_kcontig) {

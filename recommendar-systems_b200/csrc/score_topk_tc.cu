@@ -118,7 +118,9 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
   uint64_t *full = bars, *empty = bars + C::STAGES, *tfull = bars + 2 * C::STAGES, *tempty = tfull + kAcc;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kAcc);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a broadcast: provably warp-uniform, so role branches and the MMA issue
+  // loop (descriptor arithmetic included) compile to the uniform datapath
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int j_begin = blockIdx.y * items_per_split;
   const int j_end = min(n_items, j_begin + items_per_split);
   const int n_tiles = (j_end - j_begin + kTileN - 1) / kTileN;
@@ -149,7 +151,7 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp >= 4 && warp < 8) {
     // =============================== producers ===============================================

@@ -84,6 +84,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;                                // [61,64) SWIZZLE_128B
   return d;
 }
+// MN-major operands of 32-bit types (tf32) have exactly one swizzled layout: SWIZZLE_128B_BASE32B.
+// Atom = 4 K rows x 128 bytes (32 floats along M/N); inside a row the 32-byte chunk index is XORed
+// with (K row & 3). `lbo_bytes` steps to the next 32 floats of M/N, `sbo_bytes` to the next 4 K rows
+// (one K = 8 instruction reads two such groups). Atoms must be 512-byte aligned.
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                                // [61,64) SWIZZLE_128B_BASE32B
+  return d;
+}
 
 // Instruction descriptor for kind::tf32 (fp32 accumulate), dense, no negation.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
