@@ -91,7 +91,8 @@ template <int NT>
 struct GCfg {
   static constexpr uint32_t A_HALF = kBM * 128, B_HALF = NT * 128;
   static constexpr uint32_t STAGE = 2 * (A_HALF + B_HALF);
-  static constexpr int STAGES = NT <= 64 ? 4 : NT <= 128 ? 3 : 2;
+  static constexpr int STAGES = NT <= 32 ? 4 : NT <= 64 ? 3 : 2;
+  static constexpr uint32_t EPI = 4 * 32 * (NT + 4) * 4;   // epilogue staging: 4 warps x [32][NT + 4] floats
   static constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
 };
 
@@ -104,6 +105,7 @@ gemm_tc05_kernel(const GemmArgs g) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE);
   uint64_t *full = bars, *empty = bars + C::STAGES, *tfull = empty + C::STAGES, *tempty = tfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  float *stg = reinterpret_cast<float *>(tmem_slot + 4);     // 4 warps x [32][NT + 4] epilogue staging
 
   // warp index through a broadcast: provably warp-uniform, so role branches and the MMA issue
   // loop (descriptor arithmetic included) compile to the uniform datapath
@@ -231,26 +233,38 @@ gemm_tc05_kernel(const GemmArgs g) {
         fence_before_sync();
         mbar_arrive(tempty + buf);
       }
-      if (m < g.M) {
-        if constexpr (!TRANS_OUT) {
-          float *dst = Cs + (size_t)m * g.ldc + n0;
+      if constexpr (!TRANS_OUT) {
+        // TMEM hands every thread one ROW; storing it as-is touches 32 different 128-byte lines per
+        // instruction (16 bytes each) and the LSU serialises them -- it was the bottleneck of the dx
+        // GEMM. The warp's 32 x NT tile goes through shared memory instead and leaves as whole
+        // rows: one STG.128 per NT/4 lanes, 512 contiguous bytes per instruction.
+        constexpr int P = NT + 4, LPR = NT / 4, RPI = 32 / LPR;      // pitch, lanes per row, rows per instr
+        float *tr = stg + warp * (32 * P);
+        const int mw = m0 + warp * 32;
+        __syncwarp();
 #pragma unroll
-          for (int q = 0; q < NT; q += 4) {
-            if (n0 + q < g.N) {
-              float4 o = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
-              if (g.bias != nullptr) {
-                const float4 bv = ldg4(g.bias + n0 + q);
-                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-              }
-              *reinterpret_cast<float4 *>(dst + q) = o;
+        for (int q = 0; q < NT; q += 4)
+          *reinterpret_cast<float4 *>(tr + lane * P + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
+        __syncwarp();
+        const int cq = (lane % LPR) * 4, n = n0 + cq;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias != nullptr && n < g.N) bv = ldg4(g.bias + n);
+        if (n < g.N) {
+#pragma unroll 8
+          for (int r0 = 0; r0 < 32; r0 += RPI) {
+            const int rr = r0 + lane / LPR;
+            if (mw + rr < g.M) {
+              float4 o = *reinterpret_cast<const float4 *>(tr + rr * P + cq);
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              *reinterpret_cast<float4 *>(Cs + (size_t)(mw + rr) * g.ldc + n) = o;
             }
           }
-        } else {
-          // C^T: lane = column of the stored matrix, so every register is one coalesced row segment
-#pragma unroll
-          for (int q = 0; q < NT; ++q)
-            if (n0 + q < g.N) Cs[(size_t)(n0 + q) * g.ldc + m] = acc[q];
         }
+      } else if (m < g.M) {
+        // C^T: lane = column of the stored matrix, so every register is one coalesced row segment
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+          if (n0 + q < g.N) Cs[(size_t)(n0 + q) * g.ldc + m] = acc[q];
       }
       __syncwarp();
     }
@@ -266,7 +280,7 @@ gemm_tc05_kernel(const GemmArgs g) {
 template <bool A_MN, bool B_MN, int NT, bool TRANS_OUT>
 int launch_tc05(const GemmArgs &g, int k_splits, int n_chunks, cudaStream_t stream) {
   using C = GCfg<NT>;
-  const size_t smem = 1024 + (size_t)C::STAGES * C::STAGE + (2 * C::STAGES + 4) * 8 + 16;
+  const size_t smem = 1024 + (size_t)C::STAGES * C::STAGE + (2 * C::STAGES + 4) * 8 + 16 + C::EPI;
   auto kern = gemm_tc05_kernel<A_MN, B_MN, NT, TRANS_OUT>;
   static bool attr = false;
   if (!attr) {

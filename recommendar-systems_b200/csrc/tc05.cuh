@@ -134,14 +134,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// hi = round-to-nearest tf32(x); lo = tf32(x - hi): hi*hi + hi*lo + lo*hi reproduces the fp32
-// product to ~2^-22 on the tf32 tensor pipe (which ignores the 13 low mantissa bits of its inputs).
+// hi = round-to-nearest tf32(x); lo = x - hi (exact in fp32): hi*hi + hi*lo + lo*hi reproduces the
+// fp32 product to ~2^-21 on the tf32 tensor pipe. Three ALU instructions per value: the rounding is
+// integer arithmetic on the bit pattern (add half an ulp of tf32, clear the 13 low mantissa bits --
+// what cvt.rna.tf32.f32 does, minus its inf/nan guards, which cost 4 more instructions per value
+// and made the producer warps the bottleneck of every tcgen05 kernel here), and lo is left as a
+// full fp32: the tensor core ignores the 13 low mantissa bits of its tf32 operands by itself.
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
 }
 __device__ __forceinline__ void split_tf32x4(const float4 &v, float4 &hi, float4 &lo) {
   split_tf32(v.x, hi.x, lo.x);

@@ -1,0 +1,45 @@
+"""One launch of every hot kernel at Baby-shaped sizes (after a warm-up launch): the command ncu wraps."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+ops, G, synth = bench.pkg("ops"), bench.pkg("graph"), bench.pkg("synth")
+DEV = "cuda:0"
+gen = torch.Generator().manual_seed(3)
+I, U, d, F = 7050, 19445, 64, 4096
+N = U + I
+x = torch.randn(I, F, generator=gen).to(DEV)
+W = (torch.randn(d, F, generator=gen) * 0.05).to(DEV)
+b = torch.randn(d, generator=gen).to(DEV)
+dy = torch.randn(I, d, generator=gen).to(DEV)
+data = synth.make_dataset("baby", features=False)
+u, i = data.split(0)
+g = G.build_ui_graph(torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), data.n_users, data.n_items, "f32")
+X = torch.randn(N, d, device=DEV)
+Y = torch.empty(N, d, device=DEV)
+acc = torch.empty_like(X)
+ue, ie = torch.randn(9130, d, device=DEV), torch.randn(I, d, device=DEV)
+users = torch.arange(9130, device=DEV)
+layers = [torch.nn.Linear(d, d, bias=bb).to(DEV) for bb in (True, False, True, False, True, True, True)]
+ins = [torch.randn(N, d, device=DEV, requires_grad=True) for _ in range(4)]
+masks = torch.nn.functional.dropout(torch.ones(3, N, d, device=DEV), 0.1)
+side, content = torch.randn(N, d, device=DEV, requires_grad=True), torch.randn(N, d, device=DEV, requires_grad=True)
+bu = torch.randint(0, U, (2048,), device=DEV)
+bi = torch.randint(0, I, (2048,), device=DEV)
+for rep in range(2):
+    ops.gemm(x, True, W, True, I, d, F, b)
+    ops.gemm(dy, False, x, False, d, F, I)
+    ops.gemm(dy, True, W, False, I, F, d)
+    ops.spmm_raw(g, X, Y=Y, acc_in=X, acc_out=acc)
+    ops.score_mask_topk(ue, users, ie, 50)
+    a, s = ops.smore_side(*ins, layers, masks)
+    (a.sum() + s.sum()).backward()
+    l = ops.infonce_pair(side, content, U, bu, bi, 0.2)
+    l.backward()
+    torch.cuda.synchronize()
+print("done")
