@@ -277,6 +277,24 @@ int mmrec_score_mask_topk_simt_f32(const float *user_emb, const int64_t *users, 
                                    int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,
                                    int32_t k, int32_t n_splits, float *ws_val, int32_t *ws_idx,
                                    float *out_val, int64_t *out_idx, void *stream);
+/* ------------------------------------------------------------------------------------------
+ * Top-K metrics on the device (K15). Replaces TopKEvaluator.evaluate / _calculate_metrics
+ * (utils/topk_evaluator.py:58-143) and recall_/recall2_/precision_/ndcg_/map_
+ * (utils/metrics.py:12-109): the Python membership loop that builds the hit matrix and the numpy
+ * float64 reductions.
+ *   topk [n_users, k] int64 item ids (the evaluator's batch_matrix_list, concatenated), k <= 64
+ *   gt_rowptr [n_users + 1] / gt_items: ground-truth items per eval user, ascending int32 CSR
+ *   disc[k] = 1 / log2(r + 2), idcg_all[k] = cumsum(disc): float64, computed by the host in numpy
+ *   hits_out [n_users, k] uint8 or NULL
+ *   sums_out [5, k] float64: SUM over users of recall, cumulative hits (recall2 numerator),
+ *            precision, ndcg, map at every rank; the caller divides by n_users (recall2: by the
+ *            total number of positives) and rounds like topk_evaluator.py:101.
+ * Per-user values are bit-identical to numpy's (same float64 operations in the same order).
+ * ---------------------------------------------------------------------------------------- */
+size_t mmrec_topk_metrics_workspace_bytes(int32_t n_users);
+int mmrec_topk_metrics_f64(const int64_t *topk, int32_t n_users, int32_t k, const int32_t *gt_rowptr,
+                           const int32_t *gt_items, const double *disc, const double *idcg_all,
+                           uint8_t *hits_out, double *sums_out, void *workspace, void *stream);
 /* K-way merge of `n_lists` descending lists per user (local top-K of every rank after the
  * all-gather). Same tie rule. lists are [n_lists, n_users, k]. */
 int mmrec_topk_merge(const float *vals, const int32_t *idx, int32_t n_lists, int32_t n_users,

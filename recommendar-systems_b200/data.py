@@ -271,6 +271,18 @@ class EvalDataLoader(AbstractDataLoader):
         global base, cols int32). The kernel subtracts rowptr[0]."""
         return self._mask_rowptr_dev[start: stop + 1], self._mask_cols_dev
 
+    def gt_csr(self):
+        """Ground-truth items per eval user as a device CSR (int32 row pointers, ascending int32
+        item ids) for the metrics kernel; built once."""
+        if getattr(self, "_gt_csr", None) is None:
+            lens = np.asarray(self.eval_len_list, dtype=np.int64)
+            rowptr = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
+            flat = np.concatenate([np.sort(p) for p in self.eval_items_per_u]) if len(lens) else \
+                np.zeros(0, np.int64)
+            self._gt_csr = (torch.from_numpy(rowptr).to(self.device),
+                            torch.from_numpy(flat.astype(np.int32)).to(self.device))
+        return self._gt_csr
+
     def get_eval_items(self):
         return self.eval_items_per_u
 

@@ -543,3 +543,28 @@ def topk_merge(vals, idx):
     lib.call("mmrec_topk_merge", lib.ptr(vals.contiguous()), lib.ptr(idx.contiguous()), L, n, k,
              lib.ptr(out_val), lib.ptr(out_idx), lib.stream())
     return out_idx, out_val
+
+
+# ------------------------------------------------------------------------------ top-K metrics
+_METRIC_ROWS = {"recall": 0, "recall2": 1, "precision": 2, "ndcg": 3, "map": 4}
+
+
+@torch.no_grad()
+def topk_metric_sums(topk, gt_rowptr, gt_items, return_hits=False):
+    """mmrec_topk_metrics_f64: per-rank sums over users of recall / cumulative hits / precision /
+    ndcg / map (float64 [5, k] on the device) for `topk` int64 [n, k] against the ascending
+    ground-truth CSR. Replaces TopKEvaluator's hit-matrix loop + numpy reductions."""
+    import numpy as np
+    lib.require_cuda(topk, gt_rowptr, gt_items)
+    topk = topk.contiguous()
+    n, k = topk.shape
+    dev = topk.device
+    disc_np = 1.0 / np.log2(np.arange(1, k + 1, dtype=np.float64) + 1)     # metrics.py:35-64
+    disc = torch.from_numpy(disc_np).to(dev)
+    idcg = torch.from_numpy(np.cumsum(disc_np)).to(dev)
+    sums = torch.empty(5, k, dtype=torch.float64, device=dev)
+    hits = torch.empty(n, k, dtype=torch.uint8, device=dev) if return_hits else None
+    ws = torch.empty(lib.load().mmrec_topk_metrics_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    lib.call("mmrec_topk_metrics_f64", lib.ptr(topk), n, k, lib.ptr(gt_rowptr), lib.ptr(gt_items),
+             lib.ptr(disc), lib.ptr(idcg), lib.ptr(hits), lib.ptr(sums), lib.ptr(ws), lib.stream())
+    return (sums, hits) if return_hits else sums

@@ -99,17 +99,30 @@ class TopKEvaluator:
         return (keys[pos] == q.ravel()).reshape(n, k)
 
     def evaluate(self, batch_matrix_list, eval_data, is_test=False, idx=0):
-        pos_items = eval_data.get_eval_items()
         pos_len_list = eval_data.get_eval_len_list()
-        topk_index = torch.cat(batch_matrix_list, dim=0).cpu().numpy()
-        assert len(pos_len_list) == len(topk_index)
-        hits = self.hit_matrix(pos_items, topk_index)
-        result = self._calculate_metrics(pos_len_list, hits)
+        topk = torch.cat(batch_matrix_list, dim=0)
+        assert len(pos_len_list) == len(topk)
+        if topk.is_cuda and hasattr(eval_data, "gt_csr"):
+            result = self._device_metrics(topk, eval_data)
+        else:
+            hits = self.hit_matrix(eval_data.get_eval_items(), topk.numpy())
+            result = self._calculate_metrics(pos_len_list, hits)
         out = {}
         for metric, value in zip(self.metrics, result):
             for k in self.topk:
                 out["{}@{}".format(metric, k)] = round(value[k - 1], 4)
         return out
+
+    def _device_metrics(self, topk, eval_data):
+        """Hit matrix + every metric @1..K on the GPU (mmrec_topk_metrics_f64); only the [5, K]
+        float64 sums come back to the host."""
+        rowptr, items = eval_data.gt_csr()
+        sums = ops.topk_metric_sums(topk, rowptr, items).cpu().numpy()
+        n = topk.shape[0]
+        total_pos = float(np.asarray(eval_data.get_eval_len_list(), dtype=np.int64).sum())
+        rows = {"recall": sums[0] / n, "recall2": sums[1] / total_pos, "precision": sums[2] / n,
+                "ndcg": sums[3] / n, "map": sums[4] / n}
+        return np.stack([rows[m] for m in self.metrics], axis=0)
 
     def _calculate_metrics(self, pos_len_list, hits):
         return np.stack([metrics_dict[m](hits, np.asarray(pos_len_list)) for m in self.metrics],

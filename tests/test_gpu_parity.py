@@ -382,6 +382,46 @@ def test_score_mask_topk_matches_stable_sort(n_users, n_items, d, k, splits):
     assert bool((got[:, 1:][eq] > got[:, :-1][eq]).all())
 
 
+@pytest.mark.parametrize("n,n_items,k", [(9130, 7050, 50), (3, 40, 5), (1000, 300, 64), (257, 5000, 20)])
+def test_device_metrics_match_numpy_evaluator(n, n_items, k):
+    """K15: hit matrix + Recall/Recall2/Precision/NDCG/MAP on the GPU vs the numpy evaluator
+    (topk_evaluator.py:88-101, metrics.py:12-109): hits bit-exact, per-rank means to 1e-12."""
+    ops, tr = pkg("ops"), pkg("trainer")
+    rng = np.random.default_rng(5)
+    topk = np.stack([rng.permutation(n_items)[:k] for _ in range(n)]).astype(np.int64)
+    lens = rng.integers(1, 30, size=n)
+    lens[0] = 1
+    lens[-1] = min(n_items, 200)              # more positives than K: IDCG truncation path
+    pos = [np.sort(rng.permutation(n_items)[:l]).astype(np.int64) for l in lens]
+    for u in range(0, n, 3):                  # plant hits
+        topk[u, rng.integers(0, k)] = pos[u][0]
+    hits_np = tr.TopKEvaluator.hit_matrix(pos, topk)
+    want = np.stack([tr.metrics_dict[m](hits_np, lens.astype(np.int64))
+                     for m in ("recall", "recall2", "precision", "ndcg", "map")])
+    rowptr = torch.tensor(np.concatenate(([0], np.cumsum(lens))), dtype=torch.int32, device=DEV)
+    items = torch.tensor(np.concatenate(pos), dtype=torch.int32, device=DEV)
+    sums, hits = ops.topk_metric_sums(torch.from_numpy(topk).to(DEV), rowptr, items, return_hits=True)
+    assert np.array_equal(hits.cpu().numpy().astype(bool), hits_np)
+    got = sums.cpu().numpy()
+    got[[0, 2, 3, 4]] /= n
+    got[1] /= lens.sum()
+    assert np.abs(got - want).max() < 1e-12
+
+
+def test_device_metrics_known_answer():
+    """hits [[1,0,1,0,0],[0,0,0,1,0],[0,0,0,0,0]], pos_len [2,1,7]."""
+    ops = pkg("ops")
+    topk = torch.tensor([[10, 0, 11, 1, 2], [3, 4, 5, 20, 6], [7, 8, 9, 12, 13]], device=DEV)
+    gt = [[10, 11], [20], [30, 31, 32, 33, 34, 35, 36]]
+    rowptr = torch.tensor([0, 2, 3, 10], dtype=torch.int32, device=DEV)
+    items = torch.tensor(sum(gt, []), dtype=torch.int32, device=DEV)
+    got = (ops.topk_metric_sums(topk, rowptr, items) / 3).cpu().numpy()
+    assert np.allclose(got[0], [1 / 6, 1 / 6, 1 / 3, 2 / 3, 2 / 3], atol=1e-15)
+    assert np.allclose(got[3], [0.33333333, 0.20438240, 0.30657360, 0.45013245, 0.45013245], atol=1e-8)
+    assert np.allclose(got[2], [1 / 3, 1 / 6, 2 / 9, 1 / 4, 1 / 5], atol=1e-15)
+    assert np.allclose(got[4], [0.33333333, 0.16666667, 0.27777778, 0.36111111, 0.36111111], atol=1e-8)
+
+
 def test_topk_merge_matches_single_pass():
     ops = pkg("ops")
     gen = torch.Generator().manual_seed(23)
