@@ -98,6 +98,29 @@ int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const flo
                        int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
                        const float *cos_ref, float *cos_w, float *Y_pre, void *stream);
 
+/* Several independent SpMMs of the same width d in ONE launch (at most 4): the item-item and R
+ * propagation of the three modality views (smore.py:291-317, mgcn.py:170-184), which are
+ * independent of one another and each too small to fill the GPU. Fields as the arguments of
+ * mmrec_spmm_csr_f32 (no cosine epilogue). Problems that share a graph need their own `counters`
+ * and `scratch`. `problems_host` is a HOST array. */
+typedef struct MmrecSpmmProblem {
+  const int32_t *row_ptr, *col_idx;
+  const float *vals;
+  const int32_t *tasks;
+  int32_t n_tasks;
+  const int32_t *slot_base;
+  int32_t *counters;
+  float *scratch;
+  int32_t col_offset;
+  const float *X;
+  float *Y;
+  const float *acc_in;
+  float *acc_out;
+  float acc_scale;
+} MmrecSpmmProblem;
+int mmrec_spmm_csr_multi_f32(const MmrecSpmmProblem *problems_host, int32_t n_problems, int32_t d,
+                             void *stream);
+
 /* Backward row-operator of one LayerGCN layer (layergcn.py:134-135 differentiated):
  * given dE = dL/d(w*p), p = Y_pre, w = cos_w, e0 = cos_ref:
  *   dP[r]   = w*dE + <dE,p> * d cos(p,e0)/dp ;  dE0[r] += <dE,p> * d cos(p,e0)/de0        */
@@ -242,11 +265,14 @@ int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side, const floa
  * DEVICE array of two doubles: hyper[0] = learning rate, hyper[1] = update count; the call
  * increments hyper[1] and uses it for the bias corrections, so a captured CUDA graph replays
  * with the right step and a host-updated learning rate. Same formulas as torch's Adam.
+ * grad_scale multiplies every gradient as it is read (fp32; pass 1.0): the mirror-gradient step
+ * uses -mg_beta (trainer.py:325-331) instead of a separate pass over all gradients.
  * ---------------------------------------------------------------------------------------- */
 int mmrec_adam_step_f32(float *const *params_host, const float *const *grads_host,
                         float *const *exp_avg_host, float *const *exp_avg_sq_host,
                         const int64_t *numel_host, int32_t n_tensors, double *hyper, double beta1,
-                        double beta2, double eps, double weight_decay, void *stream);
+                        double beta2, double eps, double weight_decay, double grad_scale,
+                        void *stream);
 /* y_t += sign * coef[0] * x_t for n_tensors tensors in one launch; coef is a device scalar
  * (the mirror-gradient perturbation theta -/+ alpha_eff*lr*g of trainer.py:307-329 without a
  * host round trip for alpha_eff). */

@@ -31,7 +31,7 @@ __global__ void adam_tick_kernel(double *hyper) { hyper[1] += 1.0; }
 
 __global__ void __launch_bounds__(kThreads)
 adam_kernel(const __grid_constant__ AdamPack pack, const double *__restrict__ hyper, double beta1d,
-            double beta2d, float eps, float weight_decay) {
+            double beta2d, float eps, float weight_decay, float grad_scale) {
   __shared__ float s_hyper[2];
   if (threadIdx.x == 0) {
     const double lr = hyper[0], step = hyper[1];
@@ -54,6 +54,7 @@ adam_kernel(const __grid_constant__ AdamPack pack, const double *__restrict__ hy
   const float w1 = (float)(1.0 - beta1d), w2 = (float)(1.0 - beta2d);
   (void)beta1;
   auto upd = [&](float &pp, float gg, float &mm, float &vv) {
+    gg *= grad_scale;                                          // 1.0f is exact
     if (weight_decay != 0.f) gg = fmaf(weight_decay, pp, gg);
     mm = mm + w1 * (gg - mm);
     vv = vv * beta2 + w2 * gg * gg;
@@ -123,7 +124,8 @@ using namespace mmrec;
 extern "C" int mmrec_adam_step_f32(float *const *params_host, const float *const *grads_host,
                                    float *const *exp_avg_host, float *const *exp_avg_sq_host,
                                    const int64_t *numel_host, int32_t n_tensors, double *hyper, double beta1,
-                                   double beta2, double eps, double weight_decay, void *stream) {
+                                   double beta2, double eps, double weight_decay, double grad_scale,
+                                   void *stream) {
   MMREC_REQUIRE(params_host && grads_host && exp_avg_host && exp_avg_sq_host && numel_host && hyper,
                 MMREC_E_BADARG, "adam: null pointer");
   MMREC_REQUIRE(n_tensors >= 0, MMREC_E_BADARG, "adam: bad sizes");
@@ -147,7 +149,7 @@ extern "C" int mmrec_adam_step_f32(float *const *params_host, const float *const
     pack.chunk_begin[pack.n_tensors] = chunks;
     if (chunks == 0) continue;
     adam_kernel<<<chunks, kThreads, 0, (cudaStream_t)stream>>>(pack, hyper, beta1, beta2, (float)eps,
-                                                              (float)weight_decay);
+                                                              (float)weight_decay, (float)grad_scale);
     MMREC_CHECK_LAUNCH("adam_kernel");
   }
   return MMREC_OK;

@@ -156,19 +156,25 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[CHUNKS], int row, int l
   }
 }
 
+struct Problem {
+  const int32_t *row_ptr, *col_idx;
+  const float *vals;
+  const int4 *tasks;
+  int n_tasks;
+  const int32_t *slot_base;
+  int32_t *counters;
+  float *scratch;
+  int col_offset;
+  const float *X;
+  Epilogue ep;
+};
+
+// One task (<= kSeg non-zeros of one row) by one sub-warp of LANES threads.
 template <int LANES, int CHUNKS>
-__global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 4 : 3)
-spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
-                const float *__restrict__ vals, const int4 *__restrict__ tasks, int n_tasks,
-                const int32_t *__restrict__ slot_base, int32_t *__restrict__ counters,
-                float *__restrict__ scratch, int col_offset, const float *__restrict__ X, int d,
-                Epilogue ep) {
-  constexpr int GROUPS = kThreads / LANES;
-  const int lane = threadIdx.x % LANES;
-  const int t = blockIdx.x * GROUPS + threadIdx.x / LANES;
-  if (t >= n_tasks) return;
-  const int4 task = __ldg(tasks + t);          // {row, begin, end, slot}
+__device__ __forceinline__ void run_task(const Problem &P, int t, int lane, int d) {
+  const int4 task = __ldg(P.tasks + t);          // {row, begin, end, slot}
   const int row = task.x;
+  const Epilogue &ep = P.ep;
   float4 acc[CHUNKS];
 #pragma unroll
   for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -178,14 +184,14 @@ spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__
     if (ep.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.acc_in + o));
     if (ep.cos_ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.cos_ref + o));
   }
-  gather_rows<LANES, CHUNKS>(acc, col_idx, vals, task.y, task.z, lane, X, d, col_offset);
+  gather_rows<LANES, CHUNKS>(acc, P.col_idx, P.vals, task.y, task.z, lane, P.X, d, P.col_offset);
   if (task.w >= 0) {
     // heavy row: publish this part, the last arriver reduces all parts in order
     const unsigned mask = group_mask<LANES>();
-    const int r0 = row_ptr[row];
-    const int n_parts = (row_ptr[row + 1] - r0 + kSeg - 1) / kSeg;
+    const int r0 = P.row_ptr[row];
+    const int n_parts = (P.row_ptr[row + 1] - r0 + kSeg - 1) / kSeg;
     const int part = (task.y - r0) / kSeg;
-    float *base = scratch + (size_t)slot_base[task.w] * d;
+    float *base = P.scratch + (size_t)P.slot_base[task.w] * d;
 #pragma unroll
     for (int q = 0; q < CHUNKS; ++q)
       __stcg(reinterpret_cast<float4 *>(base + (size_t)part * d + (q * LANES + lane) * 4), acc[q]);
@@ -193,8 +199,8 @@ spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__
     __syncwarp(mask);
     int last = 0;
     if (lane == 0) {
-      last = atomicAdd(counters + task.w, 1) == n_parts - 1;
-      if (last) counters[task.w] = 0;
+      last = atomicAdd(P.counters + task.w, 1) == n_parts - 1;
+      if (last) P.counters[task.w] = 0;
     }
     last = __shfl_sync(mask, last, 0, LANES);
     if (!last) return;
@@ -219,6 +225,39 @@ spmm_csr_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__
     }
   }
   finish_row<LANES, CHUNKS>(acc, row, lane, d, ep);
+}
+
+template <int LANES, int CHUNKS>
+__global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 4 : 3)
+spmm_csr_kernel(const Problem P, int d) {
+  constexpr int GROUPS = kThreads / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int t = blockIdx.x * GROUPS + threadIdx.x / LANES;
+  if (t >= P.n_tasks) return;
+  run_task<LANES, CHUNKS>(P, t, lane, d);
+}
+
+// Several independent SpMMs in one launch (the three modality views of SMORE/MGCN: small graphs
+// that each fill a fraction of the GPU). block_end[p] = first block after problem p.
+constexpr int kMaxProblems = 4;
+struct MultiArgs {
+  Problem p[kMaxProblems];
+  int block_end[kMaxProblems];
+  int n;
+};
+
+template <int LANES, int CHUNKS>
+__global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 4 : 3)
+spmm_csr_multi_kernel(const MultiArgs A, int d) {
+  constexpr int GROUPS = kThreads / LANES;
+  int pi = 0;
+  while (pi + 1 < A.n && (int)blockIdx.x >= A.block_end[pi]) ++pi;
+  const int b0 = pi == 0 ? 0 : A.block_end[pi - 1];
+  const Problem &P = A.p[pi];
+  const int lane = threadIdx.x % LANES;
+  const int t = (blockIdx.x - b0) * GROUPS + threadIdx.x / LANES;
+  if (t >= P.n_tasks) return;
+  run_task<LANES, CHUNKS>(P, t, lane, d);
 }
 
 // ---- LayerGCN cosine refinement, backward row operator --------------------------------------
@@ -303,15 +342,49 @@ extern "C" int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx
                 MMREC_E_ALIGN, "spmm: dense operands and the task list must be 16-byte aligned");
   MMREC_REQUIRE(X != Y && X != acc_out, MMREC_E_BADARG, "spmm: X must not alias an output");
   if (n_tasks == 0) return MMREC_OK;
-  Epilogue ep{Y, acc_in, acc_out, acc_scale, cos_ref, cos_w, Y_pre};
+  Problem P{row_ptr, col_idx, vals, reinterpret_cast<const int4 *>(tasks), n_tasks, slot_base, counters, scratch,
+            col_offset, X, Epilogue{Y, acc_in, acc_out, acc_scale, cos_ref, cos_w, Y_pre}};
   return dispatch_width(d, [&](auto lanes, auto chunks) {
     constexpr int L = decltype(lanes)::value, C = decltype(chunks)::value;
     constexpr int GROUPS = kThreads / L;
     const int blocks = (n_tasks + GROUPS - 1) / GROUPS;
-    spmm_csr_kernel<L, C><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
-        row_ptr, col_idx, vals, reinterpret_cast<const int4 *>(tasks), n_tasks, slot_base, counters, scratch,
-        col_offset, X, d, ep);
+    spmm_csr_kernel<L, C><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
     MMREC_CHECK_LAUNCH("spmm_csr_kernel");
+    return MMREC_OK;
+  });
+}
+
+extern "C" int mmrec_spmm_csr_multi_f32(const MmrecSpmmProblem *problems_host, int32_t n_problems, int32_t d,
+                                        void *stream) {
+  MMREC_REQUIRE(problems_host && n_problems >= 1 && n_problems <= kMaxProblems, MMREC_E_BADARG,
+                "spmm_multi: 1..%d problems", kMaxProblems);
+  MultiArgs A{};
+  A.n = 0;
+  for (int i = 0; i < n_problems; ++i) {
+    const MmrecSpmmProblem &q = problems_host[i];
+    MMREC_REQUIRE(q.row_ptr && q.col_idx && q.vals && q.tasks && q.X, MMREC_E_BADARG, "spmm_multi: null input (%d)", i);
+    MMREC_REQUIRE(q.Y || q.acc_out, MMREC_E_BADARG, "spmm_multi: no output requested (%d)", i);
+    MMREC_REQUIRE(aligned16(q.X) && aligned16(q.Y) && aligned16(q.acc_in) && aligned16(q.acc_out) &&
+                      aligned16(q.tasks) && aligned16(q.scratch), MMREC_E_ALIGN,
+                  "spmm_multi: dense operands and the task list must be 16-byte aligned (%d)", i);
+    MMREC_REQUIRE(q.X != q.Y && q.X != q.acc_out, MMREC_E_BADARG, "spmm_multi: X must not alias an output (%d)", i);
+    if (q.n_tasks <= 0) continue;
+    A.p[A.n] = Problem{q.row_ptr, q.col_idx, q.vals, reinterpret_cast<const int4 *>(q.tasks), q.n_tasks, q.slot_base,
+                       q.counters, q.scratch, q.col_offset, q.X,
+                       Epilogue{q.Y, q.acc_in, q.acc_out, q.acc_scale, nullptr, nullptr, nullptr}};
+    ++A.n;
+  }
+  if (A.n == 0) return MMREC_OK;
+  return dispatch_width(d, [&](auto lanes, auto chunks) {
+    constexpr int L = decltype(lanes)::value, C = decltype(chunks)::value;
+    constexpr int GROUPS = kThreads / L;
+    int blocks = 0;
+    for (int i = 0; i < A.n; ++i) {
+      blocks += (A.p[i].n_tasks + GROUPS - 1) / GROUPS;
+      A.block_end[i] = blocks;
+    }
+    spmm_csr_multi_kernel<L, C><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(A, d);
+    MMREC_CHECK_LAUNCH("spmm_csr_multi_kernel");
     return MMREC_OK;
   });
 }

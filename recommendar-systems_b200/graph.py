@@ -61,12 +61,22 @@ class CSRGraph:
         self.nnz = int((row_ptr[-1] - row_ptr[0]).item())
         self.t = self if symmetric else None
 
-    def scratch(self, d):
-        """Partial-sum buffer of the heavy rows for embedding width d (allocated once)."""
-        if d not in self._scratch:
-            self._scratch[d] = torch.empty(max(1, self.total_parts) * d, dtype=torch.float32,
-                                           device=self.vals.device)
-        return self._scratch[d]
+    def scratch(self, d, slot=0):
+        """Partial-sum buffer of the heavy rows for embedding width d (allocated once). `slot`
+        separates concurrent uses of the same graph inside one multi-problem launch."""
+        if (d, slot) not in self._scratch:
+            self._scratch[(d, slot)] = torch.empty(max(1, self.total_parts) * d, dtype=torch.float32,
+                                                   device=self.vals.device)
+        return self._scratch[(d, slot)]
+
+    def counters_for(self, slot=0):
+        """Self-resetting arrival counters of the heavy rows; one set per concurrent use."""
+        if slot == 0:
+            return self.counters
+        extra = self.__dict__.setdefault("_extra_counters", {})
+        if slot not in extra:
+            extra[slot] = torch.zeros_like(self.counters)
+        return extra[slot]
 
     @property
     def device(self):

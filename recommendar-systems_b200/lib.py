@@ -29,6 +29,7 @@ SIGNATURES = {
                                      _p]),
     "mmrec_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p,
                                      _f32, _p, _p, _p, _p]),
+    "mmrec_spmm_csr_multi_f32": (C.c_int, [_p, _i32, _i32, _p]),
     "mmrec_layergcn_cos_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
     "mmrec_bpr_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "mmrec_bpr_bwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
@@ -53,7 +54,7 @@ SIGNATURES = {
     "mmrec_smore_side_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                            _p, _i32, _i32, _p]),
     "mmrec_adam_step_f32": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double,
-                                      C.c_double, _p]),
+                                      C.c_double, C.c_double, _p]),
     "mmrec_axpy_multi_f32": (C.c_int, [_p, _p, _p, _i32, _p, _f32, _p]),
     "mmrec_score_mask_topk_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _i32, _p, _p, _i32, _i32,
                                             _p, _p, _p, _p, _p]),
@@ -64,6 +65,15 @@ SIGNATURES = {
     "mmrec_topk_merge": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "mmrec_neg_sample_mt19937_host": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _p, _i64, _p]),
 }
+
+
+
+class SpmmProblem(C.Structure):
+    """MmrecSpmmProblem of include/mmrec_b200.h."""
+    _fields_ = [("row_ptr", _p), ("col_idx", _p), ("vals", _p), ("tasks", _p), ("n_tasks", _i32),
+                ("slot_base", _p), ("counters", _p), ("scratch", _p), ("col_offset", _i32), ("X", _p),
+                ("Y", _p), ("acc_in", _p), ("acc_out", _p), ("acc_scale", _f32)]
+
 
 _lib = None
 

@@ -389,6 +389,15 @@ class _MultiViewBase(GeneralRecommender):
             x = ops.spmm(item_graph, x)
         return torch.cat([ops.spmm(self.R, x), x], dim=0)
 
+    def _views(self, xs, item_graphs):
+        """`_view` for all modalities at once: the item-item hops of the views are independent of
+        one another (and so are their user-side R products), so each hop is ONE launch."""
+        xs = list(xs)
+        for _ in range(self.n_layers):
+            xs = ops.spmm_multi(item_graphs, xs)
+        us = ops.spmm_multi([self.R] * len(xs), xs)
+        return [torch.cat([u, x], dim=0) for u, x in zip(us, xs)]
+
     def _eval_forward(self):
         return self.forward(self.norm_adj)
 
@@ -439,8 +448,8 @@ class MGCN(_MultiViewBase):
         text_item = item * self.gate_t(text_feats)
         ego = torch.cat([self.user_embedding.weight, item], dim=0)
         content = ops.propagate_mean(adj, ego, self.n_ui_layers)
-        image_embeds = self._view(image_item, self.image_original_adj)
-        text_embeds = self._view(text_item, self.text_original_adj)
+        image_embeds, text_embeds = self._views((image_item, text_item),
+                                                (self.image_original_adj, self.text_original_adj))
         att = torch.cat([self.query_common(image_embeds), self.query_common(text_embeds)], dim=-1)
         w = self.softmax(att)
         common = w[:, 0].unsqueeze(1) * image_embeds + w[:, 1].unsqueeze(1) * text_embeds
@@ -543,9 +552,9 @@ class SMORE(_MultiViewBase):
             fusion_item = item + self.inject_scale * self.gate_f(fusion_conv)
         ego = torch.cat([self.user_embedding.weight, item], dim=0)
         content = ops.propagate_mean(adj, ego, self.n_ui_layers)
-        image_embeds = self._view(image_item, self.image_original_adj)
-        text_embeds = self._view(text_item, self.text_original_adj)
-        fusion_embeds = self._view(fusion_item, self.fusion_adj)
+        image_embeds, text_embeds, fusion_embeds = self._views(
+            (image_item, text_item, fusion_item),
+            (self.image_original_adj, self.text_original_adj, self.fusion_adj))
         # modality-aware preference module (smore.py:321-341): one fused kernel for d = 32 / 64
         if ops.smore_side_supported(self.embedding_dim):
             masks = None

@@ -61,6 +61,71 @@ class _SpMM(torch.autograd.Function):
         return dX, None
 
 
+def spmm_multi_raw(graphs, Xs, Ys=None, acc_ins=None, acc_outs=None):
+    """mmrec_spmm_csr_multi_f32: up to 4 independent SpMMs of the same width in one launch."""
+    n = len(graphs)
+    d = Xs[0].shape[1]
+    arr = (lib.SpmmProblem * n)()
+    keep = []
+    seen = {}
+    for i, (g, X) in enumerate(zip(graphs, Xs)):
+        lib.require_cuda(X)
+        if X.shape[1] != d or X.shape[0] < g.n_cols:
+            raise RuntimeError("spmm_multi: operand shapes do not match the graphs")
+        slot = seen.get(id(g), 0)                 # same graph twice in one launch: own scratch
+        seen[id(g)] = slot + 1
+        scratch, counters = g.scratch(d, slot), g.counters_for(slot)
+        keep += [scratch, counters]
+        p = arr[i]
+        p.row_ptr, p.col_idx, p.vals = lib.ptr(g.row_ptr), lib.ptr(g.col_idx), lib.ptr(g.vals)
+        p.tasks, p.n_tasks, p.slot_base = lib.ptr(g.tasks), g.n_tasks, lib.ptr(g.slot_base)
+        p.counters, p.scratch, p.col_offset = lib.ptr(counters), lib.ptr(scratch), g.col_offset
+        p.X = lib.ptr(X)
+        p.Y = lib.ptr(Ys[i]) if Ys is not None else None
+        p.acc_in = lib.ptr(acc_ins[i]) if acc_ins is not None else None
+        p.acc_out = lib.ptr(acc_outs[i]) if acc_outs is not None else None
+        p.acc_scale = 1.0
+    import ctypes
+    lib.call("mmrec_spmm_csr_multi_f32", ctypes.byref(arr), n, d, lib.stream())
+
+
+class _SpMMMulti(torch.autograd.Function):
+    """Y_i = A_i X_i for several (graph, X) pairs in one launch; backward dX_i = A_i^T dY_i in one."""
+
+    @staticmethod
+    def forward(ctx, graphs, *Xs):
+        Xs = [_f32c(x) for x in Xs]
+        Ys = [torch.empty(g.n_rows, x.shape[1], dtype=torch.float32, device=x.device)
+              for g, x in zip(graphs, Xs)]
+        spmm_multi_raw(graphs, Xs, Ys=Ys)
+        ctx.graphs = graphs
+        return tuple(Ys)
+
+    @staticmethod
+    def backward(ctx, *dYs):
+        gts = []
+        for g in ctx.graphs:
+            if g.t is None:
+                raise RuntimeError("spmm backward needs the transposed CSR (build with_transpose=True)")
+            gts.append(g.t)
+        ref = next(d for d in dYs if d is not None)
+        dYs = [_f32c(dy) if dy is not None else
+               torch.zeros(g.n_rows, ref.shape[1], dtype=torch.float32, device=ref.device)
+               for dy, g in zip(dYs, ctx.graphs)]
+        dXs = [torch.empty(gt.n_rows, dy.shape[1], dtype=torch.float32, device=dy.device)
+               for gt, dy in zip(gts, dYs)]
+        spmm_multi_raw(gts, dYs, Ys=dXs)
+        return (None, *dXs)
+
+
+def spmm_multi(graphs, Xs):
+    """[torch.sparse.mm(A_i, X_i)] for independent pairs (at most 4) in one launch each way."""
+    graphs = list(graphs)
+    if len(graphs) == 1:
+        return [spmm(graphs[0], Xs[0])]
+    return list(_SpMMMulti.apply(graphs, *Xs))
+
+
 def spmm(g: CSRGraph, X):
     """Y = A X; replaces torch.sparse.mm(A, X) (layergcn.py:133, freedom.py:169,174,
     mgcn.py:162-184, smore.py:282-317, lightgcn.py:122). Backward: dX = A^T dY."""

@@ -51,7 +51,8 @@ class FusedAdam(torch.optim.Optimizer):
         return self._hyper(g, dev)[0:1]
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, grad_scale=1.0):
+        """`grad_scale` multiplies every gradient inside the kernel (fp32, as `_foreach_mul_` would)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -80,5 +81,5 @@ class FusedAdam(torch.optim.Optimizer):
             lib.call("mmrec_adam_step_f32", _ptr_array(ps), _ptr_array(gs), _ptr_array(ms), _ptr_array(vs),
                      (C.c_int64 * n)(*[t.numel() for t in ps]), n, lib.ptr(hyper),
                      float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
-                     float(group["weight_decay"]), lib.stream())
+                     float(group["weight_decay"]), float(grad_scale), lib.stream())
         return loss

@@ -236,11 +236,16 @@ class Trainer:
         opt.zero_grad(set_to_none=True)
         loss_mirror = loss_func(mirror_input)
         (sum(loss_mirror) if isinstance(loss_mirror, tuple) else loss_mirror).backward()
+        beta = -float(getattr(model, "mg_beta", 0.2))
         with torch.no_grad():
-            mg = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
-            torch._foreach_mul_(mg, -float(getattr(model, "mg_beta", 0.2)))
             axpy_multi(params, grads, coef, sign=1.0)         # back to theta
-        opt.step()
+            if not hasattr(opt, "lr_tensor"):                 # plain torch optimizer
+                mg = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
+                torch._foreach_mul_(mg, beta)
+        if hasattr(opt, "lr_tensor"):
+            opt.step(grad_scale=beta)                         # FusedAdam scales the gradients as it reads them
+        else:
+            opt.step()
         opt.zero_grad(set_to_none=True)
 
     def _train_batch(self, interaction, batch_idx=0, loss_func=None):

@@ -46,6 +46,28 @@ def test_spmm_and_transpose_backward(d):
     assert rel(Xg.grad, Xo.grad) < 1e-5
 
 
+def test_spmm_multi_matches_separate_launches():
+    """Several independent SpMMs in one launch (modality views), same graph twice included."""
+    ops, G = pkg("ops"), pkg("graph")
+    gs = []
+    for seed, (nr, nc, nnz, heavy) in enumerate([(700, 500, 9000, 3), (500, 500, 4000, None), (300, 500, 20000, 7)]):
+        r, c, v = random_graph(nr, nc, nnz, 50 + seed, heavy_row=heavy)
+        gs.append(G.csr_from_coo(r.to(DEV), c.to(DEV), v.to(DEV), nr, nc))
+    graphs = [gs[0], gs[1], gs[2], gs[0]]
+    gen = torch.Generator().manual_seed(77)
+    Xs = [torch.randn(500, 64, generator=gen).to(DEV).requires_grad_(True) for _ in graphs]
+    gys = [torch.randn(g.n_rows, 64, generator=gen).to(DEV) for g in graphs]
+    Ys = ops.spmm_multi(graphs, Xs)
+    sum((y * gy).sum() for y, gy in zip(Ys, gys)).backward()
+    Xr = [x.detach().clone().requires_grad_(True) for x in Xs]
+    Yr = [ops.spmm(g, x) for g, x in zip(graphs, Xr)]
+    sum((y * gy).sum() for y, gy in zip(Yr, gys)).backward()
+    for a, b in zip(Ys, Yr):
+        assert torch.equal(a, b)
+    for a, b in zip(Xs, Xr):
+        assert torch.equal(a.grad, b.grad)
+
+
 def test_spmm_empty_rows_and_duplicates():
     G, ops = pkg("graph"), pkg("ops")
     rows = torch.tensor([0, 0, 0, 5, 5, 9]); cols = torch.tensor([1, 1, 2, 0, 0, 3]); vals = torch.ones(6)
