@@ -121,27 +121,54 @@ score_topk_kernel(const float *__restrict__ user_emb, const int64_t *__restrict_
 
 constexpr int kMaxLists = 64;
 
-__global__ void __launch_bounds__(128)
+// K-way merge by ranking: one warp per user. The n_lists * k candidates of the user are staged in
+// shared memory; every candidate computes its final rank directly -- its position in its own
+// (sorted) list plus, for every other list, the number of entries that beat it (binary search:
+// the lists are sorted by (score desc, id asc), padding (-inf, INT_MAX) last; list index breaks
+// exact ties so the order is total) -- and the k best write themselves to their slot. No serial
+// k-step selection loop, no per-thread local arrays, coalesced traffic.
+constexpr int kMergeWarps = 4;
+
+__global__ void __launch_bounds__(kMergeWarps * 32)
 topk_merge_kernel(const float *__restrict__ vals, const int32_t *__restrict__ idx, int n_lists,
                   int n_users, int k, float *__restrict__ out_val, int64_t *__restrict__ out_idx) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float merge_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kMergeWarps + warp;
   if (b >= n_users) return;
-  uint8_t head[kMaxLists];
-  for (int l = 0; l < n_lists; ++l) head[l] = 0;
-  for (int t = 0; t < k; ++t) {
-    float bv = -CUDART_INF_F;
-    int bi = INT_MAX, bl = -1;
-    for (int l = 0; l < n_lists; ++l) {
-      const int h = head[l];
-      if (h >= k) continue;
-      const size_t o = ((size_t)l * n_users + b) * k + h;
-      const float v = vals[o];
-      const int i = idx[o];
-      if (bl < 0 || v > bv || (v == bv && i < bi)) { bv = v; bi = i; bl = l; }
+  const int n = n_lists * k;
+  float *sv = merge_smem + (size_t)warp * 2 * n;
+  int32_t *si = reinterpret_cast<int32_t *>(sv + n);
+  for (int c = lane; c < n; c += 32) {
+    const int l = c / k, j = c % k;
+    const size_t o = ((size_t)l * n_users + b) * k + j;
+    sv[c] = vals[o];
+    si[c] = idx[o];
+  }
+  __syncwarp();
+  for (int c = lane; c < n; c += 32) {
+    const int l = c / k, j = c % k;
+    const float v = sv[c];
+    const int id = si[c];
+    int rank = j;
+    for (int l2 = 0; l2 < n_lists && rank < k; ++l2) {
+      if (l2 == l) continue;
+      const float *lv = sv + l2 * k;
+      const int32_t *li = si + l2 * k;
+      int lo = 0, hi = k;                       // first position whose entry does NOT beat (v, id)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float ev = lv[mid];
+        const int ei = li[mid];
+        const bool beats = ev > v || (ev == v && (ei < id || (ei == id && l2 < l)));
+        if (beats) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
     }
-    if (bl >= 0) ++head[bl];
-    if (out_val) out_val[(size_t)b * k + t] = bv;
-    out_idx[(size_t)b * k + t] = (int64_t)bi;
+    if (rank < k) {
+      if (out_val) out_val[(size_t)b * k + rank] = v;
+      out_idx[(size_t)b * k + rank] = (int64_t)id;
+    }
   }
 }
 
@@ -175,8 +202,15 @@ extern "C" int mmrec_topk_merge(const float *vals, const int32_t *idx, int32_t n
   MMREC_REQUIRE(vals && idx && out_idx, MMREC_E_BADARG, "topk_merge: null pointer");
   MMREC_REQUIRE(n_lists >= 1 && n_lists <= kMaxLists && n_users > 0 && k > 0 && k <= 255, MMREC_E_BADARG,
                 "topk_merge: need 1 <= n_lists <= %d, n_users > 0, 0 < k <= 255", kMaxLists);
-  topk_merge_kernel<<<(n_users + 127) / 128, 128, 0, (cudaStream_t)stream>>>(vals, idx, n_lists, n_users, k,
-                                                                            out_val, out_idx);
+  const size_t smem = (size_t)kMergeWarps * 2 * n_lists * k * sizeof(float);
+  MMREC_REQUIRE(smem <= 200 * 1024, MMREC_E_BADARG, "topk_merge: n_lists * k = %d is too large", n_lists * k);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    MMREC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  topk_merge_kernel<<<(n_users + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, smem, (cudaStream_t)stream>>>(
+      vals, idx, n_lists, n_users, k, out_val, out_idx);
   MMREC_CHECK_LAUNCH("topk_merge_kernel");
   return MMREC_OK;
 }

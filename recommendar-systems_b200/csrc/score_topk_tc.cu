@@ -69,12 +69,17 @@ __device__ __forceinline__ void heap_sift_down(float *hv, int32_t *hi_, int pos,
       v[j] = in ? hv[(c0 + j) * kTileM] : CUDART_INF_F;      // +inf never wins "worst"
       id[j] = in ? hi_[(c0 + j) * kTileM] : 0;
     }
-    int w = 0;
-    float wv = v[0];
-    int wi = id[0];
+    // worst child = lowest score, ties -> highest id. Shallow trees instead of a 7-step scan: the
+    // epilogue is one warp per scheduler, so the DEPTH of the dependent chain is what costs.
+    const float wv = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+    int t[kAry];
 #pragma unroll
-    for (int j = 1; j < kAry; ++j)
-      if (Better::worse(v[j], id[j], wv, wi)) { w = j; wv = v[j]; wi = id[j]; }
+    for (int j = 0; j < kAry; ++j) t[j] = v[j] == wv ? id[j] : -1;
+    const int wi = max(max(max(t[0], t[1]), max(t[2], t[3])), max(max(t[4], t[5]), max(t[6], t[7])));
+    int w = 0;
+#pragma unroll
+    for (int j = 1; j < kAry; ++j) w = t[j] == wi ? j : w;
+    w = t[0] == wi ? 0 : w;
     if (!Better::worse(wv, wi, sc, gid)) break;
     hv[pos * kTileM] = wv;
     hi_[pos * kTileM] = wi;
