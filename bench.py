@@ -403,19 +403,26 @@ def run_scaled(args):
     bound = (6.0 / (U + I + d)) ** 0.5
     X0 = (torch.rand(U + I, d, generator=gen, device=dev) * 2 - 1) * bound
     users = torch.randint(0, U, (Bu,), generator=gen, device=dev)
-    if world > 1:
+    nnz_full = full.nnz
+    if world > 1 and args.partition == "rows":
         sg = par.ShardedUIGraph(full, rank, world)
-        nnz_local = sg.local.nnz
         lo, hi = par.item_range(I, rank, world)
         del full
+    elif world > 1:
+        sb = par.ShardedBipartite(full, rank, world)
+        Xu, Xi = X0[sb.lo: sb.hi].contiguous(), X0[U:].contiguous()
+        del X0
     torch.cuda.empty_cache()
 
     def step():
         if world == 1:
             out = ops.propagate_mean(full, X0, L)
             return ops.score_mask_topk(out[:U], users, out[U:], k)
-        out = par.sharded_propagate_mean(sg, X0, L)
-        return par.sharded_score_topk(out[:U], users, out[U + lo: U + hi].contiguous(), lo, k)
+        if args.partition == "rows":
+            out = par.sharded_propagate_mean(sg, X0, L)
+            return par.sharded_score_topk(out[:U], users, out[U + lo: U + hi].contiguous(), lo, k)
+        ou, oi = par.bipartite_propagate_mean(sb, Xu, Xi, L)
+        return par.bipartite_score_topk(sb, ou, oi, users, k)
 
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -448,7 +455,7 @@ def run_scaled(args):
         assert lo_.item() == hi_.item(), "ranks disagree on the merged top-K"
     if rank == 0:
         peak, peak_src = measured_peaks()
-        nnz = full.nnz if world == 1 else None
+        nnz = nnz_full if world == 1 else None
         n = U + I
         line = {"metric": "propagate (4 layers) + full-rank top-50, eval users/s (scaled power-law graph)",
                 "value": Bu * args.steps / (ms / 1e3), "unit": "users/s", "n_gpus": world, "steps": args.steps,
@@ -456,7 +463,10 @@ def run_scaled(args):
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"LightGCN-style propagation + item-sharded top-50, {U} users x {I} items x "
                                        f"~{E} interactions, d=64, {Bu} eval users per step",
-                           "partition": "rows by nnz + all-gather per layer; items by range + top-K merge",
+                           "partition": ("rows by nnz + all-gather of the whole table per layer" if args.partition == "rows"
+                                         else "users by nnz, items replicated: one all-reduce of the [I, d] item table per "
+                                              "layer, overlapped with the user-side SpMM") + "; evaluation: items by range + "
+                                                                                             "top-K merge",
                            "l2": "embedding table larger than L2" if n * d * 4 > 126e6 else "fits L2"},
                 "clocks": clocks, "gpu_launches": int(launches), "checksum_ids": int(ids.sum().item())}
         if nnz is not None:
@@ -477,6 +487,7 @@ def main():
     ap.add_argument("--workload", default="smore_baby", choices=["smore_baby", "scaled"])
     ap.add_argument("--scale", type=float, default=0.05)
     ap.add_argument("--eval-users", type=int, default=16384)
+    ap.add_argument("--partition", default="bipartite", choices=["bipartite", "rows"])
     args = ap.parse_args()
     if args.workload == "scaled" and args.impl == "ours":
         run_scaled(args)

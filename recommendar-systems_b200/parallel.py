@@ -8,6 +8,15 @@ torch.distributed (NCCL over NVLink/NVSwitch on the B200 box, gloo in the CPU te
   slice of the next layer in place and `all_gather_into_tensor` needs no packing or compaction;
   the local CSR's column indices are rewritten to padded ids once.
   Backward (training with replicated loss): the same loop on the gradient (A_hat symmetric).
+* Bipartite propagation (`ShardedBipartite`, the path bench.py scales): the all-gather above moves
+  the WHOLE table every layer (4 N d bytes per rank whatever P is: 3 GB at 10M x 2M, d = 64), so
+  it stops scaling at P = 2. A user-item graph only ever needs ITEM vectors to move: rank p owns a
+  range of users; per layer it computes its users' rows from the (replicated) item table and, with
+  the transpose of the same edge block, the contribution of its users to EVERY item; one
+  all-reduce of the [I, d] item table (0.5 GB; NVLS reduces in the switch) finishes the layer and
+  overlaps with the user-side SpMM. User vectors never leave their owner, the item table ends up
+  replicated -- exactly what the item-sharded evaluation wants -- and the batch's user rows are
+  fetched with a [Bu, d] all-reduce.
 * Evaluation: items are cut into P equal ranges; every rank runs the fused score + mask + top-K
   kernel on its item slice (global ids via `item_offset`), the [n, K] (score, id) lists are
   all-gathered and merged with `mmrec_topk_merge` (same tie rule: lower id first).
@@ -176,3 +185,76 @@ def sharded_score_topk(user_emb, users, item_emb_local, item_lo, k, mask_rowptr=
     if merge is None:
         return ops.topk_merge(all_v, all_i)[0]
     return merge(all_v, all_i)
+
+
+# ------------------------------------------------------------------ user-partitioned bipartite
+def _spmm_cuda(g, X, Y=None, acc_in=None, acc_out=None, scale=1.0):
+    ops.spmm_raw(g, X, Y=Y, acc_in=acc_in, acc_out=acc_out, acc_scale=scale)
+
+
+class ShardedBipartite:
+    """Rank p's share of a symmetric user-item graph: users [lo, hi) (balanced by non-zeros) with
+    R_p = A[lo:hi, U:] (zero-copy view of the full CSR) and R_p^T (items x local users)."""
+
+    def __init__(self, full: G.CSRGraph, rank: int, world: int, bounds=None, csr_from_coo=None):
+        U, I = int(full.n_users), int(full.n_items)
+        rp = full.row_ptr[:U + 1].cpu().numpy().astype(np.int64)
+        self.bounds = partition_by_nnz(rp, world) if bounds is None else np.asarray(bounds, dtype=np.int64)
+        self.rank, self.world, self.U, self.I = rank, world, U, I
+        lo, hi = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.lo, self.hi = lo, hi
+        self.R = G.CSRGraph(full.row_ptr[lo: hi + 1], full.col_idx, full.vals, hi - lo, I, col_offset=U)
+        a, b = int(rp[lo]), int(rp[hi])
+        dev = full.vals.device
+        counts = (full.row_ptr[lo + 1: hi + 1] - full.row_ptr[lo: hi]).to(torch.int64)
+        rows_local = torch.repeat_interleave(torch.arange(hi - lo, device=dev), counts)
+        items = full.col_idx[a:b].to(torch.int64) - U
+        build = csr_from_coo or G.csr_from_coo
+        self.Rt = build(items, rows_local, full.vals[a:b], I, hi - lo, with_transpose=False)
+        self.nnz_local = b - a
+
+
+@torch.no_grad()
+def bipartite_propagate_mean(sb: ShardedBipartite, Xu_local, Xi, n_layers, group=None, spmm_fn=_spmm_cuda):
+    """mean_{l=0..L} A^l X0 for a bipartite graph, users sharded / items replicated.
+    Xu_local [hi - lo, d]: this rank's user rows of X0; Xi [I, d]: the item rows (same on every
+    rank). Returns (users' rows of this rank, all item rows)."""
+    L = n_layers
+    if L == 0:
+        return Xu_local.clone(), Xi.clone()
+    scale = 1.0 / (L + 1)
+    acc_u, acc_i = Xu_local, Xi.clone()
+    xu, xi = Xu_local.contiguous(), Xi.contiguous()
+    d = xi.shape[1]
+    for l in range(1, L + 1):
+        last = l == L
+        yi = torch.empty(sb.I, d, dtype=xi.dtype, device=xi.device)
+        spmm_fn(sb.Rt, xu, Y=yi)                              # what this rank's users add to every item
+        work = dist.all_reduce(yi, group=group, async_op=True)
+        yu = None if last else torch.empty_like(xu)
+        acc_new = torch.empty_like(xu)
+        spmm_fn(sb.R, xi, Y=yu, acc_in=acc_u, acc_out=acc_new, scale=scale if last else 1.0)   # overlaps the all-reduce
+        acc_u = acc_new
+        work.wait()
+        acc_i.add_(yi)
+        if last:
+            acc_i.mul_(scale)
+        xu, xi = yu, yi
+    return acc_u, acc_i
+
+
+@torch.no_grad()
+def bipartite_score_topk(sb: ShardedBipartite, out_u_local, out_i, users, k, group=None, local_topk=None,
+                         merge=None):
+    """Full-rank top-K for global user ids `users` on the outputs of bipartite_propagate_mean:
+    the batch's user rows come from their owners (one [Bu, d] all-reduce), items are scored in P
+    ranges and the lists merged. Every rank returns the same ids."""
+    users = users.to(torch.int64)
+    ub = torch.zeros(users.numel(), out_u_local.shape[1], dtype=out_u_local.dtype, device=out_u_local.device)
+    mine = (users >= sb.lo) & (users < sb.hi)
+    ub[mine] = out_u_local[users[mine] - sb.lo]
+    dist.all_reduce(ub, group=group)
+    lo, hi = item_range(sb.I, sb.rank, sb.world)
+    rows = torch.arange(users.numel(), device=users.device)
+    return sharded_score_topk(ub, rows, out_i[lo:hi].contiguous(), lo, k, group=group, local_topk=local_topk,
+                              merge=merge)

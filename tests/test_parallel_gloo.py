@@ -96,6 +96,35 @@ def _worker(rank, world, port, out_dir):
         got_ids = par.sharded_score_topk(ue, users, ie[lo:hi], lo, 20, local_topk=local_topk, merge=_merge_cpu)
         want_ids = torch.sort(ue @ ie.T, dim=-1, descending=True, stable=True)[1][:, :20]
         assert torch.equal(got_ids, want_ids)
+        # user-partitioned bipartite propagation (items replicated, one all-reduce per layer)
+        def cpu_csr_from_coo(rows, cols, vals, n_rows, n_cols, with_transpose=False):
+            o = np.lexsort((cols.numpy(), rows.numpy()))
+            rpn = np.concatenate(([0], np.cumsum(np.bincount(rows.numpy(), minlength=n_rows)))).astype(np.int32)
+            return pkg("graph").CSRGraph(torch.from_numpy(rpn), cols[o].to(torch.int32), vals[o], n_rows, n_cols)
+
+        def spmm_cpu(g, X_, Y=None, acc_in=None, acc_out=None, scale=1.0):
+            rp_ = g.row_ptr.long()
+            base = int(rp_[0])
+            A_ = torch.sparse_csr_tensor(rp_ - base, g.col_idx.long()[base: int(rp_[-1])] - g.col_offset,
+                                         g.vals.double()[base: int(rp_[-1])], size=(g.n_rows, g.n_cols))
+            y = torch.sparse.mm(A_, X_.double()[: g.n_cols]).to(X_.dtype)
+            if Y is not None:
+                Y.copy_(y)
+            if acc_out is not None:
+                acc_out.copy_(((acc_in + y) if acc_in is not None else y) * scale)
+
+        full.n_users, full.n_items = U, I
+        sb = par.ShardedBipartite(full, rank, world, csr_from_coo=cpu_csr_from_coo)
+        assert sb.bounds[0] == 0 and sb.bounds[-1] == U
+        Xd2 = X.double()
+        ou, oi = par.bipartite_propagate_mean(sb, Xd2[sb.lo: sb.hi], Xd2[U:], 3, spmm_fn=spmm_cpu)
+        assert torch.allclose(ou, want[sb.lo: sb.hi].detach(), atol=1e-12)
+        assert torch.allclose(oi, want[U:].detach(), atol=1e-12)
+        some_users = torch.tensor([0, U - 1, U // 2, 3, 3])
+        got2 = par.bipartite_score_topk(sb, ou, oi, some_users, 10, local_topk=local_topk, merge=_merge_cpu)
+        w = want.detach()
+        want2 = torch.sort(w[some_users] @ w[U:].T, dim=-1, descending=True, stable=True)[1][:, :10]
+        assert torch.equal(got2, want2)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
