@@ -45,6 +45,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_launch"].get(kernel)
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -57,7 +66,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -277,7 +286,7 @@ def run_ours(args):
         return
     peak, peak_src = measured_peaks()
     kr = kernel_rooflines(env, peak)
-    dom = kr[0]
+    dom = kr[1]      # the launch propagate_mean issues: SpMM + fused layer sum over the UI graph
     n_train = len(env["tr"])
     steps_per_epoch = -(-n_train // B)
     line = {
@@ -296,7 +305,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"], "traffic": ncu_traffic(dom["kernel"]),
+                     "traffic_source": "ncu --set full capture committed under profiles/ (r01_ncu_traffic.json)",
                      "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]},
         "kernels": kr,
         "train_epoch_s": steps_per_epoch * ms / K / 1e3,

@@ -234,7 +234,7 @@ int mmrec_dense_act_bwd_f32(const float *dY, const float *Y, const float *X, con
  * query_t (Linear, Tanh, Linear), nn.Softmax(dim=-1), the three gate_*_prefer (Linear, Sigmoid),
  * nn.Dropout on each gate, the products, torch.stack + torch.mean and `content + side` -- and the
  * whole autograd graph under it, by one forward and one backward launch (+ a partial-sum reduce).
- *   F = fusion_embeds, V = image_embeds, T = text_embeds, C = content_embeds: [n, d], d in {32, 64}
+ *   F = fusion_embeds, V = image_embeds, T = text_embeds, C = content_embeds: [n, d], d in {32, 64, 128}
  *   W_host / b_host: HOST arrays of 7 device pointers, order
  *       query_v.0, query_v.2, query_t.0, query_t.2, gate_image_prefer.0, gate_text_prefer.0,
  *       gate_fusion_prefer.0   (each [d, d] row-major as nn.Linear stores it; b NULL = no bias)

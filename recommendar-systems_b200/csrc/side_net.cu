@@ -150,7 +150,7 @@ __device__ __forceinline__ void softmax_rows(float (&a)[4][4]) {
 
 // ================================================================================== forward
 template <int D>
-__global__ void __launch_bounds__(kT, 2)
+__global__ void __launch_bounds__(kT, D <= 64 ? 2 : 1)
 side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const float *__restrict__ T,
                 const float *__restrict__ C_, SideWeights P, const float *__restrict__ masks,
                 float *__restrict__ saved, float *__restrict__ side, float *__restrict__ all, int n, int n_tiles) {
@@ -269,7 +269,7 @@ __device__ __forceinline__ void emit_partial(float *__restrict__ partial, int w_
 }
 
 template <int D>
-__global__ void __launch_bounds__(kT, 2)
+__global__ void __launch_bounds__(kT, D <= 64 ? 2 : 1)
 side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_side, const float *__restrict__ F,
                 const float *__restrict__ V, const float *__restrict__ T, const float *__restrict__ C_,
                 SideWeights P, const float *__restrict__ masks, const float *__restrict__ saved,
@@ -478,7 +478,7 @@ int side_bwd_launch(const float *d_all, const float *d_side, const float *F, con
 
 using namespace mmrec;
 
-extern "C" int mmrec_smore_side_supported(int32_t d) { return d == 32 || d == 64; }
+extern "C" int mmrec_smore_side_supported(int32_t d) { return d == 32 || d == 64 || d == 128; }
 
 extern "C" size_t mmrec_smore_side_bwd_workspace_bytes(int32_t n, int32_t d) {
   if (!mmrec_smore_side_supported(d)) return 0;
@@ -502,7 +502,7 @@ extern "C" int mmrec_smore_side_fwd_f32(const float *F, const float *V, const fl
                                         int32_t d, void *stream) {
   MMREC_REQUIRE(F && V && T && C_ && W_host && b_host && saved && side && all, MMREC_E_BADARG,
                 "smore_side_fwd: null pointer");
-  MMREC_REQUIRE(mmrec_smore_side_supported(d), MMREC_E_BADARG, "smore_side_fwd: d must be 32 or 64 (got %d)", d);
+  MMREC_REQUIRE(mmrec_smore_side_supported(d), MMREC_E_BADARG, "smore_side_fwd: d must be 32, 64 or 128 (got %d)", d);
   MMREC_REQUIRE(n >= 0, MMREC_E_BADARG, "smore_side_fwd: bad n");
   MMREC_REQUIRE(aligned16(F) && aligned16(V) && aligned16(T) && aligned16(C_) && aligned16(masks) &&
                     aligned16(saved) && aligned16(side) && aligned16(all), MMREC_E_ALIGN,
@@ -512,8 +512,9 @@ extern "C" int mmrec_smore_side_fwd_f32(const float *F, const float *V, const fl
   if (rc != MMREC_OK) return rc;
   if (n == 0) return MMREC_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  return d == 64 ? side_fwd_launch<64>(F, V, T, C_, P, masks, saved, side, all, n, st)
-                 : side_fwd_launch<32>(F, V, T, C_, P, masks, saved, side, all, n, st);
+  return d == 64    ? side_fwd_launch<64>(F, V, T, C_, P, masks, saved, side, all, n, st)
+         : d == 128 ? side_fwd_launch<128>(F, V, T, C_, P, masks, saved, side, all, n, st)
+                    : side_fwd_launch<32>(F, V, T, C_, P, masks, saved, side, all, n, st);
 }
 
 extern "C" int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side, const float *F, const float *V,
@@ -524,7 +525,7 @@ extern "C" int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side,
   MMREC_REQUIRE(F && V && T && C_ && W_host && b_host && saved && dF && dV && dT && dC && dW_host && db_host && ws,
                 MMREC_E_BADARG, "smore_side_bwd: null pointer");
   MMREC_REQUIRE(d_all || d_side, MMREC_E_BADARG, "smore_side_bwd: no incoming gradient");
-  MMREC_REQUIRE(mmrec_smore_side_supported(d), MMREC_E_BADARG, "smore_side_bwd: d must be 32 or 64 (got %d)", d);
+  MMREC_REQUIRE(mmrec_smore_side_supported(d), MMREC_E_BADARG, "smore_side_bwd: d must be 32, 64 or 128 (got %d)", d);
   MMREC_REQUIRE(n > 0, MMREC_E_BADARG, "smore_side_bwd: bad n");
   MMREC_REQUIRE(aligned16(d_all) && aligned16(d_side) && aligned16(F) && aligned16(V) && aligned16(T) &&
                     aligned16(C_) && aligned16(masks) && aligned16(saved) && aligned16(dF) && aligned16(dV) &&
@@ -539,6 +540,7 @@ extern "C" int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side,
     G.db[i] = db_host[i];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  return d == 64 ? side_bwd_launch<64>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, G, ws, n, st)
-                 : side_bwd_launch<32>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, G, ws, n, st);
+  return d == 64    ? side_bwd_launch<64>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, G, ws, n, st)
+         : d == 128 ? side_bwd_launch<128>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, G, ws, n, st)
+                    : side_bwd_launch<32>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, G, ws, n, st);
 }

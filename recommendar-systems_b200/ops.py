@@ -551,7 +551,11 @@ class _SmoreSide(torch.autograd.Function):
 
 
 def smore_side_supported(d):
-    return bool(lib.load().mmrec_smore_side_supported(int(d)))
+    """Widths the models route through the fused kernel. The library also instantiates d = 128
+    (tested), but there the fp32-FMA kernel holds one 255-register CTA per SM and is slower than
+    the unfused path (Clothing, d = 128: 20.6 vs 18.5 ms/step): that width waits for the
+    tensor-core version."""
+    return int(d) in (32, 64) and bool(lib.load().mmrec_smore_side_supported(int(d)))
 
 
 def smore_side(fusion, image, text, content, layers, masks=None):

@@ -11,8 +11,11 @@ import bench  # noqa: E402
 
 model_name = sys.argv[1] if len(sys.argv) > 1 else "SMORE"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-env = bench.build_env("cuda:0", model_name=model_name,
-                      overrides={} if model_name in ("SMORE", "MGCN", "FREEDOM") else {"is_multimodal_model": False})
+shape = sys.argv[3] if len(sys.argv) > 3 else "baby"
+over = {} if model_name in ("SMORE", "MGCN", "FREEDOM") else {"is_multimodal_model": False}
+if len(sys.argv) > 4:
+    over["embedding_size"] = int(sys.argv[4])
+env = bench.build_env("cuda:0", model_name=model_name, shape=shape, overrides=over)
 trainer = bench.pkg("trainer").Trainer(env["config"], env["model"])
 batches = bench.take_batches(env["train"], 8 + steps)
 env["model"].train()

@@ -317,7 +317,7 @@ def _side_reference(F, V, T, C, layers, masks):
 
 
 @pytest.mark.parametrize("n,d,drop", [(26495, 64, 0.1), (7050, 64, 0.0), (1, 64, 0.0), (333, 32, 0.2),
-                                      (70001, 64, 0.0)])
+                                      (70001, 64, 0.0), (6001, 128, 0.1)])
 def test_smore_side_network_fused_forward_backward(n, d, drop):
     """K14: the fused preference module (one fwd + one bwd launch) vs float64 torch autograd."""
     ops = pkg("ops")
