@@ -22,17 +22,25 @@ namespace {
 
 using namespace dense;
 
+constexpr int kWP = 8;   // extra pitch of the staged weight matrix (conflict-free MMA B-fragment reads)
+
+template <int ACT>
+struct EpiBiasAct {
+  const float *bias;
+  __device__ __forceinline__ float2 operator()(float2 v, int n) const {
+    if (bias != nullptr) { v.x += __ldg(bias + n); v.y += __ldg(bias + n + 1); }
+    return make_float2(act_fwd<ACT>(v.x), act_fwd<ACT>(v.y));
+  }
+};
+
 template <int K, int N, int TM, int ACT>
 __global__ void __launch_bounds__(kT, K <= 64 ? 3 : 2)
 dense_fwd_kernel(const float *__restrict__ X, const float *__restrict__ W, const float *__restrict__ bias,
                  float *__restrict__ Y, int M, int n_tiles) {
   using T = Tile<K, N, TM>;
   extern __shared__ float4 smem4[];
-  float *Ws = reinterpret_cast<float *>(smem4);      // [K][N]   Ws[k][n] = W[n][k]
-  float *Xs = Ws + K * N;                            // [BM][K+4]
-  const int cg = threadIdx.x % T::CG, rg = threadIdx.x / T::CG, c0 = cg * 4;
-  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bias != nullptr) bv = ldg4(bias + c0);
+  float *Ws = reinterpret_cast<float *>(smem4);      // [K][N + 8]   Ws[k][n] = W[n][k]
+  float *Xs = Ws + K * (N + kWP);                    // [BM][K + 4]
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int m0 = tile * T::BM;
     RowStage<K, T::BM> xs;
@@ -49,30 +57,19 @@ dense_fwd_kernel(const float *__restrict__ X, const float *__restrict__ W, const
 #pragma unroll
       for (int i = 0; i < WPER; ++i) {
         const int idx = threadIdx.x + i * kT, n = idx % N, k4 = idx / N;
-        Ws[(k4 * 4 + 0) * N + n] = w[i].x;
-        Ws[(k4 * 4 + 1) * N + n] = w[i].y;
-        Ws[(k4 * 4 + 2) * N + n] = w[i].z;
-        Ws[(k4 * 4 + 3) * N + n] = w[i].w;
+        Ws[(k4 * 4 + 0) * (N + kWP) + n] = w[i].x;
+        Ws[(k4 * 4 + 1) * (N + kWP) + n] = w[i].y;
+        Ws[(k4 * 4 + 2) * (N + kWP) + n] = w[i].z;
+        Ws[(k4 * 4 + 3) * (N + kWP) + n] = w[i].w;
       }
     } else {
       __syncthreads();                               // previous tile fully consumed
     }
     xs.store(Xs);
     __syncthreads();
-    float acc[TM][4];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
-    tile_mma<K, TM, T::RG, N>(acc, Xs, rg, Ws, c0);
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int m = m0 + rg + T::RG * i;
-      if (m < M) {
-        float4 y;
-        y.x = act_fwd<ACT>(acc[i][0]); y.y = act_fwd<ACT>(acc[i][1]);
-        y.z = act_fwd<ACT>(acc[i][2]); y.w = act_fwd<ACT>(acc[i][3]);
-        *reinterpret_cast<float4 *>(Y + (size_t)m * N + c0) = y;
-      }
-    }
+    // Y tile = act(X tile * W^T + b) on the tensor cores, written from the accumulator fragments
+    tile_mma_tc<K, N, T::BM, K + 4, N + kWP, false>(Y + (size_t)m0 * N, N, M - m0, Xs, Ws, false,
+                                                    EpiBiasAct<ACT>{bias});
   }
 }
 
@@ -82,23 +79,15 @@ __global__ void __launch_bounds__(kT, K <= 64 ? 3 : 1)
 dense_bwd_kernel(const float *__restrict__ dY, const float *__restrict__ Y, const float *__restrict__ X,
                  const float *__restrict__ W, float *__restrict__ dX, float *__restrict__ partial, int M,
                  int n_tiles) {
-  constexpr int CGK = K / 4, RGK = kT / CGK, BM = RGK * TM;   // dX tile: TM rows x 4 k-columns per thread
-  constexpr int TN = N / 16, TK = K / 16;                      // dW tile per thread (16 x 16 threads)
+  constexpr int CGK = K / 4, RGK = kT / CGK, BM = RGK * TM;
   extern __shared__ float4 smem4[];
-  float *Wn = reinterpret_cast<float *>(smem4);     // [N][K]       natural layout (n-major)
-  float *Zs = Wn + N * K;                           // [BM][N+4]    dZ tile
-  float *Xs = Zs + BM * (N + 4);                    // [BM][K+4]    X tile
-  const int cg = threadIdx.x % CGK, rg = threadIdx.x / CGK, c0 = cg * 4;
-  const int tk = threadIdx.x % 16, tn = threadIdx.x / 16, k0 = tk * TK, n0 = tn * TN;
-  float dw[TN][TK], db[TN];
-#pragma unroll
-  for (int a = 0; a < TN; ++a) {
-    db[a] = 0.f;
-#pragma unroll
-    for (int b = 0; b < TK; ++b) dw[a][b] = 0.f;
-  }
+  float *Wn = reinterpret_cast<float *>(smem4);     // [N][K + 8]   natural layout (n-major)
+  float *Zs = Wn + N * (K + kWP);                   // [BM][N + 4]  dZ tile
+  float *Xs = Zs + BM * (N + 4);                    // [BM][K + 4]  X tile
+  float *p = partial + (size_t)blockIdx.x * (N * K + N);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int m0 = tile * BM;
+    const bool first = tile == (int)blockIdx.x;
     // every global load of the tile (and, first time, of W) is in flight before the first store
     RowStage<N, BM> gs, ys;
     RowStage<K, BM> xs;
@@ -106,13 +95,16 @@ dense_bwd_kernel(const float *__restrict__ dY, const float *__restrict__ Y, cons
     gs.load(dY, m0, M);
     xs.load(X, m0, M);
     if constexpr (ACT != kNone) ys.load(Y, m0, M);
-    if (tile == (int)blockIdx.x) {
+    if (first) {
       constexpr int WPER = N * K / 4 / kT;
       float4 w[WPER];
 #pragma unroll
       for (int i = 0; i < WPER; ++i) w[i] = ldg4(W + (threadIdx.x + i * kT) * 4);
 #pragma unroll
-      for (int i = 0; i < WPER; ++i) reinterpret_cast<float4 *>(Wn)[threadIdx.x + i * kT] = w[i];
+      for (int i = 0; i < WPER; ++i) {
+        const int idx = threadIdx.x + i * kT, n = idx / (K / 4), k4 = idx % (K / 4);
+        *reinterpret_cast<float4 *>(Wn + n * (K + kWP) + k4 * 4) = w[i];
+      }
     } else {
       __syncthreads();                               // previous tile fully consumed
     }
@@ -126,27 +118,17 @@ dense_bwd_kernel(const float *__restrict__ dY, const float *__restrict__ Y, cons
     gs.store(Zs);
     xs.store(Xs);
     __syncthreads();
-    if (dX != nullptr) {
-      float acc[TM][4];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-      tile_mma<N, TM, RGK, K>(acc, Zs, rg, Wn, c0);
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const int m = m0 + rg + RGK * i;
-        if (m < M)
-          *reinterpret_cast<float4 *>(dX + (size_t)m * K + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      }
+    // dX tile = dZ W  (rows of the tile x K columns, reduction over N)
+    if (dX != nullptr)
+      tile_mma_tc<N, K, BM, N + 4, K + kWP, false>(dX + (size_t)m0 * K, K, M - m0, Zs, Wn);
+    // dW (+)= dZ^T X  (N x K, reduction over the rows of the tile; rows beyond M are zero in both)
+    tile_mma_tc<BM, K, N, N + 4, K + 4, true>(p, K, N, Zs, Xs, !first);
+    if (threadIdx.x < N) {                           // db (+)= column sums of dZ
+      float sdb = 0.f;
+#pragma unroll 8
+      for (int m = 0; m < BM; ++m) sdb += Zs[m * (N + 4) + threadIdx.x];
+      p[N * K + threadIdx.x] = first ? sdb : p[N * K + threadIdx.x] + sdb;
     }
-    // dW[n0.., k0..] += dZ[m][n0..] * X[m][k0..]   (rows beyond M are zero in both tiles)
-    tile_outer<N, K, BM, TN, TK>(dw, db, Zs, n0, Xs, k0, tk == 0);
-  }
-  float *p = partial + (size_t)blockIdx.x * (N * K + N);
-#pragma unroll
-  for (int a = 0; a < TN; ++a) {
-#pragma unroll
-    for (int b = 0; b < TK; ++b) p[(n0 + a) * K + k0 + b] = dw[a][b];
-    if (tk == 0) p[N * K + n0 + a] = db[a];
   }
 }
 
@@ -184,9 +166,9 @@ template <int D> struct RowsPerThread { static constexpr int value = D == 128 ? 
 constexpr int kMaxParts = 4 * kNumSMs;   // cap on CTAs (= dW partials) of the backward
 
 template <int D, int TM>
-constexpr size_t fwd_smem() { return sizeof(float) * (D * D + Tile<D, D, TM>::BM * (D + 4)); }
+constexpr size_t fwd_smem() { return sizeof(float) * (D * (D + kWP) + Tile<D, D, TM>::BM * (D + 4)); }
 template <int D, int TM>
-constexpr size_t bwd_smem() { return sizeof(float) * (D * D + 2 * Tile<D, D, TM>::BM * (D + 4)); }
+constexpr size_t bwd_smem() { return sizeof(float) * (D * (D + kWP) + 2 * Tile<D, D, TM>::BM * (D + 4)); }
 
 template <int D, int ACT>
 int launch_fwd(const float *X, const float *W, const float *b, float *Y, int M, cudaStream_t st) {

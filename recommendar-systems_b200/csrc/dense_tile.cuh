@@ -84,6 +84,85 @@ __device__ __forceinline__ void tile_mma(float (&acc)[TM][4], const float *__res
 }
 
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core versions of the two tile products (mma.sync m16n8k8 tf32, 3xTF32 split in
+// registers: lo*hi + hi*lo + hi*hi, fp32 accumulate -> fp32-class accuracy for K <= 128). The d x d
+// layers are 0.2-1.5 GFMA per launch and FMA-bound on the CUDA cores; the warp-level MMA does
+// the same product with ~2.5x fewer issue slots. Results go back through shared memory (or
+// straight to global for dW), so the surrounding fragment code is unchanged.
+__device__ __forceinline__ void split_tf32_u(float x, uint32_t &hi, uint32_t &lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;        // round-to-nearest tf32 (no inf/nan guard)
+  lo = __float_as_uint(x - __uint_as_float(hi));            // the tensor core ignores the low 13 bits
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Warp tiling of a [BM x NN] product over the 8 warps of the CTA: BM/16 row slabs, the warps of a
+// slab split the columns.
+template <int BM, int NN>
+struct TcTile {
+  static constexpr int SLABS = BM / 16, WPS = (kT / 32) / SLABS, WN = NN / WPS, NF = WN / 8;
+  static_assert(BM % 16 == 0 && (kT / 32) % SLABS == 0 && NN % (WPS * 8) == 0, "tile does not fit 8 warps");
+};
+
+struct EpiIdentity {
+  __device__ __forceinline__ float2 operator()(float2 v, int /*n*/) const { return v; }
+};
+
+// out[m][n] (+)= epi(sum_k A[m][k] * B[k][n]): A at As[m * PA + k] (TRANS_A: As[k * PA + m]), B at
+// Bs[k * PB + n]; out at out[m * PO + n] (shared or global; rows >= m_lim are skipped). `epi`
+// maps the two adjacent columns (n, n + 1) of a result row, e.g. bias + activation.
+template <int KK, int NN, int BM, int PA, int PB, bool TRANS_A, typename Epi = EpiIdentity>
+__device__ __forceinline__ void tile_mma_tc(float *__restrict__ out, int PO, int m_lim, const float *__restrict__ As,
+                                            const float *__restrict__ Bs, bool accumulate = false, Epi epi = Epi()) {
+  using T = TcTile<BM, NN>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int rs = (warp % T::SLABS) * 16, cs = (warp / T::SLABS) * T::WN;
+  float c[T::NF][4];
+#pragma unroll
+  for (int j = 0; j < T::NF; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+#pragma unroll 2
+  for (int k8 = 0; k8 < KK; k8 += 8) {
+    uint32_t ah[4], al[4];
+    auto A = [&](int m, int k) { return TRANS_A ? As[k * PA + m] : As[m * PA + k]; };
+    split_tf32_u(A(rs + g, k8 + t), ah[0], al[0]);
+    split_tf32_u(A(rs + g + 8, k8 + t), ah[1], al[1]);
+    split_tf32_u(A(rs + g, k8 + t + 4), ah[2], al[2]);
+    split_tf32_u(A(rs + g + 8, k8 + t + 4), ah[3], al[3]);
+#pragma unroll
+    for (int j = 0; j < T::NF; ++j) {
+      uint32_t bh[2], bl[2];
+      const int n = cs + j * 8 + g;
+      split_tf32_u(Bs[(k8 + t) * PB + n], bh[0], bl[0]);
+      split_tf32_u(Bs[(k8 + t + 4) * PB + n], bh[1], bl[1]);
+      mma_tf32_16x8x8(c[j], al, bh);
+      mma_tf32_16x8x8(c[j], ah, bl);
+      mma_tf32_16x8x8(c[j], ah, bh);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < T::NF; ++j) {
+    const int n = cs + j * 8 + 2 * t;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = rs + g + 8 * h;
+      if (m < m_lim) {
+        float2 *dst = reinterpret_cast<float2 *>(out + (size_t)m * PO + n);
+        float2 v = epi(make_float2(c[j][2 * h], c[j][2 * h + 1]), n);
+        if (accumulate) {
+          const float2 o = *dst;
+          v.x += o.x; v.y += o.y;
+        }
+        *dst = v;
+      }
+    }
+  }
+}
+
 // dw[a][b] += sum_m Z[m][n0 + a] * X[m][k0 + b] over the BM staged rows (pitches NN+4 / KK+4);
 // db[a] += sum_m Z[m][n0 + a] in the threads with `with_db`. TN, TK in {2, 4, 8}.
 template <int NN, int KK, int BM, int TN, int TK>

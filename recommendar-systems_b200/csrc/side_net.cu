@@ -36,6 +36,7 @@ struct SideGrads {
 template <int D>
 struct Cfg {
   static constexpr int TM = 4, CG = D / 4, RG = kT / CG, BM = RG * TM, P = D + 4;
+  static constexpr int PW = D + 8;     // pitch of the staged weight matrix (conflict-free MMA B fragments)
   static constexpr int WPER = D * D / 4 / kT;
 };
 
@@ -107,10 +108,10 @@ struct WStage {
 #pragma unroll
     for (int i = 0; i < Cfg<D>::WPER; ++i) {
       const int idx = threadIdx.x + i * kT, n = idx % D, k4 = idx / D;
-      Ws[(k4 * 4 + 0) * D + n] = w[i].x;
-      Ws[(k4 * 4 + 1) * D + n] = w[i].y;
-      Ws[(k4 * 4 + 2) * D + n] = w[i].z;
-      Ws[(k4 * 4 + 3) * D + n] = w[i].w;
+      Ws[(k4 * 4 + 0) * Cfg<D>::PW + n] = w[i].x;
+      Ws[(k4 * 4 + 1) * Cfg<D>::PW + n] = w[i].y;
+      Ws[(k4 * 4 + 2) * Cfg<D>::PW + n] = w[i].z;
+      Ws[(k4 * 4 + 3) * Cfg<D>::PW + n] = w[i].w;
     }
   }
   __device__ __forceinline__ void load_n(const float *__restrict__ W) {
@@ -119,16 +120,30 @@ struct WStage {
   }
   __device__ __forceinline__ void store_n(float *Wn) const {
 #pragma unroll
-    for (int i = 0; i < Cfg<D>::WPER; ++i) reinterpret_cast<float4 *>(Wn)[threadIdx.x + i * kT] = w[i];
+    for (int i = 0; i < Cfg<D>::WPER; ++i) {
+      const int idx = threadIdx.x + i * kT, n = idx / (D / 4), k4 = idx % (D / 4);
+      *reinterpret_cast<float4 *>(Wn + n * Cfg<D>::PW + k4 * 4) = w[i];
+    }
   }
 };
 
 template <int D>
-__device__ __forceinline__ void bias_init(float (&acc)[4][4], const float *__restrict__ b, int c0) {
-  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (b != nullptr) bv = ldg4(b + c0);
+__device__ __forceinline__ void bias_add(float (&acc)[4][4], const float *__restrict__ b, int c0) {
+  if (b == nullptr) return;
+  const float4 bv = ldg4(b + c0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
+  for (int i = 0; i < 4; ++i) { acc[i][0] += bv.x; acc[i][1] += bv.y; acc[i][2] += bv.z; acc[i][3] += bv.w; }
+}
+
+// acc = A tile (shared, pitch P) x staged weight (pitch PW) on the tensor cores; the product passes
+// through the shared tile sO so that every thread gets the rows/columns its fragment owns.
+// Leaves the CTA synchronised after the product is visible.
+template <int D>
+__device__ __forceinline__ void product(Frag<D> &acc, float *sO, const float *sA, const float *sW, int rg, int c0) {
+  using C = Cfg<D>;
+  tile_mma_tc<D, D, C::BM, C::P, C::PW, false>(sO, C::P, C::BM, sA, sW);
+  __syncthreads();
+  acc.load_smem(sO, rg, c0);
 }
 
 // softmax over the d columns of every row; a row is spread over the CG threads of one sub-warp
@@ -156,10 +171,11 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
                 float *__restrict__ saved, float *__restrict__ side, float *__restrict__ all, int n, int n_tiles) {
   using C = Cfg<D>;
   extern __shared__ float4 smem4[];
-  float *Ws = reinterpret_cast<float *>(smem4);   // [D][D]   transposed weight
-  float *sF = Ws + D * D;                         // [BM][P]
+  float *Ws = reinterpret_cast<float *>(smem4);   // [D][PW]  transposed weight
+  float *sF = Ws + D * C::PW;                     // [BM][P]
   float *sC = sF + C::BM * C::P;
   float *sH = sC + C::BM * C::P;
+  float *sO = sH + C::BM * C::P;                  // product staging
   const int cg = threadIdx.x % C::CG, rg = threadIdx.x / C::CG, c0 = cg * 4;
   const size_t nd = (size_t)n * D;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -179,8 +195,8 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
       w.store_t(Ws);
       w.load_t(P.W[2 * br + 1]);
       __syncthreads();
-      bias_init<D>(acc.v, P.b[2 * br], c0);
-      tile_mma<D, 4, C::RG, D>(acc.v, sF, rg, Ws, c0);
+      product<D>(acc, sO, sF, Ws, rg, c0);
+      bias_add<D>(acc.v, P.b[2 * br], c0);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -191,8 +207,7 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
       w.store_t(Ws);
       w.load_t(P.W[br == 0 ? 2 : 4]);
       __syncthreads();
-      acc.fill(0.f);
-      tile_mma<D, 4, C::RG, D>(acc.v, sH, rg, Ws, c0);
+      product<D>(acc, sO, sH, Ws, rg, c0);
       softmax_rows<D>(acc.v);
       acc.store(saved + (2 * br + 1) * nd, m0, n, rg, c0);
       x.load(br == 0 ? V : T, m0, n, rg, c0);
@@ -211,8 +226,8 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
       w.store_t(Ws);
       if (g < 2) w.load_t(P.W[5 + g]);
       __syncthreads();
-      bias_init<D>(acc.v, P.b[4 + g], c0);
-      tile_mma<D, 4, C::RG, D>(acc.v, sC, rg, Ws, c0);
+      product<D>(acc, sO, sC, Ws, rg, c0);
+      bias_add<D>(acc.v, P.b[4 + g], c0);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -249,26 +264,6 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
 // ================================================================================== backward
 // partial layout: [kNW][n_parts][D*D + D]; a CTA that owns several tiles accumulates into its slot.
 template <int D>
-__device__ __forceinline__ void emit_partial(float *__restrict__ partial, int w_idx, int n_parts, bool first,
-                                             const float (&dw)[D / 16][D / 16], const float (&db)[D / 16],
-                                             int n0, int k0, bool with_db) {
-  constexpr int TN = D / 16;
-  float *p = partial + ((size_t)w_idx * n_parts + blockIdx.x) * (D * D + D);
-#pragma unroll
-  for (int a = 0; a < TN; ++a) {
-#pragma unroll
-    for (int b = 0; b < TN; ++b) {
-      float *q = p + (n0 + a) * D + k0 + b;
-      *q = first ? dw[a][b] : *q + dw[a][b];
-    }
-    if (with_db) {
-      float *q = p + D * D + n0 + a;
-      *q = first ? db[a] : *q + db[a];
-    }
-  }
-}
-
-template <int D>
 __global__ void __launch_bounds__(kT, D <= 64 ? 2 : 1)
 side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_side, const float *__restrict__ F,
                 const float *__restrict__ V, const float *__restrict__ T, const float *__restrict__ C_,
@@ -276,15 +271,14 @@ side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_sid
                 float *__restrict__ dF, float *__restrict__ dV, float *__restrict__ dT, float *__restrict__ dC,
                 float *__restrict__ partial, int n, int n_tiles) {
   using C = Cfg<D>;
-  constexpr int TN = D / 16;
   extern __shared__ float4 smem4[];
-  float *Wn = reinterpret_cast<float *>(smem4);   // [D][D]  natural layout (output-major)
-  float *sZ = Wn + D * D;                         // [BM][P] dz tile
+  float *Wn = reinterpret_cast<float *>(smem4);   // [D][PW] natural layout (output-major)
+  float *sZ = Wn + D * C::PW;                     // [BM][P] dz tile
   float *sC = sZ + C::BM * C::P;
   float *sF = sC + C::BM * C::P;
   float *sH = sF + C::BM * C::P;
+  float *sO = sH + C::BM * C::P;                  // product staging
   const int cg = threadIdx.x % C::CG, rg = threadIdx.x / C::CG, c0 = cg * 4;
-  const int tk = threadIdx.x % 16, tn = threadIdx.x / 16, k0 = tk * TN, n0 = tn * TN;
   const size_t nd = (size_t)n * D;
   const int n_parts = gridDim.x;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -313,27 +307,30 @@ side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_sid
     fs.store(sF);
     cs.store(sC);
     WStage<D> w;
-    float dw[TN][TN], db[TN];
-    auto zero_dw = [&]() {
-#pragma unroll
-      for (int a = 0; a < TN; ++a) {
-        db[a] = 0.f;
-#pragma unroll
-        for (int b = 0; b < TN; ++b) dw[a][b] = 0.f;
-      }
-    };
     // One dense layer of the backward chain: dz is in `acc`; X is the staged input tile of the
-    // layer. out += dz W;  partial[w_idx] (+)= dz^T X, sum_rows dz.
+    // layer. out += dz W;  partial[w_idx] (+)= dz^T X, sum_rows dz. Both products on tensor cores.
     auto layer_bwd = [&](int w_idx, const float *sX, Frag<D> &out, bool with_bias) {
       w.load_n(P.W[w_idx]);
-      __syncthreads();                                  // earlier readers of sZ / Wn are done
+      __syncthreads();                                  // earlier readers of sZ / Wn / sO are done
       acc.store_smem(sZ, rg, c0);
       w.store_n(Wn);
       __syncthreads();
-      tile_mma<D, 4, C::RG, D>(out.v, sZ, rg, Wn, c0);
-      zero_dw();
-      tile_outer<D, D, C::BM, TN, TN>(dw, db, sZ, n0, sX, k0, with_bias && tk == 0);
-      emit_partial<D>(partial, w_idx, n_parts, first, dw, db, n0, k0, with_bias && tk == 0);
+      float *slot = partial + ((size_t)w_idx * n_parts + blockIdx.x) * (D * D + D);
+      tile_mma_tc<D, D, C::BM, C::P, C::PW, false>(sO, C::P, C::BM, sZ, Wn);          // dz W
+      tile_mma_tc<C::BM, D, D, C::P, C::P, true>(slot, D, D, sZ, sX, !first);         // dz^T X
+      if (with_bias && threadIdx.x < D) {
+        float sdb = 0.f;
+#pragma unroll 8
+        for (int m = 0; m < C::BM; ++m) sdb += sZ[m * C::P + threadIdx.x];
+        slot[D * D + threadIdx.x] = first ? sdb : slot[D * D + threadIdx.x] + sdb;
+      }
+      __syncthreads();
+      Frag<D> tmp;
+      tmp.load_smem(sO, rg, c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out.v[i][j] += tmp.v[i][j];
     };
 #pragma unroll 1
     for (int br = 0; br < 3; ++br) {
@@ -429,9 +426,9 @@ side_partial_reduce_kernel(const float *__restrict__ partial, int n_parts, int n
 }
 
 template <int D>
-constexpr size_t side_fwd_smem() { return sizeof(float) * (D * D + 3 * Cfg<D>::BM * Cfg<D>::P); }
+constexpr size_t side_fwd_smem() { return sizeof(float) * (D * Cfg<D>::PW + 4 * Cfg<D>::BM * Cfg<D>::P); }
 template <int D>
-constexpr size_t side_bwd_smem() { return sizeof(float) * (D * D + 4 * Cfg<D>::BM * Cfg<D>::P); }
+constexpr size_t side_bwd_smem() { return sizeof(float) * (D * Cfg<D>::PW + 5 * Cfg<D>::BM * Cfg<D>::P); }
 
 inline int side_parts(int n, int d) {
   const int bm = (kT / (d / 4)) * 4;
