@@ -114,9 +114,9 @@ struct EpiIdentity {
 };
 
 // out[m][n] (+)= epi(sum_k A[m][k] * B[k][n]): A at As[m * PA + k] (TRANS_A: As[k * PA + m]), B at
-// Bs[k * PB + n]; out at out[m * PO + n] (shared or global; rows >= m_lim are skipped). `epi`
-// maps the two adjacent columns (n, n + 1) of a result row, e.g. bias + activation.
-template <int KK, int NN, int BM, int PA, int PB, bool TRANS_A, typename Epi = EpiIdentity>
+// Bs[k * PB + n] (TRANS_B: Bs[n * PB + k]); out at out[m * PO + n] (shared or global; rows >= m_lim
+// are skipped). `epi` maps the two adjacent columns (n, n + 1) of a result row, e.g. bias + activation.
+template <int KK, int NN, int BM, int PA, int PB, bool TRANS_A, typename Epi = EpiIdentity, bool TRANS_B = false>
 __device__ __forceinline__ void tile_mma_tc(float *__restrict__ out, int PO, int m_lim, const float *__restrict__ As,
                                             const float *__restrict__ Bs, bool accumulate = false, Epi epi = Epi()) {
   using T = TcTile<BM, NN>;
@@ -137,8 +137,8 @@ __device__ __forceinline__ void tile_mma_tc(float *__restrict__ out, int PO, int
     for (int j = 0; j < T::NF; ++j) {
       uint32_t bh[2], bl[2];
       const int n = cs + j * 8 + g;
-      split_tf32_u(Bs[(k8 + t) * PB + n], bh[0], bl[0]);
-      split_tf32_u(Bs[(k8 + t + 4) * PB + n], bh[1], bl[1]);
+      split_tf32_u(TRANS_B ? Bs[n * PB + k8 + t] : Bs[(k8 + t) * PB + n], bh[0], bl[0]);
+      split_tf32_u(TRANS_B ? Bs[n * PB + k8 + t + 4] : Bs[(k8 + t + 4) * PB + n], bh[1], bl[1]);
       mma_tf32_16x8x8(c[j], al, bh);
       mma_tf32_16x8x8(c[j], ah, bl);
       mma_tf32_16x8x8(c[j], ah, bh);

@@ -34,10 +34,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// hi = round-to-nearest tf32 (integer arithmetic on the bit pattern: cvt.rna.tf32.f32 without its
+// inf/nan guards, 2 instructions instead of 4); lo = x - hi, left as fp32: the tensor core ignores
+// the 13 low mantissa bits of a tf32 operand.
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(

@@ -7,15 +7,19 @@
 // vector atomics (red.global.add.v4.f32) because users/items repeat inside a batch.
 //
 // InfoNCE: rows are gathered + L2-normalised once, then a 64x64-tile kernel streams V1 V2^T
-// through shared memory, applies exp(s/t) and keeps only row sums -- the B x B matrix never
-// reaches HBM. Backward recomputes the tiles (flash-style) for the row pass (dV1) and the column
-// pass (dV2). All scalars are reduced in a fixed order.
+// through shared memory (tile products on the tensor cores: mma.sync, 3xTF32 split = fp32-class
+// scores), applies exp(s/t) and keeps only row sums -- the B x B matrix never reaches HBM.
+// Backward recomputes the tiles (flash-style) for the row pass (dV1) and the column pass (dV2);
+// the gradient tile G goes straight back into a second tensor-core product G * V. All scalars
+// are reduced in a fixed order.
 #include "common.cuh"
+#include "dense_tile.cuh"
 
 namespace mmrec {
 namespace {
 
 constexpr int kThreads = 256;
+static_assert(kThreads == dense::kT, "the tensor-core tile helpers assume 256-thread CTAs");
 
 __device__ __forceinline__ float softplus_neg(float x) {  // -logsigmoid(x)
   return fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
@@ -171,26 +175,20 @@ __device__ __forceinline__ void load_tile(float *s, const float *__restrict__ M,
   }
 }
 
-// acc[i][j] = <A[ty + 16 i], B[tx + 16 j]> over D
+// acc[i][j] = <A[ty + 16 i], B[tx + 16 j]> over D: the 64 x 64 x D product runs on the tensor cores
+// (mma.sync, 3xTF32: fp32-class scores), passes through the shared tile sS [kTile][kTile + 4] and is
+// picked up in the (tx, ty) ownership the exp / row-sum / gradient code uses. Callers synchronise
+// before (operand tiles staged) -- this function synchronises after the product.
 template <int D>
-__device__ __forceinline__ void tile_dots(float (&acc)[4][4], const float *sA, const float *sB, int tx, int ty) {
-  constexpr int LD = D + 4;
+__device__ __forceinline__ void tile_dots(float (&acc)[4][4], float *sS, const float *sA, const float *sB, int tx,
+                                          int ty) {
+  constexpr int LD = D + 4, GL = kTile + 4;
+  dense::tile_mma_tc<D, kTile, kTile, LD, LD, false, dense::EpiIdentity, true>(sS, GL, kTile, sA, sB);
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < D; k += 4) {
-    float4 a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(sA + (ty + 16 * i) * LD + k);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4 *>(sB + (tx + 16 * j) * LD + k);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] += dot4(a[i], b[j]);
-  }
+    for (int j = 0; j < 4; ++j) acc[i][j] = sS[(ty + 16 * i) * GL + tx + 16 * j];
 }
 
 // grid = (row tiles, column splits). ttl_part[split][row] = sum over the split's columns of
@@ -206,7 +204,7 @@ infonce_fwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
                    float *__restrict__ loss_out, uint32_t *counters) {
   extern __shared__ __align__(16) float smem[];
   constexpr int LD = D + 4;
-  float *sA = smem, *sB = smem + kTile * LD;
+  float *sA = smem, *sB = smem + kTile * LD, *sS = smem + 2 * kTile * LD;
   __shared__ float red[kThreads / 32];
   __shared__ bool is_last;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -220,7 +218,7 @@ infonce_fwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
     load_tile<D>(sB, V2n, t * kTile, batch);
     __syncthreads();
     float acc[4][4];
-    tile_dots<D>(acc, sA, sB, tx, ty);
+    tile_dots<D>(acc, sS, sA, sB, tx, ty);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = row0 + ty + 16 * i;
@@ -297,19 +295,15 @@ infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
   const int t_begin = blockIdx.y * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
   float *dOut = dOutAll + (size_t)blockIdx.y * batch * D;
   load_tile<D>(sOwn, Own, own0, batch);
-  // output accumulators: thread (tx, ty) owns rows {ty + 16 i} x column chunk of D/16 floats at tx
-  constexpr int CW = D / 16;
-  float out[4][CW];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int c = 0; c < CW; ++c) out[i][c] = 0.f;
+  // Both products of a tile pair run on the tensor cores: S = Own Other^T (through sG, which then
+  // holds G in place), and dOut (+)= G Other, accumulated across the CTA's tiles in its output slab.
+  bool first = true;
   for (int t = t_begin; t < t_end; ++t) {
     __syncthreads();
     load_tile<D>(sOther, Other, t * kTile, batch);
     __syncthreads();
     float acc[4][4];
-    tile_dots<D>(acc, sOwn, sOther, tx, ty);
+    tile_dots<D>(acc, sG, sOwn, sOther, tx, ty);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int o = own0 + ty + 16 * i;
@@ -323,49 +317,17 @@ infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
           if (row == col) g -= 1.f;
           g *= scale;
         }
-        sG[(ty + 16 * i) * GL + tx + 16 * j] = g;
+        sG[(ty + 16 * i) * GL + tx + 16 * j] = g;     // same element this thread just read
       }
     }
     __syncthreads();
-    // out[own][:] += sum_x G[own][x] * Other[x][:]   (16-byte shared loads: 8 per 64 FMAs)
-#pragma unroll 2
-    for (int x = 0; x < kTile; x += 4) {
-      float4 g4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) g4[i] = *reinterpret_cast<const float4 *>(sG + (ty + 16 * i) * GL + x);
-#pragma unroll
-      for (int xx = 0; xx < 4; ++xx) {
-        float ov[CW];
-        const float *src = sOther + (x + xx) * LD + tx * CW;
-        if constexpr (CW % 4 == 0) {
-#pragma unroll
-          for (int c = 0; c < CW; c += 4) {
-            const float4 v = *reinterpret_cast<const float4 *>(src + c);
-            ov[c] = v.x; ov[c + 1] = v.y; ov[c + 2] = v.z; ov[c + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < CW; c += 2) {
-            const float2 v = *reinterpret_cast<const float2 *>(src + c);
-            ov[c] = v.x; ov[c + 1] = v.y;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float g = xx == 0 ? g4[i].x : xx == 1 ? g4[i].y : xx == 2 ? g4[i].z : g4[i].w;
-#pragma unroll
-          for (int c = 0; c < CW; ++c) out[i][c] = fmaf(g, ov[c], out[i][c]);
-        }
-      }
-    }
+    // dOut[own][:] (+)= sum_x G[own][x] * Other[x][:]
+    dense::tile_mma_tc<kTile, D, kTile, GL, LD, false>(dOut + (size_t)own0 * D, D, batch - own0, sG, sOther, !first);
+    first = false;
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int o = own0 + ty + 16 * i;
-    if (o < batch) {
-#pragma unroll
-      for (int c = 0; c < CW; ++c) dOut[(size_t)o * D + tx * CW + c] = out[i][c];
-    }
+  if (first) {                                          // a split past the last tile: zero slab
+    for (int i = threadIdx.x; i < kTile * D; i += kThreads)
+      if (own0 + i / D < batch) dOut[(size_t)own0 * D + i] = 0.f;
   }
 }
 
@@ -432,7 +394,7 @@ int infonce_fwd_launch(const float *V1n, const float *V2n, int batch, float inv_
   const int splits = infonce_splits(batch);
   const int tps = (n_tiles + splits - 1) / splits;
   // partial layout: pos[batch], ttl_part[splits][batch], tile_loss[n_tiles]
-  const size_t smem = 2 * kTile * (D + 4) * sizeof(float);
+  const size_t smem = (2 * kTile * (D + 4) + kTile * (kTile + 4)) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     MMREC_CUDA(cudaFuncSetAttribute(infonce_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
