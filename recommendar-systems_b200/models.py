@@ -384,6 +384,32 @@ class _MultiViewBase(GeneralRecommender):
         o = ops.bpr_table(all_e, self.n_users, users, pos, neg)
         return o[0] / users.shape[0] + self.reg_weight * (o[1] / self.batch_size)
 
+    # ---- independent branches of the forward on side streams ---------------------------------
+    # The user-item propagation (4 latency-bound SpMMs), the text projection and the image
+    # projection do not depend on one another until the side network; on one stream they run back
+    # to back while each leaves most of the GPU idle. Forked onto side streams they overlap -- in
+    # eager mode and, because the fork/join is captured, inside the CUDA graph of the training
+    # step; autograd replays every backward node on the stream of its forward, so the backward
+    # overlaps the same way.
+    def _fork(self, idx):
+        if not (getattr(self, "overlap_streams", False) and torch.device(self.device).type == "cuda"):
+            return None
+        streams = self.__dict__.setdefault("_aux_streams", {})
+        if idx not in streams:
+            streams[idx] = torch.cuda.Stream(device=self.device)
+        s = streams[idx]
+        s.wait_stream(torch.cuda.current_stream())
+        return s
+
+    @staticmethod
+    def _join(s, *tensors):
+        if s is None:
+            return
+        main = torch.cuda.current_stream()
+        main.wait_stream(s)
+        for t in tensors:
+            t.record_stream(main)
+
     def _view(self, x, item_graph):
         for _ in range(self.n_layers):
             x = ops.spmm(item_graph, x)
@@ -524,6 +550,7 @@ class SMORE(_MultiViewBase):
         self.inject_scale = float(config.get("inject_scale", 0.7))
         self.spectral_weight_norm = bool(config.get("spectral_weight_norm", True))
         self.cl_temp = float(config.get("cl_temp", 0.2))
+        self.overlap_streams = bool(config.get("overlap_streams", os.environ.get("MMREC_OVERLAP", "1") != "0"))
 
     def spectrum_convolution(self, image_embeds, text_embeds):
         """smore.py:209-252 without the band-energy .item() syncs (diagnostics only)."""
@@ -538,10 +565,17 @@ class SMORE(_MultiViewBase):
         return (u, i, side, content) if train else (u, i)
 
     def _forward_full(self, adj):
-        image_feats = self.image_trs(self.image_embedding.weight)
-        text_feats = self.text_trs(self.text_embedding.weight)
-        image_conv, text_conv, fusion_conv = self.spectrum_convolution(image_feats, text_feats)
+        import contextlib
         item = self.item_id_embedding.weight
+        s_ui, s_txt = self._fork(0), self._fork(1)
+        with torch.cuda.stream(s_ui) if s_ui is not None else contextlib.nullcontext():
+            ego = torch.cat([self.user_embedding.weight, item], dim=0)
+            content = ops.propagate_mean(adj, ego, self.n_ui_layers)
+        with torch.cuda.stream(s_txt) if s_txt is not None else contextlib.nullcontext():
+            text_feats = self.text_trs(self.text_embedding.weight)
+        image_feats = self.image_trs(self.image_embedding.weight)
+        self._join(s_txt, text_feats)
+        image_conv, text_conv, fusion_conv = self.spectrum_convolution(image_feats, text_feats)
         if self.inject_mode == "mul":
             image_item = item * self.gate_v(image_conv)
             text_item = item * self.gate_t(text_conv)
@@ -550,11 +584,10 @@ class SMORE(_MultiViewBase):
             image_item = item + self.inject_scale * self.gate_v(image_conv)
             text_item = item + self.inject_scale * self.gate_t(text_conv)
             fusion_item = item + self.inject_scale * self.gate_f(fusion_conv)
-        ego = torch.cat([self.user_embedding.weight, item], dim=0)
-        content = ops.propagate_mean(adj, ego, self.n_ui_layers)
         image_embeds, text_embeds, fusion_embeds = self._views(
             (image_item, text_item, fusion_item),
             (self.image_original_adj, self.text_original_adj, self.fusion_adj))
+        self._join(s_ui, content)
         # modality-aware preference module (smore.py:321-341): one fused kernel for d = 32 / 64
         if ops.smore_side_supported(self.embedding_dim):
             masks = None
