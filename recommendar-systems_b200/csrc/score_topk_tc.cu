@@ -1,5 +1,5 @@
 // Full-rank scoring on the 5th-generation tensor cores, fused with train-item masking and a
-// per-user top-K (K8/K9/K10): the tcgen05 path behind mmrec_score_mask_topk_f32 for d = 32 / 64.
+// per-user top-K (K8/K9/K10): the tcgen05 path behind mmrec_score_mask_topk_f32 for d = 32 / 64 / 128.
 //
 // One CTA owns 128 users (the M = 128 rows of the MMA = the 128 TMEM lanes) and walks its item
 // range in tiles of 64 items. Warp roles:
@@ -9,14 +9,17 @@
 //   warp  8    MMA       : one elected thread issues tcgen05.mma kind::tf32, 3 x (d/8) per tile
 //                          (lo*hi + hi*lo + hi*hi -> fp32-accurate scores), accumulating in one of
 //                          four 64-column TMEM buffers; tcgen05.commit frees the smem stage and
-//                          publishes the accumulator;
+//                          publishes the accumulator. For d >= 64 the user tile (A operand, hi and
+//                          lo halves) sits in TMEM columns [256, 256 + 2d), written once with
+//                          tcgen05.st, and the MMA is issued in its A-from-TMEM form;
 //   warps 0-3  epilogue  : tcgen05.ld -- TMEM lane i is user i, so every thread reads the scores
-//                          of its own user, 32 items at a time, filters them against the running
-//                          K-th best, applies the train-item mask (ascending cursor) and pushes the
-//                          survivors into a K-entry heap in shared memory ordered by (score, -id).
+//                          of its own user, 32 items at a time, appends those above its running
+//                          K-th best to a pending list in shared memory; warp-synchronous flushes
+//                          apply the train-item mask (ascending cursor) and push the survivors
+//                          into a K-entry 8-ary heap ordered by (score, -id).
 // Scores never reach HBM. Stages hand over through mbarriers (smem full/empty, TMEM full/empty).
 // Output: per item-split partial lists, descending score, ties -> lower id, merged by
-// topk_merge_kernel (score_topk.cu). The user tile is split once per CTA (hi/lo A operand tiles).
+// topk_merge_kernel (score_topk.cu).
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -34,14 +37,20 @@ constexpr int kAcc = 4;         // TMEM accumulator buffers (64 columns each)
 constexpr int kThreadsTC = 288; // 4 epilogue + 4 producer + 1 MMA warp
 constexpr int kChunk = 32;      // scores handled per tcgen05.ld
 
-template <int D>
+// A_TMEM: the user tile (hi and lo halves) lives in tensor memory next to the accumulators
+// (columns [256, 256 + 2D)) instead of shared memory and the MMAs are issued in the A-from-TMEM
+// form. That is what makes d = 128 fit: 128 KB of A tiles + 2 x 64 KB item stages + the heaps
+// would be 330 KB of shared memory; with A in TMEM it is 200 KB.
+template <int D, bool A_TMEM>
 struct Cfg {
   static constexpr int KB = D / 32;                         // 128-byte K atoms per row
-  static constexpr int STAGES = D <= 32 ? 4 : 2;
+  static constexpr int STAGES = D <= 32 ? 4 : (D <= 64 && A_TMEM ? 3 : 2);
   static constexpr uint32_t A_HALF = KB * kTileM * 128;     // bytes of the hi (or lo) user tile
   static constexpr uint32_t B_HALF = KB * kTileN * 128;     // bytes of the hi (or lo) item tile
   static constexpr uint32_t STAGE = 2 * B_HALF;
-  static constexpr uint32_t OFF_B = 2 * A_HALF;
+  static constexpr uint32_t OFF_B = A_TMEM ? 0 : 2 * A_HALF;
+  static constexpr uint32_t TMEM_COLS = A_TMEM ? 512 : kAcc * kTileN;   // power of two >= 256 + 2D
+  static constexpr uint32_t A_COL = kAcc * kTileN;          // first TMEM column of the hi user tile
   static constexpr uint32_t OFF_HEAP = OFF_B + STAGES * STAGE;
   static constexpr int VEC = kTileN * (D / 4) / 128;        // float4 per producer thread per tile
 };
@@ -70,7 +79,8 @@ __device__ __forceinline__ void heap_sift_down(float *hv, int32_t *hi_, int pos,
       id[j] = in ? hi_[(c0 + j) * kTileM] : 0;
     }
     // worst child = lowest score, ties -> highest id. Shallow trees instead of a 7-step scan: the
-    // epilogue is one warp per scheduler, so the DEPTH of the dependent chain is what costs.
+    // epilogue is one warp per scheduler, so the DEPTH of the dependent chain is what costs (loading
+    // the id of the chosen child only, after the min, was slower: one more dependent load per level).
     const float wv = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
     int t[kAry];
 #pragma unroll
@@ -104,22 +114,24 @@ __device__ __forceinline__ void heap_sift_up(float *hv, int32_t *hi_, int pos, f
   hi_[pos * kTileM] = gid;
 }
 
-template <int D>
+template <int D, bool A_TMEM>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restrict__ users, int n_users,
                      const float *__restrict__ item_emb, int n_items, int item_offset,
                      const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_cols, int k,
-                     int items_per_split, float *__restrict__ ws_val, int32_t *__restrict__ ws_idx, int dbg) {
-  using C = Cfg<D>;
+                     int items_per_split, float *__restrict__ ws_val, int32_t *__restrict__ ws_idx, int pend_cap,
+                     int dbg) {
+  using C = Cfg<D, A_TMEM>;
+  static_assert(!A_TMEM || kAcc * kTileN + 2 * D <= 512, "user tile does not fit beside the accumulators");
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (SW128 atoms) by an offset on the __shared__ array itself: pointers derived
   // through an integer cast would lose their address space and compile to generic LD/ST
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float *h_val = reinterpret_cast<float *>(smem + C::OFF_HEAP);              // [k][128]
   int32_t *h_idx = reinterpret_cast<int32_t *>(h_val + (size_t)k * kTileM);  // [k][128]
-  float *c_val = reinterpret_cast<float *>(h_idx + (size_t)k * kTileM);      // [32][128]
-  uint8_t *c_col = reinterpret_cast<uint8_t *>(c_val + kChunk * kTileM);     // [32][128]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(c_col + kChunk * kTileM);
+  float *p_val = reinterpret_cast<float *>(h_idx + (size_t)k * kTileM);      // [pend_cap][128] pending
+  int32_t *p_idx = reinterpret_cast<int32_t *>(p_val + (size_t)pend_cap * kTileM);   // candidates
+  uint64_t *bars = reinterpret_cast<uint64_t *>(p_idx + (size_t)pend_cap * kTileM);
   uint64_t *full = bars, *empty = bars + C::STAGES, *tfull = bars + 2 * C::STAGES, *tempty = tfull + kAcc;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kAcc);
 
@@ -136,12 +148,36 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
     for (int b = 0; b < kAcc; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, kAcc * kTileN);
+  if (warp == 8) tmem_alloc(tmem_slot, C::TMEM_COLS);
 
   // ---- user tile -> hi/lo A operand (thread = user row = TMEM lane) ------------------------
   const int b_user = blockIdx.x * kTileM + tid;
   const bool live = tid < kTileM && b_user < n_users;
-  if (tid < kTileM) {
+  if constexpr (A_TMEM) {
+    fence_before_sync();
+    __syncthreads();                 // barriers initialised, TMEM base address published
+    fence_after_sync();
+    if (tid < kTileM) {
+      const uint32_t a_row = *tmem_slot + ((uint32_t)(warp * 32) << 16) + C::A_COL;
+      const float *src = live ? user_emb + (size_t)users[b_user] * D : nullptr;
+#pragma unroll
+      for (int c32 = 0; c32 < D / 32; ++c32) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 v = live ? ldg4(src + c32 * 32 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f), h, l;
+          split_tf32x4(v, h, l);
+          hi[c4 * 4 + 0] = __float_as_uint(h.x); hi[c4 * 4 + 1] = __float_as_uint(h.y);
+          hi[c4 * 4 + 2] = __float_as_uint(h.z); hi[c4 * 4 + 3] = __float_as_uint(h.w);
+          lo[c4 * 4 + 0] = __float_as_uint(l.x); lo[c4 * 4 + 1] = __float_as_uint(l.y);
+          lo[c4 * 4 + 2] = __float_as_uint(l.z); lo[c4 * 4 + 3] = __float_as_uint(l.w);
+        }
+        tmem_st_32x32b_x32(a_row + c32 * 32, hi);          // warp-collective: dead rows store zeros
+        tmem_st_32x32b_x32(a_row + D + c32 * 32, lo);
+      }
+      tmem_st_wait();
+    }
+  } else if (tid < kTileM) {
     const float *src = live ? user_emb + (size_t)users[b_user] * D : nullptr;
 #pragma unroll
     for (int c4 = 0; c4 < D / 4; ++c4) {
@@ -196,6 +232,7 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
     constexpr uint32_t idesc = idesc_tf32(kTileM, kTileN, false, false);
     const uint64_t a_hi = smem_desc_sw128(smem_base, 16, 1024);
     const uint64_t a_lo = smem_desc_sw128(smem_base + C::A_HALF, 16, 1024);
+    const uint32_t at_hi = tmem_base + C::A_COL, at_lo = at_hi + D;   // A_TMEM: one column per K element
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % C::STAGES, b = t % kAcc;
       mbar_wait(full + s, (t / C::STAGES) & 1);
@@ -214,9 +251,14 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
         for (int kb = 0; kb < C::KB; ++kb)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = a0 + ((kb * (kTileM * 128) + ks * 32) >> 4);
             const uint64_t bd = b0 + ((kb * (kTileN * 128) + ks * 32) >> 4);
-            if (elect_one()) umma_tf32_ss(d_tmem, ad, bd, idesc, (pass | kb | ks) != 0);
+            if constexpr (A_TMEM) {
+              const uint32_t at = (pass == 0 ? at_lo : at_hi) + kb * 32 + ks * 8;
+              if (elect_one()) umma_tf32_ts(d_tmem, at, bd, idesc, (pass | kb | ks) != 0);
+            } else {
+              const uint64_t ad = a0 + ((kb * (kTileM * 128) + ks * 32) >> 4);
+              if (elect_one()) umma_tf32_ss(d_tmem, ad, bd, idesc, (pass | kb | ks) != 0);
+            }
           }
       }
       if (elect_one()) {
@@ -240,12 +282,43 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
       mp = lo;
       if (mp < mend) next_masked = mask_cols[mp];
     }
-    int cnt = 0;
+    // Candidates (scores above the user's K-th best as of the last flush) are only APPENDED to a
+    // per-user pending list while tiles stream by; the heap work happens in warp-synchronous
+    // flushes, when some lane could not take another full chunk. Inserting on arrival made every
+    // lane's insert a separate divergent excursion (~190 cycles each, 32 lanes x K ln(N/K) of
+    // them per warp: 1.35 of the 2.5 ms on 16k x 100k); in a flush all 32 lanes walk their lists
+    // together. A stale threshold only admits extra candidates, which the flush rejects with one
+    // compare against the fresh one. thr = -inf until the heap holds K entries.
+    int cnt = 0, pend = 0;
     float thr = -CUDART_INF_F;
     float *hv = h_val + tid;
     int32_t *hi_ = h_idx + tid;
-    float *cv = c_val + tid;
-    uint8_t *cc = c_col + tid;
+    float *pv = p_val + tid;
+    int32_t *pi = p_idx + tid;
+
+    auto flush = [&]() {
+      // (letting every lane skip ahead to its next live entry before each heap update was slower:
+      // 304 vs 275 us at Baby size -- the per-iteration latency chain, not lane utilisation, binds)
+      for (int i = 0; i < pend; ++i) {
+        float sc = pv[i * kTileM];
+        if (!(sc > thr)) continue;
+        const int gid = pi[i * kTileM];
+        while (next_masked < gid) {                               // ascending ids: a cursor is enough
+          ++mp;
+          next_masked = mp < mend ? mask_cols[mp] : INT_MAX;
+        }
+        if (gid == next_masked) sc = -1e10f;                      // trainer.py:524
+        if (cnt < k) {
+          heap_sift_up(hv, hi_, cnt++, sc, gid);
+          if (cnt == k) thr = hv[0];
+        } else if (sc > thr) {
+          heap_sift_down(hv, hi_, 0, k, sc, gid);                 // replace the worst kept entry
+          thr = hv[0];
+        }
+      }
+      pend = 0;
+      __syncwarp();
+    };
 
     for (int t = 0; t < n_tiles; ++t) {
       const int b = t % kAcc;
@@ -261,44 +334,38 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
           fence_before_sync();
           mbar_arrive(tempty + b);       // all columns of this buffer are in registers
         }
+        if (__any_sync(0xffffffffu, pend > pend_cap - kChunk)) flush();
         const int j0 = j_begin + t * kTileN + half * kChunk;
         const int valid = min(kChunk, j_end - j0);
-        // cheap reject: nothing in this chunk beats the current K-th best
+        if (valid < kChunk) {            // ragged last tile (warp-uniform)
+#pragma unroll
+          for (int c = 0; c < kChunk; ++c)
+            if (c >= valid) r[c] = __float_as_uint(-CUDART_INF_F);
+        }
+        // cheap reject: nothing in this chunk beats any lane's K-th best
         float m = -CUDART_INF_F;
 #pragma unroll
-        for (int c = 0; c < kChunk; ++c) m = fmaxf(m, c < valid ? __uint_as_float(r[c]) : -CUDART_INF_F);
+        for (int c = 0; c < kChunk; ++c) m = fmaxf(m, __uint_as_float(r[c]));
         if (dbg == 1) m = -CUDART_INF_F;
-        if (live && valid > 0 && (cnt < k || m > thr) && dbg != 2) {
-          int n = 0;
+        if (__any_sync(0xffffffffu, live && m > thr) && dbg != 2) {
+          const float lim = live ? thr : CUDART_INF_F;            // dead rows take nothing
+          const int g0 = item_offset + j0;
+          int off = pend * kTileM;
 #pragma unroll
           for (int c = 0; c < kChunk; ++c) {
             const float sc = __uint_as_float(r[c]);
-            if (c < valid && (cnt < k || sc > thr)) {
-              cv[n * kTileM] = sc;
-              cc[n * kTileM] = (uint8_t)c;
-              ++n;
+            if (sc > lim) {
+              pv[off] = sc;
+              pi[off] = g0 + c;
+              off += kTileM;
             }
           }
-          for (int i = 0; i < n; ++i) {
-            float sc = cv[i * kTileM];
-            const int gid = item_offset + j0 + cc[i * kTileM];
-            while (next_masked < gid) {
-              ++mp;
-              next_masked = mp < mend ? mask_cols[mp] : INT_MAX;
-            }
-            if (gid == next_masked) sc = -1e10f;                  // trainer.py:524
-            if (cnt < k) {
-              heap_sift_up(hv, hi_, cnt++, sc, gid);
-              if (cnt == k) thr = hv[0];
-            } else if (sc > thr) {
-              heap_sift_down(hv, hi_, 0, k, sc, gid);             // replace the worst kept entry
-              thr = hv[0];
-            }
-          }
+          pend = off / kTileM;
         }
-        __syncwarp();       // tcgen05.ld / mbarrier waits below are warp-collective
+        __syncwarp();       // tcgen05.ld / mbarrier waits are warp-collective
       }
     }
+    flush();
     // heap -> descending list (in-place heap sort: the worst entry moves to the end each round)
     if (live) {
       for (int size = cnt; size > 1; --size) {
@@ -320,7 +387,7 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
   __syncthreads();
   if (warp == 8) {
     fence_after_sync();
-    tmem_dealloc(tmem_base, kAcc * kTileN);
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -329,20 +396,28 @@ inline int dbg_mode() {
   return m;
 }
 
-template <int D>
+inline bool a_tmem_64() {   // A/B switch for d <= 64 (d = 128 always keeps its user tile in TMEM)
+  static int m = getenv("MMREC_TOPK_ATMEM") ? atoi(getenv("MMREC_TOPK_ATMEM")) : 0;
+  return m != 0;
+}
+
+template <int D, bool A_TMEM>
 int launch_tc(const float *user_emb, const int64_t *users, int n_users, const float *item_emb, int n_items,
               int item_offset, const int32_t *mask_rowptr, const int32_t *mask_cols, int k, int n_splits,
               float *ws_val, int32_t *ws_idx, cudaStream_t stream) {
-  using C = Cfg<D>;
-  const size_t smem = 1024 + C::OFF_HEAP + (size_t)k * kTileM * 8 + kChunk * kTileM * 5 +
-                      (2 * C::STAGES + 2 * kAcc) * 8 + 16;
-  if (smem > 227 * 1024) return 1;          // K too large for this tiling: SIMT path
-  MMREC_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  using C = Cfg<D, A_TMEM>;
+  const size_t fixed = 1024 + C::OFF_HEAP + (size_t)k * kTileM * 8 + (2 * C::STAGES + 2 * kAcc) * 8 + 16;
+  const size_t cap = 227 * 1024;
+  if (fixed + (size_t)(kChunk + 8) * kTileM * 8 > cap) return 1;     // K too large for this tiling: SIMT path
+  const int pend_cap = (int)min((size_t)64, (cap - fixed) / (kTileM * 8));
+  const size_t smem = fixed + (size_t)pend_cap * kTileM * 8;
+  MMREC_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<D, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items_per_split = ((n_items + n_splits - 1) / n_splits + kTileN - 1) / kTileN * kTileN;
   dim3 grid((n_users + kTileM - 1) / kTileM, n_splits);
-  score_topk_tc_kernel<D><<<grid, kThreadsTC, smem, stream>>>(user_emb, users, n_users, item_emb, n_items,
+  score_topk_tc_kernel<D, A_TMEM><<<grid, kThreadsTC, smem, stream>>>(user_emb, users, n_users, item_emb, n_items,
                                                               item_offset, mask_rowptr, mask_cols, k,
-                                                              items_per_split, ws_val, ws_idx, dbg_mode());
+                                                              items_per_split, ws_val, ws_idx, pend_cap,
+                                                              dbg_mode());
   MMREC_CHECK_LAUNCH("score_topk_tc_kernel");
   return MMREC_OK;
 }
@@ -354,13 +429,15 @@ int score_topk_tc_dispatch(const float *user_emb, const int64_t *users, int n_us
                            int n_items, int item_offset, int d, const int32_t *mask_rowptr,
                            const int32_t *mask_cols, int k, int n_splits, float *ws_val, int32_t *ws_idx,
                            cudaStream_t stream) {
+#define MMREC_TC(D_, T_) launch_tc<D_, T_>(user_emb, users, n_users, item_emb, n_items, item_offset, mask_rowptr, \
+                                            mask_cols, k, n_splits, ws_val, ws_idx, stream)
   switch (d) {
-    case 32: return launch_tc<32>(user_emb, users, n_users, item_emb, n_items, item_offset, mask_rowptr, mask_cols,
-                                  k, n_splits, ws_val, ws_idx, stream);
-    case 64: return launch_tc<64>(user_emb, users, n_users, item_emb, n_items, item_offset, mask_rowptr, mask_cols,
-                                  k, n_splits, ws_val, ws_idx, stream);
+    case 32: return MMREC_TC(32, false);
+    case 64: return a_tmem_64() ? MMREC_TC(64, true) : MMREC_TC(64, false);
+    case 128: return MMREC_TC(128, true);
     default: return 1;
   }
+#undef MMREC_TC
 }
 
 }  // namespace mmrec

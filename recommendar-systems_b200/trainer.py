@@ -411,11 +411,17 @@ class Trainer:
         k = max(self.config["topk"])
         users = eval_data.eval_u
         n, step = users.shape[0], eval_data.step
+        # The reference scores `eval_batch_size` users at a time because it materialises the
+        # [Bu, n_items] score matrix; the fused kernel keeps scores on chip, so several reference
+        # batches go out as one launch (a fuller wave, the top-K fill phase paid once per user) and
+        # the result is cut back into the reference's batch list.
+        fuse = step * max(1, int(self.config.get("eval_fuse_users", 32768)) // step)
         out = []
-        for start in range(0, n, step):
-            stop = min(n, start + step)
+        for start in range(0, n, fuse):
+            stop = min(n, start + fuse)
             rowptr, cols = eval_data.mask_csr(start, stop)
-            out.append(self.model.full_sort_topk(users[start:stop], k, rowptr, cols))
+            ids = self.model.full_sort_topk(users[start:stop], k, rowptr, cols)
+            out.extend(ids.split(step, dim=0))
         return out
 
     @torch.no_grad()

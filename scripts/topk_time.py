@@ -12,8 +12,8 @@ def timeit(fn, iters=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / iters
 gen = torch.Generator().manual_seed(1)
-for (nu, ni, S) in [(9130, 7050, 2), (16384, 100000, 1)]:
-    ue = torch.randn(nu, 64, generator=gen).to(DEV); ie = torch.randn(ni, 64, generator=gen).to(DEV)
+for (nu, ni, S, d) in [(9130, 7050, 2, 64), (16384, 100000, 1, 64), (17122, 23033, 1, 128), (16384, 100000, 1, 128)]:
+    ue = torch.randn(nu, d, generator=gen).to(DEV); ie = torch.randn(ni, d, generator=gen).to(DEV)
     users = torch.arange(nu, device=DEV)
     t = timeit(lambda: ops.score_mask_topk(ue, users, ie, 50, n_splits=S))
-    print(f"dbg={os.environ.get('MMREC_TOPK_DEBUG')} U={nu} I={ni} S={S}: {t*1e3:.1f} us", flush=True)
+    print(f"dbg={os.environ.get('MMREC_TOPK_DEBUG')} atmem={os.environ.get('MMREC_TOPK_ATMEM')} d={d} U={nu} I={ni} S={S}: {t*1e3:.1f} us", flush=True)

@@ -368,7 +368,8 @@ def test_smore_side_network_fused_forward_backward(n, d, drop):
 
 
 @pytest.mark.parametrize("n_users,n_items,d,k,splits", [(64, 96, 64, 50, 1), (300, 1000, 64, 50, 4),
-                                                       (129, 777, 128, 20, 3), (1000, 5000, 32, 50, None)])
+                                                       (129, 777, 128, 20, 3), (1000, 5000, 32, 50, None),
+                                                       (700, 3000, 128, 50, None)])
 def test_score_mask_topk_matches_stable_sort(n_users, n_items, d, k, splits):
     ops = pkg("ops")
     gen = torch.Generator().manual_seed(19)
