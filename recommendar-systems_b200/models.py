@@ -397,6 +397,10 @@ class _MultiViewBase(GeneralRecommender):
         streams = self.__dict__.setdefault("_aux_streams", {})
         if idx not in streams:
             streams[idx] = torch.cuda.Stream(device=self.device)
+            # parameters used on a side stream get their AccumulateGrad on it: intended here
+            hush = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if hush is not None:
+                hush(False)
         s = streams[idx]
         s.wait_stream(torch.cuda.current_stream())
         return s

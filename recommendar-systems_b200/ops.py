@@ -555,7 +555,9 @@ def smore_side_supported(d):
     (tested), but there the fp32-FMA kernel holds one 255-register CTA per SM and is slower than
     the unfused path (Clothing, d = 128: 20.6 vs 18.5 ms/step): that width waits for the
     tensor-core version."""
-    return int(d) in (32, 64) and bool(lib.load().mmrec_smore_side_supported(int(d)))
+    import os
+    widths = (32, 64, 128) if os.environ.get("MMREC_SIDE128", "0") == "1" else (32, 64)
+    return int(d) in widths and bool(lib.load().mmrec_smore_side_supported(int(d)))
 
 
 def smore_side(fusion, image, text, content, layers, masks=None):

@@ -629,3 +629,70 @@ def test_sharded_paths_nccl(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(2))
+
+
+# ------------------------------------------------------------------ accelerate(): torch.sparse.mm interception
+def _ref_style_adj(n_users, n_items, n_edges, seed):
+    """An adjacency built the way the reference builds it (layergcn.py:110-117): int64 COO through
+    the legacy constructor, symmetric, never coalesced."""
+    gen = torch.Generator().manual_seed(seed)
+    u = torch.randint(0, n_users, (n_edges,), generator=gen)
+    i = torch.randint(0, n_items, (n_edges,), generator=gen) + n_users
+    idx = torch.stack([torch.cat([u, i]), torch.cat([i, u])])
+    val = torch.rand(2 * n_edges, generator=gen)
+    n = n_users + n_items
+    return torch.sparse_coo_tensor(idx, val, (n, n)).to(DEV)      # duplicates kept, uncoalesced
+
+
+@pytest.mark.gpu
+def test_accelerate_reroutes_sparse_mm_forward_and_backward():
+    acc, L = pkg("accelerate"), pkg("lib")
+    adj = _ref_style_adj(300, 120, 2500, seed=3)
+    assert not adj.is_coalesced()
+    x0 = torch.randn(420, 64, generator=torch.Generator().manual_seed(4)).to(DEV)
+
+    def lightgcn_forward(x):                 # lightgcn.py:118-128, verbatim torch call sites
+        embs = [x]
+        for _ in range(3):
+            x = torch.sparse.mm(adj, x)
+            embs.append(x)
+        return torch.stack(embs, dim=1).mean(dim=1)
+
+    xr = x0.clone().requires_grad_(True)
+    want = lightgcn_forward(xr)
+    (want * want).sum().backward()
+    xa = x0.clone().requires_grad_(True)
+    before = L.load().mmrec_launch_count()
+    with acc.accelerate() as mode:
+        got = lightgcn_forward(xa)
+        (got * got).sum().backward()
+    assert L.load().mmrec_launch_count() - before >= 6          # 3 forward + 3 transposed backward SpMMs
+    assert mode.stats == {"spmm": 3, "converted": 1, "passed": 0}
+    assert rel(got, want) < 1e-5 and rel(xa.grad, xr.grad) < 1e-5
+
+
+@pytest.mark.gpu
+def test_accelerate_cache_follows_tensor_identity_and_version():
+    acc = pkg("accelerate")
+    adj = _ref_style_adj(50, 40, 300, seed=5)
+    x = torch.randn(90, 32, device=DEV)
+    with acc.accelerate() as mode:
+        y1 = torch.sparse.mm(adj, x)
+        torch.sparse.mm(adj, x)
+        assert mode.stats["converted"] == 1
+        adj._values().mul_(2.0)                                   # in place: same storage, new version
+        y2 = torch.sparse.mm(adj, x)
+        assert mode.stats["converted"] == 2
+        assert rel(y2, 2 * y1) < 1e-6
+        other = _ref_style_adj(50, 40, 300, seed=6)               # per-epoch rebuild (layergcn.py:70)
+        y3 = torch.sparse.mm(other, x)
+        assert mode.stats["converted"] == 3
+        # not covered by the kernel -> untouched torch path: odd width, sparse @ sparse stays torch's
+        y4 = torch.sparse.mm(adj, x[:, :7].contiguous())
+        assert mode.stats["passed"] == 1 and y4.shape == (90, 7)
+    assert rel(y3, torch.sparse.mm(other, x)) < 1e-5
+    csr = adj.coalesce().to_sparse_csr()
+    with acc.accelerate() as mode:
+        y5 = torch.mm(csr, x)
+        assert mode.stats["spmm"] == 1
+    assert rel(y5, y2) < 1e-5

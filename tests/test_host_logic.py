@@ -185,3 +185,15 @@ def test_ops_fail_loudly_without_cuda():
     ops, graph = pkg("ops"), pkg("graph")
     with pytest.raises(RuntimeError):
         graph.build_ui_graph(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 2, 2, "f32")
+
+
+def test_accelerate_passes_cpu_calls_through_untouched():
+    """The interception mode only takes CUDA float32 calls; on the host it must be transparent."""
+    acc = pkg("accelerate")
+    idx = torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]])
+    a = torch.sparse_coo_tensor(idx, torch.tensor([1.0, 2.0, 3.0, 4.0]), (3, 3))
+    x = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    want = torch.sparse.mm(a, x)
+    with acc.accelerate() as mode:
+        got = torch.sparse.mm(a, x)
+    assert torch.equal(got, want) and mode.stats == {"spmm": 0, "converted": 0, "passed": 1}
