@@ -84,6 +84,32 @@ class GeneralRecommender(AbstractRecommender):
         if len(np.unique(key)) != len(key):
             raise ValueError("duplicate (user, item) training interactions are not supported")
         self._eval_cache = None
+        # item-range sharding of the trainable feature tables over a process group
+        # (parallel.ShardedRows): config['table_shard'] = (rank, world[, group])
+        self._table_rows, self._table_group = None, None
+        ts = config.get("table_shard") if hasattr(config, "get") else None
+        if ts is not None:
+            from . import parallel
+            self._table_rows = parallel.ShardedRows(self.n_items, int(ts[0]), int(ts[1]))
+            self._table_group = ts[2] if len(ts) > 2 else None
+
+    def _feature_table(self, feat):
+        """`nn.Embedding.from_pretrained(feat, freeze=False)` (smore.py:76-77, mgcn.py:62-72,
+        freedom.py:48-55); with table sharding only this rank's item rows become a parameter."""
+        if self._table_rows is None:
+            return nn.Embedding.from_pretrained(feat, freeze=False)
+        emb = nn.Embedding.from_pretrained(self._table_rows.local(feat).clone(), freeze=False)
+        emb.weight._mmrec_sharded = True
+        emb.weight._mmrec_global_numel = int(feat.shape[0]) * int(feat.shape[1])
+        return emb
+
+    def _project(self, emb, trs):
+        """`trs(emb.weight)`; sharded tables: local rows projected, slices all-gathered."""
+        if self._table_rows is None:
+            return trs(emb.weight)
+        from . import parallel
+        return parallel.sharded_projection(emb.weight, trs.weight, trs.bias, self._table_rows,
+                                           self._table_group)
 
     def train(self, mode=True):
         self._eval_cache = None
@@ -308,10 +334,10 @@ class FREEDOM(GeneralRecommender):
         nn.init.xavier_uniform_(self.user_embedding.weight)
         nn.init.xavier_uniform_(self.item_id_embedding.weight)
         if self.v_feat is not None:
-            self.image_embedding = nn.Embedding.from_pretrained(self.v_feat, freeze=False)
+            self.image_embedding = self._feature_table(self.v_feat)
             self.image_trs = ops.Linear(self.v_feat.shape[1], self.feat_embed_dim)
         if self.t_feat is not None:
-            self.text_embedding = nn.Embedding.from_pretrained(self.t_feat, freeze=False)
+            self.text_embedding = self._feature_table(self.t_feat)
             self.text_trs = ops.Linear(self.t_feat.shape[1], self.feat_embed_dim)
         coo = _coo_override(config, "mm_adj", self.device)
         if coo is None:
@@ -356,10 +382,10 @@ class FREEDOM(GeneralRecommender):
         loss = ops.bpr(ua, ia, users, pos, neg)[0] / B
         mf_v = mf_t = 0.0
         if self.t_feat is not None:
-            text_feats = self.text_trs(self.text_embedding.weight)
+            text_feats = self._project(self.text_embedding, self.text_trs)
             mf_t = ops.bpr(ua, text_feats, users, pos, neg)[0] / B
         if self.v_feat is not None:
-            image_feats = self.image_trs(self.image_embedding.weight)
+            image_feats = self._project(self.image_embedding, self.image_trs)
             mf_v = ops.bpr(ua, image_feats, users, pos, neg)[0] / B
         return loss + self.reg_weight * (mf_t + mf_v)
 
@@ -450,9 +476,9 @@ class MGCN(_MultiViewBase):
         nn.init.xavier_uniform_(self.user_embedding.weight)
         nn.init.xavier_uniform_(self.item_id_embedding.weight)
         self._init_ui()
-        self.image_embedding = nn.Embedding.from_pretrained(self.v_feat, freeze=False)
+        self.image_embedding = self._feature_table(self.v_feat)
         _, self.image_original_adj = self._item_graph(config, "image_adj", self.v_feat, self.knn_k)
-        self.text_embedding = nn.Embedding.from_pretrained(self.t_feat, freeze=False)
+        self.text_embedding = self._feature_table(self.t_feat)
         _, self.text_original_adj = self._item_graph(config, "text_adj", self.t_feat, self.knn_k)
         self.image_trs = ops.Linear(self.v_feat.shape[1], d)
         self.text_trs = ops.Linear(self.t_feat.shape[1], d)
@@ -471,8 +497,8 @@ class MGCN(_MultiViewBase):
         return (u, i, side, content) if train else (u, i)
 
     def _forward_full(self, adj):
-        image_feats = self.image_trs(self.image_embedding.weight)
-        text_feats = self.text_trs(self.text_embedding.weight)
+        image_feats = self._project(self.image_embedding, self.image_trs)
+        text_feats = self._project(self.text_embedding, self.text_trs)
         item = self.item_id_embedding.weight
         image_item = item * self.gate_v(image_feats)
         text_item = item * self.gate_t(text_feats)
@@ -519,10 +545,10 @@ class SMORE(_MultiViewBase):
         nn.init.xavier_uniform_(self.user_embedding.weight)
         nn.init.xavier_uniform_(self.item_id_embedding.weight)
         self._init_ui()
-        self.image_embedding = nn.Embedding.from_pretrained(self.v_feat, freeze=False)
+        self.image_embedding = self._feature_table(self.v_feat)
         img_coo, self.image_original_adj = self._item_graph(config, "image_adj", self.v_feat,
                                                             self.image_knn_k)
-        self.text_embedding = nn.Embedding.from_pretrained(self.t_feat, freeze=False)
+        self.text_embedding = self._feature_table(self.t_feat)
         txt_coo, self.text_original_adj = self._item_graph(config, "text_adj", self.t_feat,
                                                            self.text_knn_k)
         fus = _coo_override(config, "fusion_adj", self.device)
@@ -576,8 +602,8 @@ class SMORE(_MultiViewBase):
             ego = torch.cat([self.user_embedding.weight, item], dim=0)
             content = ops.propagate_mean(adj, ego, self.n_ui_layers)
         with torch.cuda.stream(s_txt) if s_txt is not None else contextlib.nullcontext():
-            text_feats = self.text_trs(self.text_embedding.weight)
-        image_feats = self.image_trs(self.image_embedding.weight)
+            text_feats = self._project(self.text_embedding, self.text_trs)
+        image_feats = self._project(self.image_embedding, self.image_trs)
         self._join(s_txt, text_feats)
         image_conv, text_conv, fusion_conv = self.spectrum_convolution(image_feats, text_feats)
         if self.inject_mode == "mul":

@@ -258,3 +258,103 @@ def bipartite_score_topk(sb: ShardedBipartite, out_u_local, out_i, users, k, gro
     rows = torch.arange(users.numel(), device=users.device)
     return sharded_score_topk(ub, rows, out_i[lo:hi].contiguous(), lo, k, group=group, local_topk=local_topk,
                               merge=merge)
+
+
+# ------------------------------------------------------------------ item-range sharded modality tables
+# the trainable [I, 4096] / [I, 384] feature tables (smore.py:76-77, mgcn.py:62-72,
+# freedom.py:48-55), their projection (smore.py:256-257), its gradients and the Adam state are the
+# largest HBM consumers of a SMORE / MGCN / FREEDOM step and are independent per item row. Rank p
+# keeps rows [lo_p, hi_p) of every table (parameter + exp_avg + exp_avg_sq: 12 of the 16 bytes per
+# element stay local for good); per projection
+#   forward : Y_p = X_p W^T + b on the local rows, all-gather of the [I/P, d] slices -> Y [I, d];
+#   backward: dY is replicated (everything downstream of the projection is replicated), so
+#             dX_p = dY[lo:hi] W stays local, dW = all-reduce(dY[lo:hi]^T X_p), db likewise.
+# Slices are padded to the longest range so that all_gather_into_tensor needs no packing.
+def _linear_cuda(x, W, b):
+    return ops.linear(x, W, b)
+
+
+class ShardedRows:
+    """Contiguous, near-equal row ranges of an [n, *] table over the ranks of a process group."""
+
+    def __init__(self, n_rows: int, rank: int, world: int):
+        self.n, self.rank, self.world = int(n_rows), int(rank), int(world)
+        self.per = -(-self.n // self.world)
+        self.lo = min(self.n, self.rank * self.per)
+        self.hi = min(self.n, self.lo + self.per)
+
+    def local(self, table: torch.Tensor) -> torch.Tensor:
+        return table[self.lo: self.hi]
+
+
+class _ShardedProjection(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, W, b, rows, group, linear_fn):
+        y_local = linear_fn(x_local.detach(), W.detach(), None if b is None else b.detach())
+        d = y_local.shape[1]
+        buf = torch.empty(rows.world * rows.per, d, dtype=y_local.dtype, device=y_local.device)
+        if y_local.shape[0] == rows.per:
+            mine = y_local.contiguous()
+        else:                                   # the last range is shorter: pad its slice
+            mine = torch.zeros(rows.per, d, dtype=y_local.dtype, device=y_local.device)
+            mine[: y_local.shape[0]] = y_local
+        dist.all_gather_into_tensor(buf, mine, group=group)
+        ctx.save_for_backward(x_local, W)
+        ctx.rows, ctx.group, ctx.has_bias = rows, group, b is not None
+        return buf[: rows.n]
+
+    @staticmethod
+    def backward(ctx, dY):
+        x_local, W = ctx.saved_tensors
+        rows = ctx.rows
+        dy = dY[rows.lo: rows.hi].contiguous()
+        dx = dy @ W if ctx.needs_input_grad[0] else None
+        # dW and db travel in one buffer: one all-reduce per projection
+        n_out, n_in = W.shape
+        pack = torch.empty(n_out, n_in + 1, dtype=W.dtype, device=W.device)
+        pack[:, :n_in] = dy.t() @ x_local
+        pack[:, n_in] = dy.sum(0)
+        dist.all_reduce(pack, group=ctx.group)
+        dW = pack[:, :n_in].contiguous()
+        db = pack[:, n_in].contiguous() if ctx.has_bias else None
+        return dx, dW, db, None, None, None
+
+
+class _ShardedProjectionCuda(_ShardedProjection):
+    """Same exchange, local products on the 3xTF32 GEMMs of the library."""
+
+    @staticmethod
+    def backward(ctx, dY):
+        x_local, W = ctx.saved_tensors
+        rows = ctx.rows
+        dy = dY[rows.lo: rows.hi].contiguous()
+        M, K = x_local.shape
+        N = W.shape[0]
+        dx = ops.gemm(dy, True, W, False, M, K, N) if ctx.needs_input_grad[0] else None
+        pack = torch.empty(N, K + 1, dtype=W.dtype, device=W.device)
+        pack[:, :K] = ops.gemm(dy, False, x_local, False, N, K, M)
+        pack[:, K] = dy.sum(0)
+        dist.all_reduce(pack, group=ctx.group)
+        return dx, pack[:, :K].contiguous(), (pack[:, K].contiguous() if ctx.has_bias else None), None, None, None
+
+
+def sharded_projection(x_local, W, b, rows: ShardedRows, group=None, linear_fn=None):
+    """`Linear(table)` with the table's rows sharded over the group: every rank passes its
+    [I/P, F] slice and gets the full [I, d] projection; gradients as described above."""
+    if linear_fn is None:
+        return _ShardedProjectionCuda.apply(x_local, W, b, rows, group, _linear_cuda)
+    return _ShardedProjection.apply(x_local, W, b, rows, group, linear_fn)
+
+
+def sharded_sumsq(replicated, sharded, group=None):
+    """Sum of squares over a parameter (or gradient) list of which `sharded` tensors hold only this
+    rank's rows: local sums of the sharded part are all-reduced, the replicated part counts once.
+    Used by the mirror-gradient step for its global grad / param RMS (trainer.py:289-305)."""
+    dev = (replicated or sharded)[0].device
+    s = torch.zeros((), dtype=torch.float32, device=dev)
+    if sharded:
+        s = torch.stack(torch._foreach_norm(list(sharded))).pow(2).sum()
+        dist.all_reduce(s, group=group)
+    if replicated:
+        s = s + torch.stack(torch._foreach_norm(list(replicated))).pow(2).sum()
+    return s

@@ -222,9 +222,20 @@ class Trainer:
                 lr = opt.lr_tensor().to(torch.float32)
             else:
                 lr = torch.tensor([opt.param_groups[0].get("lr", 1.0)], dtype=torch.float32, device=dev)
-            numel = float(sum(g.numel() for g in grads))
-            g2 = torch.stack(torch._foreach_norm(grads)).pow(2).sum()
-            p2 = torch.stack(torch._foreach_norm([p.detach() for p in params])).pow(2).sum()
+            sharded = [getattr(p, "_mmrec_sharded", False) for p in params]
+            if any(sharded):
+                # item-range sharded feature tables: their rows' squares are summed over the group
+                from . import parallel
+                grp = getattr(model, "_table_group", None)
+                numel = float(sum(getattr(p, "_mmrec_global_numel", p.numel()) for p in params))
+                g2 = parallel.sharded_sumsq([g for g, s in zip(grads, sharded) if not s],
+                                            [g for g, s in zip(grads, sharded) if s], grp)
+                p2 = parallel.sharded_sumsq([p.detach() for p, s in zip(params, sharded) if not s],
+                                            [p.detach() for p, s in zip(params, sharded) if s], grp)
+            else:
+                numel = float(sum(g.numel() for g in grads))
+                g2 = torch.stack(torch._foreach_norm(grads)).pow(2).sum()
+                p2 = torch.stack(torch._foreach_norm([p.detach() for p in params])).pow(2).sum()
             grad_rms = (g2 / numel).sqrt()
             param_rms = (p2 / numel).sqrt() + 1e-12
             alpha_eff = torch.clamp(self.mg_target_rel_step * param_rms / (lr * grad_rms + 1e-12),

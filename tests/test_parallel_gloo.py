@@ -125,6 +125,25 @@ def _worker(rank, world, port, out_dir):
         w = want.detach()
         want2 = torch.sort(w[some_users] @ w[U:].T, dim=-1, descending=True, stable=True)[1][:, :10]
         assert torch.equal(got2, want2)
+        # item-range sharded feature table: projection forward / backward and the sharded norms
+        gen = torch.Generator().manual_seed(11)
+        table = torch.randn(I, 24, generator=gen).double()
+        Wt, bt = torch.randn(8, 24, generator=gen).double(), torch.randn(8, generator=gen).double()
+        Gm = torch.randn(I, 8, generator=gen).double()
+        rows = par.ShardedRows(I, rank, world)
+        assert rows.lo == min(I, rank * rows.per) and rows.world * rows.per >= I
+        xl = rows.local(table).clone().requires_grad_(True)
+        Wp, bp = Wt.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+        y = par.sharded_projection(xl, Wp, bp, rows, linear_fn=torch.nn.functional.linear)
+        tref, Wr, br = (t.clone().requires_grad_(True) for t in (table, Wt, bt))
+        yr = torch.nn.functional.linear(tref, Wr, br)
+        assert y.shape == yr.shape and torch.allclose(y, yr, atol=1e-12)
+        (y * Gm).sum().backward()
+        (yr * Gm).sum().backward()
+        assert torch.allclose(xl.grad, tref.grad[rows.lo: rows.hi], atol=1e-12)
+        assert torch.allclose(Wp.grad, Wr.grad, atol=1e-10) and torch.allclose(bp.grad, br.grad, atol=1e-10)
+        ss = par.sharded_sumsq([Wt, bt], [rows.local(table)])
+        assert torch.allclose(ss, Wt.pow(2).sum() + bt.pow(2).sum() + table.pow(2).sum(), rtol=1e-12)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
