@@ -618,6 +618,7 @@ def topk_merge(vals, idx):
 
 # ------------------------------------------------------------------------------ top-K metrics
 _METRIC_ROWS = {"recall": 0, "recall2": 1, "precision": 2, "ndcg": 3, "map": 4}
+_METRIC_TABLES = {}
 
 
 @torch.no_grad()
@@ -630,9 +631,10 @@ def topk_metric_sums(topk, gt_rowptr, gt_items, return_hits=False):
     topk = topk.contiguous()
     n, k = topk.shape
     dev = topk.device
-    disc_np = 1.0 / np.log2(np.arange(1, k + 1, dtype=np.float64) + 1)     # metrics.py:35-64
-    disc = torch.from_numpy(disc_np).to(dev)
-    idcg = torch.from_numpy(np.cumsum(disc_np)).to(dev)
+    if (k, dev) not in _METRIC_TABLES:         # constants: built once, outside any graph capture
+        disc_np = 1.0 / np.log2(np.arange(1, k + 1, dtype=np.float64) + 1)     # metrics.py:35-64
+        _METRIC_TABLES[(k, dev)] = (torch.from_numpy(disc_np).to(dev), torch.from_numpy(np.cumsum(disc_np)).to(dev))
+    disc, idcg = _METRIC_TABLES[(k, dev)]
     sums = torch.empty(5, k, dtype=torch.float64, device=dev)
     hits = torch.empty(n, k, dtype=torch.uint8, device=dev) if return_hits else None
     ws = torch.empty(lib.load().mmrec_topk_metrics_workspace_bytes(n), dtype=torch.uint8, device=dev)

@@ -117,9 +117,22 @@ class TopKEvaluator:
         """Hit matrix + every metric @1..K on the GPU (mmrec_topk_metrics_f64); only the [5, K]
         float64 sums come back to the host."""
         rowptr, items = eval_data.gt_csr()
-        sums = ops.topk_metric_sums(topk, rowptr, items).cpu().numpy()
-        n = topk.shape[0]
-        total_pos = float(np.asarray(eval_data.get_eval_len_list(), dtype=np.int64).sum())
+        return self._metrics_from_sums(ops.topk_metric_sums(topk, rowptr, items), topk.shape[0], eval_data)
+
+    def result_from_sums(self, sums, n, eval_data):
+        """The reference's result dict from the device sums of a (graph-replayed) evaluation."""
+        result = self._metrics_from_sums(sums, n, eval_data)
+        out = {}
+        for metric, value in zip(self.metrics, result):
+            for k in self.topk:
+                out["{}@{}".format(metric, k)] = round(value[k - 1], 4)
+        return out
+
+    def _metrics_from_sums(self, sums, n, eval_data):
+        sums = sums.cpu().numpy()
+        if getattr(eval_data, "_total_pos", None) is None:
+            eval_data._total_pos = float(np.asarray(eval_data.get_eval_len_list(), dtype=np.int64).sum())
+        total_pos = eval_data._total_pos
         rows = {"recall": sums[0] / n, "recall2": sums[1] / total_pos, "precision": sums[2] / n,
                 "ndcg": sums[3] / n, "map": sums[4] / n}
         return np.stack([rows[m] for m in self.metrics], axis=0)
@@ -180,10 +193,12 @@ class Trainer:
         self.mg_alpha_max_scale = float(config.get("mg_alpha_max_scale", 20.0))
         self.sync_free = bool(config.get("sync_free", True))
         # steady-state steps are replayed from a CUDA graph (needs the device-side Adam counters)
-        self.use_cuda_graph = bool(config.get("cuda_graph", True)) and self.sync_free and \
+        self.use_cuda_graph = bool(config.get("cuda_graph", True)) and \
             hasattr(self.optimizer, "lr_tensor") and not self.clip_grad_norm and not self.mg
         self.graph_warmup = int(config.get("graph_warmup", 2))
+        self.use_eval_graph = bool(config.get("cuda_graph", True)) and bool(config.get("eval_cuda_graph", True))
         self._graphs = {}
+        self._eval_graphs = {}
         self.replayed_launches = 0
 
     def _build_optimizer(self):
@@ -341,8 +356,12 @@ class Trainer:
             self.model.global_step += ent["step_delta"]
         return ent["static_out"].clone()
 
-    def _train_epoch(self, train_data, epoch_idx, loss_func=None):
-        """trainer.py:145-356."""
+    def _train_epoch(self, train_data, epoch_idx, loss_func=None, max_batches=None):
+        """trainer.py:145-356. The batch loop is software-pipelined: the step is enqueued (a CUDA
+        graph replay returns at once), THEN the loader draws the next batch -- host-side negative
+        sampling overlaps the device step -- and only then the loss is read back. Batches, RNG
+        call order and the per-step loss / NaN semantics are the reference's. `max_batches` stops
+        early (bench.py times K steps through this entry point)."""
         if not self.req_training:
             return 0.0, []
         self.model.train()
@@ -350,18 +369,35 @@ class Trainer:
         total_loss = None
         loss_batches = []
         graphed = self.use_cuda_graph and loss_func == self.model.calculate_loss
-        for batch_idx, interaction in enumerate(train_data):
+        it = iter(train_data)
+        interaction = next(it, None)
+        batch_idx = 0
+        unread = []                      # (loss, batch index) enqueued but not yet read back
+        while interaction is not None:
             loss = self._train_batch_graphed(interaction, batch_idx) if graphed \
                 else self._train_batch(interaction, batch_idx, loss_func)
+            batch_idx += 1
+            if max_batches is not None and batch_idx >= max_batches:
+                interaction = None
+                if hasattr(train_data, "pr"):
+                    train_data.pr = 0                  # abandoned epoch: the next one starts clean
+            else:
+                interaction = next(it, None)
+            loss_batches.append(loss)
             if self.sync_free:
                 total_loss = loss.clone() if total_loss is None else total_loss + loss
-            else:
-                total_loss = loss.item() if total_loss is None else total_loss + loss.item()
-                if torch.isnan(loss):
-                    self.logger.info("Loss is nan at epoch: {}, batch index: {}. Exiting.".format(
-                        epoch_idx, batch_idx))
-                    return loss, torch.tensor(0.0)
-            loss_batches.append(loss)
+                continue
+            # per-batch read-back (trainer.py:196-203), one step behind: the loss of batch i is
+            # read after batch i + 1 has been enqueued, so the device never waits for the host.
+            # A NaN therefore aborts one batch later than in the reference.
+            unread.append((loss, batch_idx - 1))
+            while len(unread) > (1 if interaction is not None else 0):
+                lt, bi = unread.pop(0)
+                v = lt.item()
+                total_loss = v if total_loss is None else total_loss + v
+                if v != v:
+                    self.logger.info("Loss is nan at epoch: {}, batch index: {}. Exiting.".format(epoch_idx, bi))
+                    return lt, torch.tensor(0.0)
         if self.sync_free and total_loss is not None:
             if torch.isnan(total_loss):
                 self.logger.info("Loss is nan at epoch: {}. Exiting.".format(epoch_idx))
@@ -437,4 +473,30 @@ class Trainer:
 
     @torch.no_grad()
     def evaluate(self, eval_data, is_test=False, idx=0):
-        return self.evaluator.evaluate(self.evaluate_topk(eval_data), eval_data, is_test=is_test, idx=idx)
+        """trainer.py:509-528. On CUDA the whole pass -- evaluation forward, fused score + mask +
+        top-K, device metrics -- is captured in a CUDA graph the second time a loader is evaluated
+        and replayed afterwards (parameters are read in place, so replays see the current model);
+        one [5, K] float64 copy comes back to the host."""
+        if not self.use_eval_graph or not hasattr(eval_data, "gt_csr") or not eval_data.eval_u.is_cuda:
+            return self.evaluator.evaluate(self.evaluate_topk(eval_data), eval_data, is_test=is_test, idx=idx)
+        key = (id(eval_data), id(self.model))
+        ent = self._eval_graphs.get(key)
+        if ent is None:
+            self._eval_graphs[key] = {"graph": None, "eval_data": eval_data}     # first pass: eager warm-up
+            return self.evaluator.evaluate(self.evaluate_topk(eval_data), eval_data, is_test=is_test, idx=idx)
+        if ent["graph"] is None:
+            from . import lib
+            rowptr, items = eval_data.gt_csr()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = lib.launch_count()
+            with torch.cuda.graph(g):
+                self.model._eval_cache = None
+                topk = torch.cat(self.evaluate_topk(eval_data), dim=0)
+                sums = ops.topk_metric_sums(topk, rowptr, items)
+            self.model._eval_cache = None          # the captured forward wrote into graph-owned memory
+            ent.update(graph=g, sums=sums, topk=topk, launches=lib.launch_count() - l0)
+        self.model.eval()
+        ent["graph"].replay()
+        self.replayed_launches += ent["launches"]
+        return self.evaluator.result_from_sums(ent["sums"], ent["topk"].shape[0], eval_data)
