@@ -303,6 +303,26 @@ int mmrec_score_mask_topk_simt_f32(const float *user_emb, const int64_t *users, 
                                    int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,
                                    int32_t k, int32_t n_splits, float *ws_val, int32_t *ws_idx,
                                    float *out_val, int64_t *out_idx, void *stream);
+/* ----------------------------------------------------------------------------------------
+ * a5 -- item-item kNN modality graphs: build_sim / build_knn_normalized_graph /
+ * get_sparse_laplacian (utils/utils.py:134-137, 171-184, 139-152) and FREEDOM.get_knn_adj_mat /
+ * compute_normalized_laplacian (freedom.py:79-100).
+ *   mmrec_row_normalize_f32: out[r] = x[r] / ||x[r]||_2 (utils.py:135, freedom.py:80); the cosine
+ *     matrix itself is mmrec_gemm_tf32x3_f32(out, out^T).
+ *   mmrec_row_topk_f32: replaces torch.topk(sim, k, dim=-1) (utils.py:172, freedom.py:81) on a
+ *     dense [n_rows, ld] matrix (first n_cols columns): values / int32 columns [n_rows, k],
+ *     descending, ties -> lower column (torch's tie order is unspecified); NaNs are never picked.
+ *   mmrec_knn_weights_f32: edge weights of the [n, k] neighbour lists.
+ *     mode 0 (MGCN / SMORE, utils.py:139-152): deg[r] = sum_j w[r][j] (row sums on BOTH sides, so the
+ *       result is not symmetric), out = deg[r]^-1/2 * w * deg[c]^-1/2 with inf -> 0; dis_ws [n].
+ *     mode 1 (FREEDOM, freedom.py:87-100): binary edges, out = ((k + 1e-7)^-1/2)^2 in float32.
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_row_normalize_f32(const float *x, int32_t n_rows, int32_t d, float *out, void *stream);
+int mmrec_row_topk_f32(const float *mat, int32_t n_rows, int32_t n_cols, int64_t ld, int32_t k, float *out_val,
+                       int32_t *out_idx, void *stream);
+int mmrec_knn_weights_f32(const int32_t *idx, const float *val, int32_t n, int32_t k, int32_t mode, float *dis_ws,
+                          float *out_vals, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Top-K metrics on the device (K15). Replaces TopKEvaluator.evaluate / _calculate_metrics
  * (utils/topk_evaluator.py:58-143) and recall_/recall2_/precision_/ndcg_/map_

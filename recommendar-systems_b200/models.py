@@ -255,37 +255,16 @@ def _edge_values_cpu(edge_u, edge_i, n_users, n_items):
 
 
 # ----------------------------------------------------------------------------- item graphs
-def _build_sim(feat):
-    """utils/utils.py:134-137."""
-    n = feat.div(torch.norm(feat, p=2, dim=-1, keepdim=True))
-    return torch.mm(n, n.transpose(1, 0))
-
-
 def knn_sym_coo(feat, k):
     """build_sim + build_knn_normalized_graph(sparse, 'sym') + get_sparse_laplacian
-    (utils/utils.py:134-152, 171-184) without the per-element Python list comprehension."""
-    sim = _build_sim(feat)
-    knn_val, knn_ind = torch.topk(sim, k, dim=-1)
-    n = sim.shape[0]
-    rows = torch.arange(n, device=feat.device).unsqueeze(1).expand(-1, k).flatten()
-    cols = knn_ind.flatten()
-    w = knn_val.flatten()
-    deg = torch.zeros(n, dtype=w.dtype, device=w.device).index_add_(0, rows, w)
-    dis = deg.pow(-0.5)
-    dis.masked_fill_(dis == float("inf"), 0)
-    return rows, cols, dis[rows] * w * dis[cols]
+    (utils/utils.py:134-152, 171-184) on the library's kNN kernels (no per-element Python loop,
+    no [I, I] torch.topk)."""
+    return ops.knn_graph(feat, k, "sym")
 
 
 def freedom_knn_coo(feat, k):
     """FREEDOM.get_knn_adj_mat + compute_normalized_laplacian (freedom.py:79-100)."""
-    sim = _build_sim(feat)
-    _, knn_ind = torch.topk(sim, k, dim=-1)
-    n = sim.shape[0]
-    rows = torch.arange(n, device=feat.device).unsqueeze(1).expand(-1, k).flatten()
-    cols = knn_ind.flatten()
-    row_sum = 1e-7 + torch.bincount(rows, minlength=n)
-    r = torch.pow(row_sum, -0.5)
-    return rows, cols, r[rows] * r[cols]
+    return ops.knn_graph(feat, k, "freedom")
 
 
 def max_pool_fusion_coo(a, b, n):

@@ -572,6 +572,39 @@ def smore_side(fusion, image, text, content, layers, masks=None):
     return _SmoreSide.apply(fusion, image, text, content, masks, *wb)
 
 
+# ------------------------------------------------------------------------------ item kNN graphs
+@torch.no_grad()
+def knn_graph(feat, k, mode):
+    """(rows, cols, weights) of the cosine top-k item graph on the device.
+    mode 'sym'     : build_sim + build_knn_normalized_graph(sparse, 'sym') + get_sparse_laplacian
+                     (utils/utils.py:134-184) -- MGCN / SMORE;
+    mode 'freedom' : FREEDOM.get_knn_adj_mat + compute_normalized_laplacian (freedom.py:79-100).
+    Row normalisation, the [I, I] cosine GEMM (3xTF32), the per-row top-k (ties -> lower id) and
+    the edge weights all run in the library; rows / cols come back int64 like the reference's
+    index tensors, in (row, rank) order."""
+    feat = _f32c(feat)
+    lib.require_cuda(feat)
+    n, F = feat.shape
+    dev = feat.device
+    if F % 4:                                   # GEMM rows are 16-byte vectors: zero-pad the features
+        feat = torch.nn.functional.pad(feat, (0, 4 - F % 4))
+        F = feat.shape[1]
+    n_pad = (n + 3) // 4 * 4                    # ... and so are the rows of the cosine matrix
+    nrm = torch.zeros(n_pad, F, dtype=torch.float32, device=dev)
+    lib.call("mmrec_row_normalize_f32", lib.ptr(feat), n, F, lib.ptr(nrm), lib.stream())
+    sim = gemm(nrm, True, nrm, True, n_pad, n_pad, F)
+    val = torch.empty(n, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(n, k, dtype=torch.int32, device=dev)
+    lib.call("mmrec_row_topk_f32", lib.ptr(sim), n, n, n_pad, k, lib.ptr(val), lib.ptr(idx), lib.stream())
+    del sim
+    w = torch.empty(n, k, dtype=torch.float32, device=dev)
+    dis = torch.empty(n, dtype=torch.float32, device=dev)
+    lib.call("mmrec_knn_weights_f32", lib.ptr(idx), lib.ptr(val), n, k, {"sym": 0, "freedom": 1}[mode],
+             lib.ptr(dis), lib.ptr(w), lib.stream())
+    rows = torch.arange(n, device=dev).unsqueeze(1).expand(-1, k).flatten()
+    return rows, idx.flatten().to(torch.int64), w.flatten()
+
+
 # -------------------------------------------------------------------------------- score + top-K
 def choose_splits(n_users, n_items):
     """Item-range splits so that (user tiles x splits) is close to one wave of 148 CTAs (the

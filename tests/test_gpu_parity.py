@@ -696,3 +696,58 @@ def test_accelerate_cache_follows_tensor_identity_and_version():
         y5 = torch.mm(csr, x)
         assert mode.stats["spmm"] == 1
     assert rel(y5, y2) < 1e-5
+
+
+# ------------------------------------------------------------------ a5: item kNN graphs on the device
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,F,k", [(300, 64, 10), (1001, 384, 20), (2500, 130, 15)])
+@pytest.mark.parametrize("mode", ["sym", "freedom"])
+def test_knn_graph_matches_oracle(n, F, k, mode):
+    """utils.py:134-184 / freedom.py:79-100: same neighbour sets as torch.topk on the oracle's
+    cosine matrix (up to near-ties between two fp32 GEMMs), weights within 1e-5."""
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(31)
+    cent = torch.randn(16, F, generator=gen)
+    feat = cent[torch.randint(0, 16, (n,), generator=gen)] + 0.5 * torch.randn(n, F, generator=gen)
+    feat[7] = feat[3]                                         # duplicated item: exact ties in every row
+    r, c, w = ops.knn_graph(feat.to(DEV), k, mode)
+    fn = ograph.knn_sym_graph if mode == "sym" else ograph.freedom_knn_adj
+    wr, wc, ww = (torch.as_tensor(np.asarray(t)) for t in fn(feat, k))
+    r, c, w = r.cpu(), c.cpu(), w.cpu()
+    assert torch.equal(r, wr.long()) and c.shape == wc.shape
+    got_sets = c.view(n, k).sort(dim=1)[0]
+    want_sets = wc.long().view(n, k).sort(dim=1)[0]
+    same_rows = (got_sets == want_sets).all(dim=1)
+    # rows whose sets differ must differ only by candidates tied to ~1e-6 in cosine
+    sim = ograph.build_sim(feat)
+    for row in torch.nonzero(~same_rows).flatten().tolist():
+        a = set(got_sets[row].tolist()) ^ set(want_sets[row].tolist())
+        vals = sim[row, list(a)]
+        assert float(vals.max() - vals.min()) < 1e-5
+    assert same_rows.float().mean() > 0.98
+    # ranks: descending similarity, ties -> lower id
+    s_got = sim[r, c].view(n, k)
+    assert bool((s_got[:, 1:] <= s_got[:, :-1] + 1e-5).all())
+    if mode == "freedom":
+        assert rel(w, ww) < 1e-6
+    else:
+        ok = same_rows.repeat_interleave(k)
+        key_g = (r * n + c)[ok]
+        key_w = (wr.long() * n + wc.long())[ok]
+        og, ow = key_g.argsort(), key_w.argsort()
+        # weights depend on row sums of the neighbour's own list, which can hold a flipped near-tie
+        assert torch.equal(key_g[og], key_w[ow])
+        assert float(((w[ok][og] - ww[ok][ow]).abs() / ww[ok][ow].abs()).median()) < 1e-6
+        assert float(((w[ok][og] - ww[ok][ow]).abs() / ww[ok][ow].abs()).max()) < 5e-3
+
+
+@pytest.mark.gpu
+def test_row_topk_ties_and_short_rows():
+    L, lib = pkg("lib"), pkg("lib")
+    m = torch.tensor([[1.0, 3.0, 3.0, 2.0, 3.0, 0.0, float("nan"), -1.0],
+                      [5.0, 5.0, 5.0, 5.0, 5.0, 5.0, 5.0, 5.0]], device=DEV)
+    val = torch.empty(2, 3, device=DEV)
+    idx = torch.empty(2, 3, dtype=torch.int32, device=DEV)
+    lib.call("mmrec_row_topk_f32", lib.ptr(m), 2, 8, 8, 3, lib.ptr(val), lib.ptr(idx), lib.stream())
+    assert idx.cpu().tolist() == [[1, 2, 4], [0, 1, 2]]       # SURVEY appendix A: lower id first
+    assert val.cpu().tolist() == [[3.0, 3.0, 3.0], [5.0, 5.0, 5.0]]
