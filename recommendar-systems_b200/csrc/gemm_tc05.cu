@@ -6,8 +6,8 @@
 //                                                                     computed as dW^T and stored transposed
 //   dx       dx = dy W       output [I, F]                            A K-major,  B MN-major, N ranges
 // One CTA owns 128 rows of the UMMA M dimension. Warp roles:
-//   warps 4-11 producers : stream 32-wide K blocks of both operands from HBM/L2 (coalesced float4,
-//                          prefetched one block ahead in registers), split every value into tf32
+//   warps 4-11 producers : four independent groups stream 32-wide K blocks of both operands from
+//                          HBM/L2 (coalesced float4, one block in flight per group), split every value into tf32
 //                          hi/lo and store both halves into swizzled canonical UMMA tiles (K-major
 //                          SWIZZLE_128B or MN-major SWIZZLE_128B_BASE32B, so neither backward
 //                          GEMM transposes the table);
@@ -28,9 +28,21 @@ using namespace tc05;
 constexpr int kBM = 128;            // UMMA M
 constexpr int kKB = 32;             // floats of K per pipeline stage (one 128-byte swizzle atom)
 constexpr int kChunkKB = 2;         // K blocks per tensor-core accumulation chain
-constexpr int kProdWarps = 8;
-constexpr int kProdThreads = kProdWarps * 32;
+// Producers work in kGroups independent groups of kGroupThreads; group g owns K blocks g, g +
+// kGroups, ... and keeps exactly ONE block of loads in flight (load -> wait -> split -> store).
+// Keeping several blocks in flight per THREAD (the first version: 4 per thread) does not work:
+// the compiler maps the loads of different blocks onto the same few scoreboards, so waiting for
+// the oldest block also waits for the one issued just before -- the kernel ran at one block per
+// DRAM round trip (20 GB/s per SM, 28 % of HBM peak). Independent warps cannot alias.
+// 256 producer threads: four groups of 64 (two of 128 for the 128-wide N tile, whose block would
+// not fit the registers of 64 threads).
+constexpr int kProdThreads = 256;
+constexpr int kMmaWarp = 4 + kProdThreads / 32;
 constexpr int kThreadsG = 128 + kProdThreads + 32;
+
+__device__ __forceinline__ void group_sync(int id, int n_threads) {     // named barrier of one producer group
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
 
 struct GemmArgs {
   const float *A, *B, *bias;
@@ -56,17 +68,17 @@ __device__ __forceinline__ uint32_t off_mnmajor(int k, int q) {
 }
 
 // One operand block [E x 32] in flight: PER float4 per producer thread.
-template <int E, bool MN>
+template <int E, bool MN, int kGroupThreads>
 struct Block {
-  static constexpr int PER = E * 8 / kProdThreads;
-  static_assert(E * 8 % kProdThreads == 0, "operand block must be a multiple of the producer count");
+  static constexpr int PER = E * 8 / kGroupThreads;
+  static_assert(E * 8 % kGroupThreads == 0, "operand block must be a multiple of the producer group");
   float4 v[PER];
   // src element (i, k): K-major src[i * ld + k]; MN-major src[k * ld + i]. i < lim_i, k < lim_k else 0.
   __device__ __forceinline__ void load(const float *__restrict__ src, int ld, int i0, int lim_i, int k0, int lim_k,
                                        int ptid) {
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-      const int idx = ptid + j * kProdThreads;
+      const int idx = ptid + j * kGroupThreads;
       int i, k;
       if constexpr (!MN) { i = i0 + idx / 8; k = k0 + (idx % 8) * 4; }
       else { k = k0 + idx / (E / 4); i = i0 + (idx % (E / 4)) * 4; }
@@ -77,7 +89,7 @@ struct Block {
   __device__ __forceinline__ void store(uint8_t *hi_tile, uint8_t *lo_tile, int ptid) const {
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-      const int idx = ptid + j * kProdThreads;
+      const int idx = ptid + j * kGroupThreads;
       const uint32_t off = MN ? off_mnmajor<E>(idx / (E / 4), idx % (E / 4)) : off_kmajor<E>(idx / 8, idx % 8);
       float4 hi, lo;
       split_tf32x4(v[j], hi, lo);
@@ -94,6 +106,8 @@ struct GCfg {
   static constexpr int STAGES = NT <= 32 ? 4 : NT <= 64 ? 3 : 2;
   static constexpr uint32_t EPI = 4 * 32 * (NT + 4) * 4;   // epilogue staging: 4 warps x [32][NT + 4] floats
   static constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
+  static constexpr int GROUPS = NT >= 128 ? 2 : 4;          // independent producer groups
+  static constexpr int GROUP_THREADS = kProdThreads / GROUPS;
 };
 
 template <bool A_MN, bool B_MN, int NT, bool TRANS_OUT>
@@ -105,6 +119,7 @@ gemm_tc05_kernel(const GemmArgs g) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE);
   uint64_t *full = bars, *empty = bars + C::STAGES, *tfull = empty + C::STAGES, *tempty = tfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  volatile int *passed = reinterpret_cast<volatile int *>(tmem_slot + 1);   // producer wait chain (see below)
   float *stg = reinterpret_cast<float *>(tmem_slot + 4);     // 4 warps x [32][NT + 4] epilogue staging
 
   // warp index through a broadcast: provably warp-uniform, so role branches and the MMA issue
@@ -121,50 +136,46 @@ gemm_tc05_kernel(const GemmArgs g) {
   const uint32_t smem_base = smem_u32(smem);
 
   if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, kProdThreads); mbar_init(empty + s, 1); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, C::GROUP_THREADS); mbar_init(empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
+    *passed = 0;
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, C::TMEM_COLS);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp >= 4 && warp < 12) {
+  if (warp >= 4 && warp < kMmaWarp) {
     // =============================== producers ===============================================
-    // PD K blocks of loads are in flight per thread (72-96 KB per SM): the stream is latency-bound
-    // otherwise -- one block per DRAM round trip is ~20 GB/s per SM, half of its HBM share.
-    const int ptid = tid - 128;
-    constexpr int PD = NT <= 64 ? 4 : 2;
-    Block<kBM, A_MN> a[PD];
-    Block<NT, B_MN> b[PD];
-    auto load_iter = [&](Block<kBM, A_MN> &ab, Block<NT, B_MN> &bb, int it) {
+    const int grp = (tid - 128) / C::GROUP_THREADS, ptid = (tid - 128) % C::GROUP_THREADS;
+    Block<kBM, A_MN, C::GROUP_THREADS> a;
+    Block<NT, B_MN, C::GROUP_THREADS> b;
+    for (int it = grp; it < n_iter; it += C::GROUPS) {
       const int nt = nt_begin + it / n_kb, kb = kb_begin + it % n_kb;
       const int k_lim = min(g.K, kb_end * kKB);
-      ab.load(g.A, g.lda, m0, g.M, kb * kKB, k_lim, ptid);
-      bb.load(g.B, g.ldb, nt * NT, g.N, kb * kKB, k_lim, ptid);
-    };
-#pragma unroll
-    for (int u = 0; u < PD; ++u)
-      if (u < n_iter) load_iter(a[u], b[u], u);
-    for (int it0 = 0; it0 < n_iter; it0 += PD) {
-#pragma unroll
-      for (int u = 0; u < PD; ++u) {
-        const int it = it0 + u;
-        if (it < n_iter) {
-          const int s = it % C::STAGES;
-          mbar_wait(empty + s, ((it / C::STAGES) & 1) ^ 1);
-          uint8_t *stage = smem + s * C::STAGE;
-          a[u].store(stage, stage + C::A_HALF, ptid);
-          b[u].store(stage + 2 * C::A_HALF, stage + 2 * C::A_HALF + C::B_HALF, ptid);
-          fence_proxy_async_smem();
-          mbar_arrive(full + s);
-          if (it + PD < n_iter) load_iter(a[u], b[u], it + PD);
-        }
+      a.load(g.A, g.lda, m0, g.M, kb * kKB, k_lim, ptid);
+      b.load(g.B, g.ldb, nt * NT, g.N, kb * kKB, k_lim, ptid);
+      const int s = it % C::STAGES;
+      // There are more groups than stages, so a group could reach its wait on empty[s] while that
+      // barrier is still TWO phases behind (the consumer of it - 2 * STAGES has not committed yet)
+      // and a parity wait would then pass at once. The waits are therefore chained in iteration
+      // order: block `it` waits only after the producer of block it - 1 is through its own wait.
+      if (ptid == 0) {
+        for (uint32_t spin = 0; *passed < it; ++spin)
+          if (spin > (1u << 26)) __trap();
       }
+      group_sync(1 + grp, C::GROUP_THREADS);
+      mbar_wait(empty + s, ((it / C::STAGES) & 1) ^ 1);
+      if (ptid == 0) *passed = it + 1;
+      uint8_t *stage = smem + s * C::STAGE;
+      a.store(stage, stage + C::A_HALF, ptid);
+      b.store(stage + 2 * C::A_HALF, stage + 2 * C::A_HALF + C::B_HALF, ptid);
+      fence_proxy_async_smem();
+      mbar_arrive(full + s);
     }
-  } else if (warp == 12) {
+  } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ==============================================
     constexpr uint32_t idesc = idesc_tf32(kBM, NT, A_MN, B_MN);
     // K-major (SWIZZLE_128B): SBO = 1024 (next 8 rows); a K step of 8 floats is +32 bytes in the atom.
@@ -271,7 +282,7 @@ gemm_tc05_kernel(const GemmArgs g) {
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kMmaWarp) {
     fence_after_sync();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
