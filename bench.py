@@ -215,6 +215,10 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     batches = take_batches(env["train"], W + K)
     model.train()
+    # clocks / throttle reasons are sampled every 20 ms from before the warm-up until the end of the
+    # end-to-end loop (the device-timed K steps alone last a few tens of ms: too short for nvidia-smi)
+    sampler = ClockSampler(local)
+    sampler.start()
     for b in batches[:W]:
         trainer._train_batch_graphed(b)          # eager twice per variant, then captured + replayed
     torch.cuda.synchronize()
@@ -224,18 +228,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     l0 = lib.launch_count() + trainer.replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("timed_steps")          # ncu --nvtx --nvtx-include "timed_steps/"
     e0.record()
     for b in batches[W:]:
         trainer._train_batch_graphed(b)
     e1.record()
+    torch.cuda.nvtx.range_pop()
     barrier()
     launches = lib.launch_count() + trainer.replayed_launches - l0
-    clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -256,6 +259,7 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     trainer.sync_free = True
+    clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -274,9 +278,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     eval_s = (time.perf_counter() - t0) / reps
     a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("timed_eval")
     a.record()
     trainer.evaluate(env["valid"])
     b_.record()
+    torch.cuda.nvtx.range_pop()
     torch.cuda.synchronize()
     eval_dev_ms = a.elapsed_time(b_)
 

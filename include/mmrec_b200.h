@@ -272,7 +272,21 @@ int mmrec_adam_step_f32(float *const *params_host, const float *const *grads_hos
                         float *const *exp_avg_host, float *const *exp_avg_sq_host,
                         const int64_t *numel_host, int32_t n_tensors, double *hyper, double beta1,
                         double beta2, double eps, double weight_decay, double grad_scale,
-                        void *stream);
+                        const float *const *undo_host, const float *undo_coef, void *stream);
+/* undo_host / undo_coef (both NULL, or n_tensors device pointers + a device scalar): every
+ * parameter is first moved by p += undo_coef[0] * undo_t, the return from the mirror point
+ * theta - c*g to theta (trainer.py:322-329), in the same pass that applies the update.
+ *
+ * mmrec_mirror_coef_f32 -- the step size of the mirror-gradient perturbation (trainer.py:289-305):
+ *   alpha_eff = clamp(target_rel_step * rms(theta) / (lr * rms(g) + 1e-12), alpha_base,
+ *                     alpha_base * alpha_max_scale),  rms over all numel_total elements,
+ *   coef_out[0] = alpha_eff * lr (device float, feeds mmrec_axpy_multi_f32 / undo_coef),
+ *   coef_out[1] = alpha_eff. One pass over parameters and gradients + a fixed-order final sum. */
+size_t mmrec_mirror_coef_workspace_bytes(const int64_t *numel_host, int32_t n_tensors);
+int mmrec_mirror_coef_f32(const float *const *params_host, const float *const *grads_host,
+                          const int64_t *numel_host, int32_t n_tensors, const double *hyper,
+                          double numel_total, double alpha_base, double alpha_max_scale,
+                          double target_rel_step, void *workspace, float *coef_out, void *stream);
 /* y_t += sign * coef[0] * x_t for n_tensors tensors in one launch; coef is a device scalar
  * (the mirror-gradient perturbation theta -/+ alpha_eff*lr*g of trainer.py:307-329 without a
  * host round trip for alpha_eff). */

@@ -92,20 +92,33 @@ topk_metrics_kernel(const int64_t *__restrict__ topk, int n_users, int k, const 
   }
 }
 
-__global__ void __launch_bounds__(64)
+// Fixed-order sum of the per-block partials: one CTA per metric, 16 slices of the part list per
+// rank (slice q adds parts q, q + 16, ... in order, four independent chains), then the slices in
+// order. (One thread per rank walking all ~1100 parts was a 116 us chain of dependent loads.)
+constexpr int kRedSlices = 16;
+__global__ void __launch_bounds__(64 * kRedSlices)
 topk_metrics_reduce_kernel(const double *__restrict__ partial, int n_parts, int k, double *__restrict__ out) {
-  const int m = blockIdx.x, r = threadIdx.x;
-  if (r >= k) return;
+  __shared__ double sh[kRedSlices][64];
+  const int m = blockIdx.x, r = threadIdx.x & 63, q = threadIdx.x >> 6;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int p = 0;
-  for (; p + 4 <= n_parts; p += 4) {
-    s0 += partial[((size_t)p * kNumMetrics + m) * 64 + r];
-    s1 += partial[((size_t)(p + 1) * kNumMetrics + m) * 64 + r];
-    s2 += partial[((size_t)(p + 2) * kNumMetrics + m) * 64 + r];
-    s3 += partial[((size_t)(p + 3) * kNumMetrics + m) * 64 + r];
+  if (r < k) {
+    int p = q;
+    for (; p + 3 * kRedSlices < n_parts; p += 4 * kRedSlices) {
+      s0 += partial[((size_t)p * kNumMetrics + m) * 64 + r];
+      s1 += partial[((size_t)(p + kRedSlices) * kNumMetrics + m) * 64 + r];
+      s2 += partial[((size_t)(p + 2 * kRedSlices) * kNumMetrics + m) * 64 + r];
+      s3 += partial[((size_t)(p + 3 * kRedSlices) * kNumMetrics + m) * 64 + r];
+    }
+    for (; p < n_parts; p += kRedSlices) s0 += partial[((size_t)p * kNumMetrics + m) * 64 + r];
   }
-  for (; p < n_parts; ++p) s0 += partial[((size_t)p * kNumMetrics + m) * 64 + r];
-  out[m * k + r] = (s0 + s1) + (s2 + s3);
+  sh[q][r] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (q == 0 && r < k) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kRedSlices; ++j) s += sh[j][r];
+    out[m * k + r] = s;
+  }
 }
 
 }  // namespace
@@ -129,7 +142,7 @@ extern "C" int mmrec_topk_metrics_f64(const int64_t *topk, int32_t n_users, int3
   topk_metrics_kernel<<<blocks, kThreadsM, 0, st>>>(topk, n_users, k, gt_rowptr, gt_items, disc, idcg_all, hits_out,
                                                    partial);
   MMREC_CHECK_LAUNCH("topk_metrics_kernel");
-  topk_metrics_reduce_kernel<<<kNumMetrics, 64, 0, st>>>(partial, blocks, k, sums_out);
+  topk_metrics_reduce_kernel<<<kNumMetrics, 64 * kRedSlices, 0, st>>>(partial, blocks, k, sums_out);
   MMREC_CHECK_LAUNCH("topk_metrics_reduce_kernel");
   return MMREC_OK;
 }

@@ -20,7 +20,16 @@ struct AdamPack {
   const float *g[kMaxTensors];
   float *m[kMaxTensors];
   float *v[kMaxTensors];
+  const float *undo[kMaxTensors];     // optional: p += undo_coef[0] * undo[t] before the update
   int chunk_begin[kMaxTensors + 1];   // prefix sum of ceil(numel / kChunk)
+  int64_t numel[kMaxTensors];
+  int n_tensors;
+};
+
+struct AxpyPack {
+  float *y[kMaxTensors];
+  const float *x[kMaxTensors];
+  int chunk_begin[kMaxTensors + 1];
   int64_t numel[kMaxTensors];
   int n_tensors;
 };
@@ -31,7 +40,7 @@ __global__ void adam_tick_kernel(double *hyper) { hyper[1] += 1.0; }
 
 __global__ void __launch_bounds__(kThreads)
 adam_kernel(const __grid_constant__ AdamPack pack, const double *__restrict__ hyper, double beta1d,
-            double beta2d, float eps, float weight_decay, float grad_scale) {
+            double beta2d, float eps, float weight_decay, float grad_scale, const float *__restrict__ undo_coef) {
   __shared__ float s_hyper[2];
   if (threadIdx.x == 0) {
     const double lr = hyper[0], step = hyper[1];
@@ -53,6 +62,11 @@ adam_kernel(const __grid_constant__ AdamPack pack, const double *__restrict__ hy
   float *__restrict__ v = pack.v[t];
   const float w1 = (float)(1.0 - beta1d), w2 = (float)(1.0 - beta2d);
   (void)beta1;
+  // mirror-gradient step (trainer.py:307-335): the parameters were moved to theta - c*g_old for the
+  // second backward; they return to theta here, in the pass that applies the update, with the same
+  // fmaf the separate axpy kernel would have used (bit-identical, one 12-byte-per-element pass less)
+  const float *__restrict__ ux = undo_coef != nullptr ? pack.undo[t] : nullptr;
+  const float uc = undo_coef != nullptr ? undo_coef[0] : 0.f;
   auto upd = [&](float &pp, float gg, float &mm, float &vv) {
     gg *= grad_scale;                                          // 1.0f is exact
     if (weight_decay != 0.f) gg = fmaf(weight_decay, pp, gg);
@@ -69,25 +83,86 @@ adam_kernel(const __grid_constant__ AdamPack pack, const double *__restrict__ hy
       float4 pp = *reinterpret_cast<float4 *>(p + i), mm = *reinterpret_cast<float4 *>(m + i),
              vv = *reinterpret_cast<float4 *>(v + i);
       const float4 gg = __ldcs(reinterpret_cast<const float4 *>(g + i));
+      if (ux != nullptr) {
+        const float4 xx = __ldcs(reinterpret_cast<const float4 *>(ux + i));
+        pp.x = fmaf(uc, xx.x, pp.x); pp.y = fmaf(uc, xx.y, pp.y); pp.z = fmaf(uc, xx.z, pp.z); pp.w = fmaf(uc, xx.w, pp.w);
+      }
       upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y);
       upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
       *reinterpret_cast<float4 *>(p + i) = pp;
       *reinterpret_cast<float4 *>(m + i) = mm;
       *reinterpret_cast<float4 *>(v + i) = vv;
     }
-    for (int64_t i = end4 + threadIdx.x; i < end; i += kThreads) upd(p[i], g[i], m[i], v[i]);
+    for (int64_t i = end4 + threadIdx.x; i < end; i += kThreads) {
+      if (ux != nullptr) p[i] = fmaf(uc, ux[i], p[i]);
+      upd(p[i], g[i], m[i], v[i]);
+    }
   } else {
-    for (int64_t i = begin + threadIdx.x; i < end; i += kThreads) upd(p[i], g[i], m[i], v[i]);
+    for (int64_t i = begin + threadIdx.x; i < end; i += kThreads) {
+      if (ux != nullptr) p[i] = fmaf(uc, ux[i], p[i]);
+      upd(p[i], g[i], m[i], v[i]);
+    }
   }
 }
 
-struct AxpyPack {
-  float *y[kMaxTensors];
-  const float *x[kMaxTensors];
-  int chunk_begin[kMaxTensors + 1];
-  int64_t numel[kMaxTensors];
-  int n_tensors;
-};
+// ---- mirror-gradient step size (trainer.py:289-305) ---------------------------------------
+// alpha_eff = clamp(target * rms(theta) / (lr * rms(g) + 1e-12), alpha, alpha * max_scale) needs
+// sum g^2 and sum theta^2 over every parameter: one pass over both lists (per-CTA partials in
+// double), then one CTA adds the partials in a fixed order and writes coef = alpha_eff * lr.
+// Replaces two _foreach_norm passes and ~20 scalar torch kernels.
+__global__ void __launch_bounds__(kThreads)
+sumsq_pair_kernel(const __grid_constant__ AxpyPack pack, double *__restrict__ partial) {
+  __shared__ float red[kThreads / 32];
+  const int chunk = blockIdx.x;
+  int t = 0;
+  while (t + 1 < pack.n_tensors && pack.chunk_begin[t + 1] <= chunk) ++t;
+  const int64_t begin = (int64_t)(chunk - pack.chunk_begin[t]) * kChunk;
+  const int64_t end = min(pack.numel[t], begin + kChunk);
+  const float *__restrict__ y = pack.y[t];
+  const float *__restrict__ x = pack.x[t];
+  float sy = 0.f, sx = 0.f;
+  const bool vec = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0;
+  if (vec) {
+    const int64_t end4 = begin + ((end - begin) & ~int64_t(3));
+    for (int64_t i = begin + threadIdx.x * 4; i < end4; i += kThreads * 4) {
+      const float4 yy = *reinterpret_cast<const float4 *>(y + i), xx = *reinterpret_cast<const float4 *>(x + i);
+      sy += dot4(yy, yy);
+      sx += dot4(xx, xx);
+    }
+    for (int64_t i = end4 + threadIdx.x; i < end; i += kThreads) { sy = fmaf(y[i], y[i], sy); sx = fmaf(x[i], x[i], sx); }
+  } else {
+    for (int64_t i = begin + threadIdx.x; i < end; i += kThreads) { sy = fmaf(y[i], y[i], sy); sx = fmaf(x[i], x[i], sx); }
+  }
+  const float ty = block_sum<kThreads>(sy, red);
+  const float tx = block_sum<kThreads>(sx, red);
+  if (threadIdx.x == 0) {
+    partial[2 * (size_t)chunk] = (double)ty;
+    partial[2 * (size_t)chunk + 1] = (double)tx;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+mirror_coef_kernel(const double *__restrict__ partial, int n_parts, const double *__restrict__ hyper, double numel,
+                   float alpha_base, float alpha_max_scale, float target_rel, float *__restrict__ out) {
+  __shared__ double sh[2][kThreads];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n_parts; i += kThreads) { a += partial[2 * (size_t)i]; b += partial[2 * (size_t)i + 1]; }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double p2 = 0.0, g2 = 0.0;
+    for (int i = 0; i < kThreads; ++i) { p2 += sh[0][i]; g2 += sh[1][i]; }
+    // float32 arithmetic in the order of the reference's tensor expression
+    const float lr = (float)hyper[0], n = (float)numel;
+    const float grad_rms = sqrtf((float)g2 / n);
+    const float param_rms = sqrtf((float)p2 / n) + 1e-12f;
+    float alpha = target_rel * param_rms / (lr * grad_rms + 1e-12f);
+    alpha = fminf(fmaxf(alpha, alpha_base), alpha_base * alpha_max_scale);
+    out[0] = alpha * lr;      // coef: theta' = theta - coef * g
+    out[1] = alpha;           // alpha_eff (logging)
+  }
+}
 
 // y_t += sign * coef[0] * x_t for every tensor t (coef is a device scalar)
 __global__ void __launch_bounds__(kThreads)
@@ -125,9 +200,11 @@ extern "C" int mmrec_adam_step_f32(float *const *params_host, const float *const
                                    float *const *exp_avg_host, float *const *exp_avg_sq_host,
                                    const int64_t *numel_host, int32_t n_tensors, double *hyper, double beta1,
                                    double beta2, double eps, double weight_decay, double grad_scale,
-                                   void *stream) {
+                                   const float *const *undo_host, const float *undo_coef, void *stream) {
   MMREC_REQUIRE(params_host && grads_host && exp_avg_host && exp_avg_sq_host && numel_host && hyper,
                 MMREC_E_BADARG, "adam: null pointer");
+  MMREC_REQUIRE((undo_host == nullptr) == (undo_coef == nullptr), MMREC_E_BADARG,
+                "adam: undo tensors and undo coefficient must be given together");
   MMREC_REQUIRE(n_tensors >= 0, MMREC_E_BADARG, "adam: bad sizes");
   adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
   MMREC_CHECK_LAUNCH("adam_tick_kernel");
@@ -140,6 +217,8 @@ extern "C" int mmrec_adam_step_f32(float *const *params_host, const float *const
       pack.g[i] = grads_host[base + i];
       pack.m[i] = exp_avg_host[base + i];
       pack.v[i] = exp_avg_sq_host[base + i];
+      pack.undo[i] = undo_host != nullptr ? undo_host[base + i] : nullptr;
+      MMREC_REQUIRE(undo_host == nullptr || pack.undo[i] != nullptr, MMREC_E_BADARG, "adam: bad undo tensor %d", base + i);
       pack.numel[i] = numel_host[base + i];
       MMREC_REQUIRE(pack.p[i] && pack.g[i] && pack.m[i] && pack.v[i] && pack.numel[i] >= 0, MMREC_E_BADARG,
                     "adam: bad tensor %d", base + i);
@@ -149,7 +228,8 @@ extern "C" int mmrec_adam_step_f32(float *const *params_host, const float *const
     pack.chunk_begin[pack.n_tensors] = chunks;
     if (chunks == 0) continue;
     adam_kernel<<<chunks, kThreads, 0, (cudaStream_t)stream>>>(pack, hyper, beta1, beta2, (float)eps,
-                                                              (float)weight_decay, (float)grad_scale);
+                                                              (float)weight_decay, (float)grad_scale,
+                                                              undo_host != nullptr ? undo_coef : nullptr);
     MMREC_CHECK_LAUNCH("adam_kernel");
   }
   return MMREC_OK;
@@ -176,5 +256,46 @@ extern "C" int mmrec_axpy_multi_f32(float *const *y_host, const float *const *x_
     axpy_multi_kernel<<<chunks, kThreads, 0, (cudaStream_t)stream>>>(pack, coef, sign);
     MMREC_CHECK_LAUNCH("axpy_multi_kernel");
   }
+  return MMREC_OK;
+}
+
+extern "C" size_t mmrec_mirror_coef_workspace_bytes(const int64_t *numel_host, int32_t n_tensors) {
+  size_t chunks = 0;
+  for (int i = 0; i < n_tensors; ++i) chunks += (size_t)((numel_host[i] + kChunk - 1) / kChunk);
+  return 2 * sizeof(double) * (chunks + 1);
+}
+
+extern "C" int mmrec_mirror_coef_f32(const float *const *params_host, const float *const *grads_host,
+                                     const int64_t *numel_host, int32_t n_tensors, const double *hyper,
+                                     double numel_total, double alpha_base, double alpha_max_scale,
+                                     double target_rel_step, void *workspace, float *coef_out, void *stream) {
+  MMREC_REQUIRE(params_host && grads_host && numel_host && hyper && workspace && coef_out, MMREC_E_BADARG,
+                "mirror_coef: null pointer");
+  MMREC_REQUIRE(n_tensors > 0 && numel_total > 0, MMREC_E_BADARG, "mirror_coef: bad sizes");
+  double *partial = static_cast<double *>(workspace);
+  int done = 0;
+  for (int base = 0; base < n_tensors; base += kMaxTensors) {
+    AxpyPack pack;
+    pack.n_tensors = min(kMaxTensors, n_tensors - base);
+    int chunks = 0;
+    for (int i = 0; i < pack.n_tensors; ++i) {
+      pack.y[i] = const_cast<float *>(params_host[base + i]);
+      pack.x[i] = grads_host[base + i];
+      pack.numel[i] = numel_host[base + i];
+      MMREC_REQUIRE(pack.y[i] && pack.x[i] && pack.numel[i] >= 0, MMREC_E_BADARG, "mirror_coef: bad tensor %d",
+                    base + i);
+      pack.chunk_begin[i] = chunks;
+      chunks += (int)((pack.numel[i] + kChunk - 1) / kChunk);
+    }
+    pack.chunk_begin[pack.n_tensors] = chunks;
+    if (chunks == 0) continue;
+    sumsq_pair_kernel<<<chunks, kThreads, 0, (cudaStream_t)stream>>>(pack, partial + 2 * (size_t)done);
+    MMREC_CHECK_LAUNCH("sumsq_pair_kernel");
+    done += chunks;
+  }
+  mirror_coef_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(partial, done, hyper, numel_total, (float)alpha_base,
+                                                             (float)alpha_max_scale, (float)target_rel_step,
+                                                             coef_out);
+  MMREC_CHECK_LAUNCH("mirror_coef_kernel");
   return MMREC_OK;
 }

@@ -54,7 +54,10 @@ SIGNATURES = {
     "mmrec_smore_side_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                            _p, _i32, _i32, _p]),
     "mmrec_adam_step_f32": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double,
-                                      C.c_double, C.c_double, _p]),
+                                      C.c_double, C.c_double, _p, _p, _p]),
+    "mmrec_mirror_coef_workspace_bytes": (_sz, [_p, _i32]),
+    "mmrec_mirror_coef_f32": (C.c_int, [_p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                        _p, _p, _p]),
     "mmrec_axpy_multi_f32": (C.c_int, [_p, _p, _p, _i32, _p, _f32, _p]),
     "mmrec_row_normalize_f32": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "mmrec_row_topk_f32": (C.c_int, [_p, _i32, _i32, _i64, _i32, _p, _p, _p]),

@@ -20,6 +20,20 @@ def axpy_multi(ys, xs, coef, sign=1.0):
                  (C.c_int64 * n)(*[t.numel() for t in ys]), n, lib.ptr(coef), float(sign), lib.stream())
 
 
+def mirror_coef(params, grads, hyper, numel_total, alpha_base, alpha_max_scale, target_rel_step):
+    """Device float [2] = (alpha_eff * lr, alpha_eff) of the mirror-gradient step
+    (trainer.py:289-305) from one pass over parameters and gradients (mmrec_mirror_coef_f32)."""
+    n = len(params)
+    numel = (C.c_int64 * n)(*[t.numel() for t in params])
+    ws = torch.empty(lib.load().mmrec_mirror_coef_workspace_bytes(numel, n), dtype=torch.uint8,
+                     device=params[0].device)
+    out = torch.empty(2, dtype=torch.float32, device=params[0].device)
+    lib.call("mmrec_mirror_coef_f32", _ptr_array(params), _ptr_array(grads), numel, n, lib.ptr(hyper),
+             float(numel_total), float(alpha_base), float(alpha_max_scale), float(target_rel_step), lib.ptr(ws),
+             lib.ptr(out), lib.stream())
+    return out
+
+
 class FusedAdam(torch.optim.Optimizer):
     """Drop-in for `optim.Adam(params, lr, weight_decay)` (betas 0.9/0.999, eps 1e-8, no amsgrad).
     State keys `exp_avg` / `exp_avg_sq` as in torch; `param_groups[i]['lr']` is honoured (LambdaLR
@@ -51,14 +65,16 @@ class FusedAdam(torch.optim.Optimizer):
         return self._hyper(g, dev)[0:1]
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=1.0):
-        """`grad_scale` multiplies every gradient inside the kernel (fp32, as `_foreach_mul_` would)."""
+    def step(self, closure=None, grad_scale=1.0, undo=None):
+        """`grad_scale` multiplies every gradient inside the kernel (fp32, as `_foreach_mul_` would).
+        `undo` = ({param: tensor}, coef): every parameter is first moved by coef * tensor (the
+        return from the mirror-gradient point) in the same pass."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         for group in self.param_groups:
-            ps, gs, ms, vs = [], [], [], []
+            ps, gs, ms, vs, us = [], [], [], [], []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -72,6 +88,8 @@ class FusedAdam(torch.optim.Optimizer):
                 gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
+                if undo is not None:
+                    us.append(undo[0][p])
             n = len(ps)
             if n == 0:
                 continue
@@ -81,5 +99,7 @@ class FusedAdam(torch.optim.Optimizer):
             lib.call("mmrec_adam_step_f32", _ptr_array(ps), _ptr_array(gs), _ptr_array(ms), _ptr_array(vs),
                      (C.c_int64 * n)(*[t.numel() for t in ps]), n, lib.ptr(hyper),
                      float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
-                     float(group["weight_decay"]), float(grad_scale), lib.stream())
+                     float(group["weight_decay"]), float(grad_scale),
+                     _ptr_array(us) if undo is not None else None,
+                     lib.ptr(undo[1]) if undo is not None else None, lib.stream())
         return loss

@@ -231,47 +231,60 @@ class Trainer:
                 params.append(p)
                 grads.append(p.grad.detach())
         alpha_base = float(getattr(model, "mg_alpha", 0.5))
+        sharded = [getattr(p, "_mmrec_sharded", False) for p in params]
+        fused = hasattr(opt, "lr_tensor") and not any(sharded) and len(opt.param_groups) == 1
         with torch.no_grad():
-            dev = params[0].device
-            if hasattr(opt, "lr_tensor"):
-                lr = opt.lr_tensor().to(torch.float32)
-            else:
-                lr = torch.tensor([opt.param_groups[0].get("lr", 1.0)], dtype=torch.float32, device=dev)
-            sharded = [getattr(p, "_mmrec_sharded", False) for p in params]
-            if any(sharded):
-                # item-range sharded feature tables: their rows' squares are summed over the group
-                from . import parallel
-                grp = getattr(model, "_table_group", None)
-                numel = float(sum(getattr(p, "_mmrec_global_numel", p.numel()) for p in params))
-                g2 = parallel.sharded_sumsq([g for g, s in zip(grads, sharded) if not s],
-                                            [g for g, s in zip(grads, sharded) if s], grp)
-                p2 = parallel.sharded_sumsq([p.detach() for p, s in zip(params, sharded) if not s],
-                                            [p.detach() for p, s in zip(params, sharded) if s], grp)
-            else:
+            from .optim import axpy_multi, mirror_coef
+            if fused:
+                # one pass over (theta, g) for both RMS values + the scalar arithmetic on the device
                 numel = float(sum(g.numel() for g in grads))
-                g2 = torch.stack(torch._foreach_norm(grads)).pow(2).sum()
-                p2 = torch.stack(torch._foreach_norm([p.detach() for p in params])).pow(2).sum()
-            grad_rms = (g2 / numel).sqrt()
-            param_rms = (p2 / numel).sqrt() + 1e-12
-            alpha_eff = torch.clamp(self.mg_target_rel_step * param_rms / (lr * grad_rms + 1e-12),
-                                    min=alpha_base, max=alpha_base * self.mg_alpha_max_scale)
-            model._alpha_eff = alpha_eff                      # device scalar (logging only)
-            coef = (alpha_eff * lr).reshape(1).contiguous()
-            from .optim import axpy_multi
+                both = mirror_coef(params, grads, opt._hyper(opt.param_groups[0], params[0].device), numel,
+                                   alpha_base, self.mg_alpha_max_scale, self.mg_target_rel_step)
+                coef, model._alpha_eff = both[0:1], both[1]
+            else:
+                dev = params[0].device
+                if hasattr(opt, "lr_tensor"):
+                    lr = opt.lr_tensor().to(torch.float32)
+                else:
+                    lr = torch.tensor([opt.param_groups[0].get("lr", 1.0)], dtype=torch.float32, device=dev)
+                if any(sharded):
+                    # item-range sharded feature tables: their rows' squares are summed over the group
+                    from . import parallel
+                    grp = getattr(model, "_table_group", None)
+                    numel = float(sum(getattr(p, "_mmrec_global_numel", p.numel()) for p in params))
+                    g2 = parallel.sharded_sumsq([g for g, s in zip(grads, sharded) if not s],
+                                                [g for g, s in zip(grads, sharded) if s], grp)
+                    p2 = parallel.sharded_sumsq([p.detach() for p, s in zip(params, sharded) if not s],
+                                                [p.detach() for p, s in zip(params, sharded) if s], grp)
+                else:
+                    numel = float(sum(g.numel() for g in grads))
+                    g2 = torch.stack(torch._foreach_norm(grads)).pow(2).sum()
+                    p2 = torch.stack(torch._foreach_norm([p.detach() for p in params])).pow(2).sum()
+                grad_rms = (g2 / numel).sqrt()
+                param_rms = (p2 / numel).sqrt() + 1e-12
+                alpha_eff = torch.clamp(self.mg_target_rel_step * param_rms / (lr * grad_rms + 1e-12),
+                                        min=alpha_base, max=alpha_base * self.mg_alpha_max_scale)
+                model._alpha_eff = alpha_eff                      # device scalar (logging only)
+                coef = (alpha_eff * lr).reshape(1).contiguous()
             axpy_multi(params, grads, coef, sign=-1.0)        # theta' = theta - alpha_eff*lr*g
         opt.zero_grad(set_to_none=True)
         loss_mirror = loss_func(mirror_input)
         (sum(loss_mirror) if isinstance(loss_mirror, tuple) else loss_mirror).backward()
         beta = -float(getattr(model, "mg_beta", 0.2))
-        with torch.no_grad():
-            axpy_multi(params, grads, coef, sign=1.0)         # back to theta
-            if not hasattr(opt, "lr_tensor"):                 # plain torch optimizer
-                mg = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
-                torch._foreach_mul_(mg, beta)
-        if hasattr(opt, "lr_tensor"):
-            opt.step(grad_scale=beta)                         # FusedAdam scales the gradients as it reads them
+        every = all(p.grad is not None for p in params)
+        if fused and every:
+            # back to theta inside the Adam pass (same fmaf as the axpy), gradients scaled as they are read
+            opt.step(grad_scale=beta, undo=({p: g for p, g in zip(params, grads)}, coef))
         else:
-            opt.step()
+            with torch.no_grad():
+                axpy_multi(params, grads, coef, sign=1.0)         # back to theta
+                if not hasattr(opt, "lr_tensor"):                 # plain torch optimizer
+                    mg = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
+                    torch._foreach_mul_(mg, beta)
+            if hasattr(opt, "lr_tensor"):
+                opt.step(grad_scale=beta)                         # FusedAdam scales the gradients as it reads them
+            else:
+                opt.step()
         opt.zero_grad(set_to_none=True)
 
     def _train_batch(self, interaction, batch_idx=0, loss_func=None):
