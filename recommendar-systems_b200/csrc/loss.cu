@@ -428,6 +428,13 @@ int infonce_bwd_launch(const float *V1n, const float *V2n, const float *ttl, int
 }
 
 }  // namespace
+
+// tcgen05 path for d = 64 (infonce_tc.cu)
+bool infonce_tc_enabled(int d);
+int infonce_fwd_tc(const float *V1n, const float *V2n, int batch, float inv_temp, int cap_splits, float *partial,
+                   float *ttl, float *loss_out, cudaStream_t stream);
+int infonce_bwd_tc(const float *V1n, const float *V2n, const float *ttl, int batch, float inv_temp, int cap_splits,
+                   const float *coef, float *dV1, float *dV2, int *splits_out, cudaStream_t stream);
 }  // namespace mmrec
 
 using namespace mmrec;
@@ -482,6 +489,8 @@ extern "C" int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d
   infonce_normalize_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(T1, T2, d, idx, batch, V1n, V2n,
                                                                            inv_norm);
   MMREC_CHECK_LAUNCH("infonce_normalize_kernel");
+  if (infonce_tc_enabled(d))
+    return infonce_fwd_tc(V1n, V2n, batch, inv_temp, infonce_splits(batch), partial, ttl, loss_out, stream);
   switch (d) {
     case 32: return infonce_fwd_launch<32>(V1n, V2n, batch, inv_temp, partial, ttl, loss_out, counter, stream);
     case 64: return infonce_fwd_launch<64>(V1n, V2n, batch, inv_temp, partial, ttl, loss_out, counter, stream);
@@ -503,6 +512,11 @@ extern "C" int mmrec_infonce_bwd_f32(const float *V1n, const float *V2n, const f
   MMREC_REQUIRE(aligned16(V1n) && aligned16(V2n) && aligned16(dV1_ws) && aligned16(dV2_ws) && aligned16(dT1) &&
                     aligned16(dT2), MMREC_E_ALIGN, "infonce_bwd: operands must be 16-byte aligned");
   int rc;
+  if (infonce_tc_enabled(d)) {
+    int used = n_splits;
+    rc = infonce_bwd_tc(V1n, V2n, ttl, batch, inv_temp, n_splits, coef, dV1_ws, dV2_ws, &used, stream);
+    n_splits = used;
+  } else
   switch (d) {
     case 32: rc = infonce_bwd_launch<32>(V1n, V2n, ttl, batch, inv_temp, n_splits, coef, dV1_ws, dV2_ws, stream); break;
     case 64: rc = infonce_bwd_launch<64>(V1n, V2n, ttl, batch, inv_temp, n_splits, coef, dV1_ws, dV2_ws, stream); break;
