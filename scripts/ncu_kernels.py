@@ -31,7 +31,12 @@ masks = torch.nn.functional.dropout(torch.ones(3, N, d, device=DEV), 0.1)
 side, content = torch.randn(N, d, device=DEV, requires_grad=True), torch.randn(N, d, device=DEV, requires_grad=True)
 bu = torch.randint(0, U, (2048,), device=DEV)
 bi = torch.randint(0, I, (2048,), device=DEV)
+img = torch.randn(I, d, device=DEV, requires_grad=True)
+txt = torch.randn(I, d, device=DEV, requires_grad=True)
+wsp = [torch.randn(d // 2 + 1, 2, device=DEV, requires_grad=True) for _ in range(3)]
+gsp = [torch.randn(I, d, device=DEV) for _ in range(3)]
 for rep in range(2):
+    torch.autograd.backward(ops.spectrum_convolution(img, txt, *wsp, True), gsp)
     ops.gemm(x, True, W, True, I, d, F, b)
     ops.gemm(dy, False, x, False, d, F, I)
     ops.gemm(dy, True, W, False, I, F, d)
