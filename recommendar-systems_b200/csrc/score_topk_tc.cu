@@ -3,9 +3,9 @@
 //
 // One CTA owns 128 users (the M = 128 rows of the MMA = the 128 TMEM lanes) and walks its item
 // range in tiles of 64 items. Warp roles:
-//   warps 4-7  producers : stream item rows from HBM/L2 (coalesced float4, prefetched one tile
-//                          ahead in registers), split every value into tf32 hi/lo and store both
-//                          halves into 128-byte-swizzled K-major shared-memory tiles;
+//   warps 4-7  producers : two independent groups stream item rows from HBM/L2 (coalesced float4,
+//                          one tile in flight per group), split every value into tf32 hi/lo and
+//                          store both halves into 128-byte-swizzled K-major shared-memory tiles;
 //   warp  8    MMA       : one elected thread issues tcgen05.mma kind::tf32, 3 x (d/8) per tile
 //                          (lo*hi + hi*lo + hi*hi -> fp32-accurate scores), accumulating in one of
 //                          four 64-column TMEM buffers; tcgen05.commit frees the smem stage and
@@ -144,7 +144,7 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
   const uint32_t smem_base = smem_u32(smem);
 
   if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 128); mbar_init(empty + s, 1); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 64); mbar_init(empty + s, 1); }
     for (int b = 0; b < kAcc; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
     fence_barrier_init();
   }
@@ -196,36 +196,41 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
 
   if (warp >= 4 && warp < 8) {
     // =============================== producers ===============================================
-    const int ptid = tid - 128;
-    float4 cur[C::VEC], nxt[C::VEC];
-    auto load_tile = [&](float4 (&dst)[C::VEC], int t) {
+    // Two independent groups of two warps; group g owns tiles g, g + 2, ... and keeps ONE batch of
+    // loads in flight (load -> wait -> split -> store). Prefetching the next tile into a second
+    // register set of the same threads ran at one tile per L2 round trip: the loads of both tiles
+    // share scoreboards, so waiting for the older one waited for the newer one too (same finding
+    // as gemm_tc05.cu). STAGES >= 2 = number of groups, so the parity waits cannot alias.
+    constexpr int GT = 64;                                   // threads per group
+    constexpr int VB = (kTileN * (D / 4) / GT) > 16 ? 16 : (kTileN * (D / 4) / GT);   // float4 per batch
+    constexpr int NB = kTileN * (D / 4) / GT / VB;           // batches per tile (2 for d = 128)
+    const int grp = (tid - 128) / GT, ptid = (tid - 128) % GT;
+    for (int t = grp; t < n_tiles; t += 2) {
       const int j0 = j_begin + t * kTileN;
-#pragma unroll
-      for (int i = 0; i < C::VEC; ++i) {
-        const int idx = ptid + 128 * i, row = idx / (D / 4), c4 = idx % (D / 4);
-        dst[i] = (j0 + row < j_end) ? ldg4(item_emb + (size_t)(j0 + row) * D + c4 * 4)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    load_tile(cur, 0);
-    for (int t = 0; t < n_tiles; ++t) {
-      if (t + 1 < n_tiles) load_tile(nxt, t + 1);
       const int s = t % C::STAGES;
-      mbar_wait(empty + s, ((t / C::STAGES) & 1) ^ 1);
       uint8_t *stage = smem + C::OFF_B + s * C::STAGE;
 #pragma unroll
-      for (int i = 0; i < C::VEC; ++i) {
-        const int idx = ptid + 128 * i, row = idx / (D / 4), c4 = idx % (D / 4);
-        float4 hi, lo;
-        split_tf32x4(cur[i], hi, lo);
-        const uint32_t off = (c4 / 8) * (kTileN * 128) + sw128_off(row, c4 % 8);
-        *reinterpret_cast<float4 *>(stage + off) = hi;
-        *reinterpret_cast<float4 *>(stage + C::B_HALF + off) = lo;
+      for (int nb = 0; nb < NB; ++nb) {
+        float4 v[VB];
+#pragma unroll
+        for (int i = 0; i < VB; ++i) {
+          const int idx = ptid + GT * (nb * VB + i), row = idx / (D / 4), c4 = idx % (D / 4);
+          v[i] = (j0 + row < j_end) ? ldg4(item_emb + (size_t)(j0 + row) * D + c4 * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (nb == 0) mbar_wait(empty + s, ((t / C::STAGES) & 1) ^ 1);
+#pragma unroll
+        for (int i = 0; i < VB; ++i) {
+          const int idx = ptid + GT * (nb * VB + i), row = idx / (D / 4), c4 = idx % (D / 4);
+          float4 hi, lo;
+          split_tf32x4(v[i], hi, lo);
+          const uint32_t off = (c4 / 8) * (kTileN * 128) + sw128_off(row, c4 % 8);
+          *reinterpret_cast<float4 *>(stage + off) = hi;
+          *reinterpret_cast<float4 *>(stage + C::B_HALF + off) = lo;
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(full + s);
-#pragma unroll
-      for (int i = 0; i < C::VEC; ++i) cur[i] = nxt[i];
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ==============================================

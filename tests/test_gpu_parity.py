@@ -615,6 +615,21 @@ def _nccl_worker(rank, world, port, out_dir):
         one = ops.score_mask_topk(want[:U].detach(), users, want[U:].detach().contiguous(), 50)
         many = par.sharded_score_topk(want[:U].detach(), users, want[U + lo: U + hi].detach().contiguous(), lo, 50)
         assert torch.equal(one, many)
+        # item-range sharded feature table on the library GEMMs
+        gen = torch.Generator().manual_seed(7)
+        table = torch.randn(I, 256, generator=gen).to(dev)
+        Wt, bt = (torch.randn(64, 256, generator=gen) * 0.05).to(dev), torch.randn(64, generator=gen).to(dev)
+        Gm = torch.randn(I, 64, generator=gen).to(dev)
+        rows = par.ShardedRows(I, rank, world)
+        xl = rows.local(table).clone().requires_grad_(True)
+        Wp, bp = Wt.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+        y = par.sharded_projection(xl, Wp, bp, rows)
+        tref, Wr, br = (t.double().requires_grad_(True) for t in (table, Wt, bt))
+        yr = torch.nn.functional.linear(tref, Wr, br)
+        (y * Gm).sum().backward()
+        (yr * Gm.double()).sum().backward()
+        assert rel(y, yr) < 1e-5 and rel(xl.grad, tref.grad[rows.lo: rows.hi]) < 1e-5
+        assert rel(Wp.grad, Wr.grad) < 1e-5 and rel(bp.grad, br.grad) < 1e-5
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
