@@ -334,6 +334,17 @@ int mmrec_score_mask_topk_simt_f32(const float *user_emb, const int64_t *users, 
 int mmrec_row_normalize_f32(const float *x, int32_t n_rows, int32_t d, float *out, void *stream);
 int mmrec_row_topk_f32(const float *mat, int32_t n_rows, int32_t n_cols, int64_t ld, int32_t k, float *out_val,
                        int32_t *out_idx, void *stream);
+/* out[N] = column sums of the row-major [M, N] matrix x (N % 4 == 0): the bias gradient
+ * `dy.sum(0)` of nn.Linear over a whole table (smore.py:257-259, mgcn.py:148-150 autograd);
+ * fixed summation order, one launch. */
+int mmrec_colsum_f32(const float *x, int32_t M, int32_t N, float *out, void *stream);
+/* SMORE residual modality injection (smore.py:269-272): o_m = item + scale * g_m for the image /
+ * text / fusion gates in one launch, and its autograd in one launch:
+ * d_item = d0 + d1 + d2, dg_m = scale * d_m. numel % 4 == 0, 16-byte aligned. */
+int mmrec_inject3_fwd_f32(const float *item, const float *g0, const float *g1, const float *g2, float scale,
+                          int64_t numel, float *o0, float *o1, float *o2, void *stream);
+int mmrec_inject3_bwd_f32(const float *d0, const float *d1, const float *d2, float scale, int64_t numel,
+                          float *d_item, float *dg0, float *dg1, float *dg2, void *stream);
 int mmrec_knn_weights_f32(const int32_t *idx, const float *val, int32_t n, int32_t k, int32_t mode, float *dis_ws,
                           float *out_vals, void *stream);
 

@@ -59,6 +59,9 @@ SIGNATURES = {
     "mmrec_mirror_coef_f32": (C.c_int, [_p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double, C.c_double,
                                         _p, _p, _p]),
     "mmrec_axpy_multi_f32": (C.c_int, [_p, _p, _p, _i32, _p, _f32, _p]),
+    "mmrec_inject3_fwd_f32": (C.c_int, [_p, _p, _p, _p, _f32, _i64, _p, _p, _p, _p]),
+    "mmrec_inject3_bwd_f32": (C.c_int, [_p, _p, _p, _f32, _i64, _p, _p, _p, _p, _p]),
+    "mmrec_colsum_f32": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "mmrec_row_normalize_f32": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "mmrec_row_topk_f32": (C.c_int, [_p, _i32, _i32, _i64, _i32, _p, _p, _p]),
     "mmrec_knn_weights_f32": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),

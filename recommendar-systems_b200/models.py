@@ -589,6 +589,9 @@ class SMORE(_MultiViewBase):
             image_item = item * self.gate_v(image_conv)
             text_item = item * self.gate_t(text_conv)
             fusion_item = item * self.gate_f(fusion_conv)
+        elif item.shape[1] % 4 == 0:
+            image_item, text_item, fusion_item = ops.inject3(
+                item, self.gate_v(image_conv), self.gate_t(text_conv), self.gate_f(fusion_conv), self.inject_scale)
         else:
             image_item = item + self.inject_scale * self.gate_v(image_conv)
             text_item = item + self.inject_scale * self.gate_t(text_conv)

@@ -391,6 +391,41 @@ def gemm(A, a_kcontig, B, b_kcontig, M, N, K, bias=None):
     return C
 
 
+class _Inject3(torch.autograd.Function):
+    """item + scale * g_m for three gates (smore.py:269-272), one launch each way."""
+
+    @staticmethod
+    def forward(ctx, item, g0, g1, g2, scale):
+        item, g0, g1, g2 = _f32c(item), _f32c(g0), _f32c(g1), _f32c(g2)
+        outs = [torch.empty_like(item) for _ in range(3)]
+        lib.call("mmrec_inject3_fwd_f32", lib.ptr(item), lib.ptr(g0), lib.ptr(g1), lib.ptr(g2), float(scale),
+                 item.numel(), lib.ptr(outs[0]), lib.ptr(outs[1]), lib.ptr(outs[2]), lib.stream())
+        ctx.scale = float(scale)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d0, d1, d2):
+        d0, d1, d2 = _f32c(d0), _f32c(d1), _f32c(d2)
+        outs = [torch.empty_like(d0) for _ in range(4)]
+        lib.call("mmrec_inject3_bwd_f32", lib.ptr(d0), lib.ptr(d1), lib.ptr(d2), ctx.scale, d0.numel(),
+                 lib.ptr(outs[0]), lib.ptr(outs[1]), lib.ptr(outs[2]), lib.ptr(outs[3]), lib.stream())
+        return outs[0], outs[1], outs[2], outs[3], None
+
+
+def inject3(item, g0, g1, g2, scale):
+    """(item + scale * g0, item + scale * g1, item + scale * g2) for [I, d] tensors, d % 4 == 0."""
+    lib.require_cuda(item, g0, g1, g2)
+    return _Inject3.apply(item, g0, g1, g2, scale)
+
+
+def colsum(x):
+    """x.sum(0) of a row-major [M, N] CUDA matrix (N % 4 == 0) in one launch (mmrec_colsum_f32)."""
+    x = _f32c(x)
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    lib.call("mmrec_colsum_f32", lib.ptr(x), x.shape[0], x.shape[1], lib.ptr(out), lib.stream())
+    return out
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, b):
@@ -407,7 +442,7 @@ class _Linear(torch.autograd.Function):
         N = W.shape[0]
         dx = gemm(dy, True, W, False, M, K, N) if ctx.needs_input_grad[0] else None
         dW = gemm(dy, False, x, False, N, K, M) if ctx.needs_input_grad[1] else None
-        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        db = colsum(dy) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dW, db
 
 
