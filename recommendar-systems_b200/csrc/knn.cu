@@ -172,24 +172,46 @@ extern "C" int mmrec_knn_weights_f32(const int32_t *idx, const float *val, int32
 // input is the [I, d] gradient that was just written: it comes from L2.
 namespace mmrec {
 namespace {
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 colsum4_kernel(const float *__restrict__ x, int M, int N, float *__restrict__ out) {
-  __shared__ float4 sh[256];
+  __shared__ float4 sh[32];
   const int c0 = blockIdx.x * 4;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = threadIdx.x; r < M; r += 256) {
-    const float4 v = ldg4(x + (size_t)r * N + c0);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-  }
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      const float4 a = sh[threadIdx.x], b = sh[threadIdx.x + o];
-      sh[threadIdx.x] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  // 1024 threads: ~7 rows each at I = 7050, four independent partial sums -> two memory round trips
+  float4 s[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int r = threadIdx.x;
+  for (; r + 3 * 1024 < M; r += 4 * 1024) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 v = ldg4(x + (size_t)(r + u * 1024) * N + c0);
+      s[u].x += v.x; s[u].y += v.y; s[u].z += v.z; s[u].w += v.w;
     }
-    __syncthreads();
   }
+  for (int u = 0; r < M; r += 1024, ++u) {
+    const float4 v = ldg4(x + (size_t)r * N + c0);
+    s[u & 3].x += v.x; s[u & 3].y += v.y; s[u & 3].z += v.z; s[u & 3].w += v.w;
+  }
+  float4 t = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
+                         (s[0].z + s[1].z) + (s[2].z + s[3].z), (s[0].w + s[1].w) + (s[2].w + s[3].w));
+  auto warp_sum4 = [](float4 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+      v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+      v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+      v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+    }
+    return v;
+  };
+  t = warp_sum4(t);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    t = warp_sum4(sh[threadIdx.x]);
+    if (threadIdx.x == 0) sh[0] = t;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) *reinterpret_cast<float4 *>(out + c0) = sh[0];
 }
 }  // namespace
@@ -199,7 +221,7 @@ extern "C" int mmrec_colsum_f32(const float *x, int32_t M, int32_t N, float *out
   MMREC_REQUIRE(x && out, MMREC_E_BADARG, "colsum: null pointer");
   MMREC_REQUIRE(M > 0 && N > 0 && N % 4 == 0, MMREC_E_BADARG, "colsum: need M > 0 and N %% 4 == 0");
   MMREC_REQUIRE(aligned16(x) && aligned16(out), MMREC_E_ALIGN, "colsum: operands must be 16-byte aligned");
-  colsum4_kernel<<<N / 4, 256, 0, (cudaStream_t)stream_>>>(x, M, N, out);
+  colsum4_kernel<<<N / 4, 1024, 0, (cudaStream_t)stream_>>>(x, M, N, out);
   MMREC_CHECK_LAUNCH("colsum4_kernel");
   return MMREC_OK;
 }
