@@ -166,122 +166,3 @@ extern "C" int mmrec_knn_weights_f32(const int32_t *idx, const float *val, int32
   return MMREC_OK;
 }
 
-// ---- column sums: the bias gradient db = dy.sum(0) of the table projections -------------------
-// (smore.py:257-259 autograd). One CTA per 4 columns, rows strided over the threads, fixed-order
-// tree in shared memory: one launch, no atomics, no counters (safe on concurrent streams). The
-// input is the [I, d] gradient that was just written: it comes from L2.
-namespace mmrec {
-namespace {
-__global__ void __launch_bounds__(1024)
-colsum4_kernel(const float *__restrict__ x, int M, int N, float *__restrict__ out) {
-  __shared__ float4 sh[32];
-  const int c0 = blockIdx.x * 4;
-  // 1024 threads: ~7 rows each at I = 7050, four independent partial sums -> two memory round trips
-  float4 s[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int r = threadIdx.x;
-  for (; r + 3 * 1024 < M; r += 4 * 1024) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float4 v = ldg4(x + (size_t)(r + u * 1024) * N + c0);
-      s[u].x += v.x; s[u].y += v.y; s[u].z += v.z; s[u].w += v.w;
-    }
-  }
-  for (int u = 0; r < M; r += 1024, ++u) {
-    const float4 v = ldg4(x + (size_t)r * N + c0);
-    s[u & 3].x += v.x; s[u & 3].y += v.y; s[u & 3].z += v.z; s[u & 3].w += v.w;
-  }
-  float4 t = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
-                         (s[0].z + s[1].z) + (s[2].z + s[3].z), (s[0].w + s[1].w) + (s[2].w + s[3].w));
-  auto warp_sum4 = [](float4 v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-      v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-      v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
-      v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
-    }
-    return v;
-  };
-  t = warp_sum4(t);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    t = warp_sum4(sh[threadIdx.x]);
-    if (threadIdx.x == 0) sh[0] = t;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) *reinterpret_cast<float4 *>(out + c0) = sh[0];
-}
-}  // namespace
-}  // namespace mmrec
-
-extern "C" int mmrec_colsum_f32(const float *x, int32_t M, int32_t N, float *out, void *stream_) {
-  MMREC_REQUIRE(x && out, MMREC_E_BADARG, "colsum: null pointer");
-  MMREC_REQUIRE(M > 0 && N > 0 && N % 4 == 0, MMREC_E_BADARG, "colsum: need M > 0 and N %% 4 == 0");
-  MMREC_REQUIRE(aligned16(x) && aligned16(out), MMREC_E_ALIGN, "colsum: operands must be 16-byte aligned");
-  colsum4_kernel<<<N / 4, 1024, 0, (cudaStream_t)stream_>>>(x, M, N, out);
-  MMREC_CHECK_LAUNCH("colsum4_kernel");
-  return MMREC_OK;
-}
-
-// ---- modality injection: item + scale * gate_m, m = image / text / fusion (smore.py:269-272) ----
-// Three axpys forward and, in autograd, three scalings plus a three-way sum backward: 12 torch
-// launches per pass; here one launch each way over the [I, d] tensors.
-namespace mmrec {
-namespace {
-__global__ void __launch_bounds__(256)
-inject3_fwd_kernel(const float4 *__restrict__ item, const float4 *__restrict__ g0, const float4 *__restrict__ g1,
-                   const float4 *__restrict__ g2, float scale, int64_t n4, float4 *__restrict__ o0,
-                   float4 *__restrict__ o1, float4 *__restrict__ o2) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n4) return;
-  const float4 it = item[i], a = g0[i], b = g1[i], c = g2[i];
-  // item + (scale * gate): the product is rounded first, like torch's mul followed by add
-  o0[i] = make_float4(it.x + __fmul_rn(scale, a.x), it.y + __fmul_rn(scale, a.y), it.z + __fmul_rn(scale, a.z), it.w + __fmul_rn(scale, a.w));
-  o1[i] = make_float4(it.x + __fmul_rn(scale, b.x), it.y + __fmul_rn(scale, b.y), it.z + __fmul_rn(scale, b.z), it.w + __fmul_rn(scale, b.w));
-  o2[i] = make_float4(it.x + __fmul_rn(scale, c.x), it.y + __fmul_rn(scale, c.y), it.z + __fmul_rn(scale, c.z), it.w + __fmul_rn(scale, c.w));
-}
-__global__ void __launch_bounds__(256)
-inject3_bwd_kernel(const float4 *__restrict__ d0, const float4 *__restrict__ d1, const float4 *__restrict__ d2,
-                   float scale, int64_t n4, float4 *__restrict__ d_item, float4 *__restrict__ dg0,
-                   float4 *__restrict__ dg1, float4 *__restrict__ dg2) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n4) return;
-  const float4 a = d0[i], b = d1[i], c = d2[i];
-  d_item[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
-  dg0[i] = make_float4(scale * a.x, scale * a.y, scale * a.z, scale * a.w);
-  dg1[i] = make_float4(scale * b.x, scale * b.y, scale * b.z, scale * b.w);
-  dg2[i] = make_float4(scale * c.x, scale * c.y, scale * c.z, scale * c.w);
-}
-}  // namespace
-}  // namespace mmrec
-
-extern "C" int mmrec_inject3_fwd_f32(const float *item, const float *g0, const float *g1, const float *g2, float scale,
-                                     int64_t numel, float *o0, float *o1, float *o2, void *stream_) {
-  MMREC_REQUIRE(item && g0 && g1 && g2 && o0 && o1 && o2, MMREC_E_BADARG, "inject3_fwd: null pointer");
-  MMREC_REQUIRE(numel > 0 && numel % 4 == 0, MMREC_E_BADARG, "inject3_fwd: numel must be a positive multiple of 4");
-  MMREC_REQUIRE(aligned16(item) && aligned16(g0) && aligned16(g1) && aligned16(g2) && aligned16(o0) && aligned16(o1) &&
-                    aligned16(o2), MMREC_E_ALIGN, "inject3_fwd: operands must be 16-byte aligned");
-  const int64_t n4 = numel / 4;
-  inject3_fwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
-      (const float4 *)item, (const float4 *)g0, (const float4 *)g1, (const float4 *)g2, scale, n4, (float4 *)o0,
-      (float4 *)o1, (float4 *)o2);
-  MMREC_CHECK_LAUNCH("inject3_fwd_kernel");
-  return MMREC_OK;
-}
-
-extern "C" int mmrec_inject3_bwd_f32(const float *d0, const float *d1, const float *d2, float scale, int64_t numel,
-                                     float *d_item, float *dg0, float *dg1, float *dg2, void *stream_) {
-  MMREC_REQUIRE(d0 && d1 && d2 && d_item && dg0 && dg1 && dg2, MMREC_E_BADARG, "inject3_bwd: null pointer");
-  MMREC_REQUIRE(numel > 0 && numel % 4 == 0, MMREC_E_BADARG, "inject3_bwd: numel must be a positive multiple of 4");
-  MMREC_REQUIRE(aligned16(d0) && aligned16(d1) && aligned16(d2) && aligned16(d_item) && aligned16(dg0) &&
-                    aligned16(dg1) && aligned16(dg2), MMREC_E_ALIGN, "inject3_bwd: operands must be 16-byte aligned");
-  const int64_t n4 = numel / 4;
-  inject3_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
-      (const float4 *)d0, (const float4 *)d1, (const float4 *)d2, scale, n4, (float4 *)d_item, (float4 *)dg0,
-      (float4 *)dg1, (float4 *)dg2);
-  MMREC_CHECK_LAUNCH("inject3_bwd_kernel");
-  return MMREC_OK;
-}

@@ -766,3 +766,77 @@ def test_row_topk_ties_and_short_rows():
     lib.call("mmrec_row_topk_f32", lib.ptr(m), 2, 8, 8, 3, lib.ptr(val), lib.ptr(idx), lib.stream())
     assert idx.cpu().tolist() == [[1, 2, 4], [0, 1, 2]]       # lower id first
     assert val.cpu().tolist() == [[3.0, 3.0, 3.0], [5.0, 5.0, 5.0]]
+
+
+# ------------------------------------------------------------------ small fused training-path ops
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N", [(7050, 64), (1, 4), (1025, 128), (4097, 32)])
+def test_colsum_matches_torch(M, N):
+    ops = pkg("ops")
+    x = torch.randn(M, N, generator=torch.Generator().manual_seed(41)).to(DEV)
+    assert rel(ops.colsum(x), x.double().sum(0)) < 2e-6
+
+
+@pytest.mark.gpu
+def test_inject3_forward_is_bitwise_torch_and_backward_matches():
+    """smore.py:269-272: item + 0.7 * gate for the three modality gates."""
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(43)
+    item = torch.randn(333, 64, generator=gen).to(DEV).requires_grad_(True)
+    gates = [torch.rand(333, 64, generator=gen).to(DEV).requires_grad_(True) for _ in range(3)]
+    outs = ops.inject3(item, *gates, 0.7)
+    want = [item + 0.7 * g for g in gates]
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w)
+    ws = [torch.randn(333, 64, generator=gen).to(DEV) for _ in range(3)]
+    sum((o * w).sum() for o, w in zip(outs, ws)).backward()
+    got = [item.grad.clone()] + [g.grad.clone() for g in gates]
+    item.grad = None
+    for g in gates:
+        g.grad = None
+    sum((o * w).sum() for o, w in zip(want, ws)).backward()
+    assert rel(got[0], item.grad) < 1e-6
+    for a, g in zip(got[1:], gates):
+        assert torch.equal(a, g.grad)
+
+
+@pytest.mark.gpu
+def test_mirror_coef_and_adam_undo_match_the_unfused_sequence():
+    """trainer.py:289-335: alpha_eff / coef from one pass, and Adam that first returns from the
+    mirror point, against the torch expression + separate axpy + plain fused Adam."""
+    opt_m = pkg("optim")
+    gen = torch.Generator().manual_seed(47)
+    shapes = [(300, 64), (64,), (4099, 33), (7,)]
+    params = [torch.randn(*s, generator=gen).to(DEV) for s in shapes]
+    grads = [(torch.randn(*s, generator=gen) * 0.01).to(DEV) for s in shapes]
+    lr, alpha, max_scale, target = 1e-3, 0.5, 20.0, 1e-3
+    hyper = torch.tensor([lr, 0.0], dtype=torch.float64, device=DEV)
+    numel = float(sum(p.numel() for p in params))
+    both = opt_m.mirror_coef(params, grads, hyper, numel, alpha, max_scale, target)
+    g2 = torch.stack(torch._foreach_norm(grads)).pow(2).sum()
+    p2 = torch.stack(torch._foreach_norm(params)).pow(2).sum()
+    lr_t = torch.tensor([lr], dtype=torch.float32, device=DEV)
+    alpha_eff = torch.clamp(target * ((p2 / numel).sqrt() + 1e-12) / (lr_t * (g2 / numel).sqrt() + 1e-12),
+                            min=alpha, max=alpha * max_scale)
+    assert abs(float(both[1]) - float(alpha_eff)) / float(alpha_eff) < 1e-5
+    assert abs(float(both[0]) - float(alpha_eff * lr_t)) / float(alpha_eff * lr_t) < 1e-5
+    # Adam with the undo fused == axpy back, then Adam
+    coef = both[0:1].contiguous()
+    new_grads = [(torch.randn(*s, generator=gen) * 0.01).to(DEV) for s in shapes]
+
+    def run(fused):
+        ps = [torch.nn.Parameter(p.clone()) for p in params]
+        opt = opt_m.FusedAdam(ps, lr=lr)
+        for p, g in zip(ps, new_grads):
+            p.grad = g.clone()
+        with torch.no_grad():
+            opt_m.axpy_multi(ps, grads, coef, sign=-1.0)             # to the mirror point
+            if fused:
+                opt.step(grad_scale=-0.2, undo=({p: g for p, g in zip(ps, grads)}, coef))
+            else:
+                opt_m.axpy_multi(ps, grads, coef, sign=1.0)
+                opt.step(grad_scale=-0.2)
+        return [p.detach().clone() for p in ps]
+
+    for a, b in zip(run(True), run(False)):
+        assert torch.equal(a, b)
