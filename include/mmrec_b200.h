@@ -228,6 +228,18 @@ int mmrec_dense_act_fwd_f32(const float *X, const float *W, const float *bias, f
 int mmrec_dense_act_bwd_f32(const float *dY, const float *Y, const float *X, const float *W,
                             float *dX, float *dW, float *db, float *ws, int32_t M, int32_t K,
                             int32_t N, int32_t act, void *stream);
+/* The same two operations for n_batch <= 4 independent layers of one shape and activation in one
+ * launch each (SMORE's gate_v / gate_t / gate_f, smore.py:269-272; MGCN's gates mgcn.py:153-154).
+ * Pointer arrays are HOST arrays of n_batch device pointers (bias / dX / db entries may be NULL);
+ * ws holds n_batch * mmrec_dense_act_bwd_workspace_bytes(K, N) bytes. */
+int mmrec_dense_act_batch_fwd_f32(const float *const *X_host, const float *const *W_host,
+                                  const float *const *bias_host, float *const *Y_host, int32_t n_batch,
+                                  int32_t M, int32_t K, int32_t N, int32_t act, void *stream);
+int mmrec_dense_act_batch_bwd_f32(const float *const *dY_host, const float *const *Y_host,
+                                  const float *const *X_host, const float *const *W_host,
+                                  float *const *dX_host, float *const *dW_host, float *const *db_host,
+                                  float *ws, int32_t n_batch, int32_t M, int32_t K, int32_t N, int32_t act,
+                                  void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * SMORE modality-aware preference module, fused (K14). Replaces smore.py:321-341 -- query_v /

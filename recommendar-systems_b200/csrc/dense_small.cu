@@ -33,11 +33,26 @@ struct EpiBiasAct {
   }
 };
 
+// Up to kMaxBatch independent layers of the same shape and activation go out as ONE launch
+// (blockIdx.y = layer): SMORE's three modality gates gate_v / gate_t / gate_f (smore.py:269-272)
+// are 7050-row problems of half a wave each -- launch-bound one by one.
+constexpr int kMaxBatch = 4;
+struct FwdBatch {
+  const float *X[kMaxBatch], *W[kMaxBatch], *bias[kMaxBatch];
+  float *Y[kMaxBatch];
+};
+struct BwdBatch {
+  const float *dY[kMaxBatch], *Y[kMaxBatch], *X[kMaxBatch], *W[kMaxBatch];
+  float *dX[kMaxBatch], *partial[kMaxBatch], *dW[kMaxBatch], *db[kMaxBatch];
+};
+
 template <int K, int N, int TM, int ACT>
 __global__ void __launch_bounds__(kT, K <= 64 ? 3 : 2)
-dense_fwd_kernel(const float *__restrict__ X, const float *__restrict__ W, const float *__restrict__ bias,
-                 float *__restrict__ Y, int M, int n_tiles) {
+dense_fwd_kernel(const __grid_constant__ FwdBatch B, int M, int n_tiles) {
   using T = Tile<K, N, TM>;
+  const float *__restrict__ X = B.X[blockIdx.y], *__restrict__ W = B.W[blockIdx.y],
+                           *__restrict__ bias = B.bias[blockIdx.y];
+  float *__restrict__ Y = B.Y[blockIdx.y];
   extern __shared__ float4 smem4[];
   float *Ws = reinterpret_cast<float *>(smem4);      // [K][N + 8]   Ws[k][n] = W[n][k]
   float *Xs = Ws + K * (N + kWP);                    // [BM][K + 4]
@@ -76,10 +91,11 @@ dense_fwd_kernel(const float *__restrict__ X, const float *__restrict__ W, const
 // Backward. partial layout per CTA: [N*K] dW then [N] db.
 template <int K, int N, int TM, int ACT>
 __global__ void __launch_bounds__(kT, K <= 64 ? 3 : 1)
-dense_bwd_kernel(const float *__restrict__ dY, const float *__restrict__ Y, const float *__restrict__ X,
-                 const float *__restrict__ W, float *__restrict__ dX, float *__restrict__ partial, int M,
-                 int n_tiles) {
+dense_bwd_kernel(const __grid_constant__ BwdBatch B, int M, int n_tiles) {
   constexpr int CGK = K / 4, RGK = kT / CGK, BM = RGK * TM;
+  const float *__restrict__ dY = B.dY[blockIdx.y], *__restrict__ Y = B.Y[blockIdx.y],
+                           *__restrict__ X = B.X[blockIdx.y], *__restrict__ W = B.W[blockIdx.y];
+  float *__restrict__ dX = B.dX[blockIdx.y], *__restrict__ partial = B.partial[blockIdx.y];
   extern __shared__ float4 smem4[];
   float *Wn = reinterpret_cast<float *>(smem4);     // [N][K + 8]   natural layout (n-major)
   float *Zs = Wn + N * (K + kWP);                   // [BM][N + 4]  dZ tile
@@ -136,9 +152,10 @@ dense_bwd_kernel(const float *__restrict__ dY, const float *__restrict__ Y, cons
 // 16 thread rows each summing every 16th partial (independent coalesced loads), combined in a
 // fixed order through shared memory: deterministic, and two memory round trips deep.
 __global__ void __launch_bounds__(1024)
-dense_partial_reduce_kernel(const float *__restrict__ partial, int n_parts, int n_w, int n_b,
-                            float *__restrict__ dW, float *__restrict__ db) {
+dense_partial_reduce_kernel(const __grid_constant__ BwdBatch B, int n_parts, int n_w, int n_b) {
   __shared__ float sm[16][64];
+  const float *__restrict__ partial = B.partial[blockIdx.y];
+  float *__restrict__ dW = B.dW[blockIdx.y], *__restrict__ db = B.db[blockIdx.y];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int j = blockIdx.x * 64 + tx;
   const size_t stride = (size_t)n_w + n_b;
@@ -171,7 +188,7 @@ template <int D, int TM>
 constexpr size_t bwd_smem() { return sizeof(float) * (D * (D + kWP) + 2 * Tile<D, D, TM>::BM * (D + 4)); }
 
 template <int D, int ACT>
-int launch_fwd(const float *X, const float *W, const float *b, float *Y, int M, cudaStream_t st) {
+int launch_fwd(const FwdBatch &B, int n_batch, int M, cudaStream_t st) {
   constexpr int TM = RowsPerThread<D>::value;
   using T = Tile<D, D, TM>;
   constexpr size_t smem = fwd_smem<D, TM>();
@@ -182,14 +199,13 @@ int launch_fwd(const float *X, const float *W, const float *b, float *Y, int M, 
   }
   const int n_tiles = (M + T::BM - 1) / T::BM;
   const int grid = min(n_tiles, 8 * kNumSMs);
-  dense_fwd_kernel<D, D, TM, ACT><<<grid, kT, smem, st>>>(X, W, b, Y, M, n_tiles);
+  dense_fwd_kernel<D, D, TM, ACT><<<dim3(grid, n_batch), kT, smem, st>>>(B, M, n_tiles);
   MMREC_CHECK_LAUNCH("dense_fwd_kernel");
   return MMREC_OK;
 }
 
 template <int D, int ACT>
-int launch_bwd(const float *dY, const float *Y, const float *X, const float *W, float *dX, float *dW, float *db,
-               float *ws, int M, cudaStream_t st) {
+int launch_bwd(BwdBatch B, int n_batch, float *ws, int M, cudaStream_t st) {
   constexpr int TM = RowsPerThread<D>::value;
   using T = Tile<D, D, TM>;
   constexpr size_t smem = bwd_smem<D, TM>();
@@ -200,10 +216,11 @@ int launch_bwd(const float *dY, const float *Y, const float *X, const float *W, 
   }
   const int n_tiles = (M + T::BM - 1) / T::BM;
   const int grid = max(1, min(n_tiles, kMaxParts));
-  dense_bwd_kernel<D, D, TM, ACT><<<grid, kT, smem, st>>>(dY, Y, X, W, dX, ws, M, n_tiles);
+  for (int i = 0; i < n_batch; ++i) B.partial[i] = ws + (size_t)i * kMaxParts * (D * D + D);
+  dense_bwd_kernel<D, D, TM, ACT><<<dim3(grid, n_batch), kT, smem, st>>>(B, M, n_tiles);
   MMREC_CHECK_LAUNCH("dense_bwd_kernel");
   const int n_out = D * D + D;
-  dense_partial_reduce_kernel<<<(n_out + 63) / 64, 1024, 0, st>>>(ws, grid, D * D, D, dW, db);
+  dense_partial_reduce_kernel<<<dim3((n_out + 63) / 64, n_batch), 1024, 0, st>>>(B, grid, D * D, D);
   MMREC_CHECK_LAUNCH("dense_partial_reduce_kernel");
   return MMREC_OK;
 }
@@ -244,7 +261,29 @@ extern "C" int mmrec_dense_act_fwd_f32(const float *X, const float *W, const flo
                 "dense_act_fwd: operands must be 16-byte aligned");
   if (M == 0) return MMREC_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  MMREC_DENSE_DISPATCH(launch_fwd, X, W, bias, Y, M, st);
+  FwdBatch B{};
+  B.X[0] = X; B.W[0] = W; B.bias[0] = bias; B.Y[0] = Y;
+  MMREC_DENSE_DISPATCH(launch_fwd, B, 1, M, st);
+  return MMREC_E_BADARG;
+}
+
+extern "C" int mmrec_dense_act_batch_fwd_f32(const float *const *X_host, const float *const *W_host,
+                                             const float *const *bias_host, float *const *Y_host, int32_t n_batch,
+                                             int32_t M, int32_t K, int32_t N, int32_t act, void *stream) {
+  MMREC_REQUIRE(X_host && W_host && bias_host && Y_host, MMREC_E_BADARG, "dense_act_batch_fwd: null pointer");
+  MMREC_REQUIRE(n_batch >= 1 && n_batch <= kMaxBatch, MMREC_E_BADARG, "dense_act_batch_fwd: 1 <= n_batch <= %d", kMaxBatch);
+  MMREC_REQUIRE(mmrec_dense_act_supported(K, N), MMREC_E_BADARG,
+                "dense_act_batch_fwd: K = N in {32, 64, 128} required (got K=%d N=%d)", K, N);
+  MMREC_REQUIRE(act >= 0 && act <= 2 && M > 0, MMREC_E_BADARG, "dense_act_batch_fwd: bad act / M");
+  FwdBatch B{};
+  for (int i = 0; i < n_batch; ++i) {
+    B.X[i] = X_host[i]; B.W[i] = W_host[i]; B.bias[i] = bias_host[i]; B.Y[i] = Y_host[i];
+    MMREC_REQUIRE(B.X[i] && B.W[i] && B.Y[i], MMREC_E_BADARG, "dense_act_batch_fwd: null tensor %d", i);
+    MMREC_REQUIRE(aligned16(B.X[i]) && aligned16(B.W[i]) && aligned16(B.Y[i]) && aligned16(B.bias[i]), MMREC_E_ALIGN,
+                  "dense_act_batch_fwd: operands must be 16-byte aligned");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  MMREC_DENSE_DISPATCH(launch_fwd, B, n_batch, M, st);
   return MMREC_E_BADARG;
 }
 
@@ -264,6 +303,33 @@ extern "C" int mmrec_dense_act_bwd_f32(const float *dY, const float *Y, const fl
     if (db) MMREC_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
     return MMREC_OK;
   }
-  MMREC_DENSE_DISPATCH(launch_bwd, dY, Y, X, W, dX, dW, db, ws, M, st);
+  BwdBatch B{};
+  B.dY[0] = dY; B.Y[0] = Y; B.X[0] = X; B.W[0] = W; B.dX[0] = dX; B.dW[0] = dW; B.db[0] = db;
+  MMREC_DENSE_DISPATCH(launch_bwd, B, 1, ws, M, st);
+  return MMREC_E_BADARG;
+}
+
+extern "C" int mmrec_dense_act_batch_bwd_f32(const float *const *dY_host, const float *const *Y_host,
+                                             const float *const *X_host, const float *const *W_host,
+                                             float *const *dX_host, float *const *dW_host, float *const *db_host,
+                                             float *ws, int32_t n_batch, int32_t M, int32_t K, int32_t N, int32_t act,
+                                             void *stream) {
+  MMREC_REQUIRE(dY_host && Y_host && X_host && W_host && dX_host && dW_host && db_host && ws, MMREC_E_BADARG,
+                "dense_act_batch_bwd: null pointer");
+  MMREC_REQUIRE(n_batch >= 1 && n_batch <= kMaxBatch, MMREC_E_BADARG, "dense_act_batch_bwd: 1 <= n_batch <= %d", kMaxBatch);
+  MMREC_REQUIRE(mmrec_dense_act_supported(K, N), MMREC_E_BADARG,
+                "dense_act_batch_bwd: K = N in {32, 64, 128} required (got K=%d N=%d)", K, N);
+  MMREC_REQUIRE(act >= 0 && act <= 2 && M > 0, MMREC_E_BADARG, "dense_act_batch_bwd: bad act / M");
+  BwdBatch B{};
+  for (int i = 0; i < n_batch; ++i) {
+    B.dY[i] = dY_host[i]; B.Y[i] = Y_host[i]; B.X[i] = X_host[i]; B.W[i] = W_host[i];
+    B.dX[i] = dX_host[i]; B.dW[i] = dW_host[i]; B.db[i] = db_host[i];
+    MMREC_REQUIRE(B.dY[i] && B.X[i] && B.W[i] && B.dW[i] && (act == 0 || B.Y[i]), MMREC_E_BADARG,
+                  "dense_act_batch_bwd: null tensor %d", i);
+    MMREC_REQUIRE(aligned16(B.dY[i]) && aligned16(B.Y[i]) && aligned16(B.X[i]) && aligned16(B.W[i]) && aligned16(B.dX[i]),
+                  MMREC_E_ALIGN, "dense_act_batch_bwd: operands must be 16-byte aligned");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  MMREC_DENSE_DISPATCH(launch_bwd, B, n_batch, ws, M, st);
   return MMREC_E_BADARG;
 }

@@ -48,6 +48,8 @@ SIGNATURES = {
     "mmrec_dense_act_bwd_workspace_bytes": (_sz, [_i32, _i32]),
     "mmrec_dense_act_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "mmrec_dense_act_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "mmrec_dense_act_batch_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mmrec_dense_act_batch_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mmrec_smore_side_supported": (C.c_int, [_i32]),
     "mmrec_smore_side_bwd_workspace_bytes": (_sz, [_i32, _i32]),
     "mmrec_smore_side_fwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),

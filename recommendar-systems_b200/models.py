@@ -479,8 +479,9 @@ class MGCN(_MultiViewBase):
         image_feats = self._project(self.image_embedding, self.image_trs)
         text_feats = self._project(self.text_embedding, self.text_trs)
         item = self.item_id_embedding.weight
-        image_item = item * self.gate_v(image_feats)
-        text_item = item * self.gate_t(text_feats)
+        gv, gt = ops.dense_stack_batch((self.gate_v, self.gate_t), (image_feats, text_feats))
+        image_item = item * gv
+        text_item = item * gt
         ego = torch.cat([self.user_embedding.weight, item], dim=0)
         content = ops.propagate_mean(adj, ego, self.n_ui_layers)
         image_embeds, text_embeds = self._views((image_item, text_item),
@@ -488,8 +489,9 @@ class MGCN(_MultiViewBase):
         att = torch.cat([self.query_common(image_embeds), self.query_common(text_embeds)], dim=-1)
         w = self.softmax(att)
         common = w[:, 0].unsqueeze(1) * image_embeds + w[:, 1].unsqueeze(1) * text_embeds
-        sep_i = self.gate_image_prefer(content) * (image_embeds - common)
-        sep_t = self.gate_text_prefer(content) * (text_embeds - common)
+        pi, pt = ops.dense_stack_batch((self.gate_image_prefer, self.gate_text_prefer), (content, content))
+        sep_i = pi * (image_embeds - common)
+        sep_t = pt * (text_embeds - common)
         side = (sep_i + sep_t + common) / 3
         return content + side, side, content
 
@@ -586,12 +588,13 @@ class SMORE(_MultiViewBase):
         self._join(s_txt, text_feats)
         image_conv, text_conv, fusion_conv = self.spectrum_convolution(image_feats, text_feats)
         if self.inject_mode == "mul":
-            image_item = item * self.gate_v(image_conv)
-            text_item = item * self.gate_t(text_conv)
-            fusion_item = item * self.gate_f(fusion_conv)
+            gv, gt, gf = ops.dense_stack_batch((self.gate_v, self.gate_t, self.gate_f),
+                                               (image_conv, text_conv, fusion_conv))
+            image_item, text_item, fusion_item = item * gv, item * gt, item * gf
         elif item.shape[1] % 4 == 0:
-            image_item, text_item, fusion_item = ops.inject3(
-                item, self.gate_v(image_conv), self.gate_t(text_conv), self.gate_f(fusion_conv), self.inject_scale)
+            gv, gt, gf = ops.dense_stack_batch((self.gate_v, self.gate_t, self.gate_f),
+                                               (image_conv, text_conv, fusion_conv))
+            image_item, text_item, fusion_item = ops.inject3(item, gv, gt, gf, self.inject_scale)
         else:
             image_item = item + self.inject_scale * self.gate_v(image_conv)
             text_item = item + self.inject_scale * self.gate_t(text_conv)
@@ -614,9 +617,9 @@ class SMORE(_MultiViewBase):
             return all_e, side, content
         agg_image = self.softmax(self.query_v(fusion_embeds)) * image_embeds
         agg_text = self.softmax(self.query_t(fusion_embeds)) * text_embeds
-        image_prefer = self.dropout(self.gate_image_prefer(content))
-        text_prefer = self.dropout(self.gate_text_prefer(content))
-        fusion_prefer = self.dropout(self.gate_fusion_prefer(content))
+        pi, pt, pf = ops.dense_stack_batch(
+            (self.gate_image_prefer, self.gate_text_prefer, self.gate_fusion_prefer), (content, content, content))
+        image_prefer, text_prefer, fusion_prefer = self.dropout(pi), self.dropout(pt), self.dropout(pf)
         side = torch.mean(torch.stack([image_prefer * agg_image, text_prefer * agg_text,
                                        fusion_prefer * fusion_embeds]), dim=0)
         return content + side, side, content

@@ -510,6 +510,69 @@ def dense_act(x, W, b=None, act=None):
     return y if act is None else (torch.tanh(y) if act == "tanh" else torch.sigmoid(y))
 
 
+class _DenseActBatch(torch.autograd.Function):
+    """n independent act(F.linear(x_i, W_i, b_i)) of one shape in one launch each way.
+    apply(act, n, x_0.., W_0.., b_0..) -> n outputs."""
+
+    @staticmethod
+    def forward(ctx, act, n, *t):
+        xs = [_f32c(v) for v in t[:n]]
+        Ws = [_f32c(v) for v in t[n:2 * n]]
+        bs = [None if v is None else _f32c(v) for v in t[2 * n:3 * n]]
+        M, K = xs[0].shape
+        N = Ws[0].shape[0]
+        ys = [torch.empty(M, N, dtype=torch.float32, device=xs[0].device) for _ in range(n)]
+        lib.call("mmrec_dense_act_batch_fwd_f32", _ptr_array(xs), _ptr_array(Ws), _ptr_array(bs), _ptr_array(ys),
+                 n, M, K, N, act, lib.stream())
+        ctx.act, ctx.n, ctx.has_bias = act, n, [b is not None for b in bs]
+        ctx.save_for_backward(*xs, *Ws, *ys)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        n = ctx.n
+        t = ctx.saved_tensors
+        xs, Ws, ys = t[:n], t[n:2 * n], t[2 * n:3 * n]
+        M, K = xs[0].shape
+        N = Ws[0].shape[0]
+        dev = xs[0].device
+        dys = [torch.zeros(M, N, dtype=torch.float32, device=dev) if g is None else _f32c(g) for g in dys]
+        dxs = [torch.empty_like(x) if ctx.needs_input_grad[2 + i] else None for i, x in enumerate(xs)]
+        dWs = [torch.empty_like(W) for W in Ws]
+        dbs = [torch.empty(N, dtype=torch.float32, device=dev) if hb else None for hb in ctx.has_bias]
+        ws = torch.empty(n * (lib.load().mmrec_dense_act_bwd_workspace_bytes(K, N) // 4), dtype=torch.float32,
+                         device=dev)
+        lib.call("mmrec_dense_act_batch_bwd_f32", _ptr_array(dys), _ptr_array(ys), _ptr_array(xs), _ptr_array(Ws),
+                 _ptr_array(dxs), _ptr_array(dWs), _ptr_array(dbs), lib.ptr(ws), n, M, K, N, ctx.act, lib.stream())
+        return (None, None, *dxs, *dWs, *dbs)
+
+
+def dense_stack_batch(stacks, xs):
+    """[stack_i(x_i)] for DenseStacks that are each one Linear(d, d) (+ Tanh / Sigmoid) of the same
+    shape, as one batched launch (SMORE / MGCN modality gates); anything else runs stack by stack."""
+    def one_layer(st):
+        mods = list(st)
+        if not mods or not isinstance(mods[0], torch.nn.Linear) or len(mods) > 2:
+            return None
+        act = None
+        if len(mods) == 2:
+            act = "tanh" if isinstance(mods[1], torch.nn.Tanh) else "sigmoid" if isinstance(mods[1], torch.nn.Sigmoid) else 0
+            if act == 0:
+                return None
+        return mods[0], act
+    info = [one_layer(st) for st in stacks]
+    ok = (1 < len(stacks) <= 4 and all(i is not None for i in info) and len({i[1] for i in info}) == 1
+          and len({tuple(i[0].weight.shape) for i in info}) == 1 and len({tuple(x.shape) for x in xs}) == 1
+          and all(x.dim() == 2 and x.is_cuda for x in xs)
+          and lib.load().mmrec_dense_act_supported(info[0][0].weight.shape[1], info[0][0].weight.shape[0])
+          and len({i[0].bias is None for i in info}) == 1)
+    if not ok:
+        return [st(x) for st, x in zip(stacks, xs)]
+    lins = [i[0] for i in info]
+    return list(_DenseActBatch.apply(_ACT_CODE[info[0][1]], len(xs), *xs, *[l.weight for l in lins],
+                                     *[l.bias for l in lins]))
+
+
 class DenseStack(torch.nn.Sequential):
     """nn.Sequential of Linear / Tanh / Sigmoid with the reference's module indices (so the
     state_dict keys `gate_v.0.weight`, `query_v.2.weight` ... are unchanged) whose forward fuses

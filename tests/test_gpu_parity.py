@@ -840,3 +840,32 @@ def test_mirror_coef_and_adam_undo_match_the_unfused_sequence():
 
     for a, b in zip(run(True), run(False)):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("d,act,n", [(64, "sigmoid", 3), (32, "tanh", 2), (128, None, 4)])
+def test_dense_stack_batch_equals_single_launches(d, act, n):
+    """smore.py:269-272 / mgcn.py:153-154: the batched gate launch is bit-identical to one launch
+    per gate, forward and backward."""
+    ops = pkg("ops")
+    torch.manual_seed(51)
+    mods = {"sigmoid": torch.nn.Sigmoid, "tanh": torch.nn.Tanh}
+
+    def make():
+        layers = [ops.Linear(d, d)] + ([mods[act]()] if act else [])
+        return ops.DenseStack(*layers).to(DEV)
+    stacks = [make() for _ in range(n)]
+    gen = torch.Generator().manual_seed(53)
+    xs = [torch.randn(777, d, generator=gen).to(DEV).requires_grad_(True) for _ in range(n)]
+    gs = [torch.randn(777, d, generator=gen).to(DEV) for _ in range(n)]
+    ys = ops.dense_stack_batch(stacks, xs)
+    sum((y * g).sum() for y, g in zip(ys, gs)).backward()
+    got = [(y.detach().clone(), x.grad.clone(), st[0].weight.grad.clone(), st[0].bias.grad.clone())
+           for y, x, st in zip(ys, xs, stacks)]
+    for x, st in zip(xs, stacks):
+        x.grad = None
+        st.zero_grad()
+    for (y0, dx0, dw0, db0), x, st, g in zip(got, xs, stacks, gs):
+        y = st(x)
+        (y * g).sum().backward()
+        assert torch.equal(y, y0) and torch.equal(x.grad, dx0)
+        assert torch.equal(st[0].weight.grad, dw0) and torch.equal(st[0].bias.grad, db0)
