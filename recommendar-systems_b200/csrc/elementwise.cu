@@ -28,9 +28,13 @@ colsum4_kernel(const float *__restrict__ x, int M, int N, float *__restrict__ ou
       s[u].x += v.x; s[u].y += v.y; s[u].z += v.z; s[u].w += v.w;
     }
   }
-  for (int u = 0; r < M; r += 1024, ++u) {
-    const float4 v = ldg4(x + (size_t)r * N + c0);
-    s[u & 3].x += v.x; s[u & 3].y += v.y; s[u & 3].z += v.z; s[u & 3].w += v.w;
+  {   // up to three more rows per thread: issue the loads together, statically indexed accumulators
+    float4 v[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      v[u] = r + u * 1024 < M ? ldg4(x + (size_t)(r + u * 1024) * N + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) { s[u].x += v[u].x; s[u].y += v[u].y; s[u].z += v[u].z; s[u].w += v[u].w; }
   }
   float4 t = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
                          (s[0].z + s[1].z) + (s[2].z + s[3].z), (s[0].w + s[1].w) + (s[2].w + s[3].w));
