@@ -14,6 +14,8 @@
 // tiles and emits dF, dV, dT, dC plus per-CTA dW/db partials summed in a fixed order (no
 // floating-point atomics). fp32 FMA arithmetic throughout: 7 (fwd) + 14 (bwd) x n*d*d MACs, so
 // the kernels are FMA-bound (Baby: 0.76 / 1.5 GFMA), not HBM-bound.
+#include <stdlib.h>
+
 #include "dense_tile.cuh"
 
 namespace mmrec {
@@ -432,7 +434,9 @@ constexpr size_t side_bwd_smem() { return sizeof(float) * (D * Cfg<D>::PW + 5 * 
 
 inline int side_parts(int n, int d) {
   const int bm = (kT / (d / 4)) * 4;
-  return max(1, min((n + bm - 1) / bm, kMaxSideParts));
+  // backward CTAs = dW / db partial slabs: two resident CTAs per SM loop over the tiles (MMREC_SIDE_PARTS overrides)
+  static const int cap = getenv("MMREC_SIDE_PARTS") ? atoi(getenv("MMREC_SIDE_PARTS")) : kMaxSideParts;
+  return max(1, min(min((n + bm - 1) / bm, kMaxSideParts), cap));
 }
 
 template <int D>
