@@ -357,6 +357,15 @@ int mmrec_inject3_fwd_f32(const float *item, const float *g0, const float *g1, c
                           int64_t numel, float *o0, float *o1, float *o2, void *stream);
 int mmrec_inject3_bwd_f32(const float *d0, const float *d1, const float *d2, float scale, int64_t numel,
                           float *d_item, float *dg0, float *dg1, float *dg2, void *stream);
+/* Loss head of MGCN / SMORE (mgcn.py:241-253, smore.py:396-411):
+ *   out[0] = o2[0] * inv_batch + reg_weight * (o2[1] * inv_train_batch_size) + cl_weight * (cl2[0] + cl2[1])
+ * with o2 = mmrec_bpr_fwd_f32's two sums and cl2 = the two InfoNCE losses (device scalars), in the
+ * float32 operation order of the reference's tensor expression; and its gradient for a device
+ * scalar g: d_o2 = (g * inv_batch, g * reg_weight * inv_train_batch_size), d_cl2 = (g * cl_weight) x 2. */
+int mmrec_loss_head_fwd_f32(const float *o2, const float *cl2, float inv_batch, float reg_weight,
+                            float inv_train_batch_size, float cl_weight, float *out, void *stream);
+int mmrec_loss_head_bwd_f32(const float *g, float inv_batch, float reg_weight, float inv_train_batch_size,
+                            float cl_weight, float *d_o2, float *d_cl2, void *stream);
 int mmrec_knn_weights_f32(const int32_t *idx, const float *val, int32_t n, int32_t k, int32_t mode, float *dis_ws,
                           float *out_vals, void *stream);
 

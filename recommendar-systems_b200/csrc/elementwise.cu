@@ -129,3 +129,47 @@ extern "C" int mmrec_inject3_bwd_f32(const float *d0, const float *d1, const flo
   MMREC_CHECK_LAUNCH("inject3_bwd_kernel");
   return MMREC_OK;
 }
+
+// ---- loss head of MGCN / SMORE (mgcn.py:241-253, smore.py:396-411) ------------------------------
+//   loss = bpr_sum / B + reg_weight * (reg_sum / train_batch_size) + cl_loss * (cl_items + cl_users)
+// Six scalar torch kernels forward and as many backward, per pass; one single-thread launch each
+// way here. Same float32 operations in the same order as the tensor expression (torch divides by a
+// host scalar as a multiplication by its float32 reciprocal), so the value is bit-identical.
+namespace mmrec {
+namespace {
+__global__ void loss_head_fwd_kernel(const float *__restrict__ o2, const float *__restrict__ cl2, float inv_b,
+                                     float rw, float inv_bs, float clw, float *__restrict__ out) {
+  const float bpr = __fmul_rn(o2[0], inv_b);
+  const float reg = __fmul_rn(rw, __fmul_rn(o2[1], inv_bs));
+  const float cl = __fmul_rn(clw, __fadd_rn(cl2[0], cl2[1]));
+  out[0] = __fadd_rn(__fadd_rn(bpr, reg), cl);
+}
+__global__ void loss_head_bwd_kernel(const float *__restrict__ g, float inv_b, float rw, float inv_bs, float clw,
+                                     float *__restrict__ d_o2, float *__restrict__ d_cl2) {
+  const float gg = g[0];
+  d_o2[0] = __fmul_rn(gg, inv_b);
+  d_o2[1] = __fmul_rn(__fmul_rn(gg, rw), inv_bs);
+  const float c = __fmul_rn(gg, clw);
+  d_cl2[0] = c;
+  d_cl2[1] = c;
+}
+}  // namespace
+}  // namespace mmrec
+
+extern "C" int mmrec_loss_head_fwd_f32(const float *o2, const float *cl2, float inv_batch, float reg_weight,
+                                       float inv_train_batch_size, float cl_weight, float *out, void *stream_) {
+  MMREC_REQUIRE(o2 && cl2 && out, MMREC_E_BADARG, "loss_head_fwd: null pointer");
+  loss_head_fwd_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(o2, cl2, inv_batch, reg_weight, inv_train_batch_size,
+                                                          cl_weight, out);
+  MMREC_CHECK_LAUNCH("loss_head_fwd_kernel");
+  return MMREC_OK;
+}
+
+extern "C" int mmrec_loss_head_bwd_f32(const float *g, float inv_batch, float reg_weight, float inv_train_batch_size,
+                                       float cl_weight, float *d_o2, float *d_cl2, void *stream_) {
+  MMREC_REQUIRE(g && d_o2 && d_cl2, MMREC_E_BADARG, "loss_head_bwd: null pointer");
+  loss_head_bwd_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(g, inv_batch, reg_weight, inv_train_batch_size, cl_weight,
+                                                          d_o2, d_cl2);
+  MMREC_CHECK_LAUNCH("loss_head_bwd_kernel");
+  return MMREC_OK;
+}

@@ -63,6 +63,8 @@ SIGNATURES = {
     "mmrec_axpy_multi_f32": (C.c_int, [_p, _p, _p, _i32, _p, _f32, _p]),
     "mmrec_inject3_fwd_f32": (C.c_int, [_p, _p, _p, _p, _f32, _i64, _p, _p, _p, _p]),
     "mmrec_inject3_bwd_f32": (C.c_int, [_p, _p, _p, _f32, _i64, _p, _p, _p, _p, _p]),
+    "mmrec_loss_head_fwd_f32": (C.c_int, [_p, _p, _f32, _f32, _f32, _f32, _p, _p]),
+    "mmrec_loss_head_bwd_f32": (C.c_int, [_p, _f32, _f32, _f32, _f32, _p, _p, _p]),
     "mmrec_colsum_f32": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "mmrec_row_normalize_f32": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "mmrec_row_topk_f32": (C.c_int, [_p, _i32, _i32, _i64, _i32, _p, _p, _p]),

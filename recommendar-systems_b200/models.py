@@ -384,11 +384,6 @@ class _MultiViewBase(GeneralRecommender):
             coo = knn_sym_coo(feat, k)
         return coo, G.csr_from_coo(*coo, self.n_items, self.n_items)
 
-    def _reg_bpr(self, all_e, users, pos, neg):
-        """mgcn.py:210-222 / smore.py:366-378: mean BPR + reg_weight * L2/2 / train_batch_size."""
-        o = ops.bpr_table(all_e, self.n_users, users, pos, neg)
-        return o[0] / users.shape[0] + self.reg_weight * (o[1] / self.batch_size)
-
     # ---- independent branches of the forward on side streams ---------------------------------
     # The user-item propagation (4 latency-bound SpMMs), the text projection and the image
     # projection do not depend on one another until the side network; on one stream they run back
@@ -499,9 +494,9 @@ class MGCN(_MultiViewBase):
         """mgcn.py:233-253."""
         users, pos, neg = interaction[0], interaction[1], interaction[2]
         all_e, side, content = self._forward_full(self.norm_adj)
-        loss = self._reg_bpr(all_e, users, pos, neg)
-        cl = ops.infonce_pair(side, content, self.n_users, users, pos, 0.2)
-        return loss + self.cl_loss * cl
+        o = ops.bpr_table(all_e, self.n_users, users, pos, neg)
+        cl = ops.infonce_pair(side, content, self.n_users, users, pos, 0.2, reduce=False)
+        return ops.loss_head(o, cl, users.shape[0], self.reg_weight, self.batch_size, self.cl_loss)
 
 
 class SMORE(_MultiViewBase):
@@ -630,9 +625,9 @@ class SMORE(_MultiViewBase):
         users, pos, neg = interaction[0], interaction[1], interaction[2]
         all_e, side, content = self._forward_full(self.norm_adj)
         self.global_step += 1
-        loss = self._reg_bpr(all_e, users, pos, neg)
-        cl = ops.infonce_pair(side, content, self.n_users, users, pos, self.cl_temp)
-        return loss + self.cl_loss * cl
+        o = ops.bpr_table(all_e, self.n_users, users, pos, neg)
+        cl = ops.infonce_pair(side, content, self.n_users, users, pos, self.cl_temp, reduce=False)
+        return ops.loss_head(o, cl, users.shape[0], self.reg_weight, self.batch_size, self.cl_loss)
 
 
 MODELS = {"LightGCN": LightGCN, "LayerGCN": LayerGCN, "FREEDOM": FREEDOM, "MGCN": MGCN,

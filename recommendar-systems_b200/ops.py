@@ -296,7 +296,7 @@ class _InfoNCEPair(torch.autograd.Function):
     stacked [users; items] tables."""
 
     @staticmethod
-    def forward(ctx, side, content, n_users, users, pos_items, temperature):
+    def forward(ctx, side, content, n_users, users, pos_items, temperature, reduce=True):
         side, content = _f32c(side), _f32c(content)
         dev, d = side.device, side.shape[1]
         inv_t = 1.0 / temperature
@@ -315,16 +315,17 @@ class _InfoNCEPair(torch.autograd.Function):
                      lib.ptr(inv_norm), lib.ptr(ttl), lib.ptr(partial), lib.ptr(_counter(dev)),
                      lib.stream())
             saved += [V1, V2, inv_norm, ttl, idx]
-        ctx.n_users, ctx.inv_t, ctx.shape = n_users, inv_t, side.shape
+        ctx.n_users, ctx.inv_t, ctx.shape, ctx.reduce = n_users, inv_t, side.shape, reduce
         ctx.save_for_backward(*saved)
-        return losses.sum()
+        return losses.sum() if reduce else losses
 
     @staticmethod
     def backward(ctx, g):
         saved = ctx.saved_tensors
         n, d = ctx.shape
         dev = g.device
-        coef = _f32c(g).reshape(1)
+        g = _f32c(g)
+        coefs = (g.reshape(1), g.reshape(1)) if ctx.reduce else (g[0:1], g[1:2])
         d_side = torch.zeros(n, d, dtype=torch.float32, device=dev)
         d_content = torch.zeros(n, d, dtype=torch.float32, device=dev)
         for slot, row0 in enumerate((ctx.n_users, 0)):
@@ -334,13 +335,44 @@ class _InfoNCEPair(torch.autograd.Function):
             ws1 = torch.empty(S, B, d, dtype=torch.float32, device=dev)
             ws2 = torch.empty_like(ws1)
             lib.call("mmrec_infonce_bwd_f32", lib.ptr(V1), lib.ptr(V2), lib.ptr(inv_norm),
-                     lib.ptr(ttl), d, lib.ptr(idx), B, ctx.inv_t, lib.ptr(coef), S, lib.ptr(ws1),
+                     lib.ptr(ttl), d, lib.ptr(idx), B, ctx.inv_t, lib.ptr(coefs[slot]), S, lib.ptr(ws1),
                      lib.ptr(ws2), lib.ptr(d_side[row0:]), lib.ptr(d_content[row0:]), lib.stream())
-        return d_side, d_content, None, None, None, None
+        return d_side, d_content, None, None, None, None, None
 
 
-def infonce_pair(side, content, n_users, users, pos_items, temperature):
-    return _InfoNCEPair.apply(side, content, n_users, users, pos_items, temperature)
+def infonce_pair(side, content, n_users, users, pos_items, temperature, reduce=True):
+    """cl_items + cl_users (reduce=False: the two losses as a [2] tensor, items first)."""
+    return _InfoNCEPair.apply(side, content, n_users, users, pos_items, temperature, reduce)
+
+
+class _LossHead(torch.autograd.Function):
+    """bpr/B + reg_weight * reg/batch_size + cl_weight * (cl_i + cl_u) in one launch each way
+    (mgcn.py:241-253, smore.py:396-411), bit-identical to the tensor expression."""
+
+    @staticmethod
+    def forward(ctx, o2, cl2, inv_b, rw, inv_bs, clw):
+        o2, cl2 = _f32c(o2), _f32c(cl2)
+        out = torch.empty(1, dtype=torch.float32, device=o2.device)
+        ctx.c = (float(inv_b), float(rw), float(inv_bs), float(clw))
+        lib.call("mmrec_loss_head_fwd_f32", lib.ptr(o2), lib.ptr(cl2), *ctx.c, lib.ptr(out), lib.stream())
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g).reshape(1)
+        d_o2 = torch.empty(2, dtype=torch.float32, device=g.device)
+        d_cl2 = torch.empty(2, dtype=torch.float32, device=g.device)
+        lib.call("mmrec_loss_head_bwd_f32", lib.ptr(g), *ctx.c, lib.ptr(d_o2), lib.ptr(d_cl2), lib.stream())
+        return d_o2, d_cl2, None, None, None, None
+
+
+def loss_head(o2, cl2, batch, reg_weight, train_batch_size, cl_weight):
+    """o2 = bpr_table(...) sums, cl2 = infonce_pair(..., reduce=False); float32 reciprocals as torch's
+    division by a host scalar."""
+    import numpy as np
+    inv_b = float(np.float32(1.0) / np.float32(batch))
+    inv_bs = float(np.float32(1.0) / np.float32(train_batch_size))
+    return _LossHead.apply(o2, cl2, inv_b, reg_weight, inv_bs, cl_weight)
 
 
 # ------------------------------------------------------------------------------------ spectral
