@@ -423,6 +423,8 @@ class _MultiViewBase(GeneralRecommender):
         """`_view` for all modalities at once: the item-item hops of the views are independent of
         one another (and so are their user-side R products), so each hop is ONE launch."""
         xs = list(xs)
+        if self.n_layers >= 1 and 1 < len(xs) <= 4 and self.R.t is not None:
+            return ops.modality_views(item_graphs, self.R, self.n_layers, xs)
         for _ in range(self.n_layers):
             xs = ops.spmm_multi(item_graphs, xs)
         us = ops.spmm_multi([self.R] * len(xs), xs)
@@ -560,8 +562,10 @@ class SMORE(_MultiViewBase):
 
     def spectrum_convolution(self, image_embeds, text_embeds):
         """smore.py:209-252 without the band-energy .item() syncs (diagnostics only)."""
-        return ops.spectrum_convolution(image_embeds, text_embeds, self.image_complex_weight[0],
-                                        self.text_complex_weight[0], self.fusion_complex_weight[0],
+        # the [1, d/2+1, 2] parameters go in whole: indexing them here would add a select-backward
+        # (zero fill + copy) per weight and pass to the autograd graph
+        return ops.spectrum_convolution(image_embeds, text_embeds, self.image_complex_weight,
+                                        self.text_complex_weight, self.fusion_complex_weight,
                                         self.spectral_weight_norm)
 
     def forward(self, adj, train=False):

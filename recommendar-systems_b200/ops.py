@@ -118,6 +118,57 @@ class _SpMMMulti(torch.autograd.Function):
         return (None, *dXs)
 
 
+class _ModalityViews(torch.autograd.Function):
+    """The modality views of MGCN / SMORE (mgcn.py:170-184, smore.py:289-317) for all modalities at
+    once: x <- A_m x (n_layers item-item hops), u = R x, view_m = cat([u, x]). The last item hop
+    writes straight into rows [U, N) of the view and the R hop into rows [0, U): no torch.cat; the
+    backward adds the direct gradient of the item rows inside the R^T launch (accumulate epilogue)
+    instead of a separate add per view."""
+
+    @staticmethod
+    def forward(ctx, item_graphs, R, n_layers, *xs):
+        xs = [_f32c(x) for x in xs]
+        n = len(xs)
+        U, I, d = R.n_rows, R.n_cols, xs[0].shape[1]
+        dev = xs[0].device
+        outs = [torch.empty(U + I, d, dtype=torch.float32, device=dev) for _ in range(n)]
+        cur = xs
+        for layer in range(n_layers):
+            last = layer == n_layers - 1
+            ys = [o[U:] for o in outs] if last else [torch.empty_like(x) for x in cur]
+            spmm_multi_raw(item_graphs, cur, Ys=ys)
+            cur = ys
+        spmm_multi_raw([R] * n, cur, Ys=[o[:U] for o in outs])
+        ctx.item_graphs, ctx.R, ctx.n_layers = item_graphs, R, n_layers
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        R, n_layers = ctx.R, ctx.n_layers
+        U, I = R.n_rows, R.n_cols
+        ref = next(g for g in douts if g is not None)
+        douts = [torch.zeros_like(ref) if g is None else _f32c(g) for g in douts]
+        n = len(douts)
+        gts = []
+        for g in ctx.item_graphs:
+            if g.t is None:
+                raise RuntimeError("modality views backward needs the transposed item graphs")
+            gts.append(g.t)
+        # d x = R^T d u + (direct gradient of the item rows), one launch for all views
+        cur = [torch.empty(I, ref.shape[1], dtype=torch.float32, device=ref.device) for _ in range(n)]
+        spmm_multi_raw([R.t] * n, [g[:U] for g in douts], acc_ins=[g[U:] for g in douts], acc_outs=cur)
+        for _ in range(n_layers):
+            nxt = [torch.empty_like(c) for c in cur]
+            spmm_multi_raw(gts, cur, Ys=nxt)
+            cur = nxt
+        return (None, None, None, *cur)
+
+
+def modality_views(item_graphs, R, n_layers, xs):
+    """[cat([R x_m', x_m'])] with x_m' = A_m^n_layers x_m, for up to 4 modalities; see _ModalityViews."""
+    return list(_ModalityViews.apply(list(item_graphs), R, int(n_layers), *xs))
+
+
 def spmm_multi(graphs, Xs):
     """[torch.sparse.mm(A_i, X_i)] for independent pairs (at most 4) in one launch each way."""
     graphs = list(graphs)

@@ -869,3 +869,39 @@ def test_dense_stack_batch_equals_single_launches(d, act, n):
         (y * g).sum().backward()
         assert torch.equal(y, y0) and torch.equal(x.grad, dx0)
         assert torch.equal(st[0].weight.grad, dw0) and torch.equal(st[0].bias.grad, db0)
+
+
+@pytest.mark.parametrize("n_layers,n_views", [(1, 3), (2, 2)])
+def test_modality_views_equal_spmm_plus_cat(n_layers, n_views):
+    """mgcn.py:170-184 / smore.py:289-317: the fused views (no torch.cat, direct item gradient folded
+    into the R^T launch) are bit-identical to item hops + R hop + cat, forward and backward."""
+    G, ops, synth = pkg("graph"), pkg("ops"), pkg("synth")
+    data = synth.make_dataset("small", features=False)
+    u, i = data.split(0)
+    U, I = data.n_users, data.n_items
+    full = G.build_ui_graph(torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), U, I, "f32")
+    R, _ = G.ui_blocks(full)
+    gen = torch.Generator().manual_seed(61)
+    graphs = []
+    for v in range(n_views):
+        r = torch.arange(I).repeat_interleave(5)
+        c = torch.randint(0, I, (5 * I,), generator=gen)
+        w = torch.rand(5 * I, generator=gen)
+        graphs.append(G.csr_from_coo(r.to(DEV), c.to(DEV), w.to(DEV), I, I))
+    xs = [torch.randn(I, 64, generator=gen).to(DEV).requires_grad_(True) for _ in range(n_views)]
+    ws = [torch.randn(U + I, 64, generator=gen).to(DEV) for _ in range(n_views)]
+    got = ops.modality_views(graphs, R, n_layers, xs)
+    sum((g * w).sum() for g, w in zip(got, ws)).backward()
+    got_g = [x.grad.clone() for x in xs]
+    for x in xs:
+        x.grad = None
+    cur = list(xs)
+    for _ in range(n_layers):
+        cur = ops.spmm_multi(graphs, cur)
+    us = ops.spmm_multi([R] * n_views, cur)
+    want = [torch.cat([a, b], dim=0) for a, b in zip(us, cur)]
+    sum((g * w).sum() for g, w in zip(want, ws)).backward()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    for a, x in zip(got_g, xs):
+        assert torch.equal(a, x.grad)
