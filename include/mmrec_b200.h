@@ -169,6 +169,22 @@ int mmrec_infonce_bwd_f32(const float *V1n, const float *V2n, const float *inv_n
                           const float *ttl, int32_t d, const int64_t *idx, int32_t batch,
                           float inv_temp, const float *coef, int32_t n_splits, float *dV1_ws,
                           float *dV2_ws, float *dT1, float *dT2, void *stream);
+/* The item-row and user-row InfoNCE problems of a batch (mgcn.py:250-251, smore.py:406-407: same
+ * batch size, same d) in ONE launch per stage. Every pointer argument is a HOST array of two device
+ * pointers; partial / workspaces are sized per problem exactly as for the single-problem calls.
+ * Available where mmrec_infonce_pair_supported(d) != 0 (d = 64: the tcgen05 kernels). */
+int mmrec_infonce_pair_supported(int32_t d);
+int mmrec_infonce_pair_fwd_f32(const float *const *T1_host, const float *const *T2_host, int32_t d,
+                               const int64_t *const *idx_host, int32_t batch, float inv_temp,
+                               float *const *loss_out_host, float *const *V1n_host, float *const *V2n_host,
+                               float *const *inv_norm_host, float *const *ttl_host, float *const *partial_host,
+                               void *stream);
+int mmrec_infonce_pair_bwd_f32(const float *const *V1n_host, const float *const *V2n_host,
+                               const float *const *inv_norm_host, const float *const *ttl_host, int32_t d,
+                               const int64_t *const *idx_host, int32_t batch, float inv_temp,
+                               const float *const *coef_host, int32_t n_splits, float *const *dV1_ws_host,
+                               float *const *dV2_ws_host, float *const *dT1_host, float *const *dT2_host,
+                               void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Spectrum-based modality fusion (K5). Replaces SMORE.spectrum_convolution

@@ -60,12 +60,21 @@ struct ICfg {
   static_assert(P_COL + 4 * kTN <= 512, "TMEM budget");
 };
 
+// Up to two independent problems of the same batch size per launch (blockIdx.z): MGCN / SMORE call
+// InfoNCE for the item rows and for the user rows of every batch (mgcn.py:250-251, smore.py:406-407).
+constexpr int kMaxProb = 2;
+struct TcArgs {
+  const float *own[kMaxProb], *other[kMaxProb], *ttl[kMaxProb], *coef[kMaxProb];
+  float *out_a[kMaxProb], *out_b[kMaxProb];
+};
+
 template <int D, int MODE>
 __global__ void __launch_bounds__(kThreadsI, 1)
-infonce_tc_kernel(const float *__restrict__ Own, const float *__restrict__ Other, int batch, float inv_temp,
-                  int tiles_per_split, const float *__restrict__ ttl, const float *__restrict__ coef,
-                  float *__restrict__ out_a, float *__restrict__ out_b) {
+infonce_tc_kernel(const __grid_constant__ TcArgs A, int batch, float inv_temp, int tiles_per_split) {
   using C = ICfg<D>;
+  const float *__restrict__ Own = A.own[blockIdx.z], *__restrict__ Other = A.other[blockIdx.z],
+                           *__restrict__ ttl = A.ttl[blockIdx.z], *__restrict__ coef = A.coef[blockIdx.z];
+  float *__restrict__ out_a = A.out_a[blockIdx.z], *__restrict__ out_b = A.out_b[blockIdx.z];
   constexpr bool BWD = MODE != kFwd;
   constexpr uint32_t STAGE = 2 * C::B1_HALF + (BWD ? 2 * C::B2_HALF : 0);
   extern __shared__ uint8_t smem_raw[];
@@ -316,10 +325,15 @@ infonce_tc_kernel(const float *__restrict__ Own, const float *__restrict__ Other
 }
 
 // ttl[r] = sum over splits, loss = mean_r( log ttl_r - s_rr / t ); one CTA, fixed order.
+struct FinishArgs {
+  const float *ttl_part[kMaxProb], *pos[kMaxProb];
+  float *ttl[kMaxProb], *loss_out[kMaxProb];
+};
 __global__ void __launch_bounds__(1024)
-infonce_finish_kernel(const float *__restrict__ ttl_part, const float *__restrict__ pos, int n_splits, int batch,
-                      float inv_temp, float *__restrict__ ttl, float *__restrict__ loss_out) {
+infonce_finish_kernel(const __grid_constant__ FinishArgs F, int n_splits, int batch, float inv_temp) {
   __shared__ float red[32];
+  const float *__restrict__ ttl_part = F.ttl_part[blockIdx.x], *__restrict__ pos = F.pos[blockIdx.x];
+  float *__restrict__ ttl = F.ttl[blockIdx.x], *__restrict__ loss_out = F.loss_out[blockIdx.x];
   float l = 0.f;
   for (int r = threadIdx.x; r < batch; r += 1024) {
     float s = 0.f;
@@ -332,8 +346,7 @@ infonce_finish_kernel(const float *__restrict__ ttl_part, const float *__restric
 }
 
 template <int MODE>
-int launch_mode(const float *Own, const float *Other, int batch, float inv_temp, int splits, int tps, const float *ttl,
-                const float *coef, float *out_a, float *out_b, cudaStream_t stream) {
+int launch_mode(const TcArgs &A, int n_prob, int batch, float inv_temp, int splits, int tps, cudaStream_t stream) {
   constexpr int D = 64;
   using C = ICfg<D>;
   constexpr uint32_t STAGE = 2 * C::B1_HALF + (MODE != kFwd ? 2 * C::B2_HALF : 0);
@@ -344,8 +357,8 @@ int launch_mode(const float *Own, const float *Other, int batch, float inv_temp,
     MMREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  dim3 grid((batch + kTM - 1) / kTM, splits);
-  kern<<<grid, kThreadsI, smem, stream>>>(Own, Other, batch, inv_temp, tps, ttl, coef, out_a, out_b);
+  dim3 grid((batch + kTM - 1) / kTM, splits, n_prob);
+  kern<<<grid, kThreadsI, smem, stream>>>(A, batch, inv_temp, tps);
   MMREC_CHECK_LAUNCH("infonce_tc_kernel");
   return MMREC_OK;
 }
@@ -359,36 +372,50 @@ bool infonce_tc_enabled(int d) {
 
 // "Other"-dimension splits of the tcgen05 path: one wave of 128-row CTAs, never more than `cap`
 // (the split count the caller sized its workspaces for).
-int infonce_tc_splits(int batch, int cap, int *tiles_per_split) {
+int infonce_tc_splits(int batch, int cap, int *tiles_per_split, int n_prob = 1) {
   const int n_rt = (batch + kTM - 1) / kTM, n_ot = (batch + kTN - 1) / kTN;
-  int s = max(1, min(min(n_ot, cap / 2), kNumSMs / n_rt));      // the forward writes two slabs per split
+  int s = max(1, min(min(n_ot, cap / 2), kNumSMs / (n_rt * n_prob)));   // one wave; the forward writes two slabs per split
   const int tps = (n_ot + s - 1) / s;
   *tiles_per_split = tps;
   return (n_ot + tps - 1) / tps;
 }
 
-// forward: partial = pos[batch] | ttl_part[splits][batch]
-int infonce_fwd_tc(const float *V1n, const float *V2n, int batch, float inv_temp, int cap_splits, float *partial,
-                   float *ttl, float *loss_out, cudaStream_t stream) {
+// forward: partial_p = pos[batch] | ttl_part[2 * splits][batch] for each of the n_prob problems
+int infonce_fwd_tc(int n_prob, const float *const *V1n, const float *const *V2n, int batch, float inv_temp,
+                   int cap_splits, float *const *partial, float *const *ttl, float *const *loss_out,
+                   cudaStream_t stream) {
   int tps;
-  const int splits = infonce_tc_splits(batch, cap_splits, &tps);
-  float *pos = partial, *ttl_part = partial + batch;
-  const int rc = launch_mode<kFwd>(V1n, V2n, batch, inv_temp, splits, tps, nullptr, nullptr, ttl_part, pos, stream);
+  const int splits = infonce_tc_splits(batch, cap_splits, &tps, n_prob);
+  TcArgs A{};
+  FinishArgs F{};
+  for (int p = 0; p < n_prob; ++p) {
+    A.own[p] = V1n[p]; A.other[p] = V2n[p];
+    A.out_a[p] = partial[p] + batch;      // ttl_part
+    A.out_b[p] = partial[p];              // pos
+    F.ttl_part[p] = partial[p] + batch; F.pos[p] = partial[p]; F.ttl[p] = ttl[p]; F.loss_out[p] = loss_out[p];
+  }
+  const int rc = launch_mode<kFwd>(A, n_prob, batch, inv_temp, splits, tps, stream);
   if (rc != MMREC_OK) return rc;
-  infonce_finish_kernel<<<1, 1024, 0, stream>>>(ttl_part, pos, 2 * splits, batch, inv_temp, ttl, loss_out);
+  infonce_finish_kernel<<<n_prob, 1024, 0, stream>>>(F, 2 * splits, batch, inv_temp);
   MMREC_CHECK_LAUNCH("infonce_finish_kernel");
   return MMREC_OK;
 }
 
-// backward: dV1 / dV2 hold `*splits_out` slabs of [batch, 64] partial sums for the scatter kernel
-int infonce_bwd_tc(const float *V1n, const float *V2n, const float *ttl, int batch, float inv_temp, int cap_splits,
-                   const float *coef, float *dV1, float *dV2, int *splits_out, cudaStream_t stream) {
+// backward: dV1_p / dV2_p hold `*splits_out` slabs of [batch, 64] partial sums for the scatter kernel
+int infonce_bwd_tc(int n_prob, const float *const *V1n, const float *const *V2n, const float *const *ttl, int batch,
+                   float inv_temp, int cap_splits, const float *const *coef, float *const *dV1, float *const *dV2,
+                   int *splits_out, cudaStream_t stream) {
   int tps;
-  const int splits = infonce_tc_splits(batch, cap_splits, &tps);
+  const int splits = infonce_tc_splits(batch, cap_splits, &tps, n_prob);
   *splits_out = splits;
-  int rc = launch_mode<kBwdRow>(V1n, V2n, batch, inv_temp, splits, tps, ttl, coef, dV1, nullptr, stream);
+  TcArgs R{}, Cc{};
+  for (int p = 0; p < n_prob; ++p) {
+    R.own[p] = V1n[p]; R.other[p] = V2n[p]; R.ttl[p] = ttl[p]; R.coef[p] = coef[p]; R.out_a[p] = dV1[p];
+    Cc.own[p] = V2n[p]; Cc.other[p] = V1n[p]; Cc.ttl[p] = ttl[p]; Cc.coef[p] = coef[p]; Cc.out_a[p] = dV2[p];
+  }
+  int rc = launch_mode<kBwdRow>(R, n_prob, batch, inv_temp, splits, tps, stream);
   if (rc != MMREC_OK) return rc;
-  return launch_mode<kBwdCol>(V2n, V1n, batch, inv_temp, splits, tps, ttl, coef, dV2, nullptr, stream);
+  return launch_mode<kBwdCol>(Cc, n_prob, batch, inv_temp, splits, tps, stream);
 }
 
 }  // namespace mmrec

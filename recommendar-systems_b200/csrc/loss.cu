@@ -124,10 +124,26 @@ bpr_bwd_kernel(const float *__restrict__ ue, const float *__restrict__ ie, int d
 }
 
 // -------------------------------------------------------------------------------------- InfoNCE
+// Up to two problems of the same batch size per launch (blockIdx.y): the item-row and user-row calls
+// of a batch (mgcn.py:250-251, smore.py:406-407).
+constexpr int kMaxInfoProb = 2;
+struct NormArgs {
+  const float *T1[kMaxInfoProb], *T2[kMaxInfoProb];
+  const int64_t *idx[kMaxInfoProb];
+  float *V1n[kMaxInfoProb], *V2n[kMaxInfoProb], *inv_norm[kMaxInfoProb];
+};
+struct ScatterArgs {
+  const float *V1n[kMaxInfoProb], *V2n[kMaxInfoProb], *inv_norm[kMaxInfoProb], *dV1[kMaxInfoProb], *dV2[kMaxInfoProb];
+  const int64_t *idx[kMaxInfoProb];
+  float *dT1[kMaxInfoProb], *dT2[kMaxInfoProb];
+};
+
 __global__ void __launch_bounds__(kThreads)
-infonce_normalize_kernel(const float *__restrict__ T1, const float *__restrict__ T2, int d,
-                         const int64_t *__restrict__ idx, int batch, float *__restrict__ V1n,
-                         float *__restrict__ V2n, float *__restrict__ inv_norm) {
+infonce_normalize_kernel(const __grid_constant__ NormArgs A, int d, int batch) {
+  const float *__restrict__ T1 = A.T1[blockIdx.y], *__restrict__ T2 = A.T2[blockIdx.y];
+  const int64_t *__restrict__ idx = A.idx[blockIdx.y];
+  float *__restrict__ V1n = A.V1n[blockIdx.y], *__restrict__ V2n = A.V2n[blockIdx.y],
+                     *__restrict__ inv_norm = A.inv_norm[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * (kThreads / 32) + warp;
   if (b >= batch) return;
@@ -333,11 +349,12 @@ infonce_bwd_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
 
 // Chain through F.normalize and scatter-add into the table-shaped gradients.
 __global__ void __launch_bounds__(kThreads)
-infonce_scatter_kernel(const float *__restrict__ V1n, const float *__restrict__ V2n,
-                       const float *__restrict__ inv_norm, const float *__restrict__ dV1,
-                       const float *__restrict__ dV2, int n_splits, int d,
-                       const int64_t *__restrict__ idx, int batch, float *__restrict__ dT1,
-                       float *__restrict__ dT2) {
+infonce_scatter_kernel(const __grid_constant__ ScatterArgs A, int n_splits, int d, int batch) {
+  const float *__restrict__ V1n = A.V1n[blockIdx.y], *__restrict__ V2n = A.V2n[blockIdx.y],
+                           *__restrict__ inv_norm = A.inv_norm[blockIdx.y], *__restrict__ dV1 = A.dV1[blockIdx.y],
+                           *__restrict__ dV2 = A.dV2[blockIdx.y];
+  const int64_t *__restrict__ idx = A.idx[blockIdx.y];
+  float *__restrict__ dT1 = A.dT1[blockIdx.y], *__restrict__ dT2 = A.dT2[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * (kThreads / 32) + warp;
   if (b >= batch) return;
@@ -431,10 +448,12 @@ int infonce_bwd_launch(const float *V1n, const float *V2n, const float *ttl, int
 
 // tcgen05 path for d = 64 (infonce_tc.cu)
 bool infonce_tc_enabled(int d);
-int infonce_fwd_tc(const float *V1n, const float *V2n, int batch, float inv_temp, int cap_splits, float *partial,
-                   float *ttl, float *loss_out, cudaStream_t stream);
-int infonce_bwd_tc(const float *V1n, const float *V2n, const float *ttl, int batch, float inv_temp, int cap_splits,
-                   const float *coef, float *dV1, float *dV2, int *splits_out, cudaStream_t stream);
+int infonce_fwd_tc(int n_prob, const float *const *V1n, const float *const *V2n, int batch, float inv_temp,
+                   int cap_splits, float *const *partial, float *const *ttl, float *const *loss_out,
+                   cudaStream_t stream);
+int infonce_bwd_tc(int n_prob, const float *const *V1n, const float *const *V2n, const float *const *ttl, int batch,
+                   float inv_temp, int cap_splits, const float *const *coef, float *const *dV1, float *const *dV2,
+                   int *splits_out, cudaStream_t stream);
 }  // namespace mmrec
 
 using namespace mmrec;
@@ -486,11 +505,15 @@ extern "C" int mmrec_infonce_fwd_f32(const float *T1, const float *T2, int32_t d
   MMREC_REQUIRE(aligned16(T1) && aligned16(T2) && aligned16(V1n) && aligned16(V2n), MMREC_E_ALIGN,
                 "infonce_fwd: operands must be 16-byte aligned");
   const int wpb = kThreads / 32;
-  infonce_normalize_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(T1, T2, d, idx, batch, V1n, V2n,
-                                                                           inv_norm);
+  NormArgs NA{};
+  NA.T1[0] = T1; NA.T2[0] = T2; NA.idx[0] = idx; NA.V1n[0] = V1n; NA.V2n[0] = V2n; NA.inv_norm[0] = inv_norm;
+  infonce_normalize_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(NA, d, batch);
   MMREC_CHECK_LAUNCH("infonce_normalize_kernel");
-  if (infonce_tc_enabled(d))
-    return infonce_fwd_tc(V1n, V2n, batch, inv_temp, infonce_splits(batch), partial, ttl, loss_out, stream);
+  if (infonce_tc_enabled(d)) {
+    const float *v1[1] = {V1n}, *v2[1] = {V2n};
+    float *pp[1] = {partial}, *tt[1] = {ttl}, *lo[1] = {loss_out};
+    return infonce_fwd_tc(1, v1, v2, batch, inv_temp, infonce_splits(batch), pp, tt, lo, stream);
+  }
   switch (d) {
     case 32: return infonce_fwd_launch<32>(V1n, V2n, batch, inv_temp, partial, ttl, loss_out, counter, stream);
     case 64: return infonce_fwd_launch<64>(V1n, V2n, batch, inv_temp, partial, ttl, loss_out, counter, stream);
@@ -514,7 +537,9 @@ extern "C" int mmrec_infonce_bwd_f32(const float *V1n, const float *V2n, const f
   int rc;
   if (infonce_tc_enabled(d)) {
     int used = n_splits;
-    rc = infonce_bwd_tc(V1n, V2n, ttl, batch, inv_temp, n_splits, coef, dV1_ws, dV2_ws, &used, stream);
+    const float *v1[1] = {V1n}, *v2[1] = {V2n}, *tt[1] = {ttl}, *cf[1] = {coef};
+    float *d1[1] = {dV1_ws}, *d2[1] = {dV2_ws};
+    rc = infonce_bwd_tc(1, v1, v2, tt, batch, inv_temp, n_splits, cf, d1, d2, &used, stream);
     n_splits = used;
   } else
   switch (d) {
@@ -527,8 +552,72 @@ extern "C" int mmrec_infonce_bwd_f32(const float *V1n, const float *V2n, const f
   }
   if (rc != MMREC_OK) return rc;
   const int wpb = kThreads / 32;
-  infonce_scatter_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(V1n, V2n, inv_norm, dV1_ws, dV2_ws,
-                                                                         n_splits, d, idx, batch, dT1, dT2);
+  ScatterArgs SA{};
+  SA.V1n[0] = V1n; SA.V2n[0] = V2n; SA.inv_norm[0] = inv_norm; SA.dV1[0] = dV1_ws; SA.dV2[0] = dV2_ws;
+  SA.idx[0] = idx; SA.dT1[0] = dT1; SA.dT2[0] = dT2;
+  infonce_scatter_kernel<<<(batch + wpb - 1) / wpb, kThreads, 0, stream>>>(SA, n_splits, d, batch);
+  MMREC_CHECK_LAUNCH("infonce_scatter_kernel");
+  return MMREC_OK;
+}
+
+// ---- both InfoNCE problems of a batch (item rows, user rows) in one launch per stage ----------
+extern "C" int mmrec_infonce_pair_supported(int32_t d) { return infonce_tc_enabled(d) ? 1 : 0; }
+
+extern "C" int mmrec_infonce_pair_fwd_f32(const float *const *T1_host, const float *const *T2_host, int32_t d,
+                                          const int64_t *const *idx_host, int32_t batch, float inv_temp,
+                                          float *const *loss_out_host, float *const *V1n_host, float *const *V2n_host,
+                                          float *const *inv_norm_host, float *const *ttl_host,
+                                          float *const *partial_host, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMREC_REQUIRE(T1_host && T2_host && idx_host && loss_out_host && V1n_host && V2n_host && inv_norm_host && ttl_host &&
+                    partial_host, MMREC_E_BADARG, "infonce_pair_fwd: null pointer");
+  MMREC_REQUIRE(infonce_tc_enabled(d), MMREC_E_BADARG, "infonce_pair_fwd: d=%d is not on the batched path", d);
+  MMREC_REQUIRE(batch > 0 && (batch + kTile - 1) / kTile <= kMaxInfoTiles, MMREC_E_BADARG,
+                "infonce_pair_fwd: batch must be in [1, %d]", kMaxInfoTiles * kTile);
+  NormArgs NA{};
+  for (int p = 0; p < kMaxInfoProb; ++p) {
+    NA.T1[p] = T1_host[p]; NA.T2[p] = T2_host[p]; NA.idx[p] = idx_host[p];
+    NA.V1n[p] = V1n_host[p]; NA.V2n[p] = V2n_host[p]; NA.inv_norm[p] = inv_norm_host[p];
+    MMREC_REQUIRE(NA.T1[p] && NA.T2[p] && NA.idx[p] && NA.V1n[p] && NA.V2n[p] && NA.inv_norm[p] && ttl_host[p] &&
+                      partial_host[p] && loss_out_host[p], MMREC_E_BADARG, "infonce_pair_fwd: null tensor %d", p);
+    MMREC_REQUIRE(aligned16(NA.T1[p]) && aligned16(NA.T2[p]) && aligned16(NA.V1n[p]) && aligned16(NA.V2n[p]),
+                  MMREC_E_ALIGN, "infonce_pair_fwd: operands must be 16-byte aligned");
+  }
+  const int wpb = kThreads / 32;
+  infonce_normalize_kernel<<<dim3((batch + wpb - 1) / wpb, kMaxInfoProb), kThreads, 0, stream>>>(NA, d, batch);
+  MMREC_CHECK_LAUNCH("infonce_normalize_kernel");
+  return infonce_fwd_tc(kMaxInfoProb, V1n_host, V2n_host, batch, inv_temp, infonce_splits(batch), partial_host,
+                        ttl_host, loss_out_host, stream);
+}
+
+extern "C" int mmrec_infonce_pair_bwd_f32(const float *const *V1n_host, const float *const *V2n_host,
+                                          const float *const *inv_norm_host, const float *const *ttl_host, int32_t d,
+                                          const int64_t *const *idx_host, int32_t batch, float inv_temp,
+                                          const float *const *coef_host, int32_t n_splits, float *const *dV1_ws_host,
+                                          float *const *dV2_ws_host, float *const *dT1_host, float *const *dT2_host,
+                                          void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMREC_REQUIRE(V1n_host && V2n_host && inv_norm_host && ttl_host && idx_host && coef_host && dV1_ws_host &&
+                    dV2_ws_host && dT1_host && dT2_host, MMREC_E_BADARG, "infonce_pair_bwd: null pointer");
+  MMREC_REQUIRE(infonce_tc_enabled(d), MMREC_E_BADARG, "infonce_pair_bwd: d=%d is not on the batched path", d);
+  MMREC_REQUIRE(batch > 0 && n_splits >= 1 && n_splits <= 64, MMREC_E_BADARG, "infonce_pair_bwd: bad sizes");
+  ScatterArgs SA{};
+  for (int p = 0; p < kMaxInfoProb; ++p) {
+    SA.V1n[p] = V1n_host[p]; SA.V2n[p] = V2n_host[p]; SA.inv_norm[p] = inv_norm_host[p];
+    SA.dV1[p] = dV1_ws_host[p]; SA.dV2[p] = dV2_ws_host[p]; SA.idx[p] = idx_host[p];
+    SA.dT1[p] = dT1_host[p]; SA.dT2[p] = dT2_host[p];
+    MMREC_REQUIRE(SA.V1n[p] && SA.V2n[p] && SA.inv_norm[p] && SA.dV1[p] && SA.dV2[p] && SA.idx[p] && SA.dT1[p] &&
+                      SA.dT2[p] && ttl_host[p] && coef_host[p], MMREC_E_BADARG, "infonce_pair_bwd: null tensor %d", p);
+    MMREC_REQUIRE(aligned16(SA.V1n[p]) && aligned16(SA.V2n[p]) && aligned16(SA.dV1[p]) && aligned16(SA.dV2[p]) &&
+                      aligned16(SA.dT1[p]) && aligned16(SA.dT2[p]), MMREC_E_ALIGN,
+                  "infonce_pair_bwd: operands must be 16-byte aligned");
+  }
+  int used = n_splits;
+  const int rc = infonce_bwd_tc(kMaxInfoProb, V1n_host, V2n_host, ttl_host, batch, inv_temp, n_splits, coef_host,
+                                dV1_ws_host, dV2_ws_host, &used, stream);
+  if (rc != MMREC_OK) return rc;
+  const int wpb = kThreads / 32;
+  infonce_scatter_kernel<<<dim3((batch + wpb - 1) / wpb, kMaxInfoProb), kThreads, 0, stream>>>(SA, used, d, batch);
   MMREC_CHECK_LAUNCH("infonce_scatter_kernel");
   return MMREC_OK;
 }

@@ -39,6 +39,9 @@ SIGNATURES = {
                                         _p]),
     "mmrec_infonce_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _f32, _p, _i32, _p, _p, _p,
                                         _p, _p]),
+    "mmrec_infonce_pair_supported": (C.c_int, [_i32]),
+    "mmrec_infonce_pair_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p, _p, _p]),
+    "mmrec_infonce_pair_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _f32, _p, _i32, _p, _p, _p, _p, _p]),
     "mmrec_spectral_fwd_f32": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "mmrec_spectral_bwd_f32": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p,
                                          _p, _p, _p, _p, _p, _p]),

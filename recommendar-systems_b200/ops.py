@@ -353,7 +353,27 @@ class _InfoNCEPair(torch.autograd.Function):
         inv_t = 1.0 / temperature
         saved = []
         losses = torch.empty(2, dtype=torch.float32, device=dev)
-        for slot, (row0, idx) in enumerate(((n_users, pos_items), (0, users))):
+        slots = ((n_users, pos_items), (0, users))
+        pair = users.numel() == pos_items.numel() and bool(lib.load().mmrec_infonce_pair_supported(d))
+        if pair:                                 # both problems in one launch per stage
+            B = users.numel()
+            n_ws = lib.load().mmrec_infonce_fwd_workspace_floats(B)
+            V1 = [torch.empty(B, d, dtype=torch.float32, device=dev) for _ in slots]
+            V2 = [torch.empty(B, d, dtype=torch.float32, device=dev) for _ in slots]
+            inv_norm = [torch.empty(2 * B, dtype=torch.float32, device=dev) for _ in slots]
+            ttl = [torch.empty(B, dtype=torch.float32, device=dev) for _ in slots]
+            partial = [torch.empty(n_ws, dtype=torch.float32, device=dev) for _ in slots]
+            T1 = [side[row0:] for row0, _ in slots]
+            T2 = [content[row0:] for row0, _ in slots]
+            idxs = [idx for _, idx in slots]
+            outs = [losses[0:], losses[1:]]
+            lib.call("mmrec_infonce_pair_fwd_f32", _ptr_array(T1), _ptr_array(T2), d, _ptr_array(idxs), B, inv_t,
+                     _ptr_array(outs), _ptr_array(V1), _ptr_array(V2), _ptr_array(inv_norm), _ptr_array(ttl),
+                     _ptr_array(partial), lib.stream())
+            for s_ in range(2):
+                saved += [V1[s_], V2[s_], inv_norm[s_], ttl[s_], idxs[s_]]
+            slots = ()
+        for slot, (row0, idx) in enumerate(slots):
             B = idx.numel()
             V1 = torch.empty(B, d, dtype=torch.float32, device=dev)
             V2 = torch.empty_like(V1)
@@ -366,7 +386,7 @@ class _InfoNCEPair(torch.autograd.Function):
                      lib.ptr(inv_norm), lib.ptr(ttl), lib.ptr(partial), lib.ptr(_counter(dev)),
                      lib.stream())
             saved += [V1, V2, inv_norm, ttl, idx]
-        ctx.n_users, ctx.inv_t, ctx.shape, ctx.reduce = n_users, inv_t, side.shape, reduce
+        ctx.n_users, ctx.inv_t, ctx.shape, ctx.reduce, ctx.pair = n_users, inv_t, side.shape, reduce, pair
         ctx.save_for_backward(*saved)
         return losses.sum() if reduce else losses
 
@@ -379,7 +399,19 @@ class _InfoNCEPair(torch.autograd.Function):
         coefs = (g.reshape(1), g.reshape(1)) if ctx.reduce else (g[0:1], g[1:2])
         d_side = torch.zeros(n, d, dtype=torch.float32, device=dev)
         d_content = torch.zeros(n, d, dtype=torch.float32, device=dev)
-        for slot, row0 in enumerate((ctx.n_users, 0)):
+        rows0 = (ctx.n_users, 0)
+        if ctx.pair:
+            B = saved[4].numel()
+            S = lib.load().mmrec_infonce_splits(B)
+            V1, V2, inv_norm, ttl, idxs = ([saved[5 * s_ + j] for s_ in range(2)] for j in range(5))
+            ws1 = [torch.empty(S, B, d, dtype=torch.float32, device=dev) for _ in range(2)]
+            ws2 = [torch.empty(S, B, d, dtype=torch.float32, device=dev) for _ in range(2)]
+            lib.call("mmrec_infonce_pair_bwd_f32", _ptr_array(V1), _ptr_array(V2), _ptr_array(inv_norm),
+                     _ptr_array(ttl), d, _ptr_array(idxs), B, ctx.inv_t, _ptr_array(list(coefs)), S,
+                     _ptr_array(ws1), _ptr_array(ws2), _ptr_array([d_side[r:] for r in rows0]),
+                     _ptr_array([d_content[r:] for r in rows0]), lib.stream())
+            rows0 = ()
+        for slot, row0 in enumerate(rows0):
             V1, V2, inv_norm, ttl, idx = saved[5 * slot: 5 * slot + 5]
             B = idx.numel()
             S = lib.load().mmrec_infonce_splits(B)
