@@ -266,8 +266,11 @@ def run_ours(args):
     # end-to-end loop (the device-timed K steps alone last a few tens of ms: too short for nvidia-smi)
     sampler = ClockSampler(local)
     sampler.start()
-    for b in batches[:W]:
-        trainer._train_batch_graphed(b)          # eager twice per variant, then captured + replayed
+    # The steady-state step is replayed from a CUDA graph that is captured on the 5th step (two eager
+    # runs per control-flow variant first): with W < 6 a few extra untimed steps go in front, so that
+    # the K timed steps are the steady state whatever W the caller chose.
+    for b in take_batches(env["train"], max(0, 6 - W)) + batches[:W]:
+        trainer._train_batch_graphed(b)
     torch.cuda.synchronize()
 
     def barrier():

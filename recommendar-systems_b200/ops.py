@@ -397,8 +397,8 @@ class _InfoNCEPair(torch.autograd.Function):
         dev = g.device
         g = _f32c(g)
         coefs = (g.reshape(1), g.reshape(1)) if ctx.reduce else (g[0:1], g[1:2])
-        d_side = torch.zeros(n, d, dtype=torch.float32, device=dev)
-        d_content = torch.zeros(n, d, dtype=torch.float32, device=dev)
+        d_both = torch.zeros(2, n, d, dtype=torch.float32, device=dev)      # one fill for both scatter targets
+        d_side, d_content = d_both[0], d_both[1]
         rows0 = (ctx.n_users, 0)
         if ctx.pair:
             B = saved[4].numel()
