@@ -234,8 +234,9 @@ int mmrec_gemm_tf32x3_f32(const float *A, int32_t a_kcontig, const float *B, int
  *   act: 0 = identity, 1 = tanh, 2 = sigmoid
  *   fwd: Y = act(X W^T + bias)                         (bias may be NULL)
  *   bwd: dZ = dY * act'(Y); dX = dZ W (skipped if dX NULL); dW = dZ^T X; db = sum_rows dZ (if db)
- * Exact fp32 FMA arithmetic. The backward needs mmrec_dense_act_bwd_workspace_bytes of scratch;
- * per-CTA partial sums of dW/db are added in a fixed order (bit-reproducible).
+ * Tile products on mma.sync tensor cores with the 3xTF32 split (fp32-class accuracy, ~1e-7).
+ * The backward needs mmrec_dense_act_bwd_workspace_bytes of scratch; per-CTA partial sums of
+ * dW/db are added in a fixed order (bit-reproducible).
  * ---------------------------------------------------------------------------------------- */
 int mmrec_dense_act_supported(int32_t K, int32_t N);
 size_t mmrec_dense_act_bwd_workspace_bytes(int32_t K, int32_t N);
@@ -272,7 +273,8 @@ int mmrec_dense_act_batch_bwd_f32(const float *const *dY_host, const float *cons
  *   fwd -> side [n, d] (smore.py:339-340) and all = C + side (smore.py:341)
  *   bwd <- d_all, d_side (either may be NULL) -> dF, dV, dT, dC (dC includes d_all), dW[7], db[7]
  *          (db entries may be NULL); ws = mmrec_smore_side_bwd_workspace_bytes(n, d) of scratch.
- * Exact fp32 FMA arithmetic; gradients are bit-reproducible (partials added in a fixed order).
+ * Tile products on mma.sync tensor cores with the 3xTF32 split (fp32-class accuracy); gradients are
+ * bit-reproducible (partials added in a fixed order).
  * ---------------------------------------------------------------------------------------- */
 int mmrec_smore_side_supported(int32_t d);
 size_t mmrec_smore_side_bwd_workspace_bytes(int32_t n, int32_t d);
@@ -337,9 +339,10 @@ int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *users, int32
                               int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,
                               int32_t k, int32_t n_splits, float *ws_val, int32_t *ws_idx,
                               float *out_val, int64_t *out_idx, void *stream);
-/* The same contract on the CUDA-core (fp32 FMA) kernel: d = 128, K too large for the tensor-core
- * tiling, and the A/B baseline of bench.py. mmrec_score_mask_topk_f32 runs the tcgen05 kernel
- * (3xTF32 split, fp32-accurate) for d = 32 / 64 and this one otherwise. */
+/* The same contract on the CUDA-core (fp32 FMA) kernel: K too large for the shared-memory heaps of
+ * the tensor-core tiling, and the A/B baseline. mmrec_score_mask_topk_f32 runs the tcgen05 kernel
+ * (3xTF32 split, fp32-accurate; d = 128 with the user tile in TMEM) for d = 32 / 64 / 128 and this
+ * one otherwise. */
 int mmrec_score_mask_topk_simt_f32(const float *user_emb, const int64_t *users, int32_t n_users,
                                    const float *item_emb, int32_t n_items, int32_t item_offset,
                                    int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,

@@ -4,8 +4,8 @@
 // for X [M, K], W [N, K] with K, N in {32, 64, 128} (the embedding width): gate_v/t/f, query_v/t,
 // gate_*_prefer of SMORE (smore.py:265-272, 321-330) and the MGCN gates (mgcn.py:153-154,
 // 188-203). These GEMMs are tall and skinny (M = 7k..60k rows, K = N = 64): 0.2 GFLOP and 14 MB
-// each, so the exact fp32 FMA pipe finishes them in the time HBM needs to stream X and Y; what
-// matters is one pass over the operands and no intermediate tensors, not tensor cores.
+// each; the tile products run on mma.sync tensor cores with the 3xTF32 split (dense_tile.cuh), and
+// what matters most is one pass over the operands, no intermediate tensors and few launches.
 //
 // Tiling: 256 threads = (256 / (N/4)) row groups x (N/4) column groups; a thread owns TM rows x 4
 // columns. X tiles are staged row-major in shared memory (pitch K+4, conflict-free float4 reads:

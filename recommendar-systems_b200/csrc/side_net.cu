@@ -12,8 +12,9 @@
 // or shared memory, and only what the backward needs (hv, sv, ht, st, gi, gt, gf) is written.
 // The backward re-reads those, chains all seven dX products and dW outer products on the same
 // tiles and emits dF, dV, dT, dC plus per-CTA dW/db partials summed in a fixed order (no
-// floating-point atomics). fp32 FMA arithmetic throughout: 7 (fwd) + 14 (bwd) x n*d*d MACs, so
-// the kernels are FMA-bound (Baby: 0.76 / 1.5 GFMA), not HBM-bound.
+// floating-point atomics). The 7 (fwd) + 14 (bwd) tile products of n*d*d MACs run on mma.sync
+// tensor cores with the 3xTF32 split (fp32-class accuracy); the kernels are tensor/latency-bound
+// (Baby: 0.76 / 1.5 GFMA x 3), not HBM-bound.
 #include <stdlib.h>
 
 #include "dense_tile.cuh"

@@ -618,7 +618,7 @@ class _DenseAct(torch.autograd.Function):
 def dense_act(x, W, b=None, act=None):
     """act(F.linear(x, W, b)) for the d x d side-network layers in ONE launch (forward) and one
     launch + a partial-sum reduce (backward: dX, dW, db and the activation derivative together);
-    exact fp32. Other shapes: `linear` + torch activation."""
+    3xTF32 tensor-core products (fp32-class accuracy). Other shapes: `linear` + torch activation."""
     if x.dim() == 2 and x.is_cuda and lib.load().mmrec_dense_act_supported(W.shape[1], W.shape[0]):
         return _DenseAct.apply(x, W, b, _ACT_CODE[act])
     y = linear(x, W, b)
