@@ -197,3 +197,73 @@ def test_accelerate_passes_cpu_calls_through_untouched():
     with acc.accelerate() as mode:
         got = torch.sparse.mm(a, x)
     assert torch.equal(got, want) and mode.stats == {"spmm": 0, "converted": 0, "passed": 1}
+
+
+class _FakeLoader:
+    """Yields [3, B] LongTensors and records when batches are drawn (trainer.py:186 loop contract)."""
+
+    def __init__(self, n):
+        self.n, self.pr, self.drawn = n, 0, []
+
+    def __iter__(self):
+        self.pr = 0
+        return self
+
+    def __next__(self):
+        if self.pr >= self.n:
+            self.pr = 0
+            raise StopIteration
+        self.pr += 1
+        self.drawn.append(self.pr - 1)
+        return torch.full((3, 4), self.pr - 1, dtype=torch.long)
+
+
+class _FakeModel(torch.nn.Module):
+    def __init__(self, nan_at=None):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.ones(1))
+        self.nan_at, self.seen = nan_at, []
+
+    def calculate_loss(self, interaction):
+        b = int(interaction[0, 0])
+        self.seen.append(b)
+        loss = (self.w * float(b + 1)).sum()
+        return loss * float("nan") if b == self.nan_at else loss
+
+    def pre_epoch_processing(self):
+        pass
+
+
+def _host_trainer(model, sync_free):
+    cfg = pkg("config").Config("LightGCN", "tiny", {"device": torch.device("cpu"), "learner": "sgd",
+                                                    "learning_rate": 0.0, "sync_free": sync_free})
+    return pkg("trainer").Trainer(cfg, model)
+
+
+@pytest.mark.parametrize("sync_free", [True, False])
+def test_train_epoch_pipelined_loop_keeps_the_reference_contract(sync_free):
+    """trainer.py:186-203: every batch is trained once and in order, the epoch loss is the sum of the
+    per-batch losses, whether the loss is read back per batch (one step behind) or once per epoch."""
+    model, loader = _FakeModel(), _FakeLoader(7)
+    tr = _host_trainer(model, sync_free)
+    total, batches = tr._train_epoch(loader, 0)
+    assert model.seen == list(range(7)) and loader.drawn == list(range(7)) and len(batches) == 7
+    assert abs(total - sum(range(1, 8))) < 1e-6
+    # an abandoned epoch stops after max_batches and leaves the loader ready for a clean restart
+    model.seen.clear()
+    total, batches = tr._train_epoch(loader, 0, max_batches=3)
+    assert model.seen == [0, 1, 2] and len(batches) == 3 and abs(total - 6.0) < 1e-6 and loader.pr == 0
+
+
+def test_train_epoch_nan_aborts_like_the_reference_one_batch_late_at_most():
+    """trainer.py:201-203: a NaN loss ends the epoch with (loss, tensor(0.0)); with the lagged
+    read-back the abort comes at most one batch after the NaN."""
+    model, loader = _FakeModel(nan_at=2), _FakeLoader(7)
+    tr = _host_trainer(model, sync_free=False)
+    loss, flag = tr._train_epoch(loader, 0)
+    assert torch.is_tensor(loss) and bool(torch.isnan(loss)) and float(flag) == 0.0
+    assert model.seen[:3] == [0, 1, 2] and len(model.seen) <= 4
+    model2 = _FakeModel(nan_at=2)
+    tr2 = _host_trainer(model2, sync_free=True)
+    loss2, _ = tr2._train_epoch(_FakeLoader(7), 0)
+    assert torch.is_tensor(loss2) and bool(torch.isnan(loss2))
