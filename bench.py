@@ -387,7 +387,7 @@ def run_ours(args):
         "eval_users": n_eval, "eval_recall@20": metrics.get("recall@20"),
     }
     if world == 1:
-        line["cpu_baseline"] = cpu_baseline(env, steps=2, warmup=3)
+        line["cpu_baseline"] = cpu_baseline(env, steps=20, warmup=3)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
