@@ -453,6 +453,7 @@ def loss_head(o2, cl2, batch, reg_weight, train_batch_size, cl_weight):
     """o2 = bpr_table(...) sums, cl2 = infonce_pair(..., reduce=False); float32 reciprocals as torch's
     division by a host scalar."""
     import numpy as np
+    lib.require_cuda(o2, cl2)
     inv_b = float(np.float32(1.0) / np.float32(batch))
     inv_bs = float(np.float32(1.0) / np.float32(train_batch_size))
     return _LossHead.apply(o2, cl2, inv_b, reg_weight, inv_bs, cl_weight)
@@ -535,6 +536,7 @@ def inject3(item, g0, g1, g2, scale):
 
 def colsum(x):
     """x.sum(0) of a row-major [M, N] CUDA matrix (N % 4 == 0) in one launch (mmrec_colsum_f32)."""
+    lib.require_cuda(x)
     x = _f32c(x)
     out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
     lib.call("mmrec_colsum_f32", lib.ptr(x), x.shape[0], x.shape[1], lib.ptr(out), lib.stream())

@@ -182,9 +182,27 @@ def test_product_does_not_import_oracle():
 
 
 def test_ops_fail_loudly_without_cuda():
+    """No CPU / eager fallback anywhere on the product path: host tensors are an error."""
     ops, graph = pkg("ops"), pkg("graph")
     with pytest.raises(RuntimeError):
         graph.build_ui_graph(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 2, 2, "f32")
+    x = torch.randn(8, 64)
+    W, b = torch.randn(64, 64), torch.randn(64)
+    idx = torch.zeros(4, dtype=torch.int64)
+    calls = [
+        lambda: ops.linear(x, W, b),
+        lambda: ops.colsum(x),
+        lambda: ops.inject3(x, x, x, x, 0.7),
+        lambda: ops.knn_graph(x, 2, "sym"),
+        lambda: ops.spectrum_convolution(x, x, torch.randn(33, 2), torch.randn(33, 2), torch.randn(33, 2)),
+        lambda: ops.bpr_table(x, 4, idx, idx, idx),
+        lambda: ops.infonce_pair(x, x, 4, idx, idx, 0.2),
+        lambda: ops.score_mask_topk(x, idx, x, 2),
+        lambda: ops.loss_head(torch.zeros(2), torch.zeros(2), 4, 0.1, 4, 0.1),
+    ]
+    for i, fn in enumerate(calls):
+        with pytest.raises((RuntimeError, ValueError), match=None):
+            fn()
 
 
 def test_accelerate_passes_cpu_calls_through_untouched():
