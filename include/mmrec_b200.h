@@ -302,7 +302,10 @@ int mmrec_adam_step_f32(float *const *params_host, const float *const *grads_hos
                         float *const *exp_avg_host, float *const *exp_avg_sq_host,
                         const int64_t *numel_host, int32_t n_tensors, double *hyper, double beta1,
                         double beta2, double eps, double weight_decay, double grad_scale,
-                        const float *const *undo_host, const float *undo_coef, void *stream);
+                        const float *const *undo_host, const float *undo_coef, int32_t tick, void *stream);
+/* tick = 1: increment the update count hyper[1] first (the normal case); 0 when another entry point
+ * of the same optimizer step (mmrec_table_adam_lowrank_f32, mmrec_adam_tick) already has. */
+int mmrec_adam_tick(double *hyper, void *stream);
 /* undo_host / undo_coef (both NULL, or n_tensors device pointers + a device scalar): every
  * parameter is first moved by p += undo_coef[0] * undo_t, the return from the mirror point
  * theta - c*g to theta (trainer.py:322-329), in the same pass that applies the update.
@@ -316,7 +319,38 @@ size_t mmrec_mirror_coef_workspace_bytes(const int64_t *numel_host, int32_t n_te
 int mmrec_mirror_coef_f32(const float *const *params_host, const float *const *grads_host,
                           const int64_t *numel_host, int32_t n_tensors, const double *hyper,
                           double numel_total, double alpha_base, double alpha_max_scale,
-                          double target_rel_step, void *workspace, float *coef_out, void *stream);
+                          double target_rel_step, const double *extra, int32_t n_extra_p2,
+                          int32_t n_extra_g2, void *workspace, float *coef_out, void *stream);
+/* extra (device doubles, may be NULL with both counts 0): extra[0 .. n_extra_p2) are added to
+ * sum theta^2 and extra[n_extra_p2 .. n_extra_p2 + n_extra_g2) to sum g^2 -- the contributions of
+ * tensors whose gradient is a never-materialised low-rank product (below); numel_total counts
+ * their elements too.
+ *
+ * ------------------------------------------------------------------------------------------
+ * Feature tables with a rank-d gradient. The trainable image / text tables X [I, F] (F = 4096 /
+ * 384; smore.py:76-77, mgcn.py:62-72, freedom.py:48-55) enter the model only through
+ * Y = X W^T + b (smore.py:257-259), so their gradient is G = dY W with dY [I, d], W [d, F]: a
+ * 115 MB tensor that torch writes in the backward and re-reads in every optimizer / mirror-gradient
+ * pass (trainer.py:268-335). It is never materialised here: tcgen05 computes each 128 x 64 tile of
+ * G (3xTF32, the products of the dX GEMM of mmrec_gemm_tf32x3_f32) into TMEM and the epilogue
+ * consumes it on the spot.
+ *   mmrec_table_adam_lowrank_f32: optim.Adam.step on X with g = grad_scale * (dY W): reads and
+ *     writes X / exp_avg / exp_avg_sq once (24 B per element instead of 28 + the 4 of writing G).
+ *     Must be enqueued BEFORE the Adam update of W itself. tick as in mmrec_adam_step_f32.
+ *     sumsq_out (device double or NULL) receives sum X'^2 of the updated table.
+ *   mmrec_table_lowrank_sumsq_f64: out = ||dY W||_F^2 (for mmrec_mirror_coef_f32's `extra`).
+ * cols % 64 == 0, d in {32, 64, 128}, 16-byte aligned rows; workspace of
+ * mmrec_table_lowrank_workspace_bytes(rows, cols) bytes.
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_table_lowrank_supported(int32_t rows, int32_t cols, int32_t d);
+size_t mmrec_table_lowrank_workspace_bytes(int32_t rows, int32_t cols);
+int mmrec_table_adam_lowrank_f32(float *table, float *exp_avg, float *exp_avg_sq, const float *dY,
+                                 const float *W, int32_t rows, int32_t cols, int32_t d, double *hyper,
+                                 double beta1, double beta2, double eps, double weight_decay,
+                                 double grad_scale, int32_t tick, double *sumsq_out, void *workspace,
+                                 void *stream);
+int mmrec_table_lowrank_sumsq_f64(const float *dY, const float *W, int32_t rows, int32_t cols, int32_t d,
+                                  void *workspace, double *out, void *stream);
 /* y_t += sign * coef[0] * x_t for n_tensors tensors in one launch; coef is a device scalar
  * (the mirror-gradient perturbation theta -/+ alpha_eff*lr*g of trainer.py:307-329 without a
  * host round trip for alpha_eff). */
@@ -387,6 +421,31 @@ int mmrec_loss_head_bwd_f32(const float *g, float inv_batch, float reg_weight, f
                             float cl_weight, float *d_o2, float *d_cl2, void *stream);
 int mmrec_knn_weights_f32(const int32_t *idx, const float *val, int32_t n, int32_t k, int32_t mode, float *dis_ws,
                           float *out_vals, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MGCN's two-way attention fuser (models/mgcn.py:188-205), one launch each way. Replaces
+ *   att = softmax(cat([query_common(image_embeds), query_common(text_embeds)], -1))   (the
+ *         Linear(d, 1) of query_common is the row dot with w2 = query_common.2.weight [1, d])
+ *   common = att[:, 0] * image_embeds + att[:, 1] * text_embeds
+ *   sep_m  = gate_m_prefer(content) * (m_embeds - common);  side = (sep_i + sep_t + common) / 3
+ *   all    = content + side
+ * Hi / Ht = tanh(query_common.0(E_m)) and Pi / Pt = sigmoid(gate_*_prefer.0(content)) come from
+ * mmrec_dense_act_batch_fwd_f32. All row tensors are [n_rows, d] float32 row-major, d in
+ * {32, 64, 128}; att [n_rows, 2] is written forward and read backward.
+ * Backward: g_all / g_side may be NULL (not both); dw2_partial is scratch of
+ * mmrec_mgcn_fuse_bwd_blocks(n_rows, d) * d floats (per-CTA column sums in fixed order; the
+ * final sum goes to dw2 [d] with mmrec_colsum_f32: no float atomics).
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_mgcn_fuse_supported(int32_t d);
+int32_t mmrec_mgcn_fuse_bwd_blocks(int32_t n_rows, int32_t d);
+int mmrec_mgcn_fuse_fwd_f32(const float *Hi, const float *Ht, const float *w2, const float *Ei, const float *Et,
+                            const float *Pi, const float *Pt, const float *content, int32_t n_rows, int32_t d,
+                            float *att, float *side, float *all, void *stream);
+int mmrec_mgcn_fuse_bwd_f32(const float *g_all, const float *g_side, const float *Hi, const float *Ht,
+                            const float *w2, const float *Ei, const float *Et, const float *Pi, const float *Pt,
+                            const float *att, int32_t n_rows, int32_t d, float *dHi, float *dHt, float *dEi,
+                            float *dEt, float *dPi, float *dPt, float *dC, float *dw2_partial, float *dw2,
+                            void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Top-K metrics on the device (K15). Replaces TopKEvaluator.evaluate / _calculate_metrics

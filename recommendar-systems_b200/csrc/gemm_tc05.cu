@@ -54,6 +54,13 @@ struct GemmArgs {
   int kb_per_split;                 // K blocks per blockIdx.y
   int nt_per_cta;                   // N tiles per blockIdx.z
   size_t slab;                      // floats between the output slabs of consecutive K splits
+  // EPI_ADAM: the product tile is a gradient that is never stored -- it is applied to the parameter
+  // tile it belongs to (C = parameters, in place) with the Adam moments beside it
+  float *exp_avg, *exp_avg_sq;
+  const double *hyper;              // device: [lr, update count]
+  double beta1, beta2;
+  float eps, weight_decay, grad_scale;
+  double *sumsq_partial;            // optional: per-CTA sum of the updated parameters' squares
 };
 
 // Byte offset of element chunk inside one operand tile (extent E along M/N, 32 along K).
@@ -101,26 +108,34 @@ struct Block {
   }
 };
 
-template <int NT>
+enum { EPI_STORE = 0, EPI_ADAM = 1, EPI_SUMSQ = 2 };
+
+template <int NT, int EPI_MODE = EPI_STORE>
 struct GCfg {
   static constexpr uint32_t A_HALF = kBM * 128, B_HALF = NT * 128;
   static constexpr uint32_t STAGE = 2 * (A_HALF + B_HALF);
-  static constexpr int STAGES = NT <= 32 ? 4 : NT <= 64 ? 3 : 2;
-  static constexpr uint32_t EPI = 4 * 32 * (NT + 4) * 4;   // epilogue staging: 4 warps x [32][NT + 4] floats
+  // EPI_ADAM keeps the parameter / moment tiles of every epilogue warp in shared memory (3 x the
+  // staging of a plain store): two operand stages (one K = 64 tile) are all that is left, and all
+  // that is needed -- the epilogue (HBM streaming) is several times longer than a tile's products
+  static constexpr int STAGES = EPI_MODE == EPI_ADAM ? 2 : NT <= 32 ? 4 : NT <= 64 ? 3 : 2;
+  // epilogue staging: 4 warps x [32][NT + 4] floats (x 3 arrays for EPI_ADAM)
+  static constexpr uint32_t EPI = (EPI_MODE == EPI_ADAM ? 3 : 1) * 4 * 32 * (NT + 4) * 4;
+  static constexpr int EXTRA_BARS = EPI_MODE == EPI_ADAM ? 4 : 0;     // one mbarrier per epilogue warp
   static constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
   static constexpr int GROUPS = NT >= 128 ? 2 : 4;          // independent producer groups
   static constexpr int GROUP_THREADS = kProdThreads / GROUPS;
 };
 
-template <bool A_MN, bool B_MN, int NT, bool TRANS_OUT>
+template <bool A_MN, bool B_MN, int NT, bool TRANS_OUT, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(kThreadsG, 1)
 gemm_tc05_kernel(const GemmArgs g) {
-  using C = GCfg<NT>;
+  using C = GCfg<NT, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE);
   uint64_t *full = bars, *empty = bars + C::STAGES, *tfull = empty + C::STAGES, *tempty = tfull + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  uint64_t *pbar = tempty + 2;                               // EPI_ADAM: tile-landed barrier per epilogue warp
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pbar + C::EXTRA_BARS);
   volatile int *passed = reinterpret_cast<volatile int *>(tmem_slot + 1);   // producer wait chain (see below)
   float *stg = reinterpret_cast<float *>(tmem_slot + 4);     // 4 warps x [32][NT + 4] epilogue staging
 
@@ -140,6 +155,7 @@ gemm_tc05_kernel(const GemmArgs g) {
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, C::GROUP_THREADS); mbar_init(empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
+    for (int b = 0; b < C::EXTRA_BARS; ++b) mbar_init(pbar + b, 1);
     *passed = 0;
     fence_barrier_init();
   }
@@ -225,8 +241,34 @@ gemm_tc05_kernel(const GemmArgs g) {
     // the chunks are added here in registers with round-to-nearest (fp32-class accuracy at K = 20k+).
     const int m = m0 + warp * 32 + lane;
     float *Cs = g.C + (size_t)blockIdx.y * g.slab;
+    // EPI_ADAM: bias-corrected step size and sqrt(bias_correction2) exactly as adam_kernel (optim.cu)
+    float step_size = 0.f, bc2_sqrt = 1.f, p2_acc = 0.f;
+    if constexpr (EPI == EPI_ADAM) {
+      const double lr = g.hyper[0], step = g.hyper[1];
+      step_size = (float)(lr / (1.0 - pow(g.beta1, step)));
+      bc2_sqrt = (float)sqrt(1.0 - pow(g.beta2, step));
+    }
+    // EPI_ADAM: this warp's 32 rows x NT columns of the table and of both moments travel HBM ->
+    // shared memory -> HBM as bulk asynchronous copies (one NT-float row segment per lane and
+    // array): no registers and no LSU address work are spent on the 24 bytes per element that bound
+    // this kernel, and the whole tile (3 x 32 x NT x 4 bytes per warp) is in flight at once.
+    constexpr int PP = NT + 4;
+    float *pmv = stg + warp * (3 * 32 * PP);
+    const int rows_valid = min(32, g.M - (m0 + warp * 32));
     for (int j = 0; j < (n_kb > 0 ? n_nt : 0); ++j) {
       const int n0 = (nt_begin + j) * NT;
+      if constexpr (EPI == EPI_ADAM) {
+        if (j > 0) bulk_wait_read();                 // the stores of tile j - 1 have left shared memory
+        __syncwarp();
+        if (lane == 0 && rows_valid > 0) mbar_arrive_expect_tx(pbar + warp, (uint32_t)rows_valid * 3u * NT * 4u);
+        __syncwarp();
+        if (lane < rows_valid) {
+          const size_t o = (size_t)(m0 + warp * 32 + lane) * g.ldc + n0;
+          bulk_load(pmv + lane * PP, g.C + o, NT * 4, pbar + warp);
+          bulk_load(pmv + (32 + lane) * PP, g.exp_avg + o, NT * 4, pbar + warp);
+          bulk_load(pmv + (64 + lane) * PP, g.exp_avg_sq + o, NT * 4, pbar + warp);
+        }
+      }
       float acc[NT];
 #pragma unroll
       for (int q = 0; q < NT; ++q) acc[q] = 0.f;
@@ -245,6 +287,50 @@ gemm_tc05_kernel(const GemmArgs g) {
         }
         fence_before_sync();
         mbar_arrive(tempty + buf);
+      }
+      if constexpr (EPI == EPI_ADAM) {
+        // lane = table row (the TMEM lane): acc[] is that row's gradient G = dY W. Same float
+        // operations in the same order as adam_kernel (optim.cu), on the row held in shared memory.
+        if (rows_valid > 0) mbar_wait(pbar + warp, j & 1);
+        if (lane < rows_valid) {
+          const float beta2 = (float)g.beta2, w1 = (float)(1.0 - g.beta1), w2 = (float)(1.0 - g.beta2);
+          float *pr = pmv + lane * PP, *mr = pmv + (32 + lane) * PP, *vr = pmv + (64 + lane) * PP;
+#pragma unroll
+          for (int q = 0; q < NT; q += 4) {
+            float4 p4 = *reinterpret_cast<float4 *>(pr + q), m4 = *reinterpret_cast<float4 *>(mr + q),
+                   v4 = *reinterpret_cast<float4 *>(vr + q);
+            auto upd = [&](float &p_, float g_, float &m_, float &v_) {
+              g_ *= g.grad_scale;
+              if (g.weight_decay != 0.f) g_ = fmaf(g.weight_decay, p_, g_);
+              m_ = m_ + w1 * (g_ - m_);
+              v_ = v_ * beta2 + w2 * g_ * g_;
+              const float denom = sqrtf(v_) / bc2_sqrt + g.eps;
+              p_ = p_ - step_size * (m_ / denom);
+              p2_acc = fmaf(p_, p_, p2_acc);
+            };
+            upd(p4.x, acc[q], m4.x, v4.x); upd(p4.y, acc[q + 1], m4.y, v4.y);
+            upd(p4.z, acc[q + 2], m4.z, v4.z); upd(p4.w, acc[q + 3], m4.w, v4.w);
+            *reinterpret_cast<float4 *>(pr + q) = p4;
+            *reinterpret_cast<float4 *>(mr + q) = m4;
+            *reinterpret_cast<float4 *>(vr + q) = v4;
+          }
+          fence_proxy_async_smem();                  // this lane's row writes -> visible to the copy engine
+          const size_t o = (size_t)(m0 + warp * 32 + lane) * g.ldc + n0;
+          bulk_store(g.C + o, pr, NT * 4);
+          bulk_store(g.exp_avg + o, mr, NT * 4);
+          bulk_store(g.exp_avg_sq + o, vr, NT * 4);
+          bulk_commit();
+        }
+        continue;
+      }
+      if constexpr (EPI == EPI_SUMSQ) {
+        // sum of squares of the product itself (the squared norm of a gradient that is never stored)
+        if (m < g.M) {
+#pragma unroll
+          for (int q = 0; q < NT; ++q)
+            if (n0 + q < g.N) p2_acc = fmaf(acc[q], acc[q], p2_acc);
+        }
+        continue;
       }
       if constexpr (!TRANS_OUT) {
         // TMEM hands every thread one ROW; storing it as-is touches 32 different 128-byte lines per
@@ -281,6 +367,23 @@ gemm_tc05_kernel(const GemmArgs g) {
       }
       __syncwarp();
     }
+    if constexpr (EPI == EPI_ADAM) bulk_wait_all();          // this thread's last stores are performed
+    if constexpr (EPI != EPI_STORE) {
+      // EPI_ADAM: sum of the updated parameters' squares of this CTA -- the mirror-gradient step size
+      // needs sum theta^2 right after this update (trainer.py:289-305), and this pass already holds
+      // every theta in registers. EPI_SUMSQ: sum of the squared products. Fixed order: lanes by
+      // butterfly, the four warps by index.
+      if (g.sumsq_partial != nullptr) {
+        const float w = warp_sum(p2_acc);
+        asm volatile("bar.sync 9, 128;" ::: "memory");      // every epilogue warp is done with its staging tile
+        if (lane == 0) stg[warp] = w;
+        asm volatile("bar.sync 9, 128;" ::: "memory");
+        if (tid == 0) {
+          const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+          g.sumsq_partial[cta] = ((double)stg[0] + (double)stg[1]) + ((double)stg[2] + (double)stg[3]);
+        }
+      }
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -303,6 +406,22 @@ int launch_tc05(const GemmArgs &g, int k_splits, int n_chunks, cudaStream_t stre
   dim3 grid((g.M + kBM - 1) / kBM, k_splits, n_chunks);
   kern<<<grid, kThreadsG, smem, stream>>>(g);
   MMREC_CHECK_LAUNCH("gemm_tc05_kernel");
+  return MMREC_OK;
+}
+
+template <int NT, int EPI>
+int launch_table_epi(const GemmArgs &g, int n_chunks, cudaStream_t stream) {
+  using C = GCfg<NT, EPI>;
+  const size_t smem = 1024 + (size_t)C::STAGES * C::STAGE + (2 * C::STAGES + 4 + C::EXTRA_BARS) * 8 + 16 + C::EPI;
+  auto kern = gemm_tc05_kernel<false, true, NT, false, EPI>;
+  static bool attr = false;
+  if (!attr) {
+    MMREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid((g.M + kBM - 1) / kBM, 1, n_chunks);
+  kern<<<grid, kThreadsG, smem, stream>>>(g);
+  MMREC_CHECK_LAUNCH(EPI == EPI_ADAM ? "gemm_tc05_kernel<adam>" : "gemm_tc05_kernel<sumsq>");
   return MMREC_OK;
 }
 
@@ -392,6 +511,42 @@ int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcon
   chunks = (n_tiles + g.nt_per_cta - 1) / g.nt_per_cta;
   if (nt == 64) return launch_tc05<false, true, 64, false>(g, 1, chunks, stream);
   return launch_tc05<false, true, 128, false>(g, 1, chunks, stream);
+}
+
+
+// ---- Adam on a feature table whose gradient is the rank-d product dY W (never materialised) ----
+int table_adam_grid(int rows, int cols, int *nt_per_cta) {
+  const int m_tiles = (rows + kBM - 1) / kBM, n_tiles = cols / 64;
+  int chunks = best_parts(m_tiles, n_tiles, n_tiles, 1);
+  const int per = (n_tiles + chunks - 1) / chunks;
+  chunks = (n_tiles + per - 1) / per;
+  if (nt_per_cta) *nt_per_cta = per;
+  return m_tiles * chunks;
+}
+
+int table_adam_dispatch(float *P, float *Mo, float *V, const float *dY, const float *W, int rows, int cols, int d,
+                        const double *hyper, double beta1, double beta2, double eps, double weight_decay,
+                        double grad_scale, double *sumsq_partial, cudaStream_t stream) {
+  GemmArgs g{};
+  g.A = dY; g.lda = d; g.B = W; g.ldb = cols; g.C = P; g.ldc = cols; g.M = rows; g.N = cols; g.K = d;
+  g.kb_per_split = (d + kKB - 1) / kKB;
+  g.exp_avg = Mo; g.exp_avg_sq = V; g.hyper = hyper; g.beta1 = beta1; g.beta2 = beta2; g.eps = (float)eps;
+  g.weight_decay = (float)weight_decay; g.grad_scale = (float)grad_scale; g.sumsq_partial = sumsq_partial;
+  const int ctas = table_adam_grid(rows, cols, &g.nt_per_cta);
+  const int m_tiles = (rows + kBM - 1) / kBM;
+  return launch_table_epi<64, EPI_ADAM>(g, ctas / m_tiles, stream);
+}
+
+// per-CTA partial sums of ||dY W||_F^2 (same grid as table_adam_dispatch)
+int table_sumsq_dispatch(const float *dY, const float *W, int rows, int cols, int d, double *sumsq_partial,
+                         cudaStream_t stream) {
+  GemmArgs g{};
+  g.A = dY; g.lda = d; g.B = W; g.ldb = cols; g.C = nullptr; g.ldc = cols; g.M = rows; g.N = cols; g.K = d;
+  g.kb_per_split = (d + kKB - 1) / kKB;
+  g.sumsq_partial = sumsq_partial;
+  const int ctas = table_adam_grid(rows, cols, &g.nt_per_cta);
+  const int m_tiles = (rows + kBM - 1) / kBM;
+  return launch_table_epi<64, EPI_SUMSQ>(g, ctas / m_tiles, stream);
 }
 
 }  // namespace mmrec

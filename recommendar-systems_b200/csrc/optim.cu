@@ -142,8 +142,9 @@ sumsq_pair_kernel(const __grid_constant__ AxpyPack pack, double *__restrict__ pa
 }
 
 __global__ void __launch_bounds__(kThreads)
-mirror_coef_kernel(const double *__restrict__ partial, int n_parts, const double *__restrict__ hyper, double numel,
-                   float alpha_base, float alpha_max_scale, float target_rel, float *__restrict__ out) {
+mirror_coef_kernel(const double *__restrict__ partial, int n_parts, const double *__restrict__ extra, int n_extra_p2,
+                   int n_extra_g2, const double *__restrict__ hyper, double numel, float alpha_base,
+                   float alpha_max_scale, float target_rel, float *__restrict__ out) {
   __shared__ double sh[2][kThreads];
   double a = 0.0, b = 0.0;
   for (int i = threadIdx.x; i < n_parts; i += kThreads) { a += partial[2 * (size_t)i]; b += partial[2 * (size_t)i + 1]; }
@@ -153,6 +154,9 @@ mirror_coef_kernel(const double *__restrict__ partial, int n_parts, const double
   if (threadIdx.x == 0) {
     double p2 = 0.0, g2 = 0.0;
     for (int i = 0; i < kThreads; ++i) { p2 += sh[0][i]; g2 += sh[1][i]; }
+    // tensors whose gradient is a never-materialised low-rank product bring their two sums along
+    for (int i = 0; i < n_extra_p2; ++i) p2 += extra[i];
+    for (int i = 0; i < n_extra_g2; ++i) g2 += extra[n_extra_p2 + i];
     // float32 arithmetic in the order of the reference's tensor expression
     const float lr = (float)hyper[0], n = (float)numel;
     const float grad_rms = sqrtf((float)g2 / n);
@@ -196,18 +200,28 @@ axpy_multi_kernel(const __grid_constant__ AxpyPack pack, const float *__restrict
 
 using namespace mmrec;
 
+extern "C" int mmrec_adam_tick(double *hyper, void *stream) {
+  MMREC_REQUIRE(hyper, MMREC_E_BADARG, "adam_tick: null pointer");
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+  MMREC_CHECK_LAUNCH("adam_tick_kernel");
+  return MMREC_OK;
+}
+
 extern "C" int mmrec_adam_step_f32(float *const *params_host, const float *const *grads_host,
                                    float *const *exp_avg_host, float *const *exp_avg_sq_host,
                                    const int64_t *numel_host, int32_t n_tensors, double *hyper, double beta1,
                                    double beta2, double eps, double weight_decay, double grad_scale,
-                                   const float *const *undo_host, const float *undo_coef, void *stream) {
+                                   const float *const *undo_host, const float *undo_coef, int32_t tick,
+                                   void *stream) {
   MMREC_REQUIRE(params_host && grads_host && exp_avg_host && exp_avg_sq_host && numel_host && hyper,
                 MMREC_E_BADARG, "adam: null pointer");
   MMREC_REQUIRE((undo_host == nullptr) == (undo_coef == nullptr), MMREC_E_BADARG,
                 "adam: undo tensors and undo coefficient must be given together");
   MMREC_REQUIRE(n_tensors >= 0, MMREC_E_BADARG, "adam: bad sizes");
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
-  MMREC_CHECK_LAUNCH("adam_tick_kernel");
+  if (tick) {
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+    MMREC_CHECK_LAUNCH("adam_tick_kernel");
+  }
   for (int base = 0; base < n_tensors; base += kMaxTensors) {
     AdamPack pack;
     pack.n_tensors = min(kMaxTensors, n_tensors - base);
@@ -268,7 +282,8 @@ extern "C" size_t mmrec_mirror_coef_workspace_bytes(const int64_t *numel_host, i
 extern "C" int mmrec_mirror_coef_f32(const float *const *params_host, const float *const *grads_host,
                                      const int64_t *numel_host, int32_t n_tensors, const double *hyper,
                                      double numel_total, double alpha_base, double alpha_max_scale,
-                                     double target_rel_step, void *workspace, float *coef_out, void *stream) {
+                                     double target_rel_step, const double *extra, int32_t n_extra_p2,
+                                     int32_t n_extra_g2, void *workspace, float *coef_out, void *stream) {
   MMREC_REQUIRE(params_host && grads_host && numel_host && hyper && workspace && coef_out, MMREC_E_BADARG,
                 "mirror_coef: null pointer");
   MMREC_REQUIRE(n_tensors > 0 && numel_total > 0, MMREC_E_BADARG, "mirror_coef: bad sizes");
@@ -293,9 +308,93 @@ extern "C" int mmrec_mirror_coef_f32(const float *const *params_host, const floa
     MMREC_CHECK_LAUNCH("sumsq_pair_kernel");
     done += chunks;
   }
-  mirror_coef_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(partial, done, hyper, numel_total, (float)alpha_base,
+  MMREC_REQUIRE(n_extra_p2 >= 0 && n_extra_g2 >= 0 && (extra != nullptr || n_extra_p2 + n_extra_g2 == 0),
+                MMREC_E_BADARG, "mirror_coef: bad extra sums");
+  mirror_coef_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(partial, done, extra, n_extra_p2, n_extra_g2, hyper,
+                                                             numel_total, (float)alpha_base,
                                                              (float)alpha_max_scale, (float)target_rel_step,
                                                              coef_out);
   MMREC_CHECK_LAUNCH("mirror_coef_kernel");
+  return MMREC_OK;
+}
+
+// ---- feature tables whose gradient is the rank-d product dY W (SMORE / MGCN / FREEDOM image and
+// text tables: d x 4096 / d x 384 projections, smore.py:257-259) -------------------------------
+namespace mmrec {
+int table_adam_grid(int rows, int cols, int *nt_per_cta);
+int table_adam_dispatch(float *P, float *Mo, float *V, const float *dY, const float *W, int rows, int cols, int d,
+                        const double *hyper, double beta1, double beta2, double eps, double weight_decay,
+                        double grad_scale, double *sumsq_partial, cudaStream_t stream);
+int table_sumsq_dispatch(const float *dY, const float *W, int rows, int cols, int d, double *sumsq_partial,
+                         cudaStream_t stream);
+namespace {
+__global__ void __launch_bounds__(kThreads) sum_partials_kernel(const double *__restrict__ partial, int n,
+                                                                double *__restrict__ out) {
+  __shared__ double sh[kThreads];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += kThreads) a += partial[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kThreads; ++i) t += sh[i];
+    out[0] = t;
+  }
+}
+bool lowrank_shape_ok(int rows, int cols, int d) {
+  return rows > 0 && cols > 0 && cols % 64 == 0 && (d == 32 || d == 64 || d == 128);
+}
+}  // namespace
+}  // namespace mmrec
+
+extern "C" int mmrec_table_lowrank_supported(int32_t rows, int32_t cols, int32_t d) {
+  return lowrank_shape_ok(rows, cols, d);
+}
+
+extern "C" size_t mmrec_table_lowrank_workspace_bytes(int32_t rows, int32_t cols) {
+  if (rows <= 0 || cols <= 0 || cols % 64) return 0;
+  return sizeof(double) * (size_t)table_adam_grid(rows, cols, nullptr);
+}
+
+extern "C" int mmrec_table_adam_lowrank_f32(float *table, float *exp_avg, float *exp_avg_sq, const float *dY,
+                                            const float *W, int32_t rows, int32_t cols, int32_t d, double *hyper,
+                                            double beta1, double beta2, double eps, double weight_decay,
+                                            double grad_scale, int32_t tick, double *sumsq_out, void *workspace,
+                                            void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMREC_REQUIRE(table && exp_avg && exp_avg_sq && dY && W && hyper, MMREC_E_BADARG, "table_adam: null pointer");
+  MMREC_REQUIRE(lowrank_shape_ok(rows, cols, d), MMREC_E_BADARG,
+                "table_adam: need cols %% 64 == 0 and d in {32, 64, 128} (got %d x %d, d = %d)", rows, cols, d);
+  MMREC_REQUIRE(aligned16(table) && aligned16(exp_avg) && aligned16(exp_avg_sq) && aligned16(dY) && aligned16(W),
+                MMREC_E_ALIGN, "table_adam: operands must be 16-byte aligned");
+  MMREC_REQUIRE(sumsq_out == nullptr || workspace != nullptr, MMREC_E_WORKSPACE,
+                "table_adam: the parameter square sum needs the workspace");
+  if (tick) {
+    adam_tick_kernel<<<1, 1, 0, stream>>>(hyper);
+    MMREC_CHECK_LAUNCH("adam_tick_kernel");
+  }
+  double *partial = sumsq_out ? static_cast<double *>(workspace) : nullptr;
+  const int rc = table_adam_dispatch(table, exp_avg, exp_avg_sq, dY, W, rows, cols, d, hyper, beta1, beta2, eps,
+                                     weight_decay, grad_scale, partial, stream);
+  if (rc != MMREC_OK) return rc;
+  if (sumsq_out) {
+    sum_partials_kernel<<<1, kThreads, 0, stream>>>(partial, table_adam_grid(rows, cols, nullptr), sumsq_out);
+    MMREC_CHECK_LAUNCH("sum_partials_kernel");
+  }
+  return MMREC_OK;
+}
+
+extern "C" int mmrec_table_lowrank_sumsq_f64(const float *dY, const float *W, int32_t rows, int32_t cols, int32_t d,
+                                             void *workspace, double *out, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMREC_REQUIRE(dY && W && workspace && out, MMREC_E_BADARG, "table_sumsq: null pointer");
+  MMREC_REQUIRE(lowrank_shape_ok(rows, cols, d), MMREC_E_BADARG,
+                "table_sumsq: need cols %% 64 == 0 and d in {32, 64, 128} (got %d x %d, d = %d)", rows, cols, d);
+  MMREC_REQUIRE(aligned16(dY) && aligned16(W), MMREC_E_ALIGN, "table_sumsq: operands must be 16-byte aligned");
+  double *partial = static_cast<double *>(workspace);
+  const int rc = table_sumsq_dispatch(dY, W, rows, cols, d, partial, stream);
+  if (rc != MMREC_OK) return rc;
+  sum_partials_kernel<<<1, kThreads, 0, stream>>>(partial, table_adam_grid(rows, cols, nullptr), out);
+  MMREC_CHECK_LAUNCH("sum_partials_kernel");
   return MMREC_OK;
 }

@@ -58,11 +58,21 @@ SIGNATURES = {
     "mmrec_smore_side_fwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "mmrec_smore_side_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                            _p, _i32, _i32, _p]),
+    "mmrec_mgcn_fuse_supported": (C.c_int, [_i32]),
+    "mmrec_mgcn_fuse_bwd_blocks": (_i32, [_i32, _i32]),
+    "mmrec_mgcn_fuse_fwd_f32": (C.c_int, [_p] * 8 + [_i32, _i32, _p, _p, _p, _p]),
+    "mmrec_mgcn_fuse_bwd_f32": (C.c_int, [_p] * 10 + [_i32, _i32] + [_p] * 10),
     "mmrec_adam_step_f32": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double,
-                                      C.c_double, C.c_double, _p, _p, _p]),
+                                      C.c_double, C.c_double, _p, _p, _i32, _p]),
+    "mmrec_adam_tick": (C.c_int, [_p, _p]),
     "mmrec_mirror_coef_workspace_bytes": (_sz, [_p, _i32]),
     "mmrec_mirror_coef_f32": (C.c_int, [_p, _p, _p, _i32, _p, C.c_double, C.c_double, C.c_double, C.c_double,
-                                        _p, _p, _p]),
+                                        _p, _i32, _i32, _p, _p, _p]),
+    "mmrec_table_lowrank_supported": (C.c_int, [_i32, _i32, _i32]),
+    "mmrec_table_lowrank_workspace_bytes": (_sz, [_i32, _i32]),
+    "mmrec_table_adam_lowrank_f32": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, C.c_double, C.c_double,
+                                               C.c_double, C.c_double, C.c_double, _i32, _p, _p, _p]),
+    "mmrec_table_lowrank_sumsq_f64": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "mmrec_axpy_multi_f32": (C.c_int, [_p, _p, _p, _i32, _p, _f32, _p]),
     "mmrec_inject3_fwd_f32": (C.c_int, [_p, _p, _p, _p, _f32, _i64, _p, _p, _p, _p]),
     "mmrec_inject3_bwd_f32": (C.c_int, [_p, _p, _p, _f32, _i64, _p, _p, _p, _p, _p]),
@@ -110,11 +120,30 @@ def load():
     return _lib
 
 
+def _check_device(t):
+    """Kernels are enqueued on the CURRENT device's current stream (see `stream`): a tensor that
+    lives on another GPU would be dereferenced by the wrong device, so that is an error here
+    (torch ops switch devices by themselves; this library asks the caller to
+    `torch.cuda.set_device` / `with torch.cuda.device(...)` first)."""
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"mmrec_b200: tensor on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device(tensor.device)")
+
+
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
+    """Device pointer of a tensor (None -> NULL); the tensor must live on the current device."""
     if t is None:
         return None
+    _check_device(t)
     return t.data_ptr()
+
+
+def ptr_array(tensors):
+    """void*[n] of device pointers (None -> NULL) for the batched entry points."""
+    for t in tensors:
+        if t is not None:
+            _check_device(t)
+    return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
 
 
 def stream():

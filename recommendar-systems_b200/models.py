@@ -106,6 +106,11 @@ class GeneralRecommender(AbstractRecommender):
     def _project(self, emb, trs):
         """`trs(emb.weight)`; sharded tables: local rows projected, slices all-gathered."""
         if self._table_rows is None:
+            # training through the fused optimizer: the [I, F] gradient stays the rank-d product
+            # dY W (ops.LowRankGrad); the Trainer switches this on when its optimizer consumes it
+            if (getattr(self, "lowrank_table_grad", False) and torch.is_grad_enabled() and
+                    emb.weight.requires_grad and ops.table_lowrank_supported(emb.weight, trs.weight)):
+                return ops.table_project(emb, trs.weight, trs.bias)
             return trs(emb.weight)
         from . import parallel
         return parallel.sharded_projection(emb.weight, trs.weight, trs.bias, self._table_rows,
@@ -114,6 +119,16 @@ class GeneralRecommender(AbstractRecommender):
     def train(self, mode=True):
         self._eval_cache = None
         return super().train(mode)
+
+    def _set_masked_adj(self, g):
+        """Replace the per-epoch dropout adjacency (layergcn.py:70, freedom.py:145). A training
+        step captured in a CUDA graph has the old CSR's pointers, task count and grid baked in, so
+        the adjacency version the trainer keys its graphs on moves with every replacement; the
+        previous CSR is kept alive until the next replacement so that a graph captured on it can
+        never outlive its buffers."""
+        self._retired_adj = self.__dict__.get("masked_adj")
+        self.masked_adj = g
+        self.graph_version = int(self.__dict__.get("graph_version", 0)) + 1
 
     # -- evaluation helpers ----------------------------------------------------------------
     def _eval_forward(self):
@@ -134,7 +149,7 @@ class GeneralRecommender(AbstractRecommender):
         """[Bu, n_items] scores (layergcn.py:179-188, freedom.py:214-222, mgcn.py:255-263,
         smore.py:414-422): API-compatible dense path. The trainer uses full_sort_topk."""
         ue, ie = self._eval_forward()
-        return torch.matmul(ue[interaction[0]], ie.transpose(0, 1))
+        return ops.score_matrix(ue[interaction[0]], ie)
 
     @torch.no_grad()
     def full_sort_topk(self, users, k, mask_rowptr=None, mask_cols=None):
@@ -217,7 +232,7 @@ class LayerGCN(GeneralRecommender):
         else:
             keep_idx = torch.multinomial(self.edge_values, keep_len)
         self.pruning_random = True ^ self.pruning_random
-        self.masked_adj = self._masked_graph(keep_idx)
+        self._set_masked_adj(self._masked_graph(keep_idx))
 
     def _masked_graph(self, keep_idx):
         keep_idx = keep_idx.to(self.device)
@@ -334,7 +349,7 @@ class FREEDOM(GeneralRecommender):
             return
         degree_len = int(self.edge_values.size(0) * (1. - self.dropout))
         degree_idx = torch.multinomial(self.edge_values, degree_len)
-        self.masked_adj = self._masked_graph(degree_idx)
+        self._set_masked_adj(self._masked_graph(degree_idx))
 
     def _masked_graph(self, keep_idx):
         keep_idx = keep_idx.to(self.device)
@@ -459,7 +474,9 @@ class MGCN(_MultiViewBase):
         self.image_trs = ops.Linear(self.v_feat.shape[1], d)
         self.text_trs = ops.Linear(self.t_feat.shape[1], d)
         self.softmax = nn.Softmax(dim=-1)
-        self.query_common = ops.DenseStack(ops.Linear(d, d), nn.Tanh(), ops.Linear(d, 1, bias=False))
+        # query_common.2 is the Linear(d, 1) of the attention head: a plain nn.Linear holder, its
+        # weight is consumed as the row-dot vector of ops.mgcn_fuse
+        self.query_common = ops.DenseStack(ops.Linear(d, d), nn.Tanh(), nn.Linear(d, 1, bias=False))
         self.gate_v = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
         self.gate_t = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
         self.gate_image_prefer = ops.DenseStack(ops.Linear(d, d), nn.Sigmoid())
@@ -483,14 +500,15 @@ class MGCN(_MultiViewBase):
         content = ops.propagate_mean(adj, ego, self.n_ui_layers)
         image_embeds, text_embeds = self._views((image_item, text_item),
                                                 (self.image_original_adj, self.text_original_adj))
-        att = torch.cat([self.query_common(image_embeds), self.query_common(text_embeds)], dim=-1)
-        w = self.softmax(att)
-        common = w[:, 0].unsqueeze(1) * image_embeds + w[:, 1].unsqueeze(1) * text_embeds
-        pi, pt = ops.dense_stack_batch((self.gate_image_prefer, self.gate_text_prefer), (content, content))
-        sep_i = pi * (image_embeds - common)
-        sep_t = pt * (text_embeds - common)
-        side = (sep_i + sep_t + common) / 3
-        return content + side, side, content
+        # attention fuser (mgcn.py:188-205): the two tanh layers and the two preference gates as one
+        # batched launch each, everything after them (Linear(d, 1), softmax, common / specific
+        # split, / 3, + content) in one kernel
+        q0 = self.query_common[0]
+        hi, ht = ops.dense_act_batch((image_embeds, text_embeds), (q0, q0), "tanh")
+        pi, pt = ops.dense_act_batch((content, content), (self.gate_image_prefer[0], self.gate_text_prefer[0]),
+                                     "sigmoid")
+        all_e, side = ops.mgcn_fuse(hi, ht, self.query_common[2].weight, image_embeds, text_embeds, pi, pt, content)
+        return all_e, side, content
 
     def calculate_loss(self, interaction):
         """mgcn.py:233-253."""

@@ -507,6 +507,23 @@ def gemm(A, a_kcontig, B, b_kcontig, M, N, K, bias=None):
     return C
 
 
+@torch.no_grad()
+def score_matrix(user_rows, item_emb):
+    """`user_rows @ item_emb.T` -> [Bu, n_items] on the library GEMM (3xTF32): the dense
+    `full_sort_predict` of layergcn.py:186-188, freedom.py:219-222, mgcn.py:260-263, smore.py:419-422
+    for callers that want the score matrix itself (the trainer uses the fused top-K instead).
+    Rows of the output are 16-byte vectors, so the item count is padded to a multiple of 4 with
+    zero rows and the view of the first n_items columns is returned."""
+    lib.require_cuda(user_rows, item_emb)
+    u, v = _f32c(user_rows), _f32c(item_emb)
+    n_items, d = v.shape
+    pad = (-n_items) % 4
+    if pad:
+        v = torch.cat([v, v.new_zeros(pad, d)], dim=0)
+    out = gemm(u, True, v, True, u.shape[0], n_items + pad, d)
+    return out[:, :n_items] if pad else out
+
+
 class _Inject3(torch.autograd.Function):
     """item + scale * g_m for three gates (smore.py:269-272), one launch each way."""
 
@@ -563,12 +580,92 @@ class _Linear(torch.autograd.Function):
         return dx, dW, db
 
 
+class LowRankGrad:
+    """Gradient of a feature table X that enters the model only through Y = X W^T + b: the rank-d
+    product G = dY @ W, kept as its two factors (dY [I, d], W [d, F]) and never materialised. The
+    optimizer (optim.FusedAdam) and the mirror-gradient step (trainer.py) consume it tile by tile
+    inside the tcgen05 kernels of mmrec_table_adam_lowrank_f32 / mmrec_table_lowrank_sumsq_f64."""
+    __slots__ = ("dY", "W")
+
+    def __init__(self, dY, W):
+        self.dY, self.W = dY, W
+
+    def dense(self):
+        """The [I, F] gradient itself (tests / fallbacks only)."""
+        return gemm(self.dY, True, self.W, False, self.dY.shape[0], self.W.shape[1], self.dY.shape[1])
+
+
+def table_lowrank_supported(table, W):
+    return (table.is_cuda and table.dim() == 2 and W.dim() == 2 and
+            bool(lib.load().mmrec_table_lowrank_supported(table.shape[0], table.shape[1], W.shape[0])))
+
+
+class _TableProject(torch.autograd.Function):
+    """`trs(emb.weight)` for a trainable feature table (smore.py:257-259, mgcn.py:148-150,
+    freedom.py:207-210) whose [I, F] gradient is never written: backward returns dW and db, and
+    leaves the table's gradient on the parameter as `_mmrec_lowrank = LowRankGrad(dY, W)`.
+
+    `delta = (coef, dY1, W1)` evaluates the projection at the mirror-gradient point
+    X' = X - coef * dY1 @ W1 (trainer.py:307-310) without touching the table:
+        Y'  = X W^T - coef * dY1 (W1 W^T) + b
+        dW' = dY^T X - coef * (dY^T dY1) W1
+    (two d x d products and two thin GEMMs instead of a read-modify-write of the 115 MB table
+    before the pass and another one after it)."""
+
+    @staticmethod
+    def forward(ctx, X, W, b, holder, delta):
+        X, W = _f32c(X), _f32c(W)
+        I, F = X.shape
+        d = W.shape[0]
+        Y = gemm(X, True, W, True, I, d, F, None if b is None else _f32c(b))
+        if delta is not None:
+            coef, dY1, W1 = delta
+            S = gemm(W1, True, W, True, d, d, F)                    # W1 W^T
+            corr = gemm(dY1, True, S, False, I, d, d)               # dY1 (W1 W^T)
+            from .optim import axpy_multi
+            axpy_multi([Y], [corr], coef, sign=-1.0)
+        ctx.holder, ctx.delta, ctx.has_bias = holder, delta, b is not None
+        ctx.save_for_backward(X, W)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W = ctx.saved_tensors
+        dY = _f32c(dY)
+        I, F = X.shape
+        d = W.shape[0]
+        dW = gemm(dY, False, X, False, d, F, I) if ctx.needs_input_grad[1] else None
+        if dW is not None and ctx.delta is not None:
+            coef, dY1, W1 = ctx.delta
+            T = gemm(dY, False, dY1, False, d, d, I)                # dY^T dY1
+            corr = gemm(T, True, W1, False, d, F, d)                # (dY^T dY1) W1
+            from .optim import axpy_multi
+            axpy_multi([dW], [corr], coef, sign=-1.0)
+        db = colsum(dY) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        param = ctx.holder.weight
+        if getattr(param, "_mmrec_lowrank", None) is not None:
+            raise RuntimeError("table_project: the table already carries a low-rank gradient (used twice in one "
+                               "backward, or zero_grad was not called); accumulate is not supported")
+        param._mmrec_lowrank = LowRankGrad(dY, W)
+        return None, dW, db, None, None
+
+
+def table_project(emb, W, b):
+    """`F.linear(emb.weight, W, b)` with the table's gradient kept low-rank (see _TableProject).
+    `emb` is the nn.Embedding that owns the table; a pending mirror-gradient displacement is read
+    from `emb.weight._mmrec_delta`."""
+    lib.require_cuda(emb.weight, W)
+    return _TableProject.apply(emb.weight, W, b, emb, getattr(emb.weight, "_mmrec_delta", None))
+
+
 def linear(x, W, b=None):
-    """F.linear(x, W, b) for 2-D x on the 3xTF32 tensor-core GEMM (K4); shapes the kernel does not
-    cover (output or input width not a multiple of 4) go to cuBLAS through F.linear."""
-    if x.dim() != 2 or W.shape[0] % 4 or W.shape[1] % 4 or not x.is_cuda:
-        lib.require_cuda(x)
-        return torch.nn.functional.linear(x, W, b)
+    """F.linear(x, W, b) for 2-D x on the 3xTF32 tensor-core GEMM (K4). There is no library
+    fallback: shapes the kernel does not cover (rows are moved as 16-byte vectors, so both widths
+    must be multiples of 4) raise."""
+    lib.require_cuda(x, W)
+    if x.dim() != 2 or W.shape[0] % 4 or W.shape[1] % 4:
+        raise RuntimeError(f"mmrec_b200.linear: unsupported shape x{tuple(x.shape)} W{tuple(W.shape)} "
+                           "(2-D input, in/out widths multiples of 4); there is no cuBLAS fallback")
     return _Linear.apply(x, W, b)
 
 
@@ -712,9 +809,7 @@ class DenseStack(torch.nn.Sequential):
 
 
 # ------------------------------------------------------------------- SMORE side network (fused)
-def _ptr_array(tensors):
-    import ctypes
-    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+_ptr_array = lib.ptr_array
 
 
 class _SmoreSide(torch.autograd.Function):
@@ -785,6 +880,60 @@ def smore_side(fusion, image, text, content, layers, masks=None):
     for m in layers:
         wb += [m.weight, m.bias]
     return _SmoreSide.apply(fusion, image, text, content, masks, *wb)
+
+
+# ------------------------------------------------------------------- MGCN attention fuser (fused)
+class _MgcnFuse(torch.autograd.Function):
+    """mgcn.py:188-205 after the d x d layers: apply(Hi, Ht, w2, Ei, Et, Pi, Pt, C) -> (all, side)."""
+
+    @staticmethod
+    def forward(ctx, Hi, Ht, w2, Ei, Et, Pi, Pt, C_):
+        Hi, Ht, Ei, Et, Pi, Pt, C_ = (_f32c(t) for t in (Hi, Ht, Ei, Et, Pi, Pt, C_))
+        w2c = _f32c(w2).reshape(-1)
+        n, d = Ei.shape
+        att = torch.empty(n, 2, dtype=torch.float32, device=Ei.device)
+        side, all_e = torch.empty_like(Ei), torch.empty_like(Ei)
+        lib.call("mmrec_mgcn_fuse_fwd_f32", lib.ptr(Hi), lib.ptr(Ht), lib.ptr(w2c), lib.ptr(Ei), lib.ptr(Et),
+                 lib.ptr(Pi), lib.ptr(Pt), lib.ptr(C_), n, d, lib.ptr(att), lib.ptr(side), lib.ptr(all_e),
+                 lib.stream())
+        ctx.w2_shape = tuple(w2.shape)
+        ctx.save_for_backward(Hi, Ht, w2c, Ei, Et, Pi, Pt, att)
+        return all_e, side
+
+    @staticmethod
+    def backward(ctx, g_all, g_side):
+        Hi, Ht, w2c, Ei, Et, Pi, Pt, att = ctx.saved_tensors
+        n, d = Ei.shape
+        g_all = None if g_all is None else _f32c(g_all)
+        g_side = None if g_side is None else _f32c(g_side)
+        dHi, dHt, dEi, dEt, dPi, dPt, dC = (torch.empty_like(Ei) for _ in range(7))
+        nb = lib.load().mmrec_mgcn_fuse_bwd_blocks(n, d)
+        part = torch.empty(nb, d, dtype=torch.float32, device=Ei.device)
+        dw2 = torch.empty(d, dtype=torch.float32, device=Ei.device)
+        lib.call("mmrec_mgcn_fuse_bwd_f32", lib.ptr(g_all), lib.ptr(g_side), lib.ptr(Hi), lib.ptr(Ht), lib.ptr(w2c),
+                 lib.ptr(Ei), lib.ptr(Et), lib.ptr(Pi), lib.ptr(Pt), lib.ptr(att), n, d, lib.ptr(dHi), lib.ptr(dHt),
+                 lib.ptr(dEi), lib.ptr(dEt), lib.ptr(dPi), lib.ptr(dPt), lib.ptr(dC), lib.ptr(part), lib.ptr(dw2),
+                 lib.stream())
+        return dHi, dHt, dw2.reshape(ctx.w2_shape), dEi, dEt, dPi, dPt, dC
+
+
+def mgcn_fuse_supported(d):
+    return bool(lib.load().mmrec_mgcn_fuse_supported(int(d)))
+
+
+def mgcn_fuse(h_img, h_txt, w2, image_embeds, text_embeds, p_img, p_txt, content):
+    """MGCN's attention fuser (mgcn.py:188-205) -> (content + side, side); h_m =
+    tanh(query_common.0(m_embeds)), w2 = query_common.2.weight, p_m = sigmoid(gate_m_prefer.0(content))."""
+    lib.require_cuda(h_img, h_txt, w2, image_embeds, text_embeds, p_img, p_txt, content)
+    return _MgcnFuse.apply(h_img, h_txt, w2, image_embeds, text_embeds, p_img, p_txt, content)
+
+
+def dense_act_batch(xs, linears, act):
+    """[act(F.linear(x_i, W_i, b_i))] for nn.Linear modules of one shape in one launch each way (the
+    same module may appear more than once: autograd sums its gradients)."""
+    lins = list(linears)
+    return list(_DenseActBatch.apply(_ACT_CODE[act], len(xs), *xs, *[l.weight for l in lins],
+                                     *[l.bias for l in lins]))
 
 
 # ------------------------------------------------------------------------------ item kNN graphs

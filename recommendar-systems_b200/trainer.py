@@ -200,6 +200,11 @@ class Trainer:
         self._graphs = {}
         self._eval_graphs = {}
         self.replayed_launches = 0
+        # the [I, F] gradients of the trainable feature tables stay low-rank (ops.LowRankGrad) when the
+        # optimizer is the fused Adam, which consumes them tile by tile; anything that needs `p.grad`
+        # itself (gradient clipping, the non-model mirror schedule, torch optimizers) keeps them dense
+        model.lowrank_table_grad = bool(config.get("lowrank_table_grad", True)) and \
+            hasattr(self.optimizer, "lowrank_params") and not self.clip_grad_norm and not self.mg
 
     def _build_optimizer(self):
         """trainer.py:126-143."""
@@ -230,17 +235,37 @@ class Trainer:
             if p.requires_grad and p.grad is not None:
                 params.append(p)
                 grads.append(p.grad.detach())
+        # feature tables whose gradient is the never-materialised product dY W (ops.LowRankGrad)
+        tables = opt.lowrank_params() if hasattr(opt, "lowrank_params") else []
         alpha_base = float(getattr(model, "mg_alpha", 0.5))
         sharded = [getattr(p, "_mmrec_sharded", False) for p in params]
         fused = hasattr(opt, "lr_tensor") and not any(sharded) and len(opt.param_groups) == 1
+        if tables and not fused:
+            raise RuntimeError("low-rank table gradients need the fused single-group optimizer path")
         with torch.no_grad():
-            from .optim import axpy_multi, mirror_coef
+            from .optim import axpy_multi, lowrank_sumsq, mirror_coef
             if fused:
-                # one pass over (theta, g) for both RMS values + the scalar arithmetic on the device
-                numel = float(sum(g.numel() for g in grads))
+                # one pass over (theta, g) for both RMS values + the scalar arithmetic on the device;
+                # a table brings sum theta^2 from the Adam pass that just updated it and sum g^2 from
+                # a tensor-core pass over the factors of its gradient
+                numel = float(sum(g.numel() for g in grads) + sum(p.numel() for p in tables))
+                extra = None
+                if tables:
+                    T = len(tables)
+                    extra = torch.empty(2 * T, dtype=torch.float64, device=params[0].device)
+                    for t, p in enumerate(tables):
+                        extra[t:t + 1].copy_(opt.state[p]["sumsq"])
+                        lowrank_sumsq(p, extra[T + t:])
                 both = mirror_coef(params, grads, opt._hyper(opt.param_groups[0], params[0].device), numel,
-                                   alpha_base, self.mg_alpha_max_scale, self.mg_target_rel_step)
+                                   alpha_base, self.mg_alpha_max_scale, self.mg_target_rel_step,
+                                   extra, len(tables), len(tables))
                 coef, model._alpha_eff = both[0:1], both[1]
+                for p in tables:
+                    # the mirror point theta - coef * dY W of a table is never written: the next
+                    # forward / backward evaluate the projection there from the factors (the W factor
+                    # is snapshotted because the live W is about to be displaced itself)
+                    lr = p._mmrec_lowrank
+                    p._mmrec_delta = (coef, lr.dY, lr.W.clone())
             else:
                 dev = params[0].device
                 if hasattr(opt, "lr_tensor"):
@@ -272,6 +297,10 @@ class Trainer:
         (sum(loss_mirror) if isinstance(loss_mirror, tuple) else loss_mirror).backward()
         beta = -float(getattr(model, "mg_beta", 0.2))
         every = all(p.grad is not None for p in params)
+        for p in tables:
+            p._mmrec_delta = None
+        if tables and not every:
+            raise RuntimeError("mirror-gradient step: a dense parameter lost its gradient in the mirror pass")
         if fused and every:
             # back to theta inside the Adam pass (same fmaf as the axpy), gradients scaled as they are read
             opt.step(grad_scale=beta, undo=({p: g for p, g in zip(params, grads)}, coef))
