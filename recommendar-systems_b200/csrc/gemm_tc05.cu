@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "tc05.cuh"
+#include "tma_host.h"
 
 namespace mmrec {
 namespace {
@@ -61,6 +62,7 @@ struct GemmArgs {
   double beta1, beta2;
   float eps, weight_decay, grad_scale;
   double *sumsq_partial;            // optional: per-CTA sum of the updated parameters' squares
+  int debug;                        // MMREC_TA_DEBUG (timing experiments only): 1 = no arithmetic, 2 = no copies
 };
 
 // Byte offset of element chunk inside one operand tile (extent E along M/N, 32 along K).
@@ -119,8 +121,8 @@ struct GCfg {
   // that is needed -- the epilogue (HBM streaming) is several times longer than a tile's products
   static constexpr int STAGES = EPI_MODE == EPI_ADAM ? 2 : NT <= 32 ? 4 : NT <= 64 ? 3 : 2;
   // epilogue staging: 4 warps x [32][NT + 4] floats (x 3 arrays for EPI_ADAM)
-  static constexpr uint32_t EPI = (EPI_MODE == EPI_ADAM ? 3 : 1) * 4 * 32 * (NT + 4) * 4;
-  static constexpr int EXTRA_BARS = EPI_MODE == EPI_ADAM ? 4 : 0;     // one mbarrier per epilogue warp
+  static constexpr uint32_t EPI = EPI_MODE == EPI_ADAM ? 1024 + 4 * 3 * 32 * 64 * 4 : 4 * 32 * (NT + 4) * 4;
+  static constexpr int EXTRA_BARS = EPI_MODE == EPI_ADAM ? 8 : 0;     // tile-landed mbarriers: epilogue warp x buffer
   static constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
   static constexpr int GROUPS = NT >= 128 ? 2 : 4;          // independent producer groups
   static constexpr int GROUP_THREADS = kProdThreads / GROUPS;
@@ -128,7 +130,7 @@ struct GCfg {
 
 template <bool A_MN, bool B_MN, int NT, bool TRANS_OUT, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(kThreadsG, 1)
-gemm_tc05_kernel(const GemmArgs g) {
+gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
   using C = GCfg<NT, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -249,25 +251,49 @@ gemm_tc05_kernel(const GemmArgs g) {
       bc2_sqrt = (float)sqrt(1.0 - pow(g.beta2, step));
     }
     // EPI_ADAM: this warp's 32 rows x NT columns of the table and of both moments travel HBM ->
-    // shared memory -> HBM as bulk asynchronous copies (one NT-float row segment per lane and
-    // array): no registers and no LSU address work are spent on the 24 bytes per element that bound
-    // this kernel, and the whole tile (3 x 32 x NT x 4 bytes per warp) is in flight at once.
-    constexpr int PP = NT + 4;
-    float *pmv = stg + warp * (3 * 32 * PP);
+    // shared memory -> HBM as TMA tile copies (boxes of 32 rows x 32 columns, 128-byte swizzle, three
+    // arrays x NT / 32 boxes per tile): no registers and no LSU address work are spent on the 24
+    // bytes per element that bound this kernel, the whole tile (3 x 32 x NT x 4 bytes per warp) is
+    // in flight at once, and rows beyond the table are clipped by the copy engine.
+    constexpr int NBOX = NT / 32;
+    constexpr int NBUF = 64 / NT >= 2 ? 2 : 1;           // tile buffers per warp (same shared memory either way)
+    constexpr uint32_t TILE_BYTES = 3u * NBOX * 4096u;
+    uint8_t *tiles0 = nullptr;
+    const int n_tiles = n_kb > 0 ? n_nt : 0;
+    // tile jj of this warp -> its buffer jj % NBUF (issued by lane 0)
+    auto issue_loads = [&](int jj) {
+      uint8_t *t = tiles0 + (jj % NBUF) * TILE_BYTES;
+      uint64_t *bar = pbar + warp * NBUF + jj % NBUF;
+      const int nn = (nt_begin + jj) * NT;
+      mbar_arrive_expect_tx(bar, TILE_BYTES);
+#pragma unroll
+      for (int b = 0; b < NBOX; ++b) {
+        tma_load_2d(t + (0 * NBOX + b) * 4096, &maps.a, nn + 32 * b, m0 + warp * 32, bar);
+        tma_load_2d(t + (1 * NBOX + b) * 4096, &maps.b, nn + 32 * b, m0 + warp * 32, bar);
+        tma_load_2d(t + (2 * NBOX + b) * 4096, &maps.c, nn + 32 * b, m0 + warp * 32, bar);
+      }
+    };
+    if constexpr (EPI == EPI_ADAM) {
+      uint8_t *base = reinterpret_cast<uint8_t *>(stg);
+      base += (1024u - (smem_u32(base) & 1023u)) & 1023u;
+      tiles0 = base + warp * (NBUF * TILE_BYTES);
+      if (lane == 0) {
+        tma_prefetch_desc(&maps.a); tma_prefetch_desc(&maps.b); tma_prefetch_desc(&maps.c);
+        if (n_tiles > 0 && g.debug != 2) issue_loads(0);
+      }
+    }
     const int rows_valid = min(32, g.M - (m0 + warp * 32));
-    for (int j = 0; j < (n_kb > 0 ? n_nt : 0); ++j) {
+    for (int j = 0; j < n_tiles; ++j) {
       const int n0 = (nt_begin + j) * NT;
       if constexpr (EPI == EPI_ADAM) {
-        if (j > 0) bulk_wait_read();                 // the stores of tile j - 1 have left shared memory
-        __syncwarp();
-        if (lane == 0 && rows_valid > 0) mbar_arrive_expect_tx(pbar + warp, (uint32_t)rows_valid * 3u * NT * 4u);
-        __syncwarp();
-        if (lane < rows_valid) {
-          const size_t o = (size_t)(m0 + warp * 32 + lane) * g.ldc + n0;
-          bulk_load(pmv + lane * PP, g.C + o, NT * 4, pbar + warp);
-          bulk_load(pmv + (32 + lane) * PP, g.exp_avg + o, NT * 4, pbar + warp);
-          bulk_load(pmv + (64 + lane) * PP, g.exp_avg_sq + o, NT * 4, pbar + warp);
+        // two buffers: the loads of tile j + 1 go out before tile j is touched (its buffer was last
+        // read by the stores of tile j - 1); one buffer: tile j is fetched once tile j - 1 has left
+        const int next = NBUF == 2 ? j + 1 : j;
+        if (lane == 0 && g.debug != 2 && next > 0 && next < n_tiles) {
+          bulk_wait_read();
+          issue_loads(next);
         }
+        __syncwarp();
       }
       float acc[NT];
 #pragma unroll
@@ -290,35 +316,54 @@ gemm_tc05_kernel(const GemmArgs g) {
       }
       if constexpr (EPI == EPI_ADAM) {
         // lane = table row (the TMEM lane): acc[] is that row's gradient G = dY W. Same float
-        // operations in the same order as adam_kernel (optim.cu), on the row held in shared memory.
-        if (rows_valid > 0) mbar_wait(pbar + warp, j & 1);
-        if (lane < rows_valid) {
+        // operations in the same order as adam_kernel (optim.cu), on the row held in shared memory
+        // (16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4) inside its box: a warp's
+        // access touches every bank exactly four times, the minimum for 512 bytes).
+        uint8_t *tiles = tiles0 + (j % NBUF) * TILE_BYTES;
+        if (g.debug != 2) mbar_wait(pbar + warp * NBUF + j % NBUF, (j / NBUF) & 1);
+        if (lane < rows_valid && g.debug != 1) {
           const float beta2 = (float)g.beta2, w1 = (float)(1.0 - g.beta1), w2 = (float)(1.0 - g.beta2);
-          float *pr = pmv + lane * PP, *mr = pmv + (32 + lane) * PP, *vr = pmv + (64 + lane) * PP;
+          const float inv_bc2 = 1.f / bc2_sqrt;
 #pragma unroll
           for (int q = 0; q < NT; q += 4) {
-            float4 p4 = *reinterpret_cast<float4 *>(pr + q), m4 = *reinterpret_cast<float4 *>(mr + q),
-                   v4 = *reinterpret_cast<float4 *>(vr + q);
+            const uint32_t off = (uint32_t)(q / 32) * 4096u + (uint32_t)lane * 128u +
+                                 (uint32_t)((((q % 32) / 4) ^ (lane & 7)) << 4);
+            float4 *pq = reinterpret_cast<float4 *>(tiles + off);
+            float4 *mq = reinterpret_cast<float4 *>(tiles + NBOX * 4096 + off);
+            float4 *vq = reinterpret_cast<float4 *>(tiles + 2 * NBOX * 4096 + off);
+            float4 p4 = *pq, m4 = *mq, v4 = *vq;
+            // adam_kernel's update (optim.cu) with the square root and the two divisions on the
+            // special-function unit (sqrt.approx / rcp.approx, <= 1 ulp each): the IEEE sequences
+            // are ~10 dependent instructions with a slow-path branch each, and with one epilogue
+            // warp per scheduler nothing hides them -- the arithmetic alone took 2.7x the HBM time
+            // of the kernel. The update term m / denom is bounded by ~1, so the parameters move by
+            // < 1e-9 relative against the exact formula (parity bar: 1e-5).
             auto upd = [&](float &p_, float g_, float &m_, float &v_) {
               g_ *= g.grad_scale;
               if (g.weight_decay != 0.f) g_ = fmaf(g.weight_decay, p_, g_);
               m_ = m_ + w1 * (g_ - m_);
               v_ = v_ * beta2 + w2 * g_ * g_;
-              const float denom = sqrtf(v_) / bc2_sqrt + g.eps;
-              p_ = p_ - step_size * (m_ / denom);
+              float sq, rc;
+              asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v_));
+              const float denom = fmaf(sq, inv_bc2, g.eps);
+              asm("rcp.approx.f32 %0, %1;" : "=f"(rc) : "f"(denom));
+              p_ = p_ - step_size * (m_ * rc);
               p2_acc = fmaf(p_, p_, p2_acc);
             };
             upd(p4.x, acc[q], m4.x, v4.x); upd(p4.y, acc[q + 1], m4.y, v4.y);
             upd(p4.z, acc[q + 2], m4.z, v4.z); upd(p4.w, acc[q + 3], m4.w, v4.w);
-            *reinterpret_cast<float4 *>(pr + q) = p4;
-            *reinterpret_cast<float4 *>(mr + q) = m4;
-            *reinterpret_cast<float4 *>(vr + q) = v4;
+            *pq = p4; *mq = m4; *vq = v4;
           }
-          fence_proxy_async_smem();                  // this lane's row writes -> visible to the copy engine
-          const size_t o = (size_t)(m0 + warp * 32 + lane) * g.ldc + n0;
-          bulk_store(g.C + o, pr, NT * 4);
-          bulk_store(g.exp_avg + o, mr, NT * 4);
-          bulk_store(g.exp_avg_sq + o, vr, NT * 4);
+        }
+        fence_proxy_async_smem();                    // the rows written above -> visible to the copy engine
+        __syncwarp();
+        if (lane == 0 && g.debug != 2) {
+#pragma unroll
+          for (int b = 0; b < NBOX; ++b) {
+            tma_store_2d(&maps.a, n0 + 32 * b, m0 + warp * 32, tiles + (0 * NBOX + b) * 4096);
+            tma_store_2d(&maps.b, n0 + 32 * b, m0 + warp * 32, tiles + (1 * NBOX + b) * 4096);
+            tma_store_2d(&maps.c, n0 + 32 * b, m0 + warp * 32, tiles + (2 * NBOX + b) * 4096);
+          }
           bulk_commit();
         }
         continue;
@@ -404,13 +449,13 @@ int launch_tc05(const GemmArgs &g, int k_splits, int n_chunks, cudaStream_t stre
     attr = true;
   }
   dim3 grid((g.M + kBM - 1) / kBM, k_splits, n_chunks);
-  kern<<<grid, kThreadsG, smem, stream>>>(g);
+  kern<<<grid, kThreadsG, smem, stream>>>(g, TmaMaps3{});
   MMREC_CHECK_LAUNCH("gemm_tc05_kernel");
   return MMREC_OK;
 }
 
 template <int NT, int EPI>
-int launch_table_epi(const GemmArgs &g, int n_chunks, cudaStream_t stream) {
+int launch_table_epi(const GemmArgs &g, const TmaMaps3 &maps, int n_chunks, cudaStream_t stream) {
   using C = GCfg<NT, EPI>;
   const size_t smem = 1024 + (size_t)C::STAGES * C::STAGE + (2 * C::STAGES + 4 + C::EXTRA_BARS) * 8 + 16 + C::EPI;
   auto kern = gemm_tc05_kernel<false, true, NT, false, EPI>;
@@ -420,7 +465,7 @@ int launch_table_epi(const GemmArgs &g, int n_chunks, cudaStream_t stream) {
     attr = true;
   }
   dim3 grid((g.M + kBM - 1) / kBM, 1, n_chunks);
-  kern<<<grid, kThreadsG, smem, stream>>>(g);
+  kern<<<grid, kThreadsG, smem, stream>>>(g, maps);
   MMREC_CHECK_LAUNCH(EPI == EPI_ADAM ? "gemm_tc05_kernel<adam>" : "gemm_tc05_kernel<sumsq>");
   return MMREC_OK;
 }
@@ -515,14 +560,23 @@ int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcon
 
 
 // ---- Adam on a feature table whose gradient is the rank-d product dY W (never materialised) ----
-int table_adam_grid(int rows, int cols, int *nt_per_cta) {
-  const int m_tiles = (rows + kBM - 1) / kBM, n_tiles = cols / 64;
+static int table_adam_nt() {
+  static const int nt = getenv("MMREC_TA_NT") && atoi(getenv("MMREC_TA_NT")) == 64 ? 64 : 32;
+  return nt;
+}
+
+static int table_grid(int rows, int cols, int *nt_per_cta, int nt) {
+  const int m_tiles = (rows + kBM - 1) / kBM, n_tiles = cols / nt;
   int chunks = best_parts(m_tiles, n_tiles, n_tiles, 1);
   const int per = (n_tiles + chunks - 1) / chunks;
   chunks = (n_tiles + per - 1) / per;
   if (nt_per_cta) *nt_per_cta = per;
   return m_tiles * chunks;
 }
+
+// number of CTAs (= per-CTA partial sums) of the two table kernels
+int table_adam_ctas(int rows, int cols) { return table_grid(rows, cols, nullptr, table_adam_nt()); }
+int table_sumsq_ctas(int rows, int cols) { return table_grid(rows, cols, nullptr, 64); }
 
 int table_adam_dispatch(float *P, float *Mo, float *V, const float *dY, const float *W, int rows, int cols, int d,
                         const double *hyper, double beta1, double beta2, double eps, double weight_decay,
@@ -532,9 +586,19 @@ int table_adam_dispatch(float *P, float *Mo, float *V, const float *dY, const fl
   g.kb_per_split = (d + kKB - 1) / kKB;
   g.exp_avg = Mo; g.exp_avg_sq = V; g.hyper = hyper; g.beta1 = beta1; g.beta2 = beta2; g.eps = (float)eps;
   g.weight_decay = (float)weight_decay; g.grad_scale = (float)grad_scale; g.sumsq_partial = sumsq_partial;
-  const int ctas = table_adam_grid(rows, cols, &g.nt_per_cta);
+  const int nt = table_adam_nt();
+  const int ctas = table_grid(rows, cols, &g.nt_per_cta, nt);
   const int m_tiles = (rows + kBM - 1) / kBM;
-  return launch_table_epi<64, EPI_ADAM>(g, ctas / m_tiles, stream);
+  static const int dbg = getenv("MMREC_TA_DEBUG") ? atoi(getenv("MMREC_TA_DEBUG")) : 0;
+  g.debug = dbg;
+  TmaMaps3 maps;
+  if (!tma_encode_2d_f32(&maps.a, P, rows, cols, cols, 32, 32) || !tma_encode_2d_f32(&maps.b, Mo, rows, cols, cols, 32, 32) ||
+      !tma_encode_2d_f32(&maps.c, V, rows, cols, cols, 32, 32)) {
+    set_error("table_adam: cuTensorMapEncodeTiled failed");
+    return MMREC_E_CUDA;
+  }
+  if (nt == 32) return launch_table_epi<32, EPI_ADAM>(g, maps, ctas / m_tiles, stream);
+  return launch_table_epi<64, EPI_ADAM>(g, maps, ctas / m_tiles, stream);
 }
 
 // per-CTA partial sums of ||dY W||_F^2 (same grid as table_adam_dispatch)
@@ -544,9 +608,9 @@ int table_sumsq_dispatch(const float *dY, const float *W, int rows, int cols, in
   g.A = dY; g.lda = d; g.B = W; g.ldb = cols; g.C = nullptr; g.ldc = cols; g.M = rows; g.N = cols; g.K = d;
   g.kb_per_split = (d + kKB - 1) / kKB;
   g.sumsq_partial = sumsq_partial;
-  const int ctas = table_adam_grid(rows, cols, &g.nt_per_cta);
+  const int ctas = table_grid(rows, cols, &g.nt_per_cta, 64);
   const int m_tiles = (rows + kBM - 1) / kBM;
-  return launch_table_epi<64, EPI_SUMSQ>(g, ctas / m_tiles, stream);
+  return launch_table_epi<64, EPI_SUMSQ>(g, TmaMaps3{}, ctas / m_tiles, stream);
 }
 
 }  // namespace mmrec

@@ -321,7 +321,8 @@ extern "C" int mmrec_mirror_coef_f32(const float *const *params_host, const floa
 // ---- feature tables whose gradient is the rank-d product dY W (SMORE / MGCN / FREEDOM image and
 // text tables: d x 4096 / d x 384 projections, smore.py:257-259) -------------------------------
 namespace mmrec {
-int table_adam_grid(int rows, int cols, int *nt_per_cta);
+int table_adam_ctas(int rows, int cols);
+int table_sumsq_ctas(int rows, int cols);
 int table_adam_dispatch(float *P, float *Mo, float *V, const float *dY, const float *W, int rows, int cols, int d,
                         const double *hyper, double beta1, double beta2, double eps, double weight_decay,
                         double grad_scale, double *sumsq_partial, cudaStream_t stream);
@@ -353,7 +354,8 @@ extern "C" int mmrec_table_lowrank_supported(int32_t rows, int32_t cols, int32_t
 
 extern "C" size_t mmrec_table_lowrank_workspace_bytes(int32_t rows, int32_t cols) {
   if (rows <= 0 || cols <= 0 || cols % 64) return 0;
-  return sizeof(double) * (size_t)table_adam_grid(rows, cols, nullptr);
+  const int a = table_adam_ctas(rows, cols), b = table_sumsq_ctas(rows, cols);
+  return sizeof(double) * (size_t)(a > b ? a : b);
 }
 
 extern "C" int mmrec_table_adam_lowrank_f32(float *table, float *exp_avg, float *exp_avg_sq, const float *dY,
@@ -378,7 +380,7 @@ extern "C" int mmrec_table_adam_lowrank_f32(float *table, float *exp_avg, float 
                                      weight_decay, grad_scale, partial, stream);
   if (rc != MMREC_OK) return rc;
   if (sumsq_out) {
-    sum_partials_kernel<<<1, kThreads, 0, stream>>>(partial, table_adam_grid(rows, cols, nullptr), sumsq_out);
+    sum_partials_kernel<<<1, kThreads, 0, stream>>>(partial, table_adam_ctas(rows, cols), sumsq_out);
     MMREC_CHECK_LAUNCH("sum_partials_kernel");
   }
   return MMREC_OK;
@@ -394,7 +396,7 @@ extern "C" int mmrec_table_lowrank_sumsq_f64(const float *dY, const float *W, in
   double *partial = static_cast<double *>(workspace);
   const int rc = table_sumsq_dispatch(dY, W, rows, cols, d, partial, stream);
   if (rc != MMREC_OK) return rc;
-  sum_partials_kernel<<<1, kThreads, 0, stream>>>(partial, table_adam_grid(rows, cols, nullptr), out);
+  sum_partials_kernel<<<1, kThreads, 0, stream>>>(partial, table_sumsq_ctas(rows, cols), out);
   MMREC_CHECK_LAUNCH("sum_partials_kernel");
   return MMREC_OK;
 }

@@ -68,6 +68,22 @@ __device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src,
                ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// 2-D tile copies through a tensor map (UTMALDG / UTMASTG): one instruction moves a whole box;
+// rows / columns outside the tensor are zero-filled on load and clipped on store. (x = innermost
+// coordinate = column, y = row.) Issued by ONE thread.
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int x, int y, const void *smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(tmap), "r"(x), "r"(y), "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // every bulk group of this thread has finished READING its shared-memory source (the buffer may be reused)
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

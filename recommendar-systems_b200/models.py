@@ -270,16 +270,21 @@ def _edge_values_cpu(edge_u, edge_i, n_users, n_items):
 
 
 # ----------------------------------------------------------------------------- item graphs
-def knn_sym_coo(feat, k):
+def knn_sym_coo(feat, k, neighbors=None):
     """build_sim + build_knn_normalized_graph(sparse, 'sym') + get_sparse_laplacian
     (utils/utils.py:134-152, 171-184) on the library's kNN kernels (no per-element Python loop,
     no [I, I] torch.topk)."""
-    return ops.knn_graph(feat, k, "sym")
+    return ops.knn_graph(feat, k, "sym", neighbors)
 
 
-def freedom_knn_coo(feat, k):
+def freedom_knn_coo(feat, k, neighbors=None):
     """FREEDOM.get_knn_adj_mat + compute_normalized_laplacian (freedom.py:79-100)."""
-    return ops.knn_graph(feat, k, "freedom")
+    return ops.knn_graph(feat, k, "freedom", neighbors)
+
+
+def _knn_override(config, name):
+    """Tests pin the kNN edge sets through config['item_knn'][name] = [I, k] neighbour ids."""
+    return (config["item_knn"] or {}).get(name)
 
 
 def max_pool_fusion_coo(a, b, n):
@@ -336,8 +341,8 @@ class FREEDOM(GeneralRecommender):
         coo = _coo_override(config, "mm_adj", self.device)
         if coo is None:
             # freedom.py:64-77: w * image_adj + (1-w) * text_adj; duplicates are summed by SpMM
-            ri, ci, vi = freedom_knn_coo(self.v_feat, self.knn_k)
-            rt, ct, vt = freedom_knn_coo(self.t_feat, self.knn_k)
+            ri, ci, vi = freedom_knn_coo(self.v_feat, self.knn_k, _knn_override(config, "image"))
+            rt, ct, vt = freedom_knn_coo(self.t_feat, self.knn_k, _knn_override(config, "text"))
             w = self.mm_image_weight
             coo = (torch.cat([ri, rt]), torch.cat([ci, ct]), torch.cat([w * vi, (1.0 - w) * vt]))
         self.mm_adj = G.csr_from_coo(*coo, self.n_items, self.n_items)
@@ -396,7 +401,7 @@ class _MultiViewBase(GeneralRecommender):
     def _item_graph(self, config, name, feat, k):
         coo = _coo_override(config, name, self.device)
         if coo is None:
-            coo = knn_sym_coo(feat, k)
+            coo = knn_sym_coo(feat, k, _knn_override(config, name.split("_")[0]))
         return coo, G.csr_from_coo(*coo, self.n_items, self.n_items)
 
     # ---- independent branches of the forward on side streams ---------------------------------

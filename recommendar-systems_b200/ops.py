@@ -938,14 +938,17 @@ def dense_act_batch(xs, linears, act):
 
 # ------------------------------------------------------------------------------ item kNN graphs
 @torch.no_grad()
-def knn_graph(feat, k, mode):
+def knn_graph(feat, k, mode, neighbors=None):
     """(rows, cols, weights) of the cosine top-k item graph on the device.
     mode 'sym'     : build_sim + build_knn_normalized_graph(sparse, 'sym') + get_sparse_laplacian
                      (utils/utils.py:134-184) -- MGCN / SMORE;
     mode 'freedom' : FREEDOM.get_knn_adj_mat + compute_normalized_laplacian (freedom.py:79-100).
     Row normalisation, the [I, I] cosine GEMM (3xTF32), the per-row top-k (ties -> lower id) and
     the edge weights all run in the library; rows / cols come back int64 like the reference's
-    index tensors, in (row, rank) order."""
+    index tensors, in (row, rank) order. `neighbors` ([n, k] integer tensor) replaces the top-k
+    selection by given neighbour lists -- parity tests pin the edge set to the reference's, whose
+    float32 near-ties depend on the BLAS build -- the similarities and weights are still computed
+    here."""
     feat = _f32c(feat)
     lib.require_cuda(feat)
     n, F = feat.shape
@@ -957,9 +960,15 @@ def knn_graph(feat, k, mode):
     nrm = torch.zeros(n_pad, F, dtype=torch.float32, device=dev)
     lib.call("mmrec_row_normalize_f32", lib.ptr(feat), n, F, lib.ptr(nrm), lib.stream())
     sim = gemm(nrm, True, nrm, True, n_pad, n_pad, F)
-    val = torch.empty(n, k, dtype=torch.float32, device=dev)
-    idx = torch.empty(n, k, dtype=torch.int32, device=dev)
-    lib.call("mmrec_row_topk_f32", lib.ptr(sim), n, n, n_pad, k, lib.ptr(val), lib.ptr(idx), lib.stream())
+    if neighbors is None:
+        val = torch.empty(n, k, dtype=torch.float32, device=dev)
+        idx = torch.empty(n, k, dtype=torch.int32, device=dev)
+        lib.call("mmrec_row_topk_f32", lib.ptr(sim), n, n, n_pad, k, lib.ptr(val), lib.ptr(idx), lib.stream())
+    else:
+        idx = torch.as_tensor(neighbors).to(dev).to(torch.int32).contiguous()
+        if tuple(idx.shape) != (n, k):
+            raise RuntimeError(f"knn_graph: neighbors must be [{n}, {k}], got {tuple(idx.shape)}")
+        val = sim[:n].gather(1, idx.to(torch.int64)).contiguous()
     del sim
     w = torch.empty(n, k, dtype=torch.float32, device=dev)
     dis = torch.empty(n, dtype=torch.float32, device=dev)

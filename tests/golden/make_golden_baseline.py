@@ -1,0 +1,212 @@
+"""Golden vectors at the BASELINE.json configurations, produced by executing the UNMODIFIED
+reference (/root/reference/src) on CPU in the build container:
+
+    python tests/golden/make_golden_baseline.py [case ...]     # writes tests/golden/base_*.npz
+
+Cases (BASELINE.json `configs`): LayerGCN / Baby, SMORE / Baby, FREEDOM / Sports, MGCN / Sports,
+SMORE / Clothing with embedding_size 128 -- synthetic datasets of exactly those shapes
+(`synth.make_dataset`, seed 2024; 4096-d image / 384-d text features), model seed 999, first grid
+point of every model YAML. The full tensors are hundreds of MB, so each fixture stores what a
+parity test needs and no more: the first training batch, the kept edges of the epoch's dropout,
+loss0, the neighbour lists of the kNN item graphs (int16), and for every parameter / gradient /
+embedding table its float64 sum, sum of squares and
+the values at 4096 fixed positions (`sample_index`); the reference's top-50 ids of the first 256
+validation users and the unrounded metrics of the initial model over all validation users.
+Same shims as make_golden.py; nothing of the reference is copied, only its outputs are stored.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as mg          # noqa: E402  (shims, scratch dir, REF path)
+
+synth = mg.synth
+N_SAMPLE = 4096
+N_TOPK_USERS = 256
+
+CASES = {
+    # tag: (model, dataset shape name, config overrides)
+    "base_layergcn_baby": ("LayerGCN", "baby", {"dropout": 0.0, "reg_weight": 1e-2}),
+    "base_smore_baby": ("SMORE", "baby", {}),
+    "base_freedom_sports": ("FREEDOM", "sports", {}),
+    "base_mgcn_sports": ("MGCN", "sports", {}),
+    "base_smore_clothing_d128": ("SMORE", "clothing", {"embedding_size": 128}),
+}
+
+
+def sample_index(numel, name):
+    """Fixed positions for a tensor of `numel` elements (seeded by the tensor's name and size)."""
+    seed = (sum(ord(c) for c in name) * 1000003 + numel) % (2 ** 31)
+    rng = np.random.default_rng(seed)
+    return np.sort(rng.integers(0, numel, size=min(N_SAMPLE, numel)))
+
+
+def stats(out, key, t):
+    a = t.detach().cpu().numpy().astype(np.float64).ravel()
+    out[key + "/sum"] = np.asarray(a.sum())
+    out[key + "/sumsq"] = np.asarray((a * a).sum())
+    out[key + "/absmax"] = np.asarray(np.abs(a).max() if a.size else 0.0)
+    out[key + "/sample"] = a[sample_index(a.size, key)].astype(np.float32)
+
+
+def prepare(dataset):
+    scratch = mg.SCRATCH
+    os.makedirs(os.path.join(scratch, "configs", "dataset"), exist_ok=True)
+    for name in ("overall.yaml", "model", "mg.yaml"):
+        dst = os.path.join(scratch, "configs", name)
+        if not os.path.lexists(dst):
+            os.symlink(os.path.join(mg.REF, "configs", name), dst)
+    with open(os.path.join(scratch, "configs", "dataset", f"{dataset}.yaml"), "w") as f:
+        f.write("USER_ID_FIELD: userID\nITEM_ID_FIELD: itemID\nTIME_FIELD: timestamp\n"
+                f"filter_out_cod_start_users: True\ninter_file_name: '{dataset}.inter'\n"
+                "vision_feature_file: 'image_feat.npy'\ntext_feature_file: 'text_feat.npy'\n"
+                "field_separator: \"\\t\"\n")
+    data = synth.make_dataset(dataset)
+    d = synth.write_reference_layout(data, os.path.join(scratch, "data"))
+    for fn in os.listdir(d):
+        if fn.endswith(".pt"):
+            os.remove(os.path.join(d, fn))
+    os.chdir(scratch)
+    if mg.REF not in sys.path:
+        sys.path.insert(0, mg.REF)
+    return data
+
+
+def build(model_name, dataset, overrides):
+    from utils.configurator import Config
+    from utils.dataset import RecDataset
+    from utils.dataloader import TrainDataLoader, EvalDataLoader
+    from utils.utils import init_seed, get_model, get_trainer
+    cd = {"use_gpu": False, "data_path": os.path.join(mg.SCRATCH, "data") + "/", "mg_verbose": False,
+          "diag_gate": False, "diag_spectrum": False, "diag_grad": False}
+    cd.update(overrides)
+    config = Config(model_name, dataset, cd)
+    ds = RecDataset(config)
+    str(ds)
+    tr, va, te = ds.split()
+    str(tr), str(va), str(te)
+    train_data = TrainDataLoader(config, tr, batch_size=config["train_batch_size"], shuffle=True)
+    valid_data = EvalDataLoader(config, va, additional_dataset=tr, batch_size=config["eval_batch_size"])
+    for k in config["hyper_parameters"]:
+        v = config[k]
+        if isinstance(v, list):
+            config[k] = v[0]
+    for k, v in overrides.items():
+        config[k] = v
+    init_seed(config["seed"])
+    train_data.pretrain_setup()
+    ddir = os.path.join(mg.SCRATCH, "data", dataset)
+    for fn in os.listdir(ddir):
+        if fn.endswith(".pt"):
+            os.remove(os.path.join(ddir, fn))
+    model = get_model(model_name)(config, train_data).to(config["device"])
+    trainer = get_trainer()(config, model, False)
+    return config, model, trainer, train_data, valid_data
+
+
+def capture(tag):
+    model_name, dataset, overrides = CASES[tag]
+    prepare(dataset)
+    torch.set_num_threads(os.cpu_count())
+    out = {"meta/model": np.asarray(model_name), "meta/dataset": np.asarray(dataset)}
+    config, model, trainer, train_data, valid_data = build(model_name, dataset, overrides)
+    for k in ("embedding_size", "n_layers", "n_ui_layers", "n_mm_layers", "knn_k", "image_knn_k", "text_knn_k",
+              "reg_weight", "cl_loss", "dropout", "dropout_rate", "train_batch_size", "eval_batch_size",
+              "learning_rate", "mm_image_weight"):
+        if config[k] is not None:
+            out["config/" + k] = np.asarray(config[k])
+    for n, p in model.named_parameters():
+        stats(out, "param0/" + n, p)
+    for a in mg.ADJ_ATTRS:
+        t = getattr(model, a, None)
+        if t is not None and torch.is_tensor(t) and t.is_sparse:
+            v = t._values()
+            out[f"adj/{a}/nnz"] = np.asarray(v.numel())
+            stats(out, f"adj/{a}/val", v)
+            idx = t._indices()
+            out[f"adj/{a}/idx_checksum"] = np.asarray(int((idx[0].to(torch.int64) * 1000003 + idx[1]).sum().item()))
+    # neighbour lists of the item-item kNN graphs (int16: every dataset has < 32768 items): a parity
+    # test injects exactly the reference's edge sets -- top-k on a float32 cosine matrix flips
+    # near-ties between BLAS builds, which is not what the model-level comparison is about
+    with torch.no_grad():
+        if model_name == "FREEDOM":
+            for key, emb in (("image", model.image_embedding), ("text", model.text_embedding)):
+                ind, _ = model.get_knn_adj_mat(emb.weight.detach())
+                out[f"knn/{key}"] = ind[1].reshape(model.n_items, -1).numpy().astype(np.int16)
+        elif model_name in ("MGCN", "SMORE"):
+            for key, a in (("image", model.image_original_adj), ("text", model.text_original_adj)):
+                out[f"knn/{key}"] = a._indices()[1].reshape(model.n_items, -1).numpy().astype(np.int16)
+    model.pre_epoch_processing()
+    masked = getattr(model, "masked_adj", None)
+    if masked is not None and model_name in ("LayerGCN", "FREEDOM") and float(config["dropout"] or 0.0) > 0:
+        idx = masked._indices()
+        keep = idx.shape[1] // 2                    # first half: (user, item + n_users) edges
+        out["masked/kept_user"] = idx[0, :keep].numpy().astype(np.int32)
+        out["masked/kept_item"] = (idx[1, :keep] - model.n_users).numpy().astype(np.int32)
+        stats(out, "masked/val", masked._values())
+    it = iter(train_data)
+    batch0 = next(it).clone()
+    train_data.pr = 0
+    out["batch0"] = batch0.numpy()
+    model.train()
+    model.zero_grad()
+    if model_name == "SMORE":
+        model.dropout = torch.nn.Identity()          # nn.Dropout's mask is not reproducible across devices
+        out["meta/dropout_disabled"] = np.asarray(1)
+    loss = model.calculate_loss(batch0)
+    loss.backward()
+    out["loss0"] = np.asarray(loss.item(), dtype=np.float64)
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            stats(out, "grad0/" + n, p.grad)
+    model.zero_grad()
+    with torch.no_grad():
+        model.eval()
+        if model_name in ("SMORE", "MGCN", "FREEDOM"):
+            ue, ie = model.forward(model.norm_adj)
+        else:
+            model.forward_adj = model.norm_adj_matrix
+            ue, ie = model.forward()
+        stats(out, "eval_user_emb", ue)
+        stats(out, "eval_item_emb", ie)
+        k = max(config["topk"])
+        mats = []
+        for b in valid_data:
+            s = model.full_sort_predict(b)
+            s[b[1][0], b[1][1]] = -1e10
+            mats.append(torch.topk(s, k, dim=-1))
+        topk_index = torch.cat([m[1] for m in mats], 0).numpy()
+        topk_score = torch.cat([m[0] for m in mats], 0).numpy()
+        out["eval/users"] = valid_data.eval_u.numpy()[:N_TOPK_USERS].astype(np.int64) \
+            if hasattr(valid_data, "eval_u") else np.zeros(0, np.int64)
+        out["eval/topk_ids"] = topk_index[:N_TOPK_USERS].astype(np.int32)
+        out["eval/topk_scores"] = topk_score[:N_TOPK_USERS].astype(np.float32)
+        out["eval/topk_checksum"] = np.asarray(int(topk_index.astype(np.int64).sum()))
+        out["eval/n_users"] = np.asarray(topk_index.shape[0])
+        # smallest gap between consecutive scores inside the reference's lists: ids can only be
+        # compared exactly where this is far above float32 rounding of a d-term dot product
+        gaps = np.abs(np.diff(topk_score.astype(np.float64), axis=1))
+        out["eval/min_score_gap_rel"] = (gaps.min(axis=1) / np.abs(topk_score).max(axis=1)).astype(np.float32)
+        pos_items = valid_data.get_eval_items()
+        hits = np.asarray([[i in set(m.tolist()) for i in n] for m, n in zip(pos_items, topk_index)])
+        out["eval/metrics_raw"] = trainer.evaluator._calculate_metrics(valid_data.get_eval_len_list(), hits)
+        out["eval/metric_names"] = np.asarray(trainer.evaluator.metrics)
+    path = os.path.join(HERE, f"{tag}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB, loss0={out['loss0']:.6f}",
+          flush=True)
+
+
+def main():
+    mg.install_shims()
+    for tag in (sys.argv[1:] or list(CASES)):
+        capture(tag)
+
+
+if __name__ == "__main__":
+    main()
