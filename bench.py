@@ -14,11 +14,18 @@ Trainer._train_epoch's batch loop: in steady state 3 forward+backward passes and
               host negative sampling, pinned H2D copy of every [3, B] batch and a D2H read of the
               loss inside the timed region.
 * extras    : train_epoch_s, eval_users_per_s (Trainer.evaluate on the validation users),
-              per-kernel rooflines (SpMM GB/s vs measured HBM peak), cpu_baseline.
-* N > 1     : replicas (one hyper-parameter grid point per GPU, the reference's own outer loop);
-              no data-path collective, weak scaling.
+              per-kernel rooflines (SpMM GB/s vs measured HBM peak), cpu_baseline,
+              torch_cuda_reference (the oracle port on stock torch CUDA kernels, N = 1).
+* N > 1     : the training step at Baby size does not shard (single-digit-microsecond kernels): the
+              headline value runs replicas (one hyper-parameter grid point per GPU, the reference's
+              own outer loop; no collective, weak scaling). The paths that DO shard run
+              in the same invocation, at every N including 1, and are reported under
+              `config.sharded_config5` (10M x 2M x 500M graph: user-sharded propagation with a
+              chunked, overlapped item-table all-reduce + item-sharded top-50 and merge; strong
+              scaling, phase split, clock record, top-K checksum) and `config.sharded_config4`
+              (SMORE / Clothing d = 128 with item-range sharded feature tables).
 * --impl reference : the reference's CPU implementation of the same step (oracle port on torch
-              CPU with all host threads), rank 0 only.
+              CPU with all host threads), rank 0 only; builds its inputs without the product.
 """
 import argparse
 import importlib
@@ -47,11 +54,14 @@ def measured_peaks():
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    try:
-        return json.load(open(p))["dram_bytes_per_launch"].get(kernel)
-    except (OSError, ValueError, KeyError):
-        return None
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"].get(kernel)
+        except (OSError, ValueError, KeyError):
+            v = None
+        if v is not None:
+            return v
+    return None
 
 
 class ClockSampler:
@@ -158,7 +168,11 @@ def kernel_rooflines(env, peak):
                 "achieved": b / ms / 1e6, "frac": b / ms / 1e6 / peak})
     acc = torch.empty_like(X)
     ms = time_kernel(lambda: ops.spmm_raw(g, X, Y=Y, acc_in=X, acc_out=acc), flush)
-    b2 = b + 8 * d * g.n_rows
+    # a fused L-layer propagation = L x the SpMM bytes + ONE 4 d N write of the
+    # accumulated output; per launch that is b + 4 d N / L (the running sum the epilogue re-reads and
+    # re-writes every layer is not algorithmic traffic)
+    L = int(model.n_ui_layers)
+    b2 = b + 4 * d * g.n_rows // max(L, 1)
     out.append({"kernel": "spmm_csr_kernel (UI graph, fused layer-sum)", "bytes": b2, "ms": ms,
                 "achieved": b2 / ms / 1e6, "frac": b2 / ms / 1e6 / peak})
     gi = model.fusion_adj
@@ -196,7 +210,19 @@ def kernel_rooflines(env, peak):
     b = 28 * n * F
     out.append({"kernel": "adam_kernel (image table)", "bytes": b, "ms": ms, "achieved": b / ms / 1e6,
                 "frac": b / ms / 1e6 / peak})
-    del opt, dy
+    # the same table updated from the factors of its gradient (never materialised): 24 B / parameter
+    par = torch.nn.Parameter(torch.randn(n, F, device=dev))
+    opt2 = pkg("optim").FusedAdam([par], lr=1e-3)
+
+    def lowrank_step():
+        par._mmrec_lowrank = ops.LowRankGrad(dy, Wt)
+        opt2.step()
+        par._mmrec_lowrank = None
+    ms = time_kernel(lowrank_step, flush)
+    b = 24 * n * F
+    out.append({"kernel": "gemm_tc05_kernel<adam> (image table, low-rank gradient, TMA-streamed)", "bytes": b,
+                "ms": ms, "achieved": b / ms / 1e6, "frac": b / ms / 1e6 / peak})
+    del opt, opt2, par, dy
     # a user-item graph whose embedding table (184 MB) does not fit the 126 MB L2
     del X, Y, acc
     su, si = pkg("synth").make_scaled_edges(dev, 600_000, 120_000, 30_000_000)
@@ -339,10 +365,30 @@ def run_ours(args):
     torch.cuda.synchronize()
     eval_dev_ms = a.elapsed_time(b_)
 
+    # ---- the paths that shard, on these same N ranks (config 5, then config 4); rank 0 gets the blocks
+    del batches
+    sharded5 = sharded4 = None
+    if not args.no_sharded_blocks:
+        try:
+            sharded5 = scaled_block(dev, rank, world, local, scale=args.scale, eval_users=args.eval_users,
+                                    steps=10, warmup=3, chunks=args.chunks)
+        except Exception as exc:                      # never lose the headline line to an auxiliary block
+            sharded5 = {"error": repr(exc)[:300]} if rank == 0 else None
+            if world > 1:
+                raise
+        torch.cuda.empty_cache()
+        try:
+            sharded4 = clothing_block(dev, rank, world)
+        except Exception as exc:
+            sharded4 = {"error": repr(exc)[:300]} if rank == 0 else None
+            if world > 1:
+                raise
+        torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    batches = take_batches(env["train"], W + K)
     peak, peak_src = measured_peaks()
     live = in_step_kernel_times(trainer, batches[W:W + min(K, 5)], ["spmm_csr_kernel<", "adam_kernel", "gemm_tc05_kernel"])
     kr = kernel_rooflines(env, peak)
@@ -357,23 +403,23 @@ def run_ours(args):
     n_train = len(env["tr"])
     steps_per_epoch = -(-n_train // B)
     line = {
-        "metric": "train interactions/s (SMORE, Baby-shaped; epoch s and eval users/s in extras)",
+        "metric": METRIC,
         "value": value, "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SMORE, synthetic Amazon-Baby-shaped (19445 users x 7050 items x 160792 "
-                               "interactions, 4096-d image / 384-d text, d=64, batch 2048, mirror-gradient "
-                               "schedule: steady-state step = 3 fwd+bwd + 2 Adam)",
+        "config": {"workload": WORKLOAD,
                    "l2": "per-step working set (~1.7 GB of tables/optimizer state) exceeds the 126 MB L2; "
                          "kernel rooflines flush L2 before every timed launch",
-                   "multi_gpu": "replicas (one seed per GPU), no collective"},
+                   "multi_gpu": "headline value: replicas (one seed per GPU), no collective -- the Baby-sized step "
+                                "does not shard; the sharded designs are measured in sharded_config5 / sharded_config4",
+                   "sharded_config5": sharded5, "sharded_config4": sharded4},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": 3 * B * 8,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"], "traffic": ncu_traffic(dom["kernel"]),
-                     "traffic_source": "ncu --set full capture committed under profiles/ (r01_ncu_traffic.json)",
+                     "traffic_source": "ncu --set full capture committed under profiles/ (r02_ncu_traffic.json, else r01)",
                      "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"],
                      "timing": "average duration of the kernel's launches inside replays of the timed step "
                                "(CUPTI activity records); isolated_* = one launch after an L2 flush, CUDA events",
@@ -386,15 +432,32 @@ def run_ours(args):
         "eval_users_per_s": n_eval / eval_s, "eval_users_per_s_device": n_eval / (eval_dev_ms / 1e3),
         "eval_users": n_eval, "eval_recall@20": metrics.get("recall@20"),
     }
+    # whole-step roofline of SURVEY 8(d): ~5.0 GB of algorithmic traffic per steady-state step
+    line["step_roofline"] = {"algorithmic_gb_per_step": 5.0, "achieved_gbs": 5.0e9 / (ms / K / 1e3) / 1e9, "peak": peak,
+                             "frac": 5.0e9 / (ms / K / 1e3) / 1e9 / peak,
+                             "note": "SURVEY 8(d) epoch roofline: 3 x 0.77 GB fwd+bwd + 2 x 0.94 GB Adam + 0.8 GB mirror "
+                                     "passes; the low-rank table gradients remove ~1.3 GB of that from what is actually moved"}
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(env, steps=20, warmup=3)
+        try:
+            del env, trainer, model
+            torch.cuda.empty_cache()
+            line["torch_cuda_reference"] = torch_cuda_reference(dev)
+        except Exception as exc:
+            line["torch_cuda_reference"] = {"error": repr(exc)[:300]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+WORKLOAD = ("SMORE, synthetic Amazon-Baby-shaped (19445 users x 7050 items x 160792 interactions, 4096-d image / "
+            "384-d text, d=64, batch 2048, mirror-gradient schedule: steady-state step = 3 fwd+bwd + 2 Adam)")
+METRIC = "train interactions/s (SMORE, Baby-shaped; epoch s and eval users/s in extras)"
+
+
 def oracle_trainer_for(env):
-    """The reference's CPU path for the same step: oracle port on torch CPU."""
+    """The reference's CPU path for the same step: oracle port on torch CPU (our arm's cpu_baseline:
+    same parameters and batches as the model that was just timed)."""
     import torch
     from oracle import build as obuild
     from oracle.train import OracleTrainer
@@ -426,46 +489,339 @@ def cpu_baseline(env, steps, warmup):
                       f"after {warmup} warm-up steps, oracle port on torch CPU; {dt / steps:.2f} s/step"}
 
 
+# ---- the reference arm: inputs built WITHOUT the product (no model, no CUDA library) ------------
+def oracle_smore_inputs(seed=999, n_batches=8):
+    """Synthetic Baby-shaped data, the oracle's graphs, SMORE parameters initialised like the model
+    (xavier id embeddings, nn.Linear defaults, randn spectral weights) and [3, B] training batches
+    -- from synth.py (numpy), config.py (constants) and oracle/ only: the reference arm never maps
+    the product's shared library."""
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    from oracle import build as obuild
+    synth, cfgm = pkg("synth"), pkg("config")
+    data = synth.make_dataset("baby")
+    tu, ti = data.split(0)
+    mc = dict(cfgm.OVERALL)
+    mc.update(cfgm.MODEL_DEFAULTS["SMORE"])
+    cfg = {k: mc[k] for k in ("n_ui_layers", "n_layers", "image_knn_k", "text_knn_k", "reg_weight", "cl_loss",
+                              "train_batch_size")}
+    G, parts = obuild.build_graphs("SMORE", tu, ti, data.n_users, data.n_items, data.image_feat, data.text_feat, cfg)
+    torch.manual_seed(seed)
+    d = mc["embedding_size"]
+    P = {"user_embedding.weight": nn.init.xavier_uniform_(torch.empty(data.n_users, d)),
+         "item_id_embedding.weight": nn.init.xavier_uniform_(torch.empty(data.n_items, d)),
+         "image_embedding.weight": torch.from_numpy(data.image_feat).clone(),
+         "text_embedding.weight": torch.from_numpy(data.text_feat).clone()}
+
+    def lin(name, n_in, n_out, bias=True):
+        m = nn.Linear(n_in, n_out, bias=bias)
+        P[name + ".weight"] = m.weight.detach().clone()
+        if bias:
+            P[name + ".bias"] = m.bias.detach().clone()
+    lin("image_trs", data.image_feat.shape[1], d)
+    lin("text_trs", data.text_feat.shape[1], d)
+    for q in ("query_v", "query_t"):
+        lin(q + ".0", d, d)
+        lin(q + ".2", d, d, bias=False)
+    for gname in ("gate_v", "gate_t", "gate_f", "gate_image_prefer", "gate_text_prefer", "gate_fusion_prefer"):
+        lin(gname + ".0", d, d)
+    for w in ("image_complex_weight", "text_complex_weight", "fusion_complex_weight"):
+        P[w] = torch.randn(1, d // 2 + 1, 2)
+    # batches: shuffled training edges + one uniform negative per row outside the user's history
+    rng = np.random.default_rng(seed)
+    B = cfg["train_batch_size"]
+    order = rng.permutation(len(tu))
+    key = np.sort(tu.astype(np.int64) * data.n_items + ti)
+    batches = []
+    for b in range(n_batches):
+        sel = order[(b * B) % len(tu):][:B]
+        if len(sel) < B:
+            sel = order[:B]
+        u, pos = tu[sel].astype(np.int64), ti[sel].astype(np.int64)
+        neg = rng.integers(0, data.n_items, size=B)
+        for _ in range(50):
+            k = u * data.n_items + neg
+            at = np.minimum(np.searchsorted(key, k), len(key) - 1)
+            bad = key[at] == k
+            if not bad.any():
+                break
+            neg[bad] = rng.integers(0, data.n_items, size=int(bad.sum()))
+        batches.append(torch.from_numpy(np.stack([u, pos, neg])))
+    return dict(data=data, cfg=cfg, mc=mc, G=G, parts=parts, P=P, batches=batches, n_train=len(tu))
+
+
+def _oracle_trainer(inp, P, G):
+    import torch
+    from oracle.train import OracleTrainer
+    mc = inp["mc"]
+    return OracleTrainer("SMORE", P, G, inp["cfg"], lr=mc["learning_rate"],
+                         lr_scheduler=tuple(mc["learning_rate_scheduler"]), dropout=torch.nn.Dropout(p=mc["dropout_rate"]))
+
+
+def torch_cuda_reference(dev, steps=10, warmup=4):
+    """The honest neighbour of the GPU-over-CPU ratio: the same oracle port
+    -- the reference's torch expressions: torch.sparse.mm on uncoalesced COO adjacencies, nn.Linear,
+    torch.fft, torch Adam -- on stock torch CUDA kernels on this B200."""
+    import numpy as np
+    import torch
+    inp = oracle_smore_inputs()
+    n, I, U = inp["data"].n_users + inp["data"].n_items, inp["data"].n_items, inp["data"].n_users
+    shapes = {"norm_adj": (n, n), "R": (U, I)}
+    G = {}
+    for k, (r, c, v) in inp["parts"].items():
+        idx = torch.from_numpy(np.vstack([r, c]).astype(np.int64))
+        G[k] = torch.sparse_coo_tensor(idx, torch.as_tensor(v), shapes.get(k, (I, I))).to(dev)   # uncoalesced, like the reference
+    P = {k: v.to(dev) for k, v in inp["P"].items()}
+    ot = _oracle_trainer(inp, P, G)
+    batches = [b.to(dev) for b in inp["batches"]]
+    B = inp["cfg"]["train_batch_size"]
+    for s_ in range(warmup):
+        ot.step(batches[s_ % len(batches)])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s_ in range(steps):
+        ot.step(batches[s_ % len(batches)])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": steps * B / dt, "unit": "interactions/s", "ms_per_step": dt / steps * 1e3,
+            "what": "oracle port of the reference's SMORE step on stock torch CUDA kernels (cuSPARSE COO SpMM, "
+                    f"cuBLAS, cuFFT, torch.optim.Adam), {steps} steady-state steps after {warmup} warm-up, wall clock "
+                    "with synchronize on both sides"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     import torch
     torch.set_num_threads(os.cpu_count())
-    dev = "cuda:0" if torch.cuda.is_available() else None
-    if dev is None:
-        print(json.dumps({"impl": "reference", "unavailable": "model/graph setup needs the CUDA library"}))
-        return
-    env = build_env(dev)
     K, W = args.steps, args.warmup
-    B = env["config"]["train_batch_size"]
-    ot = oracle_trainer_for(env)
-    batches = [b.cpu() for b in take_batches(env["train"], W + K)]
-    for b in batches[:W]:
-        ot.step(b)
+    inp = oracle_smore_inputs(n_batches=max(8, min(W + K, 32)))
+    B = inp["cfg"]["train_batch_size"]
+    ot = _oracle_trainer(inp, inp["P"], inp["G"])
+    batches = inp["batches"]
+    for s_ in range(W):
+        ot.step(batches[s_ % len(batches)])
     t0 = time.perf_counter()
-    for b in batches[W:]:
-        ot.step(b)
+    for s_ in range(K):
+        ot.step(batches[(W + s_) % len(batches)])
     dt = time.perf_counter() - t0
     value = K * B / dt
-    n_train = len(env["tr"])
-    line = {"impl": "reference",
-            "metric": "train interactions/s (SMORE, Baby-shaped; epoch s and eval users/s in extras)",
+    line = {"impl": "reference", "metric": METRIC,
             "value": value, "unit": "interactions/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
             "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SMORE, synthetic Amazon-Baby-shaped, reference CPU path (oracle port)"},
+            "config": {"workload": WORKLOAD,
+                       "arm": "reference CPU path: oracle port (restatement of the reference's torch expressions) on "
+                              "torch CPU, all host threads; inputs built from synth + oracle only"},
             "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": torch.get_num_threads(),
                              "kind": "port", "sample": f"{K} training steps after {W} warm-up steps"},
             "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "train_epoch_s": -(-n_train // B) * dt / K}
+            "train_epoch_s": -(-inp["n_train"] // B) * dt / K}
     print(json.dumps(line))
 
 
+# ---- the paths that shard (SURVEY 8e): run inside every `--gpus N` invocation -------------------
+def _phase_ms(timing, steps):
+    import torch
+    torch.cuda.synchronize()
+    return {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in timing.items()}
+
+
+def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10, warmup=3, chunks=4,
+                 partition="bipartite"):
+    """Config 5: scaled power-law graph (scale 1.0 = 10M users x 2M items x ~500M interactions),
+    LightGCN-style 4-layer propagation + full-rank top-50 for `eval_users` users per step. Strong
+    scaling: N = 1 runs the single-GPU operators on the whole graph; N > 1 shards users by non-zeros
+    (every rank generates and keeps ONLY its own edges), replicates the item table through a chunked
+    all-reduce that runs under the SpMMs, and scores items in N ranges with a K-way merge.
+    Returns the result block on rank 0 (None elsewhere)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    ops, G, par, synth, lib = pkg("ops"), pkg("graph"), pkg("parallel"), pkg("synth"), pkg("lib")
+    U, I, E = int(10_000_000 * scale), int(2_000_000 * scale), int(500_000_000 * scale)
+    d, L, k, Bu = 64, 4, 50, eval_users
+    gen = torch.Generator(device=dev).manual_seed(999)
+    bound = (6.0 / (U + I + d)) ** 0.5
+    users = torch.randint(0, U, (Bu,), generator=gen, device=dev)
+
+    def x0_rows(lo, hi):
+        """Rows [lo, hi) of the xavier-uniform [U + I, d] table, generated in fixed 1M-row blocks
+        (the same values whatever the sharding)."""
+        out = []
+        blk = 1 << 20
+        for b0 in range(lo // blk * blk, hi, blk):
+            b1 = min(U + I, b0 + blk)
+            g = torch.Generator(device=dev).manual_seed(4000 + b0 // blk)
+            x = (torch.rand(b1 - b0, d, generator=g, device=dev) * 2 - 1) * bound
+            out.append(x[max(lo, b0) - b0: min(hi, b1) - b0])
+        return torch.cat(out)
+
+    if world == 1:
+        su, si = synth.make_scaled_edges(dev, U, I, E)
+        nnz_local = int(su.numel())
+        full = G.build_ui_graph(su, si, U, I, "f64eps")
+        del su, si
+        X0 = x0_rows(0, U + I)
+    elif partition == "rows":
+        su, si = synth.make_scaled_edges(dev, U, I, E)
+        nnz_local = int(su.numel())
+        full = G.build_ui_graph(su, si, U, I, "f64eps")
+        del su, si
+        sg = par.ShardedUIGraph(full, rank, world)
+        lo_i, hi_i = par.item_range(I, rank, world)
+        del full
+        X0 = x0_rows(0, U + I)
+    else:
+        deg = synth.scaled_degrees(dev, U, E)
+        rp = np.concatenate(([0], np.cumsum(deg.cpu().numpy())))
+        bounds = par.partition_by_nnz(rp, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        su, si = synth.make_scaled_edges(dev, U, I, E, user_range=(lo, hi))
+        nnz_local = int(su.numel())
+        sb = par.ShardedBipartite.from_local_edges(su, si, bounds, rank, world, U, I, "f64eps")
+        del su, si, deg
+        Xu, Xi = x0_rows(lo, hi), x0_rows(U, U + I)
+    torch.cuda.empty_cache()
+    timing = {}
+
+    def ev(name):
+        e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        timing.setdefault(name, []).append(e)
+        e[0].record()
+        return e
+
+    def step(tm):
+        if world == 1:
+            e = ev("propagate_spmm_x4") if tm is not None else None
+            out = ops.propagate_mean(full, X0, L)
+            if e:
+                e[1].record()
+            e = ev("score_topk") if tm is not None else None
+            ids = ops.score_mask_topk(out[:U], users, out[U:], k)
+            if e:
+                e[1].record()
+            return ids
+        if partition == "rows":
+            out = par.sharded_propagate_mean(sg, X0, L)
+            return par.sharded_score_topk(out[:U], users, out[U + lo_i: U + hi_i].contiguous(), lo_i, k)
+        ou, oi = par.bipartite_propagate_mean(sb, Xu, Xi, L, chunks=chunks, timing=tm)
+        e = ev("score_topk_merge") if tm is not None else None
+        ids = par.bipartite_score_topk(sb, ou, oi, users, k)
+        if e:
+            e[1].record()
+        return ids
+
+    with torch.no_grad():
+        sampler = ClockSampler(local)
+        sampler.start()
+        for _ in range(warmup):
+            ids = step(None)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ids = step(timing)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        launches = lib.launch_count() - l0
+        clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    phases = _phase_ms(timing, steps)
+    checksum = int(ids.sum().item())
+    nnz_total = nnz_local
+    if world > 1:
+        t = torch.tensor([ms] + [phases[k_] for k_ in sorted(phases)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0].item())
+        phases = {k_: float(v) for k_, v in zip(sorted(phases), t[1:].tolist())}
+        chk = torch.tensor([float(checksum)], device=dev, dtype=torch.float64)
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        assert lo_.item() == hi_.item(), "ranks disagree on the merged top-K"
+        nz = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(nz)
+        nnz_total = int(nz.item())
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    n = U + I
+    nnz = 2 * nnz_total                                     # symmetric adjacency: both directions
+    spmm_bytes = L * (8 * nnz + 4 * (n + 1) + 8 * d * n)    # SURVEY 8(d): L x one SpMM over the whole graph
+    spmm_ms = phases.get("propagate_spmm_x4") or (phases.get("rt_spmm", 0.0) + phases.get("r_spmm", 0.0))
+    block = {"workload": f"LightGCN-style propagation (4 layers) + full-rank top-50, {U} users x {I} items x {nnz_total} "
+                         f"interactions (scale {scale}), d=64, {Bu} eval users per step",
+             "metric": "eval users/s", "value": Bu * steps / (ms / 1e3), "n_gpus": world, "scaling": "strong",
+             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "phases_ms_per_step_max_over_ranks": phases,
+             "partition": "single GPU" if world == 1 else
+                          ("rows by nnz + all-gather of the whole table per layer" if partition == "rows" else
+                           f"users by nnz (each rank builds only its own edges), items replicated: item-table all-reduce in "
+                           f"{chunks} chunks per layer issued under the SpMMs (waited for right before the next layer's user-side "
+                           "SpMM); evaluation: items by range + all-gather of (score, id) lists + K-way merge"),
+             "collective_note": "rt_spmm / r_spmm are enqueue-to-completion spans on the compute stream; exposed_all_reduce is "
+                                "the time the compute stream spent waiting for NCCL beyond them",
+             "clocks": clocks, "gpu_launches": int(launches), "checksum_ids": checksum}
+    if spmm_ms > 0:
+        gbs = spmm_bytes / (spmm_ms / 1e3) / 1e9
+        block["spmm_roofline"] = {"algorithmic_bytes_per_step": spmm_bytes, "spmm_ms_per_step": spmm_ms,
+                                  "achieved_gbs_all_gpus": gbs, "peak_gbs_per_gpu": peak, "peak_source": peak_src,
+                                  "frac_of_n_gpu_peak": gbs / (peak * world)}
+    return block
+
+
+def clothing_block(dev, rank, world, steps=10, warmup=8):
+    """Config 4: SMORE on the Clothing-shaped dataset, d = 128; N > 1 shards the [I, 4096] / [I, 384]
+    feature tables, their projections, gradients and Adam state by item range."""
+    import torch
+    import torch.distributed as dist
+    over = {"embedding_size": 128}
+    if world > 1:
+        over["table_shard"] = (rank, world)
+    env = build_env(dev, model_name="SMORE", shape="clothing", overrides=over)
+    trainer = pkg("trainer").Trainer(env["config"], env["model"])
+    batches = take_batches(env["train"], warmup + steps)
+    env["model"].train()
+    env["model"].pre_epoch_processing()
+    losses = []
+    for b in batches[:warmup]:
+        losses.append(trainer._train_batch_graphed(b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for b in batches[warmup:]:
+        losses.append(trainer._train_batch_graphed(b))
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(e) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    last = float(torch.stack(losses).float()[-1].item())
+    B = env["config"]["train_batch_size"]
+    del env, trainer
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"workload": "SMORE, synthetic Clothing-shaped (39387 x 23033 x 278677), d=128, batch 2048, mirror-gradient "
+                        "schedule", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "partition": "single GPU (low-rank table gradients, fused table Adam)" if world == 1 else
+                         "item-range sharded feature tables (projection all-gather, dW all-reduce); the rest replicated",
+            "ms_per_step": float(t.item()), "value": B / float(t.item()) * 1e3, "metric": "train interactions/s",
+            "scaling": "strong", "last_loss": last}
+
+
 def run_scaled(args):
-    """Config 5: scaled power-law graph, LightGCN-style propagation (row-sharded, NCCL all-gather per
-    layer) + item-sharded full-rank top-50 (local fused top-K + all-gather + merge). Strong scaling:
-    every rank works on the same users. `--scale 1.0` = 10M users x 2M items x 500M interactions."""
+    """`--workload scaled`: config 5 alone (see scaled_block)."""
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", 0))
@@ -477,86 +833,15 @@ def run_scaled(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    ops, G, par, synth, lib = pkg("ops"), pkg("graph"), pkg("parallel"), pkg("synth"), pkg("lib")
-    U, I, E = int(10_000_000 * args.scale), int(2_000_000 * args.scale), int(500_000_000 * args.scale)
-    d, L, k, Bu = 64, 4, 50, args.eval_users
-    su, si = synth.make_scaled_edges(dev, U, I, E)
-    full = G.build_ui_graph(su, si, U, I, "f64eps")
-    del su, si
-    gen = torch.Generator(device=dev).manual_seed(999)
-    bound = (6.0 / (U + I + d)) ** 0.5
-    X0 = (torch.rand(U + I, d, generator=gen, device=dev) * 2 - 1) * bound
-    users = torch.randint(0, U, (Bu,), generator=gen, device=dev)
-    nnz_full = full.nnz
-    if world > 1 and args.partition == "rows":
-        sg = par.ShardedUIGraph(full, rank, world)
-        lo, hi = par.item_range(I, rank, world)
-        del full
-    elif world > 1:
-        sb = par.ShardedBipartite(full, rank, world)
-        Xu, Xi = X0[sb.lo: sb.hi].contiguous(), X0[U:].contiguous()
-        del X0
-    torch.cuda.empty_cache()
-
-    def step():
-        if world == 1:
-            out = ops.propagate_mean(full, X0, L)
-            return ops.score_mask_topk(out[:U], users, out[U:], k)
-        if args.partition == "rows":
-            out = par.sharded_propagate_mean(sg, X0, L)
-            return par.sharded_score_topk(out[:U], users, out[U + lo: U + hi].contiguous(), lo, k)
-        ou, oi = par.bipartite_propagate_mean(sb, Xu, Xi, L)
-        return par.bipartite_score_topk(sb, ou, oi, users, k)
-
-    with torch.no_grad():
-        sampler = ClockSampler(local)     # from before the warm-up: the timed steps alone are < 100 ms at 8 GPUs
-        sampler.start()
-        for _ in range(args.warmup):
-            ids = step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        l0 = lib.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            ids = step()
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        launches = lib.launch_count() - l0
-        clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        chk = torch.tensor([float(ids.sum().item())], device=dev, dtype=torch.float64)
-        lo_, hi_ = chk.clone(), chk.clone()
-        dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
-        assert lo_.item() == hi_.item(), "ranks disagree on the merged top-K"
+    pkg("lib").load()
+    blk = scaled_block(dev, rank, world, local, scale=args.scale, eval_users=args.eval_users, steps=args.steps,
+                       warmup=args.warmup, chunks=args.chunks, partition=args.partition)
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        nnz = nnz_full if world == 1 else None
-        n = U + I
         line = {"metric": "propagate (4 layers) + full-rank top-50, eval users/s (scaled power-law graph)",
-                "value": Bu * args.steps / (ms / 1e3), "unit": "users/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"LightGCN-style propagation + item-sharded top-50, {U} users x {I} items x "
-                                       f"~{E} interactions, d=64, {Bu} eval users per step",
-                           "partition": ("rows by nnz + all-gather of the whole table per layer" if args.partition == "rows"
-                                         else "users by nnz, items replicated: one all-reduce of the [I, d] item table per "
-                                              "layer, overlapped with the user-side SpMM") + "; evaluation: items by range + "
-                                                                                             "top-K merge",
-                           "l2": "embedding table larger than L2" if n * d * 4 > 126e6 else "fits L2"},
-                "clocks": clocks, "gpu_launches": int(launches), "checksum_ids": int(ids.sum().item())}
-        if nnz is not None:
-            b = L * (8 * nnz + 4 * (n + 1) + 8 * d * n)
-            line["roofline"] = {"bound": "hbm", "kernel": "spmm_csr_kernel x4 (propagation share of the step)",
-                                "algorithmic_bytes_per_step": b, "peak": peak, "peak_source": peak_src, "unit": "GB/s"}
+                "value": blk["value"], "unit": "users/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": blk, "clocks": blk["clocks"],
+                "gpu_launches": blk["gpu_launches"]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -569,9 +854,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="smore_baby", choices=["smore_baby", "scaled"])
-    ap.add_argument("--scale", type=float, default=0.05)
+    ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--eval-users", type=int, default=16384)
     ap.add_argument("--partition", default="bipartite", choices=["bipartite", "rows"])
+    ap.add_argument("--chunks", type=int, default=4)
+    ap.add_argument("--no-sharded-blocks", action="store_true",
+                    help="skip the config-5 / config-4 blocks of the default workload (quick runs, ncu)")
     args = ap.parse_args()
     if args.workload == "scaled" and args.impl == "ours":
         run_scaled(args)

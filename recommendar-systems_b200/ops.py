@@ -646,7 +646,7 @@ class _TableProject(torch.autograd.Function):
         if getattr(param, "_mmrec_lowrank", None) is not None:
             raise RuntimeError("table_project: the table already carries a low-rank gradient (used twice in one "
                                "backward, or zero_grad was not called); accumulate is not supported")
-        param._mmrec_lowrank = LowRankGrad(dY, W)
+        param._mmrec_lowrank = LowRankGrad(dY.detach(), W.detach())     # factors only: no autograd history
         return None, dW, db, None, None
 
 

@@ -212,13 +212,75 @@ class ShardedBipartite:
         build = csr_from_coo or G.csr_from_coo
         self.Rt = build(items, rows_local, full.vals[a:b], I, hi - lo, with_transpose=False)
         self.nnz_local = b - a
+        self._rt_chunks = {}
+
+    @classmethod
+    def from_local_edges(cls, users, items, bounds, rank, world, n_users, n_items, recipe="f64eps", group=None,
+                         csr_from_coo=None):
+        """Build rank p's share WITHOUT ever holding the full graph: `users` / `items` are this
+        rank's unique training edges (global ids, users in [bounds[rank], bounds[rank + 1])).
+        Values follow graph.build_ui_graph's recipe (D^-1/2 A D^-1/2 with the reference's own host
+        arithmetic through a degree LUT); the item degrees are the only global quantity and come
+        from one all-reduce of the [I] histogram."""
+        self = cls.__new__(cls)
+        U, I = int(n_users), int(n_items)
+        self.bounds = np.asarray(bounds, dtype=np.int64)
+        self.rank, self.world, self.U, self.I = rank, world, U, I
+        lo, hi = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.lo, self.hi = lo, hi
+        dev = users.device
+        rows_local = users.to(torch.int64) - lo
+        items = items.to(torch.int64)
+        deg_u = torch.bincount(rows_local, minlength=hi - lo)
+        deg_i = torch.bincount(items, minlength=I)
+        if world > 1:
+            dist.all_reduce(deg_i, group=group)
+        max_deg = torch.stack([deg_u.max() if deg_u.numel() else deg_i.new_zeros(()), deg_i.max()]).max()
+        lut_np, _ = G._degree_lut(recipe, int(max_deg.item()) + 1)
+        lut = torch.from_numpy(np.asarray(lut_np, dtype=np.float64)).to(dev)
+        vals = (lut[deg_u[rows_local]] * lut[deg_i[items]]).to(torch.float32)
+        if recipe != "f64eps":                  # float32 recipes multiply in float32
+            vals = lut[deg_u[rows_local]].to(torch.float32) * lut[deg_i[items]].to(torch.float32)
+        build = csr_from_coo or G.csr_from_coo
+        self.R = build(rows_local, items, vals, hi - lo, I, with_transpose=False)
+        self.Rt = build(items, rows_local, vals, I, hi - lo, with_transpose=False)
+        self.nnz_local = int(users.numel())
+        self._rt_chunks = {}
+        return self
+
+    def rt_chunks(self, n_chunks):
+        """R_p^T cut into `n_chunks` item ranges (zero-copy row-pointer views with their own work
+        lists): the unit of the chunked all-reduce in bipartite_propagate_mean."""
+        n_chunks = max(1, min(int(n_chunks), self.I))
+        if n_chunks not in self._rt_chunks:
+            per = -(-self.I // n_chunks)
+            out = []
+            for c in range(n_chunks):
+                a, b = min(self.I, c * per), min(self.I, (c + 1) * per)
+                if b > a:
+                    g = G.CSRGraph(self.Rt.row_ptr[a: b + 1], self.Rt.col_idx, self.Rt.vals, b - a, self.Rt.n_cols,
+                                   col_offset=self.Rt.col_offset)
+                    out.append((g, a, b))
+            self._rt_chunks[n_chunks] = out
+        return self._rt_chunks[n_chunks]
 
 
 @torch.no_grad()
-def bipartite_propagate_mean(sb: ShardedBipartite, Xu_local, Xi, n_layers, group=None, spmm_fn=_spmm_cuda):
+def bipartite_propagate_mean(sb: ShardedBipartite, Xu_local, Xi, n_layers, group=None, spmm_fn=_spmm_cuda,
+                             chunks=4, timing=None):
     """mean_{l=0..L} A^l X0 for a bipartite graph, users sharded / items replicated.
     Xu_local [hi - lo, d]: this rank's user rows of X0; Xi [I, d]: the item rows (same on every
-    rank). Returns (users' rows of this rank, all item rows)."""
+    rank). Returns (users' rows of this rank, all item rows).
+
+    Per layer l a rank computes (a) what its users add to every item, yi_l = R_p^T xu_{l-1}, and
+    (b) its users' rows, yu_l = R_p xi_{l-1}; the only exchange is the all-reduce of yi_l. The item
+    table is cut into `chunks` item ranges: the all-reduce of range c is issued (on NCCL's stream)
+    as soon as its SpMM is enqueued and runs under the SpMM of range c + 1, under (b) of the same
+    layer and -- because (a) of layer l + 1 needs only yu_l, which never leaves the rank -- under
+    (a) of the next layer as well: the compute stream waits for the reduced yi_l only right before
+    (b) of layer l + 1. With P ranks (a) + (b) is ~2 nnz / P of gather work per layer against one
+    4 I d all-reduce, so the exchange hides completely while it is the shorter of the two.
+    `timing` (dict of lists of (start, end) CUDA events per phase) is filled when given."""
     L = n_layers
     if L == 0:
         return Xu_local.clone(), Xi.clone()
@@ -226,20 +288,51 @@ def bipartite_propagate_mean(sb: ShardedBipartite, Xu_local, Xi, n_layers, group
     acc_u, acc_i = Xu_local, Xi.clone()
     xu, xi = Xu_local.contiguous(), Xi.contiguous()
     d = xi.shape[1]
+    parts = sb.rt_chunks(chunks)
+
+    def mark(name):
+        if timing is None:
+            return None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        timing.setdefault(name, []).append(ev)
+        ev[0].record()
+        return ev
+
+    def done(ev):
+        if ev is not None:
+            ev[1].record()
+
+    pending = None                                            # (works, yi) of the previous layer
     for l in range(1, L + 1):
         last = l == L
         yi = torch.empty(sb.I, d, dtype=xi.dtype, device=xi.device)
-        spmm_fn(sb.Rt, xu, Y=yi)                              # what this rank's users add to every item
-        work = dist.all_reduce(yi, group=group, async_op=True)
+        works = []
+        ev = mark("rt_spmm")
+        for g, a, b in parts:
+            spmm_fn(g, xu, Y=yi[a:b])                         # (a): this rank's users -> item range [a, b)
+            works.append(dist.all_reduce(yi[a:b], group=group, async_op=True))
+        done(ev)
+        if pending is not None:                               # (b) needs the reduced item table of layer l - 1
+            ev = mark("exposed_all_reduce")
+            for w in pending[0]:
+                w.wait()
+            done(ev)
+            acc_i.add_(pending[1])
+            xi = pending[1]
         yu = None if last else torch.empty_like(xu)
         acc_new = torch.empty_like(xu)
-        spmm_fn(sb.R, xi, Y=yu, acc_in=acc_u, acc_out=acc_new, scale=scale if last else 1.0)   # overlaps the all-reduce
+        ev = mark("r_spmm")
+        spmm_fn(sb.R, xi, Y=yu, acc_in=acc_u, acc_out=acc_new, scale=scale if last else 1.0)
+        done(ev)
         acc_u = acc_new
-        work.wait()
-        acc_i.add_(yi)
-        if last:
-            acc_i.mul_(scale)
-        xu, xi = yu, yi
+        pending = (works, yi)
+        xu = yu
+    ev = mark("exposed_all_reduce")
+    for w in pending[0]:
+        w.wait()
+    done(ev)
+    acc_i.add_(pending[1])
+    acc_i.mul_(scale)
     return acc_u, acc_i
 
 

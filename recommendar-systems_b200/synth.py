@@ -138,19 +138,45 @@ def write_reference_layout(data: SynthData, root: str, uid="userID", iid="itemID
     return d
 
 
-def make_scaled_edges(device, n_users, n_items, n_edges, seed=2024):
-    """Config 5 (scaled power-law graph): edges generated directly on the device -- user degrees
-    ~ 5 + Pareto tail, item popularity ~ Zipf(0.8). Duplicate (u, i) pairs are removed, so the
-    result has slightly fewer than `n_edges` edges. Returns int64 (users, items)."""
+def scaled_degrees(device, n_users, n_edges, seed=2024):
+    """Planned user degrees of the scaled power-law graph (int64 [n_users]): 5 + Pareto tail."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
     w = torch.rand(n_users, generator=g, device=device).clamp_min(1e-6).pow(-1.0 / 1.6)
     extra = max(0, n_edges - 5 * n_users)
-    deg = 5 + torch.floor(w / w.sum() * extra).to(torch.int64)
-    users = torch.repeat_interleave(torch.arange(n_users, device=device), deg)
+    return 5 + torch.floor(w / w.sum() * extra).to(torch.int64)
+
+
+def make_scaled_edges(device, n_users, n_items, n_edges, seed=2024, user_range=None, block=1 << 20):
+    """Config 5 (scaled power-law graph): edges generated directly on the device -- user degrees
+    ~ 5 + Pareto tail, item popularity ~ Zipf(0.8). Duplicate (u, i) pairs are removed, so the
+    result has slightly fewer than `n_edges` edges. Returns int64 (users, items), sorted by
+    (user, item).
+
+    Users are generated in fixed blocks of `block` users, every block from its own seeded stream:
+    `user_range = (lo, hi)` returns exactly the edges of those users that the full call would --
+    a rank of the sharded benchmark builds its share without ever materialising the whole graph."""
+    import torch
+    deg = scaled_degrees(device, n_users, n_edges, seed)
+    g = torch.Generator(device=device).manual_seed(seed + 1)
     pop = torch.arange(1, n_items + 1, device=device, dtype=torch.float64).pow(-0.8)
     pop = pop[torch.randperm(n_items, generator=g, device=device)]
     cdf = torch.cumsum(pop / pop.sum(), 0).to(torch.float32)
-    items = torch.searchsorted(cdf, torch.rand(users.numel(), generator=g, device=device)).clamp_max(n_items - 1)
-    key = torch.unique(users * n_items + items)
-    return key // n_items, key % n_items
+    lo, hi = (0, n_users) if user_range is None else (int(user_range[0]), int(user_range[1]))
+    us, its = [], []
+    for b0 in range(lo // block * block, hi, block):
+        b1 = min(n_users, b0 + block)
+        gb = torch.Generator(device=device).manual_seed(seed + 1000 + b0 // block)
+        users = torch.repeat_interleave(torch.arange(b0, b1, device=device), deg[b0:b1])
+        items = torch.searchsorted(cdf, torch.rand(users.numel(), generator=gb, device=device)).clamp_max(n_items - 1)
+        key = torch.unique(users * n_items + items)
+        u, i = key // n_items, key % n_items
+        if b0 < lo or b1 > hi:
+            m = (u >= lo) & (u < hi)
+            u, i = u[m], i[m]
+        us.append(u)
+        its.append(i)
+    if not us:
+        z = torch.zeros(0, dtype=torch.int64, device=device)
+        return z, z
+    return torch.cat(us), torch.cat(its)

@@ -120,6 +120,18 @@ def _worker(rank, world, port, out_dir):
         ou, oi = par.bipartite_propagate_mean(sb, Xd2[sb.lo: sb.hi], Xd2[U:], 3, spmm_fn=spmm_cpu)
         assert torch.allclose(ou, want[sb.lo: sb.hi].detach(), atol=1e-12)
         assert torch.allclose(oi, want[U:].detach(), atol=1e-12)
+        # the same shard built from this rank's edges alone (no rank ever holds the full graph):
+        # bit-identical values, same result; other chunk counts of the pipelined all-reduce
+        eu, ei = torch.from_numpy(np.asarray(u, np.int64)), torch.from_numpy(np.asarray(i, np.int64))
+        mine = (eu >= sb.lo) & (eu < sb.hi)
+        sb2 = par.ShardedBipartite.from_local_edges(eu[mine], ei[mine], sb.bounds, rank, world, U, I, recipe="f32",
+                                                    csr_from_coo=cpu_csr_from_coo)
+        assert sb2.nnz_local == sb.nnz_local
+        base = int(sb.R.row_ptr[0])
+        assert torch.equal(sb2.R.vals, sb.R.vals[base: base + sb.nnz_local])
+        for n_chunks in (1, 3, 7):
+            ou2, oi2 = par.bipartite_propagate_mean(sb2, Xd2[sb.lo: sb.hi], Xd2[U:], 3, spmm_fn=spmm_cpu, chunks=n_chunks)
+            assert torch.allclose(ou2, ou, atol=1e-12) and torch.allclose(oi2, oi, atol=1e-12)
         some_users = torch.tensor([0, U - 1, U // 2, 3, 3])
         got2 = par.bipartite_score_topk(sb, ou, oi, some_users, 10, local_topk=local_topk, merge=_merge_cpu)
         w = want.detach()
