@@ -378,7 +378,8 @@ def run_ours(args):
     if not args.no_sharded_blocks:
         try:
             sharded5 = scaled_block(dev, rank, world, local, scale=args.scale, eval_users=args.eval_users,
-                                    steps=10, warmup=3, chunks=args.chunks)
+                                    steps=10, warmup=3, chunks=args.chunks, partition=args.partition,
+                                    rt_block_users=args.rt_block_users)
         except Exception as exc:                      # never lose the headline line to an auxiliary block
             sharded5 = {"error": repr(exc)[:300]} if rank == 0 else None
             if world > 1:
@@ -637,7 +638,7 @@ def _phase_ms(timing, steps):
 
 
 def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10, warmup=3, chunks=4,
-                 partition="bipartite"):
+                 partition="auto", rt_block_users=393216):
     """Config 5: scaled power-law graph (scale 1.0 = 10M users x 2M items x ~500M interactions),
     LightGCN-style 4-layer propagation + full-rank top-50 for `eval_users` users per step. Strong
     scaling: N = 1 runs the single-GPU operators on the whole graph; N > 1 shards users by non-zeros
@@ -650,6 +651,10 @@ def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10,
     ops, G, par, synth, lib = pkg("ops"), pkg("graph"), pkg("parallel"), pkg("synth"), pkg("lib")
     U, I, E = int(10_000_000 * scale), int(2_000_000 * scale), int(500_000_000 * scale)
     d, L, k, Bu = 64, 4, 50, eval_users
+    if partition == "auto":
+        # best measured layout per N (profiles/r02_config5_spmm_experiments.txt): one GPU runs the
+        # symmetric CSR over the stacked table in one launch per layer; several GPUs shard users
+        partition = "full" if world == 1 else "bipartite"
     gen = torch.Generator(device=dev).manual_seed(999)
     bound = (6.0 / (U + I + d)) ** 0.5
     users = torch.randint(0, U, (Bu,), generator=gen, device=dev)
@@ -666,7 +671,7 @@ def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10,
             out.append(x[max(lo, b0) - b0: min(hi, b1) - b0])
         return torch.cat(out)
 
-    if world == 1:
+    if world == 1 and partition == "full":
         su, si = synth.make_scaled_edges(dev, U, I, E)
         nnz_local = int(su.numel())
         full = G.build_ui_graph(su, si, U, I, "f64eps")
@@ -688,7 +693,8 @@ def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10,
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         su, si = synth.make_scaled_edges(dev, U, I, E, user_range=(lo, hi))
         nnz_local = int(su.numel())
-        sb = par.ShardedBipartite.from_local_edges(su, si, bounds, rank, world, U, I, "f64eps")
+        sb = par.ShardedBipartite.from_local_edges(su, si, bounds, rank, world, U, I, "f64eps",
+                                                   rt_block_users=rt_block_users)
         del su, si, deg
         Xu, Xi = x0_rows(lo, hi), x0_rows(U, U + I)
     torch.cuda.empty_cache()
@@ -701,7 +707,7 @@ def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10,
         return e
 
     def step(tm):
-        if world == 1:
+        if world == 1 and partition == "full":
             e = ev("propagate_spmm_x4") if tm is not None else None
             out = ops.propagate_mean(full, X0, L)
             if e:
@@ -716,7 +722,7 @@ def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10,
             return par.sharded_score_topk(out[:U], users, out[U + lo_i: U + hi_i].contiguous(), lo_i, k)
         ou, oi = par.bipartite_propagate_mean(sb, Xu, Xi, L, chunks=chunks, timing=tm)
         e = ev("score_topk_merge") if tm is not None else None
-        ids = par.bipartite_score_topk(sb, ou, oi, users, k)
+        ids = ops.score_mask_topk(ou, users, oi, k) if world == 1 else par.bipartite_score_topk(sb, ou, oi, users, k)
         if e:
             e[1].record()
         return ids
@@ -769,7 +775,10 @@ def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10,
                          f"interactions (scale {scale}), d=64, {Bu} eval users per step",
              "metric": "eval users/s", "value": Bu * steps / (ms / 1e3), "n_gpus": world, "scaling": "strong",
              "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "phases_ms_per_step_max_over_ranks": phases,
-             "partition": "single GPU" if world == 1 else
+             "rt_block_users": rt_block_users if partition == "bipartite" else None,
+             "partition": ("single GPU, symmetric CSR over the stacked table" if partition == "full" else
+                           "single GPU, bipartite: R (users x items) row-split; R^T (items x users) in user blocks of "
+                           f"{rt_block_users} rows whose vectors stay L2-resident") if world == 1 else
                           ("rows by nnz + all-gather of the whole table per layer" if partition == "rows" else
                            f"users by nnz (each rank builds only its own edges), items replicated: item-table all-reduce in "
                            f"{chunks} chunks per layer issued under the SpMMs (waited for right before the next layer's user-side "
@@ -841,7 +850,8 @@ def run_scaled(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
     pkg("lib").load()
     blk = scaled_block(dev, rank, world, local, scale=args.scale, eval_users=args.eval_users, steps=args.steps,
-                       warmup=args.warmup, chunks=args.chunks, partition=args.partition)
+                       warmup=args.warmup, chunks=args.chunks, partition=args.partition,
+                       rt_block_users=args.rt_block_users)
     if rank == 0:
         line = {"metric": "propagate (4 layers) + full-rank top-50, eval users/s (scaled power-law graph)",
                 "value": blk["value"], "unit": "users/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -862,7 +872,9 @@ def main():
     ap.add_argument("--workload", default="smore_baby", choices=["smore_baby", "scaled"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--eval-users", type=int, default=16384)
-    ap.add_argument("--partition", default="bipartite", choices=["bipartite", "rows"])
+    ap.add_argument("--partition", default="auto", choices=["auto", "bipartite", "rows", "full"])
+    ap.add_argument("--rt-block-users", type=int, default=393216,
+                    help="user rows per L2-resident column block of R^T (0 = unblocked)")
     ap.add_argument("--chunks", type=int, default=4)
     ap.add_argument("--no-sharded-blocks", action="store_true",
                     help="skip the config-5 / config-4 blocks of the default workload (quick runs, ncu)")

@@ -97,6 +97,19 @@ int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const flo
                        int32_t *counters, float *scratch, int32_t col_offset, const float *X,
                        int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
                        const float *cos_ref, float *cos_w, float *Y_pre, void *stream);
+/* The same operator with tuning flags for graphs whose operand X does not fit the 126 MB L2:
+ *   MMREC_SPMM_NARROW  half the lanes per task, two 16-byte chunks per lane: twice the tasks in
+ *                      flight for graphs of very short rows (the column blocks of an operand cut
+ *                      into L2-sized slices);
+ *   MMREC_SPMM_STREAM  L2 eviction policies: gathered X rows evict_last, everything touched once
+ *                      (CSR arrays, epilogue operand, output rows) evict_first. Not with cos_ref. */
+#define MMREC_SPMM_NARROW 1
+#define MMREC_SPMM_STREAM 2
+int mmrec_spmm_csr_ex_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
+                       const int32_t *tasks, int32_t n_tasks, const int32_t *slot_base,
+                       int32_t *counters, float *scratch, int32_t col_offset, const float *X,
+                       int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
+                       const float *cos_ref, float *cos_w, float *Y_pre, int32_t flags, void *stream);
 
 /* Several independent SpMMs of the same width d in ONE launch (at most 4): the item-item and R
  * propagation of the three modality views (smore.py:291-317, mgcn.py:170-184), which are

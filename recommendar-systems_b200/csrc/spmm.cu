@@ -42,6 +42,45 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
   return v;
 }
 
+// L2 eviction policies for operands that do not fit the cache (flags & MMREC_SPMM_STREAM). The
+// gathered X rows are the only data with reuse: they are loaded evict_last; everything that is
+// touched exactly once per launch (CSR arrays, the task list, the epilogue operand and the output
+// rows) goes through evict_first, so that ~10 GB of streamed bytes per launch do not push the hot
+// rows of a power-law graph out of the 126 MB L2 (ncu, 10M x 2M graph, default policy: 34 % sector
+// hit rate on the item table although the hottest 25 % of the items carry 75 % of the edges).
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float *ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg4_hint(float *ptr, const float4 &v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ int ld_stream_i32_hint(const int32_t *p, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32_hint(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 constexpr int kSeg = 64;   // non-zeros per task; must match graph.py SEG
 constexpr int kDepth = 8;  // embedding-row gathers in flight per lane
 
@@ -50,10 +89,12 @@ constexpr int kDepth = 8;  // embedding-row gathers in flight per lane
 // column index / value of the task is fetched in ONE round (kSeg / LANES per lane), then the rows
 // are gathered kDepth at a time (16 bytes per lane each); partial groups are predicated off, not
 // padded. The sum runs in CSR order whatever the grouping.
-template <int LANES, int CHUNKS>
+template <int LANES, int CHUNKS, bool STREAM = false>
 __device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t *__restrict__ col_idx,
                                             const float *__restrict__ vals, int begin, int end, int lane,
                                             const float *__restrict__ X, int d, int col_offset) {
+  uint64_t pol_first = 0, pol_last = 0;
+  if constexpr (STREAM) { pol_first = policy_evict_first(); pol_last = policy_evict_last(); }
   constexpr int NIDX = kSeg / LANES;
   constexpr int DEPTH = CHUNKS == 1 ? kDepth : kDepth / 2;
   const unsigned mask = group_mask<LANES>();
@@ -66,8 +107,13 @@ __device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t
     c[i] = 0;
     v[i] = 0.f;
     if (k < end) {
-      c[i] = ld_stream_i32(col_idx + k) - col_offset;
-      v[i] = ld_stream_f32(vals + k);
+      if constexpr (STREAM) {
+        c[i] = ld_stream_i32_hint(col_idx + k, pol_first) - col_offset;
+        v[i] = ld_stream_f32_hint(vals + k, pol_first);
+      } else {
+        c[i] = ld_stream_i32(col_idx + k) - col_offset;
+        v[i] = ld_stream_f32(vals + k);
+      }
     }
   }
 #pragma unroll
@@ -88,7 +134,8 @@ __device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t
         for (int t = 0; t < DEPTH; ++t)
 #pragma unroll
           for (int q = 0; q < CHUNKS; ++q)
-            x[t][q] = base + t < n ? ldg4(X + (size_t)cc[t] * d + (q * LANES + lane) * 4)
+            x[t][q] = base + t < n ? (STREAM ? ldg4_hint(X + (size_t)cc[t] * d + (q * LANES + lane) * 4, pol_last)
+                                             : ldg4(X + (size_t)cc[t] * d + (q * LANES + lane) * 4))
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < DEPTH; ++t)
@@ -109,10 +156,12 @@ struct Epilogue {
   float *Y_pre;
 };
 
-template <int LANES, int CHUNKS>
+template <int LANES, int CHUNKS, bool STREAM = false>
 __device__ __forceinline__ void finish_row(float4 (&acc)[CHUNKS], int row, int lane, int d,
                                            const Epilogue &ep) {
   const size_t off = (size_t)row * d;
+  uint64_t pol_first = 0;
+  if constexpr (STREAM) pol_first = policy_evict_first();
   if (ep.cos_ref != nullptr) {
     float4 e0[CHUNKS];
     float dot = 0.f, ny = 0.f, n0 = 0.f;
@@ -143,15 +192,21 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[CHUNKS], int row, int l
 #pragma unroll
   for (int q = 0; q < CHUNKS; ++q) {
     const size_t o = off + (q * LANES + lane) * 4;
-    if (ep.Y) *reinterpret_cast<float4 *>(ep.Y + o) = acc[q];
+    if (ep.Y) {
+      if constexpr (STREAM) stg4_hint(ep.Y + o, acc[q], pol_first);
+      else *reinterpret_cast<float4 *>(ep.Y + o) = acc[q];
+    }
     if (ep.acc_out) {
       float4 r = acc[q];
       if (ep.acc_in) {
-        const float4 a = *reinterpret_cast<const float4 *>(ep.acc_in + o);
+        float4 a;
+        if constexpr (STREAM) a = ldg4_hint(ep.acc_in + o, pol_first);   // read once (in place: before the store below)
+        else a = *reinterpret_cast<const float4 *>(ep.acc_in + o);
         r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
       }
       r.x *= ep.acc_scale; r.y *= ep.acc_scale; r.z *= ep.acc_scale; r.w *= ep.acc_scale;
-      *reinterpret_cast<float4 *>(ep.acc_out + o) = r;
+      if constexpr (STREAM) stg4_hint(ep.acc_out + o, r, pol_first);
+      else *reinterpret_cast<float4 *>(ep.acc_out + o) = r;
     }
   }
 }
@@ -170,7 +225,7 @@ struct Problem {
 };
 
 // One task (<= kSeg non-zeros of one row) by one sub-warp of LANES threads.
-template <int LANES, int CHUNKS>
+template <int LANES, int CHUNKS, bool STREAM = false>
 __device__ __forceinline__ void run_task(const Problem &P, int t, int lane, int d) {
   const int4 task = __ldg(P.tasks + t);          // {row, begin, end, slot}
   const int row = task.x;
@@ -184,7 +239,7 @@ __device__ __forceinline__ void run_task(const Problem &P, int t, int lane, int 
     if (ep.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.acc_in + o));
     if (ep.cos_ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.cos_ref + o));
   }
-  gather_rows<LANES, CHUNKS>(acc, P.col_idx, P.vals, task.y, task.z, lane, P.X, d, P.col_offset);
+  gather_rows<LANES, CHUNKS, STREAM>(acc, P.col_idx, P.vals, task.y, task.z, lane, P.X, d, P.col_offset);
   if (task.w >= 0) {
     // heavy row: publish this part, the last arriver reduces all parts in order
     const unsigned mask = group_mask<LANES>();
@@ -224,17 +279,17 @@ __device__ __forceinline__ void run_task(const Problem &P, int t, int lane, int 
         }
     }
   }
-  finish_row<LANES, CHUNKS>(acc, row, lane, d, ep);
+  finish_row<LANES, CHUNKS, STREAM>(acc, row, lane, d, ep);
 }
 
-template <int LANES, int CHUNKS>
-__global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 4 : 3)
+template <int LANES, int CHUNKS, bool STREAM = false>
+__global__ void __launch_bounds__(kThreads, CHUNKS == 1 || LANES <= 16 ? 4 : 3)
 spmm_csr_kernel(const Problem P, int d) {
   constexpr int GROUPS = kThreads / LANES;
   const int lane = threadIdx.x % LANES;
   const int t = blockIdx.x * GROUPS + threadIdx.x / LANES;
   if (t >= P.n_tasks) return;
-  run_task<LANES, CHUNKS>(P, t, lane, d);
+  run_task<LANES, CHUNKS, STREAM>(P, t, lane, d);
 }
 
 // Several independent SpMMs in one launch (the three modality views of SMORE/MGCN: small graphs
@@ -311,6 +366,23 @@ layergcn_cos_bwd_kernel(const float *__restrict__ dE, const float *__restrict__ 
   }
 }
 
+// Narrow tiling for graphs of very short rows (the column blocks of graph.ColumnBlockedCSR: a
+// handful of non-zeros per task): half the lanes per task, two float4 per lane -- twice as many
+// tasks in flight per SM for a kernel whose time is the number of dependent round trips per task
+// divided by the tasks in flight.
+template <typename F>
+int dispatch_width_narrow(int d, F &&f) {
+  switch (d) {
+    case 32: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
+    case 64: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
+    case 128: return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 2>{});
+    case 256: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 2>{});
+    default:
+      set_error("unsupported embedding width d=%d (supported: 32, 64, 128, 256)", d);
+      return MMREC_E_BADARG;
+  }
+}
+
 template <typename F>
 int dispatch_width(int d, F &&f) {
   switch (d) {
@@ -329,11 +401,11 @@ int dispatch_width(int d, F &&f) {
 
 using namespace mmrec;
 
-extern "C" int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
-                                  const int32_t *tasks, int32_t n_tasks, const int32_t *slot_base,
-                                  int32_t *counters, float *scratch, int32_t col_offset, const float *X,
-                                  int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
-                                  const float *cos_ref, float *cos_w, float *Y_pre, void *stream) {
+static int spmm_csr_impl(int flags, const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
+                         const int32_t *tasks, int32_t n_tasks, const int32_t *slot_base,
+                         int32_t *counters, float *scratch, int32_t col_offset, const float *X,
+                         int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
+                         const float *cos_ref, float *cos_w, float *Y_pre, void *stream) {
   MMREC_REQUIRE(row_ptr && col_idx && vals && tasks && X, MMREC_E_BADARG, "spmm: null input");
   MMREC_REQUIRE(Y || acc_out, MMREC_E_BADARG, "spmm: no output requested");
   MMREC_REQUIRE(n_tasks >= 0, MMREC_E_BADARG, "spmm: bad sizes");
@@ -344,14 +416,36 @@ extern "C" int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx
   if (n_tasks == 0) return MMREC_OK;
   Problem P{row_ptr, col_idx, vals, reinterpret_cast<const int4 *>(tasks), n_tasks, slot_base, counters, scratch,
             col_offset, X, Epilogue{Y, acc_in, acc_out, acc_scale, cos_ref, cos_w, Y_pre}};
-  return dispatch_width(d, [&](auto lanes, auto chunks) {
+  const bool narrow = flags & MMREC_SPMM_NARROW, streaming = flags & MMREC_SPMM_STREAM;
+  MMREC_REQUIRE(!(streaming && cos_ref), MMREC_E_BADARG, "spmm: the streaming cache policy has no cosine epilogue");
+  auto launch = [&](auto lanes, auto chunks) {
     constexpr int L = decltype(lanes)::value, C = decltype(chunks)::value;
     constexpr int GROUPS = kThreads / L;
     const int blocks = (n_tasks + GROUPS - 1) / GROUPS;
-    spmm_csr_kernel<L, C><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
+    if (streaming) spmm_csr_kernel<L, C, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
+    else spmm_csr_kernel<L, C, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
     MMREC_CHECK_LAUNCH("spmm_csr_kernel");
     return MMREC_OK;
-  });
+  };
+  return narrow ? dispatch_width_narrow(d, launch) : dispatch_width(d, launch);
+}
+
+extern "C" int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
+                                  const int32_t *tasks, int32_t n_tasks, const int32_t *slot_base,
+                                  int32_t *counters, float *scratch, int32_t col_offset, const float *X,
+                                  int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
+                                  const float *cos_ref, float *cos_w, float *Y_pre, void *stream) {
+  return spmm_csr_impl(0, row_ptr, col_idx, vals, tasks, n_tasks, slot_base, counters, scratch, col_offset, X, d,
+                       Y, acc_in, acc_out, acc_scale, cos_ref, cos_w, Y_pre, stream);
+}
+
+extern "C" int mmrec_spmm_csr_ex_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
+                                     const int32_t *tasks, int32_t n_tasks, const int32_t *slot_base,
+                                     int32_t *counters, float *scratch, int32_t col_offset, const float *X,
+                                     int32_t d, float *Y, const float *acc_in, float *acc_out, float acc_scale,
+                                     const float *cos_ref, float *cos_w, float *Y_pre, int32_t flags, void *stream) {
+  return spmm_csr_impl(flags, row_ptr, col_idx, vals, tasks, n_tasks, slot_base, counters, scratch, col_offset, X, d,
+                       Y, acc_in, acc_out, acc_scale, cos_ref, cos_w, Y_pre, stream);
 }
 
 extern "C" int mmrec_spmm_csr_multi_f32(const MmrecSpmmProblem *problems_host, int32_t n_problems, int32_t d,

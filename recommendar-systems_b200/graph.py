@@ -16,10 +16,12 @@ from . import lib
 SEG = 64            # non-zeros per SpMM task (kSeg in csrc/spmm.cu)
 
 
-def build_tasks(row_ptr):
+def build_tasks(row_ptr, skip_empty=False):
     """Work list of mmrec_spmm_csr_f32: int32 [n_tasks, 4] = {row, begin, end, slot}. Rows with at
     most SEG non-zeros are one task (slot -1, longest first so that the sub-warps of a warp have
     similar trip counts); heavier rows are cut into SEG-sized parts that share a reduction slot.
+    `skip_empty` leaves rows without non-zeros out (their output row is then not written at all:
+    only for accumulating launches, see ColumnBlockedCSR).
     Returns (tasks, slot_base int32 [n_heavy], total_parts)."""
     dev = row_ptr.device
     rp = row_ptr.to(torch.int64)
@@ -27,7 +29,7 @@ def build_tasks(row_ptr):
     deg = end - begin
     rows = torch.arange(deg.numel(), device=dev, dtype=torch.int64)
     heavy = deg > SEG
-    light_rows = rows[~heavy & (deg >= 0)]
+    light_rows = rows[~heavy & ((deg > 0) if skip_empty else (deg >= 0))]
     order = torch.argsort(deg[light_rows], descending=True, stable=True)
     light_rows = light_rows[order]
     light = torch.stack([light_rows, begin[light_rows], end[light_rows],
@@ -50,10 +52,10 @@ def build_tasks(row_ptr):
 
 
 class CSRGraph:
-    def __init__(self, row_ptr, col_idx, vals, n_rows, n_cols, col_offset=0, symmetric=False):
+    def __init__(self, row_ptr, col_idx, vals, n_rows, n_cols, col_offset=0, symmetric=False, skip_empty=False):
         self.row_ptr, self.col_idx, self.vals = row_ptr, col_idx, vals
         self.n_rows, self.n_cols, self.col_offset = int(n_rows), int(n_cols), int(col_offset)
-        self.tasks, self.slot_base, self.total_parts = build_tasks(row_ptr)
+        self.tasks, self.slot_base, self.total_parts = build_tasks(row_ptr, skip_empty)
         self.n_tasks = int(self.tasks.shape[0])
         self.counters = torch.zeros(max(1, self.slot_base.numel()), dtype=torch.int32,
                                     device=row_ptr.device)
@@ -144,7 +146,7 @@ def ui_blocks(g):
     return R, Rt
 
 
-def csr_from_coo(rows, cols, vals, n_rows, n_cols, with_transpose=True):
+def csr_from_coo(rows, cols, vals, n_rows, n_cols, with_transpose=True, skip_empty=False):
     """COO (int64, unsorted, duplicates kept) -> CSRGraph; optionally with its transpose for
     the backward of non-symmetric graphs."""
     lib.require_cuda(rows, cols, vals)
@@ -166,7 +168,7 @@ def csr_from_coo(rows, cols, vals, n_rows, n_cols, with_transpose=True):
         lib.call("mmrec_csr_from_coo", lib.ptr(rows), lib.ptr(cols), lib.ptr(vals), nnz, n_rows,
                  n_cols, int(transpose), lib.ptr(row_ptr), lib.ptr(col_idx), lib.ptr(out_vals), None,
                  lib.ptr(ws), ws_bytes, lib.stream())
-        return CSRGraph(row_ptr, col_idx, out_vals, out_rows, out_cols)
+        return CSRGraph(row_ptr, col_idx, out_vals, out_rows, out_cols, skip_empty=skip_empty)
 
     g = one(False)
     if with_transpose:
@@ -179,3 +181,41 @@ def from_torch_sparse(a, with_transpose=True):
     """A torch sparse COO tensor (as the reference builds them) -> CSRGraph."""
     idx, val = a._indices(), a._values()
     return csr_from_coo(idx[0], idx[1], val, a.shape[0], a.shape[1], with_transpose)
+
+
+class ColumnBlockedCSR:
+    """A [n_rows, n_cols] sparse matrix cut into column ranges, one CSRGraph per range, for
+    operands X that do not fit the L2 cache (126 MB on B200).
+
+    A row-split SpMM gathers one X row per non-zero. When X is larger than L2 and the column
+    pattern has no locality (user vectors seen from the item side of a recommendation graph: every
+    user row is wanted by ~deg different item rows, far apart in time) every gather is a DRAM
+    access: nnz * 4 d bytes instead of the 4 d * n_cols the operand actually holds. Cut into column
+    blocks whose X slice stays L2-resident, block b costs its X slice once plus a read-modify-write
+    of the output rows it touches (Y = A_0 X_0, then Y += A_b X_b through the accumulate epilogue
+    of the same kernel): DRAM traffic falls from nnz * 4 d to ~(n_cols + 2 * #(row, block) pairs) * 4 d.
+    Every block keeps GLOBAL column ids, so X is passed whole. Block 0 lists every row (it
+    initialises Y); later blocks list only the rows they touch."""
+
+    def __init__(self, blocks, n_rows, n_cols):
+        self.blocks, self.n_rows, self.n_cols = list(blocks), int(n_rows), int(n_cols)
+        self.nnz = sum(g.nnz for g in self.blocks)
+
+    @classmethod
+    def from_col_sorted_coo(cls, rows, cols, vals, n_rows, n_cols, block_cols, build=None):
+        """`cols` ascending (e.g. the edge list of a user-sorted interaction graph seen from the item
+        side): a column block is a contiguous slice of the three arrays."""
+        build = build or csr_from_coo
+        edges = torch.arange(0, n_cols + block_cols, block_cols, device=cols.device, dtype=cols.dtype)
+        cut = torch.searchsorted(cols.contiguous(), edges).tolist()
+        blocks = []
+        for b in range(len(cut) - 1):
+            lo, hi = cut[b], cut[b + 1]
+            if hi == lo and b > 0:
+                continue
+            blocks.append(build(rows[lo:hi], cols[lo:hi], vals[lo:hi], n_rows, n_cols, with_transpose=False,
+                                skip_empty=b > 0))
+        return cls(blocks, n_rows, n_cols)
+
+    def algorithmic_bytes(self, d):
+        return 8 * self.nnz + 4 * (self.n_rows + 1) + 4 * d * (self.n_rows + self.n_cols)

@@ -27,18 +27,47 @@ def _f32c(t):
     return t.contiguous()
 
 
+L2_BYTES = 126 << 20
+SPMM_NARROW, SPMM_STREAM = 1, 2
+# Measured on the 10M x 2M x 486M graph (profiles/r02_config5_spmm_experiments.txt): the eviction
+# hints change nothing (129.6 vs 130.1 ms for four layers), so they stay off unless asked for.
+_STREAM_DEFAULT = __import__("os").environ.get("MMREC_SPMM_STREAM", "0") == "1"
+
+
 def spmm_raw(g: CSRGraph, X, Y=None, acc_in=None, acc_out=None, acc_scale=1.0, cos_ref=None,
-             cos_w=None, y_pre=None):
-    """mmrec_spmm_csr_f32 on already-allocated tensors (no autograd)."""
+             cos_w=None, y_pre=None, narrow=False, stream_policy=None):
+    """mmrec_spmm_csr_f32 on already-allocated tensors (no autograd). narrow=True: the tiling for
+    graphs of very short rows; stream_policy: L2 eviction hints for operands larger than the cache
+    (default: on when the gathered table exceeds half of L2) -- mmrec_spmm_csr_ex_f32."""
     lib.require_cuda(X)
     d = X.shape[1]
     if X.shape[0] < g.n_cols:
         raise RuntimeError(f"spmm: X has {X.shape[0]} rows, graph has {g.n_cols} columns")
-    lib.call("mmrec_spmm_csr_f32", lib.ptr(g.row_ptr), lib.ptr(g.col_idx), lib.ptr(g.vals),
-             lib.ptr(g.tasks), g.n_tasks, lib.ptr(g.slot_base), lib.ptr(g.counters),
+    if stream_policy is None:
+        stream_policy = _STREAM_DEFAULT and cos_ref is None and 4 * d * g.n_cols > L2_BYTES // 2
+    flags = (SPMM_NARROW if narrow else 0) | (SPMM_STREAM if stream_policy else 0)
+    if flags:
+        lib.call("mmrec_spmm_csr_ex_f32", lib.ptr(g.row_ptr), lib.ptr(g.col_idx), lib.ptr(g.vals),
+                 lib.ptr(g.tasks), g.n_tasks, lib.ptr(g.slot_base), lib.ptr(g.counters),
+                 lib.ptr(g.scratch(d)), g.col_offset, lib.ptr(X), d, lib.ptr(Y),
+                 lib.ptr(acc_in), lib.ptr(acc_out), float(acc_scale), lib.ptr(cos_ref), lib.ptr(cos_w),
+                 lib.ptr(y_pre), flags, lib.stream())
+        return
+    lib.call("mmrec_spmm_csr_f32", lib.ptr(g.row_ptr), lib.ptr(g.col_idx),
+             lib.ptr(g.vals), lib.ptr(g.tasks), g.n_tasks, lib.ptr(g.slot_base), lib.ptr(g.counters),
              lib.ptr(g.scratch(d)), g.col_offset, lib.ptr(X), d, lib.ptr(Y),
              lib.ptr(acc_in), lib.ptr(acc_out), float(acc_scale), lib.ptr(cos_ref), lib.ptr(cos_w),
              lib.ptr(y_pre), lib.stream())
+
+
+def spmm_blocked_raw(bg, X, Y):
+    """Y = A X for a graph.ColumnBlockedCSR: one launch per column block, the first writes Y, the
+    others accumulate into it (the X slice of the block in flight stays L2-resident)."""
+    for b, g in enumerate(bg.blocks):
+        if b == 0:
+            spmm_raw(g, X, Y=Y, narrow=True)
+        else:
+            spmm_raw(g, X, acc_in=Y, acc_out=Y, narrow=True)
 
 
 class _SpMM(torch.autograd.Function):

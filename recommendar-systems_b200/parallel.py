@@ -188,8 +188,8 @@ def sharded_score_topk(user_emb, users, item_emb_local, item_lo, k, mask_rowptr=
 
 
 # ------------------------------------------------------------------ user-partitioned bipartite
-def _spmm_cuda(g, X, Y=None, acc_in=None, acc_out=None, scale=1.0):
-    ops.spmm_raw(g, X, Y=Y, acc_in=acc_in, acc_out=acc_out, acc_scale=scale)
+def _spmm_cuda(g, X, Y=None, acc_in=None, acc_out=None, scale=1.0, narrow=False):
+    ops.spmm_raw(g, X, Y=Y, acc_in=acc_in, acc_out=acc_out, acc_scale=scale, narrow=narrow)
 
 
 class ShardedBipartite:
@@ -211,12 +211,13 @@ class ShardedBipartite:
         items = full.col_idx[a:b].to(torch.int64) - U
         build = csr_from_coo or G.csr_from_coo
         self.Rt = build(items, rows_local, full.vals[a:b], I, hi - lo, with_transpose=False)
+        self.Rt_blocked = None
         self.nnz_local = b - a
         self._rt_chunks = {}
 
     @classmethod
     def from_local_edges(cls, users, items, bounds, rank, world, n_users, n_items, recipe="f64eps", group=None,
-                         csr_from_coo=None):
+                         csr_from_coo=None, rt_block_users=None):
         """Build rank p's share WITHOUT ever holding the full graph: `users` / `items` are this
         rank's unique training edges (global ids, users in [bounds[rank], bounds[rank + 1])).
         Values follow graph.build_ui_graph's recipe (D^-1/2 A D^-1/2 with the reference's own host
@@ -243,9 +244,17 @@ class ShardedBipartite:
             vals = lut[deg_u[rows_local]].to(torch.float32) * lut[deg_i[items]].to(torch.float32)
         build = csr_from_coo or G.csr_from_coo
         self.R = build(rows_local, items, vals, hi - lo, I, with_transpose=False)
-        self.Rt = build(items, rows_local, vals, I, hi - lo, with_transpose=False)
         self.nnz_local = int(users.numel())
         self._rt_chunks = {}
+        self.Rt_blocked = None
+        if rt_block_users and hi - lo > rt_block_users:
+            # the local user table does not fit L2: R_p^T in user (column) blocks, see
+            # graph.ColumnBlockedCSR. `users` must be ascending (edge lists sorted by user are).
+            self.Rt = None
+            self.Rt_blocked = G.ColumnBlockedCSR.from_col_sorted_coo(items, rows_local, vals, I, hi - lo,
+                                                                     int(rt_block_users), build=build)
+        else:
+            self.Rt = build(items, rows_local, vals, I, hi - lo, with_transpose=False)
         return self
 
     def rt_chunks(self, n_chunks):
@@ -288,7 +297,9 @@ def bipartite_propagate_mean(sb: ShardedBipartite, Xu_local, Xi, n_layers, group
     acc_u, acc_i = Xu_local, Xi.clone()
     xu, xi = Xu_local.contiguous(), Xi.contiguous()
     d = xi.shape[1]
-    parts = sb.rt_chunks(chunks)
+    blocked = getattr(sb, "Rt_blocked", None)
+    parts = sb.rt_chunks(chunks) if blocked is None else None
+    multi = sb.world > 1
 
     def mark(name):
         if timing is None:
@@ -308,9 +319,23 @@ def bipartite_propagate_mean(sb: ShardedBipartite, Xu_local, Xi, n_layers, group
         yi = torch.empty(sb.I, d, dtype=xi.dtype, device=xi.device)
         works = []
         ev = mark("rt_spmm")
-        for g, a, b in parts:
-            spmm_fn(g, xu, Y=yi[a:b])                         # (a): this rank's users -> item range [a, b)
-            works.append(dist.all_reduce(yi[a:b], group=group, async_op=True))
+        if blocked is not None:
+            # user table larger than L2: one launch per user block (its vectors stay L2-resident), the
+            # item table accumulates across blocks and is reduced whole; the exchange still hides
+            # under (b) of this layer and (a) of the next
+            kw = {"narrow": True} if spmm_fn is _spmm_cuda else {}
+            for bi, g in enumerate(blocked.blocks):
+                if bi == 0:
+                    spmm_fn(g, xu, Y=yi, **kw)
+                else:
+                    spmm_fn(g, xu, acc_in=yi, acc_out=yi, **kw)
+            if multi:
+                works.append(dist.all_reduce(yi, group=group, async_op=True))
+        else:
+            for g, a, b in parts:
+                spmm_fn(g, xu, Y=yi[a:b])                     # (a): this rank's users -> item range [a, b)
+                if multi:
+                    works.append(dist.all_reduce(yi[a:b], group=group, async_op=True))
         done(ev)
         if pending is not None:                               # (b) needs the reduced item table of layer l - 1
             ev = mark("exposed_all_reduce")

@@ -261,3 +261,39 @@ def test_model_full_sort_predict_matches_fused_topk():
     ids = m.full_sort_topk(users, 10)
     want = torch.sort(scores, dim=1, descending=True, stable=True)[1][:, :10]
     assert torch.equal(ids, want)
+
+
+# ------------------------------------------------------------------ column-blocked SpMM (X > L2)
+def test_column_blocked_spmm_and_shard_local_bipartite_build():
+    """graph.ColumnBlockedCSR (Y = A_0 X_0, Y += A_b X_b) == the unblocked SpMM, and a
+    ShardedBipartite built from a rank's own edges (with and without user blocks) propagates like
+    the symmetric full graph."""
+    G, ops, par, synth = pkg("graph"), pkg("ops"), pkg("parallel"), pkg("synth")
+    U, I, E, d = 20000, 3000, 400000, 64
+    su, si = synth.make_scaled_edges(DEV, U, I, E, block=4096)
+    full = G.build_ui_graph(su, si, U, I, "f64eps")
+    gen = torch.Generator().manual_seed(9)
+    X = torch.randn(U + I, d, generator=gen).to(DEV)
+    want = ops.propagate_mean(full, X, 3)
+    bounds = np.array([0, U], dtype=np.int64)
+    for blk in (None, 3000, 7001):
+        sb = par.ShardedBipartite.from_local_edges(su, si, bounds, 0, 1, U, I, "f64eps", rt_block_users=blk)
+        assert (sb.Rt_blocked is not None) == (blk is not None)
+        if blk is not None:
+            assert len(sb.Rt_blocked.blocks) == -(-U // blk) and sb.Rt_blocked.nnz == su.numel()
+            # the blocked operator alone against the plain one
+            Rt = G.csr_from_coo(si, su, sb.R.vals.new_ones(su.numel()), I, U, with_transpose=False)
+            ones = G.ColumnBlockedCSR.from_col_sorted_coo(si, su, sb.R.vals.new_ones(su.numel()), I, U, blk)
+            y0 = torch.empty(I, d, device=DEV)
+            y1 = torch.full((I, d), float("nan"), device=DEV)
+            ops.spmm_raw(Rt, X[:U].contiguous(), Y=y0)
+            ops.spmm_blocked_raw(ones, X[:U].contiguous(), y1)
+            assert rel(y1, y0) < 1e-6
+        ou, oi = par.bipartite_propagate_mean(sb, X[:U].contiguous(), X[U:].contiguous(), 3)
+        assert rel(ou, want[:U]) < 2e-6 and rel(oi, want[U:]) < 2e-6
+    # values of the shard-local build are the full graph's, bit for bit
+    r, c, v = full.to_torch_coo()
+    sb = par.ShardedBipartite.from_local_edges(su, si, bounds, 0, 1, U, I, "f64eps")
+    r2, c2, v2 = sb.R.to_torch_coo()
+    m = r < U
+    assert np.array_equal(r[m], r2) and np.array_equal(c[m] - U, c2) and np.array_equal(v[m].view(np.uint32), v2.view(np.uint32))
