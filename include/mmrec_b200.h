@@ -498,6 +498,16 @@ int mmrec_neg_sample_mt19937_host(uint32_t *mt_state_host, const int64_t *all_it
                                   const int64_t *hist_cols_host, int64_t n_hist_users,
                                   const int64_t *users_host, int64_t n, int64_t *neg_out_host);
 
+/* Counter-based negative sampler on the DEVICE (config 5: 500 M draws per epoch).
+ * Same rule as the reference (uniform item, re-drawn while it is in the user's training history,
+ * utils/dataloader.py:267-275, 307-309) on a stateless splitmix64 stream keyed by (seed, step,
+ * position, draw): any rank regenerates any batch without communication. All pointers are DEVICE
+ * pointers; hist_rowptr int64 [n_users + 1] / hist_cols int32 ascending inside a user; all_items
+ * maps the draw to an item id (NULL: identity). neg_out[b] = -1 if max_draws were all rejected. */
+int mmrec_neg_sample_counter(const int64_t *users, int64_t n, const int64_t *all_items, int64_t n_items,
+                             const int64_t *hist_rowptr, const int32_t *hist_cols, uint64_t seed, uint64_t step,
+                             int32_t max_draws, int64_t *neg_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

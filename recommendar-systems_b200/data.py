@@ -211,6 +211,63 @@ class TrainDataLoader(AbstractDataLoader):
         return batch
 
 
+class DeviceTrainLoader:
+    """Training batches produced entirely on the device (config 5: hundreds of millions of
+    interactions per epoch, where the reference's Python loop -- one `random.sample` per
+    interaction, dataloader.py:267-275 -- cannot run at all). Same batch format as
+    TrainDataLoader (`LongTensor[3, B]` = users, positive items, negative items on the device),
+    same sampling rule (uniform item, rejected while in the user's training history) on the
+    stateless counter stream of mmrec_neg_sample_counter, so every rank of a sharded run can
+    regenerate exactly the same batch from (seed, epoch, batch index) without a broadcast.
+    `users` / `items`: the training interactions on the device (int64)."""
+
+    def __init__(self, users, items, n_users, n_items, batch_size, seed=999, shuffle=True, max_draws=64):
+        from . import lib
+        lib.require_cuda(users, items)
+        self.users, self.items = users.to(torch.int64).contiguous(), items.to(torch.int64).contiguous()
+        self.n_users, self.n_items, self.step = int(n_users), int(n_items), int(batch_size)
+        self.seed, self.shuffle, self.max_draws = int(seed), bool(shuffle), int(max_draws)
+        self.device = users.device
+        # per-user history CSR, ascending item ids (the rejection test is a binary search)
+        key = torch.sort(self.users * self.n_items + self.items)[0]
+        self.hist_cols = (key % self.n_items).to(torch.int32).contiguous()
+        counts = torch.bincount(key // self.n_items, minlength=self.n_users)
+        self.hist_rowptr = torch.zeros(self.n_users + 1, dtype=torch.int64, device=self.device)
+        self.hist_rowptr[1:] = torch.cumsum(counts, 0)
+        self.epoch = -1
+        self.pr = 0
+        self.order = None
+
+    def __len__(self):
+        return -(-self.users.numel() // self.step)
+
+    def __iter__(self):
+        self.epoch += 1
+        self.pr = 0
+        if self.shuffle:
+            g = torch.Generator(device=self.device).manual_seed(self.seed + self.epoch)
+            self.order = torch.randperm(self.users.numel(), generator=g, device=self.device)
+        return self
+
+    def sample_negatives(self, u, step_id):
+        from . import lib
+        neg = torch.empty_like(u)
+        lib.call("mmrec_neg_sample_counter", lib.ptr(u), u.numel(), None, self.n_items, lib.ptr(self.hist_rowptr),
+                 lib.ptr(self.hist_cols), self.seed, int(step_id), self.max_draws, lib.ptr(neg), lib.stream())
+        return neg
+
+    def __next__(self):
+        if self.pr >= self.users.numel():
+            raise StopIteration
+        sl = slice(self.pr, self.pr + self.step)
+        idx = self.order[sl] if self.order is not None else torch.arange(sl.start, min(sl.stop, self.users.numel()),
+                                                                         device=self.device)
+        u, i = self.users[idx].contiguous(), self.items[idx]
+        step_id = self.epoch * len(self) + self.pr // self.step
+        self.pr += self.step
+        return torch.stack([u, i, self.sample_negatives(u, step_id)])
+
+
 class EvalDataLoader(AbstractDataLoader):
     """dataloader.py:321-418."""
 

@@ -91,6 +91,7 @@ SIGNATURES = {
     "mmrec_topk_metrics_workspace_bytes": (_sz, [_i32]),
     "mmrec_topk_metrics_f64": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mmrec_topk_merge": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "mmrec_neg_sample_counter": (C.c_int, [_p, _i64, _p, _i64, _p, _p, C.c_uint64, C.c_uint64, _i32, _p, _p]),
     "mmrec_neg_sample_mt19937_host": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _p, _i64, _p]),
 }
 

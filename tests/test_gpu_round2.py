@@ -297,3 +297,37 @@ def test_column_blocked_spmm_and_shard_local_bipartite_build():
     r2, c2, v2 = sb.R.to_torch_coo()
     m = r < U
     assert np.array_equal(r[m], r2) and np.array_equal(c[m] - U, c2) and np.array_equal(v[m].view(np.uint32), v2.view(np.uint32))
+
+
+# ------------------------------------------------------------------ f3: device negative sampler
+def test_device_negative_sampler_matches_numpy_restatement_and_rule():
+    """mmrec_neg_sample_counter == oracle/sampler.py bit for bit; no negative is in its user's history;
+    the draws are uniform over the items outside it; batches are reproducible from (seed, step)."""
+    from oracle import sampler as osampler
+    data_m, synth = pkg("data"), pkg("synth")
+    U, I = 3000, 500
+    su, si = synth.make_scaled_edges(DEV, U, I, 60000, block=1024)
+    dl = data_m.DeviceTrainLoader(su, si, U, I, batch_size=4096, seed=7)
+    rp, hc = dl.hist_rowptr.cpu().numpy(), dl.hist_cols.cpu().numpy()
+    seen = []
+    for step, batch in enumerate(dl):
+        assert batch.shape[0] == 3 and batch.dtype == torch.int64 and batch.is_cuda
+        u, pos, neg = (t.cpu().numpy() for t in batch)
+        want = osampler.neg_sample_counter(u, None, I, rp, hc, 7, step)
+        assert np.array_equal(neg, want)
+        key = np.sort(su.cpu().numpy() * I + si.cpu().numpy())
+        assert not np.isin(u * I + neg, key).any() and (neg >= 0).all()
+        assert np.isin(u * I + pos, key).all()
+        seen.append(neg)
+        if step == 3:
+            break
+    again = dl.sample_negatives(batch[0], 3)
+    assert torch.equal(again, batch[2])                      # stateless: (seed, step, position) -> same draw
+    counts = np.bincount(np.concatenate(seen), minlength=I)
+    assert counts.min() > 0 and counts.max() < 4 * counts.mean()      # uniform over items, not popularity-biased
+    # a user whose history is (almost) everything: the rejection loop still terminates
+    hist_u = torch.zeros(I - 1, dtype=torch.int64, device=DEV)
+    hist_i = torch.arange(I - 1, device=DEV)
+    dl2 = data_m.DeviceTrainLoader(hist_u, hist_i, 1, I, batch_size=64, seed=1, max_draws=4096)
+    neg2 = dl2.sample_negatives(torch.zeros(64, dtype=torch.int64, device=DEV), 0)
+    assert bool(((neg2 == I - 1) | (neg2 == -1)).all()) and int((neg2 == I - 1).sum()) > 0
