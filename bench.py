@@ -107,12 +107,28 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_REAL_STDOUT = None
+
+
 def quiet_nccl():
-    """stdout carries exactly one JSON line: NCCL's version banner (printed at every debug level but
-    NONE) and anything else it logs go to stderr."""
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    """stdout carries exactly one JSON line. NCCL writes its version banner (and whatever else it
+    logs) to file descriptor 1 from C, whatever NCCL_DEBUG_FILE says: until the result is printed,
+    descriptor 1 points at stderr; `emit` restores it for the one line."""
+    global _REAL_STDOUT
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    """Print the result line on the real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 def build_env(device, seed=999, model_name="SMORE", shape="baby", overrides=None):
@@ -453,7 +469,7 @@ def run_ours(args):
             line["torch_cuda_reference"] = torch_cuda_reference(dev)
         except Exception as exc:
             line["torch_cuda_reference"] = {"error": repr(exc)[:300]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -651,6 +667,8 @@ def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10,
     ops, G, par, synth, lib = pkg("ops"), pkg("graph"), pkg("parallel"), pkg("synth"), pkg("lib")
     U, I, E = int(10_000_000 * scale), int(2_000_000 * scale), int(500_000_000 * scale)
     d, L, k, Bu = 64, 4, 50, eval_users
+    sampler = ClockSampler(local)      # from the graph build on: the timed steps alone last < 0.3 s at 8 GPUs
+    sampler.start()
     if partition == "auto":
         # best measured layout per N (profiles/r02_config5_spmm_experiments.txt): one GPU runs the
         # symmetric CSR over the stacked table in one launch per layer; several GPUs shard users
@@ -728,8 +746,6 @@ def scaled_block(dev, rank, world, local, scale=1.0, eval_users=16384, steps=10,
         return ids
 
     with torch.no_grad():
-        sampler = ClockSampler(local)
-        sampler.start()
         for _ in range(warmup):
             ids = step(None)
         torch.cuda.synchronize()
@@ -858,7 +874,7 @@ def run_scaled(args):
                 "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": blk, "clocks": blk["clocks"],
                 "gpu_launches": blk["gpu_launches"]}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
