@@ -251,6 +251,16 @@ int mmrec_gemm_tf32x3_f32(const float *A, int32_t a_kcontig, const float *B, int
  * The backward needs mmrec_dense_act_bwd_workspace_bytes of scratch; per-CTA partial sums of
  * dW/db are added in a fixed order (bit-reproducible).
  * ---------------------------------------------------------------------------------------- */
+/* act(x W^T + b) for x [M, K] with MANY rows on the tcgen05 GEMM (bias and tanh / sigmoid in its
+ * store epilogue): the 128 x 128 layers of the side network and gates at d = 128 (SMORE on the
+ * Clothing-shaped data: 62k node rows; smore.py:265-272, 321-330), where the mma.sync tile kernels
+ * behind mmrec_dense_act_* run at a tenth of it. act: 0 none, 1 tanh, 2 sigmoid.
+ * Backward: dz = mmrec_act_bwd_f32(dy, y) (dy * act'(y)), then dx = dz W, dW = dz^T x on
+ * mmrec_gemm_tf32x3_f32 (tcgen05 for these shapes) and db = mmrec_colsum_f32(dz). */
+int mmrec_linear_act_tc_supported(int32_t M, int32_t K, int32_t N);
+int mmrec_linear_act_tc_f32(const float *x, const float *W, const float *b, float *y, int32_t M, int32_t K, int32_t N,
+                            int32_t act, void *stream);
+int mmrec_act_bwd_f32(const float *dy, const float *y, int64_t numel, int32_t act, float *dz, void *stream);
 int mmrec_dense_act_supported(int32_t K, int32_t N);
 size_t mmrec_dense_act_bwd_workspace_bytes(int32_t K, int32_t N);
 int mmrec_dense_act_fwd_f32(const float *X, const float *W, const float *bias, float *Y, int32_t M,

@@ -63,6 +63,7 @@ struct GemmArgs {
   float eps, weight_decay, grad_scale;
   double *sumsq_partial;            // optional: per-CTA sum of the updated parameters' squares
   int debug;                        // MMREC_TA_DEBUG (timing experiments only): 1 = no arithmetic, 2 = no copies
+  int act;                          // EPI_STORE, no split-K: 0 = none, 1 = tanh, 2 = sigmoid after the bias
 };
 
 // Byte offset of element chunk inside one operand tile (extent E along M/N, 32 along K).
@@ -400,6 +401,11 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
             if (mw + rr < g.M) {
               float4 o = *reinterpret_cast<const float4 *>(tr + rr * P + cq);
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              if (g.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+              else if (g.act == 2) {
+                o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
+                o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+              }
               *reinterpret_cast<float4 *>(Cs + (size_t)(mw + rr) * g.ldc + n) = o;
             }
           }
@@ -489,9 +495,15 @@ int launch_tc05_nt(int nt, const GemmArgs &g, int k_splits, int n_chunks, cudaSt
 //   kind 3: A [M,K], B [K,N]      (dx)        -> N ranges, no split-K
 int gemm_tc05_kind(int M, int N, int K, int a_kcontig, int b_kcontig) {
   auto tile_ok = [](int n) { return n == 32 || n == 64 || n == 128; };
-  if (a_kcontig && b_kcontig) return (M >= 1024 && K >= 256 && tile_ok(N) && K % 4 == 0) ? 1 : 0;
-  if (!a_kcontig && !b_kcontig) return (N >= 1024 && K >= 256 && tile_ok(M) && N % 4 == 0) ? 2 : 0;
-  if (a_kcontig && !b_kcontig) return (M >= 1024 && N >= 1024 && N % 128 == 0 && K % 4 == 0 && K <= 256) ? 3 : 0;
+  // the table-sized projections, and the 128 x 128 dense layers over many rows (SMORE / Clothing,
+  // d = 128: 62k node rows) where the mma.sync tile kernels run at a tenth of these
+  const bool wide_dense = K == 128 || N == 128;
+  if (a_kcontig && b_kcontig)
+    return (((M >= 1024 && K >= 256) || (M >= 8192 && K == 128 && N == 128)) && tile_ok(N) && K % 4 == 0) ? 1 : 0;
+  if (!a_kcontig && !b_kcontig)
+    return (((N >= 1024 && K >= 256) || (K >= 8192 && M == 128 && N == 128)) && tile_ok(M) && N % 4 == 0) ? 2 : 0;
+  if (a_kcontig && !b_kcontig)
+    return (((M >= 1024 && N >= 1024) || (M >= 8192 && N == 128 && wide_dense)) && N % 128 == 0 && K % 4 == 0 && K <= 256) ? 3 : 0;
   return 0;
 }
 
@@ -516,15 +528,19 @@ int gemm_tc05_splits(int M, int N, int K, int kind) {
   if (kind == 3) return 1;
   const int m_tiles = kind == 2 ? (N + kBM - 1) / kBM : (M + kBM - 1) / kBM;
   const int n_kb = (K + kKB - 1) / kKB;
-  return best_parts(m_tiles, (n_kb + kChunkKB - 1) / kChunkKB, 32, 3);
+  // a single row tile (128 x 128 weight gradients over tens of thousands of rows): the reduction
+  // dimension is all the parallelism there is
+  return best_parts(m_tiles, (n_kb + kChunkKB - 1) / kChunkKB, m_tiles == 1 ? 128 : 32, 3);
 }
 
 // Returns MMREC_OK, a negative error, or 1 when the shape is not covered.
 int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcontig, const float *bias, float *C,
-                       int M, int N, int K, int splits, float *ws, cudaStream_t stream) {
+                       int M, int N, int K, int splits, float *ws, cudaStream_t stream, int act = 0) {
   const int kind = gemm_tc05_kind(M, N, K, a_kcontig, b_kcontig);
   if (kind == 0) return 1;
+  if (act != 0 && (kind != 1 || splits != 1)) return 1;    // the activation rides in the store epilogue only
   GemmArgs g{};
+  g.act = act;
   const int n_kb = (K + kKB - 1) / kKB, n_units = (n_kb + kChunkKB - 1) / kChunkKB;
   g.kb_per_split = (n_units + splits - 1) / splits * kChunkKB;
   const int k_splits = (n_kb + g.kb_per_split - 1) / g.kb_per_split;

@@ -234,7 +234,7 @@ int launch(const float *A, const float *B, const float *bias, float *C, float *w
 int gemm_tc05_kind(int M, int N, int K, int a_kcontig, int b_kcontig);
 int gemm_tc05_splits(int M, int N, int K, int kind);
 int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcontig, const float *bias, float *C,
-                       int M, int N, int K, int splits, float *ws, cudaStream_t stream);
+                       int M, int N, int K, int splits, float *ws, cudaStream_t stream, int act);
 static bool tc05_enabled() {
   static const bool on = !(getenv("MMREC_GEMM_TC") && atoi(getenv("MMREC_GEMM_TC")) == 0);
   return on;
@@ -273,7 +273,7 @@ extern "C" int mmrec_gemm_tf32x3_f32(const float *A, int32_t a_kcontig, const fl
                 "gemm: contiguous dimensions must be multiples of 4 floats");
   MMREC_REQUIRE(splits == 1 || ws, MMREC_E_WORKSPACE, "gemm: split-K needs a workspace of splits*M*N floats");
   if (tc05_enabled()) {     // tcgen05 kernel for the table-sized projections; 1 = shape not covered
-    const int rc = gemm_tc05_dispatch(A, a_kcontig, B, b_kcontig, bias, C, M, N, K, splits, ws, stream);
+    const int rc = gemm_tc05_dispatch(A, a_kcontig, B, b_kcontig, bias, C, M, N, K, splits, ws, stream, 0);
     if (rc <= 0) {
       if (rc == MMREC_OK && splits > 1) {
         const int64_t mn = (int64_t)M * N;
@@ -302,4 +302,51 @@ extern "C" int mmrec_gemm_tf32x3_f32(const float *A, int32_t a_kcontig, const fl
   }
   set_error("gemm: layout (A M-contiguous, B K-contiguous) is not instantiated");
   return MMREC_E_BADARG;
+}
+
+// ---- Linear + activation over many rows on the tcgen05 kernel (d x d layers at d = 128) --------
+namespace mmrec {
+namespace {
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float4 *__restrict__ dy, const float4 *__restrict__ y, int64_t n4, int act, float4 *__restrict__ dz) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 g = dy[i], v = y[i];
+  float4 o;
+  if (act == 1) o = make_float4(g.x * (1.f - v.x * v.x), g.y * (1.f - v.y * v.y), g.z * (1.f - v.z * v.z), g.w * (1.f - v.w * v.w));
+  else o = make_float4(g.x * ((1.f - v.x) * v.x), g.y * ((1.f - v.y) * v.y), g.z * ((1.f - v.z) * v.z), g.w * ((1.f - v.w) * v.w));
+  dz[i] = o;
+}
+}  // namespace
+}  // namespace mmrec
+
+extern "C" int mmrec_linear_act_tc_supported(int32_t M, int32_t K, int32_t N) {
+  return tc05_enabled() && gemm_tc05_kind(M, N, K, 1, 1) == 1 && gemm_tc05_splits(M, N, K, 1) == 1;
+}
+
+extern "C" int mmrec_linear_act_tc_f32(const float *x, const float *W, const float *b, float *y, int32_t M, int32_t K,
+                                       int32_t N, int32_t act, void *stream_) {
+  MMREC_REQUIRE(x && W && y, MMREC_E_BADARG, "linear_act_tc: null pointer");
+  MMREC_REQUIRE(act >= 0 && act <= 2, MMREC_E_BADARG, "linear_act_tc: act must be 0 (none), 1 (tanh) or 2 (sigmoid)");
+  MMREC_REQUIRE(aligned16(x) && aligned16(W) && aligned16(y) && aligned16(b), MMREC_E_ALIGN,
+                "linear_act_tc: operands must be 16-byte aligned");
+  MMREC_REQUIRE(mmrec_linear_act_tc_supported(M, K, N), MMREC_E_BADARG,
+                "linear_act_tc: shape %d x %d -> %d is not covered by the tcgen05 kernel without split-K", M, K, N);
+  const int rc = gemm_tc05_dispatch(x, 1, W, 1, b, y, M, N, K, 1, nullptr, (cudaStream_t)stream_, act);
+  if (rc > 0) {
+    set_error("linear_act_tc: dispatch refused the shape");
+    return MMREC_E_BADARG;
+  }
+  return rc;
+}
+
+extern "C" int mmrec_act_bwd_f32(const float *dy, const float *y, int64_t numel, int32_t act, float *dz, void *stream_) {
+  MMREC_REQUIRE(dy && y && dz, MMREC_E_BADARG, "act_bwd: null pointer");
+  MMREC_REQUIRE(numel > 0 && numel % 4 == 0 && (act == 1 || act == 2), MMREC_E_BADARG, "act_bwd: bad arguments");
+  MMREC_REQUIRE(aligned16(dy) && aligned16(y) && aligned16(dz), MMREC_E_ALIGN, "act_bwd: operands must be 16-byte aligned");
+  const int64_t n4 = numel / 4;
+  act_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      (const float4 *)dy, (const float4 *)y, n4, act, (float4 *)dz);
+  MMREC_CHECK_LAUNCH("act_bwd_kernel");
+  return MMREC_OK;
 }

@@ -744,10 +744,49 @@ class _DenseAct(torch.autograd.Function):
         return dx, dW, db, None
 
 
+class _DenseActTC(torch.autograd.Function):
+    """act(F.linear(x, W, b)) over many rows on the tcgen05 GEMM (activation in its epilogue);
+    backward = dz = dy * act'(y), dx = dz W, dW = dz^T x (tcgen05 as well), db = colsum(dz)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        x, W = _f32c(x), _f32c(W)
+        b = None if b is None else _f32c(b)
+        M, K = x.shape
+        N = W.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        lib.call("mmrec_linear_act_tc_f32", lib.ptr(x), lib.ptr(W), lib.ptr(b), lib.ptr(y), M, K, N, act, lib.stream())
+        ctx.act, ctx.has_bias = act, b is not None
+        ctx.save_for_backward(x, W, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dy = _f32c(dy)
+        M, K = x.shape
+        N = W.shape[0]
+        if ctx.act:
+            dz = torch.empty_like(dy)
+            lib.call("mmrec_act_bwd_f32", lib.ptr(dy), lib.ptr(y), dy.numel(), ctx.act, lib.ptr(dz), lib.stream())
+        else:
+            dz = dy
+        dx = gemm(dz, True, W, False, M, K, N) if ctx.needs_input_grad[0] else None
+        dW = gemm(dz, False, x, False, N, K, M) if ctx.needs_input_grad[1] else None
+        db = colsum(dz) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dW, db, None
+
+
+def dense_act_tc_supported(M, K, N):
+    return bool(lib.load().mmrec_linear_act_tc_supported(int(M), int(K), int(N)))
+
+
 def dense_act(x, W, b=None, act=None):
     """act(F.linear(x, W, b)) for the d x d side-network layers in ONE launch (forward) and one
     launch + a partial-sum reduce (backward: dX, dW, db and the activation derivative together);
     3xTF32 tensor-core products (fp32-class accuracy). Other shapes: `linear` + torch activation."""
+    if x.dim() == 2 and x.is_cuda and W.shape[0] == 128 and dense_act_tc_supported(x.shape[0], W.shape[1], W.shape[0]):
+        return _DenseActTC.apply(x, W, b, _ACT_CODE[act])       # many rows x (128 x 128): tcgen05
     if x.dim() == 2 and x.is_cuda and lib.load().mmrec_dense_act_supported(W.shape[1], W.shape[0]):
         return _DenseAct.apply(x, W, b, _ACT_CODE[act])
     y = linear(x, W, b)
@@ -805,6 +844,10 @@ def dense_stack_batch(stacks, xs):
                 return None
         return mods[0], act
     info = [one_layer(st) for st in stacks]
+    if all(i is not None for i in info) and all(x.dim() == 2 and x.is_cuda for x in xs) and all(
+            i[0].weight.shape[0] == 128 and dense_act_tc_supported(x.shape[0], i[0].weight.shape[1], 128)
+            for i, x in zip(info, xs)):
+        return [dense_act(x, i[0].weight, i[0].bias, i[1]) for i, x in zip(info, xs)]
     ok = (1 < len(stacks) <= 4 and all(i is not None for i in info) and len({i[1] for i in info}) == 1
           and len({tuple(i[0].weight.shape) for i in info}) == 1 and len({tuple(x.shape) for x in xs}) == 1
           and all(x.dim() == 2 and x.is_cuda for x in xs)

@@ -263,7 +263,9 @@ def test_linear_tf32x3_forward_backward(M, N, K):
 @pytest.mark.parametrize("M,d,act,bias", [(26495, 64, "sigmoid", True), (7050, 64, "tanh", True),
                                           (7050, 64, None, False), (1, 64, "sigmoid", True),
                                           (333, 32, "tanh", True), (20000, 32, None, True),
-                                          (5000, 128, "sigmoid", True), (10001, 128, "tanh", False)])
+                                          (5000, 128, "sigmoid", True), (10001, 128, "tanh", False),
+                                          (23033, 128, "sigmoid", True), (62420, 128, "tanh", True),
+                                          (62420, 128, None, False)])
 def test_dense_act_forward_backward(M, d, act, bias):
     """K4b: fused act(x W^T + b) and its one-launch backward (dX, dW, db, act') vs float64 torch."""
     ops = pkg("ops")
