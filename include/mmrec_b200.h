@@ -426,6 +426,10 @@ int mmrec_row_topk_f32(const float *mat, int32_t n_rows, int32_t n_cols, int64_t
  * `dy.sum(0)` of nn.Linear over a whole table (smore.py:257-259, mgcn.py:148-150 autograd);
  * fixed summation order, one launch. */
 int mmrec_colsum_f32(const float *x, int32_t M, int32_t N, float *out, void *stream);
+/* The same with a workspace of mmrec_colsum_workspace_bytes(M, N) bytes (0: not needed): tall
+ * matrices (M >= 16384) are summed in two coalesced stages instead of one strided pass. */
+size_t mmrec_colsum_workspace_bytes(int32_t M, int32_t N);
+int mmrec_colsum_ws_f32(const float *x, int32_t M, int32_t N, float *out, float *workspace, void *stream);
 /* SMORE residual modality injection (smore.py:269-272): o_m = item + scale * g_m for the image /
  * text / fusion gates in one launch, and its autograd in one launch:
  * d_item = d0 + d1 + d2, dg_m = scale * d_m. numel % 4 == 0, 16-byte aligned. */

@@ -61,10 +61,69 @@ colsum4_kernel(const float *__restrict__ x, int M, int N, float *__restrict__ ou
 }  // namespace
 }  // namespace mmrec
 
+// Tall matrices (tens of thousands of rows: the [N_nodes, d] gradients of the side-network layers):
+// one CTA per 4 columns leaves 32 CTAs each reading 16 bytes of every 512-byte row. Stage 1 gives
+// every CTA a band of whole rows (coalesced) and writes one partial row per CTA, stage 2 is the
+// kernel above over the partials. Fixed order in both stages: deterministic.
+namespace mmrec {
+namespace {
+constexpr int kBandThreads = 256;
+__global__ void __launch_bounds__(kBandThreads)
+colsum_band_kernel(const float *__restrict__ x, int M, int N, int rows_per_cta, float *__restrict__ partial) {
+  extern __shared__ float4 sh4[];                       // [row groups][N / 4]
+  const int cg = N / 4, rg = kBandThreads / cg;         // column groups, row groups (N <= 1024, N / 4 divides 256)
+  const int c = threadIdx.x % cg, r0 = threadIdx.x / cg;
+  const int begin = blockIdx.x * rows_per_cta, end = min(M, begin + rows_per_cta);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), t = s;
+  int r = begin + r0;
+  for (; r + rg < end; r += 2 * rg) {                   // two independent loads in flight
+    const float4 a = ldg4(x + (size_t)r * N + c * 4), b = ldg4(x + (size_t)(r + rg) * N + c * 4);
+    s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+  }
+  if (r < end) {
+    const float4 a = ldg4(x + (size_t)r * N + c * 4);
+    s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+  }
+  sh4[r0 * cg + c] = make_float4(s.x + t.x, s.y + t.y, s.z + t.z, s.w + t.w);
+  __syncthreads();
+  if (r0 == 0) {
+    float4 a = sh4[c];
+    for (int g = 1; g < rg; ++g) {
+      const float4 b = sh4[g * cg + c];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4 *>(partial + (size_t)blockIdx.x * N + c * 4) = a;
+  }
+}
+}  // namespace
+}  // namespace mmrec
+
+extern "C" size_t mmrec_colsum_workspace_bytes(int32_t M, int32_t N) {
+  // tall matrices with a width whose float4 groups tile a 256-thread CTA take the two-stage path
+  if (M < 16384 || N % 4 != 0 || N > 1024 || 256 % (N / 4) != 0) return 0;
+  return (size_t)4 * kNumSMs * N * sizeof(float);
+}
+
 extern "C" int mmrec_colsum_f32(const float *x, int32_t M, int32_t N, float *out, void *stream_) {
+  return mmrec_colsum_ws_f32(x, M, N, out, nullptr, stream_);
+}
+
+extern "C" int mmrec_colsum_ws_f32(const float *x, int32_t M, int32_t N, float *out, float *workspace, void *stream_) {
   MMREC_REQUIRE(x && out, MMREC_E_BADARG, "colsum: null pointer");
   MMREC_REQUIRE(M > 0 && N > 0 && N % 4 == 0, MMREC_E_BADARG, "colsum: need M > 0 and N %% 4 == 0");
-  MMREC_REQUIRE(aligned16(x) && aligned16(out), MMREC_E_ALIGN, "colsum: operands must be 16-byte aligned");
+  MMREC_REQUIRE(aligned16(x) && aligned16(out) && aligned16(workspace), MMREC_E_ALIGN,
+                "colsum: operands must be 16-byte aligned");
+  if (workspace != nullptr && mmrec_colsum_workspace_bytes(M, N) > 0) {
+    const int ctas = 4 * kNumSMs, rows_per_cta = (M + ctas - 1) / ctas;
+    const int used = (M + rows_per_cta - 1) / rows_per_cta;
+    colsum_band_kernel<<<used, kBandThreads, (size_t)kBandThreads * sizeof(float4), (cudaStream_t)stream_>>>(
+        x, M, N, rows_per_cta, workspace);
+    MMREC_CHECK_LAUNCH("colsum_band_kernel");
+    colsum4_kernel<<<N / 4, 1024, 0, (cudaStream_t)stream_>>>(workspace, used, N, out);
+    MMREC_CHECK_LAUNCH("colsum4_kernel");
+    return MMREC_OK;
+  }
   colsum4_kernel<<<N / 4, 1024, 0, (cudaStream_t)stream_>>>(x, M, N, out);
   MMREC_CHECK_LAUNCH("colsum4_kernel");
   return MMREC_OK;

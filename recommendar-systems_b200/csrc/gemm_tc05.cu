@@ -64,6 +64,9 @@ struct GemmArgs {
   double *sumsq_partial;            // optional: per-CTA sum of the updated parameters' squares
   int debug;                        // MMREC_TA_DEBUG (timing experiments only): 1 = no arithmetic, 2 = no copies
   int act;                          // EPI_STORE, no split-K: 0 = none, 1 = tanh, 2 = sigmoid after the bias
+  int mt_per_cta;                   // consecutive 128-row tiles walked by one CTA (0 / 1: one). With more row tiles
+                                    // than SMs a CTA keeps its pipeline full across tiles instead of paying the
+                                    // fill (TMEM allocation, first DRAM round trips, drain) once per 64 KB of rows
 };
 
 // Byte offset of element chunk inside one operand tile (extent E along M/N, 32 along K).
@@ -145,13 +148,16 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
   // warp index through a broadcast: provably warp-uniform, so role branches and the MMA issue
   // loop (descriptor arithmetic included) compile to the uniform datapath
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int m0 = blockIdx.x * kBM;
+  const int mt_per = g.mt_per_cta > 1 ? g.mt_per_cta : 1;
+  const int m_tiles_total = (g.M + kBM - 1) / kBM;
+  const int n_mt = max(0, min(mt_per, m_tiles_total - (int)blockIdx.x * mt_per));
+  const int m0 = blockIdx.x * mt_per * kBM;        // first row tile of this CTA; tile j starts at m0 + (j / n_nt) * kBM
   const int n_kb_total = (g.K + kKB - 1) / kKB;
   const int kb_begin = blockIdx.y * g.kb_per_split, kb_end = min(n_kb_total, kb_begin + g.kb_per_split);
   const int n_nt_total = (g.N + NT - 1) / NT;
   const int nt_begin = blockIdx.z * g.nt_per_cta, nt_end = min(n_nt_total, nt_begin + g.nt_per_cta);
   const int n_kb = max(0, kb_end - kb_begin), n_nt = max(0, nt_end - nt_begin);
-  const int n_iter = n_kb * n_nt;
+  const int n_iter = n_kb * n_nt * n_mt;
   const int n_ck = (n_kb + kChunkKB - 1) / kChunkKB;   // accumulator chunks per N tile
   const uint32_t smem_base = smem_u32(smem);
 
@@ -174,9 +180,10 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
     Block<kBM, A_MN, C::GROUP_THREADS> a;
     Block<NT, B_MN, C::GROUP_THREADS> b;
     for (int it = grp; it < n_iter; it += C::GROUPS) {
-      const int nt = nt_begin + it / n_kb, kb = kb_begin + it % n_kb;
+      const int tile = it / n_kb, kb = kb_begin + it % n_kb;
+      const int nt = nt_begin + tile % n_nt, m0t = m0 + (tile / n_nt) * kBM;
       const int k_lim = min(g.K, kb_end * kKB);
-      a.load(g.A, g.lda, m0, g.M, kb * kKB, k_lim, ptid);
+      a.load(g.A, g.lda, m0t, g.M, kb * kKB, k_lim, ptid);
       b.load(g.B, g.ldb, nt * NT, g.N, kb * kKB, k_lim, ptid);
       const int s = it % C::STAGES;
       // There are more groups than stages, so a group could reach its wait on empty[s] while that
@@ -242,7 +249,6 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
     // The tensor core truncates its fp32 accumulator after every instruction, a bias that grows with
     // the length of the chain; chains are therefore cut every kChunkKB K blocks (24 instructions) and
     // the chunks are added here in registers with round-to-nearest (fp32-class accuracy at K = 20k+).
-    const int m = m0 + warp * 32 + lane;
     float *Cs = g.C + (size_t)blockIdx.y * g.slab;
     // EPI_ADAM: bias-corrected step size and sqrt(bias_correction2) exactly as adam_kernel (optim.cu)
     float step_size = 0.f, bc2_sqrt = 1.f, p2_acc = 0.f;
@@ -260,18 +266,18 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
     constexpr int NBUF = 64 / NT >= 2 ? 2 : 1;           // tile buffers per warp (same shared memory either way)
     constexpr uint32_t TILE_BYTES = 3u * NBOX * 4096u;
     uint8_t *tiles0 = nullptr;
-    const int n_tiles = n_kb > 0 ? n_nt : 0;
+    const int n_tiles = n_kb > 0 ? n_nt * n_mt : 0;
     // tile jj of this warp -> its buffer jj % NBUF (issued by lane 0)
     auto issue_loads = [&](int jj) {
       uint8_t *t = tiles0 + (jj % NBUF) * TILE_BYTES;
       uint64_t *bar = pbar + warp * NBUF + jj % NBUF;
-      const int nn = (nt_begin + jj) * NT;
+      const int nn = (nt_begin + jj % n_nt) * NT, mm = m0 + (jj / n_nt) * kBM + warp * 32;
       mbar_arrive_expect_tx(bar, TILE_BYTES);
 #pragma unroll
       for (int b = 0; b < NBOX; ++b) {
-        tma_load_2d(t + (0 * NBOX + b) * 4096, &maps.a, nn + 32 * b, m0 + warp * 32, bar);
-        tma_load_2d(t + (1 * NBOX + b) * 4096, &maps.b, nn + 32 * b, m0 + warp * 32, bar);
-        tma_load_2d(t + (2 * NBOX + b) * 4096, &maps.c, nn + 32 * b, m0 + warp * 32, bar);
+        tma_load_2d(t + (0 * NBOX + b) * 4096, &maps.a, nn + 32 * b, mm, bar);
+        tma_load_2d(t + (1 * NBOX + b) * 4096, &maps.b, nn + 32 * b, mm, bar);
+        tma_load_2d(t + (2 * NBOX + b) * 4096, &maps.c, nn + 32 * b, mm, bar);
       }
     };
     if constexpr (EPI == EPI_ADAM) {
@@ -283,9 +289,10 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
         if (n_tiles > 0 && g.debug != 2) issue_loads(0);
       }
     }
-    const int rows_valid = min(32, g.M - (m0 + warp * 32));
     for (int j = 0; j < n_tiles; ++j) {
-      const int n0 = (nt_begin + j) * NT;
+      const int n0 = (nt_begin + j % n_nt) * NT, m0j = m0 + (j / n_nt) * kBM;
+      const int m = m0j + warp * 32 + lane;
+      const int rows_valid = min(32, g.M - (m0j + warp * 32));
       if constexpr (EPI == EPI_ADAM) {
         // two buffers: the loads of tile j + 1 go out before tile j is touched (its buffer was last
         // read by the stores of tile j - 1); one buffer: tile j is fetched once tile j - 1 has left
@@ -361,9 +368,9 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
         if (lane == 0 && g.debug != 2) {
 #pragma unroll
           for (int b = 0; b < NBOX; ++b) {
-            tma_store_2d(&maps.a, n0 + 32 * b, m0 + warp * 32, tiles + (0 * NBOX + b) * 4096);
-            tma_store_2d(&maps.b, n0 + 32 * b, m0 + warp * 32, tiles + (1 * NBOX + b) * 4096);
-            tma_store_2d(&maps.c, n0 + 32 * b, m0 + warp * 32, tiles + (2 * NBOX + b) * 4096);
+            tma_store_2d(&maps.a, n0 + 32 * b, m0j + warp * 32, tiles + (0 * NBOX + b) * 4096);
+            tma_store_2d(&maps.b, n0 + 32 * b, m0j + warp * 32, tiles + (1 * NBOX + b) * 4096);
+            tma_store_2d(&maps.c, n0 + 32 * b, m0j + warp * 32, tiles + (2 * NBOX + b) * 4096);
           }
           bulk_commit();
         }
@@ -385,7 +392,7 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
         // rows: one STG.128 per NT/4 lanes, 512 contiguous bytes per instruction.
         constexpr int P = NT + 4, LPR = NT / 4, RPI = 32 / LPR;      // pitch, lanes per row, rows per instr
         float *tr = stg + warp * (32 * P);
-        const int mw = m0 + warp * 32;
+        const int mw = m0j + warp * 32;
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < NT; q += 4)
@@ -454,7 +461,8 @@ int launch_tc05(const GemmArgs &g, int k_splits, int n_chunks, cudaStream_t stre
     MMREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  dim3 grid((g.M + kBM - 1) / kBM, k_splits, n_chunks);
+  const int m_tiles = (g.M + kBM - 1) / kBM, mt_per = g.mt_per_cta > 1 ? g.mt_per_cta : 1;
+  dim3 grid((m_tiles + mt_per - 1) / mt_per, k_splits, n_chunks);
   kern<<<grid, kThreadsG, smem, stream>>>(g, TmaMaps3{});
   MMREC_CHECK_LAUNCH("gemm_tc05_kernel");
   return MMREC_OK;
@@ -548,8 +556,13 @@ int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcon
   float *out = splits > 1 ? ws : C;
   g.bias = splits > 1 ? nullptr : bias;
   g.slab = (size_t)M * N;
+  // more row tiles than SMs (and nothing else to parallelise over): consecutive tiles per CTA
+  auto tiles_per_cta = [](int m_tiles, int other) {
+    return other == 1 && m_tiles > kNumSMs ? (m_tiles + kNumSMs - 1) / kNumSMs : 1;
+  };
   if (kind == 1) {
     g.A = A; g.lda = K; g.B = B; g.ldb = K; g.C = out; g.ldc = N; g.M = M; g.N = N; g.K = K; g.nt_per_cta = 1;
+    g.mt_per_cta = tiles_per_cta((M + kBM - 1) / kBM, k_splits);
     return launch_tc05_nt<false, false, false>(N, g, k_splits, 1, stream);
   }
   if (kind == 2) {
@@ -570,6 +583,7 @@ int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcon
   int chunks = best_parts(m_tiles, n_tiles, n_tiles, 1);
   g.nt_per_cta = (n_tiles + chunks - 1) / chunks;
   chunks = (n_tiles + g.nt_per_cta - 1) / g.nt_per_cta;
+  g.mt_per_cta = tiles_per_cta(m_tiles, chunks);
   if (nt == 64) return launch_tc05<false, true, 64, false>(g, 1, chunks, stream);
   return launch_tc05<false, true, 128, false>(g, 1, chunks, stream);
 }

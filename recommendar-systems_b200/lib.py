@@ -84,6 +84,8 @@ SIGNATURES = {
     "mmrec_loss_head_fwd_f32": (C.c_int, [_p, _p, _f32, _f32, _f32, _f32, _p, _p]),
     "mmrec_loss_head_bwd_f32": (C.c_int, [_p, _f32, _f32, _f32, _f32, _p, _p, _p]),
     "mmrec_colsum_f32": (C.c_int, [_p, _i32, _i32, _p, _p]),
+    "mmrec_colsum_workspace_bytes": (_sz, [_i32, _i32]),
+    "mmrec_colsum_ws_f32": (C.c_int, [_p, _i32, _i32, _p, _p, _p]),
     "mmrec_row_normalize_f32": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "mmrec_row_topk_f32": (C.c_int, [_p, _i32, _i32, _i64, _i32, _p, _p, _p]),
     "mmrec_knn_weights_f32": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),

@@ -586,7 +586,9 @@ def colsum(x):
     lib.require_cuda(x)
     x = _f32c(x)
     out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
-    lib.call("mmrec_colsum_f32", lib.ptr(x), x.shape[0], x.shape[1], lib.ptr(out), lib.stream())
+    nb = lib.load().mmrec_colsum_workspace_bytes(x.shape[0], x.shape[1])
+    ws = torch.empty(nb // 4, dtype=torch.float32, device=x.device) if nb else None
+    lib.call("mmrec_colsum_ws_f32", lib.ptr(x), x.shape[0], x.shape[1], lib.ptr(out), lib.ptr(ws), lib.stream())
     return out
 
 

@@ -772,7 +772,8 @@ def test_row_topk_ties_and_short_rows():
 
 # ------------------------------------------------------------------ small fused training-path ops
 @pytest.mark.gpu
-@pytest.mark.parametrize("M,N", [(7050, 64), (1, 4), (1025, 128), (4097, 32)])
+@pytest.mark.parametrize("M,N", [(7050, 64), (1, 4), (1025, 128), (4097, 32), (62420, 128), (26495, 64), (16384, 256),
+                                 (20001, 36)])
 def test_colsum_matches_torch(M, N):
     ops = pkg("ops")
     x = torch.randn(M, N, generator=torch.Generator().manual_seed(41)).to(DEV)
