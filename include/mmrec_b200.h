@@ -450,6 +450,25 @@ int mmrec_knn_weights_f32(const int32_t *idx, const float *val, int32_t n, int32
                           float *out_vals, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Row part of SMORE's modality-aware preference module (models/smore.py:321-341) for widths whose
+ * d x d layers run as separate tensor-core launches (d = 128): everything after the seven Linear
+ * layers in one launch each way. zv / zt = query_v / query_t outputs (pre-softmax), gi / gt / gf =
+ * sigmoid outputs of the three gate_*_prefer layers, masks = [3, n, d] nn.Dropout multipliers or
+ * NULL:
+ *   side = (gi m_i softmax(zv) V + gt m_t softmax(zt) T + gf m_f F) / 3,  all = C + side.
+ * The backward recomputes the softmax; g_all / g_side may be NULL (not both). d in {32, 64, 128}.
+ * ---------------------------------------------------------------------------------------- */
+int mmrec_smore_combine_supported(int32_t d);
+int mmrec_smore_combine_fwd_f32(const float *zv, const float *zt, const float *V, const float *T, const float *F,
+                                const float *C, const float *gi, const float *gt, const float *gf,
+                                const float *masks, int32_t n, int32_t d, float *side, float *all, void *stream);
+int mmrec_smore_combine_bwd_f32(const float *g_all, const float *g_side, const float *zv, const float *zt,
+                                const float *V, const float *T, const float *F, const float *gi, const float *gt,
+                                const float *gf, const float *masks, int32_t n, int32_t d, float *dzv, float *dzt,
+                                float *dV, float *dT, float *dF, float *dC, float *dgi, float *dgt, float *dgf,
+                                void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * MGCN's two-way attention fuser (models/mgcn.py:188-205), one launch each way. Replaces
  *   att = softmax(cat([query_common(image_embeds), query_common(text_embeds)], -1))   (the
  *         Linear(d, 1) of query_common is the row dot with w2 = query_common.2.weight [1, d])

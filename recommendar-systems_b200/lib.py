@@ -63,6 +63,9 @@ SIGNATURES = {
     "mmrec_smore_side_fwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "mmrec_smore_side_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                            _p, _i32, _i32, _p]),
+    "mmrec_smore_combine_supported": (C.c_int, [_i32]),
+    "mmrec_smore_combine_fwd_f32": (C.c_int, [_p] * 10 + [_i32, _i32, _p, _p, _p]),
+    "mmrec_smore_combine_bwd_f32": (C.c_int, [_p] * 11 + [_i32, _i32] + [_p] * 10),
     "mmrec_mgcn_fuse_supported": (C.c_int, [_i32]),
     "mmrec_mgcn_fuse_bwd_blocks": (_i32, [_i32, _i32]),
     "mmrec_mgcn_fuse_fwd_f32": (C.c_int, [_p] * 8 + [_i32, _i32, _p, _p, _p, _p]),

@@ -637,6 +637,19 @@ class SMORE(_MultiViewBase):
                       self.gate_image_prefer[0], self.gate_text_prefer[0], self.gate_fusion_prefer[0])
             all_e, side = ops.smore_side(fusion_embeds, image_embeds, text_embeds, content, layers, masks)
             return all_e, side, content
+        if ops.smore_combine_supported(self.embedding_dim):
+            # wide embeddings (d = 128): the seven Linear layers as tensor-core launches, everything
+            # after them (two softmaxes, dropout, products, mean of three, + content) in one kernel
+            zv, zt = self.query_v(fusion_embeds), self.query_t(fusion_embeds)
+            gi, gt, gf = ops.dense_stack_batch(
+                (self.gate_image_prefer, self.gate_text_prefer, self.gate_fusion_prefer), (content, content, content))
+            masks = None
+            if self.training and self.dropout_rate > 0:
+                masks = torch.nn.functional.dropout(
+                    torch.ones(3, *content.shape, dtype=content.dtype, device=content.device),
+                    p=self.dropout_rate, training=True)
+            all_e, side = ops.smore_combine(zv, zt, image_embeds, text_embeds, fusion_embeds, content, gi, gt, gf, masks)
+            return all_e, side, content
         agg_image = self.softmax(self.query_v(fusion_embeds)) * image_embeds
         agg_text = self.softmax(self.query_t(fusion_embeds)) * text_embeds
         pi, pt, pf = ops.dense_stack_batch(

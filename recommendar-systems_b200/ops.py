@@ -957,6 +957,50 @@ def smore_side(fusion, image, text, content, layers, masks=None):
     return _SmoreSide.apply(fusion, image, text, content, masks, *wb)
 
 
+# ------------------------------------------- SMORE preference module, row part (wide embeddings)
+class _SmoreCombine(torch.autograd.Function):
+    """smore.py:321-341 after the seven Linear layers: apply(zv, zt, V, T, F, C, gi, gt, gf, masks)
+    -> (content + side, side); see mmrec_smore_combine_*_f32."""
+
+    @staticmethod
+    def forward(ctx, zv, zt, V, T, F, C_, gi, gt, gf, masks):
+        zv, zt, V, T, F, C_, gi, gt, gf = (_f32c(t) for t in (zv, zt, V, T, F, C_, gi, gt, gf))
+        masks = None if masks is None else _f32c(masks)
+        n, d = F.shape
+        side, all_e = torch.empty_like(F), torch.empty_like(F)
+        lib.call("mmrec_smore_combine_fwd_f32", lib.ptr(zv), lib.ptr(zt), lib.ptr(V), lib.ptr(T), lib.ptr(F), lib.ptr(C_),
+                 lib.ptr(gi), lib.ptr(gt), lib.ptr(gf), lib.ptr(masks), n, d, lib.ptr(side), lib.ptr(all_e), lib.stream())
+        ctx.has_mask = masks is not None
+        ctx.save_for_backward(zv, zt, V, T, F, gi, gt, gf, *([masks] if masks is not None else []))
+        return all_e, side
+
+    @staticmethod
+    def backward(ctx, g_all, g_side):
+        t = ctx.saved_tensors
+        zv, zt, V, T, F, gi, gt, gf = t[:8]
+        masks = t[8] if ctx.has_mask else None
+        n, d = F.shape
+        g_all = None if g_all is None else _f32c(g_all)
+        g_side = None if g_side is None else _f32c(g_side)
+        outs = [torch.empty_like(F) for _ in range(9)]          # dzv dzt dV dT dF dC dgi dgt dgf
+        lib.call("mmrec_smore_combine_bwd_f32", lib.ptr(g_all), lib.ptr(g_side), lib.ptr(zv), lib.ptr(zt), lib.ptr(V),
+                 lib.ptr(T), lib.ptr(F), lib.ptr(gi), lib.ptr(gt), lib.ptr(gf), lib.ptr(masks), n, d,
+                 *[lib.ptr(o) for o in outs], lib.stream())
+        dzv, dzt, dV, dT, dF, dC, dgi, dgt, dgf = outs
+        return dzv, dzt, dV, dT, dF, dC, dgi, dgt, dgf, None
+
+
+def smore_combine_supported(d):
+    return bool(lib.load().mmrec_smore_combine_supported(int(d)))
+
+
+def smore_combine(zv, zt, image, text, fusion, content, gi, gt, gf, masks=None):
+    """Row part of SMORE's preference module: (content + side, side) from the pre-softmax query
+    outputs, the three views, the content embeddings and the three sigmoid gates (+ dropout masks)."""
+    lib.require_cuda(zv, zt, image, text, fusion, content, gi, gt, gf)
+    return _SmoreCombine.apply(zv, zt, image, text, fusion, content, gi, gt, gf, masks)
+
+
 # ------------------------------------------------------------------- MGCN attention fuser (fused)
 class _MgcnFuse(torch.autograd.Function):
     """mgcn.py:188-205 after the d x d layers: apply(Hi, Ht, w2, Ei, Et, Pi, Pt, C) -> (all, side)."""

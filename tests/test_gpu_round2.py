@@ -331,3 +331,32 @@ def test_device_negative_sampler_matches_numpy_restatement_and_rule():
     dl2 = data_m.DeviceTrainLoader(hist_u, hist_i, 1, I, batch_size=64, seed=1, max_draws=4096)
     neg2 = dl2.sample_negatives(torch.zeros(64, dtype=torch.int64, device=DEV), 0)
     assert bool(((neg2 == I - 1) | (neg2 == -1)).all()) and int((neg2 == I - 1).sum()) > 0
+
+
+# ------------------------------------------------------------------ a10 at d = 128: row part of the preference module
+@pytest.mark.parametrize("n,d,drop", [(62420, 128, 0.1), (1, 128, 0.0), (777, 64, 0.2), (300, 32, 0.0)])
+def test_smore_combine_forward_backward(n, d, drop):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(n + d)
+    names = ("zv", "zt", "V", "T", "F", "C", "gi", "gt", "gf")
+    t = {k: torch.randn(n, d, generator=gen) for k in names}
+    for k in ("gi", "gt", "gf"):
+        t[k] = torch.sigmoid(t[k])
+    masks = None
+    if drop > 0:
+        masks = (torch.rand(3, n, d, generator=gen) >= drop).float() / (1 - drop)
+    ga, gs = torch.randn(n, d, generator=gen), torch.randn(n, d, generator=gen)
+    x = {k: v.double().requires_grad_(True) for k, v in t.items()}
+    m = masks.double() if masks is not None else torch.ones(3, n, d, dtype=torch.float64)
+    agg_i = torch.softmax(x["zv"], dim=-1) * x["V"]                                  # smore.py:324-325
+    agg_t = torch.softmax(x["zt"], dim=-1) * x["T"]
+    side_r = torch.mean(torch.stack([x["gi"] * m[0] * agg_i, x["gt"] * m[1] * agg_t, x["gf"] * m[2] * x["F"]]), dim=0)
+    all_r = x["C"] + side_r                                                            # smore.py:335-341
+    ((all_r * ga.double()).sum() + (side_r * gs.double()).sum()).backward()
+    y = {k: v.to(DEV).requires_grad_(True) for k, v in t.items()}
+    all_e, side = ops.smore_combine(y["zv"], y["zt"], y["V"], y["T"], y["F"], y["C"], y["gi"], y["gt"], y["gf"],
+                                    None if masks is None else masks.to(DEV))
+    ((all_e * ga.to(DEV)).sum() + (side * gs.to(DEV)).sum()).backward()
+    assert rel(all_e, all_r) < 1e-6 and rel(side, side_r) < 1e-6
+    for k in names:
+        assert rel(y[k].grad, x[k].grad) < 5e-6, k
