@@ -35,7 +35,36 @@ img = torch.randn(I, d, device=DEV, requires_grad=True)
 txt = torch.randn(I, d, device=DEV, requires_grad=True)
 wsp = [torch.randn(d // 2 + 1, 2, device=DEV, requires_grad=True) for _ in range(3)]
 gsp = [torch.randn(I, d, device=DEV) for _ in range(3)]
+# round 2: low-rank table Adam (TMA-streamed), its norm pass, MGCN fuser, wide-d preference module, a graph
+# whose embedding table (184 MB) does not fit L2
+optim, par = bench.pkg("optim"), bench.pkg("parallel")
+table = torch.nn.Parameter(x.clone())
+opt = optim.FusedAdam([table], lr=1e-3)
+g2 = torch.zeros(1, dtype=torch.float64, device=DEV)
+mg = [torch.randn(N, d, device=DEV, requires_grad=True) for _ in range(8)]
+w2 = torch.randn(1, d, device=DEV, requires_grad=True)
+Nw, dw = 62420, 128
+cw = [torch.randn(Nw, dw, device=DEV, requires_grad=True) for _ in range(9)]
+xw = torch.randn(Nw, dw, device=DEV, requires_grad=True)
+Ww, bw = (torch.randn(dw, dw, device=DEV) * 0.1).requires_grad_(True), torch.randn(dw, device=DEV, requires_grad=True)
+su, si = synth.make_scaled_edges(DEV, 600_000, 120_000, 30_000_000)
+big = G.build_ui_graph(su, si, 600_000, 120_000, "f64eps")
+Xb = torch.randn(big.n_cols, d, device=DEV)
+Yb = torch.empty(big.n_rows, d, device=DEV)
+sbb = par.ShardedBipartite.from_local_edges(su, si, [0, 600_000], 0, 1, 600_000, 120_000, "f64eps", rt_block_users=196608)
+yi = torch.empty(120_000, d, device=DEV)
 for rep in range(2):
+    table._mmrec_lowrank = ops.LowRankGrad(dy, W)
+    optim.lowrank_sumsq(table, g2)
+    opt.step()
+    table._mmrec_lowrank = None
+    a, s = ops.mgcn_fuse(mg[0], mg[1], w2, mg[2], mg[3], mg[4], mg[5], mg[6])
+    (a.sum() + s.sum()).backward()
+    a, s = ops.smore_combine(*cw)
+    (a.sum() + s.sum()).backward()
+    ops.dense_act(xw, Ww, bw, "sigmoid").sum().backward()
+    ops.spmm_raw(big, Xb, Y=Yb)
+    ops.spmm_blocked_raw(sbb.Rt_blocked, Xb[:600_000], yi)
     torch.autograd.backward(ops.spectrum_convolution(img, txt, *wsp, True), gsp)
     ops.gemm(x, True, W, True, I, d, F, b)
     ops.gemm(dy, False, x, False, d, F, I)
