@@ -4,7 +4,10 @@
 // loads, the two dots, -logsigmoid and the L2 term are formed in registers; per-sample results go
 // to a small buffer and the last CTA to finish reduces it in a fixed order (deterministic scalar).
 // Backward: sigma(-x) saved by the forward scales the rows, gradients are scatter-added with
-// vector atomics (red.global.add.v4.f32) because users/items repeat inside a batch.
+// vector atomics (red.global.add.v4.f32) because users/items repeat inside a batch: the order of
+// those float additions is not fixed, so rows that repeat in a batch are reproducible to rounding
+// (~1e-7), not bit for bit, from run to run -- unlike the SpMM / dense / optimizer kernels, which
+// use no floating-point atomics. The ids are trusted (see ops.CHECK_IDS for the checked mode).
 //
 // InfoNCE: rows are gathered + L2-normalised once, then a 64x64-tile kernel streams V1 V2^T
 // through shared memory (tile products on the tensor cores: mma.sync, 3xTF32 split = fp32-class

@@ -21,6 +21,20 @@ def _counter(device):
     return _counters[key]
 
 
+# Index range checks (a host sync per call): off in production, on with MMREC_CHECK_IDS=1. The
+# gather / scatter kernels trust their int64 ids the way a raw CUDA kernel does -- where torch
+# indexing would raise IndexError they would read or `red.add` out of bounds -- and
+# compute-sanitizer is not available on the GPU pool, so this is the memcheck of the id arguments.
+CHECK_IDS = __import__("os").environ.get("MMREC_CHECK_IDS", "0") == "1"
+
+
+def _check_ids(idx, n, what):
+    if CHECK_IDS and idx is not None and idx.numel():
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo < 0 or hi >= n:
+            raise IndexError(f"{what}: index range [{lo}, {hi}] outside [0, {n})")
+
+
 def _f32c(t):
     if t.dtype != torch.float32:
         raise RuntimeError(f"expected float32, got {t.dtype}")
@@ -310,6 +324,9 @@ def layergcn_propagate(g: CSRGraph, X0, n_layers):
 # ----------------------------------------------------------------------------------------- BPR
 def _bpr_fwd(ue, ie, users, pos, neg):
     B, d = users.numel(), ue.shape[1]
+    _check_ids(users, ue.shape[0], "bpr users")
+    _check_ids(pos, ie.shape[0], "bpr positive items")
+    _check_ids(neg, ie.shape[0], "bpr negative items")
     out = torch.empty(2, dtype=torch.float32, device=ue.device)
     sig = torch.empty(B, dtype=torch.float32, device=ue.device)
     partial = torch.empty(2 * B, dtype=torch.float32, device=ue.device)
@@ -379,6 +396,8 @@ class _InfoNCEPair(torch.autograd.Function):
     @staticmethod
     def forward(ctx, side, content, n_users, users, pos_items, temperature, reduce=True):
         side, content = _f32c(side), _f32c(content)
+        _check_ids(users, n_users, "infonce users")
+        _check_ids(pos_items, side.shape[0] - n_users, "infonce items")
         dev, d = side.device, side.shape[1]
         inv_t = 1.0 / temperature
         saved = []
@@ -1115,6 +1134,7 @@ def score_mask_topk(user_emb, users, item_emb, k, mask_rowptr=None, mask_cols=No
     user_emb, item_emb = _f32c(user_emb), _f32c(item_emb)
     lib.require_cuda(user_emb, item_emb, users)
     n, n_items, d = users.numel(), item_emb.shape[0], item_emb.shape[1]
+    _check_ids(users, user_emb.shape[0], "score_mask_topk users")
     dev = user_emb.device
     S = n_splits or choose_splits(n, n_items)
     ws_val = torch.empty(S, n, k, dtype=torch.float32, device=dev)

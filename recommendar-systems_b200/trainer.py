@@ -409,6 +409,7 @@ class Trainer:
         self.model.train()
         loss_func = loss_func or self.model.calculate_loss
         total_loss = None
+        first_nan = None
         loss_batches = []
         graphed = self.use_cuda_graph and loss_func == self.model.calculate_loss
         it = iter(train_data)
@@ -428,6 +429,11 @@ class Trainer:
             loss_batches.append(loss)
             if self.sync_free:
                 total_loss = loss.clone() if total_loss is None else total_loss + loss
+                # index of the first NaN batch, kept on the device (read once, at the end of the epoch)
+                bad = torch.isnan(loss).reshape(())
+                here = torch.full((), batch_idx - 1, dtype=torch.int64, device=loss.device)
+                first_nan = torch.where(bad, here, torch.full_like(here, -1)) if first_nan is None else \
+                    torch.where((first_nan < 0) & bad, here, first_nan)
                 continue
             # per-batch read-back (trainer.py:196-203), one step behind: the loss of batch i is
             # read after batch i + 1 has been enqueued, so the device never waits for the host.
@@ -442,7 +448,10 @@ class Trainer:
                     return lt, torch.tensor(0.0)
         if self.sync_free and total_loss is not None:
             if torch.isnan(total_loss):
-                self.logger.info("Loss is nan at epoch: {}. Exiting.".format(epoch_idx))
+                # trainer.py:201-203 reports the batch and returns before its backward; here the batch
+                # index is exact but the remaining batches of the epoch have already been applied
+                self.logger.info("Loss is nan at epoch: {}, batch index: {}. Exiting.".format(
+                    epoch_idx, int(first_nan.item()) if first_nan is not None else -1))
                 return total_loss, torch.tensor(0.0)
             total_loss = total_loss.item()
         return total_loss, loss_batches

@@ -360,3 +360,19 @@ def test_smore_combine_forward_backward(n, d, drop):
     assert rel(all_e, all_r) < 1e-6 and rel(side, side_r) < 1e-6
     for k in names:
         assert rel(y[k].grad, x[k].grad) < 5e-6, k
+
+
+def test_id_range_checks_catch_out_of_bounds_indices(monkeypatch):
+    """MMREC_CHECK_IDS: the gather / scatter entry points validate their ids (the stand-in for
+    compute-sanitizer's memcheck on the id arguments)."""
+    ops = pkg("ops")
+    monkeypatch.setattr(ops, "CHECK_IDS", True)
+    emb = torch.randn(50, 64, device=DEV, requires_grad=True)
+    ok = torch.tensor([0, 9], device=DEV)
+    ops.bpr_table(emb, 10, ok, ok, ok)
+    with pytest.raises(IndexError):
+        ops.bpr_table(emb, 10, torch.tensor([0, 10], device=DEV), ok, ok)          # user id == n_users
+    with pytest.raises(IndexError):
+        ops.bpr_table(emb, 10, ok, torch.tensor([0, 40], device=DEV), ok)          # item id == n_items
+    with pytest.raises(IndexError):
+        ops.score_mask_topk(emb[:10].detach(), torch.tensor([-1], device=DEV), emb[10:].detach(), 5)
