@@ -299,8 +299,31 @@ int mmrec_dense_act_batch_bwd_f32(const float *const *dY_host, const float *cons
  * Tile products on mma.sync tensor cores with the 3xTF32 split (fp32-class accuracy); gradients are
  * bit-reproducible (partials added in a fixed order).
  * ---------------------------------------------------------------------------------------- */
+/* In-kernel nn.Dropout (smore.py:331-333) for the *_drop_* entry points: no mask tensor exists.
+ * The multiplier of element (plane g of 3, row, column) is 0 or 1/(1-p), a pure function of
+ * (seed, *counter, g, row, column): forward and backward regenerate the same mask, and a step
+ * captured in a CUDA graph draws fresh masks on every replay because `counter` is read on the
+ * device (FusedAdam's update count; NULL = 0). p is applied in steps of 2^-16.
+ * mmrec_dropout_mask_f32 materialises the multipliers a *_drop_* call uses (tests, diagnostics);
+ * oracle/dropout.py restates the generator in numpy. */
+typedef struct MmrecDropout {
+  float p;                /* drop probability in [0, 1) */
+  uint64_t seed;          /* host constant of this call site / call */
+  const double *counter;  /* device pointer to one double holding an integer count, or NULL */
+} MmrecDropout;
+int mmrec_dropout_mask_f32(float *out, int32_t planes, int32_t n, int32_t d, const MmrecDropout *drop, void *stream);
+
 int mmrec_smore_side_supported(int32_t d);
 size_t mmrec_smore_side_bwd_workspace_bytes(int32_t n, int32_t d);
+int mmrec_smore_side_fwd_drop_f32(const float *F, const float *V, const float *T, const float *C,
+                                  const float *const *W_host, const float *const *b_host,
+                                  const MmrecDropout *drop, float *saved, float *side, float *all, int32_t n,
+                                  int32_t d, void *stream);
+int mmrec_smore_side_bwd_drop_f32(const float *d_all, const float *d_side, const float *F, const float *V,
+                                  const float *T, const float *C, const float *const *W_host,
+                                  const float *const *b_host, const MmrecDropout *drop, const float *saved,
+                                  float *dF, float *dV, float *dT, float *dC, float *const *dW_host,
+                                  float *const *db_host, float *ws, int32_t n, int32_t d, void *stream);
 int mmrec_smore_side_fwd_f32(const float *F, const float *V, const float *T, const float *C,
                              const float *const *W_host, const float *const *b_host,
                              const float *masks, float *saved, float *side, float *all, int32_t n,
@@ -459,6 +482,16 @@ int mmrec_knn_weights_f32(const int32_t *idx, const float *val, int32_t n, int32
  * The backward recomputes the softmax; g_all / g_side may be NULL (not both). d in {32, 64, 128}.
  * ---------------------------------------------------------------------------------------- */
 int mmrec_smore_combine_supported(int32_t d);
+/* the same with the dropout multipliers generated in the kernel (MmrecDropout above) */
+int mmrec_smore_combine_fwd_drop_f32(const float *zv, const float *zt, const float *V, const float *T, const float *F,
+                                     const float *C, const float *gi, const float *gt, const float *gf,
+                                     const MmrecDropout *drop, int32_t n, int32_t d, float *side, float *all,
+                                     void *stream);
+int mmrec_smore_combine_bwd_drop_f32(const float *g_all, const float *g_side, const float *zv, const float *zt,
+                                     const float *V, const float *T, const float *F, const float *gi, const float *gt,
+                                     const float *gf, const MmrecDropout *drop, int32_t n, int32_t d, float *dzv,
+                                     float *dzt, float *dV, float *dT, float *dF, float *dC, float *dgi, float *dgt,
+                                     float *dgf, void *stream);
 int mmrec_smore_combine_fwd_f32(const float *zv, const float *zt, const float *V, const float *T, const float *F,
                                 const float *C, const float *gi, const float *gt, const float *gf,
                                 const float *masks, int32_t n, int32_t d, float *side, float *all, void *stream);

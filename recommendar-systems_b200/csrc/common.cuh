@@ -42,6 +42,36 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- in-kernel dropout (nn.Dropout of smore.py:331-333 without mask tensors) --------------------
+// The multiplier of element (plane, row, 4-column group) is a pure function of a 64-bit stream key
+// and the element index: forward and backward regenerate the same mask, nothing is written to HBM
+// (a [3, n, d] mask costs one fill, one dropout kernel and two 4 n d reads per pass). The stream key
+// mixes a host constant (model seed, call index: baked into a captured graph) with a DEVICE counter
+// (the optimizer's update count), so replays of one captured step draw fresh masks.
+struct DropSpec {
+  const double *counter;  // device: one double holding an integer count (FusedAdam's update count), or NULL
+  uint64_t seed;          // host constant of this call
+  float p;                // drop probability, applied in steps of 2^-16; 0 = no dropout
+};
+__host__ __device__ inline uint64_t drop_mix64(uint64_t z) {       // splitmix64 finaliser
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t drop_stream(const DropSpec &d) {
+  const uint64_t c = d.counter != nullptr ? (uint64_t)d.counter[0] : 0ull;
+  return drop_mix64(d.seed ^ (c * 0xd1342543de82ef95ull));
+}
+// multipliers of the 4 consecutive elements starting at flat index `idx4 * 4` (16 bits each)
+__device__ __forceinline__ float4 drop_mask4(uint64_t stream, uint64_t idx4, float p) {
+  const uint64_t r = drop_mix64(stream + idx4 * 0x2545f4914f6cdd1dull);
+  const uint32_t thr = (uint32_t)(p * 65536.f);
+  const float s = 1.f / (1.f - p);
+  return make_float4(((r) & 0xffffu) >= thr ? s : 0.f, ((r >> 16) & 0xffffu) >= thr ? s : 0.f,
+                     ((r >> 32) & 0xffffu) >= thr ? s : 0.f, ((r >> 48) & 0xffffu) >= thr ? s : 0.f);
+}
+
 __device__ __forceinline__ float4 ldg4(const float *p) {
   return __ldg(reinterpret_cast<const float4 *>(p));
 }

@@ -82,6 +82,15 @@ struct Frag {
       if (m < n) *reinterpret_cast<float4 *>(p + (size_t)m * D + c0) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
     }
   }
+  // dropout multipliers of plane `g` ([3, n, D] layout) for this thread's rows / columns
+  __device__ __forceinline__ void fill_dropout(uint64_t stream, float p, int g, int m0, int n, int rg, int c0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + rg + C::RG * i;
+      const float4 t = drop_mask4(stream, ((uint64_t)g * n + (uint64_t)m) * (D / 4) + c0 / 4, p);
+      v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+    }
+  }
   __device__ __forceinline__ void load_smem(const float *s, int rg, int c0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -170,8 +179,9 @@ __device__ __forceinline__ void softmax_rows(float (&a)[4][4]) {
 template <int D>
 __global__ void __launch_bounds__(kT, D <= 64 ? 2 : 1)
 side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const float *__restrict__ T,
-                const float *__restrict__ C_, SideWeights P, const float *__restrict__ masks,
+                const float *__restrict__ C_, SideWeights P, const float *__restrict__ masks, const DropSpec drop,
                 float *__restrict__ saved, float *__restrict__ side, float *__restrict__ all, int n, int n_tiles) {
+  const uint64_t drop_key = drop.p > 0.f ? drop_stream(drop) : 0ull;
   using C = Cfg<D>;
   extern __shared__ float4 smem4[];
   float *Ws = reinterpret_cast<float *>(smem4);   // [D][PW]  transposed weight
@@ -236,8 +246,9 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc.v[i][j] = 1.f / (1.f + expf(-acc.v[i][j]));
       acc.store(saved + (4 + g) * nd, m0, n, rg, c0);
-      if (masks != nullptr) {
-        x.load(masks + g * nd, m0, n, rg, c0);
+      if (masks != nullptr || drop.p > 0.f) {
+        if (masks != nullptr) x.load(masks + g * nd, m0, n, rg, c0);
+        else x.fill_dropout(drop_key, drop.p, g, m0, n, rg, c0);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -270,9 +281,10 @@ template <int D>
 __global__ void __launch_bounds__(kT, D <= 64 ? 2 : 1)
 side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_side, const float *__restrict__ F,
                 const float *__restrict__ V, const float *__restrict__ T, const float *__restrict__ C_,
-                SideWeights P, const float *__restrict__ masks, const float *__restrict__ saved,
+                SideWeights P, const float *__restrict__ masks, const DropSpec drop, const float *__restrict__ saved,
                 float *__restrict__ dF, float *__restrict__ dV, float *__restrict__ dT, float *__restrict__ dC,
                 float *__restrict__ partial, int n, int n_tiles) {
+  const uint64_t drop_key = drop.p > 0.f ? drop_stream(drop) : 0ull;
   using C = Cfg<D>;
   extern __shared__ float4 smem4[];
   float *Wn = reinterpret_cast<float *>(smem4);   // [D][PW] natural layout (output-major)
@@ -349,6 +361,7 @@ side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_sid
       Frag<D> mk;
       mk.fill(1.f);
       if (masks != nullptr) mk.load(masks + br * nd, m0, n, rg, c0);
+      else if (drop.p > 0.f) mk.fill_dropout(drop_key, drop.p, br, m0, n, rg, c0);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -442,7 +455,8 @@ inline int side_parts(int n, int d) {
 
 template <int D>
 int side_fwd_launch(const float *F, const float *V, const float *T, const float *C_, const SideWeights &P,
-                    const float *masks, float *saved, float *side, float *all, int n, cudaStream_t st) {
+                    const float *masks, const DropSpec &drop, float *saved, float *side, float *all, int n,
+                    cudaStream_t st) {
   constexpr size_t smem = side_fwd_smem<D>();
   static bool attr = false;
   if (!attr) {
@@ -450,15 +464,15 @@ int side_fwd_launch(const float *F, const float *V, const float *T, const float 
     attr = true;
   }
   const int n_tiles = (n + Cfg<D>::BM - 1) / Cfg<D>::BM;
-  side_fwd_kernel<D><<<min(n_tiles, 8 * kNumSMs), kT, smem, st>>>(F, V, T, C_, P, masks, saved, side, all, n, n_tiles);
+  side_fwd_kernel<D><<<min(n_tiles, 8 * kNumSMs), kT, smem, st>>>(F, V, T, C_, P, masks, drop, saved, side, all, n, n_tiles);
   MMREC_CHECK_LAUNCH("side_fwd_kernel");
   return MMREC_OK;
 }
 
 template <int D>
 int side_bwd_launch(const float *d_all, const float *d_side, const float *F, const float *V, const float *T,
-                    const float *C_, const SideWeights &P, const float *masks, const float *saved, float *dF,
-                    float *dV, float *dT, float *dC, const SideGrads &G, float *ws, int n, cudaStream_t st) {
+                    const float *C_, const SideWeights &P, const float *masks, const DropSpec &drop, const float *saved,
+                    float *dF, float *dV, float *dT, float *dC, const SideGrads &G, float *ws, int n, cudaStream_t st) {
   constexpr size_t smem = side_bwd_smem<D>();
   static bool attr = false;
   if (!attr) {
@@ -467,7 +481,7 @@ int side_bwd_launch(const float *d_all, const float *d_side, const float *F, con
   }
   const int n_tiles = (n + Cfg<D>::BM - 1) / Cfg<D>::BM;
   const int parts = side_parts(n, D);
-  side_bwd_kernel<D><<<parts, kT, smem, st>>>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, ws, n,
+  side_bwd_kernel<D><<<parts, kT, smem, st>>>(d_all, d_side, F, V, T, C_, P, masks, drop, saved, dF, dV, dT, dC, ws, n,
                                               n_tiles);
   MMREC_CHECK_LAUNCH("side_bwd_kernel");
   side_partial_reduce_kernel<<<dim3((D * D + D + 63) / 64, kNW), 1024, 0, st>>>(ws, parts, D * D, D, G);
@@ -498,10 +512,17 @@ static int unpack_weights(const float *const *W, const float *const *b, int d, S
   return MMREC_OK;
 }
 
-extern "C" int mmrec_smore_side_fwd_f32(const float *F, const float *V, const float *T, const float *C_,
-                                        const float *const *W_host, const float *const *b_host,
-                                        const float *masks, float *saved, float *side, float *all, int32_t n,
-                                        int32_t d, void *stream) {
+static int unpack_drop(const MmrecDropout *drop, DropSpec &D) {
+  D = DropSpec{nullptr, 0ull, 0.f};
+  if (drop == nullptr) return MMREC_OK;
+  MMREC_REQUIRE(drop->p >= 0.f && drop->p < 1.f, MMREC_E_BADARG, "dropout: p must be in [0, 1) (got %g)", (double)drop->p);
+  D = DropSpec{drop->counter, drop->seed, drop->p};
+  return MMREC_OK;
+}
+
+static int side_fwd_impl(const float *F, const float *V, const float *T, const float *C_, const float *const *W_host,
+                         const float *const *b_host, const float *masks, const MmrecDropout *drop_host, float *saved,
+                         float *side, float *all, int32_t n, int32_t d, void *stream) {
   MMREC_REQUIRE(F && V && T && C_ && W_host && b_host && saved && side && all, MMREC_E_BADARG,
                 "smore_side_fwd: null pointer");
   MMREC_REQUIRE(mmrec_smore_side_supported(d), MMREC_E_BADARG, "smore_side_fwd: d must be 32, 64 or 128 (got %d)", d);
@@ -512,18 +533,20 @@ extern "C" int mmrec_smore_side_fwd_f32(const float *F, const float *V, const fl
   SideWeights P;
   int rc = unpack_weights(W_host, b_host, d, P);
   if (rc != MMREC_OK) return rc;
+  DropSpec drop;
+  rc = unpack_drop(drop_host, drop);
+  if (rc != MMREC_OK) return rc;
   if (n == 0) return MMREC_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  return d == 64    ? side_fwd_launch<64>(F, V, T, C_, P, masks, saved, side, all, n, st)
-         : d == 128 ? side_fwd_launch<128>(F, V, T, C_, P, masks, saved, side, all, n, st)
-                    : side_fwd_launch<32>(F, V, T, C_, P, masks, saved, side, all, n, st);
+  return d == 64    ? side_fwd_launch<64>(F, V, T, C_, P, masks, drop, saved, side, all, n, st)
+         : d == 128 ? side_fwd_launch<128>(F, V, T, C_, P, masks, drop, saved, side, all, n, st)
+                    : side_fwd_launch<32>(F, V, T, C_, P, masks, drop, saved, side, all, n, st);
 }
 
-extern "C" int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side, const float *F, const float *V,
-                                        const float *T, const float *C_, const float *const *W_host,
-                                        const float *const *b_host, const float *masks, const float *saved,
-                                        float *dF, float *dV, float *dT, float *dC, float *const *dW_host,
-                                        float *const *db_host, float *ws, int32_t n, int32_t d, void *stream) {
+static int side_bwd_impl(const float *d_all, const float *d_side, const float *F, const float *V, const float *T,
+                         const float *C_, const float *const *W_host, const float *const *b_host, const float *masks,
+                         const MmrecDropout *drop_host, const float *saved, float *dF, float *dV, float *dT, float *dC,
+                         float *const *dW_host, float *const *db_host, float *ws, int32_t n, int32_t d, void *stream) {
   MMREC_REQUIRE(F && V && T && C_ && W_host && b_host && saved && dF && dV && dT && dC && dW_host && db_host && ws,
                 MMREC_E_BADARG, "smore_side_bwd: null pointer");
   MMREC_REQUIRE(d_all || d_side, MMREC_E_BADARG, "smore_side_bwd: no incoming gradient");
@@ -535,6 +558,9 @@ extern "C" int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side,
   SideWeights P;
   int rc = unpack_weights(W_host, b_host, d, P);
   if (rc != MMREC_OK) return rc;
+  DropSpec drop;
+  rc = unpack_drop(drop_host, drop);
+  if (rc != MMREC_OK) return rc;
   SideGrads G;
   for (int i = 0; i < kNW; ++i) {
     MMREC_REQUIRE(dW_host[i] != nullptr, MMREC_E_BADARG, "smore_side_bwd: dW[%d] is null", i);
@@ -542,7 +568,39 @@ extern "C" int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side,
     G.db[i] = db_host[i];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  return d == 64    ? side_bwd_launch<64>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, G, ws, n, st)
-         : d == 128 ? side_bwd_launch<128>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, G, ws, n, st)
-                    : side_bwd_launch<32>(d_all, d_side, F, V, T, C_, P, masks, saved, dF, dV, dT, dC, G, ws, n, st);
+  return d == 64    ? side_bwd_launch<64>(d_all, d_side, F, V, T, C_, P, masks, drop, saved, dF, dV, dT, dC, G, ws, n, st)
+         : d == 128 ? side_bwd_launch<128>(d_all, d_side, F, V, T, C_, P, masks, drop, saved, dF, dV, dT, dC, G, ws, n, st)
+                    : side_bwd_launch<32>(d_all, d_side, F, V, T, C_, P, masks, drop, saved, dF, dV, dT, dC, G, ws, n, st);
+}
+
+extern "C" int mmrec_smore_side_fwd_f32(const float *F, const float *V, const float *T, const float *C_,
+                                        const float *const *W_host, const float *const *b_host,
+                                        const float *masks, float *saved, float *side, float *all, int32_t n,
+                                        int32_t d, void *stream) {
+  return side_fwd_impl(F, V, T, C_, W_host, b_host, masks, nullptr, saved, side, all, n, d, stream);
+}
+
+extern "C" int mmrec_smore_side_fwd_drop_f32(const float *F, const float *V, const float *T, const float *C_,
+                                             const float *const *W_host, const float *const *b_host,
+                                             const MmrecDropout *drop, float *saved, float *side, float *all,
+                                             int32_t n, int32_t d, void *stream) {
+  return side_fwd_impl(F, V, T, C_, W_host, b_host, nullptr, drop, saved, side, all, n, d, stream);
+}
+
+extern "C" int mmrec_smore_side_bwd_f32(const float *d_all, const float *d_side, const float *F, const float *V,
+                                        const float *T, const float *C_, const float *const *W_host,
+                                        const float *const *b_host, const float *masks, const float *saved,
+                                        float *dF, float *dV, float *dT, float *dC, float *const *dW_host,
+                                        float *const *db_host, float *ws, int32_t n, int32_t d, void *stream) {
+  return side_bwd_impl(d_all, d_side, F, V, T, C_, W_host, b_host, masks, nullptr, saved, dF, dV, dT, dC, dW_host,
+                       db_host, ws, n, d, stream);
+}
+
+extern "C" int mmrec_smore_side_bwd_drop_f32(const float *d_all, const float *d_side, const float *F, const float *V,
+                                             const float *T, const float *C_, const float *const *W_host,
+                                             const float *const *b_host, const MmrecDropout *drop, const float *saved,
+                                             float *dF, float *dV, float *dT, float *dC, float *const *dW_host,
+                                             float *const *db_host, float *ws, int32_t n, int32_t d, void *stream) {
+  return side_bwd_impl(d_all, d_side, F, V, T, C_, W_host, b_host, nullptr, drop, saved, dF, dV, dT, dC, dW_host,
+                       db_host, ws, n, d, stream);
 }

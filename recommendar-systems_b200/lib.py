@@ -63,6 +63,11 @@ SIGNATURES = {
     "mmrec_smore_side_fwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "mmrec_smore_side_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                            _p, _i32, _i32, _p]),
+    "mmrec_smore_side_fwd_drop_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
+    "mmrec_smore_side_bwd_drop_f32": (C.c_int, [_p] * 17 + [_i32, _i32, _p]),
+    "mmrec_dropout_mask_f32": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "mmrec_smore_combine_fwd_drop_f32": (C.c_int, [_p] * 10 + [_i32, _i32, _p, _p, _p]),
+    "mmrec_smore_combine_bwd_drop_f32": (C.c_int, [_p] * 11 + [_i32, _i32] + [_p] * 10),
     "mmrec_smore_combine_supported": (C.c_int, [_i32]),
     "mmrec_smore_combine_fwd_f32": (C.c_int, [_p] * 10 + [_i32, _i32, _p, _p, _p]),
     "mmrec_smore_combine_bwd_f32": (C.c_int, [_p] * 11 + [_i32, _i32] + [_p] * 10),
@@ -110,6 +115,18 @@ class SpmmProblem(C.Structure):
     _fields_ = [("row_ptr", _p), ("col_idx", _p), ("vals", _p), ("tasks", _p), ("n_tasks", _i32),
                 ("slot_base", _p), ("counters", _p), ("scratch", _p), ("col_offset", _i32), ("X", _p),
                 ("Y", _p), ("acc_in", _p), ("acc_out", _p), ("acc_scale", _f32)]
+
+
+class Dropout(C.Structure):
+    """MmrecDropout of include/mmrec_b200.h: in-kernel nn.Dropout (no mask tensor)."""
+    _fields_ = [("p", _f32), ("seed", C.c_uint64), ("counter", _p)]
+
+    @classmethod
+    def make(cls, p, seed, counter=None):
+        """`counter`: a 1-element float64 CUDA tensor read on the device (FusedAdam's update count) or None."""
+        if counter is not None and (counter.dtype != torch.float64 or not counter.is_cuda or counter.numel() < 1):
+            raise RuntimeError("Dropout.counter must be a float64 CUDA tensor")
+        return cls(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(counter))
 
 
 _lib = None

@@ -582,6 +582,22 @@ class SMORE(_MultiViewBase):
         self.spectral_weight_norm = bool(config.get("spectral_weight_norm", True))
         self.cl_temp = float(config.get("cl_temp", 0.2))
         self.overlap_streams = bool(config.get("overlap_streams", os.environ.get("MMREC_OVERLAP", "1") != "0"))
+        # nn.Dropout of smore.py:331-333 generated inside the preference-module kernels (no mask
+        # tensors): stream key = (seed, forward-call index, device counter). The trainer points
+        # `dropout_counter` at FusedAdam's device-side update count, so replays of a captured step
+        # draw fresh masks; without it (eager use) the call index alone advances the stream.
+        self.fused_dropout = bool(config.get("fused_dropout", os.environ.get("MMREC_FUSED_DROPOUT", "1") != "0"))
+        self.dropout_counter = None
+        self._drop_seed = int(config.get("seed", 999))
+        self._drop_calls = 0
+
+    def _dropout_spec(self):
+        """(p, seed, counter) of this forward call for ops.smore_side / ops.smore_combine."""
+        self._drop_calls += 1
+        if self.dropout_counter is None and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("SMORE: in-kernel dropout inside a captured step needs `dropout_counter` "
+                               "(a device-side count that changes between replays; Trainer sets it)")
+        return (self.dropout_rate, (self._drop_seed << 32) ^ (self._drop_calls * 0x9E3779B97F4A7C15), self.dropout_counter)
 
     def spectrum_convolution(self, image_embeds, text_embeds):
         """smore.py:209-252 without the band-energy .item() syncs (diagnostics only)."""
@@ -627,15 +643,18 @@ class SMORE(_MultiViewBase):
         self._join(s_ui, content)
         # modality-aware preference module (smore.py:321-341): one fused kernel for d = 32 / 64
         if ops.smore_side_supported(self.embedding_dim):
-            masks = None
+            masks = drop = None
             if self.training and self.dropout_rate > 0:
-                # the three nn.Dropout masks (smore.py:331-333) drawn in one call
-                masks = torch.nn.functional.dropout(
-                    torch.ones(3, *content.shape, dtype=content.dtype, device=content.device),
-                    p=self.dropout_rate, training=True)
+                if self.fused_dropout:
+                    drop = self._dropout_spec()
+                else:
+                    # the three nn.Dropout masks (smore.py:331-333) drawn in one call
+                    masks = torch.nn.functional.dropout(
+                        torch.ones(3, *content.shape, dtype=content.dtype, device=content.device),
+                        p=self.dropout_rate, training=True)
             layers = (self.query_v[0], self.query_v[2], self.query_t[0], self.query_t[2],
                       self.gate_image_prefer[0], self.gate_text_prefer[0], self.gate_fusion_prefer[0])
-            all_e, side = ops.smore_side(fusion_embeds, image_embeds, text_embeds, content, layers, masks)
+            all_e, side = ops.smore_side(fusion_embeds, image_embeds, text_embeds, content, layers, masks, drop)
             return all_e, side, content
         if ops.smore_combine_supported(self.embedding_dim):
             # wide embeddings (d = 128): the seven Linear layers as tensor-core launches, everything
@@ -643,12 +662,16 @@ class SMORE(_MultiViewBase):
             zv, zt = self.query_v(fusion_embeds), self.query_t(fusion_embeds)
             gi, gt, gf = ops.dense_stack_batch(
                 (self.gate_image_prefer, self.gate_text_prefer, self.gate_fusion_prefer), (content, content, content))
-            masks = None
+            masks = drop = None
             if self.training and self.dropout_rate > 0:
-                masks = torch.nn.functional.dropout(
-                    torch.ones(3, *content.shape, dtype=content.dtype, device=content.device),
-                    p=self.dropout_rate, training=True)
-            all_e, side = ops.smore_combine(zv, zt, image_embeds, text_embeds, fusion_embeds, content, gi, gt, gf, masks)
+                if self.fused_dropout:
+                    drop = self._dropout_spec()
+                else:
+                    masks = torch.nn.functional.dropout(
+                        torch.ones(3, *content.shape, dtype=content.dtype, device=content.device),
+                        p=self.dropout_rate, training=True)
+            all_e, side = ops.smore_combine(zv, zt, image_embeds, text_embeds, fusion_embeds, content, gi, gt, gf,
+                                            masks, drop)
             return all_e, side, content
         agg_image = self.softmax(self.query_v(fusion_embeds)) * image_embeds
         agg_text = self.softmax(self.query_t(fusion_embeds)) * text_embeds

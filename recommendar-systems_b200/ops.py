@@ -5,6 +5,8 @@ op). Everything runs on CUDA through libmmrec_b200.so; there is no CPU or eager 
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import lib
@@ -908,10 +910,12 @@ _ptr_array = lib.ptr_array
 
 class _SmoreSide(torch.autograd.Function):
     """smore.py:321-341 in one forward / one backward launch (mmrec_smore_side_*_f32).
-    apply(F, V, T, C, masks, W0, b0, ..., W6, b6) -> (all_embeds, side_embeds)."""
+    apply(F, V, T, C, masks, drop, W0, b0, ..., W6, b6) -> (all_embeds, side_embeds).
+    `drop` = (p, seed, counter) or None: the dropout multipliers are generated inside both kernels
+    (lib.Dropout) instead of being read from `masks`."""
 
     @staticmethod
-    def forward(ctx, F, V, T, C_, masks, *wb):
+    def forward(ctx, F, V, T, C_, masks, drop, *wb):
         F, V, T, C_ = _f32c(F), _f32c(V), _f32c(T), _f32c(C_)
         Ws = [_f32c(w) for w in wb[0::2]]
         bs = [None if b is None else _f32c(b) for b in wb[1::2]]
@@ -919,9 +923,17 @@ class _SmoreSide(torch.autograd.Function):
         n, d = F.shape
         saved = torch.empty(7, n, d, dtype=torch.float32, device=F.device)
         side, all_e = torch.empty_like(F), torch.empty_like(F)
-        lib.call("mmrec_smore_side_fwd_f32", lib.ptr(F), lib.ptr(V), lib.ptr(T), lib.ptr(C_),
-                 _ptr_array(Ws), _ptr_array(bs), lib.ptr(masks), lib.ptr(saved), lib.ptr(side),
-                 lib.ptr(all_e), n, d, lib.stream())
+        if drop is not None:
+            if masks is not None:
+                raise RuntimeError("smore_side: pass either mask tensors or an in-kernel dropout spec")
+            lib.call("mmrec_smore_side_fwd_drop_f32", lib.ptr(F), lib.ptr(V), lib.ptr(T), lib.ptr(C_),
+                     _ptr_array(Ws), _ptr_array(bs), ctypes.byref(lib.Dropout.make(*drop)), lib.ptr(saved), lib.ptr(side),
+                     lib.ptr(all_e), n, d, lib.stream())
+        else:
+            lib.call("mmrec_smore_side_fwd_f32", lib.ptr(F), lib.ptr(V), lib.ptr(T), lib.ptr(C_),
+                     _ptr_array(Ws), _ptr_array(bs), lib.ptr(masks), lib.ptr(saved), lib.ptr(side),
+                     lib.ptr(all_e), n, d, lib.stream())
+        ctx.drop = drop
         ctx.has_mask = masks is not None
         ctx.has_bias = [b is not None for b in bs]
         ctx.save_for_backward(F, V, T, C_, saved, *Ws, *[b for b in bs if b is not None],
@@ -944,14 +956,20 @@ class _SmoreSide(torch.autograd.Function):
         dbs = [None if b is None else torch.empty_like(b) for b in bs]
         ws = torch.empty(lib.load().mmrec_smore_side_bwd_workspace_bytes(n, d) // 4, dtype=torch.float32,
                          device=F.device)
-        lib.call("mmrec_smore_side_bwd_f32", lib.ptr(g_all), lib.ptr(g_side), lib.ptr(F), lib.ptr(V),
-                 lib.ptr(T), lib.ptr(C_), _ptr_array(Ws), _ptr_array(bs), lib.ptr(masks), lib.ptr(saved),
-                 lib.ptr(dF), lib.ptr(dV), lib.ptr(dT), lib.ptr(dC), _ptr_array(dWs), _ptr_array(dbs),
-                 lib.ptr(ws), n, d, lib.stream())
+        if ctx.drop is not None:
+            lib.call("mmrec_smore_side_bwd_drop_f32", lib.ptr(g_all), lib.ptr(g_side), lib.ptr(F), lib.ptr(V),
+                     lib.ptr(T), lib.ptr(C_), _ptr_array(Ws), _ptr_array(bs), ctypes.byref(lib.Dropout.make(*ctx.drop)),
+                     lib.ptr(saved), lib.ptr(dF), lib.ptr(dV), lib.ptr(dT), lib.ptr(dC), _ptr_array(dWs),
+                     _ptr_array(dbs), lib.ptr(ws), n, d, lib.stream())
+        else:
+            lib.call("mmrec_smore_side_bwd_f32", lib.ptr(g_all), lib.ptr(g_side), lib.ptr(F), lib.ptr(V),
+                     lib.ptr(T), lib.ptr(C_), _ptr_array(Ws), _ptr_array(bs), lib.ptr(masks), lib.ptr(saved),
+                     lib.ptr(dF), lib.ptr(dV), lib.ptr(dT), lib.ptr(dC), _ptr_array(dWs), _ptr_array(dbs),
+                     lib.ptr(ws), n, d, lib.stream())
         grads = []
         for dw, db in zip(dWs, dbs):
             grads += [dw, db]
-        return (dF, dV, dT, dC, None, *grads)
+        return (dF, dV, dT, dC, None, None, *grads)
 
 
 def smore_side_supported(d):
@@ -964,16 +982,27 @@ def smore_side_supported(d):
     return int(d) in widths and bool(lib.load().mmrec_smore_side_supported(int(d)))
 
 
-def smore_side(fusion, image, text, content, layers, masks=None):
+def dropout_mask(planes, n, d, drop, device=None):
+    """The [planes, n, d] multipliers (0 or 1/(1-p)) an in-kernel dropout spec `drop` = (p, seed,
+    counter) generates (mmrec_dropout_mask_f32) -- for tests and diagnostics; the kernels never
+    materialise them."""
+    dev = drop[2].device if drop[2] is not None else (device or torch.device("cuda", torch.cuda.current_device()))
+    out = torch.empty(planes, n, d, dtype=torch.float32, device=dev)
+    lib.call("mmrec_dropout_mask_f32", lib.ptr(out), planes, n, d, ctypes.byref(lib.Dropout.make(*drop)), lib.stream())
+    return out
+
+
+def smore_side(fusion, image, text, content, layers, masks=None, drop=None):
     """Fused modality-aware preference module. `layers` = the seven nn.Linear modules in the
     order query_v.0, query_v.2, query_t.0, query_t.2, gate_image_prefer.0, gate_text_prefer.0,
-    gate_fusion_prefer.0; masks = [3, n, d] dropout multipliers or None.
+    gate_fusion_prefer.0; masks = [3, n, d] dropout multipliers or None; drop = (p, seed, counter)
+    for dropout generated inside the kernels (no mask tensor; see lib.Dropout).
     Returns (content + side, side)."""
     lib.require_cuda(fusion, image, text, content)
     wb = []
     for m in layers:
         wb += [m.weight, m.bias]
-    return _SmoreSide.apply(fusion, image, text, content, masks, *wb)
+    return _SmoreSide.apply(fusion, image, text, content, masks, drop, *wb)
 
 
 # ------------------------------------------- SMORE preference module, row part (wide embeddings)
@@ -982,13 +1011,18 @@ class _SmoreCombine(torch.autograd.Function):
     -> (content + side, side); see mmrec_smore_combine_*_f32."""
 
     @staticmethod
-    def forward(ctx, zv, zt, V, T, F, C_, gi, gt, gf, masks):
+    def forward(ctx, zv, zt, V, T, F, C_, gi, gt, gf, masks, drop=None):
         zv, zt, V, T, F, C_, gi, gt, gf = (_f32c(t) for t in (zv, zt, V, T, F, C_, gi, gt, gf))
         masks = None if masks is None else _f32c(masks)
         n, d = F.shape
         side, all_e = torch.empty_like(F), torch.empty_like(F)
-        lib.call("mmrec_smore_combine_fwd_f32", lib.ptr(zv), lib.ptr(zt), lib.ptr(V), lib.ptr(T), lib.ptr(F), lib.ptr(C_),
-                 lib.ptr(gi), lib.ptr(gt), lib.ptr(gf), lib.ptr(masks), n, d, lib.ptr(side), lib.ptr(all_e), lib.stream())
+        if drop is not None and masks is not None:
+            raise RuntimeError("smore_combine: pass either mask tensors or an in-kernel dropout spec")
+        lib.call("mmrec_smore_combine_fwd_f32" if drop is None else "mmrec_smore_combine_fwd_drop_f32",
+                 lib.ptr(zv), lib.ptr(zt), lib.ptr(V), lib.ptr(T), lib.ptr(F), lib.ptr(C_), lib.ptr(gi), lib.ptr(gt),
+                 lib.ptr(gf), lib.ptr(masks) if drop is None else ctypes.byref(lib.Dropout.make(*drop)), n, d,
+                 lib.ptr(side), lib.ptr(all_e), lib.stream())
+        ctx.drop = drop
         ctx.has_mask = masks is not None
         ctx.save_for_backward(zv, zt, V, T, F, gi, gt, gf, *([masks] if masks is not None else []))
         return all_e, side
@@ -1002,22 +1036,25 @@ class _SmoreCombine(torch.autograd.Function):
         g_all = None if g_all is None else _f32c(g_all)
         g_side = None if g_side is None else _f32c(g_side)
         outs = [torch.empty_like(F) for _ in range(9)]          # dzv dzt dV dT dF dC dgi dgt dgf
-        lib.call("mmrec_smore_combine_bwd_f32", lib.ptr(g_all), lib.ptr(g_side), lib.ptr(zv), lib.ptr(zt), lib.ptr(V),
-                 lib.ptr(T), lib.ptr(F), lib.ptr(gi), lib.ptr(gt), lib.ptr(gf), lib.ptr(masks), n, d,
+        lib.call("mmrec_smore_combine_bwd_f32" if ctx.drop is None else "mmrec_smore_combine_bwd_drop_f32",
+                 lib.ptr(g_all), lib.ptr(g_side), lib.ptr(zv), lib.ptr(zt), lib.ptr(V), lib.ptr(T), lib.ptr(F),
+                 lib.ptr(gi), lib.ptr(gt), lib.ptr(gf),
+                 lib.ptr(masks) if ctx.drop is None else ctypes.byref(lib.Dropout.make(*ctx.drop)), n, d,
                  *[lib.ptr(o) for o in outs], lib.stream())
         dzv, dzt, dV, dT, dF, dC, dgi, dgt, dgf = outs
-        return dzv, dzt, dV, dT, dF, dC, dgi, dgt, dgf, None
+        return dzv, dzt, dV, dT, dF, dC, dgi, dgt, dgf, None, None
 
 
 def smore_combine_supported(d):
     return bool(lib.load().mmrec_smore_combine_supported(int(d)))
 
 
-def smore_combine(zv, zt, image, text, fusion, content, gi, gt, gf, masks=None):
+def smore_combine(zv, zt, image, text, fusion, content, gi, gt, gf, masks=None, drop=None):
     """Row part of SMORE's preference module: (content + side, side) from the pre-softmax query
-    outputs, the three views, the content embeddings and the three sigmoid gates (+ dropout masks)."""
+    outputs, the three views, the content embeddings and the three sigmoid gates (+ dropout: mask
+    tensors, or drop = (p, seed, counter) generated in the kernels)."""
     lib.require_cuda(zv, zt, image, text, fusion, content, gi, gt, gf)
-    return _SmoreCombine.apply(zv, zt, image, text, fusion, content, gi, gt, gf, masks)
+    return _SmoreCombine.apply(zv, zt, image, text, fusion, content, gi, gt, gf, masks, drop)
 
 
 # ------------------------------------------------------------------- MGCN attention fuser (fused)

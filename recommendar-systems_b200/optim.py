@@ -111,8 +111,14 @@ class FusedAdam(torch.optim.Optimizer):
         for group in self.param_groups:
             steps = [float(self.state[p].pop("step")) for p in group["params"]
                      if p in self.state and "step" in self.state[p]]
-            group.pop("hyper", None)
-            if steps and group["params"]:
+            # the device tensor itself is kept (captured graphs and the in-kernel dropout streams hold
+            # its address); only its contents follow the loaded state
+            h = group.get("hyper")
+            if h is not None:
+                h[0:1].fill_(group["lr"])
+                h[1:2].fill_(max(steps) if steps else 0.0)
+                group["hyper_lr"] = group["lr"]
+            elif steps and group["params"]:
                 self._hyper(group, group["params"][0].device)[1:2].fill_(max(steps))
 
     @torch.no_grad()

@@ -187,6 +187,10 @@ class Trainer:
         self.lr_scheduler = optim.lr_scheduler.LambdaLR(self.optimizer,
                                                         lr_lambda=lambda e: sch[0] ** (e / sch[1]))
         self.evaluator = TopKEvaluator(config)
+        if hasattr(model, "dropout_counter") and hasattr(self.optimizer, "_hyper") and self.optimizer.param_groups:
+            # in-kernel dropout streams follow the optimizer's device-side update count
+            g0 = self.optimizer.param_groups[0]
+            model.dropout_counter = self.optimizer._hyper(g0, g0["params"][0].device)[1:2]
         self.mg = mg
         self.alpha1, self.alpha2, self.beta = config["alpha1"], config["alpha2"], config["beta"]
         self.mg_target_rel_step = float(config.get("mg_target_rel_step", 1e-3))

@@ -1,0 +1,134 @@
+"""GPU tests added in the second half of round 2 (all through the C ABI):
+* nn.Dropout of the SMORE preference module generated inside the kernels (smore.py:331-333): the
+  generator against oracle/dropout.py bit for bit, the fused modules with in-kernel dropout against
+  the same modules fed the materialised masks (bit-identical), fresh masks on CUDA-graph replays.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import pkg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _counter(v):
+    return torch.tensor([v], dtype=torch.float64, device=DEV)
+
+
+@pytest.mark.parametrize("planes,n,d,p,seed,count", [(3, 26495, 64, 0.5, 999, 0), (3, 1, 32, 0.1, (999 << 32) ^ 12345, 17),
+                                                    (1, 777, 128, 0.25, 2 ** 64 - 1, 2 ** 31 + 5), (3, 100, 64, 0.0, 1, 1)])
+def test_inkernel_dropout_generator_matches_oracle(planes, n, d, p, seed, count):
+    from oracle import dropout as odrop
+    ops = pkg("ops")
+    got = ops.dropout_mask(planes, n, d, (p, seed, _counter(count)))
+    want = odrop.dropout_multipliers(planes, n, d, p, seed, count)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # counter = NULL reads as 0
+    got0 = ops.dropout_mask(planes, n, d, (p, seed, None), device=torch.device(DEV))
+    assert np.array_equal(got0.cpu().numpy(), odrop.dropout_multipliers(planes, n, d, p, seed, 0))
+
+
+def _layers(d, seed):
+    torch.manual_seed(seed)
+    mk = lambda bias: torch.nn.Linear(d, d, bias=bias).to(DEV)
+    return [mk(True), mk(False), mk(True), mk(False), mk(True), mk(True), mk(True)]
+
+
+@pytest.mark.parametrize("n,d,p", [(26495, 64, 0.5), (333, 32, 0.2), (6001, 128, 0.1), (65, 64, 0.9)])
+def test_smore_side_inkernel_dropout_equals_explicit_masks(n, d, p):
+    """mmrec_smore_side_*_drop_f32 == mmrec_smore_side_*_f32 fed the masks the generator writes out
+    (forward outputs and every gradient bit-identical): forward and backward regenerate one mask."""
+    ops = pkg("ops")
+    layers = _layers(d, 5)
+    gen = torch.Generator().manual_seed(n)
+    ins = [torch.randn(n, d, generator=gen).to(DEV) for _ in range(4)]
+    ga, gs = torch.randn(n, d, generator=gen).to(DEV), torch.randn(n, d, generator=gen).to(DEV)
+    spec = (p, (999 << 32) ^ 77, _counter(41))
+    res = []
+    for mode in ("drop", "masks"):
+        x = [t.clone().requires_grad_(True) for t in ins]
+        for l in layers:
+            l.zero_grad()
+        if mode == "drop":
+            a, s = ops.smore_side(*x, layers, None, spec)
+        else:
+            a, s = ops.smore_side(*x, layers, ops.dropout_mask(3, n, d, spec))
+        ((a * ga).sum() + (s * gs).sum()).backward()
+        res.append([a.detach(), s.detach()] + [t.grad for t in x] + [l.weight.grad.clone() for l in layers] +
+                   [l.bias.grad.clone() for l in layers if l.bias is not None])
+    for u, v in zip(*res):
+        assert torch.equal(u, v)
+    # and the masks matter: without dropout the output differs
+    a0, _ = ops.smore_side(*ins, layers)
+    assert not torch.equal(a0, res[0][0])
+
+
+@pytest.mark.parametrize("n,d,p", [(62420, 128, 0.5), (777, 64, 0.2), (33, 32, 0.1)])
+def test_smore_combine_inkernel_dropout_equals_explicit_masks(n, d, p):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(n + d)
+    names = ("zv", "zt", "V", "T", "F", "C", "gi", "gt", "gf")
+    t = {k: torch.randn(n, d, generator=gen).to(DEV) for k in names}
+    for k in ("gi", "gt", "gf"):
+        t[k] = torch.sigmoid(t[k])
+    ga, gs = torch.randn(n, d, generator=gen).to(DEV), torch.randn(n, d, generator=gen).to(DEV)
+    spec = (p, 31337, _counter(3))
+    res = []
+    for mode in ("drop", "masks"):
+        y = {k: v.clone().requires_grad_(True) for k, v in t.items()}
+        args = [y[k] for k in names]
+        if mode == "drop":
+            a, s = ops.smore_combine(*args, None, spec)
+        else:
+            a, s = ops.smore_combine(*args, ops.dropout_mask(3, n, d, spec))
+        ((a * ga).sum() + (s * gs).sum()).backward()
+        res.append([a.detach(), s.detach()] + [y[k].grad for k in names])
+    for u, v in zip(*res):
+        assert torch.equal(u, v)
+
+
+def test_inkernel_dropout_draws_fresh_masks_on_graph_replay():
+    """A captured launch reads the counter on the device: replays after the counter moved use the
+    mask of the new count (what FusedAdam's update count provides inside a captured training step)."""
+    ops = pkg("ops")
+    n, d, p = 4000, 64, 0.5
+    layers = _layers(d, 9)
+    ins = [torch.randn(n, d, device=DEV) for _ in range(4)]
+    cnt = _counter(5)
+    spec = (p, 4242, cnt)
+    with torch.no_grad():
+        ops.smore_side(*ins, layers, None, spec)                  # warm-up outside capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            a, s = ops.smore_side(*ins, layers, None, spec)
+        outs = []
+        for c in (5, 6, 6, 1000):
+            cnt.fill_(c)
+            g.replay()
+            want, _ = ops.smore_side(*ins, layers, ops.dropout_mask(3, n, d, (p, 4242, _counter(c))))
+            assert torch.equal(a, want)
+            outs.append(a.clone())
+    assert not torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]) and not torch.equal(outs[2], outs[3])
+
+
+def test_smore_trainer_uses_inkernel_dropout_under_graph_replay():
+    """SMORE with dropout_rate > 0 through the Trainer: no mask tensors are drawn (torch's CUDA
+    generator is not consumed by the step), the dropout counter is the optimizer's device-side
+    update count, and graph-replayed steps stay finite and keep training."""
+    from parity_util import make_env
+    env = make_env("SMORE", DEV, overrides={"cuda_graph": True, "dropout_rate": 0.5})
+    m = env["model"]
+    tr = pkg("trainer").Trainer(env["config"], m)
+    assert m.fused_dropout and m.dropout_counter is not None
+    assert m.dropout_counter.data_ptr() == tr.optimizer.param_groups[0]["hyper"].data_ptr() + 8
+    state = torch.cuda.get_rng_state(0)
+    losses = []
+    for epoch in range(3):
+        total, _ = tr._train_epoch(env["train"], epoch)
+        losses.append(float(total))
+    assert torch.equal(state, torch.cuda.get_rng_state(0))        # nn.Dropout no longer touches torch's generator
+    assert tr.replayed_launches > 0 and np.isfinite(losses).all()
+    assert float(m.dropout_counter.item()) > 0
