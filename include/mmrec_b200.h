@@ -102,15 +102,9 @@ int mmrec_spmm_csr_f32(const int32_t *row_ptr, const int32_t *col_idx, const flo
  *                      flight for graphs of very short rows (the column blocks of an operand cut
  *                      into L2-sized slices);
  *   MMREC_SPMM_STREAM  L2 eviction policies: gathered X rows evict_last, everything touched once
- *                      (CSR arrays, epilogue operand, output rows) evict_first. Not with cos_ref.
- *   MMREC_SPMM_PACKED  the task list holds PACKED tasks: slot = -n_rows < -1 means the task covers the
- *                      n_rows (<= 8) consecutive rows row .. row + n_rows - 1, whose non-zeros
- *                      [begin, end) number at most 64 (graph.py build_tasks(pack=True)); short rows
- *                      then share the index round trip and the gather groups. Results are
- *                      bit-identical to the unpacked list (every row is summed in CSR order). */
+ *                      (CSR arrays, epilogue operand, output rows) evict_first. Not with cos_ref. */
 #define MMREC_SPMM_NARROW 1
 #define MMREC_SPMM_STREAM 2
-#define MMREC_SPMM_PACKED 4
 int mmrec_spmm_csr_ex_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
                        const int32_t *tasks, int32_t n_tasks, const int32_t *slot_base,
                        int32_t *counters, float *scratch, int32_t col_offset, const float *X,
@@ -139,9 +133,6 @@ typedef struct MmrecSpmmProblem {
 } MmrecSpmmProblem;
 int mmrec_spmm_csr_multi_f32(const MmrecSpmmProblem *problems_host, int32_t n_problems, int32_t d,
                              void *stream);
-/* flags: MMREC_SPMM_PACKED if any of the task lists holds packed tasks */
-int mmrec_spmm_csr_multi_ex_f32(const MmrecSpmmProblem *problems_host, int32_t n_problems, int32_t d,
-                                int32_t flags, void *stream);
 
 /* Backward row-operator of one LayerGCN layer (layergcn.py:134-135 differentiated):
  * given dE = dL/d(w*p), p = Y_pre, w = cos_w, e0 = cos_ref:

@@ -9,10 +9,6 @@
 // a heavy row is cut into ceil(deg/SEG) tasks whose partial sums go to a scratch buffer, and
 // the last task to arrive (per-row counter, self-resetting) adds them in part order and runs
 // the fused epilogue -- no floating-point atomics, results are bit-reproducible run to run.
-// Short rows are PACKED: a light task may cover several consecutive rows (task.w = -n_rows) whose
-// non-zeros together fit one task, so the index round trip, the task decode and the gather groups
-// are shared by ~3-5 rows of a sparse graph (Baby: 12 non-zeros per row on average) and the launch
-// is one wave instead of three; every row is still summed in CSR order by itself (bit-identical).
 // Each gathered embedding row is one coalesced 16-byte-per-lane request; the column indices and
 // values of a whole task are loaded in one round and broadcast with shuffles; eight gathers are
 // kept in flight per lane. The kernel is a chain of dependent L2/DRAM round trips: on the small
@@ -228,124 +224,11 @@ struct Problem {
   Epilogue ep;
 };
 
-constexpr int kMaxPackRows = 8;   // rows per packed task; must match graph.py PACK_ROWS (<= smallest LANES)
-
-// Packed light task: consecutive rows [row0, row0 + n_rows) whose non-zeros [begin, end) number at
-// most kSeg. Indices and values of the whole task are fetched in one round together with the row
-// ends; the embedding rows are gathered kDepth at a time ACROSS row boundaries (full memory-level
-// parallelism even when the rows are 1-3 non-zeros long); a row's epilogue runs when the running
-// position passes its end (empty rows included). All control flow is uniform within the sub-warp.
-template <int LANES, int CHUNKS, bool STREAM>
-__device__ __forceinline__ void run_packed(const Problem &P, int row0, int n_rows, int begin, int end, int lane, int d) {
-  uint64_t pol_first = 0, pol_last = 0;
-  if constexpr (STREAM) { pol_first = policy_evict_first(); pol_last = policy_evict_last(); }
-  constexpr int NIDX = kSeg / LANES;
-  constexpr int DEPTH = CHUNKS == 1 ? kDepth : kDepth / 2;
-  static_assert(kMaxPackRows <= LANES, "row ends are held one per lane");
-  const unsigned mask = group_mask<LANES>();
-  const Epilogue &ep = P.ep;
-  const int n = end - begin;
-  int my_end = lane < n_rows ? P.row_ptr[row0 + lane + 1] : 0x7fffffff;
-  int c[NIDX];
-  float v[NIDX];
-#pragma unroll
-  for (int i = 0; i < NIDX; ++i) {
-    const int k = begin + i * LANES + lane;
-    c[i] = 0;
-    v[i] = 0.f;
-    if (k < end) {
-      if constexpr (STREAM) {
-        c[i] = ld_stream_i32_hint(P.col_idx + k, pol_first) - P.col_offset;
-        v[i] = ld_stream_f32_hint(P.vals + k, pol_first);
-      } else {
-        c[i] = ld_stream_i32(P.col_idx + k) - P.col_offset;
-        v[i] = ld_stream_f32(P.vals + k);
-      }
-    }
-  }
-  {  // the epilogue operands of the task's rows are contiguous: one 128-byte line per lane and pass
-    const size_t o0 = (size_t)row0 * d;
-    const int lines = (n_rows * d * 4 + 127) / 128;
-    for (int l = lane; l < lines; l += LANES) {
-      if (ep.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.acc_in + o0 + (size_t)l * 32));
-      if (ep.cos_ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.cos_ref + o0 + (size_t)l * 32));
-    }
-  }
-  float4 acc[CHUNKS];
-#pragma unroll
-  for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int cur = 0;                                           // current row of the task
-  int cur_end = __shfl_sync(mask, my_end, 0, LANES) - begin;   // its end, relative to the task
-#pragma unroll 1
-  for (int i = 0; i < NIDX; ++i) {
-    if (i * LANES >= n) break;
-    int ci = c[0];
-    float vi = v[0];
-#pragma unroll
-    for (int u = 1; u < NIDX; ++u) {
-      ci = i == u ? c[u] : ci;
-      vi = i == u ? v[u] : vi;
-    }
-#pragma unroll
-    for (int j = 0; j < LANES; j += DEPTH) {
-      const int base = i * LANES + j;
-      if (base < n) {
-        int cc[DEPTH];
-        float vv[DEPTH];
-        float4 x[DEPTH][CHUNKS];
-#pragma unroll
-        for (int t = 0; t < DEPTH; ++t) {
-          cc[t] = __shfl_sync(mask, ci, j + t, LANES);
-          vv[t] = __shfl_sync(mask, vi, j + t, LANES);
-        }
-#pragma unroll
-        for (int t = 0; t < DEPTH; ++t)
-#pragma unroll
-          for (int q = 0; q < CHUNKS; ++q)
-            x[t][q] = base + t < n ? (STREAM ? ldg4_hint(P.X + (size_t)cc[t] * d + (q * LANES + lane) * 4, pol_last)
-                                             : ldg4(P.X + (size_t)cc[t] * d + (q * LANES + lane) * 4))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int lim = min(DEPTH, n - base);            // live entries of this group
-        int t0 = 0;
-        for (;;) {
-          const int m = min(lim, cur_end - base);        // entries [t0, m) belong to the current row
-#pragma unroll
-          for (int t = 0; t < DEPTH; ++t)
-            if (t >= t0 && t < m) {
-#pragma unroll
-              for (int q = 0; q < CHUNKS; ++q) fma4(acc[q], vv[t], x[t][q]);
-            }
-          if (m >= lim) break;                           // the row continues in the next group
-          finish_row<LANES, CHUNKS, STREAM>(acc, row0 + cur, lane, d, ep);
-#pragma unroll
-          for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          ++cur;
-          cur_end = __shfl_sync(mask, my_end, cur & (LANES - 1), LANES);
-          cur_end = cur < n_rows ? cur_end - begin : 0x7fffffff;
-          t0 = max(t0, m);
-        }
-      }
-    }
-  }
-  // the row in progress and the empty rows behind it
-  for (; cur < n_rows; ++cur) {
-    finish_row<LANES, CHUNKS, STREAM>(acc, row0 + cur, lane, d, ep);
-#pragma unroll
-    for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
 // One task (<= kSeg non-zeros of one row) by one sub-warp of LANES threads.
-template <int LANES, int CHUNKS, bool STREAM = false, bool PACKED = false>
+template <int LANES, int CHUNKS, bool STREAM = false>
 __device__ __forceinline__ void run_task(const Problem &P, int t, int lane, int d) {
   const int4 task = __ldg(P.tasks + t);          // {row, begin, end, slot}
   const int row = task.x;
-  if constexpr (PACKED) {
-    if (task.w < -1) {
-      run_packed<LANES, CHUNKS, STREAM>(P, row, -task.w, task.y, task.z, lane, d);
-      return;
-    }
-  }
   const Epilogue &ep = P.ep;
   float4 acc[CHUNKS];
 #pragma unroll
@@ -399,16 +282,14 @@ __device__ __forceinline__ void run_task(const Problem &P, int t, int lane, int 
   finish_row<LANES, CHUNKS, STREAM>(acc, row, lane, d, ep);
 }
 
-// PACKED: the task list may hold packed tasks (MMREC_SPMM_PACKED). Those kernels trade one resident
-// CTA per SM for registers: a packed list has 3-5x fewer tasks, occupancy is not what limits them.
-template <int LANES, int CHUNKS, bool STREAM = false, bool PACKED = false>
-__global__ void __launch_bounds__(kThreads, PACKED ? 3 : (CHUNKS == 1 || LANES <= 16 ? 4 : 3))
+template <int LANES, int CHUNKS, bool STREAM = false>
+__global__ void __launch_bounds__(kThreads, CHUNKS == 1 || LANES <= 16 ? 4 : 3)
 spmm_csr_kernel(const Problem P, int d) {
   constexpr int GROUPS = kThreads / LANES;
   const int lane = threadIdx.x % LANES;
   const int t = blockIdx.x * GROUPS + threadIdx.x / LANES;
   if (t >= P.n_tasks) return;
-  run_task<LANES, CHUNKS, STREAM, PACKED>(P, t, lane, d);
+  run_task<LANES, CHUNKS, STREAM>(P, t, lane, d);
 }
 
 // Several independent SpMMs in one launch (the three modality views of SMORE/MGCN: small graphs
@@ -420,8 +301,8 @@ struct MultiArgs {
   int n;
 };
 
-template <int LANES, int CHUNKS, bool PACKED = false>
-__global__ void __launch_bounds__(kThreads, PACKED ? 3 : (CHUNKS == 1 ? 4 : 3))
+template <int LANES, int CHUNKS>
+__global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 4 : 3)
 spmm_csr_multi_kernel(const MultiArgs A, int d) {
   constexpr int GROUPS = kThreads / LANES;
   int pi = 0;
@@ -431,7 +312,7 @@ spmm_csr_multi_kernel(const MultiArgs A, int d) {
   const int lane = threadIdx.x % LANES;
   const int t = (blockIdx.x - b0) * GROUPS + threadIdx.x / LANES;
   if (t >= P.n_tasks) return;
-  run_task<LANES, CHUNKS, false, PACKED>(P, t, lane, d);
+  run_task<LANES, CHUNKS>(P, t, lane, d);
 }
 
 // ---- LayerGCN cosine refinement, backward row operator --------------------------------------
@@ -535,16 +416,14 @@ static int spmm_csr_impl(int flags, const int32_t *row_ptr, const int32_t *col_i
   if (n_tasks == 0) return MMREC_OK;
   Problem P{row_ptr, col_idx, vals, reinterpret_cast<const int4 *>(tasks), n_tasks, slot_base, counters, scratch,
             col_offset, X, Epilogue{Y, acc_in, acc_out, acc_scale, cos_ref, cos_w, Y_pre}};
-  const bool narrow = flags & MMREC_SPMM_NARROW, streaming = flags & MMREC_SPMM_STREAM, packed = flags & MMREC_SPMM_PACKED;
+  const bool narrow = flags & MMREC_SPMM_NARROW, streaming = flags & MMREC_SPMM_STREAM;
   MMREC_REQUIRE(!(streaming && cos_ref), MMREC_E_BADARG, "spmm: the streaming cache policy has no cosine epilogue");
   auto launch = [&](auto lanes, auto chunks) {
     constexpr int L = decltype(lanes)::value, C = decltype(chunks)::value;
     constexpr int GROUPS = kThreads / L;
     const int blocks = (n_tasks + GROUPS - 1) / GROUPS;
-    if (streaming && packed) spmm_csr_kernel<L, C, true, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
-    else if (streaming) spmm_csr_kernel<L, C, true, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
-    else if (packed) spmm_csr_kernel<L, C, false, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
-    else spmm_csr_kernel<L, C, false, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
+    if (streaming) spmm_csr_kernel<L, C, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
+    else spmm_csr_kernel<L, C, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
     MMREC_CHECK_LAUNCH("spmm_csr_kernel");
     return MMREC_OK;
   };
@@ -571,11 +450,6 @@ extern "C" int mmrec_spmm_csr_ex_f32(const int32_t *row_ptr, const int32_t *col_
 
 extern "C" int mmrec_spmm_csr_multi_f32(const MmrecSpmmProblem *problems_host, int32_t n_problems, int32_t d,
                                         void *stream) {
-  return mmrec_spmm_csr_multi_ex_f32(problems_host, n_problems, d, 0, stream);
-}
-
-extern "C" int mmrec_spmm_csr_multi_ex_f32(const MmrecSpmmProblem *problems_host, int32_t n_problems, int32_t d,
-                                           int32_t flags, void *stream) {
   MMREC_REQUIRE(problems_host && n_problems >= 1 && n_problems <= kMaxProblems, MMREC_E_BADARG,
                 "spmm_multi: 1..%d problems", kMaxProblems);
   MultiArgs A{};
@@ -603,8 +477,7 @@ extern "C" int mmrec_spmm_csr_multi_ex_f32(const MmrecSpmmProblem *problems_host
       blocks += (A.p[i].n_tasks + GROUPS - 1) / GROUPS;
       A.block_end[i] = blocks;
     }
-    if (flags & MMREC_SPMM_PACKED) spmm_csr_multi_kernel<L, C, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(A, d);
-    else spmm_csr_multi_kernel<L, C, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(A, d);
+    spmm_csr_multi_kernel<L, C><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(A, d);
     MMREC_CHECK_LAUNCH("spmm_csr_multi_kernel");
     return MMREC_OK;
   });

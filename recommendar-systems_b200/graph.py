@@ -16,26 +16,12 @@ from . import lib
 SEG = 64            # non-zeros per SpMM task (kSeg in csrc/spmm.cu)
 
 
-# packed tasks: rows of at most PACK_MAX_DEG non-zeros that START in the same window of PACK_WINDOW CSR
-# positions (so their span is at most SEG), at most PACK_ROWS of them (kMaxPackRows in csrc/spmm.cu)
-PACK_WINDOW = int(__import__("os").environ.get("MMREC_SPMM_PACK_WINDOW", "32"))
-PACK_MAX_DEG = SEG + 1 - PACK_WINDOW
-PACK_ROWS = 8
-PACK_MEAN_DEG = 24  # graphs with more non-zeros per row than this keep one-row tasks
-PACK_DEFAULT = __import__("os").environ.get("MMREC_SPMM_PACK", "1") != "0"
-
-
-def build_tasks(row_ptr, skip_empty=False, pack=False):
+def build_tasks(row_ptr, skip_empty=False):
     """Work list of mmrec_spmm_csr_f32: int32 [n_tasks, 4] = {row, begin, end, slot}. Rows with at
     most SEG non-zeros are one task (slot -1, longest first so that the sub-warps of a warp have
     similar trip counts); heavier rows are cut into SEG-sized parts that share a reduction slot.
     `skip_empty` leaves rows without non-zeros out (their output row is then not written at all:
     only for accumulating launches, see ColumnBlockedCSR).
-    `pack` (MMREC_SPMM_PACKED): consecutive short rows share a task, {first row, begin of the first,
-    end of the last, -n_rows}: rows of at most PACK_MAX_DEG non-zeros whose CSR ranges start in the
-    same window of PACK_WINDOW positions (a longer row that starts in a window ends beyond it, so it
-    is the last one to start there: the short ones are consecutive and span at most SEG positions),
-    PACK_ROWS at most.
     Returns (tasks, slot_base int32 [n_heavy], total_parts)."""
     dev = row_ptr.device
     rp = row_ptr.to(torch.int64)
@@ -43,35 +29,11 @@ def build_tasks(row_ptr, skip_empty=False, pack=False):
     deg = end - begin
     rows = torch.arange(deg.numel(), device=dev, dtype=torch.int64)
     heavy = deg > SEG
-    single = ~heavy & ((deg > 0) if skip_empty else (deg >= 0))
-    packed_tasks = None
-    if pack and not skip_empty and deg.numel() > 0:
-        short = deg <= PACK_MAX_DEG
-        srows = rows[short]
-        if srows.numel():
-            win = (begin[srows] - rp[0]) // PACK_WINDOW
-            # runs of short rows of one window are consecutive rows; cut them every PACK_ROWS rows
-            new_run = torch.ones_like(srows, dtype=torch.bool)
-            new_run[1:] = (win[1:] != win[:-1]) | (srows[1:] != srows[:-1] + 1)
-            run_id = torch.cumsum(new_run, 0) - 1
-            run_first = srows[new_run][run_id]
-            sub = (srows - run_first) // PACK_ROWS
-            new_grp = new_run.clone()
-            new_grp[1:] |= sub[1:] != sub[:-1]
-            first = srows[new_grp]
-            grp_id = torch.cumsum(new_grp, 0) - 1
-            n_rows = torch.bincount(grp_id, minlength=first.numel())
-            last = first + n_rows - 1
-            packed_tasks = torch.stack([first, begin[first], end[last], -n_rows], dim=1)
-            packed_tasks[:, 3] = torch.where(n_rows > 1, -n_rows, torch.full_like(n_rows, -1))
-            single = single & ~short
-    light_rows = rows[single]
+    light_rows = rows[~heavy & ((deg > 0) if skip_empty else (deg >= 0))]
+    order = torch.argsort(deg[light_rows], descending=True, stable=True)
+    light_rows = light_rows[order]
     light = torch.stack([light_rows, begin[light_rows], end[light_rows],
                          torch.full_like(light_rows, -1)], dim=1)
-    if packed_tasks is not None:
-        light = torch.cat([light, packed_tasks], dim=0)
-    order = torch.argsort(light[:, 2] - light[:, 1], descending=True, stable=True)
-    light = light[order]
     h_rows = rows[heavy]
     n_parts = (deg[h_rows] + SEG - 1) // SEG
     slot_base = torch.cumsum(n_parts, 0) - n_parts
@@ -90,18 +52,10 @@ def build_tasks(row_ptr, skip_empty=False, pack=False):
 
 
 class CSRGraph:
-    def __init__(self, row_ptr, col_idx, vals, n_rows, n_cols, col_offset=0, symmetric=False, skip_empty=False,
-                 pack=None):
+    def __init__(self, row_ptr, col_idx, vals, n_rows, n_cols, col_offset=0, symmetric=False, skip_empty=False):
         self.row_ptr, self.col_idx, self.vals = row_ptr, col_idx, vals
         self.n_rows, self.n_cols, self.col_offset = int(n_rows), int(n_cols), int(col_offset)
-        # short rows share tasks (MMREC_SPMM_PACKED) on graphs of short rows (the kNN item graphs, R,
-        # the Baby / Sports / Clothing adjacencies: 8-25 non-zeros per row), unless the list skips
-        # empty rows; graphs of long rows keep the one-row tasks and the 4-CTA kernel
-        if pack is None:
-            nnz = int((row_ptr[-1] - row_ptr[0]).item()) if row_ptr.numel() > 1 else 0
-            pack = PACK_DEFAULT and nnz <= PACK_MEAN_DEG * max(1, int(n_rows))
-        self.packed = bool(pack) and not skip_empty
-        self.tasks, self.slot_base, self.total_parts = build_tasks(row_ptr, skip_empty, self.packed)
+        self.tasks, self.slot_base, self.total_parts = build_tasks(row_ptr, skip_empty)
         self.n_tasks = int(self.tasks.shape[0])
         self.counters = torch.zeros(max(1, self.slot_base.numel()), dtype=torch.int32,
                                     device=row_ptr.device)

@@ -32,7 +32,6 @@ SIGNATURES = {
     "mmrec_spmm_csr_ex_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p,
                                         _f32, _p, _p, _p, _i32, _p]),
     "mmrec_spmm_csr_multi_f32": (C.c_int, [_p, _i32, _i32, _p]),
-    "mmrec_spmm_csr_multi_ex_f32": (C.c_int, [_p, _i32, _i32, _i32, _p]),
     "mmrec_layergcn_cos_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
     "mmrec_bpr_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "mmrec_bpr_bwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),

@@ -44,7 +44,7 @@ def _f32c(t):
 
 
 L2_BYTES = 126 << 20
-SPMM_NARROW, SPMM_STREAM, SPMM_PACKED = 1, 2, 4
+SPMM_NARROW, SPMM_STREAM = 1, 2
 # Measured on the 10M x 2M x 486M graph (profiles/r02_config5_spmm_experiments.txt): the eviction
 # hints change nothing (129.6 vs 130.1 ms for four layers), so they stay off unless asked for.
 _STREAM_DEFAULT = __import__("os").environ.get("MMREC_SPMM_STREAM", "0") == "1"
@@ -62,8 +62,7 @@ def spmm_raw(g: CSRGraph, X, Y=None, acc_in=None, acc_out=None, acc_scale=1.0, c
         raise RuntimeError(f"spmm: X has {X.shape[0]} rows, graph has {g.n_cols} columns")
     if stream_policy is None:
         stream_policy = _STREAM_DEFAULT and cos_ref is None and 4 * d * g.n_cols > L2_BYTES // 2
-    flags = (SPMM_NARROW if (narrow or _NARROW_ALL) else 0) | (SPMM_STREAM if stream_policy else 0) | \
-        (SPMM_PACKED if getattr(g, "packed", False) else 0)
+    flags = (SPMM_NARROW if (narrow or _NARROW_ALL) else 0) | (SPMM_STREAM if stream_policy else 0)
     if flags:
         lib.call("mmrec_spmm_csr_ex_f32", lib.ptr(g.row_ptr), lib.ptr(g.col_idx), lib.ptr(g.vals),
                  lib.ptr(g.tasks), g.n_tasks, lib.ptr(g.slot_base), lib.ptr(g.counters),
@@ -132,8 +131,8 @@ def spmm_multi_raw(graphs, Xs, Ys=None, acc_ins=None, acc_outs=None):
         p.acc_in = lib.ptr(acc_ins[i]) if acc_ins is not None else None
         p.acc_out = lib.ptr(acc_outs[i]) if acc_outs is not None else None
         p.acc_scale = 1.0
-    flags = SPMM_PACKED if any(getattr(g, "packed", False) for g in graphs) else 0
-    lib.call("mmrec_spmm_csr_multi_ex_f32", ctypes.byref(arr), n, d, flags, lib.stream())
+    import ctypes
+    lib.call("mmrec_spmm_csr_multi_f32", ctypes.byref(arr), n, d, lib.stream())
 
 
 class _SpMMMulti(torch.autograd.Function):

@@ -132,46 +132,3 @@ def test_smore_trainer_uses_inkernel_dropout_under_graph_replay():
     assert torch.equal(state, torch.cuda.get_rng_state(0))        # nn.Dropout no longer touches torch's generator
     assert tr.replayed_launches > 0 and np.isfinite(losses).all()
     assert float(m.dropout_counter.item()) > 0
-
-
-# ------------------------------------------------------------------ a6: packed SpMM task lists
-@pytest.mark.parametrize("d", [32, 64, 128, 256])
-def test_packed_spmm_tasks_are_bit_identical_to_one_row_tasks(d):
-    """MMREC_SPMM_PACKED: short consecutive rows share a task; every row is still summed in CSR order, so the
-    packed list reproduces the one-row list bit for bit -- plain, fused layer-sum, LayerGCN cosine epilogue, the
-    R / R^T views (row_ptr slices with a column offset), empty rows, heavy rows, the narrow tiling, the
-    multi-problem launch -- and matches float64."""
-    G, ops = pkg("graph"), pkg("ops")
-    rng = np.random.default_rng(d)
-    n_u, n_i = 900, 400
-    deg = rng.choice([0, 0, 1, 2, 3, 5, 8, 13, 21, 33, 70, 150], size=n_u)
-    users = np.repeat(np.arange(n_u), deg)
-    items = np.concatenate([rng.choice(n_i, size=k, replace=False) for k in deg]) if deg.sum() else np.zeros(0, int)
-    g = G.build_ui_graph(torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), n_u, n_i, "f32")
-    R, Rt = G.ui_blocks(g)
-    for name, base in (("ui", g), ("R", R), ("Rt", Rt)):
-        X = torch.randn(base.n_cols, d, device=DEV)
-        E0 = torch.randn(base.n_rows, d, device=DEV)
-        outs = {}
-        for pack in (False, True):
-            h = G.CSRGraph(base.row_ptr, base.col_idx, base.vals, base.n_rows, base.n_cols,
-                           col_offset=base.col_offset, pack=pack)
-            assert h.packed == pack and (not pack or int((h.tasks[:, 3] < -1).sum()) > 0)
-            Y, acc = torch.empty(base.n_rows, d, device=DEV), torch.empty(base.n_rows, d, device=DEV)
-            ops.spmm_raw(h, X, Y=Y, acc_in=E0, acc_out=acc, acc_scale=0.25)
-            Yc, w, Yp = torch.empty_like(Y), torch.empty(base.n_rows, device=DEV), torch.empty_like(Y)
-            ops.spmm_raw(h, X, Y=Yc, cos_ref=E0, cos_w=w, y_pre=Yp)
-            Yn = torch.empty_like(Y)
-            ops.spmm_raw(h, X, Y=Yn, narrow=True)
-            Y3 = [torch.empty_like(Y) for _ in range(3)]
-            ops.spmm_multi_raw([h, h, h], [X, X * 2, X * 3], Ys=Y3)
-            outs[pack] = (Y, acc, Yc, w, Yp, Yn, *Y3)
-        for a, b in zip(outs[False], outs[True]):
-            assert torch.equal(a, b), name
-        rows, cols, vals = base.to_torch_coo()
-        A = torch.zeros(base.n_rows, base.n_cols, dtype=torch.float64)
-        A.index_put_((torch.from_numpy(rows), torch.from_numpy(cols)), torch.from_numpy(vals).double(), accumulate=True)
-        want = A @ X.double().cpu()
-        got = outs[True][0].double().cpu()
-        assert float((got - want).abs().max() / want.abs().max().clamp_min(1e-6)) < 1e-6
-        assert torch.equal(outs[True][5], outs[True][0]) or d == 32        # narrow tiling: same sums
