@@ -14,9 +14,10 @@ import bench  # noqa: E402
 CASES = [("LayerGCN", "baby", {"is_multimodal_model": False}),
          ("FREEDOM", "sports", {}), ("MGCN", "sports", {}),
          ("SMORE", "clothing", {"embedding_size": 128}), ("SMORE", "sports", {})]
+EXTRA = [("SMORE", "baby", {})]          # the headline config: only on request (A/B runs of env switches)
 only = sys.argv[1:] or None
-for model_name, shape, over in CASES:
-    if only and model_name + ":" + shape not in only:
+for model_name, shape, over in CASES + EXTRA:
+    if (only and model_name + ":" + shape not in only) or (not only and (model_name, shape, over) in EXTRA):
         continue
     torch.cuda.empty_cache()
     env = bench.build_env("cuda:0", model_name=model_name, shape=shape, overrides=over)

@@ -1,10 +1,12 @@
+"""Fused scoring + mask + top-K timing (incl. the merge): default tiling vs MMREC_TOPK_256=0 (one 128-user tile per
+CTA); random tables, realistic train masks are not needed for the timing (the mask cursor is O(history))."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 ops = bench.pkg("ops")
 DEV = "cuda:0"
-def timeit(fn, iters=10):
+def timeit(fn, iters=20):
     for _ in range(3): fn()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -12,8 +14,10 @@ def timeit(fn, iters=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / iters
 gen = torch.Generator().manual_seed(1)
-for (nu, ni, S, d) in [(9130, 7050, 2, 64), (16384, 100000, 1, 64), (17122, 23033, 1, 128), (16384, 100000, 1, 128)]:
+for (nu, ni, d, k) in [(9130, 7050, 64, 50), (16716, 18357, 64, 50), (16384, 100000, 64, 50), (9130, 7050, 64, 20),
+                       (17122, 23033, 128, 50)]:
     ue = torch.randn(nu, d, generator=gen).to(DEV); ie = torch.randn(ni, d, generator=gen).to(DEV)
     users = torch.arange(nu, device=DEV)
-    t = timeit(lambda: ops.score_mask_topk(ue, users, ie, 50, n_splits=S))
-    print(f"dbg={os.environ.get('MMREC_TOPK_DEBUG')} atmem={os.environ.get('MMREC_TOPK_ATMEM')} d={d} U={nu} I={ni} S={S}: {t*1e3:.1f} us", flush=True)
+    S = ops.choose_splits(nu, ni, d, k)
+    t = timeit(lambda: ops.score_mask_topk(ue, users, ie, k))
+    print(f"tile256={os.environ.get('MMREC_TOPK_256', '1')} d={d} K={k} U={nu} I={ni} splits={S}: {t*1e3:.1f} us", flush=True)
