@@ -414,10 +414,6 @@ int mmrec_axpy_multi_f32(float *const *y_host, const float *const *x_host, const
  * Produces `n_splits` partial lists per user (item range split across CTAs) in ws_val/ws_idx
  * ([n_splits, n_users, k]) and merges them into out_val/out_idx ([n_users, k], ids int64).
  * ---------------------------------------------------------------------------------------- */
-/* Users per CTA of the kernel mmrec_score_mask_topk_f32 picks for (d, k): 256 for d <= 64 when 256
- * K-entry heaps fit shared memory (two 128-user tiles per CTA, eight top-K warps), else 128. Callers
- * size n_splits so that ceil(n_users / tile) * n_splits is about one wave of SMs. */
-int mmrec_score_topk_user_tile(int32_t d, int32_t k);
 int mmrec_score_mask_topk_f32(const float *user_emb, const int64_t *users, int32_t n_users,
                               const float *item_emb, int32_t n_items, int32_t item_offset,
                               int32_t d, const int32_t *mask_rowptr, const int32_t *mask_cols,

@@ -64,12 +64,6 @@ struct GemmArgs {
   double *sumsq_partial;            // optional: per-CTA sum of the updated parameters' squares
   int debug;                        // MMREC_TA_DEBUG (timing experiments only): 1 = no arithmetic, 2 = no copies
   int act;                          // EPI_STORE, no split-K: 0 = none, 1 = tanh, 2 = sigmoid after the bias
-  // split-K with the reduction inside the launch: every CTA stores its partial tile to its slab, the
-  // LAST CTA of a row tile to arrive (red_counters[blockIdx.x], self-resetting) adds the slabs in split
-  // order (+ bias) into red_out -- bit-identical to the separate reduce kernel, one launch fewer
-  int *red_counters;
-  float *red_out;
-  const float *red_bias;
   int mt_per_cta;                   // consecutive 128-row tiles walked by one CTA (0 / 1: one). With more row tiles
                                     // than SMs a CTA keeps its pipeline full across tiles instead of paying the
                                     // fill (TMEM allocation, first DRAM round trips, drain) once per 64 KB of rows
@@ -121,12 +115,6 @@ struct Block {
 };
 
 enum { EPI_STORE = 0, EPI_ADAM = 1, EPI_SUMSQ = 2 };
-
-// Arrival counters of the in-launch split-K reduction (zero at module load, self-resetting). Every
-// launch takes gridDim.x consecutive counters at a rotating offset, so launches that overlap on
-// different streams (the text projection runs beside the image projection) never share one.
-constexpr int kRedPool = 1 << 15;
-__device__ int g_red_counters[kRedPool];
 
 template <int NT, int EPI_MODE = EPI_STORE>
 struct GCfg {
@@ -437,59 +425,6 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
       }
       __syncwarp();
     }
-    if constexpr (EPI == EPI_STORE) {
-      if (g.red_counters != nullptr && n_tiles > 0) {
-        // ---- split-K: the last CTA of this row tile adds the slabs ------------------------------
-        volatile int *last_flag = reinterpret_cast<volatile int *>(tmem_slot + 2);
-        __threadfence();                                       // this thread's partial stores -> device scope
-        asm volatile("bar.sync 9, 128;" ::: "memory");
-        if (tid == 0) {
-          const int arrived = atomicAdd(g.red_counters + blockIdx.x, 1);
-          const int last = arrived == (int)gridDim.y - 1;
-          if (last) g.red_counters[blockIdx.x] = 0;            // ready for the next launch that gets this slot
-          *last_flag = last;
-        }
-        asm volatile("bar.sync 9, 128;" ::: "memory");
-        if (*last_flag) {
-          __threadfence();
-          // region of this CTA in the stored matrix: rows x [c0, c1) of a row-major [., ldc] array
-          const int r_end = TRANS_OUT ? g.N : min(g.M, m0 + kBM), r_begin = TRANS_OUT ? 0 : m0;
-          const int c_begin = TRANS_OUT ? m0 : 0, c_end = TRANS_OUT ? min(g.M, m0 + kBM) : g.N;
-          const int w4 = (c_end - c_begin) / 4;                // widths are multiples of 4 (checked by the host)
-          const int n4 = (r_end - r_begin) * w4, S = gridDim.y;
-          for (int i0 = tid; i0 < n4; i0 += 128 * 4) {
-            float4 v[4];
-            size_t off[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + u * 128;
-              off[u] = i < n4 ? (size_t)(r_begin + i / w4) * g.ldc + c_begin + (i % w4) * 4 : 0;
-              v[u] = i < n4 ? __ldcg(reinterpret_cast<const float4 *>(g.C + off[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            for (int z = 1; z < S; ++z) {
-              float4 w[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                w[u] = i0 + u * 128 < n4 ? __ldcg(reinterpret_cast<const float4 *>(g.C + (size_t)z * g.slab + off[u]))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) { v[u].x += w[u].x; v[u].y += w[u].y; v[u].z += w[u].z; v[u].w += w[u].w; }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + u * 128;
-              if (i < n4) {
-                if (g.red_bias != nullptr) {                   // bias of the stored matrix's columns
-                  const float4 b = ldg4(g.red_bias + c_begin + (i % w4) * 4);
-                  v[u].x += b.x; v[u].y += b.y; v[u].z += b.z; v[u].w += b.w;
-                }
-                *reinterpret_cast<float4 *>(g.red_out + off[u]) = v[u];
-              }
-            }
-          }
-        }
-      }
-    }
     if constexpr (EPI == EPI_ADAM) bulk_wait_all();          // this thread's last stores are performed
     if constexpr (EPI != EPI_STORE) {
       // EPI_ADAM: sum of the updated parameters' squares of this CTA -- the mirror-gradient step size
@@ -528,17 +463,7 @@ int launch_tc05(const GemmArgs &g, int k_splits, int n_chunks, cudaStream_t stre
   }
   const int m_tiles = (g.M + kBM - 1) / kBM, mt_per = g.mt_per_cta > 1 ? g.mt_per_cta : 1;
   dim3 grid((m_tiles + mt_per - 1) / mt_per, k_splits, n_chunks);
-  GemmArgs ga = g;
-  if (ga.red_out != nullptr) {
-    static int next = 0;                                    // host calls are serialised by the caller (GIL)
-    if ((int)grid.x > kRedPool || mt_per != 1 || n_chunks != 1) return 1;
-    if (next + (int)grid.x > kRedPool) next = 0;
-    static int *pool = nullptr;                             // resolved by the first (eager) call
-    if (pool == nullptr) MMREC_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&pool), g_red_counters));
-    ga.red_counters = pool + next;
-    next += grid.x;
-  }
-  kern<<<grid, kThreadsG, smem, stream>>>(ga, TmaMaps3{});
+  kern<<<grid, kThreadsG, smem, stream>>>(g, TmaMaps3{});
   MMREC_CHECK_LAUNCH("gemm_tc05_kernel");
   return MMREC_OK;
 }
@@ -617,16 +542,8 @@ int gemm_tc05_splits(int M, int N, int K, int kind) {
 }
 
 // Returns MMREC_OK, a negative error, or 1 when the shape is not covered.
-static bool fused_splitk() {   // read per call: the A/B test toggles it inside one process
-  const char *e = getenv("MMREC_GEMM_FUSED_SPLITK");
-  return !(e && atoi(e) == 0);
-}
-
-// *reduced = 1 when a split-K product was also reduced (+ bias) into C by the launch itself.
 int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcontig, const float *bias, float *C,
-                       int M, int N, int K, int splits, float *ws, cudaStream_t stream, int act = 0,
-                       int *reduced = nullptr) {
-  if (reduced) *reduced = 0;
+                       int M, int N, int K, int splits, float *ws, cudaStream_t stream, int act = 0) {
   const int kind = gemm_tc05_kind(M, N, K, a_kcontig, b_kcontig);
   if (kind == 0) return 1;
   if (act != 0 && (kind != 1 || splits != 1)) return 1;    // the activation rides in the store epilogue only
@@ -643,25 +560,16 @@ int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcon
   auto tiles_per_cta = [](int m_tiles, int other) {
     return other == 1 && m_tiles > kNumSMs ? (m_tiles + kNumSMs - 1) / kNumSMs : 1;
   };
-  // in-launch reduction: the stored matrix is row-major [., N] in both kinds; its bias (kind 1 only: the
-  // Linear bias) indexes the columns; kind 2 with a bias keeps the separate reduce kernel
-  const bool fuse = splits > 1 && fused_splitk() && reduced != nullptr && N % 4 == 0 && (kind == 1 || bias == nullptr) &&
-                    (kind == 1 || M % 4 == 0);
-  if (fuse) { g.red_out = C; g.red_bias = bias; }
   if (kind == 1) {
     g.A = A; g.lda = K; g.B = B; g.ldb = K; g.C = out; g.ldc = N; g.M = M; g.N = N; g.K = K; g.nt_per_cta = 1;
     g.mt_per_cta = tiles_per_cta((M + kBM - 1) / kBM, k_splits);
-    const int rc = launch_tc05_nt<false, false, false>(N, g, k_splits, 1, stream);
-    if (fuse && rc == MMREC_OK) *reduced = 1;
-    return rc;
+    return launch_tc05_nt<false, false, false>(N, g, k_splits, 1, stream);
   }
   if (kind == 2) {
     // C^T [N, M] = B^T [N, K] * A [K, M]: UMMA A = caller's B (MN-major), UMMA B = caller's A (MN-major)
     g.A = B; g.lda = N; g.B = A; g.ldb = M; g.C = out; g.ldc = N; g.M = N; g.N = M; g.K = K; g.nt_per_cta = 1;
     if (bias != nullptr && splits == 1) return 1;      // bias indexes the other axis here
-    const int rc = launch_tc05_nt<true, true, true>(M, g, k_splits, 1, stream);
-    if (fuse && rc == MMREC_OK) *reduced = 1;
-    return rc;
+    return launch_tc05_nt<true, true, true>(M, g, k_splits, 1, stream);
   }
   // kind 3
   if (splits != 1) return 1;

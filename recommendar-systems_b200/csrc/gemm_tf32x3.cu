@@ -234,7 +234,7 @@ int launch(const float *A, const float *B, const float *bias, float *C, float *w
 int gemm_tc05_kind(int M, int N, int K, int a_kcontig, int b_kcontig);
 int gemm_tc05_splits(int M, int N, int K, int kind);
 int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcontig, const float *bias, float *C,
-                       int M, int N, int K, int splits, float *ws, cudaStream_t stream, int act, int *reduced);
+                       int M, int N, int K, int splits, float *ws, cudaStream_t stream, int act);
 static bool tc05_enabled() {
   static const bool on = !(getenv("MMREC_GEMM_TC") && atoi(getenv("MMREC_GEMM_TC")) == 0);
   return on;
@@ -273,10 +273,9 @@ extern "C" int mmrec_gemm_tf32x3_f32(const float *A, int32_t a_kcontig, const fl
                 "gemm: contiguous dimensions must be multiples of 4 floats");
   MMREC_REQUIRE(splits == 1 || ws, MMREC_E_WORKSPACE, "gemm: split-K needs a workspace of splits*M*N floats");
   if (tc05_enabled()) {     // tcgen05 kernel for the table-sized projections; 1 = shape not covered
-    int reduced = 0;        // 1: the launch summed its split-K slabs (+ bias) into C itself
-    const int rc = gemm_tc05_dispatch(A, a_kcontig, B, b_kcontig, bias, C, M, N, K, splits, ws, stream, 0, &reduced);
+    const int rc = gemm_tc05_dispatch(A, a_kcontig, B, b_kcontig, bias, C, M, N, K, splits, ws, stream, 0);
     if (rc <= 0) {
-      if (rc == MMREC_OK && splits > 1 && !reduced) {
+      if (rc == MMREC_OK && splits > 1) {
         const int64_t mn = (int64_t)M * N;
         splitk_reduce_kernel<<<(unsigned)((mn / 4 + kThreads - 1) / kThreads), kThreads, 0, stream>>>(ws, bias, C, mn,
                                                                                                      N, splits);
@@ -333,7 +332,7 @@ extern "C" int mmrec_linear_act_tc_f32(const float *x, const float *W, const flo
                 "linear_act_tc: operands must be 16-byte aligned");
   MMREC_REQUIRE(mmrec_linear_act_tc_supported(M, K, N), MMREC_E_BADARG,
                 "linear_act_tc: shape %d x %d -> %d is not covered by the tcgen05 kernel without split-K", M, K, N);
-  const int rc = gemm_tc05_dispatch(x, 1, W, 1, b, y, M, N, K, 1, nullptr, (cudaStream_t)stream_, act, nullptr);
+  const int rc = gemm_tc05_dispatch(x, 1, W, 1, b, y, M, N, K, 1, nullptr, (cudaStream_t)stream_, act);
   if (rc > 0) {
     set_error("linear_act_tc: dispatch refused the shape");
     return MMREC_E_BADARG;

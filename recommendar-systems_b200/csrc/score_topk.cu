@@ -193,12 +193,9 @@ int score_topk_tc_dispatch(const float *user_emb, const int64_t *users, int n_us
                            int n_items, int item_offset, int d, const int32_t *mask_rowptr,
                            const int32_t *mask_cols, int k, int n_splits, float *ws_val, int32_t *ws_idx,
                            cudaStream_t stream);   // score_topk_tc.cu
-int score_topk_tc_user_tile(int d, int k);                 // score_topk_tc.cu
 }  // namespace mmrec
 
 using namespace mmrec;
-
-extern "C" int mmrec_score_topk_user_tile(int32_t d, int32_t k) { return score_topk_tc_user_tile(d, k); }
 
 extern "C" int mmrec_topk_merge(const float *vals, const int32_t *idx, int32_t n_lists, int32_t n_users,
                                 int32_t k, float *out_val, int64_t *out_idx, void *stream) {

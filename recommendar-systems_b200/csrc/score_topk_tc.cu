@@ -23,8 +23,6 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
-#include <algorithm>
-
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -398,357 +396,6 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const int64_t *__restri
   }
 }
 
-// ================================================================================================
-// Two user tiles per CTA (d <= 64): 256 users, EIGHT epilogue warps.
-// The epilogue of the kernel above is one warp per scheduler walking a chain of dependent
-// shared-memory latencies (ncu: issue slots 33 % busy, tensor pipe 9 %): the SM idles while a heap
-// update waits. Here a CTA owns two 128-user tiles: both tiles' hi / lo A operands live in TMEM
-// (columns [256, 256 + 4d)), every 64-item stage in shared memory feeds two MMA groups (the item
-// rows are split and staged once for 256 users instead of once per 128), each tile has two
-// 64-column accumulators, and warps 0-3 / 4-7 run the top-K of tile 0 / 1 concurrently -- two
-// independent latency chains per scheduler. For the same number of CTAs the item range of a CTA
-// halves (the caller doubles n_splits: mmrec_score_topk_user_tile), so a lane also performs
-// K ln(N/K) heap updates over half as many candidates. Heap and pending ids are 16-bit offsets into
-// the CTA's item range (<= 65536 items per split), which is what lets 256 heaps + pending lists fit
-// beside the stages.
-constexpr int kTile2 = 256;       // users per CTA
-constexpr int kThreads2 = 416;    // 8 epilogue + 4 producer + 1 MMA warp
-
-template <int D>
-struct Cfg2 {
-  static constexpr int KB = D / 32;
-  static constexpr int STAGES = D <= 32 ? 4 : 2;
-  static constexpr uint32_t B_HALF = KB * kTileN * 128;
-  static constexpr uint32_t STAGE = 2 * B_HALF;
-  static constexpr uint32_t ACC_COLS = 2 * 2 * kTileN;       // two tiles x two buffers
-  static constexpr uint32_t A_COL = ACC_COLS;                // tile u: hi at A_COL + 2 D u, lo at + D
-  static constexpr uint32_t TMEM_COLS = 512;
-  static constexpr uint32_t OFF_HEAP = STAGES * STAGE;
-};
-
-struct Heap16 {           // one user's K-entry 8-ary heap: column `u` of [k][256] arrays, root = worst kept
-  float *v;
-  uint16_t *id;
-  __device__ __forceinline__ void sift_down(int pos, int lim, float sc, int lid) const {
-    for (;;) {
-      const int c0 = kAry * pos + 1;
-      if (c0 >= lim) break;
-      float cv[kAry];
-      int ci[kAry];
-#pragma unroll
-      for (int j = 0; j < kAry; ++j) {
-        const bool in = c0 + j < lim;
-        cv[j] = in ? v[(c0 + j) * kTile2] : CUDART_INF_F;
-        ci[j] = in ? (int)id[(c0 + j) * kTile2] : 0;
-      }
-      const float wv = fminf(fminf(fminf(cv[0], cv[1]), fminf(cv[2], cv[3])), fminf(fminf(cv[4], cv[5]), fminf(cv[6], cv[7])));
-      int t[kAry];
-#pragma unroll
-      for (int j = 0; j < kAry; ++j) t[j] = cv[j] == wv ? ci[j] : -1;
-      const int wi = max(max(max(t[0], t[1]), max(t[2], t[3])), max(max(t[4], t[5]), max(t[6], t[7])));
-      int w = 0;
-#pragma unroll
-      for (int j = 1; j < kAry; ++j) w = t[j] == wi ? j : w;
-      w = t[0] == wi ? 0 : w;
-      if (!Better::worse(wv, wi, sc, lid)) break;
-      v[pos * kTile2] = wv;
-      id[pos * kTile2] = (uint16_t)wi;
-      pos = c0 + w;
-    }
-    v[pos * kTile2] = sc;
-    id[pos * kTile2] = (uint16_t)lid;
-  }
-  __device__ __forceinline__ void sift_up(int pos, float sc, int lid) const {
-    while (pos > 0) {
-      const int par = (pos - 1) / kAry;
-      const float pv = v[par * kTile2];
-      const int pi = id[par * kTile2];
-      if (!Better::worse(sc, lid, pv, pi)) break;
-      v[pos * kTile2] = pv;
-      id[pos * kTile2] = (uint16_t)pi;
-      pos = par;
-    }
-    v[pos * kTile2] = sc;
-    id[pos * kTile2] = (uint16_t)lid;
-  }
-};
-
-template <int D>
-__global__ void __launch_bounds__(kThreads2, 1)
-score_topk_tc256_kernel(const float *__restrict__ user_emb, const int64_t *__restrict__ users, int n_users,
-                        const float *__restrict__ item_emb, int n_items, int item_offset,
-                        const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_cols, int k,
-                        int items_per_split, float *__restrict__ ws_val, int32_t *__restrict__ ws_idx, int pend_cap) {
-  using C = Cfg2<D>;
-  static_assert(C::A_COL + 4 * D <= C::TMEM_COLS, "two user tiles do not fit beside the accumulators");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float *h_val = reinterpret_cast<float *>(smem + C::OFF_HEAP);                          // [k][256]
-  float *p_val = h_val + (size_t)k * kTile2;                                             // [pend_cap][256]
-  uint16_t *h_idx = reinterpret_cast<uint16_t *>(p_val + (size_t)pend_cap * kTile2);     // [k][256]
-  uint16_t *p_idx = h_idx + (size_t)k * kTile2;                                          // [pend_cap][256]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(
-      smem + ((C::OFF_HEAP + (size_t)(k + pend_cap) * kTile2 * 6 + 7) & ~(size_t)7));
-  uint64_t *full = bars, *empty = bars + C::STAGES, *tfull = bars + 2 * C::STAGES, *tempty = tfull + 4;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 4);
-
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int j_begin = blockIdx.y * items_per_split;
-  const int j_end = min(n_items, j_begin + items_per_split);
-  const int n_tiles = (j_end - j_begin + kTileN - 1) / kTileN;
-  const uint32_t smem_base = smem_u32(smem);
-
-  if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 64); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 4; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }   // index = tile * 2 + buffer
-    fence_barrier_init();
-  }
-  if (warp == 12) tmem_alloc(tmem_slot, C::TMEM_COLS);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-
-  // ---- both user tiles -> hi/lo A operands in TMEM (thread = user row; lane quadrant = warp % 4) ----
-  const int b_user = blockIdx.x * kTile2 + tid;
-  const bool live = tid < kTile2 && b_user < n_users;
-  const int ut = warp >> 2;                                  // user tile of this epilogue warp
-  if (tid < kTile2) {
-    const uint32_t a_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL + ut * 2 * D;
-    const float *src = live ? user_emb + (size_t)users[b_user] * D : nullptr;
-#pragma unroll
-    for (int c32 = 0; c32 < D / 32; ++c32) {
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        float4 v = live ? ldg4(src + c32 * 32 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f), h, l;
-        split_tf32x4(v, h, l);
-        hi[c4 * 4 + 0] = __float_as_uint(h.x); hi[c4 * 4 + 1] = __float_as_uint(h.y);
-        hi[c4 * 4 + 2] = __float_as_uint(h.z); hi[c4 * 4 + 3] = __float_as_uint(h.w);
-        lo[c4 * 4 + 0] = __float_as_uint(l.x); lo[c4 * 4 + 1] = __float_as_uint(l.y);
-        lo[c4 * 4 + 2] = __float_as_uint(l.z); lo[c4 * 4 + 3] = __float_as_uint(l.w);
-      }
-      tmem_st_32x32b_x32(a_row + c32 * 32, hi);
-      tmem_st_32x32b_x32(a_row + D + c32 * 32, lo);
-    }
-    tmem_st_wait();
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-
-  if (warp >= 8 && warp < 12) {
-    // =============================== producers (two independent groups, one tile in flight each) ====
-    constexpr int GT = 64;
-    constexpr int VB = kTileN * (D / 4) / GT;                // float4 per thread and tile (16 for d = 64)
-    const int grp = (tid - 256) / GT, ptid = (tid - 256) % GT;
-    for (int t = grp; t < n_tiles; t += 2) {
-      const int j0 = j_begin + t * kTileN;
-      const int s = t % C::STAGES;
-      uint8_t *stage = smem + s * C::STAGE;
-      float4 v[VB];
-#pragma unroll
-      for (int i = 0; i < VB; ++i) {
-        const int idx = ptid + GT * i, row = idx / (D / 4), c4 = idx % (D / 4);
-        v[i] = (j0 + row < j_end) ? ldg4(item_emb + (size_t)(j0 + row) * D + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      mbar_wait(empty + s, ((t / C::STAGES) & 1) ^ 1);
-#pragma unroll
-      for (int i = 0; i < VB; ++i) {
-        const int idx = ptid + GT * i, row = idx / (D / 4), c4 = idx % (D / 4);
-        float4 hi, lo;
-        split_tf32x4(v[i], hi, lo);
-        const uint32_t off = (c4 / 8) * (kTileN * 128) + sw128_off(row, c4 % 8);
-        *reinterpret_cast<float4 *>(stage + off) = hi;
-        *reinterpret_cast<float4 *>(stage + C::B_HALF + off) = lo;
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(full + s);
-    }
-  } else if (warp == 12) {
-    // =============================== MMA issuer: every stage feeds both user tiles ==================
-    constexpr uint32_t idesc = idesc_tf32(kTileM, kTileN, false, false);
-    for (int t = 0; t < n_tiles; ++t) {
-      const int s = t % C::STAGES, b = t & 1;
-      mbar_wait(full + s, (t / C::STAGES) & 1);
-      const uint64_t b_hi = smem_desc_sw128(smem_base + s * C::STAGE, 16, 1024);
-      const uint64_t b_lo = b_hi + (C::B_HALF >> 4);
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        mbar_wait(tempty + u * 2 + b, ((t >> 1) & 1) ^ 1);
-        fence_after_sync();
-        const uint32_t d_tmem = tmem_base + u * (2 * kTileN) + b * kTileN;
-        const uint32_t at_hi = tmem_base + C::A_COL + u * 2 * D, at_lo = at_hi + D;
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint64_t b0 = pass == 1 ? b_lo : b_hi;
-#pragma unroll
-          for (int kb = 0; kb < C::KB; ++kb)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t bd = b0 + ((kb * (kTileN * 128) + ks * 32) >> 4);
-              const uint32_t at = (pass == 0 ? at_lo : at_hi) + kb * 32 + ks * 8;
-              if (elect_one()) umma_tf32_ts(d_tmem, at, bd, idesc, (pass | kb | ks) != 0);
-            }
-        }
-        if (elect_one()) {
-          if (u == 1) umma_commit(empty + s);    // both tiles have read the stage
-          umma_commit(tfull + u * 2 + b);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // =============================== epilogue: mask + top-K (warps 0-3: tile 0, 4-7: tile 1) ========
-    int mp = 0, mend = 0, next_masked = INT_MAX;
-    const int g_base = item_offset + j_begin;                 // global id of local id 0
-    if (live && mask_rowptr != nullptr) {
-      int lo = mask_rowptr[b_user];
-      mend = mask_rowptr[b_user + 1];
-      int hi = mend;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (mask_cols[mid] < g_base) lo = mid + 1; else hi = mid;
-      }
-      mp = lo;
-      if (mp < mend) next_masked = mask_cols[mp];
-    }
-    int cnt = 0, pend = 0;
-    float thr = -CUDART_INF_F;
-    const Heap16 heap{h_val + tid, h_idx + tid};
-    float *pv = p_val + tid;
-    uint16_t *pi = p_idx + tid;
-
-    auto flush = [&]() {
-      for (int i = 0; i < pend; ++i) {
-        float sc = pv[i * kTile2];
-        if (!(sc > thr)) continue;
-        const int lid = pi[i * kTile2];
-        const int gid = g_base + lid;
-        while (next_masked < gid) {
-          ++mp;
-          next_masked = mp < mend ? mask_cols[mp] : INT_MAX;
-        }
-        if (gid == next_masked) sc = -1e10f;                      // trainer.py:524
-        if (cnt < k) {
-          heap.sift_up(cnt++, sc, lid);
-          if (cnt == k) thr = heap.v[0];
-        } else if (sc > thr) {
-          heap.sift_down(0, k, sc, lid);
-          thr = heap.v[0];
-        }
-      }
-      pend = 0;
-      __syncwarp();
-    };
-
-    for (int t = 0; t < n_tiles; ++t) {
-      const int b = t & 1;
-      mbar_wait(tfull + ut * 2 + b, (t >> 1) & 1);
-      fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ut * (2 * kTileN) + b * kTileN;
-#pragma unroll
-      for (int half = 0; half < kTileN / kChunk; ++half) {
-        uint32_t r[kChunk];
-        tmem_ld_32x32b_x32(taddr + half * kChunk, r);
-        tmem_ld_wait();
-        if (half == kTileN / kChunk - 1) {
-          fence_before_sync();
-          mbar_arrive(tempty + ut * 2 + b);
-        }
-        if (__any_sync(0xffffffffu, pend > pend_cap - kChunk)) flush();
-        const int l0 = t * kTileN + half * kChunk;                // local id of column 0 of this chunk
-        const int valid = min(kChunk, j_end - j_begin - l0);
-        if (valid < kChunk) {
-#pragma unroll
-          for (int c = 0; c < kChunk; ++c)
-            if (c >= valid) r[c] = __float_as_uint(-CUDART_INF_F);
-        }
-        float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;      // four short chains instead of one of 32
-#pragma unroll
-        for (int c = 0; c < kChunk; c += 4) {
-          m0 = fmaxf(m0, __uint_as_float(r[c]));
-          m1 = fmaxf(m1, __uint_as_float(r[c + 1]));
-          m2 = fmaxf(m2, __uint_as_float(r[c + 2]));
-          m3 = fmaxf(m3, __uint_as_float(r[c + 3]));
-        }
-        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        if (__any_sync(0xffffffffu, live && m > thr)) {
-          const float lim = live ? thr : CUDART_INF_F;
-          int off = pend * kTile2;
-#pragma unroll
-          for (int c = 0; c < kChunk; ++c) {
-            const float sc = __uint_as_float(r[c]);
-            if (sc > lim) {
-              pv[off] = sc;
-              pi[off] = (uint16_t)(l0 + c);
-              off += kTile2;
-            }
-          }
-          pend = off / kTile2;
-        }
-        __syncwarp();
-      }
-    }
-    flush();
-    if (live) {
-      for (int size = cnt; size > 1; --size) {
-        const float lv = heap.v[(size - 1) * kTile2];
-        const int li = heap.id[(size - 1) * kTile2];
-        heap.v[(size - 1) * kTile2] = heap.v[0];
-        heap.id[(size - 1) * kTile2] = heap.id[0];
-        heap.sift_down(0, size - 1, lv, li);
-      }
-      float *ov = ws_val + ((size_t)blockIdx.y * n_users + b_user) * k;
-      int32_t *oi = ws_idx + ((size_t)blockIdx.y * n_users + b_user) * k;
-      for (int t = 0; t < k; ++t) {
-        ov[t] = t < cnt ? heap.v[t * kTile2] : -CUDART_INF_F;
-        oi[t] = t < cnt ? g_base + (int)heap.id[t * kTile2] : INT_MAX;
-      }
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 12) {
-    fence_after_sync();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-inline bool tile256_enabled() {   // A/B switch (default on)
-  static int m = getenv("MMREC_TOPK_256") ? atoi(getenv("MMREC_TOPK_256")) : 1;
-  return m != 0;
-}
-
-// shared-memory need of the 256-user kernel for (d, k) with the smallest useful pending list; 0 = does not fit
-template <int D>
-size_t tc256_fixed_smem(int k) {
-  using C = Cfg2<D>;
-  return 1024 + C::OFF_HEAP + (size_t)k * kTile2 * 6 + (2 * C::STAGES + 8) * 8 + 32;
-}
-template <int D>
-bool tc256_fits(int k, int items_per_split) {
-  return items_per_split <= 65536 && tc256_fixed_smem<D>(k) + (size_t)(kChunk + 8) * kTile2 * 6 <= 227 * 1024;
-}
-
-template <int D>
-int launch_tc256(const float *user_emb, const int64_t *users, int n_users, const float *item_emb, int n_items,
-                 int item_offset, const int32_t *mask_rowptr, const int32_t *mask_cols, int k, int n_splits,
-                 float *ws_val, int32_t *ws_idx, cudaStream_t stream) {
-  const int items_per_split = ((n_items + n_splits - 1) / n_splits + kTileN - 1) / kTileN * kTileN;
-  if (!tc256_fits<D>(k, items_per_split)) return 1;
-  const size_t fixed = tc256_fixed_smem<D>(k), cap = 227 * 1024;
-  const int pend_cap = (int)std::min((size_t)64, (cap - fixed) / (kTile2 * 6));
-  const size_t smem = fixed + (size_t)pend_cap * kTile2 * 6;
-  MMREC_CUDA(cudaFuncSetAttribute(score_topk_tc256_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((n_users + kTile2 - 1) / kTile2, n_splits);
-  score_topk_tc256_kernel<D><<<grid, kThreads2, smem, stream>>>(user_emb, users, n_users, item_emb, n_items, item_offset,
-                                                               mask_rowptr, mask_cols, k, items_per_split, ws_val,
-                                                               ws_idx, pend_cap);
-  MMREC_CHECK_LAUNCH("score_topk_tc256_kernel");
-  return MMREC_OK;
-}
-
 inline int dbg_mode() {
   static int m = getenv("MMREC_TOPK_DEBUG") ? atoi(getenv("MMREC_TOPK_DEBUG")) : 0;
   return m;
@@ -789,13 +436,6 @@ int score_topk_tc_dispatch(const float *user_emb, const int64_t *users, int n_us
                            cudaStream_t stream) {
 #define MMREC_TC(D_, T_) launch_tc<D_, T_>(user_emb, users, n_users, item_emb, n_items, item_offset, mask_rowptr, \
                                             mask_cols, k, n_splits, ws_val, ws_idx, stream)
-  if (tile256_enabled() && (d == 32 || d == 64)) {
-    const int rc = d == 64 ? launch_tc256<64>(user_emb, users, n_users, item_emb, n_items, item_offset, mask_rowptr,
-                                              mask_cols, k, n_splits, ws_val, ws_idx, stream)
-                           : launch_tc256<32>(user_emb, users, n_users, item_emb, n_items, item_offset, mask_rowptr,
-                                              mask_cols, k, n_splits, ws_val, ws_idx, stream);
-    if (rc != 1) return rc;        // 1 = K or the item range too large for this tiling: 128-user kernel below
-  }
   switch (d) {
     case 32: return MMREC_TC(32, false);
     case 64: return a_tmem_64() ? MMREC_TC(64, true) : MMREC_TC(64, false);
@@ -803,13 +443,6 @@ int score_topk_tc_dispatch(const float *user_emb, const int64_t *users, int n_us
     default: return 1;
   }
 #undef MMREC_TC
-}
-
-// users per CTA of the kernel mmrec_score_mask_topk_f32 will pick for (d, k) when every split holds at most
-// 65536 items (callers size n_splits with it: mmrec_score_topk_user_tile)
-int score_topk_tc_user_tile(int d, int k) {
-  if (tile256_enabled() && ((d == 64 && tc256_fits<64>(k, 1)) || (d == 32 && tc256_fits<32>(k, 1)))) return kTile2;
-  return kTileM;
 }
 
 }  // namespace mmrec

@@ -97,7 +97,6 @@ SIGNATURES = {
     "mmrec_row_normalize_f32": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "mmrec_row_topk_f32": (C.c_int, [_p, _i32, _i32, _i64, _i32, _p, _p, _p]),
     "mmrec_knn_weights_f32": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
-    "mmrec_score_topk_user_tile": (C.c_int, [_i32, _i32]),
     "mmrec_score_mask_topk_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _i32, _p, _p, _i32, _i32,
                                             _p, _p, _p, _p, _p]),
     "mmrec_score_mask_topk_simt_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _i32, _p, _p, _i32, _i32,

@@ -1154,12 +1154,10 @@ def knn_graph(feat, k, mode, neighbors=None):
 
 
 # -------------------------------------------------------------------------------- score + top-K
-def choose_splits(n_users, n_items, d=None, k=None):
+def choose_splits(n_users, n_items):
     """Item-range splits so that (user tiles x splits) is close to one wave of 148 CTAs (the
-    tensor-core kernel runs one CTA of 128 or 256 users per SM: mmrec_score_topk_user_tile);
-    never fewer than 256 items per split."""
-    tile = 128 if d is None or k is None else int(lib.load().mmrec_score_topk_user_tile(int(d), int(k)))
-    tiles = (n_users + tile - 1) // tile
+    tensor-core kernel runs one 128-user CTA per SM); never fewer than 256 items per split."""
+    tiles = (n_users + 127) // 128
     want = max(1, 148 // tiles)
     return int(max(1, min(want, 32, (n_items + 255) // 256)))
 
@@ -1175,7 +1173,7 @@ def score_mask_topk(user_emb, users, item_emb, k, mask_rowptr=None, mask_cols=No
     n, n_items, d = users.numel(), item_emb.shape[0], item_emb.shape[1]
     _check_ids(users, user_emb.shape[0], "score_mask_topk users")
     dev = user_emb.device
-    S = n_splits or choose_splits(n, n_items, None if simt else d, k)
+    S = n_splits or choose_splits(n, n_items)
     ws_val = torch.empty(S, n, k, dtype=torch.float32, device=dev)
     ws_idx = torch.empty(S, n, k, dtype=torch.int32, device=dev)
     out_val = torch.empty(n, k, dtype=torch.float32, device=dev)

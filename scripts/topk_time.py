@@ -18,6 +18,6 @@ for (nu, ni, d, k) in [(9130, 7050, 64, 50), (16716, 18357, 64, 50), (16384, 100
                        (17122, 23033, 128, 50)]:
     ue = torch.randn(nu, d, generator=gen).to(DEV); ie = torch.randn(ni, d, generator=gen).to(DEV)
     users = torch.arange(nu, device=DEV)
-    S = ops.choose_splits(nu, ni, d, k)
+    S = ops.choose_splits(nu, ni)
     t = timeit(lambda: ops.score_mask_topk(ue, users, ie, k))
     print(f"tile256={os.environ.get('MMREC_TOPK_256', '1')} d={d} K={k} U={nu} I={ni} splits={S}: {t*1e3:.1f} us", flush=True)

@@ -132,51 +132,3 @@ def test_smore_trainer_uses_inkernel_dropout_under_graph_replay():
     assert torch.equal(state, torch.cuda.get_rng_state(0))        # nn.Dropout no longer touches torch's generator
     assert tr.replayed_launches > 0 and np.isfinite(losses).all()
     assert float(m.dropout_counter.item()) > 0
-
-
-# ------------------------------------------------------------------ a8: split-K reduced inside the GEMM launch
-@pytest.mark.parametrize("M,K,N", [(7050, 4096, 64), (7050, 384, 64), (23033, 4096, 128), (1500, 640, 32)])
-def test_gemm_split_k_reduced_in_launch_is_bit_identical(M, K, N, monkeypatch):
-    """The tcgen05 projection GEMMs (forward y = x W^T + b, dW = dy^T x) with split-K: the last CTA of
-    a row tile adds the K-split slabs in split order (+ bias) inside the launch. Same sums in the same
-    order as the separate reduce kernel (MMREC_GEMM_FUSED_SPLITK=0): bit-identical, also when calls
-    repeat (self-resetting counters) and overlap on two streams; and equal to float64."""
-    ops = pkg("ops")
-    gen = torch.Generator().manual_seed(M + K)
-    x = torch.randn(M, K, generator=gen).to(DEV)
-    W = torch.randn(N, K, generator=gen).to(DEV) / K ** 0.5
-    b = torch.randn(N, generator=gen).to(DEV)
-    dy = torch.randn(M, N, generator=gen).to(DEV)
-    L = pkg("lib").load()
-    assert L.mmrec_gemm_splits(M, N, K, 1, 1) > 1 or L.mmrec_gemm_splits(N, K, M, 0, 0) > 1
-
-    def run():
-        y = ops.gemm(x, True, W, True, M, N, K, bias=b)              # forward
-        dW = ops.gemm(dy, False, x, False, N, K, M)                  # dW = dy^T x
-        return y, dW
-
-    monkeypatch.setenv("MMREC_GEMM_FUSED_SPLITK", "0")
-    y0, dW0 = run()
-    monkeypatch.setenv("MMREC_GEMM_FUSED_SPLITK", "1")
-    before = pkg("lib").launch_count()
-    y1, dW1 = run()
-    dw_on_tc05 = K >= 1024                                           # gemm_tc05_kind: the dW GEMM needs a table-sized N
-    dw_launches = 1 if dw_on_tc05 or L.mmrec_gemm_splits(N, K, M, 0, 0) == 1 else 2
-    assert pkg("lib").launch_count() - before == 1 + dw_launches     # no reduce launch after a tcgen05 GEMM
-    for _ in range(3):
-        y2, dW2 = run()
-        assert torch.equal(y2, y1) and torch.equal(dW2, dW1)
-    assert torch.equal(y0, y1) and torch.equal(dW0, dW1)
-    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-    torch.cuda.synchronize()
-    outs = []
-    for s in (s1, s2, s1, s2):
-        with torch.cuda.stream(s):
-            outs.append(run())
-    torch.cuda.synchronize()
-    for y3, dW3 in outs:
-        assert torch.equal(y3, y1) and torch.equal(dW3, dW1)
-    want_y = x.double() @ W.double().t() + b.double()
-    want_dW = dy.double().t() @ x.double()
-    rel = lambda a, w: float((a.double() - w).abs().max() / w.abs().max())
-    assert rel(y1, want_y) < 2e-6 and rel(dW1, want_dW) < 2e-6
