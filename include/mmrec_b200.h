@@ -261,6 +261,10 @@ int mmrec_linear_act_tc_supported(int32_t M, int32_t K, int32_t N);
 int mmrec_linear_act_tc_f32(const float *x, const float *W, const float *b, float *y, int32_t M, int32_t K, int32_t N,
                             int32_t act, void *stream);
 int mmrec_act_bwd_f32(const float *dy, const float *y, int64_t numel, int32_t act, float *dz, void *stream);
+/* The activation forms every fused kernel uses (nn.Tanh / nn.Sigmoid / the exp of nn.Softmax on the
+ * special-function unit, csrc/common.cuh), elementwise, for the accuracy tests:
+ * act 1 tanh, 2 sigmoid, 3 exp. */
+int mmrec_activation_f32(const float *x, int64_t numel, int32_t act, float *y, void *stream);
 int mmrec_dense_act_supported(int32_t K, int32_t N);
 size_t mmrec_dense_act_bwd_workspace_bytes(int32_t K, int32_t N);
 int mmrec_dense_act_fwd_f32(const float *X, const float *W, const float *bias, float *Y, int32_t M,

@@ -13,8 +13,8 @@ enum Act { kNone = 0, kTanh = 1, kSigmoid = 2 };
 
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float z) {
-  if constexpr (ACT == kTanh) return tanhf(z);
-  if constexpr (ACT == kSigmoid) return 1.f / (1.f + expf(-z));
+  if constexpr (ACT == kTanh) return fast_tanh(z);
+  if constexpr (ACT == kSigmoid) return fast_sigmoid(z);
   return z;
 }
 template <int ACT>
@@ -160,6 +160,46 @@ __device__ __forceinline__ void tile_mma_tc(float *__restrict__ out, int PO, int
         *dst = v;
       }
     }
+  }
+}
+
+// The same product with a PRE-SPLIT B operand: Bs2[k * PB2 + n] = (hi, lo) of B[k][n] as one float2
+// (PB2 in float2 units; PB2 % 16 == 4 keeps the 64-bit fragment loads conflict-free). A weight matrix
+// staged once per tile is read by every warp of the CTA: splitting it at staging time instead of
+// at every fragment load takes 24 of the 60 instructions of a k-step out of the inner loop.
+template <int KK, int NN, int BM, int PA, int PB2>
+__device__ __forceinline__ void tile_mma_tc_b2(float *__restrict__ out, int PO, const float *__restrict__ As,
+                                               const float2 *__restrict__ Bs2) {
+  using T = TcTile<BM, NN>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int rs = (warp % T::SLABS) * 16, cs = (warp / T::SLABS) * T::WN;
+  float c[T::NF][4];
+#pragma unroll
+  for (int j = 0; j < T::NF; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+#pragma unroll 2
+  for (int k8 = 0; k8 < KK; k8 += 8) {
+    uint32_t ah[4], al[4];
+    split_tf32_u(As[(rs + g) * PA + k8 + t], ah[0], al[0]);
+    split_tf32_u(As[(rs + g + 8) * PA + k8 + t], ah[1], al[1]);
+    split_tf32_u(As[(rs + g) * PA + k8 + t + 4], ah[2], al[2]);
+    split_tf32_u(As[(rs + g + 8) * PA + k8 + t + 4], ah[3], al[3]);
+#pragma unroll
+    for (int j = 0; j < T::NF; ++j) {
+      const int n = cs + j * 8 + g;
+      const float2 b0 = Bs2[(k8 + t) * PB2 + n], b1 = Bs2[(k8 + t + 4) * PB2 + n];
+      const uint32_t bh[2] = {__float_as_uint(b0.x), __float_as_uint(b1.x)};
+      const uint32_t bl[2] = {__float_as_uint(b0.y), __float_as_uint(b1.y)};
+      mma_tf32_16x8x8(c[j], al, bh);
+      mma_tf32_16x8x8(c[j], ah, bl);
+      mma_tf32_16x8x8(c[j], ah, bh);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < T::NF; ++j) {
+    const int n = cs + j * 8 + 2 * t;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      *reinterpret_cast<float2 *>(out + (size_t)(rs + g + 8 * h) * PO + n) = make_float2(c[j][2 * h], c[j][2 * h + 1]);
   }
 }
 

@@ -2,6 +2,8 @@
 // training path -- include/mmrec_b200.h:
 //   mmrec_colsum_f32        bias gradient dy.sum(0) of the table projections
 //   mmrec_inject3_fwd/bwd   SMORE's residual modality injection item + scale * gate_m and its autograd
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace mmrec;
@@ -230,5 +232,27 @@ extern "C" int mmrec_loss_head_bwd_f32(const float *g, float inv_batch, float re
   loss_head_bwd_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(g, inv_batch, reg_weight, inv_train_batch_size, cl_weight,
                                                           d_o2, d_cl2);
   MMREC_CHECK_LAUNCH("loss_head_bwd_kernel");
+  return MMREC_OK;
+}
+
+// ---- the fused kernels' activation forms, elementwise (accuracy tests) ---------------------------
+namespace mmrec {
+namespace {
+__global__ void __launch_bounds__(256)
+activation_kernel(const float *__restrict__ x, int64_t n, int act, float *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = act == 1 ? fast_tanh(v) : act == 2 ? fast_sigmoid(v) : fast_exp(v);
+  }
+}
+}  // namespace
+}  // namespace mmrec
+
+extern "C" int mmrec_activation_f32(const float *x, int64_t numel, int32_t act, float *y, void *stream_) {
+  MMREC_REQUIRE(x && y && numel >= 0 && act >= 1 && act <= 3, MMREC_E_BADARG, "activation: bad arguments");
+  if (numel == 0) return MMREC_OK;
+  const int blocks = (int)std::min<int64_t>((numel + 255) / 256, (int64_t)kNumSMs * 16);
+  activation_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(x, numel, act, y);
+  MMREC_CHECK_LAUNCH("activation_kernel");
   return MMREC_OK;
 }

@@ -408,10 +408,9 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
             if (mw + rr < g.M) {
               float4 o = *reinterpret_cast<const float4 *>(tr + rr * P + cq);
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-              if (g.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+              if (g.act == 1) { o.x = fast_tanh(o.x); o.y = fast_tanh(o.y); o.z = fast_tanh(o.z); o.w = fast_tanh(o.w); }
               else if (g.act == 2) {
-                o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
-                o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+                o.x = fast_sigmoid(o.x); o.y = fast_sigmoid(o.y); o.z = fast_sigmoid(o.z); o.w = fast_sigmoid(o.w);
               }
               *reinterpret_cast<float4 *>(Cs + (size_t)(mw + rr) * g.ldc + n) = o;
             }

@@ -38,8 +38,8 @@ __device__ __forceinline__ float sub_max(float v) {
 template <int LANES>
 __device__ __forceinline__ float4 row_softmax(const float4 &z) {
   const float m = sub_max<LANES>(fmaxf(fmaxf(z.x, z.y), fmaxf(z.z, z.w)));
-  float4 e = make_float4(expf(z.x - m), expf(z.y - m), expf(z.z - m), expf(z.w - m));
-  const float inv = 1.f / group_sum<LANES>((e.x + e.y) + (e.z + e.w));
+  float4 e = make_float4(fast_exp(z.x - m), fast_exp(z.y - m), fast_exp(z.z - m), fast_exp(z.w - m));
+  const float inv = fast_rcp(group_sum<LANES>((e.x + e.y) + (e.z + e.w)));
   e.x *= inv; e.y *= inv; e.z *= inv; e.w *= inv;
   return e;
 }

@@ -40,6 +40,7 @@ template <int D>
 struct Cfg {
   static constexpr int TM = 4, CG = D / 4, RG = kT / CG, BM = RG * TM, P = D + 4;
   static constexpr int PW = D + 8;     // pitch of the staged weight matrix (conflict-free MMA B fragments)
+  static constexpr int PW2 = D + 4;    // forward: pitch in float2 (hi, lo) pairs, PW2 % 16 == 4
   static constexpr int WPER = D * D / 4 / kT;
 };
 
@@ -126,6 +127,20 @@ struct WStage {
       Ws[(k4 * 4 + 3) * Cfg<D>::PW + n] = w[i].w;
     }
   }
+  // transposed and split: Ws2[k][n] = (tf32 hi, lo) of W[n][k]
+  __device__ __forceinline__ void store_t2(float2 *Ws2) const {
+#pragma unroll
+    for (int i = 0; i < Cfg<D>::WPER; ++i) {
+      const int idx = threadIdx.x + i * kT, n = idx % D, k4 = idx / D;
+      const float e[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t hi, lo;
+        split_tf32_u(e[q], hi, lo);
+        Ws2[(k4 * 4 + q) * Cfg<D>::PW2 + n] = make_float2(__uint_as_float(hi), __uint_as_float(lo));
+      }
+    }
+  }
   __device__ __forceinline__ void load_n(const float *__restrict__ W) {
 #pragma unroll
     for (int i = 0; i < Cfg<D>::WPER; ++i) w[i] = ldg4(W + (size_t)(threadIdx.x + i * kT) * 4);
@@ -151,9 +166,9 @@ __device__ __forceinline__ void bias_add(float (&acc)[4][4], const float *__rest
 // through the shared tile sO so that every thread gets the rows/columns its fragment owns.
 // Leaves the CTA synchronised after the product is visible.
 template <int D>
-__device__ __forceinline__ void product(Frag<D> &acc, float *sO, const float *sA, const float *sW, int rg, int c0) {
+__device__ __forceinline__ void product(Frag<D> &acc, float *sO, const float *sA, const float2 *sW2, int rg, int c0) {
   using C = Cfg<D>;
-  tile_mma_tc<D, D, C::BM, C::P, C::PW, false>(sO, C::P, C::BM, sA, sW);
+  tile_mma_tc_b2<D, D, C::BM, C::P, C::PW2>(sO, C::P, sA, sW2);
   __syncthreads();
   acc.load_smem(sO, rg, c0);
 }
@@ -168,10 +183,10 @@ __device__ __forceinline__ void softmax_rows(float (&a)[4][4]) {
     mx = group_max<CG>(mx);
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { a[i][j] = expf(a[i][j] - mx); s += a[i][j]; }
-    s = group_sum<CG>(s);
+    for (int j = 0; j < 4; ++j) { a[i][j] = fast_exp(a[i][j] - mx); s += a[i][j]; }
+    s = fast_rcp(group_sum<CG>(s));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[i][j] = a[i][j] / s;
+    for (int j = 0; j < 4; ++j) a[i][j] = a[i][j] * s;
   }
 }
 
@@ -184,8 +199,8 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
   const uint64_t drop_key = drop.p > 0.f ? drop_stream(drop) : 0ull;
   using C = Cfg<D>;
   extern __shared__ float4 smem4[];
-  float *Ws = reinterpret_cast<float *>(smem4);   // [D][PW]  transposed weight
-  float *sF = Ws + D * C::PW;                     // [BM][P]
+  float2 *Ws = reinterpret_cast<float2 *>(smem4); // [D][PW2] transposed weight, (hi, lo) pairs
+  float *sF = reinterpret_cast<float *>(Ws + D * C::PW2);   // [BM][P]
   float *sC = sF + C::BM * C::P;
   float *sH = sC + C::BM * C::P;
   float *sO = sH + C::BM * C::P;                  // product staging
@@ -205,7 +220,7 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
     // ---- query_v / query_t: tanh(W1 f + b) -> W2 h -> softmax -> * v | t ----
 #pragma unroll
     for (int br = 0; br < 2; ++br) {
-      w.store_t(Ws);
+      w.store_t2(Ws);
       w.load_t(P.W[2 * br + 1]);
       __syncthreads();
       product<D>(acc, sO, sF, Ws, rg, c0);
@@ -213,11 +228,11 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc.v[i][j] = tanhf(acc.v[i][j]);
+        for (int j = 0; j < 4; ++j) acc.v[i][j] = fast_tanh(acc.v[i][j]);
       acc.store_smem(sH, rg, c0);
       acc.store(saved + (2 * br) * nd, m0, n, rg, c0);
       __syncthreads();                                  // sH complete, Ws free
-      w.store_t(Ws);
+      w.store_t2(Ws);
       w.load_t(P.W[br == 0 ? 2 : 4]);
       __syncthreads();
       product<D>(acc, sO, sH, Ws, rg, c0);
@@ -236,7 +251,7 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
     sd.fill(0.f);
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
-      w.store_t(Ws);
+      w.store_t2(Ws);
       if (g < 2) w.load_t(P.W[5 + g]);
       __syncthreads();
       product<D>(acc, sO, sC, Ws, rg, c0);
@@ -244,7 +259,7 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc.v[i][j] = 1.f / (1.f + expf(-acc.v[i][j]));
+        for (int j = 0; j < 4; ++j) acc.v[i][j] = fast_sigmoid(acc.v[i][j]);
       acc.store(saved + (4 + g) * nd, m0, n, rg, c0);
       if (masks != nullptr || drop.p > 0.f) {
         if (masks != nullptr) x.load(masks + g * nd, m0, n, rg, c0);
@@ -442,7 +457,7 @@ side_partial_reduce_kernel(const float *__restrict__ partial, int n_parts, int n
 }
 
 template <int D>
-constexpr size_t side_fwd_smem() { return sizeof(float) * (D * Cfg<D>::PW + 4 * Cfg<D>::BM * Cfg<D>::P); }
+constexpr size_t side_fwd_smem() { return sizeof(float) * (2 * D * Cfg<D>::PW2 + 4 * Cfg<D>::BM * Cfg<D>::P); }
 template <int D>
 constexpr size_t side_bwd_smem() { return sizeof(float) * (D * Cfg<D>::PW + 5 * Cfg<D>::BM * Cfg<D>::P); }
 

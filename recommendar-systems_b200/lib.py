@@ -52,6 +52,7 @@ SIGNATURES = {
     "mmrec_linear_act_tc_supported": (C.c_int, [_i32, _i32, _i32]),
     "mmrec_linear_act_tc_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "mmrec_act_bwd_f32": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "mmrec_activation_f32": (C.c_int, [_p, _i64, _i32, _p, _p]),
     "mmrec_dense_act_supported": (C.c_int, [_i32, _i32]),
     "mmrec_dense_act_bwd_workspace_bytes": (_sz, [_i32, _i32]),
     "mmrec_dense_act_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),

@@ -328,6 +328,7 @@ class FREEDOM(GeneralRecommender):
         # freedom.py:45-46: edge values live on the device (multinomial draws from the CUDA RNG)
         self.edge_values = _edge_values_cpu(self._edge_u, self._edge_i, self.n_users,
                                             self.n_items).to(self.device)
+        self.edge_dropout_rng = str(config.get("edge_dropout_rng", "device"))
         self.user_embedding = nn.Embedding(self.n_users, self.embedding_dim)
         self.item_id_embedding = nn.Embedding(self.n_items, self.embedding_dim)
         nn.init.xavier_uniform_(self.user_embedding.weight)
@@ -353,7 +354,11 @@ class FREEDOM(GeneralRecommender):
             self.masked_adj = self.norm_adj
             return
         degree_len = int(self.edge_values.size(0) * (1. - self.dropout))
-        degree_idx = torch.multinomial(self.edge_values, degree_len)
+        # the reference draws on whatever device its model lives on (freedom.py:46, 136): the CUDA
+        # generator on a GPU. edge_dropout_rng = "cpu" draws from torch's CPU generator instead --
+        # the stream a CPU run of the reference consumes, which is what its fixtures were made with
+        ev = self.edge_values.cpu() if self.edge_dropout_rng == "cpu" else self.edge_values
+        degree_idx = torch.multinomial(ev, degree_len)
         self._set_masked_adj(self._masked_graph(degree_idx))
 
     def _masked_graph(self, keep_idx):

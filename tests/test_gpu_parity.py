@@ -483,14 +483,22 @@ def test_layergcn_edge_dropout_parity():
 
 @pytest.mark.parametrize("model,tag,over", [
     ("LayerGCN", "tiny_layergcn", {}), ("MGCN", "tiny_mgcn", {}), ("SMORE", "tiny_smore", {}),
-    ("SMORE", "tiny_smore_nomg", {"mg_enable": False})])
+    ("SMORE", "tiny_smore_nomg", {"mg_enable": False}),
+    ("LayerGCN", "tiny_layergcn_drop", {"dropout": 0.1, "reg_weight": 1e-3}),
+    ("FREEDOM", "tiny_freedom", {"edge_dropout_rng": "cpu"})])
 def test_trainer_two_epochs_match_reference(model, tag, over):
-    """Our Trainer (fused eval, sync-free loss accumulation, mirror-gradient schedule) reproduces
-    the reference Trainer's two-epoch trajectory: epoch losses, global_step, final metrics."""
+    """Our Trainer (fused eval, sync-free loss accumulation, mirror-gradient schedule, CUDA-graph
+    replay) reproduces the reference Trainer's two-epoch trajectory: epoch losses to 1e-5 (measured:
+    2e-8 .. 1.3e-7), global_step, the UNROUNDED Recall / NDCG / Precision / MAP @1..K of the final
+    model (measured: 1e-16), every top-K id of every validation user, the final parameters. The
+    per-epoch edge dropout of LayerGCN / FREEDOM is part of it: same draws (python `random` and
+    torch's CPU generator, as in the CPU run that made the fixture), re-normalised adjacency, graphs
+    re-captured per adjacency version."""
     from parity_util import make_env, golden_params
     env = make_env(model, DEV, tag=tag, overrides=over)
     g, m, train, valid, test = env["golden"], env["model"], env["train"], env["valid"], env["test"]
     m.load_state_dict({k: v.to(DEV) for k, v in golden_params(g).items()})
+    m.pre_epoch_processing()      # the fixture's prologue drew one edge-dropout sample before its fit loop
     it = iter(train)
     next(it), next(it)
     train.pr = 0
@@ -504,14 +512,22 @@ def test_trainer_two_epochs_match_reference(model, tag, over):
         v = tr.evaluate(valid)
         tr.evaluate(test)
         valids.append([v[str(k)] for k in g["fit/metric_keys"]])
-    np.testing.assert_allclose(losses, g["fit/train_loss"], rtol=1e-4)
+    np.testing.assert_allclose(losses, g["fit/train_loss"], rtol=1e-5)
     if "fit/global_step" in g.files:
         assert m.global_step == int(g["fit/global_step"])
-    np.testing.assert_allclose(np.asarray(valids), g["fit/valid"], atol=2e-3)
+    np.testing.assert_allclose(np.asarray(valids), g["fit/valid"], atol=1e-12)     # the rounded values of the log
+    # final model: every top-K id and the unrounded metrics the reference computes from them
+    ids = torch.cat(tr.evaluate_topk(valid), dim=0)
+    assert np.array_equal(ids.cpu().numpy(), g["fit/valid_topk"])
+    rowptr, items = valid.gt_csr()
+    raw = tr.evaluator._metrics_from_sums(pkg("ops").topk_metric_sums(ids, rowptr, items), ids.shape[0], valid)
+    names = [str(x).lower() for x in g["fit/metric_names"]]
+    ours_raw = np.stack([raw[tr.evaluator.metrics.index(n)] for n in names], axis=0)
+    np.testing.assert_allclose(ours_raw, g["fit/valid_metrics_raw"], rtol=0, atol=1e-12)
     for k in g.files:
         if k.startswith("fit/param/"):
             ours = m.state_dict()[k[len("fit/param/"):]].cpu().numpy()
-            assert np.abs(ours - g[k]).max() / np.abs(g[k]).max() < 1e-3, k
+            assert np.abs(ours - g[k]).max() / np.abs(g[k]).max() < 3e-4, k     # measured: <= 8e-5 after 2 epochs of Adam
 
 
 def test_fused_adam_matches_torch_adam():

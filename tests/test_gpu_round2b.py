@@ -132,3 +132,29 @@ def test_smore_trainer_uses_inkernel_dropout_under_graph_replay():
     assert torch.equal(state, torch.cuda.get_rng_state(0))        # nn.Dropout no longer touches torch's generator
     assert tr.replayed_launches > 0 and np.isfinite(losses).all()
     assert float(m.dropout_counter.item()) > 0
+
+
+# ------------------------------------------------------------------ activations on the special-function unit
+def test_fast_activations():
+    """tanh / sigmoid / exp as the fused kernels evaluate them (ex2.approx / rcp.approx + a polynomial
+    for small |x|, csrc/common.cuh) against float64: relative error far below the 1e-5 parity bar over
+    the whole range, exact limits, no NaN at the extremes."""
+    lib = pkg("lib")
+    xs = torch.cat([torch.linspace(-30, 30, 2_000_001), torch.logspace(-30, 1.5, 200_001), -torch.logspace(-30, 1.5, 200_001),
+                    torch.tensor([0.0, -0.0, 0.6, -0.6, 0.59999996, 88.0, -88.0, 1e4, -1e4, 1e-38, -1e-38])]).to(DEV)
+    x64 = xs.double()
+    want = {1: torch.tanh(x64), 2: torch.sigmoid(x64), 3: torch.exp(x64)}
+    bound = {1: 4e-7, 2: 4e-7, 3: 2e-6}          # exp: the argument rounding grows with |x| (softmax only sees x <= 0)
+    for act in (1, 2, 3):
+        y = torch.empty_like(xs)
+        lib.call("mmrec_activation_f32", lib.ptr(xs), xs.numel(), act, lib.ptr(y), lib.stream())
+        assert bool(torch.isfinite(y[xs.abs() < 80]).all())
+        ok = want[act].abs() > 1e-30
+        if act == 3:
+            ok &= xs.abs() < 30
+        rel = ((y.double() - want[act]).abs() / want[act].abs())[ok]
+        assert float(rel.max()) < bound[act], (act, float(rel.max()))
+    t = torch.empty_like(xs)
+    lib.call("mmrec_activation_f32", lib.ptr(xs), xs.numel(), 1, lib.ptr(t), lib.stream())
+    assert float(t[xs == 1e4]) == 1.0 and float(t[xs == -1e4]) == -1.0 and float(t[xs == 0][0]) == 0.0
+    assert bool((t.abs() <= 1).all())
