@@ -152,6 +152,11 @@ def test_fast_activations():
         ok = want[act].abs() > 1e-30
         if act == 3:
             ok &= xs.abs() < 30
+        if act == 2:
+            # far in the negative tail sigmoid(x) ~ e^x inherits exp's argument rounding (|x| * 6e-8): relative
+            # to values of 1e-13 that is irrelevant; what matters is the absolute error on the (0, 1) scale
+            assert float((y.double() - want[act]).abs().max()) < 1.5e-7
+            ok &= xs.abs() <= 8
         rel = ((y.double() - want[act]).abs() / want[act].abs())[ok]
         assert float(rel.max()) < bound[act], (act, float(rel.max()))
     t = torch.empty_like(xs)
