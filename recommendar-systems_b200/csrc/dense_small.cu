@@ -159,16 +159,18 @@ dense_partial_reduce_kernel(const __grid_constant__ BwdBatch B, int n_parts, int
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int j = blockIdx.x * 64 + tx;
   const size_t stride = (size_t)n_w + n_b;
-  float s0 = 0.f, s1 = 0.f;
+  float s[8];                                  // eight independent loads in flight per thread
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s[u] = 0.f;
   if (j < n_w + n_b) {
     int p = ty;
-    for (; p + 16 < n_parts; p += 32) {
-      s0 += partial[(size_t)p * stride + j];
-      s1 += partial[(size_t)(p + 16) * stride + j];
+    for (; p + 16 * 7 < n_parts; p += 16 * 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += __ldcs(partial + (size_t)(p + 16 * u) * stride + j);
     }
-    if (p < n_parts) s0 += partial[(size_t)p * stride + j];
+    for (; p < n_parts; p += 16) s[0] += __ldcs(partial + (size_t)p * stride + j);
   }
-  sm[ty][tx] = s0 + s1;
+  sm[ty][tx] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   __syncthreads();
   if (ty == 0 && j < n_w + n_b) {
     float s = 0.f;

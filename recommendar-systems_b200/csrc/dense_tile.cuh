@@ -163,13 +163,16 @@ __device__ __forceinline__ void tile_mma_tc(float *__restrict__ out, int PO, int
   }
 }
 
-// The same product with a PRE-SPLIT B operand: Bs2[k * PB2 + n] = (hi, lo) of B[k][n] as one float2
-// (PB2 in float2 units; PB2 % 16 == 4 keeps the 64-bit fragment loads conflict-free). A weight matrix
-// staged once per tile is read by every warp of the CTA: splitting it at staging time instead of
-// at every fragment load takes 24 of the 60 instructions of a k-step out of the inner loop.
+// The same product with a PRE-SPLIT B operand in MMA fragment order: for the k-step kb (8 rows of
+// B) and t < 4, Bhi[(kb * 4 + t) * PB2 + n] = (hi of B[8 kb + t][n], hi of B[8 kb + t + 4][n]) as one
+// float2 -- exactly the register pair {b0, b1} of mma.m16n8k8 -- and Blo the low parts (PB2 in float2
+// units; PB2 % 16 == 4 keeps the 64-bit loads conflict-free). A weight matrix staged once per tile
+// is read by every warp of the CTA: splitting it at staging time instead of at every fragment load
+// takes the 24 split instructions of a k-step out of the inner loop, and the pair layout the
+// register moves an interleaved (hi, lo) layout would need.
 template <int KK, int NN, int BM, int PA, int PB2>
 __device__ __forceinline__ void tile_mma_tc_b2(float *__restrict__ out, int PO, const float *__restrict__ As,
-                                               const float2 *__restrict__ Bs2) {
+                                               const float2 *__restrict__ Bhi, const float2 *__restrict__ Blo) {
   using T = TcTile<BM, NN>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int rs = (warp % T::SLABS) * 16, cs = (warp / T::SLABS) * T::WN;
@@ -185,10 +188,10 @@ __device__ __forceinline__ void tile_mma_tc_b2(float *__restrict__ out, int PO, 
     split_tf32_u(As[(rs + g + 8) * PA + k8 + t + 4], ah[3], al[3]);
 #pragma unroll
     for (int j = 0; j < T::NF; ++j) {
-      const int n = cs + j * 8 + g;
-      const float2 b0 = Bs2[(k8 + t) * PB2 + n], b1 = Bs2[(k8 + t + 4) * PB2 + n];
-      const uint32_t bh[2] = {__float_as_uint(b0.x), __float_as_uint(b1.x)};
-      const uint32_t bl[2] = {__float_as_uint(b0.y), __float_as_uint(b1.y)};
+      const int o = ((k8 >> 1) + t) * PB2 + cs + j * 8 + g;
+      const float2 h = Bhi[o], l = Blo[o];
+      const uint32_t bh[2] = {__float_as_uint(h.x), __float_as_uint(h.y)};
+      const uint32_t bl[2] = {__float_as_uint(l.x), __float_as_uint(l.y)};
       mma_tf32_16x8x8(c[j], al, bh);
       mma_tf32_16x8x8(c[j], ah, bl);
       mma_tf32_16x8x8(c[j], ah, bh);

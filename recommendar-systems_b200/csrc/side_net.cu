@@ -127,8 +127,12 @@ struct WStage {
       Ws[(k4 * 4 + 3) * Cfg<D>::PW + n] = w[i].w;
     }
   }
-  // transposed and split: Ws2[k][n] = (tf32 hi, lo) of W[n][k]
+  // transposed, split and paired for tile_mma_tc_b2: element k of output column n goes to half
+  // (k % 8) / 4 of the float2 at [(k / 8) * 4 + k % 4][n] of the hi plane (Ws2) and of the lo plane
+  // (Ws2 + (D / 2) * PW2)
   __device__ __forceinline__ void store_t2(float2 *Ws2) const {
+    float *hi_plane = reinterpret_cast<float *>(Ws2);
+    float *lo_plane = reinterpret_cast<float *>(Ws2 + (D / 2) * Cfg<D>::PW2);
 #pragma unroll
     for (int i = 0; i < Cfg<D>::WPER; ++i) {
       const int idx = threadIdx.x + i * kT, n = idx % D, k4 = idx / D;
@@ -137,7 +141,9 @@ struct WStage {
       for (int q = 0; q < 4; ++q) {
         uint32_t hi, lo;
         split_tf32_u(e[q], hi, lo);
-        Ws2[(k4 * 4 + q) * Cfg<D>::PW2 + n] = make_float2(__uint_as_float(hi), __uint_as_float(lo));
+        const int o = 2 * (((k4 >> 1) * 4 + q) * Cfg<D>::PW2 + n) + (k4 & 1);
+        hi_plane[o] = __uint_as_float(hi);
+        lo_plane[o] = __uint_as_float(lo);
       }
     }
   }
@@ -168,7 +174,7 @@ __device__ __forceinline__ void bias_add(float (&acc)[4][4], const float *__rest
 template <int D>
 __device__ __forceinline__ void product(Frag<D> &acc, float *sO, const float *sA, const float2 *sW2, int rg, int c0) {
   using C = Cfg<D>;
-  tile_mma_tc_b2<D, D, C::BM, C::P, C::PW2>(sO, C::P, sA, sW2);
+  tile_mma_tc_b2<D, D, C::BM, C::P, C::PW2>(sO, C::P, sA, sW2, sW2 + (D / 2) * C::PW2);
   __syncthreads();
   acc.load_smem(sO, rg, c0);
 }
@@ -199,7 +205,7 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
   const uint64_t drop_key = drop.p > 0.f ? drop_stream(drop) : 0ull;
   using C = Cfg<D>;
   extern __shared__ float4 smem4[];
-  float2 *Ws = reinterpret_cast<float2 *>(smem4); // [D][PW2] transposed weight, (hi, lo) pairs
+  float2 *Ws = reinterpret_cast<float2 *>(smem4); // transposed weight, hi plane [D/2][PW2] + lo plane, k-paired float2
   float *sF = reinterpret_cast<float *>(Ws + D * C::PW2);   // [BM][P]
   float *sC = sF + C::BM * C::P;
   float *sH = sC + C::BM * C::P;
@@ -436,16 +442,20 @@ side_partial_reduce_kernel(const float *__restrict__ partial, int n_parts, int n
   const int j = blockIdx.x * 64 + tx, wi = blockIdx.y;
   const size_t stride = (size_t)n_w + n_b;
   const float *base = partial + (size_t)wi * n_parts * stride;
-  float s0 = 0.f, s1 = 0.f;
+  // eight independent loads in flight per thread (two left the 48 MB of slabs at 1.9 TB/s: the
+  // kernel is a pure stream and was bound by its own memory-level parallelism)
+  float s[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s[u] = 0.f;
   if (j < n_w + n_b) {
     int p = ty;
-    for (; p + 16 < n_parts; p += 32) {
-      s0 += base[(size_t)p * stride + j];
-      s1 += base[(size_t)(p + 16) * stride + j];
+    for (; p + 16 * 7 < n_parts; p += 16 * 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += __ldcs(base + (size_t)(p + 16 * u) * stride + j);
     }
-    if (p < n_parts) s0 += base[(size_t)p * stride + j];
+    for (; p < n_parts; p += 16) s[0] += __ldcs(base + (size_t)p * stride + j);
   }
-  sm[ty][tx] = s0 + s1;
+  sm[ty][tx] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   __syncthreads();
   if (ty == 0 && j < n_w + n_b) {
     float s = 0.f;
