@@ -297,7 +297,7 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
 }
 
 // ================================================================================== backward
-// partial layout: [kNW][n_parts][D*D + D]; a CTA that owns several tiles accumulates into its slot.
+// partial layout: [kNW][D + 1 rows (dW rows, then db)][n_parts][D]; a CTA that owns several tiles accumulates into its slot.
 template <int D>
 __global__ void __launch_bounds__(kT, D <= 64 ? 2 : 1)
 side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_side, const float *__restrict__ F,
@@ -351,14 +351,19 @@ side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_sid
       acc.store_smem(sZ, rg, c0);
       w.store_n(Wn);
       __syncthreads();
-      float *slot = partial + ((size_t)w_idx * n_parts + blockIdx.x) * (D * D + D);
+      // row r of this CTA's dW partial (r = D: the bias row) sits at [w][r][part][D]: the reduce
+      // kernel then streams n_parts contiguous rows per output row instead of 256 bytes out of
+      // every 116 KB slab
+      float *slot = partial + (size_t)w_idx * (D + 1) * n_parts * D + (size_t)blockIdx.x * D;
+      const int pitch = n_parts * D;
       tile_mma_tc<D, D, C::BM, C::P, C::PW, false>(sO, C::P, C::BM, sZ, Wn);          // dz W
-      tile_mma_tc<C::BM, D, D, C::P, C::P, true>(slot, D, D, sZ, sX, !first);         // dz^T X
+      tile_mma_tc<C::BM, D, D, C::P, C::P, true>(slot, pitch, D, sZ, sX, !first);     // dz^T X
       if (with_bias && threadIdx.x < D) {
         float sdb = 0.f;
 #pragma unroll 8
         for (int m = 0; m < C::BM; ++m) sdb += sZ[m * C::P + threadIdx.x];
-        slot[D * D + threadIdx.x] = first ? sdb : slot[D * D + threadIdx.x] + sdb;
+        float *bslot = slot + (size_t)D * pitch + threadIdx.x;
+        *bslot = first ? sdb : *bslot + sdb;
       }
       __syncthreads();
       Frag<D> tmp;
@@ -440,8 +445,10 @@ side_partial_reduce_kernel(const float *__restrict__ partial, int n_parts, int n
   __shared__ float sm[16][64];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int j = blockIdx.x * 64 + tx, wi = blockIdx.y;
-  const size_t stride = (size_t)n_w + n_b;
-  const float *base = partial + (size_t)wi * n_parts * stride;
+  // j -> (row, col) of the [D + 1, D] result; its n_parts partials are D floats apart: contiguous
+  const int D = n_b, row = j / D, col = j % D;
+  const size_t stride = (size_t)D;
+  const float *base = partial + ((size_t)wi * (D + 1) + row) * n_parts * D + col - j;
   // eight independent loads in flight per thread (two left the 48 MB of slabs at 1.9 TB/s: the
   // kernel is a pure stream and was bound by its own memory-level parallelism)
   float s[8];

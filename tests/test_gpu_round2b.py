@@ -144,7 +144,7 @@ def test_fast_activations():
                     torch.tensor([0.0, -0.0, 0.6, -0.6, 0.59999996, 88.0, -88.0, 1e4, -1e4, 1e-38, -1e-38])]).to(DEV)
     x64 = xs.double()
     want = {1: torch.tanh(x64), 2: torch.sigmoid(x64), 3: torch.exp(x64)}
-    bound = {1: 4e-7, 2: 4e-7, 3: 2e-6}          # exp: the argument rounding grows with |x| (softmax only sees x <= 0)
+    bound = {1: 4e-7, 2: 1e-6, 3: 2e-6}          # exp: the argument rounding grows with |x| (softmax only sees x <= 0)
     for act in (1, 2, 3):
         y = torch.empty_like(xs)
         lib.call("mmrec_activation_f32", lib.ptr(xs), xs.numel(), act, lib.ptr(y), lib.stream())
