@@ -175,6 +175,20 @@ def time_kernel(fn, flush, iters=20, warm=3):
     return sum(a.elapsed_time(b) for a, b in ev) / iters
 
 
+# L2 -> SM crossbar peak of the B200 as ncu reports it (derived__lts__lts2xbar_bytes.sum.peak_sustained in
+# profiles/r02_kernels_ncu_raw.csv): the bound of the row gathers of a CSR SpMM, which move nnz * 4 d bytes
+# through the L2 whatever the HBM traffic is (on the 600k x 120k graph ncu measures 10.7 TB/s = 91 % of it)
+L2_XBAR_PEAK_GBS = 11776.0
+
+
+def _l2_view(g, d, ms, extra_rows=0):
+    """Bytes a row-gather SpMM pulls through the L2 (every gathered row, the CSR arrays, the output and
+    epilogue rows) against the crossbar peak."""
+    b = g.nnz * (8 + 4 * d) + 4 * (g.n_rows + 1) + 4 * d * g.n_rows * (1 + extra_rows)
+    return {"l2_bytes": b, "l2_achieved": b / ms / 1e6, "l2_peak": L2_XBAR_PEAK_GBS,
+            "l2_frac": b / ms / 1e6 / L2_XBAR_PEAK_GBS}
+
+
 def kernel_rooflines(env, peak):
     """Per-kernel achieved algorithmic GB/s (SURVEY 8d byte formulas), L2 flushed per launch."""
     import torch
@@ -189,7 +203,7 @@ def kernel_rooflines(env, peak):
     ms = time_kernel(lambda: ops.spmm_raw(g, X, Y=Y), flush)
     b = g.algorithmic_bytes(d)
     out.append({"kernel": "spmm_csr_kernel (UI graph, one layer)", "bytes": b, "ms": ms,
-                "achieved": b / ms / 1e6, "frac": b / ms / 1e6 / peak})
+                "achieved": b / ms / 1e6, "frac": b / ms / 1e6 / peak, **_l2_view(g, d, ms)})
     acc = torch.empty_like(X)
     ms = time_kernel(lambda: ops.spmm_raw(g, X, Y=Y, acc_in=X, acc_out=acc), flush)
     # a fused L-layer propagation = L x the SpMM bytes + ONE 4 d N write of the
@@ -198,7 +212,7 @@ def kernel_rooflines(env, peak):
     L = int(model.n_ui_layers)
     b2 = b + 4 * d * g.n_rows // max(L, 1)
     out.append({"kernel": "spmm_csr_kernel (UI graph, fused layer-sum)", "bytes": b2, "ms": ms,
-                "achieved": b2 / ms / 1e6, "frac": b2 / ms / 1e6 / peak})
+                "achieved": b2 / ms / 1e6, "frac": b2 / ms / 1e6 / peak, **_l2_view(g, d, ms, extra_rows=2)})
     gi = model.fusion_adj
     Xi = torch.randn(gi.n_cols, d, device=dev)
     Yi = torch.empty(gi.n_rows, d, device=dev)
@@ -259,7 +273,7 @@ def kernel_rooflines(env, peak):
     gather = gl.nnz * (8 + 4 * d) + 4 * (gl.n_rows + 1) + 4 * d * gl.n_rows
     out.append({"kernel": f"spmm_csr_kernel (scaled UI graph 600k x 120k, nnz {gl.nnz}, > L2)", "bytes": b,
                 "ms": ms, "achieved": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
-                "no_reuse_gather_bytes": gather, "no_reuse_gather_gbps": gather / ms / 1e6})
+                "no_reuse_gather_bytes": gather, "no_reuse_gather_gbps": gather / ms / 1e6, **_l2_view(gl, d, ms)})
     for o in out:
         o["unit"] = "GB/s"
     return out
@@ -461,7 +475,13 @@ def run_ours(args):
                                "(CUPTI activity records); isolated_* = one launch after an L2 flush, CUDA events",
                      "launches_per_step": dom.get("launches_per_step"),
                      "isolated_ms_per_launch": dom["isolated_ms"], "isolated_frac": dom["isolated_frac"],
-                     "in_step": live},
+                     "in_step": live,
+                     "l2_bound": {"note": "what bounds this kernel is not HBM: every gathered row crosses the L2 -> SM "
+                                          "crossbar (nnz * 4 d bytes per launch whatever the DRAM traffic); peak = ncu "
+                                          "derived__lts__lts2xbar_bytes.sum.peak_sustained",
+                                  "bytes_per_launch": dom.get("l2_bytes"), "peak": L2_XBAR_PEAK_GBS, "unit": "GB/s",
+                                  "achieved": (dom["l2_bytes"] / dom["ms"] / 1e6) if dom.get("l2_bytes") else None,
+                                  "frac": (dom["l2_bytes"] / dom["ms"] / 1e6 / L2_XBAR_PEAK_GBS) if dom.get("l2_bytes") else None}},
         "kernels": kr,
         "train_epoch_s": steps_per_epoch * ms / K / 1e3,
         "train_epoch_s_e2e": e2e_s / n_epochs_e2e,

@@ -296,7 +296,8 @@ int mmrec_dense_act_batch_bwd_f32(const float *const *dY_host, const float *cons
  *       gate_fusion_prefer.0   (each [d, d] row-major as nn.Linear stores it; b NULL = no bias)
  *   masks: [3, n, d] dropout multipliers (0 or 1/(1-p)) for the image / text / fusion gate, or
  *          NULL (eval, p = 0)
- *   saved: [7, n, d] written by fwd, read by bwd (tanh outputs, softmax outputs, gate sigmoids)
+ *   saved: [7, n, d] written by fwd, read by bwd (tanh outputs, softmax outputs, gate sigmoids);
+ *          NULL in fwd = inference (full_sort_predict under no_grad): nothing is kept
  *   fwd -> side [n, d] (smore.py:339-340) and all = C + side (smore.py:341)
  *   bwd <- d_all, d_side (either may be NULL) -> dF, dV, dT, dC (dC includes d_all), dW[7], db[7]
  *          (db entries may be NULL); ws = mmrec_smore_side_bwd_workspace_bytes(n, d) of scratch.

@@ -236,14 +236,14 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc.v[i][j] = fast_tanh(acc.v[i][j]);
       acc.store_smem(sH, rg, c0);
-      acc.store(saved + (2 * br) * nd, m0, n, rg, c0);
+      if (saved != nullptr) acc.store(saved + (2 * br) * nd, m0, n, rg, c0);
       __syncthreads();                                  // sH complete, Ws free
       w.store_t2(Ws);
       w.load_t(P.W[br == 0 ? 2 : 4]);
       __syncthreads();
       product<D>(acc, sO, sH, Ws, rg, c0);
       softmax_rows<D>(acc.v);
-      acc.store(saved + (2 * br + 1) * nd, m0, n, rg, c0);
+      if (saved != nullptr) acc.store(saved + (2 * br + 1) * nd, m0, n, rg, c0);
       x.load(br == 0 ? V : T, m0, n, rg, c0);
       Frag<D> &agg = br == 0 ? agg_v : agg_t;
 #pragma unroll
@@ -266,7 +266,7 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc.v[i][j] = fast_sigmoid(acc.v[i][j]);
-      acc.store(saved + (4 + g) * nd, m0, n, rg, c0);
+      if (saved != nullptr) acc.store(saved + (4 + g) * nd, m0, n, rg, c0);
       if (masks != nullptr || drop.p > 0.f) {
         if (masks != nullptr) x.load(masks + g * nd, m0, n, rg, c0);
         else x.fill_dropout(drop_key, drop.p, g, m0, n, rg, c0);
@@ -568,8 +568,8 @@ static int unpack_drop(const MmrecDropout *drop, DropSpec &D) {
 static int side_fwd_impl(const float *F, const float *V, const float *T, const float *C_, const float *const *W_host,
                          const float *const *b_host, const float *masks, const MmrecDropout *drop_host, float *saved,
                          float *side, float *all, int32_t n, int32_t d, void *stream) {
-  MMREC_REQUIRE(F && V && T && C_ && W_host && b_host && saved && side && all, MMREC_E_BADARG,
-                "smore_side_fwd: null pointer");
+  MMREC_REQUIRE(F && V && T && C_ && W_host && b_host && side && all, MMREC_E_BADARG,
+                "smore_side_fwd: null pointer");      // saved may be NULL: inference, nothing kept for a backward
   MMREC_REQUIRE(mmrec_smore_side_supported(d), MMREC_E_BADARG, "smore_side_fwd: d must be 32, 64 or 128 (got %d)", d);
   MMREC_REQUIRE(n >= 0, MMREC_E_BADARG, "smore_side_fwd: bad n");
   MMREC_REQUIRE(aligned16(F) && aligned16(V) && aligned16(T) && aligned16(C_) && aligned16(masks) &&

@@ -921,7 +921,9 @@ class _SmoreSide(torch.autograd.Function):
         bs = [None if b is None else _f32c(b) for b in wb[1::2]]
         masks = None if masks is None else _f32c(masks)
         n, d = F.shape
-        saved = torch.empty(7, n, d, dtype=torch.float32, device=F.device)
+        # nothing is kept for a backward that cannot come (evaluation forward under no_grad)
+        need_bwd = any(ctx.needs_input_grad)
+        saved = torch.empty(7, n, d, dtype=torch.float32, device=F.device) if need_bwd else None
         side, all_e = torch.empty_like(F), torch.empty_like(F)
         if drop is not None:
             if masks is not None:
@@ -936,8 +938,9 @@ class _SmoreSide(torch.autograd.Function):
         ctx.drop = drop
         ctx.has_mask = masks is not None
         ctx.has_bias = [b is not None for b in bs]
-        ctx.save_for_backward(F, V, T, C_, saved, *Ws, *[b for b in bs if b is not None],
-                              *([masks] if masks is not None else []))
+        if need_bwd:
+            ctx.save_for_backward(F, V, T, C_, saved, *Ws, *[b for b in bs if b is not None],
+                                  *([masks] if masks is not None else []))
         return all_e, side
 
     @staticmethod

@@ -163,3 +163,19 @@ def test_fast_activations():
     lib.call("mmrec_activation_f32", lib.ptr(xs), xs.numel(), 1, lib.ptr(t), lib.stream())
     assert float(t[xs == 1e4]) == 1.0 and float(t[xs == -1e4]) == -1.0 and float(t[xs == 0][0]) == 0.0
     assert bool((t.abs() <= 1).all())
+
+
+def test_smore_side_inference_forward_keeps_nothing():
+    """Under no_grad (full_sort_predict) the fused preference module writes no saved tensors
+    (saved = NULL in mmrec_smore_side_fwd_f32) and returns the same bits as the training forward."""
+    ops = pkg("ops")
+    n, d = 7050 + 19445, 64
+    layers = _layers(d, 3)
+    ins = [torch.randn(n, d, device=DEV) for _ in range(4)]
+    a1, s1 = ops.smore_side(*ins, layers)
+    before = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        a0, s0 = ops.smore_side(*ins, layers)
+    assert torch.equal(a0, a1) and torch.equal(s0, s1)
+    assert not a0.requires_grad and a1.requires_grad
+    assert torch.cuda.memory_allocated() - before <= 2 * n * d * 4 + (1 << 20)      # the two outputs, no [7, n, d]
