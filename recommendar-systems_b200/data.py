@@ -108,9 +108,18 @@ class AbstractDataLoader:
         return math.ceil(self.pr_end / self.step)
 
     def __iter__(self):
-        if self.shuffle:
+        if self.shuffle and not self.__dict__.pop("_preshuffled", False):
             self._shuffle()
         return self
+
+    def prefetch_shuffle(self):
+        """Draw the NEXT epoch's shuffle now (Trainer calls this while the device still runs the last
+        steps of the current epoch, so the ~4 ms permutation of the interactions is off the critical
+        path). The next `iter()` then skips its shuffle: same draws from numpy's global state in the
+        same order -- nothing else in the training loop consumes that generator."""
+        if self.shuffle and self.pr == 0 and not self.__dict__.get("_preshuffled", False):   # between epochs only
+            self._shuffle()
+            self._preshuffled = True
 
     def __next__(self):
         if self.pr >= self.pr_end:

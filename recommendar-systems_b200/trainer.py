@@ -430,6 +430,10 @@ class Trainer:
                     train_data.pr = 0                  # abandoned epoch: the next one starts clean
             else:
                 interaction = next(it, None)
+                if interaction is None and epoch_idx + 1 < self.epochs and hasattr(train_data, "prefetch_shuffle") \
+                        and bool(self.config.get("prefetch_epoch_shuffle", True)):
+                    # the device still has the last step(s) queued: shuffle for the next epoch under them
+                    train_data.prefetch_shuffle()
             loss_batches.append(loss)
             if self.sync_free:
                 total_loss = loss.clone() if total_loss is None else total_loss + loss

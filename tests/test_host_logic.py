@@ -285,3 +285,51 @@ def test_train_epoch_nan_aborts_like_the_reference_one_batch_late_at_most():
     tr2 = _host_trainer(model2, sync_free=True)
     loss2, _ = tr2._train_epoch(_FakeLoader(7), 0)
     assert torch.is_tensor(loss2) and bool(torch.isnan(loss2))
+
+
+def test_epoch_shuffle_prefetch_draws_the_same_permutations(tiny_data):
+    """Trainer._train_epoch shuffles for the NEXT epoch while the device runs the last steps of the
+    current one (TrainDataLoader.prefetch_shuffle): the loader then skips its shuffle at iter(). Same
+    numpy draws in the same order -> the same batches as without the prefetch, epoch after epoch, and
+    never a second shuffle; the last epoch of a run draws nothing extra."""
+    import random
+    cfgm, data_m = pkg("config"), pkg("data")
+    seen = {}
+    for prefetch in (False, True):
+        cfg = cfgm.Config("LightGCN", "tiny", {"device": torch.device("cpu"), "learner": "sgd", "learning_rate": 0.0,
+                                                "sync_free": True, "epochs": 3, "prefetch_epoch_shuffle": prefetch,
+                                                "is_multimodal_model": False, "data_path": None})
+        ds = data_m.RecDataset(cfg, tiny_data.users, tiny_data.items, tiny_data.labels)
+        tr_split = ds.split()[0]
+        loader = data_m.TrainDataLoader(cfg, tr_split, batch_size=cfg["train_batch_size"], shuffle=True)
+        cfgm.init_seed(999)
+        loader.pretrain_setup()
+
+        class Rec(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.w = torch.nn.Parameter(torch.ones(1))
+                self.batches = []
+
+            def calculate_loss(self, interaction):
+                self.batches.append(interaction.clone())
+                return (self.w * 1.0).sum()
+
+            def pre_epoch_processing(self):
+                pass
+
+        model = Rec()
+        tr = pkg("trainer").Trainer(cfg, model)
+        shuffles = []
+        orig = loader._shuffle
+        loader._shuffle = lambda: (shuffles.append(len(model.batches)), orig())[1]
+        for epoch in range(3):
+            tr._train_epoch(loader, epoch)
+        n_per = len(loader)
+        # one shuffle per epoch; with the prefetch they happen when the previous epoch's batches are all drawn
+        assert len(shuffles) == 3
+        assert shuffles == ([0, n_per, 2 * n_per] if prefetch else [0, n_per, 2 * n_per])
+        seen[prefetch] = (torch.stack([b for b in model.batches if b.shape[1] == model.batches[0].shape[1]]),
+                          np.random.get_state()[1].copy(), random.getstate())
+    assert torch.equal(seen[False][0], seen[True][0])
+    assert np.array_equal(seen[False][1], seen[True][1]) and seen[False][2] == seen[True][2]
