@@ -194,17 +194,10 @@ splitk_reduce_kernel(const float *__restrict__ ws, const float *__restrict__ bia
                      int64_t mn, int N, int splits) {
   const int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
   if (i >= mn) return;
-  // all slabs of a batch in flight at once (one memory round trip instead of one per split), added in
-  // split order
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z0 = 0; z0 < splits; z0 += 8) {
-    float4 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      v[u] = z0 + u < splits ? __ldcs(reinterpret_cast<const float4 *>(ws + (size_t)(z0 + u) * mn + i))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+  float4 s = *reinterpret_cast<const float4 *>(ws + i);
+  for (int z = 1; z < splits; ++z) {
+    const float4 v = *reinterpret_cast<const float4 *>(ws + (size_t)z * mn + i);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   if (bias) {
     const int c = (int)(i % N);

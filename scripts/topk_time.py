@@ -1,5 +1,5 @@
-"""Fused scoring + mask + top-K timing (incl. the merge): default tiling vs MMREC_TOPK_256=0 (one 128-user tile per
-CTA); random tables, realistic train masks are not needed for the timing (the mask cursor is O(history))."""
+"""Fused scoring + mask + top-K timing (incl. the merge); random tables, realistic train masks are not needed for the
+timing (the mask cursor is O(history))."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,4 +20,4 @@ for (nu, ni, d, k) in [(9130, 7050, 64, 50), (16716, 18357, 64, 50), (16384, 100
     users = torch.arange(nu, device=DEV)
     S = ops.choose_splits(nu, ni)
     t = timeit(lambda: ops.score_mask_topk(ue, users, ie, k))
-    print(f"tile256={os.environ.get('MMREC_TOPK_256', '1')} d={d} K={k} U={nu} I={ni} splits={S}: {t*1e3:.1f} us", flush=True)
+    print(f"d={d} K={k} U={nu} I={ni} splits={S}: {t*1e3:.1f} us", flush=True)
