@@ -925,9 +925,17 @@ class _SmoreSide(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad)
         saved = torch.empty(7, n, d, dtype=torch.float32, device=F.device) if need_bwd else None
         side, all_e = torch.empty_like(F), torch.empty_like(F)
-        if drop is not None:
-            if masks is not None:
-                raise RuntimeError("smore_side: pass either mask tensors or an in-kernel dropout spec")
+        if drop is not None and masks is not None:
+            raise RuntimeError("smore_side: pass either mask tensors or an in-kernel dropout spec")
+        tc_ws = lib.load().mmrec_smore_side_fwd_tc_workspace_bytes(d) if masks is None else 0
+        if tc_ws:
+            # tcgen05 forward (d = 64): weights pre-split into UMMA images in a 224 KB workspace
+            ws = torch.empty(tc_ws + 1024, dtype=torch.uint8, device=F.device)
+            ws_ptr = (ws.data_ptr() + 1023) & ~1023
+            lib.call("mmrec_smore_side_fwd_tc_f32", lib.ptr(F), lib.ptr(V), lib.ptr(T), lib.ptr(C_),
+                     _ptr_array(Ws), _ptr_array(bs), ctypes.byref(lib.Dropout.make(*drop)) if drop is not None else None,
+                     lib.ptr(saved), lib.ptr(side), lib.ptr(all_e), n, d, ws_ptr, lib.stream())
+        elif drop is not None:
             lib.call("mmrec_smore_side_fwd_drop_f32", lib.ptr(F), lib.ptr(V), lib.ptr(T), lib.ptr(C_),
                      _ptr_array(Ws), _ptr_array(bs), ctypes.byref(lib.Dropout.make(*drop)), lib.ptr(saved), lib.ptr(side),
                      lib.ptr(all_e), n, d, lib.stream())

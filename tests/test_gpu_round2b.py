@@ -37,9 +37,11 @@ def _layers(d, seed):
 
 
 @pytest.mark.parametrize("n,d,p", [(26495, 64, 0.5), (333, 32, 0.2), (6001, 128, 0.1), (65, 64, 0.9)])
-def test_smore_side_inkernel_dropout_equals_explicit_masks(n, d, p):
+def test_smore_side_inkernel_dropout_equals_explicit_masks(n, d, p, monkeypatch):
     """mmrec_smore_side_*_drop_f32 == mmrec_smore_side_*_f32 fed the masks the generator writes out
-    (forward outputs and every gradient bit-identical): forward and backward regenerate one mask."""
+    (forward outputs and every gradient bit-identical): forward and backward regenerate one mask.
+    (Both on the mma.sync forward: the tcgen05 forward is compared with it in its own test.)"""
+    monkeypatch.setenv("MMREC_SIDE_TC", "0")
     ops = pkg("ops")
     layers = _layers(d, 5)
     gen = torch.Generator().manual_seed(n)
@@ -89,9 +91,12 @@ def test_smore_combine_inkernel_dropout_equals_explicit_masks(n, d, p):
         assert torch.equal(u, v)
 
 
-def test_inkernel_dropout_draws_fresh_masks_on_graph_replay():
+@pytest.mark.parametrize("tc", ["0", "1"])
+def test_inkernel_dropout_draws_fresh_masks_on_graph_replay(tc, monkeypatch):
     """A captured launch reads the counter on the device: replays after the counter moved use the
-    mask of the new count (what FusedAdam's update count provides inside a captured training step)."""
+    mask of the new count (what FusedAdam's update count provides inside a captured training step).
+    Both forwards: mma.sync (bit-identical to the explicit-mask module) and tcgen05 (to fp32 rounding)."""
+    monkeypatch.setenv("MMREC_SIDE_TC", tc)
     ops = pkg("ops")
     n, d, p = 4000, 64, 0.5
     layers = _layers(d, 9)
@@ -109,7 +114,10 @@ def test_inkernel_dropout_draws_fresh_masks_on_graph_replay():
             cnt.fill_(c)
             g.replay()
             want, _ = ops.smore_side(*ins, layers, ops.dropout_mask(3, n, d, (p, 4242, _counter(c))))
-            assert torch.equal(a, want)
+            if tc == "0":
+                assert torch.equal(a, want)
+            else:
+                assert float((a - want).abs().max() / want.abs().max()) < 2e-6
             outs.append(a.clone())
     assert not torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]) and not torch.equal(outs[2], outs[3])
 
@@ -179,3 +187,61 @@ def test_smore_side_inference_forward_keeps_nothing():
     assert torch.equal(a0, a1) and torch.equal(s0, s1)
     assert not a0.requires_grad and a1.requires_grad
     assert torch.cuda.memory_allocated() - before <= 2 * n * d * 4 + (1 << 20)      # the two outputs, no [7, n, d]
+
+
+# ------------------------------------------------------------------ a10: preference module forward on tcgen05
+@pytest.mark.parametrize("n,p,keep", [(26495, 0.5, True), (26495, 0.0, False), (1, 0.0, True), (129, 0.3, True),
+                                      (128 * 148 * 2 + 77, 0.1, True)])
+def test_smore_side_forward_tcgen05_matches_mma_sync_and_float64(n, p, keep, monkeypatch):
+    """mmrec_smore_side_fwd_tc_f32 (d = 64: A operands in TMEM, pre-split weight images streamed by bulk
+    copies, sixteen epilogue warps) against the mma.sync forward and against float64: outputs and the
+    seven saved tensors to fp32 rounding, the same dropout pattern, the mma.sync backward on its saved
+    tensors gives the same gradients; ragged last tile, one row, more tiles than SMs, inference
+    (saved = NULL)."""
+    ops = pkg("ops")
+    d = 64
+    layers = _layers(d, 11)
+    for l in layers:
+        l.weight.data *= 3.0
+    gen = torch.Generator().manual_seed(n)
+    ins = [torch.randn(n, d, generator=gen).to(DEV) for _ in range(4)]
+    ga, gs = torch.randn(n, d, generator=gen).to(DEV), torch.randn(n, d, generator=gen).to(DEV)
+    spec = (p, 99, _counter(7)) if p > 0 else None
+    res = {}
+    for tc in ("0", "1"):
+        monkeypatch.setenv("MMREC_SIDE_TC", tc)
+        x = [t.clone().requires_grad_(keep) for t in ins]
+        for l in layers:
+            l.zero_grad()
+        if keep:
+            a, s = ops.smore_side(*x, layers, None, spec)
+            ((a * ga).sum() + (s * gs).sum()).backward()
+            res[tc] = [a.detach(), s.detach()] + [t.grad for t in x] + [l.weight.grad.clone() for l in layers]
+        else:
+            with torch.no_grad():
+                a, s = ops.smore_side(*x, layers, None, spec)
+            res[tc] = [a, s]
+    rel = lambda u, v: float((u.double() - v.double()).abs().max() / v.double().abs().max().clamp_min(1e-12))
+    for i, (u, v) in enumerate(zip(res["1"], res["0"])):
+        assert rel(u, v) < 5e-6, i
+    if p > 0:      # the same elements are dropped: side - (pf f)/3 ... is not observable directly; compare zero patterns of a probe
+        monkeypatch.setenv("MMREC_SIDE_TC", "1")
+        probe = [torch.ones(n, d, device=DEV) for _ in range(4)]
+        a1, s1 = ops.smore_side(*probe, layers, None, spec)
+        monkeypatch.setenv("MMREC_SIDE_TC", "0")
+        a0, s0 = ops.smore_side(*probe, layers, None, spec)
+        assert rel(s1, s0) < 5e-6
+    # float64 reference (masks materialised by the generator)
+    masks = ops.dropout_mask(3, n, d, spec).double().cpu() if p > 0 else None
+    lin = torch.nn.functional.linear
+    L64 = [torch.nn.Linear(d, d, bias=l.bias is not None).double() for l in layers]
+    for a_, b_ in zip(L64, layers):
+        a_.load_state_dict({k: v.double().cpu() for k, v in b_.state_dict().items()})
+    F, V, T, C = [t.double().cpu() for t in ins]
+    qv = lin(torch.tanh(lin(F, L64[0].weight, L64[0].bias)), L64[1].weight)
+    qt = lin(torch.tanh(lin(F, L64[2].weight, L64[2].bias)), L64[3].weight)
+    gate = lambda l: torch.sigmoid(lin(C, l.weight, l.bias))
+    m = masks if masks is not None else torch.ones(3, n, d, dtype=torch.float64)
+    side64 = (m[0] * gate(L64[4]) * torch.softmax(qv, -1) * V + m[1] * gate(L64[5]) * torch.softmax(qt, -1) * T +
+              m[2] * gate(L64[6]) * F) / 3
+    assert rel(res["1"][1], side64) < 1e-5 and rel(res["1"][0], C + side64) < 1e-5
