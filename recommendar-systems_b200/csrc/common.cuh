@@ -42,6 +42,35 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (griddepcontrol) ----------------------------------------------
+// A kernel launched with launch_pdl(..., pdl = true) may start while the kernel before it on the
+// stream is still running, once every CTA of that kernel has executed pdl_trigger() (or exited). What
+// it does before pdl_wait() overlaps the predecessor's tail: only data no kernel of the step writes
+// (CSR arrays, task lists) may be touched there. pdl_wait() returns when the predecessor grid has
+// completed and its writes are visible. Without the launch attribute both instructions are no-ops.
+// Works inside stream capture (the edge becomes a programmatic graph edge). MMREC_PDL=0 turns the
+// attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- in-kernel dropout (nn.Dropout of smore.py:331-333 without mask tensors) --------------------
 // The multiplier of element (plane, row, 4-column group) is a pure function of a 64-bit stream key
 // and the element index: forward and backward regenerate the same mask, nothing is written to HBM

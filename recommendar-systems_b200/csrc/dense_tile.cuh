@@ -129,16 +129,23 @@ __device__ __forceinline__ void tile_mma_tc(float *__restrict__ out, int PO, int
   for (int k8 = 0; k8 < KK; k8 += 8) {
     uint32_t ah[4], al[4];
     auto A = [&](int m, int k) { return TRANS_A ? As[k * PA + m] : As[m * PA + k]; };
-    split_tf32_u(A(rs + g, k8 + t), ah[0], al[0]);
-    split_tf32_u(A(rs + g + 8, k8 + t), ah[1], al[1]);
-    split_tf32_u(A(rs + g, k8 + t + 4), ah[2], al[2]);
-    split_tf32_u(A(rs + g + 8, k8 + t + 4), ah[3], al[3]);
+    // Both operands k-major in shared memory (the dW = dz^T X products): with the MMA's own k slots
+    // (t, t + 4) a warp's 32 loads fall on banks 4 t + g of a pitch = 4 (mod 32) tile -- two-way
+    // conflicts on every A and B fragment load (29 % of side_bwd's shared wavefronts, ncu). The sum
+    // over k does not care which staged row feeds which slot as long as A and B agree: slot t reads row
+    // 2 t, slot t + 4 row 2 t + 1 -> banks 8 t + g, conflict-free.
+    constexpr bool KPERM = TRANS_A && !TRANS_B;
+    const int ka = KPERM ? k8 + 2 * t : k8 + t, kb = KPERM ? k8 + 2 * t + 1 : k8 + t + 4;
+    split_tf32_u(A(rs + g, ka), ah[0], al[0]);
+    split_tf32_u(A(rs + g + 8, ka), ah[1], al[1]);
+    split_tf32_u(A(rs + g, kb), ah[2], al[2]);
+    split_tf32_u(A(rs + g + 8, kb), ah[3], al[3]);
 #pragma unroll
     for (int j = 0; j < T::NF; ++j) {
       uint32_t bh[2], bl[2];
       const int n = cs + j * 8 + g;
-      split_tf32_u(TRANS_B ? Bs[n * PB + k8 + t] : Bs[(k8 + t) * PB + n], bh[0], bl[0]);
-      split_tf32_u(TRANS_B ? Bs[n * PB + k8 + t + 4] : Bs[(k8 + t + 4) * PB + n], bh[1], bl[1]);
+      split_tf32_u(TRANS_B ? Bs[n * PB + ka] : Bs[ka * PB + n], bh[0], bl[0]);
+      split_tf32_u(TRANS_B ? Bs[n * PB + kb] : Bs[kb * PB + n], bh[1], bl[1]);
       mma_tf32_16x8x8(c[j], al, bh);
       mma_tf32_16x8x8(c[j], ah, bl);
       mma_tf32_16x8x8(c[j], ah, bh);

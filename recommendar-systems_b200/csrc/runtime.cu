@@ -2,6 +2,8 @@
 #include <atomic>
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mmrec {
@@ -17,6 +19,10 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {   // read per call so that one process can compare both settings
+  const char *e = getenv("MMREC_PDL");
+  return !(e && atoi(e) == 0);
+}
 }  // namespace mmrec
 
 extern "C" int mmrec_abi_version(void) { return 1; }

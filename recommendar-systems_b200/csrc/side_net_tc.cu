@@ -410,9 +410,17 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
   }
 }
 
-inline bool side_tc_enabled() {   // read per call: the tests compare both forwards inside one process
+// Which forward runs (read per call: the tests compare both inside one process). MMREC_SIDE_TC=1 / 0 forces
+// the tcgen05 / the mma.sync kernel; unset, the measured cost model decides (B200, profiles/r02_side_tc.txt):
+// a CTA walks its 128-row tiles one after another at ~26.5 us per tile after ~25 us of fill, the mma.sync
+// kernel streams ~2.3 ns per row -- the tensor-memory kernel wins from ~31 k rows on (Sports: 89 vs 125 us),
+// loses at Baby size (26 495 rows = two rounds of tiles on 148 SMs: 79 vs 69 us).
+inline bool side_tc_pick(int n, int d) {
+  if (d != kD) return false;
   const char *e = getenv("MMREC_SIDE_TC");
-  return !(e && atoi(e) == 0);
+  if (e) return atoi(e) != 0;
+  const long tiles = ((long)n + kRows - 1) / kRows, rounds = (tiles + kNumSMs - 1) / kNumSMs;
+  return 25000 + 26500 * rounds < 6000 + 2300 * (long)n / 1000;
 }
 
 }  // namespace
@@ -420,8 +428,8 @@ inline bool side_tc_enabled() {   // read per call: the tests compare both forwa
 
 using namespace mmrec;
 
-extern "C" size_t mmrec_smore_side_fwd_tc_workspace_bytes(int32_t d) {
-  return d == kD && side_tc_enabled() ? (size_t)kImgTotal : 0;
+extern "C" size_t mmrec_smore_side_fwd_tc_workspace_bytes(int32_t n, int32_t d) {
+  return side_tc_pick(n, d) ? (size_t)kImgTotal : 0;
 }
 
 extern "C" int mmrec_smore_side_fwd_tc_f32(const float *F, const float *V, const float *T, const float *C_,

@@ -89,10 +89,12 @@ constexpr int kDepth = 8;  // embedding-row gathers in flight per lane
 // column index / value of the task is fetched in ONE round (kSeg / LANES per lane), then the rows
 // are gathered kDepth at a time (16 bytes per lane each); partial groups are predicated off, not
 // padded. The sum runs in CSR order whatever the grouping.
-template <int LANES, int CHUNKS, bool STREAM = false>
+// `after_indices()` runs between the index round and the first gather: the kernels put pdl_wait() there
+// (the CSR arrays and the task list are never written by a kernel of the step, X is).
+template <int LANES, int CHUNKS, bool STREAM = false, typename Hook>
 __device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t *__restrict__ col_idx,
                                             const float *__restrict__ vals, int begin, int end, int lane,
-                                            const float *__restrict__ X, int d, int col_offset) {
+                                            const float *__restrict__ X, int d, int col_offset, Hook &&after_indices) {
   uint64_t pol_first = 0, pol_last = 0;
   if constexpr (STREAM) { pol_first = policy_evict_first(); pol_last = policy_evict_last(); }
   constexpr int NIDX = kSeg / LANES;
@@ -115,6 +117,15 @@ __device__ __forceinline__ void gather_rows(float4 (&acc)[CHUNKS], const int32_t
         v[i] = ld_stream_f32(vals + k);
       }
     }
+  }
+  {
+    // ptxas is free to sink loads below griddepcontrol.wait (an acquire): the hook gets a value that
+    // depends on every index load and makes its wait conditional on it (never false), which pins the
+    // loads in front of the wait.
+    int probe = 0;
+#pragma unroll
+    for (int i = 0; i < NIDX; ++i) probe |= c[i] | (int)__float_as_uint(v[i]);
+    after_indices(probe);
   }
 #pragma unroll
   for (int i = 0; i < NIDX; ++i) {
@@ -233,13 +244,18 @@ __device__ __forceinline__ void run_task(const Problem &P, int t, int lane, int 
   float4 acc[CHUNKS];
 #pragma unroll
   for (int q = 0; q < CHUNKS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (task.w < 0) {
-    // start fetching the epilogue operands of this row while the gathers are in flight
-    const size_t o = (size_t)row * d + lane * 4;
-    if (ep.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.acc_in + o));
-    if (ep.cos_ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.cos_ref + o));
-  }
-  gather_rows<LANES, CHUNKS, STREAM>(acc, P.col_idx, P.vals, task.y, task.z, lane, P.X, d, P.col_offset);
+  gather_rows<LANES, CHUNKS, STREAM>(acc, P.col_idx, P.vals, task.y, task.z, lane, P.X, d, P.col_offset, [&](int probe) {
+    // Everything above read graph constants only (task, column indices, values): under programmatic
+    // dependent launch it ran while the previous layer's launch was still finishing. From here on the
+    // kernel touches what that launch wrote.
+    if (probe != 0x7fc00001) pdl_wait();      // (a NaN payload no adjacency value carries, OR-ed with indices >= 0)
+    if (task.w < 0) {
+      // start fetching the epilogue operands of this row while the gathers are in flight
+      const size_t o = (size_t)row * d + lane * 4;
+      if (ep.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.acc_in + o));
+      if (ep.cos_ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.cos_ref + o));
+    }
+  });
   if (task.w >= 0) {
     // heavy row: publish this part, the last arriver reduces all parts in order
     const unsigned mask = group_mask<LANES>();
@@ -286,6 +302,7 @@ template <int LANES, int CHUNKS, bool STREAM = false>
 __global__ void __launch_bounds__(kThreads, CHUNKS == 1 || LANES <= 16 ? 4 : 3)
 spmm_csr_kernel(const Problem P, int d) {
   constexpr int GROUPS = kThreads / LANES;
+  pdl_trigger();     // the next launch may park its CTAs (and read its task list) behind this one's last wave
   const int lane = threadIdx.x % LANES;
   const int t = blockIdx.x * GROUPS + threadIdx.x / LANES;
   if (t >= P.n_tasks) return;
@@ -305,6 +322,7 @@ template <int LANES, int CHUNKS>
 __global__ void __launch_bounds__(kThreads, CHUNKS == 1 ? 4 : 3)
 spmm_csr_multi_kernel(const MultiArgs A, int d) {
   constexpr int GROUPS = kThreads / LANES;
+  pdl_trigger();
   int pi = 0;
   while (pi + 1 < A.n && (int)blockIdx.x >= A.block_end[pi]) ++pi;
   const int b0 = pi == 0 ? 0 : A.block_end[pi - 1];
@@ -422,8 +440,8 @@ static int spmm_csr_impl(int flags, const int32_t *row_ptr, const int32_t *col_i
     constexpr int L = decltype(lanes)::value, C = decltype(chunks)::value;
     constexpr int GROUPS = kThreads / L;
     const int blocks = (n_tasks + GROUPS - 1) / GROUPS;
-    if (streaming) spmm_csr_kernel<L, C, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
-    else spmm_csr_kernel<L, C, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P, d);
+    if (streaming) MMREC_CUDA(launch_pdl(spmm_csr_kernel<L, C, true>, blocks, kThreads, 0, (cudaStream_t)stream, P, d));
+    else MMREC_CUDA(launch_pdl(spmm_csr_kernel<L, C, false>, blocks, kThreads, 0, (cudaStream_t)stream, P, d));
     MMREC_CHECK_LAUNCH("spmm_csr_kernel");
     return MMREC_OK;
   };
@@ -477,7 +495,7 @@ extern "C" int mmrec_spmm_csr_multi_f32(const MmrecSpmmProblem *problems_host, i
       blocks += (A.p[i].n_tasks + GROUPS - 1) / GROUPS;
       A.block_end[i] = blocks;
     }
-    spmm_csr_multi_kernel<L, C><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(A, d);
+    MMREC_CUDA(launch_pdl(spmm_csr_multi_kernel<L, C>, blocks, kThreads, 0, (cudaStream_t)stream, A, d));
     MMREC_CHECK_LAUNCH("spmm_csr_multi_kernel");
     return MMREC_OK;
   });

@@ -244,4 +244,4 @@ def test_smore_side_forward_tcgen05_matches_mma_sync_and_float64(n, p, keep, mon
     m = masks if masks is not None else torch.ones(3, n, d, dtype=torch.float64)
     side64 = (m[0] * gate(L64[4]) * torch.softmax(qv, -1) * V + m[1] * gate(L64[5]) * torch.softmax(qt, -1) * T +
               m[2] * gate(L64[6]) * F) / 3
-    assert rel(res["1"][1], side64) < 1e-5 and rel(res["1"][0], C + side64) < 1e-5
+    assert rel(res["1"][1].cpu(), side64) < 1e-5 and rel(res["1"][0].cpu(), C + side64) < 1e-5
