@@ -327,8 +327,8 @@ int mmrec_smore_side_fwd_drop_f32(const float *F, const float *V, const float *T
 /* The forward on the 5th-generation tensor cores (tcgen05 + TMEM, d = 64, no mask tensor: in-kernel
  * dropout or none): same outputs as mmrec_smore_side_fwd_drop_f32 to fp32 rounding. `ws` = scratch of
  * mmrec_smore_side_fwd_tc_workspace_bytes(n, d) bytes, 1024-byte aligned (the pre-split weight images);
- * that function returns 0 when this path does not cover d, or when the mma.sync forward is the faster
- * one for n rows (measured cost model; MMREC_SIDE_TC=1 / 0 forces either kernel). */
+ * that function returns 0 when this path does not cover d (or under MMREC_SIDE_TC=0, which keeps the
+ * mma.sync forward: the A/B switch of the tests and of profiles/r02_side_tc.txt). */
 size_t mmrec_smore_side_fwd_tc_workspace_bytes(int32_t n, int32_t d);
 int mmrec_smore_side_fwd_tc_f32(const float *F, const float *V, const float *T, const float *C,
                                 const float *const *W_host, const float *const *b_host,

@@ -48,8 +48,8 @@ constexpr int kNumSMs = 148;  // B200
 // it does before pdl_wait() overlaps the predecessor's tail: only data no kernel of the step writes
 // (CSR arrays, task lists) may be touched there. pdl_wait() returns when the predecessor grid has
 // completed and its writes are visible. Without the launch attribute both instructions are no-ops.
-// Works inside stream capture (the edge becomes a programmatic graph edge). MMREC_PDL=0 turns the
-// attribute off.
+// Works inside stream capture (the edge becomes a programmatic graph edge). The attribute is set only
+// under MMREC_PDL=1 (see pdl_enabled() in runtime.cu for the measurement).
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -119,7 +119,8 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
   float *buf0 = reinterpret_cast<float *>(smem + 2 * kStageBytes);
   float *buf1 = buf0 + kRows * kPitch;
   float *red = buf1 + kRows * kPitch;                          // [4][4][128] softmax exchanges
-  uint64_t *bars = reinterpret_cast<uint64_t *>(red + 4 * 4 * kRows);
+  float *sbias = red + 4 * 4 * kRows;                          // [5][64]: b of q1v, q1t, gi, gt, gf (0 where absent)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sbias + 5 * kD);
   uint64_t *wfull = bars, *wempty = bars + 2, *a_ready = bars + 4, *s1_done = bars + 5, *e1_done = bars + 6,
            *s2_done = bars + 7, *e2_done = bars + 8, *s3_done = bars + 9;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
@@ -132,6 +133,11 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
     fence_barrier_init();
   }
   if (warp == kMmaWarpS) tmem_alloc(tmem_slot, 512);
+  if (tid < 5 * kD) {                                          // a global round trip per bias use otherwise
+    const int k = tid / kD;
+    const float *b = A.b[k == 0 ? 0 : k == 1 ? 2 : k + 2];
+    sbias[tid] = b != nullptr ? b[tid % kD] : 0.f;
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -197,7 +203,9 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
     const uint64_t drop_key = A.drop.p > 0.f ? drop_stream(A.drop) : 0ull;
     const size_t nd = (size_t)n * kD;
 
-    // coalesced global -> staging of one [128, 64] tile (rows past n: zeros)
+    // coalesced global -> staging of one [128, 64] tile (rows past n: zeros). (Hoisting these loads above the
+    // previous phase's write-out -- two-phase staging with the values parked in registers -- was measured:
+    // 45.7 vs 45.3 us, the 32 extra live registers spill at the 96-register cap of a 17-warp CTA.)
     auto stage_in = [&](float *buf, const float *__restrict__ src, int row0) {
       float4 v[4];
 #pragma unroll
@@ -253,11 +261,10 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(t[j]);
     };
-    auto add_bias = [&](float (&x)[16], const float *__restrict__ b) {
-      if (b == nullptr) return;
+    auto add_bias = [&](float (&x)[16], int k) {               // k: row of sbias
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 t = ldg4(b + c0 + 4 * j);
+        const float4 t = *reinterpret_cast<const float4 *>(sbias + k * kD + c0 + 4 * j);
         x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w;
       }
     };
@@ -266,14 +273,14 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
     for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t p = it & 1;
       const int row0 = tile * kRows, grow = row0 + r;
-      float x[16], y[16];
+      float x[16], y[16], f[16];
       // ---------------- E0: F, C -> A operands in TMEM
       stage_in(buf0, A.F, row0);
       stage_in(buf1, A.C, row0);
       epi_bar();
-      own_load(buf0, x);
+      own_load(buf0, f);                         // kept in registers for E3 (Hv takes its TMEM columns)
       own_load(buf1, y);
-      to_tmem(kColF, x);
+      to_tmem(kColF, f);
       to_tmem(kColC, y);
       tmem_st_wait();
       fence_before_sync();
@@ -283,8 +290,8 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
       fence_after_sync();
       from_tmem(kColQ, x);
       from_tmem(kColQ + 64, y);
-      add_bias(x, A.b[0]);
-      add_bias(y, A.b[2]);
+      add_bias(x, 0);
+      add_bias(y, 1);
 #pragma unroll
       for (int j = 0; j < 16; ++j) { x[j] = fast_tanh(x[j]); y[j] = fast_tanh(y[j]); }
       to_tmem(kColF, x);                         // Hv over F (S1 is complete)
@@ -352,8 +359,6 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
         epi_bar();
       }
       // ---------------- E3: gates, dropout, side, all
-      stage_in(buf0, A.F, row0);
-      stage_in(buf1, A.C, row0);
       mbar_wait(s3_done, p);
       fence_after_sync();
       float sd[16];
@@ -361,15 +366,10 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
       for (int j = 0; j < 16; ++j) sd[j] = 0.f;
       float *const sv_out[3] = {A.saved != nullptr ? A.saved + 4 * nd : nullptr, A.saved != nullptr ? A.saved + 5 * nd : nullptr,
                                 A.saved != nullptr ? A.saved + 6 * nd : nullptr};
-      epi_bar();                                 // F, C tiles are staged
-      float f[16];
-      own_load(buf0, f);
-      own_load(buf1, y);                         // c
-      epi_bar();                                 // the buffers now stage the gate outputs
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         from_tmem(g == 0 ? kColQ : g == 1 ? kColQ + 64 : kColG, x);
-        add_bias(x, A.b[4 + g]);
+        add_bias(x, 2 + g);
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = fast_sigmoid(x[j]);
         float *buf = (g & 1) ? buf1 : buf0;
@@ -388,11 +388,15 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
           stage_out(buf, sv_out[g], row0);       // (the next gate stages into the other buffer)
         }
       }
+      // c comes back from its A-operand columns: hi + lo is the fp32 value exactly (lo = c - hi is exact and
+      // the columns keep all 32 bits; the tensor core is what ignores the low ones)
+      from_tmem(kColC, y);
+      from_tmem(kColC + kD, x);
       epi_bar();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         sd[j] *= (1.f / 3.f);
-        y[j] += sd[j];
+        y[j] = (y[j] + x[j]) + sd[j];
       }
       own_store(buf0, sd);
       own_store(buf1, y);
@@ -410,17 +414,16 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
   }
 }
 
-// Which forward runs (read per call: the tests compare both inside one process). MMREC_SIDE_TC=1 / 0 forces
-// the tcgen05 / the mma.sync kernel; unset, the measured cost model decides (B200, profiles/r02_side_tc.txt):
-// a CTA walks its 128-row tiles one after another at ~26.5 us per tile after ~25 us of fill, the mma.sync
-// kernel streams ~2.3 ns per row -- the tensor-memory kernel wins from ~31 k rows on (Sports: 89 vs 125 us),
-// loses at Baby size (26 495 rows = two rounds of tiles on 148 SMs: 79 vs 69 us).
+// Which forward runs (read per call: the tests compare both inside one process): the tcgen05 kernel for
+// d = 64 unless MMREC_SIDE_TC=0. Measured inside the captured SMORE / Baby step (profiles/r02_side_tc.txt):
+// 50 + 2 us (kernel + weight images) against 61 us for the mma.sync kernel, step 2.374 -> 2.325 ms; Sports
+// (54 k rows): 89 against 125 us. (Timed as an eager op the order flips at Baby size -- 77 vs 69 us -- because
+// the two launches and the workspace allocation cost ~10 us of host time that a graph replay does not pay.)
 inline bool side_tc_pick(int n, int d) {
+  (void)n;
   if (d != kD) return false;
   const char *e = getenv("MMREC_SIDE_TC");
-  if (e) return atoi(e) != 0;
-  const long tiles = ((long)n + kRows - 1) / kRows, rounds = (tiles + kNumSMs - 1) / kNumSMs;
-  return 25000 + 26500 * rounds < 6000 + 2300 * (long)n / 1000;
+  return !(e && atoi(e) == 0);
 }
 
 }  // namespace
@@ -464,7 +467,7 @@ extern "C" int mmrec_smore_side_fwd_tc_f32(const float *F, const float *V, const
   A.ws = static_cast<const uint8_t *>(ws);
   A.n = n;
   A.n_tiles = (n + kRows - 1) / kRows;
-  const size_t smem = 1024 + 2 * (size_t)kStageBytes + 2 * (size_t)kBufBytes + 4 * 4 * kRows * 4 + 10 * 8 + 16;
+  const size_t smem = 1024 + 2 * (size_t)kStageBytes + 2 * (size_t)kBufBytes + 4 * 4 * kRows * 4 + 5 * kD * 4 + 10 * 8 + 16;
   static bool attr = false;
   if (!attr) {
     MMREC_CUDA(cudaFuncSetAttribute(side_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -929,8 +929,7 @@ class _SmoreSide(torch.autograd.Function):
             raise RuntimeError("smore_side: pass either mask tensors or an in-kernel dropout spec")
         tc_ws = lib.load().mmrec_smore_side_fwd_tc_workspace_bytes(n, d) if masks is None else 0
         if tc_ws:
-            # tcgen05 forward (d = 64, row counts where it beats the mma.sync kernel): weights pre-split into UMMA
-            # images in a 224 KB workspace
+            # tcgen05 forward (d = 64): weights pre-split into UMMA images in a 224 KB workspace
             ws = torch.empty(tc_ws + 1024, dtype=torch.uint8, device=F.device)
             ws_ptr = (ws.data_ptr() + 1023) & ~1023
             lib.call("mmrec_smore_side_fwd_tc_f32", lib.ptr(F), lib.ptr(V), lib.ptr(T), lib.ptr(C_),

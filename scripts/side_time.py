@@ -29,3 +29,15 @@ for n in [int(a) for a in sys.argv[1:]] or [26495, 54738, 85268]:
                     return ops.smore_side(*x, layers, None, (0.5, 7, cnt))
             t = timeit(run)
             print(f"n={n} saved={keep} MMREC_SIDE_TC={tc}: {t*1e3:.1f} us", flush=True)
+# training forward + backward on the mma.sync kernels (the backward has no tcgen05 version)
+os.environ["MMREC_SIDE_TC"] = "0"
+for n in [26495]:
+    x = [t.clone().requires_grad_(True) for t in ins] if ins[0].shape[0] == n else None
+    if x is None:
+        ins = [torch.randn(n, 64, device=DEV) for _ in range(4)]
+        x = [t.clone().requires_grad_(True) for t in ins]
+    ga, gs = torch.randn(n, 64, device=DEV), torch.randn(n, 64, device=DEV)
+    def run_fb():
+        a, s = ops.smore_side(*x, layers, None, (0.5, 7, cnt))
+        torch.autograd.backward([a, s], [ga, gs])
+    print(f"n={n} fwd+bwd (mma.sync): {timeit(run_fb)*1e3:.1f} us", flush=True)

@@ -245,3 +245,34 @@ def test_smore_side_forward_tcgen05_matches_mma_sync_and_float64(n, p, keep, mon
     side64 = (m[0] * gate(L64[4]) * torch.softmax(qv, -1) * V + m[1] * gate(L64[5]) * torch.softmax(qt, -1) * T +
               m[2] * gate(L64[6]) * F) / 3
     assert rel(res["1"][1].cpu(), side64) < 1e-5 and rel(res["1"][0].cpu(), C + side64) < 1e-5
+
+
+# ------------------------------------------------------------------ a6: programmatic dependent launch (opt-in)
+def test_spmm_chain_under_programmatic_dependent_launch_is_bit_identical(monkeypatch):
+    """MMREC_PDL=1: the SpMM launches of a propagation carry the programmatic-serialization attribute,
+    read their task / index round before griddepcontrol.wait and everything the previous launch wrote
+    after it. Eager and CUDA-graph replay, forward chain and Horner backward: same bits as MMREC_PDL=0."""
+    ops, G, synth = pkg("ops"), pkg("graph"), pkg("synth")
+    d = synth.make_dataset("tiny", features=False)
+    u, i = d.split(0)
+    g = G.build_ui_graph(torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), d.n_users, d.n_items, "f32")
+    X = torch.randn(g.n_cols, 64, device=DEV)
+    res = {}
+    for pdl in ("0", "1"):
+        monkeypatch.setenv("MMREC_PDL", pdl)
+        y = ops._PropagateMean.apply(X, g, 4)
+        z = ops._horner(g, y, 4, 0.2)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            ops._PropagateMean.apply(X, g, 4)
+            s.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                yg = ops._PropagateMean.apply(X, g, 4)
+                zg = ops._horner(g, yg, 4, 0.2)
+            for _ in range(3):
+                gr.replay()
+            s.synchronize()
+        assert torch.equal(y, yg) and torch.equal(z, zg)
+        res[pdl] = (y, z)
+    assert torch.equal(res["0"][0], res["1"][0]) and torch.equal(res["0"][1], res["1"][1])
