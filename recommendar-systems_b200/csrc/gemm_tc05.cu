@@ -64,6 +64,10 @@ struct GemmArgs {
   double *sumsq_partial;            // optional: per-CTA sum of the updated parameters' squares
   int debug;                        // MMREC_TA_DEBUG (timing experiments only): 1 = no arithmetic, 2 = no copies
   int act;                          // EPI_STORE, no split-K: 0 = none, 1 = tanh, 2 = sigmoid after the bias
+  int flat;                         // table epilogues (no split-K): the (row tile, N tile) space is cut into gridDim.x
+                                    // equal contiguous shares instead of rectangles -- 56 x 128 tiles on 148 SMs are
+                                    // 48.4 tiles per CTA in ONE wave, where the best rectangle (5 column ranges) was
+                                    // 280 CTAs = two waves of 26 tiles, each paying its own pipeline fill
   int mt_per_cta;                   // consecutive 128-row tiles walked by one CTA (0 / 1: one). With more row tiles
                                     // than SMs a CTA keeps its pipeline full across tiles instead of paying the
                                     // fill (TMEM allocation, first DRAM round trips, drain) once per 64 KB of rows
@@ -157,7 +161,15 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
   const int n_nt_total = (g.N + NT - 1) / NT;
   const int nt_begin = blockIdx.z * g.nt_per_cta, nt_end = min(n_nt_total, nt_begin + g.nt_per_cta);
   const int n_kb = max(0, kb_end - kb_begin), n_nt = max(0, nt_end - nt_begin);
-  const int n_iter = n_kb * n_nt * n_mt;
+  // tile j of this CTA -> (N tile, first row): rectangular (row tiles x N range) or a contiguous share of the
+  // flattened (row tile, N tile) space
+  const long flat_total = (long)m_tiles_total * n_nt_total;
+  const int u0 = g.flat ? (int)(flat_total * blockIdx.x / gridDim.x) : 0;
+  const int u1 = g.flat ? (int)(flat_total * (blockIdx.x + 1) / gridDim.x) : 0;
+  const int n_tiles_cta = g.flat ? u1 - u0 : n_nt * n_mt;
+  auto tile_nt = [&](int j) { return g.flat ? (u0 + j) % n_nt_total : nt_begin + j % n_nt; };
+  auto tile_m0 = [&](int j) { return g.flat ? ((u0 + j) / n_nt_total) * kBM : m0 + (j / n_nt) * kBM; };
+  const int n_iter = n_kb * n_tiles_cta;
   const int n_ck = (n_kb + kChunkKB - 1) / kChunkKB;   // accumulator chunks per N tile
   const uint32_t smem_base = smem_u32(smem);
 
@@ -181,7 +193,7 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
     Block<NT, B_MN, C::GROUP_THREADS> b;
     for (int it = grp; it < n_iter; it += C::GROUPS) {
       const int tile = it / n_kb, kb = kb_begin + it % n_kb;
-      const int nt = nt_begin + tile % n_nt, m0t = m0 + (tile / n_nt) * kBM;
+      const int nt = tile_nt(tile), m0t = tile_m0(tile);
       const int k_lim = min(g.K, kb_end * kKB);
       a.load(g.A, g.lda, m0t, g.M, kb * kKB, k_lim, ptid);
       b.load(g.B, g.ldb, nt * NT, g.N, kb * kKB, k_lim, ptid);
@@ -266,12 +278,12 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
     constexpr int NBUF = 64 / NT >= 2 ? 2 : 1;           // tile buffers per warp (same shared memory either way)
     constexpr uint32_t TILE_BYTES = 3u * NBOX * 4096u;
     uint8_t *tiles0 = nullptr;
-    const int n_tiles = n_kb > 0 ? n_nt * n_mt : 0;
+    const int n_tiles = n_kb > 0 ? n_tiles_cta : 0;
     // tile jj of this warp -> its buffer jj % NBUF (issued by lane 0)
     auto issue_loads = [&](int jj) {
       uint8_t *t = tiles0 + (jj % NBUF) * TILE_BYTES;
       uint64_t *bar = pbar + warp * NBUF + jj % NBUF;
-      const int nn = (nt_begin + jj % n_nt) * NT, mm = m0 + (jj / n_nt) * kBM + warp * 32;
+      const int nn = tile_nt(jj) * NT, mm = tile_m0(jj) + warp * 32;
       mbar_arrive_expect_tx(bar, TILE_BYTES);
 #pragma unroll
       for (int b = 0; b < NBOX; ++b) {
@@ -290,7 +302,7 @@ gemm_tc05_kernel(const GemmArgs g, const __grid_constant__ TmaMaps3 maps) {
       }
     }
     for (int j = 0; j < n_tiles; ++j) {
-      const int n0 = (nt_begin + j % n_nt) * NT, m0j = m0 + (j / n_nt) * kBM;
+      const int n0 = tile_nt(j) * NT, m0j = tile_m0(j);
       const int m = m0j + warp * 32 + lane;
       const int rows_valid = min(32, g.M - (m0j + warp * 32));
       if constexpr (EPI == EPI_ADAM) {
@@ -478,6 +490,7 @@ int launch_table_epi(const GemmArgs &g, const TmaMaps3 &maps, int n_chunks, cuda
     attr = true;
   }
   dim3 grid((g.M + kBM - 1) / kBM, 1, n_chunks);
+  if (g.flat) grid = dim3(n_chunks, 1, 1);          // n_chunks = CTAs of the flat partition
   kern<<<grid, kThreadsG, smem, stream>>>(g, maps);
   MMREC_CHECK_LAUNCH(EPI == EPI_ADAM ? "gemm_tc05_kernel<adam>" : "gemm_tc05_kernel<sumsq>");
   return MMREC_OK;
@@ -594,8 +607,17 @@ static int table_adam_nt() {
   return nt;
 }
 
+static bool table_flat() {      // MMREC_TA_FLAT=0: the rectangular partition (A/B switch)
+  static const bool on = !(getenv("MMREC_TA_FLAT") && atoi(getenv("MMREC_TA_FLAT")) == 0);
+  return on;
+}
+
 static int table_grid(int rows, int cols, int *nt_per_cta, int nt) {
   const int m_tiles = (rows + kBM - 1) / kBM, n_tiles = cols / nt;
+  if (table_flat()) {
+    if (nt_per_cta) *nt_per_cta = n_tiles;
+    return (int)min((long)kNumSMs, (long)m_tiles * n_tiles);
+  }
   int chunks = best_parts(m_tiles, n_tiles, n_tiles, 1);
   const int per = (n_tiles + chunks - 1) / chunks;
   chunks = (n_tiles + per - 1) / per;
@@ -626,8 +648,9 @@ int table_adam_dispatch(float *P, float *Mo, float *V, const float *dY, const fl
     set_error("table_adam: cuTensorMapEncodeTiled failed");
     return MMREC_E_CUDA;
   }
-  if (nt == 32) return launch_table_epi<32, EPI_ADAM>(g, maps, ctas / m_tiles, stream);
-  return launch_table_epi<64, EPI_ADAM>(g, maps, ctas / m_tiles, stream);
+  g.flat = table_flat();
+  if (nt == 32) return launch_table_epi<32, EPI_ADAM>(g, maps, g.flat ? ctas : ctas / m_tiles, stream);
+  return launch_table_epi<64, EPI_ADAM>(g, maps, g.flat ? ctas : ctas / m_tiles, stream);
 }
 
 // per-CTA partial sums of ||dY W||_F^2 (same grid as table_adam_dispatch)
@@ -639,7 +662,8 @@ int table_sumsq_dispatch(const float *dY, const float *W, int rows, int cols, in
   g.sumsq_partial = sumsq_partial;
   const int ctas = table_grid(rows, cols, &g.nt_per_cta, 64);
   const int m_tiles = (rows + kBM - 1) / kBM;
-  return launch_table_epi<64, EPI_SUMSQ>(g, TmaMaps3{}, ctas / m_tiles, stream);
+  g.flat = table_flat();
+  return launch_table_epi<64, EPI_SUMSQ>(g, TmaMaps3{}, g.flat ? ctas : ctas / m_tiles, stream);
 }
 
 }  // namespace mmrec

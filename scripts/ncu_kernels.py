@@ -28,6 +28,7 @@ users = torch.arange(9130, device=DEV)
 layers = [torch.nn.Linear(d, d, bias=bb).to(DEV) for bb in (True, False, True, False, True, True, True)]
 ins = [torch.randn(N, d, device=DEV, requires_grad=True) for _ in range(4)]
 masks = torch.nn.functional.dropout(torch.ones(3, N, d, device=DEV), 0.1)
+drop_cnt = torch.tensor([3.0], dtype=torch.float64, device=DEV)
 side, content = torch.randn(N, d, device=DEV, requires_grad=True), torch.randn(N, d, device=DEV, requires_grad=True)
 bu = torch.randint(0, U, (2048,), device=DEV)
 bi = torch.randint(0, I, (2048,), device=DEV)
@@ -71,7 +72,9 @@ for rep in range(2):
     ops.gemm(dy, True, W, False, I, F, d)
     ops.spmm_raw(g, X, Y=Y, acc_in=X, acc_out=acc)
     ops.score_mask_topk(ue, users, ie, 50)
-    a, s = ops.smore_side(*ins, layers, masks)
+    a, s = ops.smore_side(*ins, layers, masks)                       # explicit masks: the mma.sync forward
+    (a.sum() + s.sum()).backward()
+    a, s = ops.smore_side(*ins, layers, None, (0.5, 7, drop_cnt))     # in-kernel dropout: the tcgen05 forward (d = 64)
     (a.sum() + s.sum()).backward()
     l = ops.infonce_pair(side, content, U, bu, bi, 0.2)
     l.backward()
