@@ -37,7 +37,8 @@ LABELS = [
     ("gemm_tc05_kernel dW", "gemm_tc05_kernel<1, 1, 64, 1, 0>", "last"),
     ("gemm_tc05_kernel<adam> (image table, low-rank gradient)", "gemm_tc05_kernel<0, 1, 32, 0, 1>", "last"),
     ("score_topk_tc_kernel (9130 x 7050, K=50)", "score_topk_tc_kernel", "last"),
-    ("side_fwd_kernel", "side_fwd_kernel", "last"), ("side_bwd_kernel", "side_bwd_kernel", "last"),
+    ("side_fwd_kernel (mma.sync)", "side_fwd_kernel", "last"), ("side_fwd_tc_kernel (tcgen05, shipped for d = 64)", "side_fwd_tc_kernel", "last"),
+    ("side_bwd_kernel", "side_bwd_kernel", "last"),
     ("infonce_tc_kernel fwd", "infonce_tc_kernel<64, 0>", "last"),
     ("infonce_tc_kernel bwd row", "infonce_tc_kernel<64, 1>", "last"),
     ("infonce_tc_kernel bwd col", "infonce_tc_kernel<64, 2>", "last"),
