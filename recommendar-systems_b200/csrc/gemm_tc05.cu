@@ -544,13 +544,49 @@ static int best_parts(int row_tiles, int units, int max_parts, int fill) {
   return best;
 }
 
+// The split-K GEMMs (forward, dW) with several row tiles: a CTA may also walk `mt` consecutive row tiles of its K
+// range with the pipeline kept full (mt_per_cta), which turns e.g. 56 row tiles x 5 splits = 280 CTAs = two waves of
+// 13 units + two fills into 28 x 5 = 140 CTAs = one wave of 26 units + one fill. Same cost model, searched over
+// (parts, mt); returns the parts, *mt_out the row tiles per CTA. MMREC_GEMM_MT=0 keeps mt = 1 (A/B switch).
+static long parts_cost(int row_tiles, int units, int p, int mt, int fill) {
+  const int per = (units + p - 1) / p, parts = (units + per - 1) / per;
+  if (parts != p) return -1;
+  const long ctas = (long)((row_tiles + mt - 1) / mt) * parts, waves = (ctas + kNumSMs - 1) / kNumSMs;
+  return waves * ((long)per * mt + fill);
+}
+static int best_mt(int row_tiles, int units, int p, int fill) {
+  static const bool on = !(getenv("MMREC_GEMM_MT") && atoi(getenv("MMREC_GEMM_MT")) == 0);
+  int best = 1;
+  long best_cost = parts_cost(row_tiles, units, p, 1, fill);
+  if (!on || best_cost < 0) return 1;
+  for (int mt = 2; mt <= 4 && mt <= row_tiles; ++mt) {
+    const long c = parts_cost(row_tiles, units, p, mt, fill);
+    if (c >= 0 && c < best_cost) { best_cost = c; best = mt; }
+  }
+  return best;
+}
+static int best_parts_mt(int row_tiles, int units, int max_parts, int fill) {
+  int best = 1;
+  long best_cost = -1;
+  for (int p = 1; p <= max_parts; ++p) {
+    const int mt = best_mt(row_tiles, units, p, fill);
+    long cost = parts_cost(row_tiles, units, p, mt, fill);
+    if (cost < 0) continue;
+    cost = 2 * cost + p;          // every split writes a slab and the reduce reads it: ~half a work unit each
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = p; }
+  }
+  return best;
+}
+
 int gemm_tc05_splits(int M, int N, int K, int kind) {
   if (kind == 3) return 1;
   const int m_tiles = kind == 2 ? (N + kBM - 1) / kBM : (M + kBM - 1) / kBM;
   const int n_kb = (K + kKB - 1) / kKB;
   // a single row tile (128 x 128 weight gradients over tens of thousands of rows): the reduction
   // dimension is all the parallelism there is
-  return best_parts(m_tiles, (n_kb + kChunkKB - 1) / kChunkKB, m_tiles == 1 ? 128 : 32, 3);
+  const int units = (n_kb + kChunkKB - 1) / kChunkKB;
+  if (m_tiles == 1) return best_parts(m_tiles, units, 128, 3);
+  return best_parts_mt(m_tiles, units, 32, 3);
 }
 
 // Returns MMREC_OK, a negative error, or 1 when the shape is not covered.
@@ -574,13 +610,14 @@ int gemm_tc05_dispatch(const float *A, int a_kcontig, const float *B, int b_kcon
   };
   if (kind == 1) {
     g.A = A; g.lda = K; g.B = B; g.ldb = K; g.C = out; g.ldc = N; g.M = M; g.N = N; g.K = K; g.nt_per_cta = 1;
-    g.mt_per_cta = tiles_per_cta((M + kBM - 1) / kBM, k_splits);
+    g.mt_per_cta = k_splits > 1 ? best_mt((M + kBM - 1) / kBM, n_units, k_splits, 3) : tiles_per_cta((M + kBM - 1) / kBM, k_splits);
     return launch_tc05_nt<false, false, false>(N, g, k_splits, 1, stream);
   }
   if (kind == 2) {
     // C^T [N, M] = B^T [N, K] * A [K, M]: UMMA A = caller's B (MN-major), UMMA B = caller's A (MN-major)
     g.A = B; g.lda = N; g.B = A; g.ldb = M; g.C = out; g.ldc = N; g.M = N; g.N = M; g.K = K; g.nt_per_cta = 1;
     if (bias != nullptr && splits == 1) return 1;      // bias indexes the other axis here
+    if (k_splits > 1) g.mt_per_cta = best_mt((N + kBM - 1) / kBM, n_units, k_splits, 3);
     return launch_tc05_nt<true, true, true>(M, g, k_splits, 1, stream);
   }
   // kind 3
