@@ -315,8 +315,26 @@ typedef struct MmrecDropout {
   float p;                /* drop probability in [0, 1) */
   uint64_t seed;          /* host constant of this call site / call */
   const double *counter;  /* device pointer to one double holding an integer count, or NULL */
+  /* Batch-row calls (the module evaluated on rows gathered by mmrec_gather_batch_rows_f32): row m of the
+   * call draws the multipliers of row row_ids[m] (device, int64) of a dense [n_total, d] call, so the
+   * compact and the dense evaluation drop the same elements. NULL / 0 = identity. */
+  const int64_t *row_ids;
+  int32_t n_total;
 } MmrecDropout;
 int mmrec_dropout_mask_f32(float *out, int32_t planes, int32_t n, int32_t d, const MmrecDropout *drop, void *stream);
+
+/* Batch rows of node tables around a row-local module (the preference module above; smore.py:395-407
+ * consumes only ua[users], ia[pos], ia[neg], side / content [users], [pos] of it). Row m of the compact
+ * tables is users[m] (m < B), n_users + pos[m - B], n_users + neg[m - 2 B]: gather copies those rows of
+ * up to 4 tables [*, d] into [3 B, d] tables and writes the row ids (int64 [3 B]: the `row_ids` of
+ * MmrecDropout and the index of the scatter); scatter_add adds [n_rows, d] gradient tables into dense,
+ * ZEROED tables at those ids (rows repeat in a batch: vector reductions, order not fixed -- like the BPR
+ * scatter). A NULL source table is skipped. Replaces nothing in the reference: it computes all rows. */
+int mmrec_gather_batch_rows_f32(const float *const *src_host, int32_t n_tables, const int64_t *users,
+                                const int64_t *pos, const int64_t *neg, int32_t batch, int32_t n_users, int32_t d,
+                                float *const *dst_host, int64_t *idx_out, void *stream);
+int mmrec_scatter_batch_rows_add_f32(const float *const *dsrc_host, int32_t n_tables, const int64_t *idx,
+                                     int32_t n_rows, int32_t d, float *const *ddst_host, void *stream);
 
 int mmrec_smore_side_supported(int32_t d);
 size_t mmrec_smore_side_bwd_workspace_bytes(int32_t n, int32_t d);

@@ -81,7 +81,18 @@ struct DropSpec {
   const double *counter;  // device: one double holding an integer count (FusedAdam's update count), or NULL
   uint64_t seed;          // host constant of this call
   float p;                // drop probability, applied in steps of 2^-16; 0 = no dropout
+  // Batch-row calls (the module evaluated on gathered rows only): row m of the call draws the multipliers
+  // of row row_ids[m] of a dense [n_total, d] call -- the compact and the dense evaluation drop the same
+  // elements. NULL = identity (row m of n).
+  const long long *row_ids;
+  int n_total;
 };
+// first float4 index of (plane g, row m) in the [planes, n, d] index space; m < n
+__device__ __forceinline__ uint64_t drop_row4(const DropSpec &d, int g, int m, int n, int d4) {
+  const uint64_t row = d.row_ids != nullptr ? (uint64_t)d.row_ids[m] : (uint64_t)m;
+  const uint64_t nt = d.row_ids != nullptr ? (uint64_t)d.n_total : (uint64_t)n;
+  return ((uint64_t)g * nt + row) * (uint64_t)d4;
+}
 __host__ __device__ inline uint64_t drop_mix64(uint64_t z) {       // splitmix64 finaliser
   z += 0x9e3779b97f4a7c15ull;
   z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;

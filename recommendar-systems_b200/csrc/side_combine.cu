@@ -59,7 +59,7 @@ struct CombIn {
 template <int LANES>
 __device__ __forceinline__ float4 comb_mask(const CombIn &in, uint64_t key, int g, int r, int lane, int n, size_t o) {
   if (in.mask != nullptr) return ldg4(in.mask + (size_t)g * n * (LANES * 4) + o);
-  if (in.drop.p > 0.f) return drop_mask4(key, ((uint64_t)g * n + (uint64_t)r) * LANES + lane, in.drop.p);
+  if (in.drop.p > 0.f) return drop_mask4(key, drop_row4(in.drop, g, r, n, LANES) + lane, in.drop.p);
   return make_float4(1.f, 1.f, 1.f, 1.f);
 }
 
@@ -140,10 +140,11 @@ dropout_mask_kernel(float4 *__restrict__ out, size_t n4, const DropSpec drop) {
 }
 
 inline int comb_drop(const MmrecDropout *h, DropSpec &D) {
-  D = DropSpec{nullptr, 0ull, 0.f};
+  D = DropSpec{nullptr, 0ull, 0.f, nullptr, 0};
   if (h == nullptr) return MMREC_OK;
   MMREC_REQUIRE(h->p >= 0.f && h->p < 1.f, MMREC_E_BADARG, "dropout: p must be in [0, 1) (got %g)", (double)h->p);
-  D = DropSpec{h->counter, h->seed, h->p};
+  MMREC_REQUIRE(h->row_ids == nullptr || h->n_total > 0, MMREC_E_BADARG, "dropout: row_ids needs n_total");
+  D = DropSpec{h->counter, h->seed, h->p, reinterpret_cast<const long long *>(h->row_ids), h->n_total};
   return MMREC_OK;
 }
 

@@ -84,11 +84,12 @@ struct Frag {
     }
   }
   // dropout multipliers of plane `g` ([3, n, D] layout) for this thread's rows / columns
-  __device__ __forceinline__ void fill_dropout(uint64_t stream, float p, int g, int m0, int n, int rg, int c0) {
+  __device__ __forceinline__ void fill_dropout(uint64_t stream, const DropSpec &ds, int g, int m0, int n, int rg, int c0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = m0 + rg + C::RG * i;
-      const float4 t = drop_mask4(stream, ((uint64_t)g * n + (uint64_t)m) * (D / 4) + c0 / 4, p);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < n) t = drop_mask4(stream, drop_row4(ds, g, m, n, D / 4) + c0 / 4, ds.p);
       v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
     }
   }
@@ -269,7 +270,7 @@ side_fwd_kernel(const float *__restrict__ F, const float *__restrict__ V, const 
       if (saved != nullptr) acc.store(saved + (4 + g) * nd, m0, n, rg, c0);
       if (masks != nullptr || drop.p > 0.f) {
         if (masks != nullptr) x.load(masks + g * nd, m0, n, rg, c0);
-        else x.fill_dropout(drop_key, drop.p, g, m0, n, rg, c0);
+        else x.fill_dropout(drop_key, drop, g, m0, n, rg, c0);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -387,7 +388,7 @@ side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_sid
       Frag<D> mk;
       mk.fill(1.f);
       if (masks != nullptr) mk.load(masks + br * nd, m0, n, rg, c0);
-      else if (drop.p > 0.f) mk.fill_dropout(drop_key, drop.p, br, m0, n, rg, c0);
+      else if (drop.p > 0.f) mk.fill_dropout(drop_key, drop, br, m0, n, rg, c0);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -558,10 +559,11 @@ static int unpack_weights(const float *const *W, const float *const *b, int d, S
 }
 
 static int unpack_drop(const MmrecDropout *drop, DropSpec &D) {
-  D = DropSpec{nullptr, 0ull, 0.f};
+  D = DropSpec{nullptr, 0ull, 0.f, nullptr, 0};
   if (drop == nullptr) return MMREC_OK;
   MMREC_REQUIRE(drop->p >= 0.f && drop->p < 1.f, MMREC_E_BADARG, "dropout: p must be in [0, 1) (got %g)", (double)drop->p);
-  D = DropSpec{drop->counter, drop->seed, drop->p};
+  MMREC_REQUIRE(drop->row_ids == nullptr || drop->n_total > 0, MMREC_E_BADARG, "dropout: row_ids needs n_total");
+  D = DropSpec{drop->counter, drop->seed, drop->p, reinterpret_cast<const long long *>(drop->row_ids), drop->n_total};
   return MMREC_OK;
 }
 

@@ -366,6 +366,11 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
       for (int j = 0; j < 16; ++j) sd[j] = 0.f;
       float *const sv_out[3] = {A.saved != nullptr ? A.saved + 4 * nd : nullptr, A.saved != nullptr ? A.saved + 5 * nd : nullptr,
                                 A.saved != nullptr ? A.saved + 6 * nd : nullptr};
+      uint64_t drop_base[3] = {0, 0, 0};         // first float4 index of this row in each mask plane
+      if (A.drop.p > 0.f && grow < n) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) drop_base[g] = drop_row4(A.drop, g, grow, n, kD / 4);
+      }
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         from_tmem(g == 0 ? kColQ : g == 1 ? kColQ + 64 : kColG, x);
@@ -377,7 +382,7 @@ side_fwd_tc_kernel(const __grid_constant__ SideTcArgs A) {
         if (A.drop.p > 0.f) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 m = drop_mask4(drop_key, ((uint64_t)g * n + (uint64_t)grow) * (kD / 4) + (c0 >> 2) + j, A.drop.p);
+            const float4 m = drop_mask4(drop_key, drop_base[g] + (c0 >> 2) + j, A.drop.p);
             x[4 * j] *= m.x; x[4 * j + 1] *= m.y; x[4 * j + 2] *= m.z; x[4 * j + 3] *= m.w;
           }
         }
@@ -454,10 +459,11 @@ extern "C" int mmrec_smore_side_fwd_tc_f32(const float *F, const float *V, const
     P.b[i] = b_host[i];
     A.b[i] = b_host[i];
   }
-  A.drop = DropSpec{nullptr, 0ull, 0.f};
+  A.drop = DropSpec{nullptr, 0ull, 0.f, nullptr, 0};
   if (drop != nullptr) {
     MMREC_REQUIRE(drop->p >= 0.f && drop->p < 1.f, MMREC_E_BADARG, "dropout: p must be in [0, 1) (got %g)", (double)drop->p);
-    A.drop = DropSpec{drop->counter, drop->seed, drop->p};
+    MMREC_REQUIRE(drop->row_ids == nullptr || drop->n_total > 0, MMREC_E_BADARG, "dropout: row_ids needs n_total");
+    A.drop = DropSpec{drop->counter, drop->seed, drop->p, reinterpret_cast<const long long *>(drop->row_ids), drop->n_total};
   }
   if (n == 0) return MMREC_OK;
   cudaStream_t st = (cudaStream_t)stream;

@@ -67,6 +67,8 @@ SIGNATURES = {
     "mmrec_smore_side_fwd_drop_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "mmrec_smore_side_bwd_drop_f32": (C.c_int, [_p] * 17 + [_i32, _i32, _p]),
     "mmrec_smore_side_fwd_tc_workspace_bytes": (_sz, [_i32, _i32]),
+    "mmrec_gather_batch_rows_f32": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "mmrec_scatter_batch_rows_add_f32": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _p]),
     "mmrec_smore_side_fwd_tc_f32": (C.c_int, [_p] * 10 + [_i32, _i32, _p, _p]),
     "mmrec_dropout_mask_f32": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "mmrec_smore_combine_fwd_drop_f32": (C.c_int, [_p] * 10 + [_i32, _i32, _p, _p, _p]),
@@ -122,14 +124,19 @@ class SpmmProblem(C.Structure):
 
 class Dropout(C.Structure):
     """MmrecDropout of include/mmrec_b200.h: in-kernel nn.Dropout (no mask tensor)."""
-    _fields_ = [("p", _f32), ("seed", C.c_uint64), ("counter", _p)]
+    _fields_ = [("p", _f32), ("seed", C.c_uint64), ("counter", _p), ("row_ids", _p), ("n_total", _i32)]
 
     @classmethod
-    def make(cls, p, seed, counter=None):
-        """`counter`: a 1-element float64 CUDA tensor read on the device (FusedAdam's update count) or None."""
+    def make(cls, p, seed, counter=None, row_ids=None, n_total=0):
+        """`counter`: a 1-element float64 CUDA tensor read on the device (FusedAdam's update count) or None.
+        `row_ids` (int64 CUDA tensor) / `n_total`: the call evaluates gathered rows of a dense [n_total, d]
+        table and draws the multipliers of those rows (batch-row calls)."""
         if counter is not None and (counter.dtype != torch.float64 or not counter.is_cuda or counter.numel() < 1):
             raise RuntimeError("Dropout.counter must be a float64 CUDA tensor")
-        return cls(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(counter))
+        if row_ids is not None and (row_ids.dtype != torch.int64 or not row_ids.is_cuda or not row_ids.is_contiguous()
+                                    or int(n_total) <= 0):
+            raise RuntimeError("Dropout.row_ids must be a contiguous int64 CUDA tensor with n_total > 0")
+        return cls(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(counter), ptr(row_ids), int(n_total))
 
 
 _lib = None

@@ -592,17 +592,23 @@ class SMORE(_MultiViewBase):
         # `dropout_counter` at FusedAdam's device-side update count, so replays of a captured step
         # draw fresh masks; without it (eager use) the call index alone advances the stream.
         self.fused_dropout = bool(config.get("fused_dropout", os.environ.get("MMREC_FUSED_DROPOUT", "1") != "0"))
+        # Training evaluates the (row-local) preference module on the rows of the batch only: smore.py:395-407
+        # consumes ua[users], ia[pos], ia[neg], side / content [users], [pos] and nothing else of it, and a row
+        # nothing consumes gets a zero gradient (ops.gather_batch_rows, csrc/batch_rows.cu). Same loss, same
+        # gradients; MMREC_BATCH_ROWS=0 / config["batch_rows"] = False evaluates all rows like the reference.
+        self.batch_rows = bool(config.get("batch_rows", os.environ.get("MMREC_BATCH_ROWS", "1") != "0"))
         self.dropout_counter = None
         self._drop_seed = int(config.get("seed", 999))
         self._drop_calls = 0
 
-    def _dropout_spec(self):
-        """(p, seed, counter) of this forward call for ops.smore_side / ops.smore_combine."""
+    def _dropout_spec(self, row_ids=None, n_total=0):
+        """(p, seed, counter[, row_ids, n_total]) of this forward call for ops.smore_side / ops.smore_combine."""
         self._drop_calls += 1
         if self.dropout_counter is None and torch.cuda.is_current_stream_capturing():
             raise RuntimeError("SMORE: in-kernel dropout inside a captured step needs `dropout_counter` "
                                "(a device-side count that changes between replays; Trainer sets it)")
-        return (self.dropout_rate, (self._drop_seed << 32) ^ (self._drop_calls * 0x9E3779B97F4A7C15), self.dropout_counter)
+        spec = (self.dropout_rate, (self._drop_seed << 32) ^ (self._drop_calls * 0x9E3779B97F4A7C15), self.dropout_counter)
+        return spec if row_ids is None else spec + (row_ids, int(n_total))
 
     def spectrum_convolution(self, image_embeds, text_embeds):
         """smore.py:209-252 without the band-energy .item() syncs (diagnostics only)."""
@@ -618,7 +624,9 @@ class SMORE(_MultiViewBase):
         u, i = _split(all_e, self.n_users)
         return (u, i, side, content) if train else (u, i)
 
-    def _forward_full(self, adj):
+    def _forward_full(self, adj, batch=None):
+        """(all_embeds, side_embeds, content_embeds) over all nodes; with `batch` = (users, pos, neg) and
+        `batch_rows` on, over the 3 B rows users | n_users + pos | n_users + neg of the batch instead."""
         import contextlib
         item = self.item_id_embedding.weight
         s_ui, s_txt = self._fork(0), self._fork(1)
@@ -646,12 +654,17 @@ class SMORE(_MultiViewBase):
             (image_item, text_item, fusion_item),
             (self.image_original_adj, self.text_original_adj, self.fusion_adj))
         self._join(s_ui, content)
+        row_ids, n_total = None, int(content.shape[0])
+        if batch is not None:
+            # everything below is row-local: keep the rows of the batch only (gradients scatter back)
+            row_ids, (fusion_embeds, image_embeds, text_embeds, content) = ops.gather_batch_rows(
+                (fusion_embeds, image_embeds, text_embeds, content), batch[0], batch[1], batch[2], self.n_users)
         # modality-aware preference module (smore.py:321-341): one fused kernel for d = 32 / 64
         if ops.smore_side_supported(self.embedding_dim):
             masks = drop = None
             if self.training and self.dropout_rate > 0:
                 if self.fused_dropout:
-                    drop = self._dropout_spec()
+                    drop = self._dropout_spec(row_ids, n_total)
                 else:
                     # the three nn.Dropout masks (smore.py:331-333) drawn in one call
                     masks = torch.nn.functional.dropout(
@@ -670,7 +683,7 @@ class SMORE(_MultiViewBase):
             masks = drop = None
             if self.training and self.dropout_rate > 0:
                 if self.fused_dropout:
-                    drop = self._dropout_spec()
+                    drop = self._dropout_spec(row_ids, n_total)
                 else:
                     masks = torch.nn.functional.dropout(
                         torch.ones(3, *content.shape, dtype=content.dtype, device=content.device),
@@ -691,11 +704,29 @@ class SMORE(_MultiViewBase):
         """smore.py:389-411 (global_step is bumped here, which is what makes every step after
         the second a mirror-gradient step in the trainer -- SURVEY 3.2)."""
         users, pos, neg = interaction[0], interaction[1], interaction[2]
+        if self.batch_rows and users.is_cuda:
+            # compact tables [3 B, d]: rows 0..B-1 = users, B..2B-1 = positive items, 2B..3B-1 = negative items --
+            # the "user table" of the gathers below has B rows, the "item table" 2 B
+            all_e, side, content = self._forward_full(self.norm_adj, batch=(users, pos, neg))
+            self.global_step += 1
+            B = int(users.shape[0])
+            ar = self._batch_arange(B, users.device)
+            o = ops.bpr_table(all_e, B, ar[:B], ar[:B], ar[B:])
+            cl = ops.infonce_pair(side, content, B, ar[:B], ar[:B], self.cl_temp, reduce=False)
+            return ops.loss_head(o, cl, B, self.reg_weight, self.batch_size, self.cl_loss)
         all_e, side, content = self._forward_full(self.norm_adj)
         self.global_step += 1
         o = ops.bpr_table(all_e, self.n_users, users, pos, neg)
         cl = ops.infonce_pair(side, content, self.n_users, users, pos, self.cl_temp, reduce=False)
         return ops.loss_head(o, cl, users.shape[0], self.reg_weight, self.batch_size, self.cl_loss)
+
+    def _batch_arange(self, B, device):
+        """arange(2 B) on the device, kept per batch size (index tensors of the compact gathers)."""
+        cache = self.__dict__.setdefault("_arange_cache", {})
+        key = (B, str(device))
+        if key not in cache:
+            cache[key] = torch.arange(2 * B, dtype=torch.int64, device=device)
+        return cache[key]
 
 
 MODELS = {"LightGCN": LightGCN, "LayerGCN": LayerGCN, "FREEDOM": FREEDOM, "MGCN": MGCN,

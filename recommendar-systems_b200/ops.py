@@ -1006,14 +1006,63 @@ def dropout_mask(planes, n, d, drop, device=None):
 def smore_side(fusion, image, text, content, layers, masks=None, drop=None):
     """Fused modality-aware preference module. `layers` = the seven nn.Linear modules in the
     order query_v.0, query_v.2, query_t.0, query_t.2, gate_image_prefer.0, gate_text_prefer.0,
-    gate_fusion_prefer.0; masks = [3, n, d] dropout multipliers or None; drop = (p, seed, counter)
-    for dropout generated inside the kernels (no mask tensor; see lib.Dropout).
+    gate_fusion_prefer.0; masks = [3, n, d] dropout multipliers or None; drop = (p, seed, counter[,
+    row_ids, n_total]) for dropout generated inside the kernels (no mask tensor; see lib.Dropout --
+    with row_ids the call runs on gathered rows and drops what the dense call would drop there).
     Returns (content + side, side)."""
     lib.require_cuda(fusion, image, text, content)
     wb = []
     for m in layers:
         wb += [m.weight, m.bias]
     return _SmoreSide.apply(fusion, image, text, content, masks, drop, *wb)
+
+
+# ------------------------------------------- batch rows of node tables (row-local modules in training)
+class _GatherBatchRows(torch.autograd.Function):
+    """apply(users, pos, neg, n_users, *tables) -> (row_ids, *compact tables): rows users | n_users + pos |
+    n_users + neg of every [N, d] table as [3 B, d] tables (mmrec_gather_batch_rows_f32). Backward: the
+    compact gradients scatter-added into dense zero tables (mmrec_scatter_batch_rows_add_f32)."""
+
+    @staticmethod
+    def forward(ctx, users, pos, neg, n_users, *tables):
+        tables = [_f32c(t) for t in tables]
+        lib.require_cuda(users, pos, neg, *tables)
+        if not (users.dtype == pos.dtype == neg.dtype == torch.int64) or not (users.numel() == pos.numel() == neg.numel()):
+            raise RuntimeError("gather_batch_rows: users / pos / neg must be int64 tensors of one length")
+        B, (N, d) = users.numel(), tables[0].shape
+        if any(t.shape != (N, d) for t in tables) or not 1 <= len(tables) <= 4:
+            raise RuntimeError("gather_batch_rows: 1..4 tables of one shape")
+        if CHECK_IDS:
+            _check_ids(users, n_users, "batch users")
+            _check_ids(pos, N - n_users, "batch pos items")
+            _check_ids(neg, N - n_users, "batch neg items")
+        idx = torch.empty(3 * B, dtype=torch.int64, device=users.device)
+        outs = [torch.empty(3 * B, d, dtype=torch.float32, device=users.device) for _ in tables]
+        lib.call("mmrec_gather_batch_rows_f32", _ptr_array(tables), len(tables), lib.ptr(users.contiguous()),
+                 lib.ptr(pos.contiguous()), lib.ptr(neg.contiguous()), B, int(n_users), d, _ptr_array(outs), lib.ptr(idx),
+                 lib.stream())
+        ctx.shape, ctx.n_tables = (N, d), len(tables)
+        ctx.save_for_backward(idx)
+        ctx.mark_non_differentiable(idx)
+        return (idx, *outs)
+
+    @staticmethod
+    def backward(ctx, _d_idx, *d_outs):
+        (idx,) = ctx.saved_tensors
+        N, d = ctx.shape
+        dense = torch.zeros(ctx.n_tables, N, d, dtype=torch.float32, device=idx.device)      # one fill for all tables
+        srcs = [None if g is None else _f32c(g) for g in d_outs]
+        if any(g is not None for g in srcs):
+            lib.call("mmrec_scatter_batch_rows_add_f32", _ptr_array(srcs), ctx.n_tables, lib.ptr(idx), idx.numel(), d,
+                     _ptr_array([dense[t] for t in range(ctx.n_tables)]), lib.stream())
+        return (None, None, None, None, *[dense[t] if ctx.needs_input_grad[4 + t] else None for t in range(ctx.n_tables)])
+
+
+def gather_batch_rows(tables, users, pos, neg, n_users):
+    """(row_ids int64 [3 B], [table[row_ids] for table in tables]) with row_ids = users | n_users + pos |
+    n_users + neg -- the rows of a training batch, for modules that are row-local (see csrc/batch_rows.cu)."""
+    out = _GatherBatchRows.apply(users, pos, neg, int(n_users), *tables)
+    return out[0], list(out[1:])
 
 
 # ------------------------------------------- SMORE preference module, row part (wide embeddings)

@@ -276,3 +276,36 @@ def test_spmm_chain_under_programmatic_dependent_launch_is_bit_identical(monkeyp
         assert torch.equal(y, yg) and torch.equal(z, zg)
         res[pdl] = (y, z)
     assert torch.equal(res["0"][0], res["1"][0]) and torch.equal(res["0"][1], res["1"][1])
+
+
+# ------------------------------------------------------------------ a10: the preference module on the batch rows
+@pytest.mark.parametrize("shape,d,p", [("tiny", 64, 0.0), ("tiny", 64, 0.5), ("small", 32, 0.3), ("small", 128, 0.2),
+                                       ("baby", 64, 0.5)])
+def test_smore_batch_rows_training_equals_all_rows(shape, d, p):
+    """SMORE.calculate_loss with the preference module evaluated on the 3 B rows of the batch
+    (ops.gather_batch_rows; smore.py:395-407 consumes nothing else of it) against the same step over all
+    rows: the same loss and the same gradient for every parameter -- with dropout too (the compact call
+    draws the multipliers of the rows it gathered). Repeated users / items inside the batch included."""
+    import bench
+    over = {"embedding_size": d, "dropout_rate": p, "cuda_graph": False}
+    res = {}
+    for mode in (False, True):
+        env = bench.build_env(DEV, shape=shape, overrides=dict(over, batch_rows=mode))
+        m = env["model"]
+        m.train()
+        m.dropout_counter = _counter(5)
+        assert m.batch_rows is mode
+        batch = bench.take_batches(env["train"], 1)[0]
+        batch[0, 1::7] = batch[0, 0]                    # one user many times
+        batch[1, 2::5] = batch[1, 1]                    # one positive item many times
+        batch[2, ::3] = batch[1, ::3].roll(1)           # negatives that are other rows' positives
+        m.zero_grad()
+        loss = m.calculate_loss(batch)
+        loss.backward()
+        res[mode] = (float(loss), {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None})
+    (l0, g0), (l1, g1) = res[False], res[True]
+    assert abs(l0 - l1) <= 2e-6 * abs(l0)
+    assert set(g0) == set(g1)
+    for k in g0:
+        scale = float(g0[k].abs().max().clamp_min(1e-12))
+        assert float((g0[k] - g1[k]).abs().max()) <= 2e-5 * scale, k
