@@ -336,6 +336,24 @@ int mmrec_gather_batch_rows_f32(const float *const *src_host, int32_t n_tables, 
 int mmrec_scatter_batch_rows_add_f32(const float *const *dsrc_host, int32_t n_tables, const int64_t *idx,
                                      int32_t n_rows, int32_t d, float *const *ddst_host, void *stream);
 
+/* The same for the modality views cat([R x', x']) of smore.py:289-317 / mgcn.py:170-184: compact row m < B
+ * is row users[m] of R (CSR of the users x items block; col_idx - col_offset = item) times the item tables
+ * x'_v [I, d] (1..3 views in one pass over the row), rows B .. 3 B - 1 are the item rows pos / neg of x'_v; the
+ * content table [U + I, d] (may be NULL) is gathered alongside. This replaces the user-side SpMM of the views
+ * (torch.sparse.mm(self.R, x)) and its R^T backward in TRAINING, where only the batch rows are consumed.
+ * scatter_add: the gradients of the compact views / content added into ZEROED dense item tables [I, d] /
+ * [U + I, d] along the same non-zeros (vector reductions). d in {32, 64, 128}. */
+int mmrec_gather_batch_views_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals, int32_t col_offset,
+                                 const float *const *item_tables_host, int32_t n_views, const float *content,
+                                 const int64_t *users, const int64_t *pos, const int64_t *neg, int32_t batch,
+                                 int32_t n_users, int32_t d, float *const *views_out_host, float *content_out,
+                                 int64_t *idx_out, void *stream);
+int mmrec_scatter_batch_views_add_f32(const int32_t *row_ptr, const int32_t *col_idx, const float *vals,
+                                      int32_t col_offset, const float *const *d_views_host, int32_t n_views,
+                                      const float *d_content, const int64_t *users, const int64_t *pos,
+                                      const int64_t *neg, int32_t batch, int32_t n_users, int32_t d,
+                                      float *const *d_item_tables_host, float *d_content_out, void *stream);
+
 int mmrec_smore_side_supported(int32_t d);
 size_t mmrec_smore_side_bwd_workspace_bytes(int32_t n, int32_t d);
 int mmrec_smore_side_fwd_drop_f32(const float *F, const float *V, const float *T, const float *C,

@@ -69,6 +69,8 @@ SIGNATURES = {
     "mmrec_smore_side_fwd_tc_workspace_bytes": (_sz, [_i32, _i32]),
     "mmrec_gather_batch_rows_f32": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "mmrec_scatter_batch_rows_add_f32": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _p]),
+    "mmrec_gather_batch_views_f32": (C.c_int, [_p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "mmrec_scatter_batch_views_add_f32": (C.c_int, [_p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "mmrec_smore_side_fwd_tc_f32": (C.c_int, [_p] * 10 + [_i32, _i32, _p, _p]),
     "mmrec_dropout_mask_f32": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "mmrec_smore_combine_fwd_drop_f32": (C.c_int, [_p] * 10 + [_i32, _i32, _p, _p, _p]),

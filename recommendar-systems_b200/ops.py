@@ -1065,6 +1065,64 @@ def gather_batch_rows(tables, users, pos, neg, n_users):
     return out[0], list(out[1:])
 
 
+class _GatherBatchViews(torch.autograd.Function):
+    """apply(R, users, pos, neg, content, *item_tables) -> (row_ids, content_c, *views_c): the batch rows of
+    the modality views cat([R x', x']) without forming them -- user rows are rows of R times x' (only for the
+    users of the batch), item rows are copied (mmrec_gather_batch_views_f32). Backward: scatter-add along the
+    same non-zeros into dense zero tables."""
+
+    @staticmethod
+    def forward(ctx, R, users, pos, neg, content, *tables):
+        tables = [_f32c(t) for t in tables]
+        content = _f32c(content)
+        lib.require_cuda(users, pos, neg, content, *tables)
+        if not (users.dtype == pos.dtype == neg.dtype == torch.int64) or not (users.numel() == pos.numel() == neg.numel()):
+            raise RuntimeError("gather_batch_views: users / pos / neg must be int64 tensors of one length")
+        B, (I, d) = users.numel(), tables[0].shape
+        if any(t.shape != (I, d) for t in tables) or not 1 <= len(tables) <= 3 or I != R.n_cols or \
+                content.shape != (R.n_rows + I, d):
+            raise RuntimeError("gather_batch_views: 1..3 item tables [I, d] and a content table [U + I, d]")
+        if CHECK_IDS:
+            _check_ids(users, R.n_rows, "batch users")
+            _check_ids(pos, I, "batch pos items")
+            _check_ids(neg, I, "batch neg items")
+        users, pos, neg = users.contiguous(), pos.contiguous(), neg.contiguous()
+        dev = users.device
+        idx = torch.empty(3 * B, dtype=torch.int64, device=dev)
+        content_c = torch.empty(3 * B, d, dtype=torch.float32, device=dev)
+        outs = [torch.empty(3 * B, d, dtype=torch.float32, device=dev) for _ in tables]
+        lib.call("mmrec_gather_batch_views_f32", lib.ptr(R.row_ptr), lib.ptr(R.col_idx), lib.ptr(R.vals), R.col_offset,
+                 _ptr_array(tables), len(tables), lib.ptr(content), lib.ptr(users), lib.ptr(pos), lib.ptr(neg), B,
+                 R.n_rows, d, _ptr_array(outs), lib.ptr(content_c), lib.ptr(idx), lib.stream())
+        ctx.R, ctx.dims, ctx.n_tables = R, (I, d), len(tables)
+        ctx.save_for_backward(users, pos, neg)
+        ctx.mark_non_differentiable(idx)
+        return (idx, content_c, *outs)
+
+    @staticmethod
+    def backward(ctx, _d_idx, d_content, *d_outs):
+        users, pos, neg = ctx.saved_tensors
+        R, (I, d), n = ctx.R, ctx.dims, ctx.n_tables
+        dev = users.device
+        d_tables = torch.zeros(n, I, d, dtype=torch.float32, device=dev)
+        d_dense_content = torch.zeros(R.n_rows + I, d, dtype=torch.float32, device=dev)
+        srcs = [None if g is None else _f32c(g) for g in d_outs]
+        dc = None if d_content is None else _f32c(d_content)
+        lib.call("mmrec_scatter_batch_views_add_f32", lib.ptr(R.row_ptr), lib.ptr(R.col_idx), lib.ptr(R.vals),
+                 R.col_offset, _ptr_array(srcs), n, lib.ptr(dc), lib.ptr(users), lib.ptr(pos), lib.ptr(neg),
+                 users.numel(), R.n_rows, d, _ptr_array([d_tables[t] for t in range(n)]),
+                 lib.ptr(d_dense_content) if dc is not None else None, lib.stream())
+        return (None, None, None, None, d_dense_content if ctx.needs_input_grad[4] else None,
+                *[d_tables[t] if ctx.needs_input_grad[5 + t] else None for t in range(n)])
+
+
+def gather_batch_views(R, item_tables, content, users, pos, neg):
+    """(row_ids [3 B], content[row_ids], [cat([R x, x])[row_ids] for x in item_tables]) for the rows users |
+    n_users + pos | n_users + neg of a training batch, without the user-side SpMM over all users."""
+    out = _GatherBatchViews.apply(R, users, pos, neg, content, *item_tables)
+    return out[0], out[1], list(out[2:])
+
+
 # ------------------------------------------- SMORE preference module, row part (wide embeddings)
 class _SmoreCombine(torch.autograd.Function):
     """smore.py:321-341 after the seven Linear layers: apply(zv, zt, V, T, F, C, gi, gt, gf, masks)
