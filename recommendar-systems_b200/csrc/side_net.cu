@@ -442,33 +442,39 @@ side_bwd_kernel(const float *__restrict__ d_all, const float *__restrict__ d_sid
 
 // out[w][row][col] = sum over parts of partial[w][row][part][col] (row D = the bias). A CTA owns 64
 // consecutive outputs (one row at D = 64) and ALL their partials: thread (tx, ty) takes the float4
-// column tx of parts ty, ty + 64, ... -- every load of a thread is in flight at once (the kernel used to
+// column tx of parts ty, ty + TY, ... -- every load of a thread is in flight at once (the kernel used to
 // walk its parts in dependent batches: four memory round trips per CTA times 1.5 waves = 26 us for a
 // 48 MB stream), a warp reads 512 contiguous bytes per request, the sums run in a fixed order.
-__global__ void __launch_bounds__(1024, 1)
+// TY = 64 (1024 threads, one CTA per SM) for the ~400 partial slabs of an all-rows backward; TY = 16 (256
+// threads, eight CTAs per SM: the 455 CTAs are one wave instead of three) for the <= 128 slabs of a
+// batch-row backward, where the 1024-thread CTAs spent 19 us on an 11 MB stream (ncu,
+// profiles/r02_batch_rows_ncu_summary.txt).
+template <int TY>
+__global__ void __launch_bounds__(16 * TY, TY == 64 ? 1 : 4)
 side_partial_reduce_kernel(const float *__restrict__ partial, int n_parts, int n_w, int n_b, SideGrads G) {
-  __shared__ float4 sm[64][16];
+  static_assert(TY % 8 == 0 && TY >= 8, "two-stage tree over groups of eight");
+  __shared__ float4 sm[TY][16];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int j = (blockIdx.x * 16 + tx) * 4, wi = blockIdx.y;
   const int D = n_b, row = j / D, col = j % D;
   const bool live = j < n_w + n_b;
   const float *base = partial + ((size_t)wi * (D + 1) + row) * n_parts * D + col;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p0 = ty; p0 < n_parts; p0 += 64 * 8) {
+  for (int p0 = ty; p0 < n_parts; p0 += TY * 8) {
     float4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      v[u] = live && p0 + 64 * u < n_parts ? __ldcs(reinterpret_cast<const float4 *>(base + (size_t)(p0 + 64 * u) * D))
+      v[u] = live && p0 + TY * u < n_parts ? __ldcs(reinterpret_cast<const float4 *>(base + (size_t)(p0 + TY * u) * D))
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
   }
   sm[ty][tx] = s;
   __syncthreads();
-  if (ty < 8) {                                   // parts ty, ty + 8, ... of the 64 partial sums
+  if (ty < 8) {                                   // parts ty, ty + 8, ... of the TY partial sums
     float4 a = sm[ty][tx];
 #pragma unroll
-    for (int g = 1; g < 8; ++g) {
+    for (int g = 1; g < TY / 8; ++g) {
       const float4 b = sm[ty + 8 * g][tx];
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
@@ -530,7 +536,10 @@ int side_bwd_launch(const float *d_all, const float *d_side, const float *F, con
   side_bwd_kernel<D><<<parts, kT, smem, st>>>(d_all, d_side, F, V, T, C_, P, masks, drop, saved, dF, dV, dT, dC, ws, n,
                                               n_tiles);
   MMREC_CHECK_LAUNCH("side_bwd_kernel");
-  side_partial_reduce_kernel<<<dim3((D * D + D + 63) / 64, kNW), 1024, 0, st>>>(ws, parts, D * D, D, G);
+  const dim3 rgrid((D * D + D + 63) / 64, kNW);
+  static const bool wide_only = getenv("MMREC_SIDE_REDUCE_WIDE") && atoi(getenv("MMREC_SIDE_REDUCE_WIDE")) != 0;   // A/B
+  if (parts <= 128 && !wide_only) side_partial_reduce_kernel<16><<<rgrid, 256, 0, st>>>(ws, parts, D * D, D, G);
+  else side_partial_reduce_kernel<64><<<rgrid, 1024, 0, st>>>(ws, parts, D * D, D, G);
   MMREC_CHECK_LAUNCH("side_partial_reduce_kernel");
   return MMREC_OK;
 }
