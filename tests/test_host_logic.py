@@ -173,6 +173,27 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.mmrec_abi_version() == 1
 
 
+def test_ctypes_signatures_have_the_header_arity():
+    """Every prototype of include/mmrec_b200.h and its ctypes mirror (lib.SIGNATURES) take the same number of
+    arguments, pointer arguments are bound as pointers and `void *stream` comes last where the header has it: a
+    miscounted argtypes list would otherwise only show up as a wrong result on the GPU."""
+    import ctypes
+    lib = pkg("lib")
+    hdr = open(os.path.join(REPO, "include", "mmrec_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    protos = re.findall(r"\b(mmrec_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr)
+    assert len(protos) == len(lib.SIGNATURES)
+    for name, args in protos:
+        args = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
+        res, argtypes = lib.SIGNATURES[name]
+        assert len(args) == len(argtypes), (name, len(args), len(argtypes))
+        for a, t in zip(args, argtypes):
+            assert ("*" in a) == (t is ctypes.c_void_p), (name, a, t)
+        if args and re.search(r"void\s*\*\s*stream$", args[-1]):
+            assert argtypes[-1] is ctypes.c_void_p, name
+
+
 def test_product_does_not_import_oracle():
     root = os.path.join(REPO, "recommendar-systems_b200")
     for fn in os.listdir(root):
@@ -199,6 +220,7 @@ def test_ops_fail_loudly_without_cuda():
         lambda: ops.infonce_pair(x, x, 4, idx, idx, 0.2),
         lambda: ops.score_mask_topk(x, idx, x, 2),
         lambda: ops.loss_head(torch.zeros(2), torch.zeros(2), 4, 0.1, 4, 0.1),
+        lambda: ops.gather_batch_rows([x], idx, idx, idx, 4),
     ]
     for i, fn in enumerate(calls):
         with pytest.raises((RuntimeError, ValueError), match=None):
